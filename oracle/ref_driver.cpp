@@ -1,0 +1,166 @@
+/*
+ * ref_driver.cpp -- thin C-ABI driver around the UNMODIFIED reference sources (TEST INFRASTRUCTURE).
+ *
+ * Compiled by oracle/Makefile together with, by path and never copied,
+ *   /root/reference/src/window.cpp
+ *   /root/reference/vendor/spoa/src/{alignment_engine,graph,simd_alignment_engine,sisd_alignment_engine}.cpp
+ * into oracle/_ref/libracon_ref.so.  It drives racon::Window exactly the way
+ * racon::Polisher::polish does (src/polisher.cpp:181-185, 491-504): one spoa NW engine per
+ * thread, prealloc(window_length, 5), one generate_consensus call per window.
+ *
+ * Used by tests (oracle validation) and by bench.py --impl reference / cpu_baseline.
+ * The product never loads it.
+ */
+#include <algorithm>
+#include <atomic>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "spoa/spoa.hpp"
+#include "window.hpp"
+
+namespace {
+
+struct FlatBatch {
+    int64_t n_windows;
+    const int64_t* win_seq_off; /* [n_windows+1] first sequence index of each window */
+    const int64_t* seq_off;     /* [n_seqs+1] byte offset of each sequence in bases/weights */
+    const uint8_t* bases;
+    const int8_t* weights;      /* same offsets as bases */
+    const uint8_t* has_weights; /* [n_seqs] 0 => no quality (weight 1) */
+    const int32_t* begins;      /* [n_seqs] */
+    const int32_t* ends;        /* [n_seqs] */
+};
+
+/* Build a racon::Window for window w.  Quality strings are rebuilt as PHRED+33 chars and kept
+ * alive in `store` because racon::Window keeps raw pointers (src/window.cpp:34-36,60-62). */
+std::shared_ptr<racon::Window> make_window(const FlatBatch& b, int64_t w, bool tgs,
+                                           std::vector<std::string>& store) {
+    const int64_t s0 = b.win_seq_off[w], s1 = b.win_seq_off[w + 1];
+    store.clear();
+    store.reserve(static_cast<size_t>(s1 - s0));
+    for (int64_t s = s0; s < s1; ++s) {
+        const int64_t len = b.seq_off[s + 1] - b.seq_off[s];
+        std::string q;
+        if (b.has_weights[s]) {
+            q.resize(static_cast<size_t>(len));
+            for (int64_t k = 0; k < len; ++k)
+                q[static_cast<size_t>(k)] = static_cast<char>(b.weights[b.seq_off[s] + k] + 33);
+        } else if (s == s0) {
+            /* backbone without quality: racon uses the dummy '!' string (polisher.cpp:171,392-395)
+             * only when the caller says so; here "no weights" on the backbone means weight 1. */
+            q.assign(static_cast<size_t>(len), static_cast<char>(1 + 33));
+        }
+        store.push_back(std::move(q));
+    }
+    const char* bb = reinterpret_cast<const char*>(b.bases + b.seq_off[s0]);
+    const uint32_t bl = static_cast<uint32_t>(b.seq_off[s0 + 1] - b.seq_off[s0]);
+    auto win = racon::createWindow(static_cast<uint64_t>(w), 0,
+                                   tgs ? racon::WindowType::kTGS : racon::WindowType::kNGS, bb, bl,
+                                   store[0].data(), bl);
+    for (int64_t s = s0 + 1; s < s1; ++s) {
+        const uint32_t len = static_cast<uint32_t>(b.seq_off[s + 1] - b.seq_off[s]);
+        const std::string& q = store[static_cast<size_t>(s - s0)];
+        win->add_layer(reinterpret_cast<const char*>(b.bases + b.seq_off[s]), len,
+                       b.has_weights[s] ? q.data() : nullptr, b.has_weights[s] ? len : 0,
+                       static_cast<uint32_t>(b.begins[s]), static_cast<uint32_t>(b.ends[s]));
+    }
+    return win;
+}
+
+} // namespace
+
+extern "C" {
+
+/* The order racon processes a window's sequences in: window.cpp:78-85 (same call as
+ * cudabatch.cpp:96-104).  rank_out[0] == 0. */
+void ref_layer_order(int32_t n, const int32_t* begins, int32_t* rank_out) {
+    std::vector<uint32_t> rank;
+    rank.reserve(static_cast<size_t>(n));
+    for (int32_t i = 0; i < n; ++i) rank.emplace_back(static_cast<uint32_t>(i));
+    std::sort(rank.begin() + 1, rank.end(),
+              [&](uint32_t lhs, uint32_t rhs) { return begins[lhs] < begins[rhs]; });
+    for (int32_t i = 0; i < n; ++i) rank_out[i] = static_cast<int32_t>(rank[static_cast<size_t>(i)]);
+}
+
+/*
+ * Polish every window of a flat batch with racon::Window::generate_consensus using
+ * n_threads host threads (dynamic window cursor, one engine per thread).
+ * Sequences must be given in ADD order (window.cpp sorts them itself).
+ * cons_out: n_windows rows of `stride` bytes; cons_len/polished: [n_windows].
+ */
+void ref_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int64_t* seq_off,
+                        const uint8_t* bases, const int8_t* weights, const uint8_t* has_weights,
+                        const int32_t* begins, const int32_t* ends, int32_t tgs, int32_t trim,
+                        int32_t m, int32_t x, int32_t g, int32_t window_length, int32_t n_threads,
+                        char* cons_out, int32_t stride, int32_t* cons_len, uint8_t* polished) {
+    FlatBatch b{n_windows, win_seq_off, seq_off, bases, weights, has_weights, begins, ends};
+    if (n_threads < 1) n_threads = 1;
+    std::atomic<int64_t> cursor{0};
+    auto worker = [&]() {
+        std::shared_ptr<spoa::AlignmentEngine> engine = spoa::createAlignmentEngine(
+            spoa::AlignmentType::kNW, static_cast<int8_t>(m), static_cast<int8_t>(x),
+            static_cast<int8_t>(g));
+        engine->prealloc(static_cast<uint32_t>(window_length), 5);
+        std::vector<std::string> store;
+        while (true) {
+            const int64_t w = cursor.fetch_add(1);
+            if (w >= n_windows) break;
+            auto win = make_window(b, w, tgs != 0, store);
+            const bool ok = win->generate_consensus(engine, trim != 0);
+            const std::string& c = win->consensus();
+            const int32_t len = static_cast<int32_t>(std::min<size_t>(c.size(), static_cast<size_t>(stride)));
+            std::memcpy(cons_out + w * static_cast<int64_t>(stride), c.data(), static_cast<size_t>(len));
+            cons_len[w] = static_cast<int32_t>(c.size());
+            polished[w] = ok ? 1 : 0;
+        }
+    };
+    if (n_threads == 1) {
+        worker();
+    } else {
+        std::vector<std::thread> pool;
+        for (int32_t t = 0; t < n_threads; ++t) pool.emplace_back(worker);
+        for (auto& t : pool) t.join();
+    }
+}
+
+/*
+ * Same spoa call sequence as window.cpp:73-116 for ONE full-span window, but returning the
+ * untrimmed consensus AND spoa's per-base coverages (window.cpp keeps them private), plus the
+ * final rank_to_node order, so coverage / topological order can be pinned too.
+ * Sequences are given in PROCESSING order.  Returns consensus length.
+ */
+int32_t ref_spoa_window(int32_t n_seqs, const char* const* seqs, const int32_t* lens,
+                        const int8_t* const* weights, int32_t m, int32_t x, int32_t g,
+                        char* cons_out, uint32_t* cov_out, int32_t max_out, int32_t* rank_out,
+                        int32_t max_nodes, int32_t* n_nodes_out) {
+    auto engine = spoa::createAlignmentEngine(spoa::AlignmentType::kNW, static_cast<int8_t>(m),
+                                              static_cast<int8_t>(x), static_cast<int8_t>(g));
+    auto graph = spoa::createGraph();
+    for (int32_t i = 0; i < n_seqs; ++i) {
+        spoa::Alignment aln;
+        if (i > 0) aln = engine->align(seqs[i], static_cast<uint32_t>(lens[i]), graph);
+        std::vector<uint32_t> w(static_cast<size_t>(lens[i]), 1u);
+        if (weights[i])
+            for (int32_t k = 0; k < lens[i]; ++k) w[static_cast<size_t>(k)] = static_cast<uint32_t>(weights[i][k]);
+        graph->add_alignment(aln, seqs[i], static_cast<uint32_t>(lens[i]), w);
+    }
+    std::vector<uint32_t> cov;
+    std::string cons = graph->generate_consensus(cov);
+    const int32_t len = static_cast<int32_t>(cons.size());
+    if (len <= max_out) {
+        std::memcpy(cons_out, cons.data(), cons.size());
+        if (cov_out) std::memcpy(cov_out, cov.data(), sizeof(uint32_t) * cov.size());
+    }
+    const auto& r2n = graph->rank_to_node_id();
+    if (n_nodes_out) *n_nodes_out = static_cast<int32_t>(r2n.size());
+    if (rank_out && static_cast<int32_t>(r2n.size()) <= max_nodes)
+        for (size_t i = 0; i < r2n.size(); ++i) rank_out[i] = static_cast<int32_t>(r2n[i]);
+    return len;
+}
+
+} // extern "C"

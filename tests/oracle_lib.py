@@ -1,0 +1,124 @@
+"""ctypes loaders for the parity checkers (TEST INFRASTRUCTURE: tests/, smoke(), bench cpu legs only).
+
+  Oracle  -> oracle/liboracle.so          plain-C restatement of racon's spoa path
+  Ref     -> oracle/_ref/libracon_ref.so  the unmodified reference (racon::Window + spoa), built
+                                          here from /root/reference by oracle/Makefile
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+
+def build_oracle(quiet: bool = True) -> None:
+    """(Re)build liboracle.so and, when /root/reference is present, _ref/libracon_ref.so."""
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True,
+                   stdout=subprocess.DEVNULL if quiet else None,
+                   stderr=subprocess.DEVNULL if quiet else None)
+
+
+def _p(a: np.ndarray, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _flat_args(b):
+    return (C.c_int64(b.n_windows), _p(b.win_seq_off, C.c_int64), _p(b.seq_off, C.c_int64),
+            _p(b.bases, C.c_uint8), _p(b.weights, C.c_int8), _p(b.has_weights, C.c_uint8),
+            _p(b.begins, C.c_int32), _p(b.ends, C.c_int32))
+
+
+class Oracle:
+    def __init__(self):
+        path = os.path.join(ORACLE_DIR, "liboracle.so")
+        if not os.path.exists(path):
+            build_oracle()
+        self.lib = C.CDLL(path)
+        self.lib.poa_oracle_polish_windows.restype = None
+
+    def polish(self, batch, order: np.ndarray, m: int, x: int, g: int, tgs: bool = True,
+               trim: bool = True, threads: int = 1, stride: int = 4096, want_stats: bool = False):
+        """Returns (list of consensus bytes, list of coverage arrays, polished flags[, stats])."""
+        W = batch.n_windows
+        cons = np.zeros((W, stride), dtype=np.uint8)
+        cov = np.zeros((W, stride), dtype=np.uint16)
+        clen = np.zeros(W, dtype=np.int32)
+        pol = np.zeros(W, dtype=np.uint8)
+        stats = np.zeros((W, 4), dtype=np.int64)
+        order = np.ascontiguousarray(order, dtype=np.int32)
+        self.lib.poa_oracle_polish_windows(
+            *_flat_args(batch), _p(order, C.c_int32), C.c_int32(int(tgs)), C.c_int32(int(trim)),
+            C.c_int32(m), C.c_int32(x), C.c_int32(g), C.c_int32(threads),
+            cons.ctypes.data_as(C.c_char_p), _p(cov, C.c_uint16), C.c_int32(stride),
+            _p(clen, C.c_int32), _p(pol, C.c_uint8), _p(stats, C.c_int64))
+        assert (clen >= 0).all(), "oracle output stride too small"
+        out = [cons[w, :clen[w]].tobytes() for w in range(W)]
+        covs = [cov[w, :clen[w]].copy() for w in range(W)]
+        if want_stats:
+            return out, covs, pol.astype(bool), stats
+        return out, covs, pol.astype(bool)
+
+
+class Ref:
+    """The unmodified reference.  `available` is False when oracle/_ref was not built/shipped."""
+
+    def __init__(self):
+        path = os.path.join(ORACLE_DIR, "_ref", "libracon_ref.so")
+        if not os.path.exists(path) and os.path.isdir("/root/reference/vendor/spoa/src"):
+            build_oracle()
+        self.available = os.path.exists(path)
+        self.lib = C.CDLL(path) if self.available else None
+
+    def layer_order(self, begins: np.ndarray) -> np.ndarray:
+        begins = np.ascontiguousarray(begins, dtype=np.int32)
+        out = np.zeros(begins.shape[0], dtype=np.int32)
+        self.lib.ref_layer_order(C.c_int32(begins.shape[0]), _p(begins, C.c_int32), _p(out, C.c_int32))
+        return out
+
+    def polish(self, batch, m: int, x: int, g: int, tgs: bool = True, trim: bool = True,
+               threads: int = 1, window_length: int = 500, stride: int = 4096):
+        W = batch.n_windows
+        cons = np.zeros((W, stride), dtype=np.uint8)
+        clen = np.zeros(W, dtype=np.int32)
+        pol = np.zeros(W, dtype=np.uint8)
+        self.lib.ref_polish_windows(
+            *_flat_args(batch), C.c_int32(int(tgs)), C.c_int32(int(trim)), C.c_int32(m),
+            C.c_int32(x), C.c_int32(g), C.c_int32(window_length), C.c_int32(threads),
+            cons.ctypes.data_as(C.c_char_p), C.c_int32(stride), _p(clen, C.c_int32),
+            _p(pol, C.c_uint8))
+        assert (clen <= stride).all()
+        return [cons[w, :clen[w]].tobytes() for w in range(W)], pol.astype(bool)
+
+    def spoa_window(self, seqs, weights, m: int, x: int, g: int, max_nodes: int = 1 << 16):
+        """seqs in PROCESSING order.  Returns (consensus, coverage, rank_to_node)."""
+        n = len(seqs)
+        arr_s = (C.c_char_p * n)(*[bytes(s) for s in seqs])
+        lens = np.asarray([len(s) for s in seqs], dtype=np.int32)
+        keep = [None if w is None else np.ascontiguousarray(w, dtype=np.int8) for w in weights]
+        arr_w = (C.POINTER(C.c_int8) * n)(*[
+            C.cast(None, C.POINTER(C.c_int8)) if w is None else _p(w, C.c_int8) for w in keep])
+        max_out = int(lens.sum()) + 8
+        cons = np.zeros(max_out, dtype=np.uint8)
+        cov = np.zeros(max_out, dtype=np.uint32)
+        rank = np.zeros(max_nodes, dtype=np.int32)
+        nn = C.c_int32(0)
+        self.lib.ref_spoa_window.restype = C.c_int32
+        ln = self.lib.ref_spoa_window(
+            C.c_int32(n), arr_s, _p(lens, C.c_int32), arr_w, C.c_int32(m), C.c_int32(x),
+            C.c_int32(g), cons.ctypes.data_as(C.c_char_p), _p(cov, C.c_uint32), C.c_int32(max_out),
+            _p(rank, C.c_int32), C.c_int32(max_nodes), C.byref(nn))
+        return cons[:ln].tobytes(), cov[:ln].copy(), rank[:nn.value].copy()
+
+
+def processing_order(batch, layer_order_fn) -> np.ndarray:
+    """order[s] for a flat batch using a layer-order function (begins[n] -> rank[n])."""
+    order = np.zeros(batch.n_seqs, dtype=np.int32)
+    for w in range(batch.n_windows):
+        s0, s1 = int(batch.win_seq_off[w]), int(batch.win_seq_off[w + 1])
+        order[s0:s1] = layer_order_fn(batch.begins[s0:s1])
+    return order
