@@ -1,0 +1,165 @@
+/*
+ * b200poa.h -- C ABI of the B200-native batched POA consensus engine.
+ *
+ * This is the drop-in boundary for racon's CUDA polishing path.  Each entry point replaces one
+ * member of the C++ interface racon binds today (paths relative to the racon-gpu repository):
+ *
+ *   b200poa_init                 <- cudapoa::Init()                         vendor/GenomeWorks/cudapoa/include/claraparabricks/genomeworks/cudapoa/cudapoa.hpp:56
+ *   b200poa_config_default       <- BatchConfig::BatchConfig(max_seq_sz, max_seq_per_poa, band_width, banding)
+ *                                                                           .../cudapoa/batch.hpp:57-80, cudapoa/src/batch.cu:34-71
+ *   b200poa_batch_create         <- create_batch(device, stream, max_gpu_mem, output_mask, config, gap, mismatch, match)
+ *                                                                           .../cudapoa/batch.hpp:174-181
+ *   b200poa_batch_add_group      <- Batch::add_poa_group(per_seq_status, group)   .../cudapoa/batch.hpp:104-105
+ *   b200poa_batch_total_poas     <- Batch::get_total_poas()                 .../cudapoa/batch.hpp:110
+ *   b200poa_batch_generate       <- Batch::generate_poa()                   .../cudapoa/batch.hpp:113
+ *   b200poa_batch_get_consensus  <- Batch::get_consensus(consensus, coverage, output_status)  .../cudapoa/batch.hpp:125-127
+ *   b200poa_batch_id             <- Batch::batch_id()                       .../cudapoa/batch.hpp:155
+ *   b200poa_batch_reset          <- Batch::reset()                          .../cudapoa/batch.hpp:158
+ *   b200poa_batch_destroy        <- Batch::~Batch()
+ *   b200poa_layer_order          <- the std::sort in CUDABatchProcessor::addWindow   src/cuda/cudabatch.cpp:96-104
+ *                                   (same call as Window::generate_consensus, src/window.cpp:78-85)
+ *   b200poa_batch_add_windows    <- the addWindow loop of CUDAPolisher::polish's fill_next_batch
+ *                                   src/cuda/cudapolisher.cpp:254-276, over a columnar window arena
+ *
+ * Plain C types only: no C++ objects, no exceptions, no torch types cross this boundary.
+ * Status codes are the values of cudapoa::StatusType (cudapoa.hpp:32-45) plus three extensions.
+ *
+ * Semantics differ from the reference GPU path in one deliberate way: results equal racon's CPU
+ * (spoa) path -- spoa's topological order, strict ">" consensus tie-breaks, spoa coverage -- which
+ * the reference GPU path does not reproduce (test/racon_test.cpp:311-312 vs :106-107).
+ */
+#ifndef B200POA_H
+#define B200POA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* cudapoa::StatusType values (cudapoa.hpp:32-45) */
+enum {
+    B200POA_SUCCESS = 0,
+    B200POA_EXCEEDED_MAXIMUM_POAS = 1,              /* batch full: launch what you have */
+    B200POA_EXCEEDED_MAXIMUM_SEQUENCE_SIZE = 2,     /* per-entry, soft: entry skipped */
+    B200POA_EXCEEDED_MAXIMUM_SEQUENCES_PER_POA = 3, /* per-entry, soft: entry skipped */
+    B200POA_NODE_COUNT_EXCEEDED_MAXIMUM_GRAPH_SIZE = 4,
+    B200POA_EDGE_COUNT_EXCEEDED_MAXIMUM_GRAPH_SIZE = 5,
+    B200POA_EXCEEDED_ADAPTIVE_BANDED_MATRIX_SIZE = 6,
+    B200POA_SEQ_LEN_EXCEEDED_MAXIMUM_NODES_PER_WINDOW = 7,
+    B200POA_LOOP_COUNT_EXCEEDED_UPPER_BOUND = 8,
+    B200POA_OUTPUT_TYPE_UNAVAILABLE = 9,
+    B200POA_GENERIC_ERROR = 10,
+    /* extensions */
+    B200POA_ALIGNED_COUNT_EXCEEDED = 11, /* more than 8 mutually aligned nodes in one column */
+    B200POA_SCORE_RANGE_EXCEEDED = 12,   /* alignment does not fit int16 cells */
+    B200POA_TRACEBACK_LOST = 13,         /* static band did not contain a consistent path */
+    B200POA_PARTIAL_SPAN_UNSUPPORTED = 14, /* layer does not span the window (window.cpp:92-103 subgraph path) */
+    B200POA_INVALID_ARGUMENT = 15,       /* what the C++ API reports by throwing std::invalid_argument */
+    B200POA_CUDA_ERROR = 16              /* what the C++ API reports by aborting in GW_CU_CHECK_ERR */
+};
+
+/* cudapoa::BandMode (cudapoa.hpp:47-53); adaptive_band is not selectable from racon (cudabatch.cpp:59) */
+enum { B200POA_FULL_BAND = 0, B200POA_STATIC_BAND = 1 };
+
+/* cudapoa::OutputType (cudapoa.hpp:59-63); racon asks for consensus only (cudabatch.cpp:64) */
+enum { B200POA_OUTPUT_CONSENSUS = 0x1, B200POA_OUTPUT_MSA = 0x2 };
+
+/* cudapoa::BatchConfig (batch.hpp:57-80).  Fill with b200poa_config_default. */
+typedef struct b200poa_config {
+    int32_t max_sequence_size;     /* racon: 1023 (cudabatch.cpp:56) */
+    int32_t max_consensus_size;    /* 2 * max_sequence_size */
+    int32_t max_nodes_per_graph;   /* 3x (full band) / 4x (static band) max_sequence_size */
+    int32_t alignment_band_width;  /* racon: 256 */
+    int32_t max_sequences_per_poa; /* racon: 200 (cudapolisher.cpp:226) */
+    int32_t band_mode;             /* B200POA_FULL_BAND | B200POA_STATIC_BAND */
+} b200poa_config;
+
+/* cudapoa::Entry (batch.hpp:45-53) + the layer span racon's Window knows (window.hpp:73) */
+typedef struct b200poa_entry {
+    const char* seq;       /* borrowed for the duration of the call */
+    const int8_t* weights; /* per-base weight (PHRED-33); NULL => 1 per base */
+    int32_t length;
+    int32_t begin;         /* layer span on the backbone; ignored for entry 0 */
+    int32_t end;           /* (begin,end) = (0, backbone_len-1) or (-1,-1) => spans the window */
+} b200poa_entry;
+
+typedef struct b200poa_batch b200poa_batch;
+
+int32_t b200poa_init(void);
+
+void b200poa_config_default(b200poa_config* cfg, int32_t max_seq_sz, int32_t max_seq_per_poa,
+                            int32_t band_width, int32_t band_mode);
+
+/* stream: a cudaStream_t owned by the caller (cudabatch.cpp:54,74).  max_gpu_mem: device bytes the
+ * batch may use (cudapolisher.cpp:233-238 passes 0.9*free/batches). */
+int32_t b200poa_batch_create(int32_t device_id, void* stream, size_t max_gpu_mem, int32_t output_mask,
+                             const b200poa_config* cfg, int16_t gap_score, int16_t mismatch_score,
+                             int16_t match_score, b200poa_batch** out);
+
+/* entries[0] is the backbone, entries[1..n) the layers ALREADY in processing order.
+ * per_seq_status (nullable) receives n codes.  Returns B200POA_EXCEEDED_MAXIMUM_POAS when the batch
+ * is full (nothing added). */
+int32_t b200poa_batch_add_group(b200poa_batch* b, const b200poa_entry* entries, int32_t n,
+                                int32_t* per_seq_status);
+
+/* The order racon processes a window's sequences in (rank_out[0] == 0): src/window.cpp:78-85. */
+void b200poa_layer_order(int32_t n, const int32_t* begins, int32_t* rank_out);
+
+/*
+ * Columnar fast path: add windows [first, n_windows) of a flat arena (layout documented in
+ * racon_gpu_b200/windows.py) until the batch is full.  Sequences are in ADD order; the processing
+ * order is derived inside with b200poa_layer_order.  *n_added receives the number of windows
+ * accepted; seqs_added (nullable, one per accepted window) the number of layers actually staged
+ * (cudabatch.cpp:134-153's seqs_added_per_window_).
+ */
+int32_t b200poa_batch_add_windows(b200poa_batch* b, int64_t n_windows, int64_t first,
+                                  const int64_t* win_seq_off, const int64_t* seq_off,
+                                  const uint8_t* bases, const int8_t* weights,
+                                  const uint8_t* has_weights, const int32_t* begins,
+                                  const int32_t* ends, int64_t* n_added, int32_t* seqs_added);
+
+int32_t b200poa_batch_total_poas(const b200poa_batch* b);
+
+/* Asynchronous on the batch's stream: H2D of the staged arena, the POA kernel, D2H of the results. */
+int32_t b200poa_batch_generate(b200poa_batch* b);
+
+/* The three stages of b200poa_batch_generate, separately (benchmarks time the kernel alone with
+ * inputs already resident in HBM). All asynchronous on the batch's stream. */
+int32_t b200poa_batch_upload(b200poa_batch* b);
+int32_t b200poa_batch_launch(b200poa_batch* b);
+int32_t b200poa_batch_download(b200poa_batch* b);
+
+/*
+ * Synchronises the stream.  Row i of cons/cov (row stride *stride elements) holds window i's
+ * UNTRIMMED consensus and per-base coverage, lens[i] its length, status[i] its StatusType.
+ * Pointers are into batch-owned pinned host memory, valid until reset/destroy.
+ */
+int32_t b200poa_batch_get_consensus(b200poa_batch* b, const uint8_t** cons, const uint16_t** cov,
+                                    const int32_t** lens, const int32_t** status, int32_t* stride);
+
+int32_t b200poa_batch_id(const b200poa_batch* b);
+int32_t b200poa_batch_reset(b200poa_batch* b);
+void b200poa_batch_destroy(b200poa_batch* b);
+
+/* introspection used by benchmarks and tests */
+typedef struct b200poa_batch_info {
+    int32_t n_slots;          /* resident warps = windows in flight on the device */
+    int32_t max_poas;         /* window capacity of the batch */
+    int64_t arena_capacity;   /* bases capacity */
+    int64_t slot_bytes;       /* device bytes per slot */
+    int64_t device_bytes;     /* total device allocation */
+    int64_t staged_bases;     /* bases currently staged */
+    int64_t kernel_launches;  /* kernels launched since creation */
+    int32_t smem_bytes;       /* dynamic shared memory per block */
+    int32_t blocks_per_sm;    /* occupancy the launch was sized for */
+} b200poa_batch_info;
+int32_t b200poa_batch_get_info(const b200poa_batch* b, b200poa_batch_info* info);
+
+const char* b200poa_status_string(int32_t status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200POA_H */

@@ -1,0 +1,290 @@
+"""ctypes binding of the C ABI (include/b200poa.h) and the Python mirror of racon's batch adapter.
+
+`PoaBatch` wraps one `b200poa_batch` (== one `cudapoa::Batch`, /root/reference/vendor/GenomeWorks/
+cudapoa/include/claraparabricks/genomeworks/cudapoa/batch.hpp:88-160).  `CUDABatchProcessor` mirrors
+racon's adapter of the same name (/root/reference/src/cuda/cudabatch.cpp:41-278): addWindow ->
+generateConsensus -> trimmed consensus + per-window status, but with the CPU path's trimming rule
+(src/window.cpp:118-139), which is the parity target.
+
+There is no CPU fallback anywhere in this module: if libb200poa.so cannot be built or loaded, or no
+CUDA device is visible, it raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .windows import WindowBatch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libb200poa.so")
+
+SUCCESS = 0
+EXCEEDED_MAXIMUM_POAS = 1
+EXCEEDED_MAXIMUM_SEQUENCE_SIZE = 2
+EXCEEDED_MAXIMUM_SEQUENCES_PER_POA = 3
+PARTIAL_SPAN_UNSUPPORTED = 14
+FULL_BAND = 0
+STATIC_BAND = 1
+OUTPUT_CONSENSUS = 1
+
+#: every symbol include/b200poa.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = (
+    "b200poa_init", "b200poa_config_default", "b200poa_batch_create", "b200poa_batch_add_group",
+    "b200poa_layer_order", "b200poa_batch_add_windows", "b200poa_batch_total_poas",
+    "b200poa_batch_generate", "b200poa_batch_upload", "b200poa_batch_launch",
+    "b200poa_batch_download", "b200poa_batch_get_consensus", "b200poa_batch_id",
+    "b200poa_batch_reset", "b200poa_batch_destroy", "b200poa_batch_get_info",
+    "b200poa_status_string", "b200poa_polish_windows",
+)
+
+
+class Config(C.Structure):
+    _fields_ = [("max_sequence_size", C.c_int32), ("max_consensus_size", C.c_int32),
+                ("max_nodes_per_graph", C.c_int32), ("alignment_band_width", C.c_int32),
+                ("max_sequences_per_poa", C.c_int32), ("band_mode", C.c_int32)]
+
+
+class Entry(C.Structure):
+    _fields_ = [("seq", C.c_char_p), ("weights", C.POINTER(C.c_int8)), ("length", C.c_int32),
+                ("begin", C.c_int32), ("end", C.c_int32)]
+
+
+class BatchInfo(C.Structure):
+    _fields_ = [("n_slots", C.c_int32), ("max_poas", C.c_int32), ("arena_capacity", C.c_int64),
+                ("slot_bytes", C.c_int64), ("device_bytes", C.c_int64), ("staged_bases", C.c_int64),
+                ("kernel_launches", C.c_int64), ("smem_bytes", C.c_int32), ("blocks_per_sm", C.c_int32)]
+
+
+_lib = None
+
+
+def load_library(build_if_missing: bool = True) -> C.CDLL:
+    """Load libb200poa.so (building it in-tree with nvcc if needed).  Raises if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing:
+        from . import build as _build
+        if _build.needs_build():
+            _build.build()
+    if not os.path.exists(_LIB_PATH):
+        raise RuntimeError(f"{_LIB_PATH} is missing: build it with `python -m racon_gpu_b200.build` "
+                           "(the B200 POA engine has no CPU fallback)")
+    lib = C.CDLL(_LIB_PATH)
+    lib.b200poa_status_string.restype = C.c_char_p
+    lib.b200poa_batch_destroy.restype = None
+    lib.b200poa_config_default.restype = None
+    lib.b200poa_layer_order.restype = None
+    _lib = lib
+    return lib
+
+
+def status_string(st: int) -> str:
+    return load_library().b200poa_status_string(C.c_int32(int(st))).decode()
+
+
+def _p(a: np.ndarray, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def layer_order(begins: np.ndarray) -> np.ndarray:
+    """Processing order of a window's sequences (src/window.cpp:78-85)."""
+    begins = np.ascontiguousarray(begins, dtype=np.int32)
+    out = np.zeros(begins.shape[0], dtype=np.int32)
+    load_library().b200poa_layer_order(C.c_int32(begins.shape[0]), _p(begins, C.c_int32), _p(out, C.c_int32))
+    return out
+
+
+def processing_order(batch: WindowBatch) -> np.ndarray:
+    order = np.zeros(batch.n_seqs, dtype=np.int32)
+    for w in range(batch.n_windows):
+        s0, s1 = int(batch.win_seq_off[w]), int(batch.win_seq_off[w + 1])
+        order[s0:s1] = layer_order(batch.begins[s0:s1])
+    return order
+
+
+class PoaBatch:
+    """One `b200poa_batch`.  `stream` is a raw cudaStream_t (int) owned by the caller, 0 = default."""
+
+    def __init__(self, device: int = 0, stream: int = 0, max_gpu_mem: int = 8 << 30,
+                 max_sequence_size: int = 1023, max_sequences_per_poa: int = 200,
+                 band_width: int = 256, banded: bool = False, gap: int = -4, mismatch: int = -5,
+                 match: int = 3, output_mask: int = OUTPUT_CONSENSUS):
+        self.lib = load_library()
+        self.cfg = Config()
+        self.lib.b200poa_config_default(C.byref(self.cfg), C.c_int32(max_sequence_size),
+                                        C.c_int32(max_sequences_per_poa), C.c_int32(band_width),
+                                        C.c_int32(STATIC_BAND if banded else FULL_BAND))
+        self.handle = C.c_void_p()
+        st = self.lib.b200poa_batch_create(C.c_int32(device), C.c_void_p(stream), C.c_size_t(max_gpu_mem),
+                                           C.c_int32(output_mask), C.byref(self.cfg), C.c_int16(gap),
+                                           C.c_int16(mismatch), C.c_int16(match), C.byref(self.handle))
+        if st != SUCCESS:
+            raise RuntimeError(f"b200poa_batch_create failed: {status_string(st)}")
+
+    def close(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            self.lib.b200poa_batch_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- cudapoa::Batch method set -------------------------------------------------------------
+    def add_poa_group(self, entries):
+        """entries: list of (seq: bytes, weights: np.int8 array | None[, begin, end]) in processing
+        order.  Returns (status, per_seq_status list)."""
+        n = len(entries)
+        arr = (Entry * n)()
+        keep = []
+        for i, e in enumerate(entries):
+            seq, wt = e[0], e[1]
+            bg, en = (e[2], e[3]) if len(e) >= 4 else (-1, -1)
+            arr[i].seq = seq
+            if wt is None:
+                arr[i].weights = C.cast(None, C.POINTER(C.c_int8))
+            else:
+                wt = np.ascontiguousarray(wt, dtype=np.int8)
+                keep.append(wt)
+                arr[i].weights = _p(wt, C.c_int8)
+            arr[i].length = len(seq)
+            arr[i].begin = bg
+            arr[i].end = en
+        per = np.zeros(n, dtype=np.int32)
+        st = self.lib.b200poa_batch_add_group(self.handle, arr, C.c_int32(n), _p(per, C.c_int32))
+        return st, per.tolist()
+
+    def add_windows(self, batch: WindowBatch, first: int = 0):
+        """Columnar add: stage windows [first, ...) until full.  Returns (n_added, seqs_added)."""
+        n_added = C.c_int64(0)
+        seqs_added = np.zeros(max(batch.n_windows - first, 1), dtype=np.int32)
+        st = self.lib.b200poa_batch_add_windows(
+            self.handle, C.c_int64(batch.n_windows), C.c_int64(first), _p(batch.win_seq_off, C.c_int64),
+            _p(batch.seq_off, C.c_int64), _p(batch.bases, C.c_uint8), _p(batch.weights, C.c_int8),
+            _p(batch.has_weights, C.c_uint8), _p(batch.begins, C.c_int32), _p(batch.ends, C.c_int32),
+            C.byref(n_added), _p(seqs_added, C.c_int32))
+        if st != SUCCESS:
+            raise RuntimeError(f"b200poa_batch_add_windows failed: {status_string(st)}")
+        return int(n_added.value), seqs_added[:n_added.value]
+
+    def get_total_poas(self) -> int:
+        return int(self.lib.b200poa_batch_total_poas(self.handle))
+
+    def _check(self, st, what):
+        if st != SUCCESS:
+            raise RuntimeError(f"{what} failed: {status_string(st)}")
+
+    def generate_poa(self):
+        self._check(self.lib.b200poa_batch_generate(self.handle), "b200poa_batch_generate")
+
+    def upload(self):
+        self._check(self.lib.b200poa_batch_upload(self.handle), "b200poa_batch_upload")
+
+    def launch(self):
+        self._check(self.lib.b200poa_batch_launch(self.handle), "b200poa_batch_launch")
+
+    def download(self):
+        self._check(self.lib.b200poa_batch_download(self.handle), "b200poa_batch_download")
+
+    def get_consensus(self):
+        """Synchronises.  Returns (consensus list[bytes], coverage list[np.uint16], status np.int32)."""
+        cons = C.POINTER(C.c_uint8)()
+        cov = C.POINTER(C.c_uint16)()
+        lens = C.POINTER(C.c_int32)()
+        stat = C.POINTER(C.c_int32)()
+        stride = C.c_int32(0)
+        self._check(self.lib.b200poa_batch_get_consensus(self.handle, C.byref(cons), C.byref(cov),
+                                                         C.byref(lens), C.byref(stat), C.byref(stride)),
+                    "b200poa_batch_get_consensus")
+        n = self.get_total_poas()
+        if n == 0:
+            return [], [], np.zeros(0, dtype=np.int32)
+        s = stride.value
+        lens_a = np.ctypeslib.as_array(lens, shape=(n,)).copy()
+        stat_a = np.ctypeslib.as_array(stat, shape=(n,)).copy()
+        cons_a = np.ctypeslib.as_array(cons, shape=(n, s))
+        cov_a = np.ctypeslib.as_array(cov, shape=(n, s))
+        out_c = [cons_a[i, :lens_a[i]].tobytes() for i in range(n)]
+        out_v = [cov_a[i, :lens_a[i]].copy() for i in range(n)]
+        return out_c, out_v, stat_a
+
+    def batch_id(self) -> int:
+        return int(self.lib.b200poa_batch_id(self.handle))
+
+    def reset(self):
+        self.lib.b200poa_batch_reset(self.handle)
+
+    def info(self) -> dict:
+        inf = BatchInfo()
+        self.lib.b200poa_batch_get_info(self.handle, C.byref(inf))
+        return {k: getattr(inf, k) for k, _ in BatchInfo._fields_}
+
+
+def trim_consensus(cons: bytes, cov: np.ndarray, n_seqs: int):
+    """racon's TGS coverage trim, CPU semantics (src/window.cpp:118-139).
+    Returns (consensus, chimeric_warning)."""
+    avg = (n_seqs - 1) // 2
+    ok = np.nonzero(cov >= avg)[0]
+    if ok.shape[0] == 0:
+        return cons, True
+    b, e = int(ok[0]), int(ok[-1])
+    if b >= e:
+        return cons, True
+    return cons[b:e + 1], False
+
+
+class CUDABatchProcessor:
+    """Python mirror of racon::CUDABatchProcessor (src/cuda/cudabatch.cpp) over a columnar arena.
+
+    Differences from the reference adapter, all on purpose: the trim threshold,
+    the chimeric-window status and the NGS status follow the CPU path (src/window.cpp:65-142), so a
+    window this class reports `True` for is byte-identical to racon's CPU consensus.
+    """
+
+    def __init__(self, max_window_depth: int = 200, device: int = 0, avail_mem: int = 8 << 30,
+                 gap: int = -4, mismatch: int = -5, match: int = 3, cuda_banded_alignment: bool = False,
+                 stream: int = 0, tgs: bool = True, trim: bool = True):
+        # cudabatch.cpp:56-68: BatchConfig(1023, max_window_depth, 256, band mode)
+        self.batch = PoaBatch(device=device, stream=stream, max_gpu_mem=avail_mem,
+                              max_sequence_size=1023, max_sequences_per_poa=max_window_depth,
+                              band_width=256, banded=cuda_banded_alignment, gap=gap,
+                              mismatch=mismatch, match=match)
+        self.tgs, self.trim = tgs, trim
+        self.n_seqs = []
+
+    def add_windows(self, windows: WindowBatch, first: int = 0) -> int:
+        """The addWindow loop of cudapolisher.cpp:254-276.  Returns how many windows fitted."""
+        n, seqs_added = self.batch.add_windows(windows, first)
+        s = windows.win_seq_off
+        self.n_seqs.extend((s[first + 1:first + n + 1] - s[first:first + n]).tolist())
+        return n
+
+    def has_windows(self) -> bool:
+        return self.batch.get_total_poas() > 0
+
+    def generate_consensus(self):
+        """Returns (list of consensus bytes, list of bool status) for the windows in the batch."""
+        self.batch.generate_poa()
+        cons, cov, status = self.batch.get_consensus()
+        out, ok = [], []
+        for i in range(len(cons)):
+            if status[i] != SUCCESS:
+                out.append(b"")
+                ok.append(False)  # cudabatch.cpp:209-213: left to the caller's CPU path
+                continue
+            c = cons[i]
+            if self.tgs and self.trim:
+                c, _ = trim_consensus(c, cov[i], self.n_seqs[i])
+            out.append(c)
+            ok.append(True)
+        return out, ok
+
+    def reset(self):
+        self.batch.reset()
+        self.n_seqs = []

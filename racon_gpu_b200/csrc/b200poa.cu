@@ -1,0 +1,594 @@
+/*
+ * b200poa.cu -- C ABI (include/b200poa.h) + batch runtime + the POA kernel launch.
+ *
+ * Batch runtime = what vendor/GenomeWorks/cudapoa/src/cudapoa_batch.cuh:62-646 and
+ * allocate_block.hpp:53-479 do in the reference, re-designed:
+ *   - device memory is split into (a) per-RESIDENT-WARP workspaces ("slots": graph + score band)
+ *     and (b) the batch's columnar input arena and compact outputs.  The reference sizes the batch
+ *     by score-matrix memory per window (allocate_block.hpp:81-83: ~20-35k windows per 180 GB);
+ *     here a batch is limited only by its arena, because a slot is reused by every window the warp
+ *     pulls from the work queue;
+ *   - one persistent launch per batch: grid = resident warps, each warp pops windows from an
+ *     atomic cursor over a longest-first work list (depth/length-divergent windows);
+ *   - H2D is 4 contiguous async copies of exactly the staged bytes, D2H copies exactly
+ *     poa_count rows (the reference copies max_poas full rows, cudapoa_batch.cuh:213-222).
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <numeric>
+#include <vector>
+
+#include "../../include/b200poa.h"
+#include "poa_core.cuh"
+#include "poa_fill.cuh"
+
+using namespace b200poa;
+
+/* ------------------------------------------------------------------------------------------ */
+/* kernel                                                                                      */
+/* ------------------------------------------------------------------------------------------ */
+struct KernelArgs {
+    Params p;
+    uint8_t* slab;       /* n_slots * slot_bytes */
+    size_t slot_bytes;
+    int32_t n_windows;
+    const int32_t* work; /* window ids, most expensive first */
+    int32_t* cursor;     /* atomic work cursor (zeroed before launch) */
+    const uint8_t* bases;
+    const int8_t* weights;
+    const int64_t* seq_off;     /* [n_seqs+1] */
+    const int32_t* win_seq_off; /* [n_windows+1] */
+    const int32_t* win_flags;   /* per window: pre-set status (!= 0 => skip) */
+    uint8_t* out_cons;
+    uint16_t* out_cov;
+    int32_t* out_len;
+    int32_t* out_status;
+    int32_t prof_stride;
+};
+
+__global__ void __launch_bounds__(32) poa_window_kernel(const KernelArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Slot s;
+    slot_bind(s, a.slab + (size_t)blockIdx.x * a.slot_bytes, a.p, nullptr);
+    CudaFill fill;
+    fill.prof = reinterpret_cast<int16_t*>(smem_raw);
+    fill.prof_stride = a.prof_stride;
+    fill.dyn_code = -1;
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        int32_t t = 0;
+        if (lane == 0) t = atomicAdd(a.cursor, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= a.n_windows) break;
+        const int32_t w = a.work[t];
+        const size_t orow = (size_t)w * (size_t)a.p.max_cons;
+        if (a.win_flags[w] != 0) {
+            if (lane == 0) {
+                a.out_len[w] = 0;
+                a.out_status[w] = a.win_flags[w];
+            }
+            continue;
+        }
+        WindowView wv;
+        const int32_t s0 = a.win_seq_off[w];
+        wv.n_seqs = a.win_seq_off[w + 1] - s0;
+        wv.bases = a.bases;
+        wv.weights = a.weights;
+        wv.seq_off = a.seq_off + s0;
+        process_window(s, a.p, wv, fill, a.out_cons + orow, a.out_cov + orow, a.out_len + w,
+                       a.out_status + w);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* batch object                                                                                */
+/* ------------------------------------------------------------------------------------------ */
+#define CU_TRY(expr)                                                                         \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            std::fprintf(stderr, "[b200poa] CUDA error %s at %s:%d: %s\n", #expr, __FILE__,  \
+                         __LINE__, cudaGetErrorString(_e));                                  \
+            return B200POA_CUDA_ERROR;                                                       \
+        }                                                                                    \
+    } while (0)
+
+namespace {
+
+std::atomic<int32_t> g_batches{0};
+
+struct DeviceGuard { /* scoped_device_switch (GenomeWorks common/base cudautils.hpp) */
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+} // namespace
+
+struct b200poa_batch {
+    int32_t id = 0;
+    int32_t device = 0;
+    cudaStream_t stream = nullptr;
+    int32_t output_mask = 0;
+    b200poa_config cfg{};
+    Params p{};
+    /* capacity */
+    int32_t max_poas = 0;
+    int64_t max_seqs = 0;
+    int64_t arena_cap = 0;
+    int32_t n_slots = 0;
+    size_t slot_bytes = 0;
+    int32_t smem_bytes = 0;
+    int32_t prof_stride = 0;
+    int32_t blocks_per_sm = 0;
+    size_t device_bytes = 0;
+    /* pinned host staging */
+    uint8_t* h_bases = nullptr;
+    int8_t* h_weights = nullptr;
+    int64_t* h_seq_off = nullptr;
+    int32_t* h_win_seq_off = nullptr;
+    int32_t* h_win_flags = nullptr;
+    int32_t* h_work = nullptr;
+    uint8_t* h_cons = nullptr;
+    uint16_t* h_cov = nullptr;
+    int32_t* h_len = nullptr;
+    int32_t* h_status = nullptr;
+    /* device */
+    uint8_t* d_slab = nullptr;
+    uint8_t* d_bases = nullptr;
+    int8_t* d_weights = nullptr;
+    int64_t* d_seq_off = nullptr;
+    int32_t* d_win_seq_off = nullptr;
+    int32_t* d_win_flags = nullptr;
+    int32_t* d_work = nullptr;
+    int32_t* d_cursor = nullptr;
+    uint8_t* d_cons = nullptr;
+    uint16_t* d_cov = nullptr;
+    int32_t* d_len = nullptr;
+    int32_t* d_status = nullptr;
+    /* fill state */
+    int32_t poa_count = 0;
+    int64_t seq_count = 0;
+    int64_t base_count = 0;
+    std::vector<int64_t> cost; /* per window work estimate for the longest-first work list */
+    int64_t launches = 0;
+    bool uploaded = false;
+};
+
+static void free_batch(b200poa_batch* b) {
+    if (!b) return;
+    DeviceGuard g(b->device);
+    cudaFreeHost(b->h_bases);
+    cudaFreeHost(b->h_weights);
+    cudaFreeHost(b->h_seq_off);
+    cudaFreeHost(b->h_win_seq_off);
+    cudaFreeHost(b->h_win_flags);
+    cudaFreeHost(b->h_work);
+    cudaFreeHost(b->h_cons);
+    cudaFreeHost(b->h_cov);
+    cudaFreeHost(b->h_len);
+    cudaFreeHost(b->h_status);
+    cudaFree(b->d_slab);
+    cudaFree(b->d_bases);
+    cudaFree(b->d_weights);
+    cudaFree(b->d_seq_off);
+    cudaFree(b->d_win_seq_off);
+    cudaFree(b->d_win_flags);
+    cudaFree(b->d_work);
+    cudaFree(b->d_cursor);
+    cudaFree(b->d_cons);
+    cudaFree(b->d_cov);
+    cudaFree(b->d_len);
+    cudaFree(b->d_status);
+    delete b;
+}
+
+/* stage one window whose sequences are given in processing order through a getter */
+template <class Get>
+static int32_t stage_window(b200poa_batch* b, int32_t n, Get get, int32_t* per_seq_status, int32_t* n_added_out) {
+    /* cudapoa_batch.cuh:108-148: the whole group must fit or the batch reports "full" */
+    if (b->poa_count >= b->max_poas) return B200POA_EXCEEDED_MAXIMUM_POAS;
+    int64_t bytes = 0;
+    int32_t n_ok = 0;
+    for (int32_t i = 0; i < n; ++i) {
+        const char* seq; const int8_t* w; int32_t len, bg, en;
+        get(i, seq, w, len, bg, en);
+        if (len <= b->cfg.max_sequence_size && n_ok < b->cfg.max_sequences_per_poa) {
+            bytes += len;
+            ++n_ok;
+        }
+    }
+    if (b->base_count + bytes > b->arena_cap || b->seq_count + n_ok > b->max_seqs)
+        return B200POA_EXCEEDED_MAXIMUM_POAS;
+
+    int32_t flag = 0, added = 0;
+    int64_t cost = 0;
+    int32_t bb_len = 0;
+    for (int32_t i = 0; i < n; ++i) {
+        const char* seq; const int8_t* w; int32_t len, bg, en;
+        get(i, seq, w, len, bg, en);
+        int32_t st = B200POA_SUCCESS;
+        if (len > b->cfg.max_sequence_size) st = B200POA_EXCEEDED_MAXIMUM_SEQUENCE_SIZE; /* cudapoa_batch.cuh:501-504 */
+        else if (added >= b->cfg.max_sequences_per_poa) st = B200POA_EXCEEDED_MAXIMUM_SEQUENCES_PER_POA; /* :513-516 */
+        if (per_seq_status) per_seq_status[i] = st;
+        if (st != B200POA_SUCCESS) continue;
+        if (w) {
+            for (int32_t k = 0; k < len; ++k)
+                if (w[k] < 0) return B200POA_INVALID_ARGUMENT; /* cudapoa_batch.cuh:533-537 throws */
+        }
+        if (added == 0) {
+            bb_len = len;
+        } else if (!(bg == -1 && en == -1)) {
+            /* window.cpp:87,92-93: does the layer span the whole window? */
+            const uint32_t L = (uint32_t)bb_len;
+            const uint32_t offset = (uint32_t)(0.01 * L);
+            if (!((uint32_t)bg < offset && (uint32_t)en > L - offset)) flag = B200POA_PARTIAL_SPAN_UNSUPPORTED;
+        }
+        std::memcpy(b->h_bases + b->base_count, seq, (size_t)len);
+        if (w) std::memcpy(b->h_weights + b->base_count, w, (size_t)len);
+        else std::memset(b->h_weights + b->base_count, 1, (size_t)len); /* cudapoa_batch.cuh:525-530 */
+        b->base_count += len;
+        b->seq_count += 1;
+        b->h_seq_off[b->seq_count] = b->base_count;
+        cost += (int64_t)len * (bb_len + (int64_t)added * (bb_len / 8 + 1));
+        ++added;
+    }
+    b->h_win_flags[b->poa_count] = flag;
+    b->poa_count += 1;
+    b->h_win_seq_off[b->poa_count] = (int32_t)b->seq_count;
+    b->cost.push_back(cost);
+    b->uploaded = false;
+    if (n_added_out) *n_added_out = added > 0 ? added - 1 : 0;
+    return B200POA_SUCCESS;
+}
+
+static int32_t alloc_batch_memory(b200poa_batch* b) {
+    const Params& p = b->p;
+    const size_t MP = (size_t)b->max_poas, MS = (size_t)b->max_seqs, AC = (size_t)b->arena_cap;
+    CU_TRY(cudaMalloc(&b->d_slab, (size_t)b->n_slots * b->slot_bytes));
+    CU_TRY(cudaMalloc(&b->d_bases, AC));
+    CU_TRY(cudaMalloc(&b->d_weights, AC));
+    CU_TRY(cudaMalloc(&b->d_seq_off, (MS + 1) * sizeof(int64_t)));
+    CU_TRY(cudaMalloc(&b->d_win_seq_off, (MP + 1) * sizeof(int32_t)));
+    CU_TRY(cudaMalloc(&b->d_win_flags, MP * sizeof(int32_t)));
+    CU_TRY(cudaMalloc(&b->d_work, MP * sizeof(int32_t)));
+    CU_TRY(cudaMalloc(&b->d_cursor, sizeof(int32_t)));
+    CU_TRY(cudaMalloc(&b->d_cons, MP * (size_t)p.max_cons));
+    CU_TRY(cudaMalloc(&b->d_cov, MP * (size_t)p.max_cons * sizeof(uint16_t)));
+    CU_TRY(cudaMalloc(&b->d_len, MP * sizeof(int32_t)));
+    CU_TRY(cudaMalloc(&b->d_status, MP * sizeof(int32_t)));
+    b->device_bytes = (size_t)b->n_slots * b->slot_bytes + 2 * AC + (MS + 1) * 8 + MP * (16 + 3 * (size_t)p.max_cons);
+    CU_TRY(cudaHostAlloc(&b->h_bases, AC, cudaHostAllocDefault));
+    CU_TRY(cudaHostAlloc(&b->h_weights, AC, cudaHostAllocDefault));
+    CU_TRY(cudaHostAlloc(&b->h_seq_off, (MS + 1) * sizeof(int64_t), cudaHostAllocDefault));
+    CU_TRY(cudaHostAlloc(&b->h_win_seq_off, (MP + 1) * sizeof(int32_t), cudaHostAllocDefault));
+    CU_TRY(cudaHostAlloc(&b->h_win_flags, MP * sizeof(int32_t), cudaHostAllocDefault));
+    CU_TRY(cudaHostAlloc(&b->h_work, MP * sizeof(int32_t), cudaHostAllocDefault));
+    CU_TRY(cudaHostAlloc(&b->h_cons, MP * (size_t)p.max_cons, cudaHostAllocDefault));
+    CU_TRY(cudaHostAlloc(&b->h_cov, MP * (size_t)p.max_cons * sizeof(uint16_t), cudaHostAllocDefault));
+    CU_TRY(cudaHostAlloc(&b->h_len, MP * sizeof(int32_t), cudaHostAllocDefault));
+    CU_TRY(cudaHostAlloc(&b->h_status, MP * sizeof(int32_t), cudaHostAllocDefault));
+    return B200POA_SUCCESS;
+}
+
+extern "C" {
+
+int32_t b200poa_init(void) { return B200POA_SUCCESS; } /* cudapoa.cpp:29-35: nothing to set up */
+
+const char* b200poa_status_string(int32_t st) {
+    switch (st) {
+        case B200POA_SUCCESS: return "success";
+        case B200POA_EXCEEDED_MAXIMUM_POAS: return "exceeded_maximum_poas";
+        case B200POA_EXCEEDED_MAXIMUM_SEQUENCE_SIZE: return "exceeded_maximum_sequence_size";
+        case B200POA_EXCEEDED_MAXIMUM_SEQUENCES_PER_POA: return "exceeded_maximum_sequences_per_poa";
+        case B200POA_NODE_COUNT_EXCEEDED_MAXIMUM_GRAPH_SIZE: return "node_count_exceeded_maximum_graph_size";
+        case B200POA_EDGE_COUNT_EXCEEDED_MAXIMUM_GRAPH_SIZE: return "edge_count_exceeded_maximum_graph_size";
+        case B200POA_EXCEEDED_ADAPTIVE_BANDED_MATRIX_SIZE: return "exceeded_adaptive_banded_matrix_size";
+        case B200POA_SEQ_LEN_EXCEEDED_MAXIMUM_NODES_PER_WINDOW: return "seq_len_exceeded_maximum_nodes_per_window";
+        case B200POA_LOOP_COUNT_EXCEEDED_UPPER_BOUND: return "loop_count_exceeded_upper_bound";
+        case B200POA_OUTPUT_TYPE_UNAVAILABLE: return "output_type_unavailable";
+        case B200POA_GENERIC_ERROR: return "generic_error";
+        case B200POA_ALIGNED_COUNT_EXCEEDED: return "aligned_count_exceeded";
+        case B200POA_SCORE_RANGE_EXCEEDED: return "score_range_exceeded";
+        case B200POA_TRACEBACK_LOST: return "traceback_lost";
+        case B200POA_PARTIAL_SPAN_UNSUPPORTED: return "partial_span_unsupported";
+        case B200POA_INVALID_ARGUMENT: return "invalid_argument";
+        case B200POA_CUDA_ERROR: return "cuda_error";
+        default: return "unknown";
+    }
+}
+
+void b200poa_config_default(b200poa_config* cfg, int32_t max_seq_sz, int32_t max_seq_per_poa,
+                            int32_t band_width, int32_t band_mode) {
+    /* batch.cu:34-71 */
+    cfg->max_sequence_size = max_seq_sz;
+    cfg->max_consensus_size = 2 * max_seq_sz;
+    cfg->alignment_band_width = (band_width + 127) / 128 * 128;
+    cfg->max_sequences_per_poa = max_seq_per_poa;
+    cfg->band_mode = band_mode;
+    const int32_t mult = (band_mode == B200POA_FULL_BAND) ? 3 : 4;
+    cfg->max_nodes_per_graph = (mult * max_seq_sz + 3) / 4 * 4;
+}
+
+void b200poa_layer_order(int32_t n, const int32_t* begins, int32_t* rank_out) {
+    /* src/window.cpp:78-85 == src/cuda/cudabatch.cpp:96-104: libstdc++ std::sort is not stable, so
+     * the SAME call on the SAME initial vector is what reproduces racon's processing order. */
+    std::vector<uint32_t> rank;
+    rank.reserve(static_cast<size_t>(n));
+    for (int32_t i = 0; i < n; ++i) rank.emplace_back(static_cast<uint32_t>(i));
+    if (n > 1)
+        std::sort(rank.begin() + 1, rank.end(),
+                  [&](uint32_t lhs, uint32_t rhs) { return begins[lhs] < begins[rhs]; });
+    for (int32_t i = 0; i < n; ++i) rank_out[i] = static_cast<int32_t>(rank[static_cast<size_t>(i)]);
+}
+
+int32_t b200poa_batch_create(int32_t device_id, void* stream, size_t max_gpu_mem, int32_t output_mask,
+                             const b200poa_config* cfg, int16_t gap_score, int16_t mismatch_score,
+                             int16_t match_score, b200poa_batch** out) {
+    if (!out || !cfg) return B200POA_INVALID_ARGUMENT;
+    *out = nullptr;
+    /* batch.cu:64-66,93-98 argument checks */
+    if (cfg->max_sequence_size <= 0 || cfg->max_sequences_per_poa <= 0 || cfg->alignment_band_width < 0 ||
+        cfg->max_nodes_per_graph < cfg->max_sequence_size || cfg->max_consensus_size < cfg->max_sequence_size ||
+        cfg->max_nodes_per_graph > 32768 || cfg->max_sequence_size > 16380 ||
+        (cfg->band_mode != B200POA_FULL_BAND && cfg->band_mode != B200POA_STATIC_BAND))
+        return B200POA_INVALID_ARGUMENT;
+    if (max_gpu_mem == 0) return B200POA_INVALID_ARGUMENT; /* Test_CudapoaBatch.cu: zero memory throws */
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device_id < 0 || device_id >= ndev) return B200POA_CUDA_ERROR;
+
+    b200poa_batch* b = new (std::nothrow) b200poa_batch();
+    if (!b) return B200POA_GENERIC_ERROR;
+    b->id = g_batches++;
+    b->device = device_id;
+    b->stream = static_cast<cudaStream_t>(stream);
+    b->output_mask = output_mask;
+    b->cfg = *cfg;
+    DeviceGuard guard(device_id);
+
+    Params& p = b->p;
+    p.max_nodes = cfg->max_nodes_per_graph;
+    p.max_edges = std::min(6 * cfg->max_nodes_per_graph, 65000);
+    p.max_len = cfg->max_sequence_size;
+    const int32_t colsP = (p.max_len + 1 + 7) & ~7;
+    p.band_width = (cfg->band_mode == B200POA_STATIC_BAND) ? ((cfg->alignment_band_width + 7) & ~7) : 0;
+    p.stride = (p.band_width > 0 && p.band_width < colsP) ? p.band_width : colsP;
+    p.max_cons = cfg->max_consensus_size;
+    p.match = match_score;
+    p.mismatch = mismatch_score;
+    p.gap = gap_score;
+    p.serial_topsort = std::getenv("B200POA_SERIAL_TOPSORT") ? 1 : 0;
+    if (p.max_nodes > 65000) {
+        delete b;
+        return B200POA_INVALID_ARGUMENT;
+    }
+
+    Slot probe;
+    slot_bind(probe, nullptr, p, &b->slot_bytes);
+    b->prof_stride = colsP;
+    b->smem_bytes = PROF_ROWS * colsP * (int32_t)sizeof(int16_t);
+
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device_id));
+    CU_TRY(cudaFuncSetAttribute(poa_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes));
+    int blocks_per_sm = 0;
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, poa_window_kernel, 32, b->smem_bytes));
+    if (const char* env = std::getenv("B200POA_BLOCKS_PER_SM")) {
+        int v = std::atoi(env);
+        if (v > 0 && v < blocks_per_sm) blocks_per_sm = v;
+    }
+    if (blocks_per_sm < 1) {
+        delete b;
+        return B200POA_INVALID_ARGUMENT;
+    }
+    b->blocks_per_sm = blocks_per_sm;
+    int64_t want_slots = (int64_t)blocks_per_sm * prop.multiProcessorCount;
+
+    /* memory plan: at most half of the budget for slots, the rest for the arena + outputs */
+    int64_t slots_by_mem = (int64_t)((max_gpu_mem / 2) / b->slot_bytes);
+    if (slots_by_mem < 1) {
+        std::fprintf(stderr, "[b200poa] batch %d: %.2f GB is not enough for one window workspace (%.2f MB)\n",
+                     b->id, max_gpu_mem / 1073741824.0, b->slot_bytes / 1048576.0);
+        delete b;
+        return B200POA_INVALID_ARGUMENT;
+    }
+    b->n_slots = (int32_t)std::min(want_slots, slots_by_mem);
+    size_t rest = max_gpu_mem - (size_t)b->n_slots * b->slot_bytes;
+    /* staging is pinned host memory too: keep it bounded (B200POA_MAX_STAGING_MB, default 3 GiB) */
+    size_t cap = 3ull << 30;
+    if (const char* env = std::getenv("B200POA_MAX_STAGING_MB")) cap = (size_t)std::atoll(env) << 20;
+    if (rest > cap) rest = cap;
+    /* per window: outputs 3*max_cons + ~64 B tables; per base: 2 B; per sequence: 8 B */
+    const size_t out_per_win = (size_t)p.max_cons * 3 + 64;
+    int64_t max_poas = (int64_t)(rest / 4 / out_per_win);
+    if (max_poas < 1) max_poas = 1;
+    if (max_poas > (1 << 22)) max_poas = 1 << 22;
+    b->max_poas = (int32_t)max_poas;
+    size_t arena = (rest - (size_t)max_poas * out_per_win) / 2;
+    arena = arena / 10 * 9; /* 10% of the arena budget goes to the sequence offset table */
+    if (arena < (size_t)p.max_len * 4) arena = (size_t)p.max_len * 4;
+    b->arena_cap = (int64_t)arena;
+    b->max_seqs = std::max<int64_t>((int64_t)(arena / 10 / 8), 1024) + max_poas;
+
+    {
+        const int32_t ast = alloc_batch_memory(b);
+        if (ast != B200POA_SUCCESS) {
+            free_batch(b);
+            return ast;
+        }
+    }
+    b->h_seq_off[0] = 0;
+    b->h_win_seq_off[0] = 0;
+    b->cost.reserve((size_t)b->max_poas);
+    *out = b;
+    return B200POA_SUCCESS;
+}
+
+int32_t b200poa_batch_add_group(b200poa_batch* b, const b200poa_entry* entries, int32_t n, int32_t* per_seq_status) {
+    if (!b || !entries || n <= 0) return B200POA_INVALID_ARGUMENT;
+    auto get = [&](int32_t i, const char*& seq, const int8_t*& w, int32_t& len, int32_t& bg, int32_t& en) {
+        seq = entries[i].seq;
+        w = entries[i].weights;
+        len = entries[i].length;
+        bg = entries[i].begin;
+        en = entries[i].end;
+    };
+    return stage_window(b, n, get, per_seq_status, nullptr);
+}
+
+int32_t b200poa_batch_add_windows(b200poa_batch* b, int64_t n_windows, int64_t first,
+                                  const int64_t* win_seq_off, const int64_t* seq_off,
+                                  const uint8_t* bases, const int8_t* weights,
+                                  const uint8_t* has_weights, const int32_t* begins,
+                                  const int32_t* ends, int64_t* n_added, int32_t* seqs_added) {
+    if (!b || !n_added) return B200POA_INVALID_ARGUMENT;
+    *n_added = 0;
+    std::vector<int32_t> rank;
+    for (int64_t w = first; w < n_windows; ++w) {
+        const int64_t s0 = win_seq_off[w];
+        const int32_t n = (int32_t)(win_seq_off[w + 1] - s0);
+        rank.resize((size_t)n);
+        b200poa_layer_order(n, begins + s0, rank.data());
+        auto get = [&](int32_t i, const char*& seq, const int8_t*& wt, int32_t& len, int32_t& bg, int32_t& en) {
+            const int64_t s = s0 + rank[(size_t)i];
+            seq = reinterpret_cast<const char*>(bases + seq_off[s]);
+            wt = has_weights[s] ? weights + seq_off[s] : nullptr;
+            len = (int32_t)(seq_off[s + 1] - seq_off[s]);
+            bg = begins[s];
+            en = ends[s];
+        };
+        int32_t added = 0;
+        const int32_t st = stage_window(b, n, get, nullptr, &added);
+        if (st == B200POA_EXCEEDED_MAXIMUM_POAS) break;
+        if (st != B200POA_SUCCESS) return st;
+        if (seqs_added) seqs_added[*n_added] = added;
+        ++*n_added;
+    }
+    return B200POA_SUCCESS;
+}
+
+int32_t b200poa_batch_total_poas(const b200poa_batch* b) { return b ? b->poa_count : 0; }
+int32_t b200poa_batch_id(const b200poa_batch* b) { return b ? b->id : -1; }
+
+int32_t b200poa_batch_upload(b200poa_batch* b) {
+    if (!b) return B200POA_INVALID_ARGUMENT;
+    if (b->poa_count == 0) return B200POA_SUCCESS;
+    DeviceGuard g(b->device);
+    /* longest-first work list */
+    std::iota(b->h_work, b->h_work + b->poa_count, 0);
+    std::stable_sort(b->h_work, b->h_work + b->poa_count,
+                     [&](int32_t x, int32_t y) { return b->cost[(size_t)x] > b->cost[(size_t)y]; });
+    const size_t W = (size_t)b->poa_count;
+    CU_TRY(cudaMemcpyAsync(b->d_bases, b->h_bases, (size_t)b->base_count, cudaMemcpyHostToDevice, b->stream));
+    CU_TRY(cudaMemcpyAsync(b->d_weights, b->h_weights, (size_t)b->base_count, cudaMemcpyHostToDevice, b->stream));
+    CU_TRY(cudaMemcpyAsync(b->d_seq_off, b->h_seq_off, ((size_t)b->seq_count + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, b->stream));
+    CU_TRY(cudaMemcpyAsync(b->d_win_seq_off, b->h_win_seq_off, (W + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream));
+    CU_TRY(cudaMemcpyAsync(b->d_win_flags, b->h_win_flags, W * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream));
+    CU_TRY(cudaMemcpyAsync(b->d_work, b->h_work, W * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream));
+    b->uploaded = true;
+    return B200POA_SUCCESS;
+}
+
+int32_t b200poa_batch_launch(b200poa_batch* b) {
+    if (!b) return B200POA_INVALID_ARGUMENT;
+    if (b->poa_count == 0) return B200POA_SUCCESS;
+    if (!b->uploaded) return B200POA_INVALID_ARGUMENT;
+    DeviceGuard g(b->device);
+    CU_TRY(cudaMemsetAsync(b->d_cursor, 0, sizeof(int32_t), b->stream));
+    KernelArgs a;
+    a.p = b->p;
+    a.slab = b->d_slab;
+    a.slot_bytes = b->slot_bytes;
+    a.n_windows = b->poa_count;
+    a.work = b->d_work;
+    a.cursor = b->d_cursor;
+    a.bases = b->d_bases;
+    a.weights = b->d_weights;
+    a.seq_off = b->d_seq_off;
+    a.win_seq_off = b->d_win_seq_off;
+    a.win_flags = b->d_win_flags;
+    a.out_cons = b->d_cons;
+    a.out_cov = b->d_cov;
+    a.out_len = b->d_len;
+    a.out_status = b->d_status;
+    a.prof_stride = b->prof_stride;
+    const int grid = std::min(b->n_slots, b->poa_count);
+    poa_window_kernel<<<grid, 32, (size_t)b->smem_bytes, b->stream>>>(a);
+    CU_TRY(cudaGetLastError());
+    b->launches += 1;
+    return B200POA_SUCCESS;
+}
+
+int32_t b200poa_batch_download(b200poa_batch* b) {
+    if (!b) return B200POA_INVALID_ARGUMENT;
+    if (b->poa_count == 0) return B200POA_SUCCESS;
+    DeviceGuard g(b->device);
+    const size_t W = (size_t)b->poa_count;
+    CU_TRY(cudaMemcpyAsync(b->h_cons, b->d_cons, W * (size_t)b->p.max_cons, cudaMemcpyDeviceToHost, b->stream));
+    CU_TRY(cudaMemcpyAsync(b->h_cov, b->d_cov, W * (size_t)b->p.max_cons * sizeof(uint16_t), cudaMemcpyDeviceToHost, b->stream));
+    CU_TRY(cudaMemcpyAsync(b->h_len, b->d_len, W * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
+    CU_TRY(cudaMemcpyAsync(b->h_status, b->d_status, W * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
+    return B200POA_SUCCESS;
+}
+
+int32_t b200poa_batch_generate(b200poa_batch* b) {
+    int32_t st = b200poa_batch_upload(b);
+    if (st != B200POA_SUCCESS) return st;
+    st = b200poa_batch_launch(b);
+    if (st != B200POA_SUCCESS) return st;
+    return b200poa_batch_download(b);
+}
+
+int32_t b200poa_batch_get_consensus(b200poa_batch* b, const uint8_t** cons, const uint16_t** cov,
+                                    const int32_t** lens, const int32_t** status, int32_t* stride) {
+    if (!b) return B200POA_INVALID_ARGUMENT;
+    if (!(b->output_mask & B200POA_OUTPUT_CONSENSUS)) return B200POA_OUTPUT_TYPE_UNAVAILABLE; /* cudapoa_batch.cuh:205-209 */
+    DeviceGuard g(b->device);
+    CU_TRY(cudaStreamSynchronize(b->stream));
+    if (cons) *cons = b->h_cons;
+    if (cov) *cov = b->h_cov;
+    if (lens) *lens = b->h_len;
+    if (status) *status = b->h_status;
+    if (stride) *stride = b->p.max_cons;
+    return B200POA_SUCCESS;
+}
+
+int32_t b200poa_batch_reset(b200poa_batch* b) {
+    if (!b) return B200POA_INVALID_ARGUMENT;
+    b->poa_count = 0;
+    b->seq_count = 0;
+    b->base_count = 0;
+    b->cost.clear();
+    b->uploaded = false;
+    return B200POA_SUCCESS;
+}
+
+void b200poa_batch_destroy(b200poa_batch* b) { free_batch(b); }
+
+int32_t b200poa_batch_get_info(const b200poa_batch* b, b200poa_batch_info* info) {
+    if (!b || !info) return B200POA_INVALID_ARGUMENT;
+    info->n_slots = b->n_slots;
+    info->max_poas = b->max_poas;
+    info->arena_capacity = b->arena_cap;
+    info->slot_bytes = (int64_t)b->slot_bytes;
+    info->device_bytes = (int64_t)b->device_bytes;
+    info->staged_bases = b->base_count;
+    info->kernel_launches = b->launches;
+    info->smem_bytes = b->smem_bytes;
+    info->blocks_per_sm = b->blocks_per_sm;
+    return B200POA_SUCCESS;
+}
+
+} // extern "C"

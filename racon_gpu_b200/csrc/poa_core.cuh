@@ -1,0 +1,950 @@
+/*
+ * poa_core.cuh -- one-window-per-warp partial order alignment consensus (graph phases).
+ *
+ * Replaces, for racon's consensus path, what the reference runs in
+ *   vendor/GenomeWorks/cudapoa/src/cudapoa_kernels.cuh:74-434   (generatePOAKernel)
+ *   vendor/GenomeWorks/cudapoa/src/cudapoa_add_alignment.cuh:66-287
+ *   vendor/GenomeWorks/cudapoa/src/cudapoa_topsort.cuh:101-195
+ *   vendor/GenomeWorks/cudapoa/src/cudapoa_generate_consensus.cuh:35-354
+ * but with the SEMANTICS of racon's CPU path (spoa), which is the parity target:
+ *   vendor/spoa/src/sisd_alignment_engine.cpp:260-435, vendor/spoa/src/graph.cpp:94-589.
+ *
+ * Design (not a port): everything a window needs lives in a compact per-warp workspace
+ * ("slot") -- nodes are SoA arrays of u8/u16, in-edges are a pooled linked list kept in insertion
+ * order (spoa's in_edges_ order decides every tie-break), aligned-node cliques are <= KA inline ids.
+ * cudapoa's fixed 50-edge / 50-aligned strides (cudapoa_structs.cuh:24-27) are gone, so a slot is
+ * ~100 KB + the score band instead of 2-2.6 MB + 2-6 MB, and slots are per RESIDENT WARP, not per
+ * window in the batch.
+ *
+ * The serial lane-0 phases of the reference are re-formulated as warp-parallel phases:
+ *   - add_alignment: every read position is resolved independently (a path visits each aligned
+ *     clique once), new node / edge ids come from warp prefix sums, each node receives at most one
+ *     new in-edge per read so list order is preserved;
+ *   - topological sort: spoa's DFS order is decomposed by ROOT (root[v] = smallest id whose
+ *     ancestor-closure contains v).  root[] is fixed when a node is created, DFS_i for different
+ *     roots are independent, so 32 roots are sorted concurrently and concatenated by a prefix sum.
+ *     The plain serial DFS is kept (topsort_serial) as the in-kernel cross-check for tests.
+ *   - traceback: the predecessors of a cell are tested by different lanes, first-match by ballot.
+ *
+ * Score cells are int16 in the "skewed" domain S[i][j] = H[i][j] - j*gap so that the horizontal
+ * recurrence H[i][j-1]+gap becomes a pure prefix max:
+ *   S[i][j] = max( max_p S[p][j-1] + (s(i,j) - gap), max_p S[p][j] + gap, S[i][j-1] ).
+ * The DP fill itself is in poa_fill.cuh (CUDA) / emu_fill.hpp (scalar twin for the CPU tests).
+ */
+#pragma once
+#include "poa_simt.cuh"
+
+namespace b200poa {
+
+POA_FN void poa_atomic_add(uint32_t* p, uint32_t v) {
+#if POA_DEVICE
+    atomicAdd(p, v);
+#else
+    *p += v;
+#endif
+}
+
+constexpr int KA = 7;                  /* max aligned nodes per node (clique size - 1) */
+constexpr uint16_t NONE16 = 0xFFFFu;
+constexpr int NEG = -30000;            /* "minus infinity" for int16 cells; see DESIGN.md */
+constexpr int LANE_CELLS = 8;          /* int16 cells per lane per chunk (one 128-bit vector) */
+constexpr int CHUNK = 32 * LANE_CELLS; /* 256 columns per warp pass */
+
+/* status codes mirror claraparabricks::genomeworks::cudapoa::StatusType (cudapoa.hpp:32-45) */
+enum Status : int32_t {
+    ST_SUCCESS = 0,
+    ST_EXCEEDED_MAX_POAS = 1,
+    ST_EXCEEDED_MAX_SEQ_SIZE = 2,
+    ST_EXCEEDED_MAX_SEQS_PER_POA = 3,
+    ST_NODE_COUNT_EXCEEDED = 4,
+    ST_EDGE_COUNT_EXCEEDED = 5,
+    ST_EXCEEDED_ADAPTIVE_BAND = 6,
+    ST_SEQ_LEN_EXCEEDED_MAX_NODES = 7,
+    ST_LOOP_COUNT_EXCEEDED = 8,
+    ST_OUTPUT_UNAVAILABLE = 9,
+    ST_GENERIC_ERROR = 10,
+    /* extensions (never returned by cudapoa) */
+    ST_ALIGNED_COUNT_EXCEEDED = 11,  /* clique larger than KA+1 */
+    ST_SCORE_RANGE_EXCEEDED = 12,    /* int16 cells cannot hold this alignment */
+    ST_TRACEBACK_LOST = 13           /* band did not contain a consistent path */
+};
+
+struct Params {
+    int32_t max_nodes;   /* MN : node capacity of a slot            */
+    int32_t max_edges;   /* ME : edge pool capacity                 */
+    int32_t max_len;     /* longest sequence accepted               */
+    int32_t stride;      /* int16 cells per score row (multiple of 8) */
+    int32_t band_width;  /* 0 = full band, else W (multiple of 8)   */
+    int32_t max_cons;    /* row stride of the consensus / coverage outputs */
+    int32_t match, mismatch, gap;
+    int32_t serial_topsort; /* tests: use the serial DFS instead of the per-root sort */
+};
+
+/* Per resident warp workspace.  All pointers are into one device slab (see slot_bytes()). */
+struct Slot {
+    /* graph */
+    uint8_t* code;      /* [MN] node letter                                  */
+    uint16_t* nin;      /* [MN] in-degree                                    */
+    uint16_t* nout;     /* [MN] out-degree (only == 0 is ever asked)         */
+    uint16_t* in_head;  /* [MN] first in-edge (pool index) or NONE16         */
+    uint16_t* in_tail;  /* [MN] last in-edge                                 */
+    uint16_t* cov;      /* [MN] number of sequences through the node         */
+    uint8_t* aln_cnt;   /* [MN] number of aligned nodes                      */
+    uint16_t* aln;      /* [MN*KA] aligned node ids in insertion order       */
+    uint16_t* root;     /* [MN] topological-sort root of the node            */
+    uint16_t* lpos;     /* [MN] scratch: position inside the root's DFS      */
+    uint16_t* rank_of;  /* [MN] node -> rank                                 */
+    uint16_t* node_at;  /* [MN] rank -> node                                 */
+    uint16_t* e_src;    /* [ME] */
+    uint16_t* e_dst;    /* [ME] */
+    uint16_t* e_next;   /* [ME] next in-edge of e_dst, insertion order       */
+    int32_t* e_w;       /* [ME] total weight                                 */
+    /* per-read "row program": the graph linearised in rank order (row = rank + 1) */
+    uint32_t* row_info; /* [MN+1] code | sink<<8 | npred<<16                 */
+    uint32_t* row_poff; /* [MN+2] offset of the row's predecessor list       */
+    uint32_t* row_pred; /* [ME+MN] predecessor ROW index (0 = virtual row) | its band start << 16, in in-edge order */
+    uint16_t* row_bs;   /* [MN+1] first column of the row's band             */
+    /* scores */
+    int16_t* S;         /* [(MN+1)*stride]                                   */
+    /* traceback output, written back to front */
+    int16_t* tb_node;   /* [MN+ML+2] */
+    int16_t* tb_pos;    /* [MN+ML+2] */
+    int32_t* asg;       /* [ML+1] node assigned to each read position        */
+    /* topological sort scratch */
+    uint32_t* cnt;      /* [MN+1] nodes per root                             */
+    uint32_t* roff;     /* [MN+1] output offset per root / stack offset      */
+    uint32_t* need;     /* [MN+1] stack need per root                        */
+    uint8_t* marks;     /* [MN] */
+    uint8_t* check;     /* [MN] */
+    uint16_t* stack;    /* [ME+2*MN*? ] see slot layout                      */
+    /* consensus scratch */
+    int32_t* c_score;   /* [MN] */
+    int32_t* c_pred;    /* [MN] */
+};
+
+struct SlotLayout {
+    size_t off[40];
+    size_t total;
+};
+
+/* One definition of the slab carve-up, used by host allocation, the kernel and the emulation. */
+POA_FN size_t poa_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+#if POA_DEVICE
+__host__ __device__ __forceinline__
+#else
+static inline
+#endif
+void slot_bind(Slot& s, uint8_t* base, const Params& p, size_t* total_out) {
+    const size_t MN = (size_t)p.max_nodes, ME = (size_t)p.max_edges, ML = (size_t)p.max_len;
+    size_t o = 0;
+#define POA_CARVE(field, type, count)                                  \
+    do {                                                               \
+        o = (o + 15) / 16 * 16;                                        \
+        s.field = base ? reinterpret_cast<type*>(base + o) : nullptr;  \
+        o += sizeof(type) * (size_t)(count);                           \
+    } while (0)
+    POA_CARVE(code, uint8_t, MN);
+    POA_CARVE(nin, uint16_t, MN);
+    POA_CARVE(nout, uint16_t, MN);
+    POA_CARVE(in_head, uint16_t, MN);
+    POA_CARVE(in_tail, uint16_t, MN);
+    POA_CARVE(cov, uint16_t, MN);
+    POA_CARVE(aln_cnt, uint8_t, MN);
+    POA_CARVE(aln, uint16_t, MN * KA);
+    POA_CARVE(root, uint16_t, MN);
+    POA_CARVE(lpos, uint16_t, MN);
+    POA_CARVE(rank_of, uint16_t, MN);
+    POA_CARVE(node_at, uint16_t, MN);
+    POA_CARVE(e_src, uint16_t, ME);
+    POA_CARVE(e_dst, uint16_t, ME);
+    POA_CARVE(e_next, uint16_t, ME);
+    POA_CARVE(e_w, int32_t, ME);
+    POA_CARVE(row_info, uint32_t, MN + 1);
+    POA_CARVE(row_poff, uint32_t, MN + 2);
+    POA_CARVE(row_pred, uint32_t, ME + MN);
+    POA_CARVE(row_bs, uint16_t, MN + 1);
+    POA_CARVE(tb_node, int16_t, MN + ML + 2);
+    POA_CARVE(tb_pos, int16_t, MN + ML + 2);
+    POA_CARVE(asg, int32_t, ML + 1);
+    POA_CARVE(cnt, uint32_t, MN + 1);
+    POA_CARVE(roff, uint32_t, MN + 1);
+    POA_CARVE(need, uint32_t, MN + 1);
+    POA_CARVE(marks, uint8_t, MN);
+    POA_CARVE(check, uint8_t, MN);
+    POA_CARVE(stack, uint16_t, ME + (KA + 2) * MN);
+    POA_CARVE(c_score, int32_t, MN);
+    POA_CARVE(c_pred, int32_t, MN);
+    o = (o + 255) / 256 * 256;
+    s.S = base ? reinterpret_cast<int16_t*>(base + o) : nullptr;
+    o += sizeof(int16_t) * (MN + 1) * (size_t)p.stride;
+    o = (o + 255) / 256 * 256;
+#undef POA_CARVE
+    if (total_out) *total_out = o;
+}
+
+/* One window as the kernel sees it: sequences already in processing order. */
+struct WindowView {
+    int32_t n_seqs;
+    const uint8_t* bases;    /* batch arena */
+    const int8_t* weights;   /* batch arena (always materialised; 1 when racon has no quality) */
+    const int64_t* seq_off;  /* [n_seqs+1] offsets of this window's sequences in the arenas */
+};
+
+/* Mutable per-window state (warp-uniform scalars). */
+struct WinState {
+    int32_t n_nodes;
+    int32_t n_edges;
+    int32_t status;
+};
+
+/* ------------------------------------------------------------------------------------------
+ * Phase 0: backbone chain  (graph.cpp:274-292 add_sequence + :177-185; window.cpp:73-76)
+ * ---------------------------------------------------------------------------------------- */
+POA_FN void init_backbone(const Slot& s, const Params& p, WinState& st, const uint8_t* seq,
+                          const int8_t* w, int32_t len) {
+    if (len > p.max_nodes || len - 1 > p.max_edges) {
+        st.status = ST_SEQ_LEN_EXCEEDED_MAX_NODES;
+        return;
+    }
+    for (int32_t base = 0; base < len; base += 32) {
+        POA_LANES(l) {
+            const int32_t k = base + l;
+            if (k >= len) continue;
+            s.code[k] = seq[k];
+            s.nin[k] = (k > 0) ? 1 : 0;
+            s.nout[k] = (k + 1 < len) ? 1 : 0;
+            s.in_head[k] = (k > 0) ? (uint16_t)(k - 1) : NONE16;
+            s.in_tail[k] = s.in_head[k];
+            s.cov[k] = (len >= 2) ? 1 : 0; /* Node::coverage counts edge labels (graph.cpp:44-58) */
+            s.aln_cnt[k] = 0;
+            s.root[k] = (uint16_t)k;
+            s.rank_of[k] = (uint16_t)k;
+            s.node_at[k] = (uint16_t)k;
+            if (k > 0) { /* edge k-1 : (k-1) -> k */
+                s.e_src[k - 1] = (uint16_t)(k - 1);
+                s.e_dst[k - 1] = (uint16_t)k;
+                s.e_next[k - 1] = NONE16;
+                s.e_w[k - 1] = (int32_t)w[k - 1] + (int32_t)w[k];
+            }
+        }
+    }
+    POA_SYNC();
+    st.n_nodes = len;
+    st.n_edges = len - 1;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Phase 1: row program.  Linearise the graph in rank order for the DP fill and traceback.
+ *   row r+1  <->  node_at[r];  predecessor rows in in-edge order; a node without in-edges gets the
+ *   single virtual predecessor row 0 (sisd_alignment_engine.cpp:289-290).
+ * Band: static, centred on the (0,0)-(N,len) diagonal like cudapoa_nw_banded.cuh:35-55, but
+ * snapped to 8-cell lanes so a row shift is a whole-lane shift.
+ * ---------------------------------------------------------------------------------------- */
+struct ReadGeom {
+    int32_t len;    /* read length                                    */
+    int32_t colsP;  /* (len+1) rounded up to a multiple of 8          */
+    int32_t bw;     /* cells per row actually computed (multiple of 8) */
+    int32_t banded; /* 1 if bw < colsP                                 */
+};
+
+POA_FN ReadGeom read_geometry(const Params& p, int32_t len) {
+    ReadGeom g;
+    g.len = len;
+    g.colsP = (len + 1 + 7) & ~7;
+    g.banded = (p.band_width > 0 && g.colsP > p.band_width) ? 1 : 0;
+    g.bw = g.banded ? p.band_width : g.colsP;
+    return g;
+}
+
+POA_FN int32_t band_start(const ReadGeom& g, int32_t row, int32_t n_rows) {
+    if (!g.banded) return 0;
+    int32_t center = (int32_t)(((int64_t)row * g.len) / n_rows);
+    int32_t bs = center - g.bw / 2;
+    if (bs > g.colsP - g.bw) bs = g.colsP - g.bw;
+    if (bs < 0) bs = 0;
+    return bs & ~7;
+}
+
+POA_FN void build_program(const Slot& s, const Params& p, WinState& st, const ReadGeom& g) {
+    const int32_t N = st.n_nodes;
+    int32_t run = 0; /* running predecessor offset (uniform) */
+    POA_LANE0 {
+        s.row_info[0] = 0;
+        s.row_bs[0] = 0;
+    }
+    for (int32_t base = 0; base < N; base += 32) {
+        PerLane<int> c;
+        POA_LANES(l) {
+            const int32_t r = base + l;
+            c[l] = 0;
+            if (r < N) {
+                const int32_t v = s.node_at[r];
+                const int32_t d = s.nin[v];
+                c[l] = d ? d : 1;
+            }
+        }
+        PerLane<int> off = c;
+        const int32_t tot = warp_exscan(off);
+        POA_LANES(l) {
+            const int32_t r = base + l;
+            if (r >= N) continue;
+            const int32_t v = s.node_at[r];
+            const int32_t o = run + off[l];
+            s.row_poff[r + 1] = (uint32_t)o;
+            const int32_t d = s.nin[v];
+            if (d == 0) {
+                s.row_pred[o] = 0;
+            } else {
+                int32_t k = 0;
+                for (uint16_t e = s.in_head[v]; e != NONE16; e = s.e_next[e], ++k) {
+                    const int32_t pr = s.rank_of[s.e_src[e]] + 1;
+                    s.row_pred[o + k] = (uint32_t)pr | ((uint32_t)band_start(g, pr, N) << 16);
+                }
+            }
+            s.row_info[r + 1] = (uint32_t)s.code[v] | ((s.nout[v] == 0) ? 0x100u : 0u) |
+                                ((uint32_t)c[l] << 16);
+            s.row_bs[r + 1] = (uint16_t)band_start(g, r + 1, N);
+        }
+        run += tot;
+    }
+    POA_LANE0 { s.row_poff[N + 1] = (uint32_t)run; }
+    POA_SYNC();
+}
+
+/* Score accessor used by the traceback (and by the scalar fill): cells outside the row's band
+ * read as NEG (cudapoa_nw_banded.cuh:103-116 does the same with min_score_value). */
+POA_FN int32_t score_at(const Slot& s, const Params& p, const ReadGeom& g, int32_t row, int32_t col) {
+    if (col < 0) return NEG;
+    const int32_t bs = s.row_bs[row];
+    const int32_t o = col - bs;
+    if (o < 0 || o >= g.bw) return NEG;
+    return s.S[(size_t)row * p.stride + o];
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Phase 3: traceback  (sisd_alignment_engine.cpp:340-431)
+ *   priority: diagonal over in-edges in order, vertical over in-edges in order, horizontal.
+ *   Lanes test different predecessors; the first match is the lowest set ballot bit.
+ *   Output: tb_node/tb_pos filled back to front; returns the index of the first (leftmost) entry.
+ * ---------------------------------------------------------------------------------------- */
+POA_FN int32_t traceback(const Slot& s, const Params& p, WinState& st, const ReadGeom& g,
+                         const uint8_t* read, int32_t end_row) {
+    const int32_t cap = p.max_nodes + p.max_len + 2;
+    int32_t w = cap; /* write cursor (uniform) */
+    int32_t i = end_row, j = g.len;
+    const int32_t mg = p.match - p.gap, xg = p.mismatch - p.gap;
+    int32_t guard = p.max_nodes + p.max_len + 4;
+    while (!(i == 0 && j == 0)) {
+        if (--guard < 0 || w <= 0) {
+            st.status = ST_TRACEBACK_LOST;
+            return cap;
+        }
+        int32_t ni = i, nj = j;
+        if (i == 0) {
+            nj = j - 1; /* first row: S[0][*] == 0, only horizontal moves */
+        } else {
+            const int32_t cur = score_at(s, p, g, i, j);
+            const uint32_t info = s.row_info[i];
+            const int32_t np = (int32_t)(info >> 16);
+            const int32_t po = (int32_t)s.row_poff[i];
+            const int32_t prof = (j > 0 && (uint8_t)(info & 0xFF) == read[j - 1]) ? mg : xg;
+            int32_t found = 0;
+            for (int32_t b = 0; b < np && !found; b += 32) {
+                PerLane<int> dm, vm, pr;
+                POA_LANES(l) {
+                    dm[l] = 0;
+                    vm[l] = 0;
+                    pr[l] = 0;
+                    if (b + l < np) {
+                        const int32_t pi = (int32_t)(s.row_pred[po + b + l] & 0xFFFFu);
+                        pr[l] = pi;
+                        dm[l] = (j > 0) && (score_at(s, p, g, pi, j - 1) + prof == cur);
+                        vm[l] = (score_at(s, p, g, pi, j) + p.gap == cur);
+                    }
+                }
+                /* diagonal matches of ALL predecessors come before any vertical match, so a
+                 * vertical hit in this group of 32 only counts if no later group has a diagonal
+                 * hit; groups > 1 only exist for in-degree > 32, handled by the two-pass below. */
+                const unsigned dmask = warp_ballot(dm);
+                if (dmask) {
+                    ni = warp_get(pr, poa_ffs(dmask));
+                    nj = j - 1;
+                    found = 1;
+                } else if (np <= 32) {
+                    const unsigned vmask = warp_ballot(vm);
+                    if (vmask) {
+                        ni = warp_get(pr, poa_ffs(vmask));
+                        nj = j;
+                        found = 1;
+                    }
+                }
+            }
+            if (!found && np > 32) { /* second pass: vertical candidates of a very wide node */
+                for (int32_t b = 0; b < np && !found; b += 32) {
+                    PerLane<int> vm, pr;
+                    POA_LANES(l) {
+                        vm[l] = 0;
+                        pr[l] = 0;
+                        if (b + l < np) {
+                            const int32_t pi = (int32_t)(s.row_pred[po + b + l] & 0xFFFFu);
+                            pr[l] = pi;
+                            vm[l] = (score_at(s, p, g, pi, j) + p.gap == cur);
+                        }
+                    }
+                    const unsigned vmask = warp_ballot(vm);
+                    if (vmask) {
+                        ni = warp_get(pr, poa_ffs(vmask));
+                        nj = j;
+                        found = 1;
+                    }
+                }
+            }
+            if (!found) {
+                if (j > 0 && score_at(s, p, g, i, j - 1) == cur) {
+                    nj = j - 1;
+                } else {
+                    st.status = ST_TRACEBACK_LOST;
+                    return cap;
+                }
+            }
+        }
+        --w;
+        POA_LANE0 {
+            s.tb_node[w] = (int16_t)((i == ni) ? -1 : (int32_t)s.node_at[i - 1]);
+            s.tb_pos[w] = (int16_t)((j == nj) ? -1 : (j - 1));
+        }
+        i = ni;
+        j = nj;
+    }
+    POA_SYNC();
+    return w;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Phase 4: add the alignment to the graph  (graph.cpp:155-272, 94-116)
+ * ---------------------------------------------------------------------------------------- */
+POA_FN void add_alignment(const Slot& s, const Params& p, WinState& st, const uint8_t* read,
+                          const int8_t* wt, int32_t len, int32_t tb_begin) {
+    const int32_t cap = p.max_nodes + p.max_len + 2;
+    const int32_t N0 = st.n_nodes;
+
+    /* (a) resolve every read position: existing node, or a new node (unaligned / aligned to x).
+     *     asg[pos] >= 0 : existing node;  -1 : new, unaligned;  -2-x : new, aligned to node x. */
+    for (int32_t base = tb_begin; base < cap; base += 32) {
+        POA_LANES(l) {
+            const int32_t k = base + l;
+            if (k >= cap) continue;
+            const int32_t pos = s.tb_pos[k];
+            if (pos < 0) continue;
+            const int32_t x = s.tb_node[k];
+            const uint8_t letter = read[pos];
+            int32_t a;
+            if (x < 0) {
+                a = -1;
+            } else if (s.code[x] == letter) {
+                a = x;
+            } else {
+                a = -2 - x;
+                const int32_t na = s.aln_cnt[x];
+                for (int32_t q = 0; q < na; ++q) {
+                    const int32_t y = s.aln[x * KA + q];
+                    if (s.code[y] == letter) {
+                        a = y;
+                        break;
+                    }
+                }
+            }
+            s.asg[pos] = a;
+        }
+    }
+    POA_SYNC();
+
+    /* (b) create the new nodes; ids follow read order exactly like the serial add_node calls. */
+    int32_t n_new = 0;
+    int32_t fail = 0;
+    for (int32_t base = 0; base < len; base += 32) {
+        PerLane<int> isnew;
+        POA_LANES(l) {
+            const int32_t pos = base + l;
+            isnew[l] = (pos < len && s.asg[pos] < 0) ? 1 : 0;
+        }
+        PerLane<int> off = isnew;
+        const int32_t tot = warp_exscan(off);
+        if (N0 + n_new + tot > p.max_nodes) {
+            fail = ST_NODE_COUNT_EXCEEDED;
+            break;
+        }
+        PerLane<int> bad;
+        POA_LANES(l) {
+            bad[l] = 0;
+            const int32_t pos = base + l;
+            if (pos >= len || !isnew[l]) continue;
+            const int32_t v = N0 + n_new + off[l];
+            const int32_t a = s.asg[pos];
+            s.code[v] = read[pos];
+            s.nin[v] = 0;
+            s.nout[v] = 0;
+            s.in_head[v] = NONE16;
+            s.in_tail[v] = NONE16;
+            s.cov[v] = 0;
+            s.aln_cnt[v] = 0;
+            s.root[v] = NONE16; /* resolved in (c) */
+            if (a <= -2) {      /* graph.cpp:226-237: join x's clique */
+                const int32_t x = -2 - a;
+                const int32_t na = s.aln_cnt[x];
+                if (na + 1 > KA) {
+                    bad[l] = 1;
+                } else {
+                    for (int32_t q = 0; q < na; ++q) {
+                        const int32_t y = s.aln[x * KA + q];
+                        s.aln[v * KA + q] = (uint16_t)y;
+                        s.aln[y * KA + s.aln_cnt[y]] = (uint16_t)v;
+                        s.aln_cnt[y] = (uint8_t)(s.aln_cnt[y] + 1);
+                    }
+                    s.aln[v * KA + na] = (uint16_t)x;
+                    s.aln_cnt[v] = (uint8_t)(na + 1);
+                    s.aln[x * KA + na] = (uint16_t)v;
+                    s.aln_cnt[x] = (uint8_t)(na + 1);
+                    s.root[v] = s.root[x];
+                }
+            }
+            s.asg[pos] = v | 0x40000000; /* mark "new" until (c) is done */
+        }
+        if (warp_ballot(bad)) {
+            fail = ST_ALIGNED_COUNT_EXCEEDED;
+            break;
+        }
+        n_new += tot;
+    }
+    POA_SYNC();
+    if (fail) {
+        st.status = fail;
+        return;
+    }
+
+    /* (c) roots of new unaligned nodes: root[v] = min(v, root[next node on the read path]); a run
+     *     of consecutive new unaligned nodes all see the node that ends the run. */
+    for (int32_t base = 0; base < len; base += 32) {
+        POA_LANES(l) {
+            const int32_t pos = base + l;
+            if (pos >= len) continue;
+            const int32_t a = s.asg[pos];
+            if (!(a & 0x40000000)) continue;
+            const int32_t v = a & 0x3FFFFFFF;
+            if (s.root[v] != NONE16) continue; /* aligned new node: root copied from its clique */
+            int32_t q = pos + 1;
+            int32_t r = v;
+            while (q < len) {
+                const int32_t b = s.asg[q];
+                const int32_t u = b & 0x3FFFFFFF;
+                if ((b & 0x40000000) && s.root[u] == NONE16) { /* still inside the run */
+                    ++q;
+                    continue;
+                }
+                /* u is an old node, or a new aligned node whose root is already final */
+                if ((int32_t)s.root[u] < r) r = s.root[u];
+                break;
+            }
+            s.lpos[v] = (uint16_t)r; /* stage: root[] of run members is still NONE16 for the others */
+        }
+    }
+    POA_SYNC();
+    for (int32_t base = 0; base < len; base += 32) {
+        POA_LANES(l) {
+            const int32_t pos = base + l;
+            if (pos >= len) continue;
+            const int32_t a = s.asg[pos];
+            if (!(a & 0x40000000)) continue;
+            const int32_t v = a & 0x3FFFFFFF;
+            if (s.root[v] == NONE16) s.root[v] = s.lpos[v];
+            s.asg[pos] = v;
+        }
+    }
+    POA_SYNC();
+    st.n_nodes = N0 + n_new;
+
+    /* (d) edges prev -> cur for consecutive read positions (graph.cpp:248-259, 94-116), and
+     * (e) coverage: every node on the read's path carries this sequence's label. */
+    int32_t n_edges = st.n_edges;
+    for (int32_t base = 0; base < len; base += 32) {
+        PerLane<int> need;
+        PerLane<int> hit;
+        POA_LANES(l) {
+            const int32_t pos = base + l;
+            need[l] = 0;
+            hit[l] = -1;
+            if (pos >= len) continue;
+            const int32_t cur = s.asg[pos];
+            if (len >= 2) s.cov[cur] = (uint16_t)(s.cov[cur] + 1);
+            if (pos == 0) continue;
+            const int32_t prev = s.asg[pos - 1];
+            int32_t found = -1;
+            for (uint16_t e = s.in_head[cur]; e != NONE16; e = s.e_next[e]) {
+                if (s.e_src[e] == prev) {
+                    found = e;
+                    break;
+                }
+            }
+            hit[l] = found;
+            need[l] = (found < 0) ? 1 : 0;
+        }
+        PerLane<int> off = need;
+        const int32_t tot = warp_exscan(off);
+        if (n_edges + tot > p.max_edges) {
+            fail = ST_EDGE_COUNT_EXCEEDED;
+            break;
+        }
+        POA_LANES(l) {
+            const int32_t pos = base + l;
+            if (pos >= len || pos == 0) continue;
+            const int32_t cur = s.asg[pos], prev = s.asg[pos - 1];
+            const int32_t w = (int32_t)wt[pos - 1] + (int32_t)wt[pos];
+            if (hit[l] >= 0) {
+                s.e_w[hit[l]] += w;
+            } else {
+                const int32_t e = n_edges + off[l];
+                s.e_src[e] = (uint16_t)prev;
+                s.e_dst[e] = (uint16_t)cur;
+                s.e_next[e] = NONE16;
+                s.e_w[e] = w;
+                if (s.in_tail[cur] == NONE16) s.in_head[cur] = (uint16_t)e;
+                else s.e_next[s.in_tail[cur]] = (uint16_t)e;
+                s.in_tail[cur] = (uint16_t)e;
+                s.nin[cur] = (uint16_t)(s.nin[cur] + 1);
+                s.nout[prev] = (uint16_t)(s.nout[prev] + 1);
+            }
+        }
+        n_edges += tot;
+    }
+    POA_SYNC();
+    if (fail) {
+        st.status = fail;
+        return;
+    }
+    st.n_edges = n_edges;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Phase 5a: serial topological sort, the literal restatement of graph.cpp:294-354.
+ * Kept for the test-suite (Params::serial_topsort) as the cross-check of the per-root sort.
+ * ---------------------------------------------------------------------------------------- */
+POA_FN void topsort_serial(const Slot& s, const Params& p, WinState& st) {
+    const int32_t N = st.n_nodes;
+    for (int32_t base = 0; base < N; base += 32) {
+        POA_LANES(l) {
+            if (base + l < N) {
+                s.marks[base + l] = 0;
+                s.check[base + l] = 1;
+            }
+        }
+    }
+    POA_SYNC();
+    POA_LANE0 {
+        int32_t out = 0, sp = 0;
+        for (int32_t i = 0; i < N; ++i) {
+            if (s.marks[i] != 0) continue;
+            s.stack[sp++] = (uint16_t)i;
+            while (sp != 0) {
+                const int32_t id = s.stack[sp - 1];
+                bool valid = true;
+                if (s.marks[id] != 2) {
+                    for (uint16_t e = s.in_head[id]; e != NONE16; e = s.e_next[e]) {
+                        const int32_t u = s.e_src[e];
+                        if (s.marks[u] != 2) {
+                            s.stack[sp++] = (uint16_t)u;
+                            valid = false;
+                        }
+                    }
+                    const int32_t na = s.aln_cnt[id];
+                    if (s.check[id]) {
+                        for (int32_t q = 0; q < na; ++q) {
+                            const int32_t a = s.aln[id * KA + q];
+                            if (s.marks[a] != 2) {
+                                s.stack[sp++] = (uint16_t)a;
+                                s.check[a] = 0;
+                                valid = false;
+                            }
+                        }
+                    }
+                    if (valid) {
+                        s.marks[id] = 2;
+                        if (s.check[id]) {
+                            s.node_at[out++] = (uint16_t)id;
+                            for (int32_t q = 0; q < na; ++q) s.node_at[out++] = s.aln[id * KA + q];
+                        }
+                    } else {
+                        s.marks[id] = 1;
+                    }
+                }
+                if (valid) --sp;
+            }
+        }
+    }
+    POA_SYNC();
+    for (int32_t base = 0; base < N; base += 32) {
+        POA_LANES(l) {
+            if (base + l < N) s.rank_of[s.node_at[base + l]] = (uint16_t)(base + l);
+        }
+    }
+    POA_SYNC();
+    (void)p;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Phase 5b: per-root topological sort.
+ *   spoa's outer loop visits ids in increasing order; the DFS started at i emits exactly the
+ *   not-yet-emitted members of i's ancestor closure (in-edges + aligned cliques), i.e. the nodes
+ *   with root[v] == i, and it only needs to know WHICH other nodes are already emitted
+ *   (root[u] < i), not their order.  Hence DFS_i for different i are independent:
+ *     1. cnt[i]  = |{v : root[v] == i}|, need[i] = stack bound for DFS_i
+ *     2. roff    = exclusive prefix sums (output offset, stack offset)
+ *     3. 32 roots at a time: singleton roots are written directly, the others run spoa's DFS
+ *        restricted to their own nodes.
+ * ---------------------------------------------------------------------------------------- */
+POA_FN void topsort_roots(const Slot& s, const Params& p, WinState& st) {
+    const int32_t N = st.n_nodes;
+    for (int32_t base = 0; base < N; base += 32) {
+        POA_LANES(l) {
+            if (base + l < N) {
+                s.cnt[base + l] = 0;
+                s.need[base + l] = 0;
+                s.marks[base + l] = 0;
+                s.check[base + l] = 1;
+            }
+        }
+    }
+    POA_SYNC();
+    /* 1. histogram by root (lanes of one step may hit the same root: atomic adds) */
+    for (int32_t base = 0; base < N; base += 32) {
+        POA_LANES(l) {
+            const int32_t v = base + l;
+            if (v >= N) continue;
+            const int32_t r = s.root[v];
+            poa_atomic_add(&s.cnt[r], 1u);
+            poa_atomic_add(&s.need[r], (uint32_t)(s.nin[v] + s.aln_cnt[v] + 1));
+        }
+    }
+    POA_SYNC();
+    /* 2 + 3. walk the roots in id order */
+    int32_t out_run = 0, stk_run = 0;
+    for (int32_t base = 0; base < N; base += 32) {
+        PerLane<int> c, nd;
+        POA_LANES(l) {
+            const int32_t i = base + l;
+            c[l] = (i < N) ? (int)s.cnt[i] : 0;
+            nd[l] = (i < N && s.cnt[i] > 1) ? (int)s.need[i] + 1 : 0;
+        }
+        PerLane<int> oo = c, so = nd;
+        const int32_t ctot = warp_exscan(oo);
+        const int32_t stot = warp_exscan(so);
+        POA_LANES(l) {
+            const int32_t i = base + l;
+            if (i >= N || c[l] == 0) continue;
+            int32_t out = out_run + oo[l];
+            if (c[l] == 1) {
+                s.node_at[out] = (uint16_t)i;
+                s.rank_of[i] = (uint16_t)out;
+                continue;
+            }
+            uint16_t* stk = s.stack + stk_run + so[l];
+            int32_t sp = 0;
+            stk[sp++] = (uint16_t)i;
+            while (sp != 0) {
+                const int32_t id = stk[sp - 1];
+                bool valid = true;
+                if (s.marks[id] != 2) {
+                    for (uint16_t e = s.in_head[id]; e != NONE16; e = s.e_next[e]) {
+                        const int32_t u = s.e_src[e];
+                        if ((int32_t)s.root[u] == i && s.marks[u] != 2) {
+                            stk[sp++] = (uint16_t)u;
+                            valid = false;
+                        }
+                    }
+                    const int32_t na = s.aln_cnt[id];
+                    if (s.check[id]) {
+                        for (int32_t q = 0; q < na; ++q) {
+                            const int32_t a = s.aln[id * KA + q];
+                            if (s.marks[a] != 2) { /* clique mates always share the root */
+                                stk[sp++] = (uint16_t)a;
+                                s.check[a] = 0;
+                                valid = false;
+                            }
+                        }
+                    }
+                    if (valid) {
+                        s.marks[id] = 2;
+                        if (s.check[id]) {
+                            s.node_at[out] = (uint16_t)id;
+                            s.rank_of[id] = (uint16_t)out;
+                            ++out;
+                            for (int32_t q = 0; q < na; ++q) {
+                                const int32_t a = s.aln[id * KA + q];
+                                s.node_at[out] = (uint16_t)a;
+                                s.rank_of[a] = (uint16_t)out;
+                                ++out;
+                            }
+                        }
+                    } else {
+                        s.marks[id] = 1;
+                    }
+                }
+                if (valid) --sp;
+            }
+        }
+        out_run += ctot;
+        stk_run += stot;
+    }
+    POA_SYNC();
+    (void)p;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Consensus: heaviest bundle  (graph.cpp:494-542 traverse_heaviest_bundle, :544-589
+ * branch_completion) and coverage (graph.cpp:447-453).  Writes the consensus FORWARD.
+ * ---------------------------------------------------------------------------------------- */
+POA_FN void consensus_scores_from(const Slot& s, int32_t N, int32_t first_rank, bool skip_dead,
+                                  int32_t& max_id, int32_t& max_score, bool strict_init) {
+    /* serial over ranks (lane 0) -- scores of predecessors must be final */
+    for (int32_t r = first_rank; r < N; ++r) {
+        const int32_t id = s.node_at[r];
+        int32_t sc = -1, pd = -1;
+        for (uint16_t e = s.in_head[id]; e != NONE16; e = s.e_next[e]) {
+            const int32_t u = s.e_src[e];
+            if (skip_dead && s.c_score[u] == -1) continue;
+            const int32_t w = s.e_w[e];
+            if (sc < w || (sc == w && s.c_score[pd] <= s.c_score[u])) {
+                sc = w;
+                pd = u;
+            }
+        }
+        if (pd != -1) sc += s.c_score[pd];
+        s.c_score[id] = sc;
+        s.c_pred[id] = pd;
+        if (strict_init) {
+            if (s.c_score[max_id] < sc) max_id = id;
+        } else if (max_score < sc) {
+            max_score = sc;
+            max_id = id;
+        }
+    }
+}
+
+POA_FN void generate_consensus(const Slot& s, const Params& p, WinState& st, uint8_t* out_cons,
+                               uint16_t* out_cov, int32_t* out_len) {
+    const int32_t N = st.n_nodes;
+    int32_t len = 0;
+    POA_LANE0 {
+        int32_t max_id = 0, dummy = 0;
+        s.c_score[0] = -1; /* scores[max_score_id] is read before node 0 is scored only if rank 0 != node 0 */
+        for (int32_t i = 0; i < N; ++i) {
+            s.c_score[i] = -1;
+            s.c_pred[i] = -1;
+        }
+        consensus_scores_from(s, N, 0, false, max_id, dummy, true);
+        int32_t guard = N + 1;
+        while (s.nout[max_id] != 0 && guard-- > 0) { /* graph.cpp:520-530 */
+            const int32_t node_id = max_id;
+            const int32_t rank = s.rank_of[node_id];
+            /* invalidate the other sources of every out-neighbour (graph.cpp:547-554) */
+            for (int32_t e = 0; e < st.n_edges; ++e) {
+                if (s.e_src[e] != node_id) continue;
+                const int32_t d = s.e_dst[e];
+                for (uint16_t f = s.in_head[d]; f != NONE16; f = s.e_next[f])
+                    if (s.e_src[f] != node_id) s.c_score[s.e_src[f]] = -1;
+            }
+            int32_t ms = 0;
+            max_id = 0;
+            consensus_scores_from(s, N, rank + 1, true, max_id, ms, false);
+        }
+        /* backtrack into c_score as scratch (path reversed), then emit forward */
+        int32_t n = 0;
+        int32_t v = max_id;
+        while (s.c_pred[v] != -1 && n < N) {
+            s.stack[n++] = (uint16_t)v;
+            v = s.c_pred[v];
+        }
+        s.stack[n++] = (uint16_t)v;
+        if (n > p.max_cons) {
+            st.status = ST_GENERIC_ERROR;
+            n = 0;
+        }
+        for (int32_t k = 0; k < n; ++k) {
+            const int32_t id = s.stack[n - 1 - k];
+            out_cons[k] = s.code[id];
+            int32_t c = s.cov[id];
+            for (int32_t q = 0; q < s.aln_cnt[id]; ++q) c += s.cov[s.aln[id * KA + q]];
+            out_cov[k] = (uint16_t)c;
+        }
+        len = n;
+        *out_len = n;
+    }
+    POA_SYNC();
+    (void)len;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * int16 safety: every real cell of the skewed matrix must stay far from NEG and from +32767.
+ * (spoa switches to int32 with the rule at simd_alignment_engine.cpp:668-673; cudapoa picks the
+ * width statically, cudapoa_limits.hpp:34-53.  We report ST_SCORE_RANGE_EXCEEDED instead and let
+ * the caller's CPU path handle such a window, like any other per-window failure.)
+ * ---------------------------------------------------------------------------------------- */
+POA_FN bool score_range_ok(const Params& p, int32_t n_nodes, int32_t len) {
+    int32_t mn = p.match < p.mismatch ? p.match : p.mismatch;
+    if (p.gap < mn) mn = p.gap;
+    if (mn > 0) mn = 0;
+    int32_t mx = p.match > p.mismatch ? p.match : p.mismatch;
+    if (p.gap > mx) mx = p.gap;
+    if (mx < 0) mx = 0;
+    const int64_t steps = (int64_t)n_nodes + len + 1;
+    const int64_t lo = (int64_t)mn * steps - (p.gap > 0 ? (int64_t)p.gap * (len + 1) : 0);
+    const int64_t hi = (int64_t)mx * steps + (p.gap < 0 ? (int64_t)(-p.gap) * (len + 1) : 0);
+    return lo > NEG + 512 && hi < 32000;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * One window, start to finish  (racon::Window::generate_consensus, src/window.cpp:65-116, for
+ * full-span layers; the caller trims).  Fill is the DP-fill functor:
+ *     int32_t operator()(slot, params, state, geom, read) -> end row (0 = none)
+ * ---------------------------------------------------------------------------------------- */
+template <class Fill>
+POA_FN void process_window(const Slot& s, const Params& p, const WindowView& wv, Fill& fill,
+                           uint8_t* out_cons, uint16_t* out_cov, int32_t* out_len,
+                           int32_t* out_status) {
+    WinState st;
+    st.n_nodes = 0;
+    st.n_edges = 0;
+    st.status = ST_SUCCESS;
+    const int32_t len0 = (int32_t)(wv.seq_off[1] - wv.seq_off[0]);
+    init_backbone(s, p, st, wv.bases + wv.seq_off[0], wv.weights + wv.seq_off[0], len0);
+    for (int32_t r = 1; r < wv.n_seqs && st.status == ST_SUCCESS; ++r) {
+        const uint8_t* read = wv.bases + wv.seq_off[r];
+        const int8_t* wt = wv.weights + wv.seq_off[r];
+        const int32_t len = (int32_t)(wv.seq_off[r + 1] - wv.seq_off[r]);
+        if (!score_range_ok(p, st.n_nodes, len)) {
+            st.status = ST_SCORE_RANGE_EXCEEDED;
+            break;
+        }
+        const ReadGeom g = read_geometry(p, len);
+        build_program(s, p, st, g);
+        const int32_t end_row = fill(s, p, st, g, read);
+        if (end_row <= 0) {
+            st.status = ST_TRACEBACK_LOST;
+            break;
+        }
+        const int32_t tb = traceback(s, p, st, g, read, end_row);
+        if (st.status != ST_SUCCESS) break;
+        add_alignment(s, p, st, read, wt, len, tb);
+        if (st.status != ST_SUCCESS) break;
+        if (p.serial_topsort) topsort_serial(s, p, st);
+        else topsort_roots(s, p, st);
+    }
+    if (st.status == ST_SUCCESS) generate_consensus(s, p, st, out_cons, out_cov, out_len);
+    POA_LANE0 {
+        if (st.status != ST_SUCCESS) *out_len = 0;
+        *out_status = st.status;
+    }
+    POA_SYNC();
+}
+
+} // namespace b200poa

@@ -1,0 +1,127 @@
+/*
+ * poa_simt.cuh -- the tiny warp-programming layer the POA engine is written against.
+ *
+ * The engine (poa_core.cuh) is one-window-per-warp code.  It is written ONCE and compiled in two
+ * flavours:
+ *   - nvcc (__CUDACC__): the product.  POA_LANES(l) runs its body once with l = this thread's lane,
+ *     PerLane<T> is a register, collectives are warp shuffles / ballots.
+ *   - g++  (tests/emu only): a lock-step emulation used by the CPU test-suite to check every graph
+ *     phase against the oracle without a GPU.  POA_LANES(l) loops l = 0..31, PerLane<T> is an array
+ *     of 32 values, collectives are plain loops.  The emulation is test infrastructure; the product
+ *     library never contains it.
+ *
+ * Rules the engine code obeys so both flavours mean the same thing:
+ *   - state that must survive from one POA_LANES block to the next lives in PerLane<T> variables
+ *     (or in the workspace memory);
+ *   - lanes inside one POA_LANES block never read what another lane writes in the same block;
+ *   - a POA_SYNC() separates blocks that communicate through memory.
+ */
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define POA_FN __device__ __forceinline__
+#define POA_FN_NOINLINE __device__ __noinline__
+#define POA_DEVICE 1
+#else
+#define POA_FN static inline
+#define POA_FN_NOINLINE static
+#define POA_DEVICE 0
+#endif
+
+namespace b200poa {
+
+#if POA_DEVICE
+
+template <class T>
+struct PerLane {
+    T v;
+    __device__ __forceinline__ T& operator[](int) { return v; }
+    __device__ __forceinline__ const T& operator[](int) const { return v; }
+};
+
+#define POA_LANES(l) for (int l = (int)(threadIdx.x & 31u), _poa_once = 1; _poa_once; _poa_once = 0)
+#define POA_LANE0 if ((threadIdx.x & 31u) == 0u)
+#define POA_SYNC() __syncwarp()
+
+/* exclusive prefix sum over lanes, returns the warp total */
+POA_FN int warp_exscan(PerLane<int>& x) {
+    const int lane = (int)(threadIdx.x & 31u);
+    int v = x.v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += t;
+    }
+    int total = __shfl_sync(0xffffffffu, v, 31);
+    x.v = v - x.v;
+    return total;
+}
+POA_FN unsigned warp_ballot(const PerLane<int>& p) { return __ballot_sync(0xffffffffu, p.v != 0); }
+POA_FN int warp_max(const PerLane<int>& x) { return __reduce_max_sync(0xffffffffu, x.v); }
+POA_FN int warp_min(const PerLane<int>& x) { return __reduce_min_sync(0xffffffffu, x.v); }
+POA_FN int warp_sum(const PerLane<int>& x) { return __reduce_add_sync(0xffffffffu, x.v); }
+/* value held by lane `src` (src uniform) */
+POA_FN int warp_get(const PerLane<int>& x, int src) { return __shfl_sync(0xffffffffu, x.v, src); }
+/* make a lane-0 scalar uniform across the warp */
+POA_FN int warp_bcast0(int x) { return __shfl_sync(0xffffffffu, x, 0); }
+
+#else /* ---------------------------------------------------------------- host emulation */
+
+template <class T>
+struct PerLane {
+    T v[32];
+    T& operator[](int l) { return v[l]; }
+    const T& operator[](int l) const { return v[l]; }
+};
+
+#define POA_LANES(l) for (int l = 0; l < 32; ++l)
+#define POA_LANE0
+#define POA_SYNC() ((void)0)
+
+POA_FN int warp_exscan(PerLane<int>& x) {
+    int run = 0;
+    for (int l = 0; l < 32; ++l) {
+        int t = x.v[l];
+        x.v[l] = run;
+        run += t;
+    }
+    return run;
+}
+POA_FN unsigned warp_ballot(const PerLane<int>& p) {
+    unsigned m = 0;
+    for (int l = 0; l < 32; ++l)
+        if (p.v[l]) m |= 1u << l;
+    return m;
+}
+POA_FN int warp_max(const PerLane<int>& x) {
+    int m = x.v[0];
+    for (int l = 1; l < 32; ++l)
+        if (x.v[l] > m) m = x.v[l];
+    return m;
+}
+POA_FN int warp_min(const PerLane<int>& x) {
+    int m = x.v[0];
+    for (int l = 1; l < 32; ++l)
+        if (x.v[l] < m) m = x.v[l];
+    return m;
+}
+POA_FN int warp_sum(const PerLane<int>& x) {
+    int s = 0;
+    for (int l = 0; l < 32; ++l) s += x.v[l];
+    return s;
+}
+POA_FN int warp_get(const PerLane<int>& x, int src) { return x.v[src]; }
+POA_FN int warp_bcast0(int x) { return x; }
+
+#endif
+
+POA_FN int poa_ffs(unsigned m) { /* index of lowest set bit, m != 0 */
+#if POA_DEVICE
+    return __ffs((int)m) - 1;
+#else
+    return __builtin_ctz(m);
+#endif
+}
+
+} // namespace b200poa
