@@ -159,6 +159,55 @@ int32_t b200poa_batch_get_info(const b200poa_batch* b, b200poa_batch_info* info)
 
 const char* b200poa_status_string(int32_t status);
 
+/*
+ * Whole-job entry: racon's GPU window scheduler (CUDAPolisher::polish, src/cuda/cudapolisher.cpp:
+ * 216-345) over a columnar window arena with HOST buffers: `batches_per_device` batch processors
+ * per device (racon -c), one host thread each, a shared window cursor, pinned staging, H2D, the POA
+ * kernel, D2H and racon's coverage trim (src/window.cpp:118-139).
+ *   device_ids NULL / n_devices 0 => every visible device.
+ *   mem_per_batch 0 => 0.9 * free / batches_per_device (cudapolisher.cpp:233-236).
+ *   cons_out: n_windows rows of `stride` bytes; cons_len[w] the (trimmed) length; polished[w] is
+ *   racon's per-window bool (false => the caller's CPU path must polish it: < 3 sequences,
+ *   or status_out[w] != success).
+ */
+int32_t b200poa_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int64_t* seq_off,
+                               const uint8_t* bases, const int8_t* weights, const uint8_t* has_weights,
+                               const int32_t* begins, const int32_t* ends, int32_t tgs, int32_t trim,
+                               int32_t match, int32_t mismatch, int32_t gap, int32_t banded,
+                               int32_t n_devices, const int32_t* device_ids, int32_t batches_per_device,
+                               size_t mem_per_batch, int32_t max_windows_per_round, uint8_t* cons_out,
+                               int32_t stride, int32_t* cons_len, uint8_t* polished, int32_t* status_out,
+                               int64_t* kernel_launches);
+
+/* Persistent form of b200poa_polish_windows: the batch processors (device workspaces, pinned
+ * staging, streams) are created once -- as CUDAPolisher::polish does per run,
+ * src/cuda/cudapolisher.cpp:226-240 -- and reused by every polish call.  h2d_bytes / d2h_bytes
+ * (nullable) receive the bytes copied across PCIe by the call. */
+typedef struct b200poa_polisher b200poa_polisher;
+int32_t b200poa_polisher_create(int32_t n_devices, const int32_t* device_ids, int32_t batches_per_device,
+                                size_t mem_per_batch, int32_t banded, int32_t match, int32_t mismatch,
+                                int32_t gap, b200poa_polisher** out);
+int32_t b200poa_polisher_polish(b200poa_polisher* h, int64_t n_windows, const int64_t* win_seq_off,
+                                const int64_t* seq_off, const uint8_t* bases, const int8_t* weights,
+                                const uint8_t* has_weights, const int32_t* begins, const int32_t* ends,
+                                int32_t tgs, int32_t trim, int32_t max_windows_per_round, uint8_t* cons_out,
+                                int32_t stride, int32_t* cons_len, uint8_t* polished, int32_t* status_out,
+                                int64_t* kernel_launches, int64_t* h2d_bytes, int64_t* d2h_bytes);
+void b200poa_polisher_destroy(b200poa_polisher* h);
+
+/* The same job driven through the C++ class API that mirrors racon's (racon_b200::createWindow /
+ * Window::add_layer / CUDABatchProcessor / polish_windows, racon_gpu_b200/csrc/host/): the path a
+ * racon maintainer's code takes.  Same arguments as b200poa_polish_windows. */
+int32_t b200poa_polish_windows_via_adapter(int64_t n_windows, const int64_t* win_seq_off,
+                                           const int64_t* seq_off, const uint8_t* bases,
+                                           const int8_t* weights, const uint8_t* has_weights,
+                                           const int32_t* begins, const int32_t* ends, int32_t tgs,
+                                           int32_t trim, int32_t match, int32_t mismatch, int32_t gap,
+                                           int32_t banded, int32_t n_devices, const int32_t* device_ids,
+                                           int32_t batches_per_device, size_t mem_per_batch,
+                                           int32_t max_windows_per_round, uint8_t* cons_out, int32_t stride,
+                                           int32_t* cons_len, uint8_t* polished);
+
 #ifdef __cplusplus
 }
 #endif

@@ -525,7 +525,7 @@ int32_t poa_oracle_window_consensus(int32_t n_seqs, const char* const* seqs, con
                                     const int32_t* ends, int32_t tgs, int32_t trim, int32_t m,
                                     int32_t x, int32_t gap, char* cons_out, uint32_t* cov_out,
                                     int32_t max_out, int32_t* polished, int64_t* stats) {
-    if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    if (stats) stats[0] = stats[1] = stats[2] = stats[3] = stats[4] = stats[5] = 0;
     if (n_seqs < 3) { /* window.cpp:68-71 */
         if (polished) *polished = 0;
         if (lens[0] > max_out) return -1;
@@ -548,12 +548,18 @@ int32_t poa_oracle_window_consensus(int32_t n_seqs, const char* const* seqs, con
         poa_pair* aln = NULL;
         int32_t n_aln;
         if ((uint32_t)begins[i] < offset && (uint32_t)ends[i] > L - offset) { /* window.cpp:92-95 */
-            if (stats) stats[2] += (int64_t)g->nn * (lens[i] + 1);
+            if (stats) {
+                stats[2] += (int64_t)g->nn * (lens[i] + 1);
+                stats[4] += (int64_t)g->nn * (lens[i] + 1 < 256 ? lens[i] + 1 : 256);
+            }
             n_aln = poa_align_nw(g, seqs[i], lens[i], m, x, gap, &aln);
         } else { /* window.cpp:96-103 */
             int32_t* mapping = (int32_t*)malloc(sizeof(int32_t) * (size_t)(g->nn + 1));
             poa_graph* s = subgraph(g, begins[i], ends[i], mapping);
-            if (stats) stats[2] += (int64_t)s->nn * (lens[i] + 1);
+            if (stats) {
+                stats[2] += (int64_t)s->nn * (lens[i] + 1);
+                stats[4] += (int64_t)s->nn * (lens[i] + 1 < 256 ? lens[i] + 1 : 256);
+            }
             n_aln = poa_align_nw(s, seqs[i], lens[i], m, x, gap, &aln);
             for (int32_t k = 0; k < n_aln; ++k)
                 if (aln[k].node != -1) aln[k].node = mapping[aln[k].node];
@@ -663,7 +669,7 @@ static void* batch_worker(void* arg) {
         int32_t len = poa_oracle_window_consensus(
             n, seqs, lens, wts, bg, en, job->tgs, job->trim, job->m, job->x, job->gap,
             job->cons_out + w * (int64_t)job->stride, cov, job->stride, &pol,
-            job->stats ? job->stats + 4 * w : NULL);
+            job->stats ? job->stats + 6 * w : NULL);
         job->cons_len[w] = len;
         job->polished[w] = (uint8_t)pol;
         if (job->cov_out && len > 0)

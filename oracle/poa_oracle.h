@@ -62,8 +62,9 @@ int32_t poa_graph_consensus(poa_graph* g, char** cons, uint32_t** cov);
  *   tgs != 0 && trim != 0 enables the coverage trim (window.cpp:118-139).
  * Outputs: cons_out must hold max_out bytes, cov_out (nullable) max_out uint32 (coverage of the
  * UNTRIMMED consensus is trimmed alongside).  Returns consensus length, or -1 if max_out too small.
- * *polished receives window.cpp's return value; *stats (nullable, 4 x int64) receives
- * {final node count, final edge count, sum over reads of (rows x (len+1)) DP cells, #reads aligned}.
+ * *polished receives window.cpp's return value; *stats (nullable, 6 x int64) receives
+ * {final node count, final edge count, sum over reads of rows x (len+1) DP cells, #reads aligned,
+ *  sum over reads of rows x min(len+1, 256) (the cells of a 256-column band), 0}.
  */
 int32_t poa_oracle_window_consensus(int32_t n_seqs, const char* const* seqs, const int32_t* lens,
                                     const int8_t* const* weights, const int32_t* begins,
@@ -77,7 +78,7 @@ int32_t poa_oracle_window_consensus(int32_t n_seqs, const char* const* seqs, con
  * local index of the sequence processed at that step (order[win_seq_off[w]] == 0), i.e. the
  * permutation window.cpp:78-85 computes.  n_threads pthreads share a window cursor.
  * cons_out: n_windows rows of `stride` bytes; cov_out nullable (n_windows x stride uint16).
- * stats nullable: n_windows x 4 int64 (see poa_oracle_window_consensus).
+ * stats nullable: n_windows x 6 int64 (see poa_oracle_window_consensus).
  */
 void poa_oracle_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int64_t* seq_off,
                                const uint8_t* bases, const int8_t* weights,

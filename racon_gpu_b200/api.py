@@ -37,7 +37,8 @@ ABI_SYMBOLS = (
     "b200poa_batch_generate", "b200poa_batch_upload", "b200poa_batch_launch",
     "b200poa_batch_download", "b200poa_batch_get_consensus", "b200poa_batch_id",
     "b200poa_batch_reset", "b200poa_batch_destroy", "b200poa_batch_get_info",
-    "b200poa_status_string", "b200poa_polish_windows",
+    "b200poa_status_string", "b200poa_polish_windows", "b200poa_polish_windows_via_adapter",
+    "b200poa_polisher_create", "b200poa_polisher_polish", "b200poa_polisher_destroy",
 )
 
 
@@ -288,3 +289,100 @@ class CUDABatchProcessor:
     def reset(self):
         self.batch.reset()
         self.n_seqs = []
+
+
+def polish_windows(windows: WindowBatch, match: int = 3, mismatch: int = -5, gap: int = -4,
+                   banded: bool = False, tgs: bool = True, trim: bool = True, devices=None,
+                   batches_per_device: int = 1, mem_per_batch: int = 0, max_windows_per_round: int = 0,
+                   stride: int = 2048, via_adapter: bool = False):
+    """Whole-job call with HOST buffers (b200poa_polish_windows): racon's GPU window scheduler
+    (src/cuda/cudapolisher.cpp:216-345) over a columnar arena.
+
+    Returns (cons uint8 [W, stride], cons_len int32 [W], polished bool [W], status int32 [W],
+    kernel_launches)."""
+    lib = load_library()
+    W = windows.n_windows
+    cons = np.zeros((W, stride), dtype=np.uint8)
+    clen = np.zeros(W, dtype=np.int32)
+    pol = np.zeros(W, dtype=np.uint8)
+    status = np.zeros(W, dtype=np.int32)
+    dev = np.asarray(devices if devices is not None else [], dtype=np.int32)
+    launches = C.c_int64(0)
+    if via_adapter:  # the C++ class API mirroring racon's Window / CUDABatchProcessor / polish()
+        st = lib.b200poa_polish_windows_via_adapter(
+            C.c_int64(W), _p(windows.win_seq_off, C.c_int64), _p(windows.seq_off, C.c_int64),
+            _p(windows.bases, C.c_uint8), _p(windows.weights, C.c_int8), _p(windows.has_weights, C.c_uint8),
+            _p(windows.begins, C.c_int32), _p(windows.ends, C.c_int32), C.c_int32(int(tgs)), C.c_int32(int(trim)),
+            C.c_int32(match), C.c_int32(mismatch), C.c_int32(gap), C.c_int32(int(banded)),
+            C.c_int32(dev.shape[0]), _p(dev, C.c_int32) if dev.shape[0] else None, C.c_int32(batches_per_device),
+            C.c_size_t(mem_per_batch), C.c_int32(max_windows_per_round), _p(cons, C.c_uint8), C.c_int32(stride),
+            _p(clen, C.c_int32), _p(pol, C.c_uint8))
+        if st != SUCCESS:
+            raise RuntimeError(f"b200poa_polish_windows_via_adapter failed: {status_string(st)}")
+        return cons, clen, pol.astype(bool), status, 0
+    st = lib.b200poa_polish_windows(
+        C.c_int64(W), _p(windows.win_seq_off, C.c_int64), _p(windows.seq_off, C.c_int64),
+        _p(windows.bases, C.c_uint8), _p(windows.weights, C.c_int8), _p(windows.has_weights, C.c_uint8),
+        _p(windows.begins, C.c_int32), _p(windows.ends, C.c_int32), C.c_int32(int(tgs)), C.c_int32(int(trim)),
+        C.c_int32(match), C.c_int32(mismatch), C.c_int32(gap), C.c_int32(int(banded)),
+        C.c_int32(dev.shape[0]), _p(dev, C.c_int32) if dev.shape[0] else None, C.c_int32(batches_per_device),
+        C.c_size_t(mem_per_batch), C.c_int32(max_windows_per_round), _p(cons, C.c_uint8), C.c_int32(stride),
+        _p(clen, C.c_int32), _p(pol, C.c_uint8), _p(status, C.c_int32), C.byref(launches))
+    if st != SUCCESS:
+        raise RuntimeError(f"b200poa_polish_windows failed: {status_string(st)}")
+    return cons, clen, pol.astype(bool), status, int(launches.value)
+
+
+def consensus_list(cons: np.ndarray, clen: np.ndarray):
+    return [cons[w, :clen[w]].tobytes() for w in range(cons.shape[0])]
+
+
+class Polisher:
+    """Persistent GPU window polisher (b200poa_polisher_*): batch processors are created once and
+    reused by every `polish` call, like one `CUDAPolisher::polish` run does (cudapolisher.cpp:226-240)."""
+
+    def __init__(self, devices=None, batches_per_device: int = 1, mem_per_batch: int = 0, banded: bool = False,
+                 match: int = 3, mismatch: int = -5, gap: int = -4):
+        self.lib = load_library()
+        self.lib.b200poa_polisher_destroy.restype = None
+        dev = np.asarray(devices if devices is not None else [], dtype=np.int32)
+        self.handle = C.c_void_p()
+        st = self.lib.b200poa_polisher_create(C.c_int32(dev.shape[0]), _p(dev, C.c_int32) if dev.shape[0] else None,
+                                              C.c_int32(batches_per_device), C.c_size_t(mem_per_batch),
+                                              C.c_int32(int(banded)), C.c_int32(match), C.c_int32(mismatch),
+                                              C.c_int32(gap), C.byref(self.handle))
+        if st != SUCCESS:
+            raise RuntimeError(f"b200poa_polisher_create failed: {status_string(st)}")
+        self.last = {}
+
+    def polish(self, windows: WindowBatch, tgs: bool = True, trim: bool = True, max_windows_per_round: int = 0,
+               stride: int = 2048, out=None):
+        """Returns (cons [W, stride] uint8, cons_len, polished, status).  `out` lets the caller reuse
+        output arrays between calls."""
+        W = windows.n_windows
+        if out is None:
+            out = (np.zeros((W, stride), dtype=np.uint8), np.zeros(W, dtype=np.int32),
+                   np.zeros(W, dtype=np.uint8), np.zeros(W, dtype=np.int32))
+        cons, clen, pol, status = out
+        launches, h2d, d2h = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        st = self.lib.b200poa_polisher_polish(
+            self.handle, C.c_int64(W), _p(windows.win_seq_off, C.c_int64), _p(windows.seq_off, C.c_int64),
+            _p(windows.bases, C.c_uint8), _p(windows.weights, C.c_int8), _p(windows.has_weights, C.c_uint8),
+            _p(windows.begins, C.c_int32), _p(windows.ends, C.c_int32), C.c_int32(int(tgs)), C.c_int32(int(trim)),
+            C.c_int32(max_windows_per_round), _p(cons, C.c_uint8), C.c_int32(stride), _p(clen, C.c_int32),
+            _p(pol, C.c_uint8), _p(status, C.c_int32), C.byref(launches), C.byref(h2d), C.byref(d2h))
+        if st != SUCCESS:
+            raise RuntimeError(f"b200poa_polisher_polish failed: {status_string(st)}")
+        self.last = {"kernel_launches": int(launches.value), "h2d_bytes": int(h2d.value), "d2h_bytes": int(d2h.value)}
+        return cons, clen, pol.astype(bool), status
+
+    def close(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            self.lib.b200poa_polisher_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,350 @@
+/* cuda_polisher.cpp -- see cuda_polisher.hpp and include/b200poa.h (b200poa_polish_windows). */
+#include "cuda_polisher.hpp"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <stdexcept>
+#include <thread>
+
+#include "b200poa.h"
+#include "cuda_batch.hpp"
+
+namespace racon_b200 {
+
+static std::vector<int32_t> resolve_devices(const std::vector<int32_t>& want) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1)
+        throw std::runtime_error("[racon_b200] no CUDA device visible (this engine has no CPU fallback)");
+    std::vector<int32_t> d = want;
+    if (d.empty())
+        for (int i = 0; i < n; ++i) d.push_back(i);
+    for (int32_t x : d)
+        if (x < 0 || x >= n) throw std::invalid_argument("[racon_b200] invalid device id");
+    return d;
+}
+
+static size_t batch_memory(int32_t device, uint32_t batches, size_t requested) {
+    if (requested) return requested;
+    size_t free_b = 0, total = 0;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(device);
+    cudaMemGetInfo(&free_b, &total);
+    cudaSetDevice(prev);
+    return static_cast<size_t>(0.9 * static_cast<double>(free_b) / batches); /* cudapolisher.cpp:233-236 */
+}
+
+std::vector<bool> polish_windows(std::vector<std::shared_ptr<Window>>& windows, const PolishOptions& opt) {
+    const std::vector<int32_t> devices = resolve_devices(opt.devices);
+    const uint32_t nb = std::max<uint32_t>(opt.cudapoa_batches, 1);
+    std::vector<std::unique_ptr<CUDABatchProcessor>> processors;
+    for (int32_t dev : devices) {
+        const size_t mem = batch_memory(dev, nb, opt.mem_per_batch);
+        for (uint32_t b = 0; b < nb; ++b)
+            processors.emplace_back(createCUDABatch(opt.max_depth_per_window, static_cast<uint32_t>(dev), mem, opt.gap,
+                                                    opt.mismatch, opt.match, opt.cuda_banded_alignment, opt.trim));
+    }
+    std::vector<bool> status(windows.size(), false);
+    std::mutex mutex_windows;
+    uint32_t next_window_index = 0;
+
+    /* cudapolisher.cpp:254-276 */
+    auto fill_next_batch = [&](CUDABatchProcessor* batch) -> std::pair<uint32_t, uint32_t> {
+        batch->reset();
+        std::lock_guard<std::mutex> guard(mutex_windows);
+        const uint32_t initial_count = next_window_index;
+        const uint32_t count = static_cast<uint32_t>(windows.size());
+        while (next_window_index < count) {
+            if (opt.max_windows_per_round && next_window_index - initial_count >= opt.max_windows_per_round) break;
+            if (batch->addWindow(windows.at(next_window_index))) next_window_index++;
+            else break;
+        }
+        return {initial_count, next_window_index};
+    };
+    /* cudapolisher.cpp:286-333 */
+    auto process_batch = [&](CUDABatchProcessor* batch) {
+        while (true) {
+            const std::pair<uint32_t, uint32_t> range = fill_next_batch(batch);
+            if (!batch->hasWindows()) break;
+            const std::vector<bool>& results = batch->generateConsensus();
+            if (results.size() != (range.second - range.first))
+                throw std::runtime_error("Windows processed doesn't match range of windows passed to batch");
+            std::lock_guard<std::mutex> guard(mutex_windows);
+            for (uint32_t i = 0; i < results.size(); i++) status.at(range.first + i) = results.at(i);
+        }
+    };
+    std::vector<std::thread> threads; /* cudapolisher.cpp:336-350 (thread_pool_->submit per processor) */
+    std::vector<std::string> errors(processors.size());
+    for (size_t t = 0; t < processors.size(); ++t)
+        threads.emplace_back([&, t]() {
+            try {
+                process_batch(processors[t].get());
+            } catch (const std::exception& e) {
+                errors[t] = e.what();
+            }
+        });
+    for (auto& t : threads) t.join();
+    for (const auto& e : errors)
+        if (!e.empty()) throw std::runtime_error(e);
+    return status;
+}
+
+} // namespace racon_b200
+
+/* ------------------------------------------------------------------------------------------------
+ * Columnar entry point: the same scheduler over a flat window arena, without materialising
+ * racon_b200::Window objects.  Each batch thread claims a chunk of windows under the mutex, packs it
+ * into its pinned staging OUTSIDE the mutex, runs the batch and writes trimmed results.
+ * ---------------------------------------------------------------------------------------------- */
+namespace {
+
+struct FlatProc {
+    int32_t device = 0;
+    cudaStream_t stream = nullptr;
+    b200poa_batch* batch = nullptr;
+};
+
+} // namespace
+
+struct b200poa_polisher {
+    std::vector<FlatProc> procs;
+    int32_t banded = 0;
+};
+
+extern "C" void b200poa_polisher_destroy(b200poa_polisher* h) {
+    if (!h) return;
+    for (auto& p : h->procs) {
+        cudaSetDevice(p.device);
+        if (p.batch) b200poa_batch_destroy(p.batch);
+        if (p.stream) cudaStreamDestroy(p.stream);
+    }
+    delete h;
+}
+
+extern "C" int32_t b200poa_polisher_create(int32_t n_devices, const int32_t* device_ids, int32_t batches_per_device,
+                                           size_t mem_per_batch, int32_t banded, int32_t match, int32_t mismatch,
+                                           int32_t gap, b200poa_polisher** out) {
+    using namespace racon_b200;
+    if (!out) return B200POA_INVALID_ARGUMENT;
+    *out = nullptr;
+    std::vector<int32_t> devices;
+    try {
+        std::vector<int32_t> want;
+        for (int32_t i = 0; i < n_devices; ++i) want.push_back(device_ids[i]);
+        devices = resolve_devices(want);
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "%s\n", e.what());
+        return B200POA_CUDA_ERROR;
+    }
+    const uint32_t nb = static_cast<uint32_t>(std::max(batches_per_device, 1));
+    b200poa_polisher* h = new b200poa_polisher();
+    h->banded = banded;
+    int32_t rc = B200POA_SUCCESS;
+    b200poa_config cfg;
+    b200poa_config_default(&cfg, 1023, 200, 256, banded ? B200POA_STATIC_BAND : B200POA_FULL_BAND); /* cudabatch.cpp:56-59 */
+    for (int32_t dev : devices) {
+        const size_t mem = batch_memory(dev, nb, mem_per_batch);
+        for (uint32_t k = 0; k < nb && rc == B200POA_SUCCESS; ++k) {
+            FlatProc p;
+            p.device = dev;
+            cudaSetDevice(dev);
+            if (cudaStreamCreate(&p.stream) != cudaSuccess) rc = B200POA_CUDA_ERROR;
+            else rc = b200poa_batch_create(dev, p.stream, mem, B200POA_OUTPUT_CONSENSUS, &cfg, static_cast<int16_t>(gap),
+                                           static_cast<int16_t>(mismatch), static_cast<int16_t>(match), &p.batch);
+            h->procs.push_back(p);
+        }
+    }
+    if (rc != B200POA_SUCCESS) {
+        b200poa_polisher_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return B200POA_SUCCESS;
+}
+
+extern "C" int32_t b200poa_polisher_polish(b200poa_polisher* h, int64_t n_windows, const int64_t* win_seq_off,
+                                           const int64_t* seq_off, const uint8_t* bases, const int8_t* weights,
+                                           const uint8_t* has_weights, const int32_t* begins, const int32_t* ends,
+                                           int32_t tgs, int32_t trim, int32_t max_windows_per_round, uint8_t* cons_out,
+                                           int32_t stride, int32_t* cons_len, uint8_t* polished, int32_t* status_out,
+                                           int64_t* kernel_launches, int64_t* h2d_bytes, int64_t* d2h_bytes) {
+    if (!h || n_windows < 0 || !win_seq_off || !seq_off || !cons_out || !cons_len || !polished) return B200POA_INVALID_ARGUMENT;
+    std::vector<FlatProc>& procs = h->procs;
+    std::mutex mu;
+    int64_t cursor = 0;
+    int64_t launches = 0, up_bytes = 0, down_bytes = 0;
+    const int64_t chunk = max_windows_per_round > 0
+                              ? max_windows_per_round
+                              : std::max<int64_t>(256, (n_windows + (int64_t)procs.size() * 4 - 1) / ((int64_t)procs.size() * 4));
+    auto worker = [&](FlatProc* p) -> int32_t {
+        cudaSetDevice(p->device);
+        int64_t lo = 0, hi = 0; /* claimed but not yet processed windows */
+        std::vector<int32_t> seqs_added;
+        for (;;) {
+            if (lo == hi) {
+                std::lock_guard<std::mutex> g(mu);
+                lo = cursor;
+                hi = std::min<int64_t>(n_windows, lo + chunk);
+                cursor = hi;
+            }
+            if (lo == hi) return B200POA_SUCCESS;
+            b200poa_batch_reset(p->batch);
+            int64_t first = lo, n_added = 0;
+            seqs_added.resize(static_cast<size_t>(hi - lo));
+            /* stage [lo, hi) but stop at the first window that does not fit */
+            int32_t st = b200poa_batch_add_windows(p->batch, hi, first, win_seq_off, seq_off, bases, weights, has_weights,
+                                                   begins, ends, &n_added, seqs_added.data());
+            if (st != B200POA_SUCCESS) return st;
+            if (n_added == 0) return B200POA_EXCEEDED_MAXIMUM_POAS; /* a single window larger than the batch */
+            st = b200poa_batch_generate(p->batch);
+            if (st != B200POA_SUCCESS) return st;
+            const uint8_t* c; const uint16_t* v; const int32_t* l; const int32_t* s; int32_t bstride;
+            st = b200poa_batch_get_consensus(p->batch, &c, &v, &l, &s, &bstride);
+            if (st != B200POA_SUCCESS) return st;
+            b200poa_batch_info info;
+            b200poa_batch_get_info(p->batch, &info);
+            for (int64_t i = 0; i < n_added; ++i) {
+                const int64_t w = first + i;
+                const int64_t nseq = win_seq_off[w + 1] - win_seq_off[w];
+                const size_t o = static_cast<size_t>(i) * static_cast<size_t>(bstride);
+                uint8_t* dst = cons_out + static_cast<size_t>(w) * static_cast<size_t>(stride);
+                if (status_out) status_out[w] = s[i];
+                if (nseq < 3) { /* window.cpp:68-71: backbone, not polished */
+                    const int64_t a = seq_off[win_seq_off[w]], b = seq_off[win_seq_off[w] + 1];
+                    const int64_t n = std::min<int64_t>(b - a, stride);
+                    std::memcpy(dst, bases + a, static_cast<size_t>(n));
+                    cons_len[w] = static_cast<int32_t>(b - a);
+                    polished[w] = 0;
+                    continue;
+                }
+                if (s[i] != B200POA_SUCCESS || seqs_added[static_cast<size_t>(i)] != nseq - 1) {
+                    /* kernel failure, or layers dropped by the batch limits: the caller's CPU path */
+                    cons_len[w] = 0;
+                    polished[w] = 0;
+                    continue;
+                }
+                int32_t begin = 0, end = l[i] - 1;
+                if (tgs && trim) { /* window.cpp:118-139 */
+                    const uint32_t avg = static_cast<uint32_t>(nseq - 1) / 2;
+                    for (; begin < l[i]; ++begin)
+                        if (v[o + begin] >= avg) break;
+                    for (; end >= 0; --end)
+                        if (v[o + end] >= avg) break;
+                    if (begin >= end) {
+                        begin = 0;
+                        end = l[i] - 1;
+                    }
+                }
+                const int32_t n = end - begin + 1;
+                std::memcpy(dst, c + o + begin, static_cast<size_t>(std::min(n, stride)));
+                cons_len[w] = n;
+                polished[w] = 1;
+            }
+            {
+                std::lock_guard<std::mutex> g(mu);
+                launches += 1;
+                up_bytes += 2 * info.staged_bases + 8 * (win_seq_off[first + n_added] - win_seq_off[first] + 1) + 12 * n_added + 4;
+                down_bytes += n_added * (3 * static_cast<int64_t>(bstride) + 8);
+            }
+            lo = first + n_added;
+        }
+    };
+    std::vector<int32_t> results(procs.size(), B200POA_SUCCESS);
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < procs.size(); ++t) th.emplace_back([&, t]() { results[t] = worker(&procs[t]); });
+    for (auto& t : th) t.join();
+    int32_t rc = B200POA_SUCCESS;
+    for (int32_t r : results)
+        if (r != B200POA_SUCCESS) rc = r;
+    if (kernel_launches) *kernel_launches = launches;
+    if (h2d_bytes) *h2d_bytes = up_bytes;
+    if (d2h_bytes) *d2h_bytes = down_bytes;
+    return rc;
+}
+
+extern "C" int32_t b200poa_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int64_t* seq_off,
+                                          const uint8_t* bases, const int8_t* weights, const uint8_t* has_weights,
+                                          const int32_t* begins, const int32_t* ends, int32_t tgs, int32_t trim,
+                                          int32_t match, int32_t mismatch, int32_t gap, int32_t banded,
+                                          int32_t n_devices, const int32_t* device_ids, int32_t batches_per_device,
+                                          size_t mem_per_batch, int32_t max_windows_per_round, uint8_t* cons_out,
+                                          int32_t stride, int32_t* cons_len, uint8_t* polished, int32_t* status_out,
+                                          int64_t* kernel_launches) {
+    b200poa_polisher* h = nullptr;
+    int32_t rc = b200poa_polisher_create(n_devices, device_ids, batches_per_device, mem_per_batch, banded, match, mismatch, gap, &h);
+    if (rc != B200POA_SUCCESS) return rc;
+    rc = b200poa_polisher_polish(h, n_windows, win_seq_off, seq_off, bases, weights, has_weights, begins, ends, tgs, trim,
+                                 max_windows_per_round, cons_out, stride, cons_len, polished, status_out, kernel_launches,
+                                 nullptr, nullptr);
+    b200poa_polisher_destroy(h);
+    return rc;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Same job through the class API a racon maintainer would use: racon_b200::createWindow / add_layer
+ * (== racon::createWindow / Window::add_layer), then polish_windows (== CUDAPolisher::polish's GPU
+ * section) driving racon_b200::CUDABatchProcessor::addWindow / generateConsensus.  Qualities are
+ * passed as PHRED+33 strings exactly as racon holds them (polisher.cpp:392-395, 430-441).
+ * ---------------------------------------------------------------------------------------------- */
+extern "C" int32_t b200poa_polish_windows_via_adapter(int64_t n_windows, const int64_t* win_seq_off,
+                                                      const int64_t* seq_off, const uint8_t* bases,
+                                                      const int8_t* weights, const uint8_t* has_weights,
+                                                      const int32_t* begins, const int32_t* ends, int32_t tgs,
+                                                      int32_t trim, int32_t match, int32_t mismatch, int32_t gap,
+                                                      int32_t banded, int32_t n_devices, const int32_t* device_ids,
+                                                      int32_t batches_per_device, size_t mem_per_batch,
+                                                      int32_t max_windows_per_round, uint8_t* cons_out, int32_t stride,
+                                                      int32_t* cons_len, uint8_t* polished) {
+    using namespace racon_b200;
+    try {
+        const int64_t n_bases = seq_off[win_seq_off[n_windows]];
+        std::string quality(static_cast<size_t>(n_bases), '!');
+        for (int64_t i = 0; i < n_bases; ++i) quality[static_cast<size_t>(i)] = static_cast<char>(weights[i] + 33);
+        std::vector<std::shared_ptr<Window>> windows;
+        windows.reserve(static_cast<size_t>(n_windows));
+        for (int64_t w = 0; w < n_windows; ++w) {
+            const int64_t s0 = win_seq_off[w], s1 = win_seq_off[w + 1];
+            const uint32_t bl = static_cast<uint32_t>(seq_off[s0 + 1] - seq_off[s0]);
+            auto win = createWindow(static_cast<uint64_t>(w), 0, tgs ? WindowType::kTGS : WindowType::kNGS,
+                                    reinterpret_cast<const char*>(bases + seq_off[s0]), bl, quality.data() + seq_off[s0], bl);
+            if (!win) return B200POA_INVALID_ARGUMENT;
+            for (int64_t s = s0 + 1; s < s1; ++s) {
+                const uint32_t len = static_cast<uint32_t>(seq_off[s + 1] - seq_off[s]);
+                if (!win->add_layer(reinterpret_cast<const char*>(bases + seq_off[s]), len,
+                                    has_weights[s] ? quality.data() + seq_off[s] : nullptr, has_weights[s] ? len : 0,
+                                    static_cast<uint32_t>(begins[s]), static_cast<uint32_t>(ends[s])))
+                    return B200POA_INVALID_ARGUMENT;
+            }
+            windows.push_back(win);
+        }
+        PolishOptions opt;
+        for (int32_t i = 0; i < n_devices; ++i) opt.devices.push_back(device_ids[i]);
+        opt.cudapoa_batches = static_cast<uint32_t>(std::max(batches_per_device, 1));
+        opt.cuda_banded_alignment = banded != 0;
+        opt.match = static_cast<int8_t>(match);
+        opt.mismatch = static_cast<int8_t>(mismatch);
+        opt.gap = static_cast<int8_t>(gap);
+        opt.trim = trim != 0;
+        opt.mem_per_batch = mem_per_batch;
+        opt.max_windows_per_round = static_cast<uint32_t>(std::max(max_windows_per_round, 0));
+        const std::vector<bool> st = polish_windows(windows, opt);
+        for (int64_t w = 0; w < n_windows; ++w) {
+            const std::string& c = windows[static_cast<size_t>(w)]->consensus();
+            std::memcpy(cons_out + static_cast<size_t>(w) * static_cast<size_t>(stride), c.data(),
+                        std::min<size_t>(c.size(), static_cast<size_t>(stride)));
+            cons_len[w] = static_cast<int32_t>(c.size());
+            polished[w] = st[static_cast<size_t>(w)] ? 1 : 0;
+        }
+    } catch (const std::invalid_argument& e) {
+        std::fprintf(stderr, "[b200poa] %s\n", e.what());
+        return B200POA_INVALID_ARGUMENT;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "[b200poa] %s\n", e.what());
+        return B200POA_GENERIC_ERROR;
+    }
+    return B200POA_SUCCESS;
+}

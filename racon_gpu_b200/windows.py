@@ -114,15 +114,17 @@ def _mutate_many(truth: np.ndarray, errs: np.ndarray, rng: np.random.Generator):
     """
     W, L = truth.shape
     C = errs.shape[0]
-    e = errs.astype(np.float32)[None, :, None]
-    u = rng.random((W, C, L), dtype=np.float32)
+    # one uint16 decides the edit class, one uint8 supplies the substituted / inserted base
+    thr = np.round(errs * 65536.0 / 3.0).astype(np.int64)[None, :, None]
+    u = rng.integers(0, 65536, size=(W, C, L), dtype=np.uint16).astype(np.int64)
+    r8 = rng.integers(0, 256, size=(W, C, L), dtype=np.uint8)
     t = np.broadcast_to(truth[:, None, :], (W, C, L))
-    sub = u < e / 3.0
-    dele = (u >= e / 3.0) & (u < 2.0 * e / 3.0)
-    ins = (u >= 2.0 * e / 3.0) & (u < e)
-    shift = rng.integers(1, 4, size=(W, C, L), dtype=np.uint8)
+    sub = u < thr
+    dele = (u >= thr) & (u < 2 * thr)
+    ins = (u >= 2 * thr) & (u < 3 * thr)
+    shift = (r8 % 3 + 1).astype(np.uint8)
     emitted = np.where(sub, (t + shift) & 3, t).astype(np.uint8)
-    ins_base = rng.integers(0, 4, size=(W, C, L), dtype=np.uint8)
+    ins_base = ((r8 >> 4) & 3).astype(np.uint8)
     # each truth base emits 0 (deleted), 1, or 2 (base + inserted base) symbols
     count = np.where(dele, 0, np.where(ins, 2, 1)).astype(np.int64)
     empty = count.sum(axis=2) == 0  # a sequence must not be empty

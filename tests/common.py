@@ -1,0 +1,57 @@
+"""Shared helpers for the test-suite: golden fixtures and window builders."""
+from __future__ import annotations
+
+import gzip
+import json
+import os
+
+import numpy as np
+
+from racon_gpu_b200.windows import WindowBatch, synth_windows
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+M, X, G = 3, -5, -4  # racon scoring named by BASELINE.json
+
+
+def spoa_sample():
+    """(reads, qualities) of spoa's sample.fastq (tests/golden/make_golden.py)."""
+    with gzip.open(os.path.join(GOLDEN, "spoa_sample.fastq.gz"), "rt") as fh:
+        lines = [l.rstrip("\n") for l in fh]
+    reads = [lines[i + 1].encode() for i in range(0, len(lines) - 3, 4)]
+    quals = [lines[i + 3].encode() for i in range(0, len(lines) - 3, 4)]
+    return reads, quals
+
+
+def spoa_golden():
+    return json.load(open(os.path.join(GOLDEN, "spoa_golden.json")))
+
+
+def spoa_window(use_quality: bool) -> WindowBatch:
+    """spoa's GlobalConsensus test as one window: read 0 is the backbone, the rest full-span layers."""
+    reads, quals = spoa_sample()
+    L = len(reads[0])
+    win = []
+    for r, q in zip(reads, quals):
+        w = (np.frombuffer(q, dtype=np.uint8).astype(np.int16) - 33).astype(np.int8) if use_quality else None
+        win.append((r, w, 0, L - 1))
+    win[0] = (win[0][0], win[0][1] if use_quality else None, 0, 0)
+    return WindowBatch.from_lists([win])
+
+
+def ref_fixture(name: str):
+    """(WindowBatch, reference consensus untrimmed, reference consensus trimmed) for fixture `name`."""
+    z = np.load(os.path.join(GOLDEN, "ref_windows.npz"))
+    n, L, D, e1000, q, seed = [int(v) for v in z[name + "_params"]]
+    b = synth_windows(n, L, D, e1000 / 1000.0, seed=seed, with_quality=bool(q))
+    c0 = z[name + "_cons_0"].tobytes().split(b"\n")
+    c1 = z[name + "_cons_1"].tobytes().split(b"\n")
+    assert len(c0) == n and len(c1) == n
+    return b, c0, c1
+
+
+def identity_order(batch: WindowBatch) -> np.ndarray:
+    order = np.zeros(batch.n_seqs, dtype=np.int32)
+    for w in range(batch.n_windows):
+        s0, s1 = int(batch.win_seq_off[w]), int(batch.win_seq_off[w + 1])
+        order[s0:s1] = np.arange(s1 - s0)
+    return order

@@ -1,0 +1,38 @@
+"""ctypes loader of the host-flavour engine build (tests/emu/libpoa_emu.so; TEST INFRASTRUCTURE)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from oracle_lib import _flat_args, _p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class Emu:
+    def __init__(self):
+        subprocess.run(["make", "-s", "-C", os.path.join(HERE, "emu")], check=True,
+                       stdout=subprocess.DEVNULL)
+        self.lib = C.CDLL(os.path.join(HERE, "emu", "libpoa_emu.so"))
+
+    def polish(self, b, order, m, x, g, max_nodes=4096, max_edges=24576, max_len=1023, band=0,
+               serial_topsort=False, threads=8, stride=4096):
+        """Untrimmed consensus, coverage, status and DP cell count of the emulated engine."""
+        W = b.n_windows
+        cons = np.zeros((W, stride), dtype=np.uint8)
+        cov = np.zeros((W, stride), dtype=np.uint16)
+        clen = np.zeros(W, dtype=np.int32)
+        st = np.zeros(W, dtype=np.int32)
+        cells = C.c_int64(0)
+        order = np.ascontiguousarray(order, dtype=np.int32)
+        a = _flat_args(b)
+        self.lib.emu_polish_windows(
+            a[0], a[1], a[2], a[3], a[4], a[5], _p(order, C.c_int32), C.c_int32(m), C.c_int32(x), C.c_int32(g),
+            C.c_int32(max_nodes), C.c_int32(max_edges), C.c_int32(max_len), C.c_int32(band),
+            C.c_int32(int(serial_topsort)), C.c_int32(threads), _p(cons, C.c_uint8), _p(cov, C.c_uint16),
+            C.c_int32(stride), _p(clen, C.c_int32), _p(st, C.c_int32), None, None, C.byref(cells))
+        return ([cons[w, :clen[w]].tobytes() for w in range(W)], [cov[w, :clen[w]].copy() for w in range(W)],
+                st, cells.value)

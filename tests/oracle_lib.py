@@ -49,7 +49,7 @@ class Oracle:
         cov = np.zeros((W, stride), dtype=np.uint16)
         clen = np.zeros(W, dtype=np.int32)
         pol = np.zeros(W, dtype=np.uint8)
-        stats = np.zeros((W, 4), dtype=np.int64)
+        stats = np.zeros((W, 6), dtype=np.int64)
         order = np.ascontiguousarray(order, dtype=np.int32)
         self.lib.poa_oracle_polish_windows(
             *_flat_args(batch), _p(order, C.c_int32), C.c_int32(int(tgs)), C.c_int32(int(trim)),

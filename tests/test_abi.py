@@ -1,0 +1,65 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/b200poa.h declares."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+from racon_gpu_b200 import api
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "b200poa.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200poa_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = api.load_library()
+    names = declared_symbols()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(api.ABI_SYMBOLS) == names
+
+
+def test_config_default_follows_cudapoa_batchconfig():
+    """vendor/GenomeWorks/cudapoa/src/batch.cu:34-71 for racon's BatchConfig(1023, 200, 256, mode)."""
+    lib = api.load_library()
+    for mode, nodes in ((api.FULL_BAND, 3072), (api.STATIC_BAND, 4092)):
+        cfg = api.Config()
+        lib.b200poa_config_default(C.byref(cfg), 1023, 200, 256, mode)
+        assert cfg.max_sequence_size == 1023 and cfg.max_consensus_size == 2046
+        assert cfg.max_sequences_per_poa == 200 and cfg.alignment_band_width == 256
+        assert cfg.max_nodes_per_graph == nodes and cfg.band_mode == mode
+
+
+def test_layer_order_is_racons_sort(ref):
+    """src/window.cpp:78-85: libstdc++ introsort is unstable; 33 equal keys give 0,17,32,31,...."""
+    got = api.layer_order(np.zeros(33, dtype=np.int32))
+    assert got[:5].tolist() == [0, 17, 32, 31, 30]
+    assert sorted(got.tolist()) == list(range(33))
+    assert api.layer_order(np.zeros(17, dtype=np.int32)).tolist() == list(range(17))
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 3, 16, 17, 40, 201):
+        begins = rng.integers(0, 50, size=n).astype(np.int32)
+        got = api.layer_order(begins)
+        assert got[0] == 0 and sorted(got.tolist()) == list(range(n))
+        assert (np.diff(begins[got[1:]]) >= 0).all()
+        if ref.available:
+            assert got.tolist() == ref.layer_order(begins).tolist()
+
+
+def test_status_strings_and_invalid_arguments():
+    lib = api.load_library()
+    assert api.status_string(0) == "success" and api.status_string(1) == "exceeded_maximum_poas"
+    assert api.status_string(14) == "partial_span_unsupported"
+    handle = C.c_void_p()
+    cfg = api.Config()
+    lib.b200poa_config_default(C.byref(cfg), 1023, 200, 256, api.FULL_BAND)
+    # zero memory is a configuration error (Test_CudapoaBatch.cu: zero-memory batch throws)
+    st = lib.b200poa_batch_create(0, None, C.c_size_t(0), 1, C.byref(cfg), C.c_int16(-4), C.c_int16(-5), C.c_int16(3), C.byref(handle))
+    assert st == 15 and not handle.value
+    assert lib.b200poa_batch_total_poas(None) == 0

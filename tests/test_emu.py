@@ -1,0 +1,77 @@
+"""CPU: the engine's graph phases (racon_gpu_b200/csrc/poa_core.cuh, host flavour) against the oracle.
+
+The same source compiles into the CUDA kernel; here POA_LANES loops over 32 lanes so the parallel
+add_alignment, the per-root topological sort, the ballot traceback, the band definition and the
+consensus are checked bit-for-bit without a GPU.
+"""
+import numpy as np
+import pytest
+
+from common import G, M, X, identity_order, spoa_golden, spoa_window
+from emu_lib import Emu
+from racon_gpu_b200 import api
+from racon_gpu_b200.windows import edit_distance, synth_windows
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return Emu()
+
+
+@pytest.mark.parametrize("cfg", [(24, 500, 8, 0.05, False), (24, 500, 32, 0.15, False), (16, 400, 20, 0.12, True),
+                                 (4, 900, 40, 0.12, False), (12, 300, 60, 0.25, False)])
+@pytest.mark.parametrize("serial", [True, False])
+def test_full_band_is_bit_exact(emu, oracle, cfg, serial):
+    n, L, D, e, q = cfg
+    b = synth_windows(n, L, D, e, seed=31, with_quality=q)
+    order = api.processing_order(b)
+    oc, ocov, _ = oracle.polish(b, order, M, X, G, tgs=False, trim=False, threads=8)
+    ec, ecov, st, _ = emu.polish(b, order, M, X, G, band=0, serial_topsort=serial)
+    assert (st == 0).all()
+    assert ec == oc
+    assert all((a == c).all() for a, c in zip(ecov, ocov))
+
+
+def test_per_root_topsort_equals_serial_dfs_on_deep_windows(emu):
+    """Deep, noisy, quality-weighted windows: the decomposed sort must equal spoa's DFS order."""
+    b = synth_windows(8, 250, 150, 0.2, seed=8, with_quality=True)
+    order = api.processing_order(b)
+    a = emu.polish(b, order, M, X, G, serial_topsort=True)
+    c = emu.polish(b, order, M, X, G, serial_topsort=False)
+    assert (a[2] == 0).all() and a[0] == c[0]
+    assert all((x == y).all() for x, y in zip(a[1], c[1]))
+
+
+def test_spoa_known_answers(emu):
+    gold = spoa_golden()
+    sc = gold["scoring"]
+    for use_q, key in ((False, "GlobalConsensus"), (True, "GlobalConsensusWithQualities")):
+        b = spoa_window(use_q)
+        ec, _, st, _ = emu.polish(b, identity_order(b), sc["m"], sc["x"], sc["g"])
+        assert st[0] == 0 and ec[0].decode() == gold[key]
+
+
+def test_static_band_256_tolerance(emu, oracle):
+    """Banded mode is compared with the UNBANDED oracle.  Stated tolerance: >= 99% of
+    windows identical, per-window edit distance <= 2."""
+    for (n, L, D, e) in [(48, 500, 32, 0.15), (6, 900, 64, 0.12)]:
+        b = synth_windows(n, L, D, e, seed=17)
+        order = api.processing_order(b)
+        oc, _, _ = oracle.polish(b, order, M, X, G, tgs=False, trim=False, threads=8)
+        ec, _, st, cells = emu.polish(b, order, M, X, G, band=256)
+        assert (st == 0).all()
+        d = [edit_distance(a, c) for a, c in zip(oc, ec)]
+        assert sum(x == 0 for x in d) >= 0.99 * n and max(d) <= 2
+
+
+def test_limits_report_status_instead_of_crashing(emu):
+    b = synth_windows(4, 500, 32, 0.15, seed=3)
+    order = api.processing_order(b)
+    _, _, st, _ = emu.polish(b, order, M, X, G, max_nodes=700, max_edges=8000)
+    assert (st == 4).all()  # node_count_exceeded_maximum_graph_size
+    _, _, st, _ = emu.polish(b, order, M, X, G, max_nodes=4096, max_edges=1500)
+    assert (st == 5).all()  # edge_count_exceeded_maximum_graph_size
+    _, _, st, _ = emu.polish(b, order, M, X, G, max_len=400)
+    assert (st == 2).all()  # exceeded_maximum_sequence_size
+    _, _, st, _ = emu.polish(b, order, 120, -120, -120)
+    assert (st == 12).all()  # int16 score range

@@ -1,0 +1,179 @@
+"""GPU (-m gpu): the CUDA engine, called through the C ABI, against the oracle and the golden fixtures."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from common import G, M, X, identity_order, ref_fixture, spoa_golden, spoa_window
+from racon_gpu_b200 import api
+from racon_gpu_b200.windows import WindowBatch, edit_distance, synth_windows
+
+pytestmark = pytest.mark.gpu
+MEM = 6 << 30
+
+
+def gpu_untrimmed(b, banded=False, mem=MEM, **kw):
+    pb = api.PoaBatch(max_gpu_mem=mem, banded=banded, **kw)
+    n, _ = pb.add_windows(b)
+    assert n == b.n_windows
+    pb.generate_poa()
+    out = pb.get_consensus()
+    info = pb.info()
+    pb.close()
+    assert info["kernel_launches"] == 1
+    return out
+
+
+@pytest.mark.parametrize("cfg", [(64, 500, 8, 0.05, False), (96, 500, 32, 0.15, False), (48, 400, 20, 0.12, True),
+                                 (8, 900, 64, 0.12, False), (16, 300, 120, 0.2, True)])
+def test_full_band_bit_exact_vs_oracle(oracle, cfg):
+    n, L, D, e, q = cfg
+    b = synth_windows(n, L, D, e, seed=41, with_quality=q)
+    order = api.processing_order(b)
+    oc, ocov, _ = oracle.polish(b, order, M, X, G, tgs=False, trim=False, threads=16)
+    gc, gcov, st = gpu_untrimmed(b)
+    assert (st == 0).all()
+    assert gc == oc
+    assert all((a == c).all() for a, c in zip(gcov, ocov))
+
+
+@pytest.mark.parametrize("name", ["A", "C", "Q", "B"])
+@pytest.mark.parametrize("via_adapter", [False, True])
+def test_reference_fixtures_through_the_polisher_api(name, via_adapter):
+    """Whole job with host buffers against the committed outputs of the unmodified reference."""
+    b, ref_untrimmed, ref_trimmed = ref_fixture(name)
+    cons, clen, pol, status, _ = api.polish_windows(b, M, X, G, tgs=True, trim=True, mem_per_batch=MEM,
+                                                    via_adapter=via_adapter)
+    assert pol.all()
+    assert api.consensus_list(cons, clen) == ref_trimmed
+    cons, clen, pol, status, _ = api.polish_windows(b, M, X, G, tgs=False, trim=False, mem_per_batch=MEM,
+                                                    via_adapter=via_adapter)
+    assert api.consensus_list(cons, clen) == ref_untrimmed
+
+
+def test_spoa_known_answers_through_add_group():
+    """vendor/spoa/test/spoa_test.cpp:220-238,283-301 (5/-4/-8), entries in file order."""
+    gold = spoa_golden()
+    sc = gold["scoring"]
+    for use_q, key in ((False, "GlobalConsensus"), (True, "GlobalConsensusWithQualities")):
+        b = spoa_window(use_q)
+        seqs, wts, _, _ = b.window(0)
+        pb = api.PoaBatch(max_gpu_mem=MEM, gap=sc["g"], mismatch=sc["x"], match=sc["m"])
+        st, per = pb.add_poa_group([(s, w) for s, w in zip(seqs, wts)])
+        assert st == 0 and all(p == 0 for p in per)
+        pb.generate_poa()
+        cons, _, status = pb.get_consensus()
+        pb.close()
+        assert status[0] == 0 and cons[0].decode() == gold[key]
+
+
+def test_static_band_tolerance_vs_unbanded_oracle(oracle):
+    """BASELINE config 2 shape (500 bp x 32, 15%, band 256): >= 99% identical, edit distance <= 2."""
+    b = synth_windows(256, 500, 32, 0.15, seed=43)
+    order = api.processing_order(b)
+    oc, _, _ = oracle.polish(b, order, M, X, G, tgs=False, trim=False, threads=16)
+    gc, _, st = gpu_untrimmed(b, banded=True)
+    assert (st == 0).all()
+    d = [edit_distance(a, c) for a, c in zip(oc, gc)]
+    assert sum(x == 0 for x in d) >= 0.99 * len(d) and max(d) <= 2
+    # long-window stress shape (1024 x 64, 12%): the band is what makes it fit; same tolerance
+    b = synth_windows(8, 900, 64, 0.12, seed=44)
+    order = api.processing_order(b)
+    oc, _, _ = oracle.polish(b, order, M, X, G, tgs=False, trim=False, threads=16)
+    gc, _, st = gpu_untrimmed(b, banded=True)
+    d = [edit_distance(a, c) for a, c in zip(oc, gc)]
+    assert (st == 0).all() and max(d) <= 2
+
+
+def test_banded_gpu_equals_banded_emulation():
+    """The CUDA fill and its scalar twin must produce the same banded result bit for bit."""
+    from emu_lib import Emu
+    b = synth_windows(32, 700, 24, 0.15, seed=45)
+    order = api.processing_order(b)
+    ec, ecov, est, _ = Emu().polish(b, order, M, X, G, band=256, max_nodes=4092)
+    gc, gcov, st = gpu_untrimmed(b, banded=True)
+    assert (st == est).all() and gc == ec
+    assert all((a == c).all() for a, c in zip(gcov, ecov))
+
+
+def test_edge_cases_follow_the_reference_contract():
+    lib = api.load_library()
+    pb = api.PoaBatch(max_gpu_mem=MEM, max_sequences_per_poa=4)
+    # empty batch: generate/get are no-ops
+    pb.generate_poa()
+    assert pb.get_consensus()[0] == [] and pb.get_total_poas() == 0
+    # too long entry is skipped softly, too many entries too (cudapoa_batch.cuh:501-516)
+    long_seq = b"A" * 1100
+    st, per = pb.add_poa_group([(b"ACGTACGTAC", None), (b"ACGTACGTAC", None), (long_seq, None),
+                                (b"ACGAACGTAC", None), (b"ACGTACGTAC", None), (b"ACGTACGTAC", None)])
+    assert st == 0 and per == [0, 0, 2, 0, 0, 3]
+    # negative weights are an argument error (cudapoa_batch.cuh:533-537 throws)
+    st, _ = pb.add_poa_group([(b"ACGT", None), (b"ACGT", np.asarray([1, -1, 1, 1], dtype=np.int8)), (b"ACGT", None)])
+    assert st == 15
+    # identical reads: consensus == read (Test_CudapoaBatch.cu)
+    st, _ = pb.add_poa_group([(b"ACGTTGCAACGT", None)] * 4)
+    assert st == 0 and pb.get_total_poas() == 2
+    pb.generate_poa()
+    cons, cov, status = pb.get_consensus()
+    assert status.tolist() == [0, 0] and cons[1] == b"ACGTTGCAACGT" and (cov[1] == 4).all()
+    # reset then reuse
+    pb.reset()
+    assert pb.get_total_poas() == 0
+    st, _ = pb.add_poa_group([(b"ACGTTGCAACGT", None)] * 3)
+    pb.generate_poa()
+    cons, _, status = pb.get_consensus()
+    assert cons == [b"ACGTTGCAACGT"] and status[0] == 0
+    pb.close()
+
+
+def test_short_windows_and_partial_spans_are_reported_not_guessed():
+    """< 3 sequences: backbone + false (window.cpp:68-71).  Partial-span layers (window.cpp:96-103)
+    are not aligned on the device yet: the window is handed back to the caller's CPU path."""
+    two = [(b"ACGTACGTAC", None, 0, 0), (b"ACGTTCGTAC", None, 0, 9)]
+    bb = b"ACGTACGTACGGTTAACCGGTTAACCGGTTAAACGTACGTACGGTTAACCGGTTAACCGGTTAAACGTACGTACGGTTAACCGGTTAACCGGTTAAACGTACGTACGGTTAACCGGTTAACCGGTTAA"
+    partial = [(bb, None, 0, 0), (bb, None, 0, len(bb) - 1), (bb[10:60], None, 10, 60), (bb, None, 0, len(bb) - 1)]
+    b = WindowBatch.from_lists([two, partial])
+    cons, clen, pol, status, _ = api.polish_windows(b, M, X, G, mem_per_batch=MEM)
+    assert not pol[0] and api.consensus_list(cons, clen)[0] == b"ACGTACGTAC"
+    assert not pol[1] and status[1] == api.PARTIAL_SPAN_UNSUPPORTED
+
+
+def test_batch_full_backpressure_and_multi_batch_concurrency(oracle):
+    """exceeded_maximum_poas back-pressure (cudapoa_batch.cuh:122-125) and the End2End pattern of
+    2 and 4 concurrent batches (Test_CudapoaBatchEnd2End.cu:39-91): results must not depend on how
+    windows are split into batches."""
+    b = synth_windows(300, 500, 12, 0.1, seed=47)
+    order = api.processing_order(b)
+    oc, _, _ = oracle.polish(b, order, M, X, G, tgs=True, trim=True, threads=16)
+    base = None
+    for batches, cap in ((1, 0), (2, 37), (4, 16)):
+        cons, clen, pol, status, launches = api.polish_windows(b, M, X, G, mem_per_batch=3 << 30, batches_per_device=batches,
+                                                               max_windows_per_round=cap)
+        got = api.consensus_list(cons, clen)
+        assert pol.all() and got == oc
+        assert launches >= (1 if cap == 0 else 300 // cap)
+    # a batch whose arena is tiny must accept a prefix and report it
+    pb = api.PoaBatch(max_gpu_mem=MEM)
+    cap = pb.info()["arena_capacity"]
+    n, _ = pb.add_windows(b)
+    assert n == 300 and cap > 0
+    pb.close()
+
+
+def test_ten_thousand_windows_are_deterministic_across_batch_splits():
+    """BASELINE config 2 at full size (10k windows): a checksum of all consensus strings must not
+    depend on the batch split, and windows that are duplicates must give identical consensus."""
+    b = synth_windows(5000, 500, 32, 0.15, seed=49)
+    # duplicate the set so that window i and i+5000 are identical inputs
+    dup = WindowBatch(
+        win_seq_off=np.concatenate([b.win_seq_off, b.win_seq_off[1:] + b.win_seq_off[-1]]),
+        seq_off=np.concatenate([b.seq_off, b.seq_off[1:] + b.seq_off[-1]]),
+        bases=np.concatenate([b.bases, b.bases]), weights=np.concatenate([b.weights, b.weights]),
+        has_weights=np.concatenate([b.has_weights, b.has_weights]),
+        begins=np.concatenate([b.begins, b.begins]), ends=np.concatenate([b.ends, b.ends]))
+    c1, l1, p1, _, _ = api.polish_windows(dup, M, X, G, banded=True, mem_per_batch=24 << 30)
+    c2, l2, p2, _, _ = api.polish_windows(dup, M, X, G, banded=True, mem_per_batch=24 << 30, batches_per_device=3,
+                                          max_windows_per_round=777)
+    assert p1.all() and p2.all()
+    assert (l1 == l2).all() and (c1 == c2).all()
+    assert (l1[:5000] == l1[5000:]).all() and (c1[:5000] == c1[5000:]).all()
