@@ -49,16 +49,21 @@ struct KernelArgs {
     uint16_t* out_cov;
     int32_t* out_len;
     int32_t* out_status;
-    int32_t prof_stride;
+    int32_t prof_stride; /* int16 cells per profile row  */
+    int32_t ring_stride; /* int16 cells per ring row     */
+    int32_t ring_rows;   /* power of two                 */
 };
 
-__global__ void __launch_bounds__(32) poa_window_kernel(const KernelArgs a) {
+__global__ void __launch_bounds__(32, 16) poa_window_kernel(const KernelArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Slot s;
     slot_bind(s, a.slab + (size_t)blockIdx.x * a.slot_bytes, a.p, nullptr);
     CudaFill fill;
     fill.prof = reinterpret_cast<int16_t*>(smem_raw);
     fill.prof_stride = a.prof_stride;
+    fill.ring = fill.prof + PROF_ROWS * a.prof_stride;
+    fill.ring_stride = a.ring_stride;
+    fill.ring_mask = a.ring_rows - 1;
     fill.dyn_code = -1;
     const int lane = threadIdx.x & 31;
     for (;;) {
@@ -132,7 +137,11 @@ struct b200poa_batch {
     size_t slot_bytes = 0;
     int32_t smem_bytes = 0;
     int32_t prof_stride = 0;
+    int32_t ring_stride = 0;
+    int32_t ring_rows = 0;
     int32_t blocks_per_sm = 0;
+    int32_t sm_count = 0;
+    int32_t max_len_staged = 0;
     size_t device_bytes = 0;
     /* pinned host staging */
     uint8_t* h_bases = nullptr;
@@ -206,6 +215,10 @@ static int32_t stage_window(b200poa_batch* b, int32_t n, Get get, int32_t* per_s
         const char* seq; const int8_t* w; int32_t len, bg, en;
         get(i, seq, w, len, bg, en);
         if (len <= b->cfg.max_sequence_size && n_ok < b->cfg.max_sequences_per_poa) {
+            if (len <= 0) return B200POA_INVALID_ARGUMENT;
+            if (w) /* validate BEFORE anything is staged (cudapoa_batch.cuh:533-537 throws) */
+                for (int32_t k = 0; k < len; ++k)
+                    if (w[k] < 0) return B200POA_INVALID_ARGUMENT;
             bytes += len;
             ++n_ok;
         }
@@ -224,10 +237,6 @@ static int32_t stage_window(b200poa_batch* b, int32_t n, Get get, int32_t* per_s
         else if (added >= b->cfg.max_sequences_per_poa) st = B200POA_EXCEEDED_MAXIMUM_SEQUENCES_PER_POA; /* :513-516 */
         if (per_seq_status) per_seq_status[i] = st;
         if (st != B200POA_SUCCESS) continue;
-        if (w) {
-            for (int32_t k = 0; k < len; ++k)
-                if (w[k] < 0) return B200POA_INVALID_ARGUMENT; /* cudapoa_batch.cuh:533-537 throws */
-        }
         if (added == 0) {
             bb_len = len;
         } else if (!(bg == -1 && en == -1)) {
@@ -236,6 +245,7 @@ static int32_t stage_window(b200poa_batch* b, int32_t n, Get get, int32_t* per_s
             const uint32_t offset = (uint32_t)(0.01 * L);
             if (!((uint32_t)bg < offset && (uint32_t)en > L - offset)) flag = B200POA_PARTIAL_SPAN_UNSUPPORTED;
         }
+        if (len > b->max_len_staged) b->max_len_staged = len;
         std::memcpy(b->h_bases + b->base_count, seq, (size_t)len);
         if (w) std::memcpy(b->h_weights + b->base_count, w, (size_t)len);
         else std::memset(b->h_weights + b->base_count, 1, (size_t)len); /* cudapoa_batch.cuh:525-530 */
@@ -377,14 +387,15 @@ int32_t b200poa_batch_create(int32_t device_id, void* stream, size_t max_gpu_mem
 
     Slot probe;
     slot_bind(probe, nullptr, p, &b->slot_bytes);
-    b->prof_stride = colsP;
-    b->smem_bytes = PROF_ROWS * colsP * (int32_t)sizeof(int16_t);
-
     cudaDeviceProp prop;
     CU_TRY(cudaGetDeviceProperties(&prop, device_id));
-    CU_TRY(cudaFuncSetAttribute(poa_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes));
+    b->sm_count = prop.multiProcessorCount;
+    /* worst-case shared memory (longest admissible read) must be launchable */
+    CU_TRY(cudaFuncSetAttribute(poa_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                PROF_ROWS * colsP * (int32_t)sizeof(int16_t) + 16384));
+    /* slots are sized for the best occupancy a launch can reach (short reads => small profile) */
     int blocks_per_sm = 0;
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, poa_window_kernel, 32, b->smem_bytes));
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, poa_window_kernel, 32, 4096));
     if (const char* env = std::getenv("B200POA_BLOCKS_PER_SM")) {
         int v = std::atoi(env);
         if (v > 0 && v < blocks_per_sm) blocks_per_sm = v;
@@ -523,8 +534,24 @@ int32_t b200poa_batch_launch(b200poa_batch* b) {
     a.out_cov = b->d_cov;
     a.out_len = b->d_len;
     a.out_status = b->d_status;
+    /* shared memory geometry follows the longest read actually staged */
+    const int32_t colsP = (b->max_len_staged + 1 + 7) & ~7;
+    b->prof_stride = colsP;
+    b->ring_stride = (b->p.band_width > 0 && b->p.band_width < colsP) ? b->p.band_width : colsP;
+    int32_t ring_bytes = 8192;
+    if (const char* env = std::getenv("B200POA_RING_BYTES")) ring_bytes = std::atoi(env);
+    int32_t rows = 2;
+    while (rows < 32 && rows * 2 * b->ring_stride * (int32_t)sizeof(int16_t) <= ring_bytes) rows *= 2;
+    b->ring_rows = rows;
+    b->smem_bytes = (PROF_ROWS * b->prof_stride + b->ring_rows * b->ring_stride) * (int32_t)sizeof(int16_t);
+    int occ = 0;
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, poa_window_kernel, 32, (size_t)b->smem_bytes));
+    if (occ < 1) return B200POA_INVALID_ARGUMENT;
+    b->blocks_per_sm = std::min(occ, b->n_slots / std::max(b->sm_count, 1) > 0 ? occ : occ);
     a.prof_stride = b->prof_stride;
-    const int grid = std::min(b->n_slots, b->poa_count);
+    a.ring_stride = b->ring_stride;
+    a.ring_rows = b->ring_rows;
+    const int grid = std::min(std::min(b->n_slots, occ * b->sm_count), b->poa_count);
     poa_window_kernel<<<grid, 32, (size_t)b->smem_bytes, b->stream>>>(a);
     CU_TRY(cudaGetLastError());
     b->launches += 1;
@@ -572,6 +599,7 @@ int32_t b200poa_batch_reset(b200poa_batch* b) {
     b->base_count = 0;
     b->cost.clear();
     b->uploaded = false;
+    b->max_len_staged = 0;
     return B200POA_SUCCESS;
 }
 

@@ -92,7 +92,7 @@ struct Slot {
     uint8_t* aln_cnt;   /* [MN] number of aligned nodes                      */
     uint16_t* aln;      /* [MN*KA] aligned node ids in insertion order       */
     uint16_t* root;     /* [MN] topological-sort root of the node            */
-    uint16_t* lpos;     /* [MN] scratch: position inside the root's DFS      */
+    uint16_t* lpos;     /* [MN] position of the node inside its root's DFS order */
     uint16_t* rank_of;  /* [MN] node -> rank                                 */
     uint16_t* node_at;  /* [MN] rank -> node                                 */
     uint16_t* e_src;    /* [ME] */
@@ -100,10 +100,9 @@ struct Slot {
     uint16_t* e_next;   /* [ME] next in-edge of e_dst, insertion order       */
     int32_t* e_w;       /* [ME] total weight                                 */
     /* per-read "row program": the graph linearised in rank order (row = rank + 1) */
-    uint32_t* row_info; /* [MN+1] code | sink<<8 | npred<<16                 */
+    uint32_t* row_rec;  /* [MN+1] packed row record, see rec_make()                */
     uint32_t* row_poff; /* [MN+2] offset of the row's predecessor list       */
     uint32_t* row_pred; /* [ME+MN] predecessor ROW index (0 = virtual row) | its band start << 16, in in-edge order */
-    uint16_t* row_bs;   /* [MN+1] first column of the row's band             */
     /* scores */
     int16_t* S;         /* [(MN+1)*stride]                                   */
     /* traceback output, written back to front */
@@ -114,6 +113,7 @@ struct Slot {
     uint32_t* cnt;      /* [MN+1] nodes per root                             */
     uint32_t* roff;     /* [MN+1] output offset per root / stack offset      */
     uint32_t* need;     /* [MN+1] stack need per root                        */
+    uint8_t* dirty;     /* [MN+1] root needs its DFS redone after this read   */
     uint8_t* marks;     /* [MN] */
     uint8_t* check;     /* [MN] */
     uint16_t* stack;    /* [ME+2*MN*? ] see slot layout                      */
@@ -160,16 +160,16 @@ void slot_bind(Slot& s, uint8_t* base, const Params& p, size_t* total_out) {
     POA_CARVE(e_dst, uint16_t, ME);
     POA_CARVE(e_next, uint16_t, ME);
     POA_CARVE(e_w, int32_t, ME);
-    POA_CARVE(row_info, uint32_t, MN + 1);
+    POA_CARVE(row_rec, uint32_t, MN + 1 + 64); /* +64: the fill prefetches 32-row blocks past the end */
     POA_CARVE(row_poff, uint32_t, MN + 2);
     POA_CARVE(row_pred, uint32_t, ME + MN);
-    POA_CARVE(row_bs, uint16_t, MN + 1);
     POA_CARVE(tb_node, int16_t, MN + ML + 2);
     POA_CARVE(tb_pos, int16_t, MN + ML + 2);
     POA_CARVE(asg, int32_t, ML + 1);
     POA_CARVE(cnt, uint32_t, MN + 1);
     POA_CARVE(roff, uint32_t, MN + 1);
     POA_CARVE(need, uint32_t, MN + 1);
+    POA_CARVE(dirty, uint8_t, MN + 1);
     POA_CARVE(marks, uint8_t, MN);
     POA_CARVE(check, uint8_t, MN);
     POA_CARVE(stack, uint16_t, ME + (KA + 2) * MN);
@@ -219,6 +219,9 @@ POA_FN void init_backbone(const Slot& s, const Params& p, WinState& st, const ui
             s.cov[k] = (len >= 2) ? 1 : 0; /* Node::coverage counts edge labels (graph.cpp:44-58) */
             s.aln_cnt[k] = 0;
             s.root[k] = (uint16_t)k;
+            s.lpos[k] = 0;
+            s.cnt[k] = 1;
+            s.dirty[k] = 0;
             s.rank_of[k] = (uint16_t)k;
             s.node_at[k] = (uint16_t)k;
             if (k > 0) { /* edge k-1 : (k-1) -> k */
@@ -241,6 +244,30 @@ POA_FN void init_backbone(const Slot& s, const Params& p, WinState& st, const ui
  * Band: static, centred on the (0,0)-(N,len) diagonal like cudapoa_nw_banded.cuh:35-55, but
  * snapped to 8-cell lanes so a row shift is a whole-lane shift.
  * ---------------------------------------------------------------------------------------- */
+/* Packed row record (one u32 per row, read 32 rows at a time by the fill and distributed by
+ * shuffle):  code[0:8) | sink[8] | profile row[9:12) | pred0-is-previous-row[12] | npred[13:21) |
+ * band start / 8 [21:32). */
+POA_FN uint32_t rec_make(int32_t code, bool sink, int32_t prow, bool p0prev, int32_t npred, int32_t bs) {
+    return (uint32_t)code | (sink ? 0x100u : 0u) | ((uint32_t)prow << 9) | (p0prev ? 0x1000u : 0u) |
+           ((uint32_t)npred << 13) | ((uint32_t)(bs >> 3) << 21);
+}
+POA_FN int32_t rec_code(uint32_t r) { return (int32_t)(r & 0xFFu); }
+POA_FN bool rec_sink(uint32_t r) { return (r & 0x100u) != 0; }
+POA_FN int32_t rec_prow(uint32_t r) { return (int32_t)((r >> 9) & 7u); }
+POA_FN bool rec_p0prev(uint32_t r) { return (r & 0x1000u) != 0; }
+POA_FN int32_t rec_npred(uint32_t r) { return (int32_t)((r >> 13) & 0xFFu); }
+POA_FN int32_t rec_bs(uint32_t r) { return (int32_t)(r >> 21) << 3; }
+POA_FN int32_t prof_row_of(int32_t code) { /* A,C,G,T -> 0..3, N -> 4, anything else -> 5 (built on demand) */
+    switch (code) {
+        case 'A': return 0;
+        case 'C': return 1;
+        case 'G': return 2;
+        case 'T': return 3;
+        case 'N': return 4;
+        default: return 5;
+    }
+}
+
 struct ReadGeom {
     int32_t len;    /* read length                                    */
     int32_t colsP;  /* (len+1) rounded up to a multiple of 8          */
@@ -269,10 +296,9 @@ POA_FN int32_t band_start(const ReadGeom& g, int32_t row, int32_t n_rows) {
 POA_FN void build_program(const Slot& s, const Params& p, WinState& st, const ReadGeom& g) {
     const int32_t N = st.n_nodes;
     int32_t run = 0; /* running predecessor offset (uniform) */
-    POA_LANE0 {
-        s.row_info[0] = 0;
-        s.row_bs[0] = 0;
-    }
+    POA_LANE0 { s.row_rec[0] = 0; }
+    PerLane<int> wide;
+    POA_LANES(l) { wide[l] = 0; }
     for (int32_t base = 0; base < N; base += 32) {
         PerLane<int> c;
         POA_LANES(l) {
@@ -293,30 +319,43 @@ POA_FN void build_program(const Slot& s, const Params& p, WinState& st, const Re
             const int32_t o = run + off[l];
             s.row_poff[r + 1] = (uint32_t)o;
             const int32_t d = s.nin[v];
+            int32_t first = 0;
             if (d == 0) {
                 s.row_pred[o] = 0;
             } else {
                 int32_t k = 0;
                 for (uint16_t e = s.in_head[v]; e != NONE16; e = s.e_next[e], ++k) {
                     const int32_t pr = s.rank_of[s.e_src[e]] + 1;
+                    if (k == 0) first = pr;
                     s.row_pred[o + k] = (uint32_t)pr | ((uint32_t)band_start(g, pr, N) << 16);
                 }
             }
-            s.row_info[r + 1] = (uint32_t)s.code[v] | ((s.nout[v] == 0) ? 0x100u : 0u) |
-                                ((uint32_t)c[l] << 16);
-            s.row_bs[r + 1] = (uint16_t)band_start(g, r + 1, N);
+            if (c[l] > 255) wide[l] = 1;
+            const int32_t code = s.code[v];
+            s.row_rec[r + 1] = rec_make(code, s.nout[v] == 0, prof_row_of(code), first == r, c[l] & 0xFF,
+                                        band_start(g, r + 1, N));
         }
         run += tot;
     }
     POA_LANE0 { s.row_poff[N + 1] = (uint32_t)run; }
+    if (warp_ballot(wide)) st.status = ST_EDGE_COUNT_EXCEEDED; /* in-degree > 255 does not fit the record */
     POA_SYNC();
+    (void)p;
 }
 
 /* Score accessor used by the traceback (and by the scalar fill): cells outside the row's band
  * read as NEG (cudapoa_nw_banded.cuh:103-116 does the same with min_score_value). */
 POA_FN int32_t score_at(const Slot& s, const Params& p, const ReadGeom& g, int32_t row, int32_t col) {
     if (col < 0) return NEG;
-    const int32_t bs = s.row_bs[row];
+    const int32_t bs = rec_bs(s.row_rec[row]);
+    const int32_t o = col - bs;
+    if (o < 0 || o >= g.bw) return NEG;
+    return s.S[(size_t)row * p.stride + o];
+}
+
+/* score accessor when the row's band start is already known (row_pred carries it) */
+POA_FN int32_t score_at_bs(const Slot& s, const Params& p, const ReadGeom& g, int32_t row, int32_t bs, int32_t col) {
+    if (col < 0) return NEG;
     const int32_t o = col - bs;
     if (o < 0 || o >= g.bw) return NEG;
     return s.S[(size_t)row * p.stride + o];
@@ -325,7 +364,15 @@ POA_FN int32_t score_at(const Slot& s, const Params& p, const ReadGeom& g, int32
 /* ------------------------------------------------------------------------------------------
  * Phase 3: traceback  (sisd_alignment_engine.cpp:340-431)
  *   priority: diagonal over in-edges in order, vertical over in-edges in order, horizontal.
- *   Lanes test different predecessors; the first match is the lowest set ballot bit.
+ *
+ *   Fast path: the first test spoa makes at a cell is "diagonal through in-edge 0".  Lane l
+ *   speculates that the previous l steps all took that move AND that in-edge 0 was the previous
+ *   row, i.e. that the path sits on (i-l, j-l); it checks its own cell against lane l+1's cell.
+ *   The number of leading lanes whose check holds is the length of a run of steps that is
+ *   resolved with ONE round of (independent) loads instead of one dependent round per step.
+ *   Slow path (first lane fails): the general rule, predecessors tested by different lanes and
+ *   the first match taken by ballot.
+ *   The current cell value is carried along (S[p][j-1] = S[i][j] - prof etc.), never re-read.
  *   Output: tb_node/tb_pos filled back to front; returns the index of the first (leftmost) entry.
  * ---------------------------------------------------------------------------------------- */
 POA_FN int32_t traceback(const Slot& s, const Params& p, WinState& st, const ReadGeom& g,
@@ -335,20 +382,77 @@ POA_FN int32_t traceback(const Slot& s, const Params& p, WinState& st, const Rea
     int32_t i = end_row, j = g.len;
     const int32_t mg = p.match - p.gap, xg = p.mismatch - p.gap;
     int32_t guard = p.max_nodes + p.max_len + 4;
+    int32_t cur = score_at(s, p, g, i, j);
     while (!(i == 0 && j == 0)) {
-        if (--guard < 0 || w <= 0) {
+        if (--guard < 0 || w <= 32) {
             st.status = ST_TRACEBACK_LOST;
             return cap;
         }
-        int32_t ni = i, nj = j;
-        if (i == 0) {
-            nj = j - 1; /* first row: S[0][*] == 0, only horizontal moves */
-        } else {
-            const int32_t cur = score_at(s, p, g, i, j);
-            const uint32_t info = s.row_info[i];
-            const int32_t np = (int32_t)(info >> 16);
+        if (i == 0) { /* first row: S[0][*] == 0, only horizontal moves are left */
+            for (int32_t b = 0; b < j; b += 32) {
+                POA_LANES(l) {
+                    const int32_t jj = j - b - l;
+                    if (jj >= 1 && w - 1 - b - l >= 0) {
+                        s.tb_node[w - 1 - b - l] = -1;
+                        s.tb_pos[w - 1 - b - l] = (int16_t)(jj - 1);
+                    }
+                }
+            }
+            w -= j;
+            j = 0;
+            if (w < 0) {
+                st.status = ST_TRACEBACK_LOST;
+                return cap;
+            }
+            break;
+        }
+        /* ---- fast path: run of "diagonal via in-edge 0 == previous row" steps ---- */
+        PerLane<int> val, flag, nodeid;
+        POA_LANES(l) {
+            const int32_t ii = i - l, jj = j - l;
+            val[l] = NEG;
+            flag[l] = 0;
+            nodeid[l] = 0;
+            if (ii >= 0 && jj >= 0) {
+                const uint32_t rec = s.row_rec[ii];
+                val[l] = (l == 0) ? cur : score_at_bs(s, p, g, ii, rec_bs(rec), jj);
+                if (ii >= 1 && jj >= 1) {
+                    const int32_t prof = (rec_code(rec) == (int32_t)read[jj - 1]) ? mg : xg;
+                    flag[l] = rec_p0prev(rec) ? (prof + 1000000) : 0; /* carries prof to the check */
+                    nodeid[l] = s.node_at[ii - 1];
+                }
+            }
+        }
+        PerLane<int> nxt;
+        warp_shift_down1(val, nxt);
+        PerLane<int> ok;
+        POA_LANES(l) {
+            ok[l] = (l < 31 && flag[l] != 0 && val[l] > NEG && nxt[l] > NEG &&
+                     val[l] == nxt[l] + (flag[l] - 1000000)) ? 1 : 0;
+        }
+        const unsigned okm = warp_ballot(ok);
+        const int32_t k = (okm == 0xFFFFFFFFu) ? 32 : poa_ffs(~okm);
+        if (k > 0) {
+            POA_LANES(l) {
+                if (l < k) {
+                    s.tb_node[w - 1 - l] = (int16_t)nodeid[l];
+                    s.tb_pos[w - 1 - l] = (int16_t)(j - l - 1);
+                }
+            }
+            w -= k;
+            i -= k;
+            j -= k;
+            cur = warp_get(val, k);
+            guard -= (k - 1);
+            continue;
+        }
+        /* ---- slow path: the general rule at (i, j) ---- */
+        int32_t ni = i, nj = j, ncur = cur;
+        {
+            const uint32_t rec = s.row_rec[i];
+            const int32_t np = rec_npred(rec);
             const int32_t po = (int32_t)s.row_poff[i];
-            const int32_t prof = (j > 0 && (uint8_t)(info & 0xFF) == read[j - 1]) ? mg : xg;
+            const int32_t prof = (j > 0 && rec_code(rec) == (int32_t)read[j - 1]) ? mg : xg;
             int32_t found = 0;
             for (int32_t b = 0; b < np && !found; b += 32) {
                 PerLane<int> dm, vm, pr;
@@ -357,10 +461,12 @@ POA_FN int32_t traceback(const Slot& s, const Params& p, WinState& st, const Rea
                     vm[l] = 0;
                     pr[l] = 0;
                     if (b + l < np) {
-                        const int32_t pi = (int32_t)(s.row_pred[po + b + l] & 0xFFFFu);
+                        const uint32_t pe = s.row_pred[po + b + l];
+                        const int32_t pi = (int32_t)(pe & 0xFFFFu);
+                        const int32_t pbs = (int32_t)(pe >> 16);
                         pr[l] = pi;
-                        dm[l] = (j > 0) && (score_at(s, p, g, pi, j - 1) + prof == cur);
-                        vm[l] = (score_at(s, p, g, pi, j) + p.gap == cur);
+                        dm[l] = (j > 0) && (score_at_bs(s, p, g, pi, pbs, j - 1) + prof == cur);
+                        vm[l] = (score_at_bs(s, p, g, pi, pbs, j) + p.gap == cur);
                     }
                 }
                 /* diagonal matches of ALL predecessors come before any vertical match, so a
@@ -370,12 +476,14 @@ POA_FN int32_t traceback(const Slot& s, const Params& p, WinState& st, const Rea
                 if (dmask) {
                     ni = warp_get(pr, poa_ffs(dmask));
                     nj = j - 1;
+                    ncur = cur - prof;
                     found = 1;
                 } else if (np <= 32) {
                     const unsigned vmask = warp_ballot(vm);
                     if (vmask) {
                         ni = warp_get(pr, poa_ffs(vmask));
                         nj = j;
+                        ncur = cur - p.gap;
                         found = 1;
                     }
                 }
@@ -387,21 +495,23 @@ POA_FN int32_t traceback(const Slot& s, const Params& p, WinState& st, const Rea
                         vm[l] = 0;
                         pr[l] = 0;
                         if (b + l < np) {
-                            const int32_t pi = (int32_t)(s.row_pred[po + b + l] & 0xFFFFu);
+                            const uint32_t pe = s.row_pred[po + b + l];
+                            const int32_t pi = (int32_t)(pe & 0xFFFFu);
                             pr[l] = pi;
-                            vm[l] = (score_at(s, p, g, pi, j) + p.gap == cur);
+                            vm[l] = (score_at_bs(s, p, g, pi, (int32_t)(pe >> 16), j) + p.gap == cur);
                         }
                     }
                     const unsigned vmask = warp_ballot(vm);
                     if (vmask) {
                         ni = warp_get(pr, poa_ffs(vmask));
                         nj = j;
+                        ncur = cur - p.gap;
                         found = 1;
                     }
                 }
             }
             if (!found) {
-                if (j > 0 && score_at(s, p, g, i, j - 1) == cur) {
+                if (j > 0 && score_at_bs(s, p, g, i, rec_bs(rec), j - 1) == cur) {
                     nj = j - 1;
                 } else {
                     st.status = ST_TRACEBACK_LOST;
@@ -416,6 +526,7 @@ POA_FN int32_t traceback(const Slot& s, const Params& p, WinState& st, const Rea
         }
         i = ni;
         j = nj;
+        cur = ncur;
     }
     POA_SYNC();
     return w;
@@ -489,6 +600,9 @@ POA_FN void add_alignment(const Slot& s, const Params& p, WinState& st, const ui
             s.in_tail[v] = NONE16;
             s.cov[v] = 0;
             s.aln_cnt[v] = 0;
+            s.cnt[v] = 0;   /* v may become a root itself */
+            s.dirty[v] = 0;
+            s.lpos[v] = 0;
             s.root[v] = NONE16; /* resolved in (c) */
             if (a <= -2) {      /* graph.cpp:226-237: join x's clique */
                 const int32_t x = -2 - a;
@@ -546,7 +660,7 @@ POA_FN void add_alignment(const Slot& s, const Params& p, WinState& st, const ui
                 if ((int32_t)s.root[u] < r) r = s.root[u];
                 break;
             }
-            s.lpos[v] = (uint16_t)r; /* stage: root[] of run members is still NONE16 for the others */
+            s.roff[v] = (uint32_t)r; /* stage: root[] of run members is still NONE16 for the others */
         }
     }
     POA_SYNC();
@@ -557,8 +671,11 @@ POA_FN void add_alignment(const Slot& s, const Params& p, WinState& st, const ui
             const int32_t a = s.asg[pos];
             if (!(a & 0x40000000)) continue;
             const int32_t v = a & 0x3FFFFFFF;
-            if (s.root[v] == NONE16) s.root[v] = s.lpos[v];
+            if (s.root[v] == NONE16) s.root[v] = (uint16_t)s.roff[v];
             s.asg[pos] = v;
+            /* bookkeeping of the per-root topological sort: one more member, DFS must be redone */
+            poa_atomic_add(&s.cnt[s.root[v]], 1u);
+            s.dirty[s.root[v]] = 1;
         }
     }
     POA_SYNC();
@@ -613,6 +730,7 @@ POA_FN void add_alignment(const Slot& s, const Params& p, WinState& st, const ui
                 s.in_tail[cur] = (uint16_t)e;
                 s.nin[cur] = (uint16_t)(s.nin[cur] + 1);
                 s.nout[prev] = (uint16_t)(s.nout[prev] + 1);
+                if (s.root[prev] == s.root[cur]) s.dirty[s.root[cur]] = 1;
             }
         }
         n_edges += tot;
@@ -692,63 +810,63 @@ POA_FN void topsort_serial(const Slot& s, const Params& p, WinState& st) {
 }
 
 /* ------------------------------------------------------------------------------------------
- * Phase 5b: per-root topological sort.
+ * Phase 5b: per-root, incremental topological sort.
  *   spoa's outer loop visits ids in increasing order; the DFS started at i emits exactly the
  *   not-yet-emitted members of i's ancestor closure (in-edges + aligned cliques), i.e. the nodes
  *   with root[v] == i, and it only needs to know WHICH other nodes are already emitted
- *   (root[u] < i), not their order.  Hence DFS_i for different i are independent:
- *     1. cnt[i]  = |{v : root[v] == i}|, need[i] = stack bound for DFS_i
- *     2. roff    = exclusive prefix sums (output offset, stack offset)
- *     3. 32 roots at a time: singleton roots are written directly, the others run spoa's DFS
- *        restricted to their own nodes.
+ *   (root[u] < i), not their order.  Hence rank(v) = (number of nodes with a smaller root) +
+ *   (position of v inside DFS_root), and DFS_i only changes when root i gains a node or an
+ *   internal edge -- add_alignment marks exactly those roots dirty.  Per read:
+ *     1. nodes of dirty roots: reset DFS marks, accumulate the root's stack bound;
+ *     2. 32 roots at a time: prefix-sum the member counts; dirty multi-node roots re-run spoa's
+ *        DFS restricted to their own members and store each member's position (lpos);
+ *     3. every node: rank = offset[root] + lpos.
  * ---------------------------------------------------------------------------------------- */
 POA_FN void topsort_roots(const Slot& s, const Params& p, WinState& st) {
     const int32_t N = st.n_nodes;
     for (int32_t base = 0; base < N; base += 32) {
         POA_LANES(l) {
-            if (base + l < N) {
-                s.cnt[base + l] = 0;
-                s.need[base + l] = 0;
-                s.marks[base + l] = 0;
-                s.check[base + l] = 1;
-            }
+            if (base + l < N) s.need[base + l] = 0;
         }
     }
     POA_SYNC();
-    /* 1. histogram by root (lanes of one step may hit the same root: atomic adds) */
+    /* 1. members of dirty roots */
     for (int32_t base = 0; base < N; base += 32) {
         POA_LANES(l) {
             const int32_t v = base + l;
             if (v >= N) continue;
             const int32_t r = s.root[v];
-            poa_atomic_add(&s.cnt[r], 1u);
+            if (!s.dirty[r]) continue;
+            s.marks[v] = 0;
+            s.check[v] = 1;
             poa_atomic_add(&s.need[r], (uint32_t)(s.nin[v] + s.aln_cnt[v] + 1));
         }
     }
     POA_SYNC();
-    /* 2 + 3. walk the roots in id order */
+    /* 2. walk the roots in id order */
     int32_t out_run = 0, stk_run = 0;
     for (int32_t base = 0; base < N; base += 32) {
         PerLane<int> c, nd;
         POA_LANES(l) {
             const int32_t i = base + l;
             c[l] = (i < N) ? (int)s.cnt[i] : 0;
-            nd[l] = (i < N && s.cnt[i] > 1) ? (int)s.need[i] + 1 : 0;
+            nd[l] = (i < N && c[l] > 1 && s.dirty[i]) ? (int)s.need[i] + 1 : 0;
         }
         PerLane<int> oo = c, so = nd;
         const int32_t ctot = warp_exscan(oo);
         const int32_t stot = warp_exscan(so);
         POA_LANES(l) {
             const int32_t i = base + l;
-            if (i >= N || c[l] == 0) continue;
-            int32_t out = out_run + oo[l];
+            if (i >= N) continue;
+            s.roff[i] = (uint32_t)(out_run + oo[l]);
+            if (c[l] == 0 || !s.dirty[i]) continue;
+            s.dirty[i] = 0;
             if (c[l] == 1) {
-                s.node_at[out] = (uint16_t)i;
-                s.rank_of[i] = (uint16_t)out;
+                s.lpos[i] = 0;
                 continue;
             }
             uint16_t* stk = s.stack + stk_run + so[l];
-            int32_t sp = 0;
+            int32_t sp = 0, out = 0;
             stk[sp++] = (uint16_t)i;
             while (sp != 0) {
                 const int32_t id = stk[sp - 1];
@@ -775,15 +893,8 @@ POA_FN void topsort_roots(const Slot& s, const Params& p, WinState& st) {
                     if (valid) {
                         s.marks[id] = 2;
                         if (s.check[id]) {
-                            s.node_at[out] = (uint16_t)id;
-                            s.rank_of[id] = (uint16_t)out;
-                            ++out;
-                            for (int32_t q = 0; q < na; ++q) {
-                                const int32_t a = s.aln[id * KA + q];
-                                s.node_at[out] = (uint16_t)a;
-                                s.rank_of[a] = (uint16_t)out;
-                                ++out;
-                            }
+                            s.lpos[id] = (uint16_t)out++;
+                            for (int32_t q = 0; q < na; ++q) s.lpos[s.aln[id * KA + q]] = (uint16_t)out++;
                         }
                     } else {
                         s.marks[id] = 1;
@@ -794,6 +905,17 @@ POA_FN void topsort_roots(const Slot& s, const Params& p, WinState& st) {
         }
         out_run += ctot;
         stk_run += stot;
+    }
+    POA_SYNC();
+    /* 3. ranks */
+    for (int32_t base = 0; base < N; base += 32) {
+        POA_LANES(l) {
+            const int32_t v = base + l;
+            if (v >= N) continue;
+            const int32_t r = (int32_t)s.roff[s.root[v]] + (int32_t)s.lpos[v];
+            s.rank_of[v] = (uint16_t)r;
+            s.node_at[r] = (uint16_t)v;
+        }
     }
     POA_SYNC();
     (void)p;
@@ -927,6 +1049,7 @@ POA_FN void process_window(const Slot& s, const Params& p, const WindowView& wv,
         }
         const ReadGeom g = read_geometry(p, len);
         build_program(s, p, st, g);
+        if (st.status != ST_SUCCESS) break;
         const int32_t end_row = fill(s, p, st, g, read);
         if (end_row <= 0) {
             st.status = ST_TRACEBACK_LOST;

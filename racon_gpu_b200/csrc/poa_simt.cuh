@@ -65,6 +65,8 @@ POA_FN int warp_sum(const PerLane<int>& x) { return __reduce_add_sync(0xffffffff
 POA_FN int warp_get(const PerLane<int>& x, int src) { return __shfl_sync(0xffffffffu, x.v, src); }
 /* make a lane-0 scalar uniform across the warp */
 POA_FN int warp_bcast0(int x) { return __shfl_sync(0xffffffffu, x, 0); }
+/* out[l] = x[l+1] (lane 31 keeps its own value) */
+POA_FN void warp_shift_down1(const PerLane<int>& x, PerLane<int>& out) { out.v = __shfl_down_sync(0xffffffffu, x.v, 1); }
 
 #else /* ---------------------------------------------------------------- host emulation */
 
@@ -113,6 +115,10 @@ POA_FN int warp_sum(const PerLane<int>& x) {
 }
 POA_FN int warp_get(const PerLane<int>& x, int src) { return x.v[src]; }
 POA_FN int warp_bcast0(int x) { return x; }
+POA_FN void warp_shift_down1(const PerLane<int>& x, PerLane<int>& out) {
+    for (int l = 0; l < 31; ++l) out.v[l] = x.v[l + 1];
+    out.v[31] = x.v[31];
+}
 
 #endif
 

@@ -1,0 +1,27 @@
+"""Small driver for ncu captures: stage N windows, upload once, launch the POA kernel a few times."""
+import argparse, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from racon_gpu_b200 import api
+from racon_gpu_b200.windows import synth_windows
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--windows", type=int, default=1776)
+ap.add_argument("--banded", type=int, default=1)
+ap.add_argument("--launches", type=int, default=2)
+ap.add_argument("--length", type=int, default=500)
+ap.add_argument("--depth", type=int, default=32)
+ap.add_argument("--err", type=float, default=0.15)
+args = ap.parse_args()
+b = synth_windows(args.windows, args.length, args.depth, args.err, seed=12345)
+pb = api.PoaBatch(max_gpu_mem=48 << 30, banded=bool(args.banded))
+n, _ = pb.add_windows(b)
+assert n == args.windows
+pb.upload()
+for _ in range(args.launches):
+    pb.launch()
+torch.cuda.synchronize()
+pb.download()
+cons, cov, st = pb.get_consensus()
+print("windows", n, "failed", int((st != 0).sum()), "info", pb.info())

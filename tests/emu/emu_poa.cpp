@@ -32,11 +32,11 @@ struct ScalarFill {
         for (int32_t c = 0; c < g.bw; ++c) s.S[c] = 0; /* row 0: H = j*gap  =>  S = 0 */
         int32_t best = NEG, end_row = 0;
         for (int32_t i = 1; i <= N; ++i) {
-            const uint32_t info = s.row_info[i];
-            const uint8_t code = (uint8_t)(info & 0xFF);
-            const int32_t np = (int32_t)(info >> 16);
+            const uint32_t rec = s.row_rec[i];
+            const uint8_t code = (uint8_t)rec_code(rec);
+            const int32_t np = rec_npred(rec);
             const int32_t po = (int32_t)s.row_poff[i];
-            const int32_t bs = s.row_bs[i];
+            const int32_t bs = rec_bs(rec);
             int16_t* row = s.S + (size_t)i * p.stride;
             int32_t left = NEG;
             for (int32_t o = 0; o < g.bw; ++o) {
@@ -56,7 +56,7 @@ struct ScalarFill {
                 left = t;
             }
             cells += g.bw;
-            if (info & 0x100u) {
+            if (rec_sink(rec)) {
                 const int32_t v = score_at(s, p, g, i, g.len);
                 if (v > best) {
                     best = v;
