@@ -157,6 +157,10 @@ typedef struct b200poa_batch_info {
 } b200poa_batch_info;
 int32_t b200poa_batch_get_info(const b200poa_batch* b, b200poa_batch_info* info);
 
+/* diagnostics: with B200POA_PHASE_TIMERS=1 in the environment at batch creation, the kernel sums
+ * clock64() cycles per phase {program, fill, traceback, add_alignment, topsort, consensus, other}. */
+int32_t b200poa_batch_phase_cycles(b200poa_batch* b, uint64_t* out, int32_t n);
+
 const char* b200poa_status_string(int32_t status);
 
 /*

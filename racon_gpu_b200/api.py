@@ -37,7 +37,7 @@ ABI_SYMBOLS = (
     "b200poa_batch_generate", "b200poa_batch_upload", "b200poa_batch_launch",
     "b200poa_batch_download", "b200poa_batch_get_consensus", "b200poa_batch_id",
     "b200poa_batch_reset", "b200poa_batch_destroy", "b200poa_batch_get_info",
-    "b200poa_status_string", "b200poa_polish_windows", "b200poa_polish_windows_via_adapter",
+    "b200poa_status_string", "b200poa_batch_phase_cycles", "b200poa_polish_windows", "b200poa_polish_windows_via_adapter",
     "b200poa_polisher_create", "b200poa_polisher_polish", "b200poa_polisher_destroy",
 )
 
@@ -220,6 +220,15 @@ class PoaBatch:
 
     def reset(self):
         self.lib.b200poa_batch_reset(self.handle)
+
+    def phase_cycles(self):
+        """Diagnostics (B200POA_PHASE_TIMERS=1): dict phase -> summed cycles."""
+        out = np.zeros(7, dtype=np.uint64)
+        st = self.lib.b200poa_batch_phase_cycles(self.handle, _p(out, C.c_uint64), C.c_int32(7))
+        if st != SUCCESS:
+            return None
+        names = ["program", "fill", "traceback", "add_alignment", "topsort", "consensus", "other"]
+        return dict(zip(names, out.tolist()))
 
     def info(self) -> dict:
         inf = BatchInfo()

@@ -52,19 +52,23 @@ struct KernelArgs {
     int32_t prof_stride; /* int16 cells per profile row  */
     int32_t ring_stride; /* int16 cells per ring row     */
     int32_t ring_rows;   /* power of two                 */
+    unsigned long long* phase_cycles; /* diagnostics: [PH_COUNT] or nullptr */
 };
 
-__global__ void __launch_bounds__(32, 16) poa_window_kernel(const KernelArgs a) {
+__global__ void __launch_bounds__(32, 24) poa_window_kernel(const KernelArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    /* The workspace descriptor is pure arithmetic on kernel parameters (constant bank): the
+     * compiler rematerialises the few pointers a phase needs instead of pinning 33 of them. */
     Slot s;
     slot_bind(s, a.slab + (size_t)blockIdx.x * a.slot_bytes, a.p, nullptr);
     CudaFill fill;
-    fill.prof = reinterpret_cast<int16_t*>(smem_raw);
+    fill.smem_sa = (uint32_t)__cvta_generic_to_shared(smem_raw);
     fill.prof_stride = a.prof_stride;
-    fill.ring = fill.prof + PROF_ROWS * a.prof_stride;
     fill.ring_stride = a.ring_stride;
     fill.ring_mask = a.ring_rows - 1;
-    fill.dyn_code = -1;
+    /* the traceback tile reuses the score-row ring (idle during the traceback) */
+    TbScratch tbs;
+    tb_bind(tbs, smem_raw + 32 + (size_t)PROF_ROWS * a.prof_stride * sizeof(int16_t));
     const int lane = threadIdx.x & 31;
     for (;;) {
         int32_t t = 0;
@@ -86,8 +90,8 @@ __global__ void __launch_bounds__(32, 16) poa_window_kernel(const KernelArgs a) 
         wv.bases = a.bases;
         wv.weights = a.weights;
         wv.seq_off = a.seq_off + s0;
-        process_window(s, a.p, wv, fill, a.out_cons + orow, a.out_cov + orow, a.out_len + w,
-                       a.out_status + w);
+        process_window(s, a.p, wv, fill, tbs, a.out_cons + orow, a.out_cov + orow, a.out_len + w,
+                       a.out_status + w, PhaseTimer{a.phase_cycles, 0});
     }
 }
 
@@ -167,6 +171,7 @@ struct b200poa_batch {
     uint16_t* d_cov = nullptr;
     int32_t* d_len = nullptr;
     int32_t* d_status = nullptr;
+    unsigned long long* d_phase = nullptr; /* B200POA_PHASE_TIMERS diagnostics */
     /* fill state */
     int32_t poa_count = 0;
     int64_t seq_count = 0;
@@ -201,6 +206,7 @@ static void free_batch(b200poa_batch* b) {
     cudaFree(b->d_cov);
     cudaFree(b->d_len);
     cudaFree(b->d_status);
+    cudaFree(b->d_phase);
     delete b;
 }
 
@@ -279,6 +285,10 @@ static int32_t alloc_batch_memory(b200poa_batch* b) {
     CU_TRY(cudaMalloc(&b->d_cov, MP * (size_t)p.max_cons * sizeof(uint16_t)));
     CU_TRY(cudaMalloc(&b->d_len, MP * sizeof(int32_t)));
     CU_TRY(cudaMalloc(&b->d_status, MP * sizeof(int32_t)));
+    if (std::getenv("B200POA_PHASE_TIMERS")) {
+        CU_TRY(cudaMalloc(&b->d_phase, PH_COUNT * sizeof(unsigned long long)));
+        CU_TRY(cudaMemset(b->d_phase, 0, PH_COUNT * sizeof(unsigned long long)));
+    }
     b->device_bytes = (size_t)b->n_slots * b->slot_bytes + 2 * AC + (MS + 1) * 8 + MP * (16 + 3 * (size_t)p.max_cons);
     CU_TRY(cudaHostAlloc(&b->h_bases, AC, cudaHostAllocDefault));
     CU_TRY(cudaHostAlloc(&b->h_weights, AC, cudaHostAllocDefault));
@@ -392,7 +402,7 @@ int32_t b200poa_batch_create(int32_t device_id, void* stream, size_t max_gpu_mem
     b->sm_count = prop.multiProcessorCount;
     /* worst-case shared memory (longest admissible read) must be launchable */
     CU_TRY(cudaFuncSetAttribute(poa_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                PROF_ROWS * colsP * (int32_t)sizeof(int16_t) + 16384));
+                                32 + PROF_ROWS * colsP * (int32_t)sizeof(int16_t) + 8192 + 5 * colsP * (int32_t)sizeof(int16_t)));
     /* slots are sized for the best occupancy a launch can reach (short reads => small profile) */
     int blocks_per_sm = 0;
     CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, poa_window_kernel, 32, 4096));
@@ -538,12 +548,13 @@ int32_t b200poa_batch_launch(b200poa_batch* b) {
     const int32_t colsP = (b->max_len_staged + 1 + 7) & ~7;
     b->prof_stride = colsP;
     b->ring_stride = (b->p.band_width > 0 && b->p.band_width < colsP) ? b->p.band_width : colsP;
-    int32_t ring_bytes = 8192;
+    int32_t ring_bytes = 4096;
     if (const char* env = std::getenv("B200POA_RING_BYTES")) ring_bytes = std::atoi(env);
     int32_t rows = 2;
     while (rows < 32 && rows * 2 * b->ring_stride * (int32_t)sizeof(int16_t) <= ring_bytes) rows *= 2;
     b->ring_rows = rows;
-    b->smem_bytes = (PROF_ROWS * b->prof_stride + b->ring_rows * b->ring_stride) * (int32_t)sizeof(int16_t);
+    b->smem_bytes = 32 + PROF_ROWS * b->prof_stride * (int32_t)sizeof(int16_t) +
+                    std::max((b->ring_rows + 1) * b->ring_stride * (int32_t)sizeof(int16_t), (int32_t)TB_SCRATCH_BYTES);
     int occ = 0;
     CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, poa_window_kernel, 32, (size_t)b->smem_bytes));
     if (occ < 1) return B200POA_INVALID_ARGUMENT;
@@ -551,6 +562,7 @@ int32_t b200poa_batch_launch(b200poa_batch* b) {
     a.prof_stride = b->prof_stride;
     a.ring_stride = b->ring_stride;
     a.ring_rows = b->ring_rows;
+    a.phase_cycles = b->d_phase;
     const int grid = std::min(std::min(b->n_slots, occ * b->sm_count), b->poa_count);
     poa_window_kernel<<<grid, 32, (size_t)b->smem_bytes, b->stream>>>(a);
     CU_TRY(cudaGetLastError());
@@ -604,6 +616,17 @@ int32_t b200poa_batch_reset(b200poa_batch* b) {
 }
 
 void b200poa_batch_destroy(b200poa_batch* b) { free_batch(b); }
+
+int32_t b200poa_batch_phase_cycles(b200poa_batch* b, uint64_t* out, int32_t n) {
+    /* diagnostics (B200POA_PHASE_TIMERS=1): cycles per phase summed over warps since creation */
+    if (!b || !out || !b->d_phase) return B200POA_OUTPUT_TYPE_UNAVAILABLE;
+    unsigned long long h[PH_COUNT];
+    DeviceGuard g(b->device);
+    CU_TRY(cudaStreamSynchronize(b->stream));
+    CU_TRY(cudaMemcpy(h, b->d_phase, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int32_t i = 0; i < n && i < PH_COUNT; ++i) out[i] = h[i];
+    return B200POA_SUCCESS;
+}
 
 int32_t b200poa_batch_get_info(const b200poa_batch* b, b200poa_batch_info* info) {
     if (!b || !info) return B200POA_INVALID_ARGUMENT;

@@ -162,7 +162,7 @@ void slot_bind(Slot& s, uint8_t* base, const Params& p, size_t* total_out) {
     POA_CARVE(e_w, int32_t, ME);
     POA_CARVE(row_rec, uint32_t, MN + 1 + 64); /* +64: the fill prefetches 32-row blocks past the end */
     POA_CARVE(row_poff, uint32_t, MN + 2);
-    POA_CARVE(row_pred, uint32_t, ME + MN);
+    POA_CARVE(row_pred, uint32_t, ME + MN + 96); /* +96: the fill prefetches 32-entry blocks past the end */
     POA_CARVE(tb_node, int16_t, MN + ML + 2);
     POA_CARVE(tb_pos, int16_t, MN + ML + 2);
     POA_CARVE(asg, int32_t, ML + 1);
@@ -196,6 +196,29 @@ struct WinState {
     int32_t n_nodes;
     int32_t n_edges;
     int32_t status;
+};
+
+/* optional per-phase cycle counters (diagnostics: B200POA_PHASE_TIMERS=1), device flavour only */
+enum Phase { PH_PROGRAM = 0, PH_FILL, PH_TRACEBACK, PH_ADD, PH_TOPSORT, PH_CONSENSUS, PH_OTHER, PH_COUNT };
+struct PhaseTimer {
+    unsigned long long* acc; /* [PH_COUNT] global accumulators, or nullptr */
+    long long t;
+    POA_FN void start() {
+#if POA_DEVICE
+        if (acc) t = clock64();
+#endif
+    }
+    POA_FN void lap(int ph) {
+#if POA_DEVICE
+        if (acc) {
+            const long long n = clock64();
+            if ((threadIdx.x & 31u) == 0u) atomicAdd(&acc[ph], (unsigned long long)(n - t));
+            t = n;
+        }
+#else
+        (void)ph;
+#endif
+    }
 };
 
 /* ------------------------------------------------------------------------------------------
@@ -257,14 +280,13 @@ POA_FN int32_t rec_prow(uint32_t r) { return (int32_t)((r >> 9) & 7u); }
 POA_FN bool rec_p0prev(uint32_t r) { return (r & 0x1000u) != 0; }
 POA_FN int32_t rec_npred(uint32_t r) { return (int32_t)((r >> 13) & 0xFFu); }
 POA_FN int32_t rec_bs(uint32_t r) { return (int32_t)(r >> 21) << 3; }
-POA_FN int32_t prof_row_of(int32_t code) { /* A,C,G,T -> 0..3, N -> 4, anything else -> 5 (built on demand) */
+POA_FN int32_t prof_row_of(int32_t code) { /* A,C,G,T -> 0..3, anything else -> 4 (profile row built on demand) */
     switch (code) {
         case 'A': return 0;
         case 'C': return 1;
         case 'G': return 2;
         case 'T': return 3;
-        case 'N': return 4;
-        default: return 5;
+        default: return 4;
     }
 }
 
@@ -286,7 +308,7 @@ POA_FN ReadGeom read_geometry(const Params& p, int32_t len) {
 
 POA_FN int32_t band_start(const ReadGeom& g, int32_t row, int32_t n_rows) {
     if (!g.banded) return 0;
-    int32_t center = (int32_t)(((int64_t)row * g.len) / n_rows);
+    const int32_t center = (int32_t)(((uint32_t)row * (uint32_t)g.len) / (uint32_t)n_rows); /* < 2^31 by the config limits */
     int32_t bs = center - g.bw / 2;
     if (bs > g.colsP - g.bw) bs = g.colsP - g.bw;
     if (bs < 0) bs = 0;
@@ -365,24 +387,65 @@ POA_FN int32_t score_at_bs(const Slot& s, const Params& p, const ReadGeom& g, in
  * Phase 3: traceback  (sisd_alignment_engine.cpp:340-431)
  *   priority: diagonal over in-edges in order, vertical over in-edges in order, horizontal.
  *
- *   Fast path: the first test spoa makes at a cell is "diagonal through in-edge 0".  Lane l
- *   speculates that the previous l steps all took that move AND that in-edge 0 was the previous
- *   row, i.e. that the path sits on (i-l, j-l); it checks its own cell against lane l+1's cell.
- *   The number of leading lanes whose check holds is the length of a run of steps that is
- *   resolved with ONE round of (independent) loads instead of one dependent round per step.
- *   Slow path (first lane fails): the general rule, predecessors tested by different lanes and
- *   the first match taken by ballot.
- *   The current cell value is carried along (S[p][j-1] = S[i][j] - prof etc.), never re-read.
+ *   The score matrix lives in HBM and a step needs 3 dependent reads of it (row record ->
+ *   predecessor list -> cells), ~600 steps per read: done naively that is ~2000 serial
+ *   round-trips to memory per read.  Instead the path is followed through a TILE: the 32 rows
+ *   below the current cell x 56 columns left of it are fetched in ONE round of independent loads
+ *   (lane l fetches row i-l: its record, its predecessor list, seven 16-byte score chunks) into
+ *   on-chip scratch (shared memory on the device), and ~25 steps are then resolved from the tile.
+ *   Predecessors of a step are tested by different lanes and the first match (spoa's priority) is
+ *   taken by ballot.  The current cell value is carried along, never re-read.
+ *   A step whose data is not in the tile (predecessor > 31 rows back, in-degree > 32) falls back
+ *   to reading global memory directly.
  *   Output: tb_node/tb_pos filled back to front; returns the index of the first (leftmost) entry.
  * ---------------------------------------------------------------------------------------- */
+constexpr int TB_ROWS = 32;    /* tile rows (one per lane when loading) */
+constexpr int TB_CHUNKS = 7;   /* tile columns in 8-cell chunks */
+constexpr int TB_COLS = TB_CHUNKS * 8;
+constexpr int TB_PRED_CAP = 192; /* predecessor entries a tile can hold */
+
+struct TbScratch {           /* device: shared memory (the fill's ring area); emulation: heap */
+    int16_t* cells;          /* [TB_ROWS * TB_COLS]  row (r_hi - k) at k*TB_COLS, column c at c - c_lo */
+    uint32_t* rec;           /* [TB_ROWS]   row records                                 */
+    uint32_t* poff;          /* [TB_ROWS+1] poff[k] = CSR offset of row (r_hi - k); poff[TB_ROWS] unused */
+    uint32_t* pred;          /* [TB_PRED_CAP] predecessor entries of the rows, per row at poff - pred_base */
+    uint16_t* node;          /* [TB_ROWS]   node id of row (r_hi - k)                   */
+};
+constexpr int TB_SCRATCH_BYTES = TB_ROWS * TB_COLS * 2 + TB_ROWS * 4 + (TB_ROWS + 1) * 4 + TB_PRED_CAP * 4 + TB_ROWS * 2 + 28;
+
+struct alignas(16) Vec16 { /* 8 int16 cells moved as one 128-bit access */
+    uint32_t x, y, z, w;
+};
+POA_FN void copy8(int16_t* dst, const int16_t* src) { *reinterpret_cast<Vec16*>(dst) = *reinterpret_cast<const Vec16*>(src); }
+POA_FN void fill8(int16_t* dst, int32_t v) {
+    const uint32_t pk = ((uint32_t)v & 0xFFFFu) | ((uint32_t)v << 16);
+    Vec16 q;
+    q.x = q.y = q.z = q.w = pk;
+    *reinterpret_cast<Vec16*>(dst) = q;
+}
+
+POA_FN void tb_bind(TbScratch& t, uint8_t* base) {
+    t.cells = reinterpret_cast<int16_t*>(base);
+    base += TB_ROWS * TB_COLS * 2;
+    t.rec = reinterpret_cast<uint32_t*>(base);
+    base += TB_ROWS * 4;
+    t.poff = reinterpret_cast<uint32_t*>(base);
+    base += (TB_ROWS + 1) * 4;
+    t.pred = reinterpret_cast<uint32_t*>(base);
+    base += TB_PRED_CAP * 4;
+    t.node = reinterpret_cast<uint16_t*>(base);
+}
+
 POA_FN int32_t traceback(const Slot& s, const Params& p, WinState& st, const ReadGeom& g,
-                         const uint8_t* read, int32_t end_row) {
+                         const uint8_t* read, int32_t end_row, const TbScratch& t) {
     const int32_t cap = p.max_nodes + p.max_len + 2;
     int32_t w = cap; /* write cursor (uniform) */
     int32_t i = end_row, j = g.len;
     const int32_t mg = p.match - p.gap, xg = p.mismatch - p.gap;
     int32_t guard = p.max_nodes + p.max_len + 4;
     int32_t cur = score_at(s, p, g, i, j);
+    /* tile state (uniform) */
+    int32_t r_hi = -1, r_lo = 0, c_lo = 0, c_hi = -1, pred_base = 0, pred_n = 0;
     while (!(i == 0 && j == 0)) {
         if (--guard < 0 || w <= 32) {
             st.status = ST_TRACEBACK_LOST;
@@ -406,79 +469,90 @@ POA_FN int32_t traceback(const Slot& s, const Params& p, WinState& st, const Rea
             }
             break;
         }
-        /* ---- fast path: run of "diagonal via in-edge 0 == previous row" steps ---- */
-        PerLane<int> val, flag, nodeid;
-        POA_LANES(l) {
-            const int32_t ii = i - l, jj = j - l;
-            val[l] = NEG;
-            flag[l] = 0;
-            nodeid[l] = 0;
-            if (ii >= 0 && jj >= 0) {
-                const uint32_t rec = s.row_rec[ii];
-                val[l] = (l == 0) ? cur : score_at_bs(s, p, g, ii, rec_bs(rec), jj);
-                if (ii >= 1 && jj >= 1) {
-                    const int32_t prof = (rec_code(rec) == (int32_t)read[jj - 1]) ? mg : xg;
-                    flag[l] = rec_p0prev(rec) ? (prof + 1000000) : 0; /* carries prof to the check */
-                    nodeid[l] = s.node_at[ii - 1];
-                }
-            }
-        }
-        PerLane<int> nxt;
-        warp_shift_down1(val, nxt);
-        PerLane<int> ok;
-        POA_LANES(l) {
-            ok[l] = (l < 31 && flag[l] != 0 && val[l] > NEG && nxt[l] > NEG &&
-                     val[l] == nxt[l] + (flag[l] - 1000000)) ? 1 : 0;
-        }
-        const unsigned okm = warp_ballot(ok);
-        const int32_t k = (okm == 0xFFFFFFFFu) ? 32 : poa_ffs(~okm);
-        if (k > 0) {
+        /* ---- make sure row i and columns j-1..j are in the tile ---- */
+        bool reloaded = false;
+        if (i > r_hi || i < r_lo || j > c_hi || j - 1 < c_lo) {
+            r_hi = i;
+            r_lo = i - (TB_ROWS - 1) < 0 ? 0 : i - (TB_ROWS - 1);
+            c_hi = j;
+            c_lo = ((j + 1 - TB_COLS) < 0 ? 0 : (j + 1 - TB_COLS + 7)) & ~7; /* 8-aligned, covers j */
+            POA_SYNC();
+            /* level 1: per-row metadata (lane k <-> row r_hi - k) */
+            PerLane<int> cnt;
             POA_LANES(l) {
-                if (l < k) {
-                    s.tb_node[w - 1 - l] = (int16_t)nodeid[l];
-                    s.tb_pos[w - 1 - l] = (int16_t)(j - l - 1);
+                const int32_t row = r_hi - l;
+                cnt[l] = 0;
+                if (row >= r_lo) {
+                    const uint32_t rec = s.row_rec[row];
+                    t.rec[l] = rec;
+                    t.poff[l] = row >= 1 ? s.row_poff[row] : 0u;
+                    t.node[l] = row >= 1 ? s.node_at[row - 1] : (uint16_t)0;
+                    cnt[l] = row >= 1 ? rec_npred(rec) : 0;
                 }
             }
-            w -= k;
-            i -= k;
-            j -= k;
-            cur = warp_get(val, k);
-            guard -= (k - 1);
-            continue;
-        }
-        /* ---- slow path: the general rule at (i, j) ---- */
-        int32_t ni = i, nj = j, ncur = cur;
-        {
-            const uint32_t rec = s.row_rec[i];
-            const int32_t np = rec_npred(rec);
-            const int32_t po = (int32_t)s.row_poff[i];
-            const int32_t prof = (j > 0 && rec_code(rec) == (int32_t)read[j - 1]) ? mg : xg;
-            int32_t found = 0;
-            for (int32_t b = 0; b < np && !found; b += 32) {
-                PerLane<int> dm, vm, pr;
-                POA_LANES(l) {
-                    dm[l] = 0;
-                    vm[l] = 0;
-                    pr[l] = 0;
-                    if (b + l < np) {
-                        const uint32_t pe = s.row_pred[po + b + l];
-                        const int32_t pi = (int32_t)(pe & 0xFFFFu);
-                        const int32_t pbs = (int32_t)(pe >> 16);
-                        pr[l] = pi;
-                        dm[l] = (j > 0) && (score_at_bs(s, p, g, pi, pbs, j - 1) + prof == cur);
-                        vm[l] = (score_at_bs(s, p, g, pi, pbs, j) + p.gap == cur);
+            POA_SYNC();
+            /* CSR entries of rows r_lo..r_hi are contiguous: [poff(r_lo'), poff(r_hi) + np(r_hi)) */
+            const int32_t lo_row = r_lo < 1 ? 1 : r_lo;
+            pred_base = (int32_t)t.poff[r_hi - lo_row];
+            pred_n = (int32_t)t.poff[0] + rec_npred(t.rec[0]) - pred_base;
+            if (pred_n > TB_PRED_CAP) pred_n = TB_PRED_CAP; /* rows beyond the cap fall back to global */
+            /* level 2: score chunks and predecessor entries */
+            POA_LANES(l) {
+                const int32_t row = r_hi - l;
+                if (row >= r_lo) {
+                    const int32_t bs = rec_bs(t.rec[l]);
+                    for (int32_t k = 0; k < TB_CHUNKS; ++k) {
+                        const int32_t c = c_lo + 8 * k; /* 8-aligned, bs is 8-aligned: whole chunk in or out */
+                        const int32_t o = c - bs;
+                        int16_t* dst = t.cells + l * TB_COLS + 8 * k;
+                        if (o >= 0 && o + 8 <= g.bw) copy8(dst, s.S + (size_t)row * p.stride + o);
+                        else fill8(dst, NEG);
                     }
                 }
-                /* diagonal matches of ALL predecessors come before any vertical match, so a
-                 * vertical hit in this group of 32 only counts if no later group has a diagonal
-                 * hit; groups > 1 only exist for in-degree > 32, handled by the two-pass below. */
+                for (int32_t e = l; e < pred_n; e += 32) t.pred[e] = s.row_pred[pred_base + e];
+            }
+            POA_SYNC();
+            reloaded = true;
+        }
+        /* ---- one step at (i, j) ---- */
+        int32_t ni = i, nj = j, ncur = cur;
+        const int32_t ti = r_hi - i; /* tile row index of row i */
+        const uint32_t rec = t.rec[ti];
+        const int32_t np = rec_npred(rec);
+        const int32_t po = (int32_t)t.poff[ti];
+        const int32_t prof = (j > 0 && rec_code(rec) == (int32_t)read[j - 1]) ? mg : xg;
+        bool in_tile = (np <= 32) && (po - pred_base + np <= pred_n);
+        int32_t found = 0;
+        if (in_tile) {
+            PerLane<int> dm, vm, pr, miss;
+            POA_LANES(l) {
+                dm[l] = 0;
+                vm[l] = 0;
+                pr[l] = 0;
+                miss[l] = 0;
+                if (l < np) {
+                    const uint32_t pe = t.pred[po - pred_base + l];
+                    const int32_t pi = (int32_t)(pe & 0xFFFFu);
+                    pr[l] = pi;
+                    if (pi < r_lo) {
+                        miss[l] = 1;
+                    } else {
+                        const int16_t* cells = t.cells + (r_hi - pi) * TB_COLS - c_lo;
+                        dm[l] = (j > 0) && ((int32_t)cells[j - 1] + prof == cur);
+                        vm[l] = ((int32_t)cells[j] + p.gap == cur);
+                    }
+                }
+            }
+            if (warp_ballot(miss)) {
+                in_tile = false;
+            } else {
                 const unsigned dmask = warp_ballot(dm);
                 if (dmask) {
                     ni = warp_get(pr, poa_ffs(dmask));
                     nj = j - 1;
                     ncur = cur - prof;
                     found = 1;
-                } else if (np <= 32) {
+                } else {
                     const unsigned vmask = warp_ballot(vm);
                     if (vmask) {
                         ni = warp_get(pr, poa_ffs(vmask));
@@ -487,25 +561,45 @@ POA_FN int32_t traceback(const Slot& s, const Params& p, WinState& st, const Rea
                         found = 1;
                     }
                 }
+                if (!found) {
+                    if (j > 0 && (int32_t)t.cells[ti * TB_COLS + (j - 1 - c_lo)] == cur) {
+                        nj = j - 1;
+                        found = 1;
+                    } else {
+                        st.status = ST_TRACEBACK_LOST;
+                        return cap;
+                    }
+                }
             }
-            if (!found && np > 32) { /* second pass: vertical candidates of a very wide node */
+        }
+        if (!in_tile) {
+            if (!reloaded) { /* a predecessor fell off the tile: re-anchor the tile at (i, j) and retry */
+                r_hi = -1;
+                ++guard;
+                continue;
+            }
+            /* even a tile anchored here does not hold the step: read global memory directly */
+            const int32_t gpo = (int32_t)s.row_poff[i];
+            for (int pass = 0; pass < 2 && !found; ++pass) { /* pass 0: diagonal, pass 1: vertical */
                 for (int32_t b = 0; b < np && !found; b += 32) {
-                    PerLane<int> vm, pr;
+                    PerLane<int> hit, pr;
                     POA_LANES(l) {
-                        vm[l] = 0;
+                        hit[l] = 0;
                         pr[l] = 0;
                         if (b + l < np) {
-                            const uint32_t pe = s.row_pred[po + b + l];
+                            const uint32_t pe = s.row_pred[gpo + b + l];
                             const int32_t pi = (int32_t)(pe & 0xFFFFu);
+                            const int32_t pbs = (int32_t)(pe >> 16);
                             pr[l] = pi;
-                            vm[l] = (score_at_bs(s, p, g, pi, (int32_t)(pe >> 16), j) + p.gap == cur);
+                            hit[l] = pass == 0 ? ((j > 0) && (score_at_bs(s, p, g, pi, pbs, j - 1) + prof == cur))
+                                               : (score_at_bs(s, p, g, pi, pbs, j) + p.gap == cur);
                         }
                     }
-                    const unsigned vmask = warp_ballot(vm);
-                    if (vmask) {
-                        ni = warp_get(pr, poa_ffs(vmask));
-                        nj = j;
-                        ncur = cur - p.gap;
+                    const unsigned m = warp_ballot(hit);
+                    if (m) {
+                        ni = warp_get(pr, poa_ffs(m));
+                        nj = pass == 0 ? j - 1 : j;
+                        ncur = pass == 0 ? cur - prof : cur - p.gap;
                         found = 1;
                     }
                 }
@@ -521,7 +615,7 @@ POA_FN int32_t traceback(const Slot& s, const Params& p, WinState& st, const Rea
         }
         --w;
         POA_LANE0 {
-            s.tb_node[w] = (int16_t)((i == ni) ? -1 : (int32_t)s.node_at[i - 1]);
+            s.tb_node[w] = (int16_t)((i == ni) ? -1 : (int32_t)t.node[ti]);
             s.tb_pos[w] = (int16_t)((j == nj) ? -1 : (j - 1));
         }
         i = ni;
@@ -1030,14 +1124,15 @@ POA_FN bool score_range_ok(const Params& p, int32_t n_nodes, int32_t len) {
  *     int32_t operator()(slot, params, state, geom, read) -> end row (0 = none)
  * ---------------------------------------------------------------------------------------- */
 template <class Fill>
-POA_FN void process_window(const Slot& s, const Params& p, const WindowView& wv, Fill& fill,
+POA_FN void process_window(const Slot& s, const Params& p, const WindowView& wv, Fill& fill, const TbScratch& tbs,
                            uint8_t* out_cons, uint16_t* out_cov, int32_t* out_len,
-                           int32_t* out_status) {
+                           int32_t* out_status, PhaseTimer tm = PhaseTimer{nullptr, 0}) {
     WinState st;
     st.n_nodes = 0;
     st.n_edges = 0;
     st.status = ST_SUCCESS;
     const int32_t len0 = (int32_t)(wv.seq_off[1] - wv.seq_off[0]);
+    tm.start();
     init_backbone(s, p, st, wv.bases + wv.seq_off[0], wv.weights + wv.seq_off[0], len0);
     for (int32_t r = 1; r < wv.n_seqs && st.status == ST_SUCCESS; ++r) {
         const uint8_t* read = wv.bases + wv.seq_off[r];
@@ -1048,21 +1143,28 @@ POA_FN void process_window(const Slot& s, const Params& p, const WindowView& wv,
             break;
         }
         const ReadGeom g = read_geometry(p, len);
+        tm.lap(PH_OTHER);
         build_program(s, p, st, g);
+        tm.lap(PH_PROGRAM);
         if (st.status != ST_SUCCESS) break;
         const int32_t end_row = fill(s, p, st, g, read);
+        tm.lap(PH_FILL);
         if (end_row <= 0) {
             st.status = ST_TRACEBACK_LOST;
             break;
         }
-        const int32_t tb = traceback(s, p, st, g, read, end_row);
+        const int32_t tb = traceback(s, p, st, g, read, end_row, tbs);
+        tm.lap(PH_TRACEBACK);
         if (st.status != ST_SUCCESS) break;
         add_alignment(s, p, st, read, wt, len, tb);
+        tm.lap(PH_ADD);
         if (st.status != ST_SUCCESS) break;
         if (p.serial_topsort) topsort_serial(s, p, st);
         else topsort_roots(s, p, st);
+        tm.lap(PH_TOPSORT);
     }
     if (st.status == ST_SUCCESS) generate_consensus(s, p, st, out_cons, out_cov, out_len);
+    tm.lap(PH_CONSENSUS);
     POA_LANE0 {
         if (st.status != ST_SUCCESS) *out_len = 0;
         *out_status = st.status;

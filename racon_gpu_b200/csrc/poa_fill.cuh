@@ -14,12 +14,16 @@
  *   - the matrix is kept in the skewed domain S = H - j*gap, which turns the horizontal dependency
  *     H[i][j-1]+gap into a plain prefix max: 14 packed ops inside the lane + a 5-step warp scan,
  *     instead of the reference's iterate-until-stable loop (cudapoa_nw.cuh:272-317);
- *   - the graph is consumed as a stream of packed 32-bit row records: 32 rows are fetched by one
- *     coalesced load (one record per lane), double-buffered, and handed out by a shuffle, so the
- *     row loop has no dependent global load for its own metadata;
- *   - the last R score rows live in a shared-memory ring (predecessors are almost always within a
- *     few ranks); only older predecessors are re-read from global/L2.  Every
- *     row is also written once to HBM for the traceback (that write is the algorithmic traffic);
+ *   - the graph is consumed as two register-resident streams: packed 32-bit row records and the
+ *     CSR predecessor list.  Each is fetched 32 entries at a time by one coalesced load (one entry
+ *     per lane), double-buffered, and handed out by a shuffle -- the row loop issues no dependent
+ *     global load for its own metadata;
+ *   - predecessor rows are read from a shared-memory ring holding the last R score rows
+ *     (predecessors are almost always within a few ranks); an older predecessor
+ *     is first copied from global/L2 into a spare shared row.  Every row is also written once to
+ *     HBM for the traceback (that write is the algorithmic traffic);
+ *   - shared memory is addressed with 32-bit shared-window addresses (ld/st.shared via PTX), which
+ *     keeps the per-predecessor address arithmetic to one IMAD;
  *   - the band is snapped to multiples of 8 columns, so a predecessor row with a different band
  *     start is the same 128-bit load at a lane-shifted address; cells outside a band read NEG;
  *   - match/mismatch terms come from a per-read profile in shared memory (one LDS.128 per lane per
@@ -34,195 +38,282 @@ namespace b200poa {
 
 #if POA_DEVICE
 
-constexpr int PROF_ROWS = 6; /* A C G T N + dynamic */
+constexpr int PROF_ROWS = 5; /* A C G T + one on-demand row for any other letter (N, IUPAC, ...) */
 
 __device__ __forceinline__ uint32_t pack2(int lo, int hi) {
     return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16);
 }
+/* shared memory through 32-bit shared-window addresses */
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts16(uint32_t addr, int v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+/*
+ * Shared memory of one block (one warp), in int16 cells:
+ *   [0, 8)                                  eight NEG cells: where out-of-band lanes point their loads
+ *   [8, 16)                                 eight zero cells: profile of lanes beyond the band
+ *   [16, 16 + PROF_ROWS*prof_stride)        profile rows
+ *   [.., + (ring_rows+1)*ring_stride)       ring of score rows + one spare row for old predecessors
+ */
+struct FillArgs { /* everything the row loop needs, and nothing else (keeps its register set small) */
+    int16_t* S;
+    const uint32_t* row_rec;
+    const uint32_t* row_pred;
+    const uint8_t* read;
+    uint32_t smem_sa;
+    int32_t stride;      /* cells per global score row */
+    int32_t prof_stride;
+    int32_t ring_stride;
+    int32_t ring_mask;
+    int32_t N, len, colsP, bw;
+    int32_t mg, xg, gap;
+};
+
+/* rare: predecessor older than the ring -> copy its row from global memory into the spare row */
+__device__ __noinline__ void fill_stage_far_row(const int16_t* src, uint32_t far_sa, int bw) {
+    const int lane8 = (threadIdx.x & 31) * 8;
+    __syncwarp();
+#pragma unroll 1
+    for (int o = lane8; o < bw; o += CHUNK)
+        sts128(far_sa + (uint32_t)o * 2u, *reinterpret_cast<const uint4*>(src + o));
+    __syncwarp();
+}
+
+__device__ __noinline__ void fill_build_dyn_prof_row(uint32_t row_sa, int c, const uint8_t* read, int len,
+                                                     int colsP, int mg, int xg) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+#pragma unroll 1
+    for (int col = lane; col < colsP; col += 32) {
+        int v = xg;
+        if (col >= 1 && col <= len && (int)read[col - 1] == c) v = mg;
+        sts16(row_sa + (uint32_t)col * 2u, v);
+    }
+    __syncwarp();
+}
+
+/* The row loop.  Deliberately NOT inlined into the window loop: compiled on its own, its loop
+ * invariants stay in registers instead of being rematerialised around every use. */
+__device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
+    int lane; /* read once through volatile asm so that it is kept, not re-derived from S2R per use */
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+    const int N = fa.N;
+    const int mg = fa.mg, xg = fa.xg;
+    const uint32_t NEG2 = pack2(NEG, NEG);
+    const uint32_t G2 = pack2(fa.gap, fa.gap);
+    const int bw = fa.bw;
+    const int nchunks = (bw + CHUNK - 1) / CHUNK;
+    const size_t stride = (size_t)fa.stride;
+    int16_t* const S = fa.S;
+    const uint32_t* const row_rec = fa.row_rec;
+    const uint32_t* const row_pred = fa.row_pred;
+    const uint8_t* const read = fa.read;
+    const int ring_mask = fa.ring_mask;
+    const int R = ring_mask + 1;
+    const int prof_stride = fa.prof_stride;
+    const uint32_t neg_sa = fa.smem_sa;
+    const uint32_t zero_sa = fa.smem_sa + 16u;
+    const uint32_t prof_sa = fa.smem_sa + 32u;
+    const uint32_t ring_sa = prof_sa + (uint32_t)(PROF_ROWS * prof_stride) * 2u;
+    const uint32_t ring_row_bytes = (uint32_t)fa.ring_stride * 2u;
+    const uint32_t far_sa = ring_sa + (uint32_t)R * ring_row_bytes;
+    const int lane8 = lane * 8;
+    int dyn_code = -1; /* letter currently held by the on-demand profile row */
+
+    __syncwarp();
+    if (lane < 8) sts16(neg_sa + (uint32_t)lane * 2u, NEG);
+    else if (lane < 16) sts16(neg_sa + (uint32_t)lane * 2u, 0);
+#pragma unroll 1
+    for (int col = lane; col < fa.colsP; col += 32) { /* the four fixed profile rows in one pass */
+        const int ch = (col >= 1 && col <= fa.len) ? (int)read[col - 1] : -1;
+        sts16(prof_sa + (uint32_t)(0 * prof_stride + col) * 2u, ch == 'A' ? mg : xg);
+        sts16(prof_sa + (uint32_t)(1 * prof_stride + col) * 2u, ch == 'C' ? mg : xg);
+        sts16(prof_sa + (uint32_t)(2 * prof_stride + col) * 2u, ch == 'G' ? mg : xg);
+        sts16(prof_sa + (uint32_t)(3 * prof_stride + col) * 2u, ch == 'T' ? mg : xg);
+    }
+    /* row 0: H[0][j] = j*gap  =>  S = 0 (global copy for the traceback, ring slot 0 for the fill) */
+#pragma unroll 1
+    for (int o = lane8; o < bw; o += CHUNK) {
+        *reinterpret_cast<uint4*>(S + o) = make_uint4(0u, 0u, 0u, 0u);
+        sts128(ring_sa + (uint32_t)o * 2u, make_uint4(0u, 0u, 0u, 0u));
+    }
+    /* register-resident streams: lane l holds entry (base + l); the next 32 are prefetched */
+    uint32_t recA = row_rec[lane];
+    uint32_t recB = row_rec[32 + lane];
+    int pbase = 0; /* row_pred index held by lane 0 of predA */
+    uint32_t predA = row_pred[lane];
+    uint32_t predB = row_pred[32 + lane];
+    __syncwarp();
+
+    int best = NEG, end_row = 0;
+    int po = 0;      /* running offset into row_pred (CSR is contiguous in row order) */
+    int bs_prev = 0; /* band start of row i-1 */
+#pragma unroll 1
+    for (int i = 1; i <= N; ++i) {
+        if ((i & 31) == 0) {
+            recA = recB;
+            recB = row_rec[i + 32 + lane];
+        }
+        const uint32_t rec = __shfl_sync(0xffffffffu, recA, i & 31);
+        const int np = rec_npred(rec);
+        const int bs = rec_bs(rec);
+        const int prow = rec_prow(rec);
+        if (prow == 4) {
+            const int code = rec_code(rec);
+            if (dyn_code != code) {
+                fill_build_dyn_prof_row(prof_sa + (uint32_t)(4 * prof_stride) * 2u, code, read, fa.len, fa.colsP, mg, xg);
+                dyn_code = code;
+            }
+        }
+        const uint32_t prof_row_sa = prof_sa + (uint32_t)(prow * prof_stride + bs + lane8) * 2u;
+        int16_t* Srow = S + (size_t)i * stride;
+        const uint32_t ring_row_sa = ring_sa + (uint32_t)(i & ring_mask) * ring_row_bytes;
+        uint32_t carry = NEG2; /* S[i][last column of the previous chunk], both halves */
+        const bool p0prev = rec_p0prev(rec);
+#pragma unroll 1
+        while (po - pbase >= 32) { /* advance the predecessor stream window (uniform) */
+            pbase += 32;
+            predA = predB;
+            predB = row_pred[pbase + 32 + lane];
+        }
+
+#pragma unroll 1
+        for (int k = 0; k < nchunks; ++k) {
+            const int o0 = k * CHUNK + lane8; /* offset of this lane's cells in the row */
+            const bool active = o0 < bw;
+            const int c0 = bs + o0;           /* first column of this lane */
+            const uint4 P = lds128(active ? prof_row_sa + (uint32_t)(k * CHUNK) * 2u : zero_sa);
+            uint32_t a0 = NEG2, a1 = NEG2, a2 = NEG2, a3 = NEG2;
+
+#pragma unroll 1
+            for (int q = 0; q < np; ++q) {
+                /* predecessor row and its band start, from the register-resident CSR stream */
+                const int idx = po + q - pbase; /* >= 0: the window only advances between rows */
+                uint32_t pe = __shfl_sync(0xffffffffu, idx < 32 ? predA : predB, idx & 31);
+                if (idx >= 64) pe = row_pred[po + q]; /* in-degree > 32: straight from memory */
+                const bool useprev = (q == 0) & p0prev;
+                const int pr = useprev ? i - 1 : (int)(pe & 0xFFFFu);
+                const int bsp = useprev ? bs_prev : (int)(pe >> 16);
+                uint32_t src_sa = ring_sa + (uint32_t)(pr & ring_mask) * ring_row_bytes;
+                if (i - pr >= R) {
+                    fill_stage_far_row(S + (size_t)pr * stride, far_sa, bw);
+                    src_sa = far_sa;
+                }
+                const int off = c0 - bsp; /* offset of column c0 in the predecessor row */
+                const uint32_t cell_sa = src_sa + (uint32_t)off * 2u;
+                /* out-of-band loads are redirected to the NEG cells: no branches, no predicates */
+                const bool inband = active & ((unsigned)off <= (unsigned)(bw - 8));
+                const bool leftin = active & (c0 >= 1) & ((unsigned)(off - 1) < (unsigned)bw);
+                const uint4 V = lds128(inband ? cell_sa : neg_sa);
+                const uint32_t leftw = lds_u16(leftin ? cell_sa - 2u : neg_sa) << 16; /* cell (pr, c0-1) */
+                const uint32_t d0 = __funnelshift_l(leftw, V.x, 16);
+                const uint32_t d1 = __funnelshift_l(V.x, V.y, 16);
+                const uint32_t d2 = __funnelshift_l(V.y, V.z, 16);
+                const uint32_t d3 = __funnelshift_l(V.z, V.w, 16);
+                a0 = __viaddmax_s16x2(d0, P.x, a0);
+                a1 = __viaddmax_s16x2(d1, P.y, a1);
+                a2 = __viaddmax_s16x2(d2, P.z, a2);
+                a3 = __viaddmax_s16x2(d3, P.w, a3);
+                a0 = __viaddmax_s16x2(V.x, G2, a0);
+                a1 = __viaddmax_s16x2(V.y, G2, a1);
+                a2 = __viaddmax_s16x2(V.z, G2, a2);
+                a3 = __viaddmax_s16x2(V.w, G2, a3);
+            }
+
+            /* horizontal: inclusive prefix max over the 8 cells of the lane ... */
+            a0 = __vmaxs2(a0, __byte_perm(a0, NEG2, 0x1054));
+            a1 = __vmaxs2(a1, __byte_perm(a1, NEG2, 0x1054));
+            a2 = __vmaxs2(a2, __byte_perm(a2, NEG2, 0x1054));
+            a3 = __vmaxs2(a3, __byte_perm(a3, NEG2, 0x1054));
+            a1 = __vmaxs2(a1, __byte_perm(a0, a0, 0x3232));
+            a2 = __vmaxs2(a2, __byte_perm(a1, a1, 0x3232));
+            a3 = __vmaxs2(a3, __byte_perm(a2, a2, 0x3232));
+            /* ... then across lanes (packed, both halves equal).  Lanes below the shift distance
+             * max with NEG instead of branching. */
+            uint32_t tt = __byte_perm(a3, a3, 0x3232);
+            tt = __vmaxs2(tt, lane == 0 ? carry : NEG2);
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, tt, d);
+                tt = __vmaxs2(tt, lane >= d ? u : NEG2);
+            }
+            uint32_t excl = __shfl_up_sync(0xffffffffu, tt, 1);
+            excl = lane == 0 ? carry : excl;
+            a0 = __vimax3_s16x2(a0, excl, NEG2);
+            a1 = __vimax3_s16x2(a1, excl, NEG2);
+            a2 = __vimax3_s16x2(a2, excl, NEG2);
+            a3 = __vimax3_s16x2(a3, excl, NEG2);
+            if (nchunks > 1) {
+                carry = __shfl_sync(0xffffffffu, tt, 31);
+                carry = __vmaxs2(carry, NEG2);
+            }
+
+            if (active) {
+                const uint4 out = make_uint4(a0, a1, a2, a3);
+                *reinterpret_cast<uint4*>(Srow + o0) = out;
+                sts128(ring_row_sa + (uint32_t)o0 * 2u, out);
+            }
+
+            if (rec_sink(rec)) { /* sink row: candidate end cell at column len */
+                const int eo = fa.len - bs - k * CHUNK;
+                if (eo >= 0 && eo < CHUNK && eo + k * CHUNK < bw) {
+                    const int e8 = eo & 7;
+                    uint32_t w = (e8 < 2) ? a0 : (e8 < 4) ? a1 : (e8 < 6) ? a2 : a3;
+                    int val = (e8 & 1) ? ((int)w >> 16) : (int)(int16_t)(w & 0xFFFFu);
+                    val = __shfl_sync(0xffffffffu, val, eo >> 3);
+                    if (val > best) {
+                        best = val;
+                        end_row = i;
+                    }
+                }
+            }
+        }
+        po += np;
+        bs_prev = bs;
+        __syncwarp(); /* row i (ring + global) is visible to every lane before it is read */
+    }
+    return end_row;
+}
 
 struct CudaFill {
-    int16_t* prof;       /* shared: PROF_ROWS rows of prof_stride int16 */
-    int16_t* ring;       /* shared: ring_rows rows of ring_stride int16 */
+    uint32_t smem_sa;    /* shared-window address of the block's dynamic shared memory */
     int32_t prof_stride;
     int32_t ring_stride; /* cells per ring row (>= widest band of the batch) */
     int32_t ring_mask;   /* ring_rows - 1 (power of two) */
-    int32_t dyn_code;    /* letter currently held by profile row 5, or -1 */
 
-    __device__ __forceinline__ void build_prof_row(int row, int c, const ReadGeom& g,
-                                                   const uint8_t* read, int mg, int xg) {
-        const int lane = threadIdx.x & 31;
-        int16_t* dst = prof + row * prof_stride;
-        for (int col = lane; col < g.colsP; col += 32) {
-            int v = xg;
-            if (col >= 1 && col <= g.len && (int)read[col - 1] == c) v = mg;
-            dst[col] = (int16_t)v;
-        }
-    }
-
-    __device__ int32_t operator()(const Slot& s, const Params& p, WinState& st, const ReadGeom& g,
-                                  const uint8_t* read) {
-        const int lane = threadIdx.x & 31;
-        const int N = st.n_nodes;
-        const int mg = p.match - p.gap, xg = p.mismatch - p.gap;
-        const uint32_t NEG2 = pack2(NEG, NEG);
-        const uint32_t G2 = pack2(p.gap, p.gap);
-        const int bw = g.bw;
-        const int nchunks = (bw + CHUNK - 1) / CHUNK;
-        const size_t stride = (size_t)p.stride;
-        int16_t* const S = s.S;
-        const uint32_t* const row_rec = s.row_rec;
-        const uint32_t* const row_pred = s.row_pred;
-        const int R = ring_mask + 1;
-
-        __syncwarp();
-        {   /* all five fixed profile rows in one pass over the read */
-            for (int col = lane; col < g.colsP; col += 32) {
-                const int ch = (col >= 1 && col <= g.len) ? (int)read[col - 1] : -1;
-                prof[0 * prof_stride + col] = (int16_t)(ch == 'A' ? mg : xg);
-                prof[1 * prof_stride + col] = (int16_t)(ch == 'C' ? mg : xg);
-                prof[2 * prof_stride + col] = (int16_t)(ch == 'G' ? mg : xg);
-                prof[3 * prof_stride + col] = (int16_t)(ch == 'T' ? mg : xg);
-                prof[4 * prof_stride + col] = (int16_t)(ch == 'N' ? mg : xg);
-            }
-        }
-        dyn_code = -1;
-        /* row 0: H[0][j] = j*gap  =>  S = 0 (global copy for the traceback, ring slot 0 for the fill) */
-        for (int o = lane * 8; o < bw; o += CHUNK) {
-            *reinterpret_cast<uint4*>(S + o) = make_uint4(0u, 0u, 0u, 0u);
-            *reinterpret_cast<uint4*>(ring + o) = make_uint4(0u, 0u, 0u, 0u);
-        }
-        /* row records: lane l holds the record of row (block*32 + l); next block prefetched */
-        uint32_t recA = row_rec[lane];
-        uint32_t recB = row_rec[32 + lane];
-        __syncwarp();
-
-        int best = NEG, end_row = 0;
-        int po = 0;      /* running offset into row_pred (CSR is contiguous in row order) */
-        int bs_prev = 0; /* band start of row i-1 */
-        for (int i = 1; i <= N; ++i) {
-            if ((i & 31) == 0) {
-                recA = recB;
-                recB = row_rec[i + 32 + lane];
-            }
-            const uint32_t rec = __shfl_sync(0xffffffffu, recA, i & 31);
-            const int np = rec_npred(rec);
-            const int bs = rec_bs(rec);
-            int prow = rec_prow(rec);
-            if (prow == 5) {
-                const int code = rec_code(rec);
-                if (dyn_code != code) {
-                    __syncwarp();
-                    build_prof_row(5, code, g, read, mg, xg);
-                    dyn_code = code;
-                    __syncwarp();
-                }
-            }
-            const int16_t* profrow = prof + prow * prof_stride;
-            int16_t* Srow = S + (size_t)i * stride;
-            int16_t* Rrow = ring + (i & ring_mask) * ring_stride;
-            uint32_t carry = NEG2; /* S[i][last column of the previous chunk], both halves */
-
-            for (int k = 0; k < nchunks; ++k) {
-                const int o0 = k * CHUNK + lane * 8; /* offset of this lane's cells in the row */
-                const bool active = o0 < bw;
-                const int c0 = bs + o0;              /* first column of this lane */
-                uint4 P = make_uint4(0u, 0u, 0u, 0u);
-                if (active) P = *reinterpret_cast<const uint4*>(profrow + c0);
-                uint32_t a0 = NEG2, a1 = NEG2, a2 = NEG2, a3 = NEG2;
-
-                for (int q = 0; q < np; ++q) {
-                    int pr, bsp;
-                    if (q == 0 && rec_p0prev(rec)) {
-                        pr = i - 1;
-                        bsp = bs_prev;
-                    } else {
-                        const uint32_t pe = row_pred[po + q];
-                        pr = (int)(pe & 0xFFFFu);
-                        bsp = (int)(pe >> 16);
-                    }
-                    const int off = c0 - bsp; /* offset of column c0 in the predecessor row */
-                    const bool inband = active && off >= 0 && off + 8 <= bw;
-                    const int lo = off - 1;   /* cell (pr, c0-1), needed by lane 0 only */
-                    const bool need_left = (lane == 0) && c0 >= 1 && lo >= 0 && lo < bw;
-                    uint4 V = make_uint4(NEG2, NEG2, NEG2, NEG2);
-                    int lv = NEG;
-                    if (i - pr < R) { /* recent row: shared-memory ring */
-                        const int16_t* src = ring + (pr & ring_mask) * ring_stride;
-                        if (inband) V = *reinterpret_cast<const uint4*>(src + off);
-                        if (need_left) lv = src[lo];
-                    } else {          /* old row: global / L2 */
-                        const int16_t* src = S + (size_t)pr * stride;
-                        if (inband) V = *reinterpret_cast<const uint4*>(src + off);
-                        if (need_left) lv = src[lo];
-                    }
-                    uint32_t leftw = __shfl_up_sync(0xffffffffu, V.w, 1);
-                    if (lane == 0) leftw = ((uint32_t)lv) << 16;
-                    const uint32_t d0 = __funnelshift_l(leftw, V.x, 16);
-                    const uint32_t d1 = __funnelshift_l(V.x, V.y, 16);
-                    const uint32_t d2 = __funnelshift_l(V.y, V.z, 16);
-                    const uint32_t d3 = __funnelshift_l(V.z, V.w, 16);
-                    a0 = __viaddmax_s16x2(d0, P.x, a0);
-                    a1 = __viaddmax_s16x2(d1, P.y, a1);
-                    a2 = __viaddmax_s16x2(d2, P.z, a2);
-                    a3 = __viaddmax_s16x2(d3, P.w, a3);
-                    a0 = __viaddmax_s16x2(V.x, G2, a0);
-                    a1 = __viaddmax_s16x2(V.y, G2, a1);
-                    a2 = __viaddmax_s16x2(V.z, G2, a2);
-                    a3 = __viaddmax_s16x2(V.w, G2, a3);
-                }
-
-                /* horizontal: inclusive prefix max over the 8 cells of the lane ... */
-                a0 = __vmaxs2(a0, __byte_perm(a0, NEG2, 0x1054));
-                a1 = __vmaxs2(a1, __byte_perm(a1, NEG2, 0x1054));
-                a2 = __vmaxs2(a2, __byte_perm(a2, NEG2, 0x1054));
-                a3 = __vmaxs2(a3, __byte_perm(a3, NEG2, 0x1054));
-                a1 = __vmaxs2(a1, __byte_perm(a0, a0, 0x3232));
-                a2 = __vmaxs2(a2, __byte_perm(a1, a1, 0x3232));
-                a3 = __vmaxs2(a3, __byte_perm(a2, a2, 0x3232));
-                /* ... then across lanes (packed, both halves equal) */
-                uint32_t tt = __byte_perm(a3, a3, 0x3232);
-                if (lane == 0) tt = __vmaxs2(tt, carry);
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t u = __shfl_up_sync(0xffffffffu, tt, d);
-                    if (lane >= d) tt = __vmaxs2(tt, u);
-                }
-                uint32_t excl = __shfl_up_sync(0xffffffffu, tt, 1);
-                if (lane == 0) excl = carry;
-                a0 = __vimax3_s16x2(a0, excl, NEG2);
-                a1 = __vimax3_s16x2(a1, excl, NEG2);
-                a2 = __vimax3_s16x2(a2, excl, NEG2);
-                a3 = __vimax3_s16x2(a3, excl, NEG2);
-                if (nchunks > 1) {
-                    carry = __shfl_sync(0xffffffffu, tt, 31);
-                    carry = __vmaxs2(carry, NEG2);
-                }
-
-                if (active) {
-                    const uint4 out = make_uint4(a0, a1, a2, a3);
-                    *reinterpret_cast<uint4*>(Srow + o0) = out;
-                    *reinterpret_cast<uint4*>(Rrow + o0) = out;
-                }
-
-                if (rec_sink(rec)) { /* sink row: candidate end cell at column len */
-                    const int eo = g.len - bs - k * CHUNK;
-                    if (eo >= 0 && eo < CHUNK && eo + k * CHUNK < bw) {
-                        const int e = eo & 7;
-                        uint32_t w = (e < 2) ? a0 : (e < 4) ? a1 : (e < 6) ? a2 : a3;
-                        int val = (e & 1) ? ((int)w >> 16) : (int)(int16_t)(w & 0xFFFFu);
-                        val = __shfl_sync(0xffffffffu, val, eo >> 3);
-                        if (val > best) {
-                            best = val;
-                            end_row = i;
-                        }
-                    }
-                }
-            }
-            po += np;
-            bs_prev = bs;
-            __syncwarp(); /* row i (ring + global) is visible to every lane before it is read */
-        }
-        return end_row;
+    __device__ __forceinline__ int32_t operator()(const Slot& s, const Params& p, WinState& st, const ReadGeom& g,
+                                                  const uint8_t* read) {
+        FillArgs fa;
+        fa.S = s.S;
+        fa.row_rec = s.row_rec;
+        fa.row_pred = s.row_pred;
+        fa.read = read;
+        fa.smem_sa = smem_sa;
+        fa.stride = p.stride;
+        fa.prof_stride = prof_stride;
+        fa.ring_stride = ring_stride;
+        fa.ring_mask = ring_mask;
+        fa.N = st.n_nodes;
+        fa.len = g.len;
+        fa.colsP = g.colsP;
+        fa.bw = g.bw;
+        fa.mg = p.match - p.gap;
+        fa.xg = p.mismatch - p.gap;
+        fa.gap = p.gap;
+        return fill_rows(fa);
     }
 };
 

@@ -87,3 +87,24 @@ for (fn, ln), s in by_line.most_common(top):
         src_cache[fn] = open(path).read().splitlines()
     text = src_cache.get(fn, [""] * (ln + 1))[ln - 1].strip() if ln and fn in src_cache else ""
     print(f"{100*s/total:6.2f}%  {fn}:{ln:<5d} {text[:100]}")
+
+if "--inst" in sys.argv:
+    by_line_inst = collections.Counter()
+    for r in rows[hdr_i + 1:]:
+        if len(r) < len(hdr):
+            continue
+        try:
+            addr = int(r[ci["Address"]], 16) if r[ci["Address"]].startswith("0x") else int(r[ci["Address"]])
+        except ValueError:
+            continue
+        inst = int(float(r[ci["Instructions Executed"]] or 0))
+        key = addr2line.get(addr - base)
+        if key is None:
+            continue
+        (fn, ln), sass = key
+        by_line_inst[(fn, ln)] += inst
+    scale = float(sys.argv[sys.argv.index("--inst") + 1])  # divide counts by this (e.g. total rows)
+    print("--- instructions per unit by line (top 60)")
+    for (fn, ln), c in by_line_inst.most_common(60):
+        text = src_cache.get(fn, [""] * (ln + 1))[ln - 1].strip() if ln and fn in src_cache else ""
+        print(f"{c/scale:8.2f}  {fn}:{ln:<5d} {text[:90]}")

@@ -25,3 +25,7 @@ torch.cuda.synchronize()
 pb.download()
 cons, cov, st = pb.get_consensus()
 print("windows", n, "failed", int((st != 0).sum()), "info", pb.info())
+pc = pb.phase_cycles()
+if pc:
+    tot = sum(pc.values())
+    print("phase cycles per window per launch:", {k: round(v / n / args.launches / 1e6, 2) for k, v in pc.items()}, "Mcycles; total", round(tot / n / args.launches / 1e6, 2))

@@ -101,13 +101,16 @@ void emu_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int
     std::atomic<int64_t> cursor{0};
     std::atomic<int64_t> total_cells{0};
     auto worker = [&]() {
-        std::vector<uint8_t> slab(slot_bytes + 64);
+        std::vector<uint8_t> slab(slot_bytes + 512);
         Slot s;
-        slot_bind(s, slab.data(), p, nullptr);
+        slot_bind(s, reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(slab.data()) + 255) & ~uintptr_t(255)), p, nullptr);
         std::vector<uint8_t> wbases;
         std::vector<int8_t> wweights;
         std::vector<int64_t> woff;
         ScalarFill fill;
+        std::vector<uint8_t> tb_mem(TB_SCRATCH_BYTES + 64);
+        TbScratch tbs;
+        tb_bind(tbs, reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tb_mem.data()) + 15) & ~uintptr_t(15)));
         for (;;) {
             const int64_t w = cursor.fetch_add(1);
             if (w >= n_windows) break;
@@ -137,7 +140,7 @@ void emu_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int
             wv.weights = wweights.data();
             wv.seq_off = woff.data();
             /* process_window writes its node count nowhere; recover it from the slot afterwards */
-            process_window(s, p, wv, fill, cons_out + w * (int64_t)stride_out,
+            process_window(s, p, wv, fill, tbs, cons_out + w * (int64_t)stride_out,
                            cov_out + w * (int64_t)stride_out, &cons_len[w], &status[w]);
             if (rank_out || n_nodes_out) {
                 /* n_nodes = 1 + max rank_of over nodes is not stored; count nodes via root != unset:
