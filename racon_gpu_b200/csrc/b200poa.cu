@@ -390,6 +390,8 @@ int32_t b200poa_batch_create(int32_t device_id, void* stream, size_t max_gpu_mem
     p.mismatch = mismatch_score;
     p.gap = gap_score;
     p.serial_topsort = std::getenv("B200POA_SERIAL_TOPSORT") ? 1 : 0;
+    p.ring_rows = 8;
+    p.ring_stride = p.stride;
     if (p.max_nodes > 65000) {
         delete b;
         return B200POA_INVALID_ARGUMENT;
@@ -562,6 +564,8 @@ int32_t b200poa_batch_launch(b200poa_batch* b) {
     a.prof_stride = b->prof_stride;
     a.ring_stride = b->ring_stride;
     a.ring_rows = b->ring_rows;
+    a.p.ring_rows = b->ring_rows;
+    a.p.ring_stride = b->ring_stride;
     a.phase_cycles = b->d_phase;
     const int grid = std::min(std::min(b->n_slots, occ * b->sm_count), b->poa_count);
     poa_window_kernel<<<grid, 32, (size_t)b->smem_bytes, b->stream>>>(a);

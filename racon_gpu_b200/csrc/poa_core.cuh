@@ -78,6 +78,8 @@ struct Params {
     int32_t max_cons;    /* row stride of the consensus / coverage outputs */
     int32_t match, mismatch, gap;
     int32_t serial_topsort; /* tests: use the serial DFS instead of the per-root sort */
+    int32_t ring_rows;      /* fill: rows in the shared-memory score ring (power of two) */
+    int32_t ring_stride;    /* fill: int16 cells per ring row */
 };
 
 /* Per resident warp workspace.  All pointers are into one device slab (see slot_bytes()). */
@@ -103,6 +105,7 @@ struct Slot {
     uint32_t* row_rec;  /* [MN+1] packed row record, see rec_make()                */
     uint32_t* row_poff; /* [MN+2] offset of the row's predecessor list       */
     uint32_t* row_pred; /* [ME+MN] predecessor ROW index (0 = virtual row) | its band start << 16, in in-edge order */
+    uint32_t* row_pfill; /* [ME+MN] the same list pre-digested for the fill, see pfill_make() */
     /* scores */
     int16_t* S;         /* [(MN+1)*stride]                                   */
     /* traceback output, written back to front */
@@ -162,7 +165,8 @@ void slot_bind(Slot& s, uint8_t* base, const Params& p, size_t* total_out) {
     POA_CARVE(e_w, int32_t, ME);
     POA_CARVE(row_rec, uint32_t, MN + 1 + 64); /* +64: the fill prefetches 32-row blocks past the end */
     POA_CARVE(row_poff, uint32_t, MN + 2);
-    POA_CARVE(row_pred, uint32_t, ME + MN + 96); /* +96: the fill prefetches 32-entry blocks past the end */
+    POA_CARVE(row_pred, uint32_t, ME + MN + 96);
+    POA_CARVE(row_pfill, uint32_t, ME + MN + 96); /* +96: the fill prefetches 32-entry blocks past the end */
     POA_CARVE(tb_node, int16_t, MN + ML + 2);
     POA_CARVE(tb_pos, int16_t, MN + ML + 2);
     POA_CARVE(asg, int32_t, ML + 1);
@@ -290,6 +294,15 @@ POA_FN int32_t prof_row_of(int32_t code) { /* A,C,G,T -> 0..3, anything else -> 
     }
 }
 
+/* Predecessor entry as the fill consumes it:  far[0] | band start/8 [1:12) | delta[12:32) (signed), with
+ * delta = (ring slot of the predecessor row) * ring_row_bytes - band_start * 2, so that the shared-memory
+ * address of the predecessor cell under column c is  ring_base + c*2 + delta  (one add per predecessor). */
+POA_FN uint32_t pfill_make(int32_t row, int32_t pr, int32_t bsp, int32_t ring_rows, int32_t ring_stride) {
+    const int32_t far = (row - pr >= ring_rows) ? 1 : 0;
+    const int32_t delta = (pr & (ring_rows - 1)) * ring_stride * 2 - bsp * 2;
+    return (uint32_t)far | ((uint32_t)(bsp >> 3) << 1) | ((uint32_t)delta << 12);
+}
+
 struct ReadGeom {
     int32_t len;    /* read length                                    */
     int32_t colsP;  /* (len+1) rounded up to a multiple of 8          */
@@ -344,12 +357,15 @@ POA_FN void build_program(const Slot& s, const Params& p, WinState& st, const Re
             int32_t first = 0;
             if (d == 0) {
                 s.row_pred[o] = 0;
+                s.row_pfill[o] = pfill_make(r + 1, 0, 0, p.ring_rows, p.ring_stride);
             } else {
                 int32_t k = 0;
                 for (uint16_t e = s.in_head[v]; e != NONE16; e = s.e_next[e], ++k) {
                     const int32_t pr = s.rank_of[s.e_src[e]] + 1;
                     if (k == 0) first = pr;
-                    s.row_pred[o + k] = (uint32_t)pr | ((uint32_t)band_start(g, pr, N) << 16);
+                    const int32_t pbs = band_start(g, pr, N);
+                    s.row_pred[o + k] = (uint32_t)pr | ((uint32_t)pbs << 16);
+                    s.row_pfill[o + k] = pfill_make(r + 1, pr, pbs, p.ring_rows, p.ring_stride);
                 }
             }
             if (c[l] > 255) wide[l] = 1;
@@ -912,8 +928,9 @@ POA_FN void topsort_serial(const Slot& s, const Params& p, WinState& st) {
  *   (position of v inside DFS_root), and DFS_i only changes when root i gains a node or an
  *   internal edge -- add_alignment marks exactly those roots dirty.  Per read:
  *     1. nodes of dirty roots: reset DFS marks, accumulate the root's stack bound;
- *     2. 32 roots at a time: prefix-sum the member counts; dirty multi-node roots re-run spoa's
- *        DFS restricted to their own members and store each member's position (lpos);
+ *     2. prefix-sum the member counts over root ids and compact the dirty multi-node roots into a
+ *        work list; then, 32 work items at a time, re-run spoa's DFS restricted to the root's own
+ *        members and store each member's position (lpos);
  *     3. every node: rank = offset[root] + lpos.
  * ---------------------------------------------------------------------------------------- */
 POA_FN void topsort_roots(const Slot& s, const Params& p, WinState& st) {
@@ -937,29 +954,46 @@ POA_FN void topsort_roots(const Slot& s, const Params& p, WinState& st) {
         }
     }
     POA_SYNC();
-    /* 2. walk the roots in id order */
-    int32_t out_run = 0, stk_run = 0;
+    /* 2a. offsets: prefix-sum the member counts over root ids; collect the dirty multi-node roots
+     *     into a compact work list (so that the DFS below keeps all 32 lanes busy) */
+    int32_t out_run = 0, stk_run = 0, n_work = 0;
     for (int32_t base = 0; base < N; base += 32) {
-        PerLane<int> c, nd;
+        PerLane<int> c, nd, wk;
         POA_LANES(l) {
             const int32_t i = base + l;
             c[l] = (i < N) ? (int)s.cnt[i] : 0;
-            nd[l] = (i < N && c[l] > 1 && s.dirty[i]) ? (int)s.need[i] + 1 : 0;
+            const int dirty = (i < N && c[l] > 0) ? (int)s.dirty[i] : 0;
+            wk[l] = (dirty && c[l] > 1) ? 1 : 0;
+            nd[l] = wk[l] ? (int)s.need[i] + 1 : 0;
+            if (dirty) {
+                s.dirty[i] = 0;
+                if (c[l] == 1) s.lpos[i] = 0;
+            }
         }
-        PerLane<int> oo = c, so = nd;
+        PerLane<int> oo = c, so = nd, wo = wk;
         const int32_t ctot = warp_exscan(oo);
         const int32_t stot = warp_exscan(so);
+        const int32_t wtot = warp_exscan(wo);
         POA_LANES(l) {
             const int32_t i = base + l;
             if (i >= N) continue;
             s.roff[i] = (uint32_t)(out_run + oo[l]);
-            if (c[l] == 0 || !s.dirty[i]) continue;
-            s.dirty[i] = 0;
-            if (c[l] == 1) {
-                s.lpos[i] = 0;
-                continue;
+            if (wk[l]) { /* work item: root id and where its DFS stack lives (c_score/c_pred are free here) */
+                s.c_score[n_work + wo[l]] = i;
+                s.c_pred[n_work + wo[l]] = stk_run + so[l];
             }
-            uint16_t* stk = s.stack + stk_run + so[l];
+        }
+        out_run += ctot;
+        stk_run += stot;
+        n_work += wtot;
+    }
+    POA_SYNC();
+    /* 2b. spoa's DFS restricted to the members of each dirty root, 32 roots at a time */
+    for (int32_t base = 0; base < n_work; base += 32) {
+        POA_LANES(l) {
+            if (base + l >= n_work) continue;
+            const int32_t i = s.c_score[base + l];
+            uint16_t* stk = s.stack + s.c_pred[base + l];
             int32_t sp = 0, out = 0;
             stk[sp++] = (uint16_t)i;
             while (sp != 0) {
@@ -997,8 +1031,6 @@ POA_FN void topsort_roots(const Slot& s, const Params& p, WinState& st) {
                 if (valid) --sp;
             }
         }
-        out_run += ctot;
-        stk_run += stot;
     }
     POA_SYNC();
     /* 3. ranks */

@@ -71,7 +71,8 @@ __device__ __forceinline__ void sts16(uint32_t addr, int v) {
 struct FillArgs { /* everything the row loop needs, and nothing else (keeps its register set small) */
     int16_t* S;
     const uint32_t* row_rec;
-    const uint32_t* row_pred;
+    const uint32_t* row_pred;  /* rank | band start: only read for predecessors older than the ring */
+    const uint32_t* row_pfill; /* the stream the row loop consumes */
     const uint8_t* read;
     uint32_t smem_sa;
     int32_t stride;      /* cells per global score row */
@@ -120,6 +121,7 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
     int16_t* const S = fa.S;
     const uint32_t* const row_rec = fa.row_rec;
     const uint32_t* const row_pred = fa.row_pred;
+    const uint32_t* const row_pfill = fa.row_pfill;
     const uint8_t* const read = fa.read;
     const int ring_mask = fa.ring_mask;
     const int R = ring_mask + 1;
@@ -154,8 +156,8 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
     uint32_t recA = row_rec[lane];
     uint32_t recB = row_rec[32 + lane];
     int pbase = 0; /* row_pred index held by lane 0 of predA */
-    uint32_t predA = row_pred[lane];
-    uint32_t predB = row_pred[32 + lane];
+    uint32_t predA = row_pfill[lane];
+    uint32_t predB = row_pfill[32 + lane];
     __syncwarp();
 
     int best = NEG, end_row = 0;
@@ -182,12 +184,11 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
         int16_t* Srow = S + (size_t)i * stride;
         const uint32_t ring_row_sa = ring_sa + (uint32_t)(i & ring_mask) * ring_row_bytes;
         uint32_t carry = NEG2; /* S[i][last column of the previous chunk], both halves */
-        const bool p0prev = rec_p0prev(rec);
 #pragma unroll 1
         while (po - pbase >= 32) { /* advance the predecessor stream window (uniform) */
             pbase += 32;
             predA = predB;
-            predB = row_pred[pbase + 32 + lane];
+            predB = row_pfill[pbase + 32 + lane];
         }
 
 #pragma unroll 1
@@ -197,28 +198,27 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
             const int c0 = bs + o0;           /* first column of this lane */
             const uint4 P = lds128(active ? prof_row_sa + (uint32_t)(k * CHUNK) * 2u : zero_sa);
             uint32_t a0 = NEG2, a1 = NEG2, a2 = NEG2, a3 = NEG2;
+            /* per-chunk constants of the band tests: an inactive lane can never be "in band" */
+            const unsigned lim_v = active ? (unsigned)(bw - 8) : 0u;         /* off <= lim_v; inactive lanes have off >= bw > 0 */
+            const unsigned lim_l = active ? (unsigned)bw : 0u;               /* off - 1 < lim_l */
+            const uint32_t c0_sa = ring_sa + (uint32_t)c0 * 2u;
 
 #pragma unroll 1
             for (int q = 0; q < np; ++q) {
-                /* predecessor row and its band start, from the register-resident CSR stream */
+                /* predecessor entry from the register-resident CSR stream (pre-digested by build_program) */
                 const int idx = po + q - pbase; /* >= 0: the window only advances between rows */
                 uint32_t pe = __shfl_sync(0xffffffffu, idx < 32 ? predA : predB, idx & 31);
-                if (idx >= 64) pe = row_pred[po + q]; /* in-degree > 32: straight from memory */
-                const bool useprev = (q == 0) & p0prev;
-                const int pr = useprev ? i - 1 : (int)(pe & 0xFFFFu);
-                const int bsp = useprev ? bs_prev : (int)(pe >> 16);
-                uint32_t src_sa = ring_sa + (uint32_t)(pr & ring_mask) * ring_row_bytes;
-                if (i - pr >= R) {
+                if (idx >= 64) pe = row_pfill[po + q]; /* in-degree > 32: straight from memory */
+                const int off = c0 - (int)((pe & 0xFFEu) << 2);  /* offset of column c0 in the predecessor row */
+                uint32_t cell_sa = c0_sa + (uint32_t)((int)pe >> 12);
+                if (pe & 1u) { /* rare: predecessor older than the ring */
+                    const int pr = (int)(row_pred[po + q] & 0xFFFFu);
                     fill_stage_far_row(S + (size_t)pr * stride, far_sa, bw);
-                    src_sa = far_sa;
+                    cell_sa = far_sa + (uint32_t)off * 2u;
                 }
-                const int off = c0 - bsp; /* offset of column c0 in the predecessor row */
-                const uint32_t cell_sa = src_sa + (uint32_t)off * 2u;
                 /* out-of-band loads are redirected to the NEG cells: no branches, no predicates */
-                const bool inband = active & ((unsigned)off <= (unsigned)(bw - 8));
-                const bool leftin = active & (c0 >= 1) & ((unsigned)(off - 1) < (unsigned)bw);
-                const uint4 V = lds128(inband ? cell_sa : neg_sa);
-                const uint32_t leftw = lds_u16(leftin ? cell_sa - 2u : neg_sa) << 16; /* cell (pr, c0-1) */
+                const uint4 V = lds128((unsigned)off <= lim_v ? cell_sa : neg_sa);
+                const uint32_t leftw = lds_u16((unsigned)(off - 1) < lim_l ? cell_sa - 2u : neg_sa) << 16; /* cell (pr, c0-1) */
                 const uint32_t d0 = __funnelshift_l(leftw, V.x, 16);
                 const uint32_t d1 = __funnelshift_l(V.x, V.y, 16);
                 const uint32_t d2 = __funnelshift_l(V.y, V.z, 16);
@@ -241,15 +241,12 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
             a1 = __vmaxs2(a1, __byte_perm(a0, a0, 0x3232));
             a2 = __vmaxs2(a2, __byte_perm(a1, a1, 0x3232));
             a3 = __vmaxs2(a3, __byte_perm(a2, a2, 0x3232));
-            /* ... then across lanes (packed, both halves equal).  Lanes below the shift distance
-             * max with NEG instead of branching. */
+            /* ... then across lanes (packed, both halves equal) */
             uint32_t tt = __byte_perm(a3, a3, 0x3232);
-            tt = __vmaxs2(tt, lane == 0 ? carry : NEG2);
+            if (nchunks > 1) tt = __vmaxs2(tt, lane == 0 ? carry : NEG2);
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t u = __shfl_up_sync(0xffffffffu, tt, d);
-                tt = __vmaxs2(tt, lane >= d ? u : NEG2);
-            }
+            for (int d = 1; d < 32; d <<= 1) /* lanes below d get their own value back from SHFL.UP: max is a no-op */
+                tt = __vmaxs2(tt, __shfl_up_sync(0xffffffffu, tt, d));
             uint32_t excl = __shfl_up_sync(0xffffffffu, tt, 1);
             excl = lane == 0 ? carry : excl;
             a0 = __vimax3_s16x2(a0, excl, NEG2);
@@ -300,6 +297,7 @@ struct CudaFill {
         fa.S = s.S;
         fa.row_rec = s.row_rec;
         fa.row_pred = s.row_pred;
+        fa.row_pfill = s.row_pfill;
         fa.read = read;
         fa.smem_sa = smem_sa;
         fa.stride = p.stride;

@@ -94,6 +94,8 @@ void emu_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int
     p.mismatch = x;
     p.gap = gap;
     p.serial_topsort = serial_topsort;
+    p.ring_rows = 8;
+    p.ring_stride = p.stride;
     Slot probe;
     size_t slot_bytes = 0;
     slot_bind(probe, nullptr, p, &slot_bytes);
