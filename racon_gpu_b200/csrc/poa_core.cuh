@@ -228,7 +228,7 @@ struct PhaseTimer {
 /* ------------------------------------------------------------------------------------------
  * Phase 0: backbone chain  (graph.cpp:274-292 add_sequence + :177-185; window.cpp:73-76)
  * ---------------------------------------------------------------------------------------- */
-POA_FN void init_backbone(const Slot& s, const Params& p, WinState& st, const uint8_t* seq,
+POA_FN_NOINLINE void init_backbone(const Slot& s, const Params& p, WinState& st, const uint8_t* seq,
                           const int8_t* w, int32_t len) {
     if (len > p.max_nodes || len - 1 > p.max_edges) {
         st.status = ST_SEQ_LEN_EXCEEDED_MAX_NODES;
@@ -328,7 +328,7 @@ POA_FN int32_t band_start(const ReadGeom& g, int32_t row, int32_t n_rows) {
     return bs & ~7;
 }
 
-POA_FN void build_program(const Slot& s, const Params& p, WinState& st, const ReadGeom& g) {
+POA_FN_NOINLINE void build_program(const Slot& s, const Params& p, WinState& st, const ReadGeom& g) {
     const int32_t N = st.n_nodes;
     int32_t run = 0; /* running predecessor offset (uniform) */
     POA_LANE0 { s.row_rec[0] = 0; }
@@ -452,7 +452,7 @@ POA_FN void tb_bind(TbScratch& t, uint8_t* base) {
     t.node = reinterpret_cast<uint16_t*>(base);
 }
 
-POA_FN int32_t traceback(const Slot& s, const Params& p, WinState& st, const ReadGeom& g,
+POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, const ReadGeom& g,
                          const uint8_t* read, int32_t end_row, const TbScratch& t) {
     const int32_t cap = p.max_nodes + p.max_len + 2;
     int32_t w = cap; /* write cursor (uniform) */
@@ -645,7 +645,7 @@ POA_FN int32_t traceback(const Slot& s, const Params& p, WinState& st, const Rea
 /* ------------------------------------------------------------------------------------------
  * Phase 4: add the alignment to the graph  (graph.cpp:155-272, 94-116)
  * ---------------------------------------------------------------------------------------- */
-POA_FN void add_alignment(const Slot& s, const Params& p, WinState& st, const uint8_t* read,
+POA_FN_NOINLINE void add_alignment(const Slot& s, const Params& p, WinState& st, const uint8_t* read,
                           const int8_t* wt, int32_t len, int32_t tb_begin) {
     const int32_t cap = p.max_nodes + p.max_len + 2;
     const int32_t N0 = st.n_nodes;
@@ -857,7 +857,7 @@ POA_FN void add_alignment(const Slot& s, const Params& p, WinState& st, const ui
  * Phase 5a: serial topological sort, the literal restatement of graph.cpp:294-354.
  * Kept for the test-suite (Params::serial_topsort) as the cross-check of the per-root sort.
  * ---------------------------------------------------------------------------------------- */
-POA_FN void topsort_serial(const Slot& s, const Params& p, WinState& st) {
+POA_FN_NOINLINE void topsort_serial(const Slot& s, const Params& p, WinState& st) {
     const int32_t N = st.n_nodes;
     for (int32_t base = 0; base < N; base += 32) {
         POA_LANES(l) {
@@ -933,7 +933,7 @@ POA_FN void topsort_serial(const Slot& s, const Params& p, WinState& st) {
  *        members and store each member's position (lpos);
  *     3. every node: rank = offset[root] + lpos.
  * ---------------------------------------------------------------------------------------- */
-POA_FN void topsort_roots(const Slot& s, const Params& p, WinState& st) {
+POA_FN_NOINLINE void topsort_roots(const Slot& s, const Params& p, WinState& st) {
     const int32_t N = st.n_nodes;
     for (int32_t base = 0; base < N; base += 32) {
         POA_LANES(l) {
@@ -1078,7 +1078,7 @@ POA_FN void consensus_scores_from(const Slot& s, int32_t N, int32_t first_rank, 
     }
 }
 
-POA_FN void generate_consensus(const Slot& s, const Params& p, WinState& st, uint8_t* out_cons,
+POA_FN_NOINLINE void generate_consensus(const Slot& s, const Params& p, WinState& st, uint8_t* out_cons,
                                uint16_t* out_cov, int32_t* out_len) {
     const int32_t N = st.n_nodes;
     int32_t len = 0;

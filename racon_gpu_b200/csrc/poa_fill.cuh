@@ -107,7 +107,10 @@ __device__ __noinline__ void fill_build_dyn_prof_row(uint32_t row_sa, int c, con
 }
 
 /* The row loop.  Deliberately NOT inlined into the window loop: compiled on its own, its loop
- * invariants stay in registers instead of being rematerialised around every use. */
+ * invariants stay in registers instead of being rematerialised around every use.
+ * FULLW = the row is exactly one 256-column chunk with all 32 lanes active (static band 256 on reads
+ * longer than the band: the headline configuration) -- no chunk loop, no lane masking, no carry. */
+template <bool FULLW>
 __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
     int lane; /* read once through volatile asm so that it is kept, not re-derived from S2R per use */
     asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
@@ -116,7 +119,7 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
     const uint32_t NEG2 = pack2(NEG, NEG);
     const uint32_t G2 = pack2(fa.gap, fa.gap);
     const int bw = fa.bw;
-    const int nchunks = (bw + CHUNK - 1) / CHUNK;
+    const int nchunks = FULLW ? 1 : (bw + CHUNK - 1) / CHUNK;
     const size_t stride = (size_t)fa.stride;
     int16_t* const S = fa.S;
     const uint32_t* const row_rec = fa.row_rec;
@@ -152,17 +155,19 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
         *reinterpret_cast<uint4*>(S + o) = make_uint4(0u, 0u, 0u, 0u);
         sts128(ring_sa + (uint32_t)o * 2u, make_uint4(0u, 0u, 0u, 0u));
     }
-    /* register-resident streams: lane l holds entry (base + l); the next 32 are prefetched */
+    /* register-resident streams: lane l holds entry (base + l); the next 32 are prefetched.
+     * predA always starts at or before the current row's first entry and is re-aligned (two shuffles)
+     * whenever a row's entries would run past it, so a row with <= 32 predecessors reads them all
+     * from predA with a single shuffle each. */
     uint32_t recA = row_rec[lane];
     uint32_t recB = row_rec[32 + lane];
-    int pbase = 0; /* row_pred index held by lane 0 of predA */
+    int pbase = 0; /* row_pfill index held by lane 0 of predA */
     uint32_t predA = row_pfill[lane];
     uint32_t predB = row_pfill[32 + lane];
     __syncwarp();
 
     int best = NEG, end_row = 0;
-    int po = 0;      /* running offset into row_pred (CSR is contiguous in row order) */
-    int bs_prev = 0; /* band start of row i-1 */
+    int po = 0; /* running offset into row_pfill (CSR is contiguous in row order) */
 #pragma unroll 1
     for (int i = 1; i <= N; ++i) {
         if ((i & 31) == 0) {
@@ -184,32 +189,37 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
         int16_t* Srow = S + (size_t)i * stride;
         const uint32_t ring_row_sa = ring_sa + (uint32_t)(i & ring_mask) * ring_row_bytes;
         uint32_t carry = NEG2; /* S[i][last column of the previous chunk], both halves */
-#pragma unroll 1
-        while (po - pbase >= 32) { /* advance the predecessor stream window (uniform) */
-            pbase += 32;
-            predA = predB;
-            predB = row_pfill[pbase + 32 + lane];
+        int rel = po - pbase;  /* lane of predA holding this row's first entry */
+        if (rel + np > 32) {   /* re-align the stream so that predA starts at this row (uniform, ~1 row in 18) */
+            const int src = (lane + rel) & 31;
+            const uint32_t xa = __shfl_sync(0xffffffffu, predA, src);
+            const uint32_t xb = __shfl_sync(0xffffffffu, predB, src);
+            predA = (lane + rel < 32) ? xa : xb;
+            if (rel >= 32) predA = row_pfill[po + lane]; /* a row with > 32 entries jumped past predB */
+            pbase = po;
+            predB = row_pfill[po + 32 + lane];
+            rel = 0;
         }
 
 #pragma unroll 1
         for (int k = 0; k < nchunks; ++k) {
-            const int o0 = k * CHUNK + lane8; /* offset of this lane's cells in the row */
-            const bool active = o0 < bw;
-            const int c0 = bs + o0;           /* first column of this lane */
-            const uint4 P = lds128(active ? prof_row_sa + (uint32_t)(k * CHUNK) * 2u : zero_sa);
+            const int o0 = FULLW ? lane8 : k * CHUNK + lane8; /* offset of this lane's cells in the row */
+            const bool active = FULLW ? true : (o0 < bw);
+            const int c0 = bs + o0;                            /* first column of this lane */
+            const uint4 P = lds128(active ? prof_row_sa + (uint32_t)(FULLW ? 0 : k * CHUNK) * 2u : zero_sa);
             uint32_t a0 = NEG2, a1 = NEG2, a2 = NEG2, a3 = NEG2;
             /* per-chunk constants of the band tests: an inactive lane can never be "in band" */
-            const unsigned lim_v = active ? (unsigned)(bw - 8) : 0u;         /* off <= lim_v; inactive lanes have off >= bw > 0 */
-            const unsigned lim_l = active ? (unsigned)bw : 0u;               /* off - 1 < lim_l */
+            const unsigned lim_v = active ? (unsigned)(bw - 8) : 0u; /* off <= lim_v; inactive lanes have off >= bw > 0 */
+            const unsigned lim_l = active ? (unsigned)bw : 0u;       /* off - 1 < lim_l */
             const uint32_t c0_sa = ring_sa + (uint32_t)c0 * 2u;
 
 #pragma unroll 1
             for (int q = 0; q < np; ++q) {
                 /* predecessor entry from the register-resident CSR stream (pre-digested by build_program) */
-                const int idx = po + q - pbase; /* >= 0: the window only advances between rows */
-                uint32_t pe = __shfl_sync(0xffffffffu, idx < 32 ? predA : predB, idx & 31);
-                if (idx >= 64) pe = row_pfill[po + q]; /* in-degree > 32: straight from memory */
-                const int off = c0 - (int)((pe & 0xFFEu) << 2);  /* offset of column c0 in the predecessor row */
+                uint32_t pe;
+                if (rel + q < 32) pe = __shfl_sync(0xffffffffu, predA, rel + q);
+                else pe = row_pfill[po + q]; /* in-degree > 32: straight from memory */
+                const int off = c0 - (int)((pe & 0xFFEu) << 2); /* offset of column c0 in the predecessor row */
                 uint32_t cell_sa = c0_sa + (uint32_t)((int)pe >> 12);
                 if (pe & 1u) { /* rare: predecessor older than the ring */
                     const int pr = (int)(row_pred[po + q] & 0xFFFFu);
@@ -243,7 +253,7 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
             a3 = __vmaxs2(a3, __byte_perm(a2, a2, 0x3232));
             /* ... then across lanes (packed, both halves equal) */
             uint32_t tt = __byte_perm(a3, a3, 0x3232);
-            if (nchunks > 1) tt = __vmaxs2(tt, lane == 0 ? carry : NEG2);
+            if (!FULLW && nchunks > 1) tt = __vmaxs2(tt, lane == 0 ? carry : NEG2);
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) /* lanes below d get their own value back from SHFL.UP: max is a no-op */
                 tt = __vmaxs2(tt, __shfl_up_sync(0xffffffffu, tt, d));
@@ -253,7 +263,7 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
             a1 = __vimax3_s16x2(a1, excl, NEG2);
             a2 = __vimax3_s16x2(a2, excl, NEG2);
             a3 = __vimax3_s16x2(a3, excl, NEG2);
-            if (nchunks > 1) {
+            if (!FULLW && nchunks > 1) {
                 carry = __shfl_sync(0xffffffffu, tt, 31);
                 carry = __vmaxs2(carry, NEG2);
             }
@@ -265,8 +275,8 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
             }
 
             if (rec_sink(rec)) { /* sink row: candidate end cell at column len */
-                const int eo = fa.len - bs - k * CHUNK;
-                if (eo >= 0 && eo < CHUNK && eo + k * CHUNK < bw) {
+                const int eo = fa.len - bs - (FULLW ? 0 : k * CHUNK);
+                if (eo >= 0 && eo < CHUNK && eo + (FULLW ? 0 : k * CHUNK) < bw) {
                     const int e8 = eo & 7;
                     uint32_t w = (e8 < 2) ? a0 : (e8 < 4) ? a1 : (e8 < 6) ? a2 : a3;
                     int val = (e8 & 1) ? ((int)w >> 16) : (int)(int16_t)(w & 0xFFFFu);
@@ -279,7 +289,6 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
             }
         }
         po += np;
-        bs_prev = bs;
         __syncwarp(); /* row i (ring + global) is visible to every lane before it is read */
     }
     return end_row;
@@ -311,7 +320,7 @@ struct CudaFill {
         fa.mg = p.match - p.gap;
         fa.xg = p.mismatch - p.gap;
         fa.gap = p.gap;
-        return fill_rows(fa);
+        return (g.bw == CHUNK) ? fill_rows<true>(fa) : fill_rows<false>(fa);
     }
 };
 
