@@ -101,6 +101,7 @@ struct Slot {
     uint16_t* e_dst;    /* [ME] */
     uint16_t* e_next;   /* [ME] next in-edge of e_dst, insertion order       */
     int32_t* e_w;       /* [ME] total weight                                 */
+    uint8_t* e_ord;     /* [ME] position of the edge in its target's in-edge list (fixed at creation) */
     /* per-read "row program": the graph linearised in rank order (row = rank + 1) */
     uint32_t* row_rec;  /* [MN+1] packed row record, see rec_make()                */
     uint32_t* row_poff; /* [MN+2] offset of the row's predecessor list       */
@@ -163,6 +164,7 @@ void slot_bind(Slot& s, uint8_t* base, const Params& p, size_t* total_out) {
     POA_CARVE(e_dst, uint16_t, ME);
     POA_CARVE(e_next, uint16_t, ME);
     POA_CARVE(e_w, int32_t, ME);
+    POA_CARVE(e_ord, uint8_t, ME);
     POA_CARVE(row_rec, uint32_t, MN + 1 + 64); /* +64: the fill prefetches 32-row blocks past the end */
     POA_CARVE(row_poff, uint32_t, MN + 2);
     POA_CARVE(row_pred, uint32_t, ME + MN + 96);
@@ -248,6 +250,7 @@ POA_FN_NOINLINE void init_backbone(const Slot& s, const Params& p, WinState& st,
             s.root[k] = (uint16_t)k;
             s.lpos[k] = 0;
             s.cnt[k] = 1;
+            s.need[k] = 0;
             s.dirty[k] = 0;
             s.rank_of[k] = (uint16_t)k;
             s.node_at[k] = (uint16_t)k;
@@ -256,6 +259,7 @@ POA_FN_NOINLINE void init_backbone(const Slot& s, const Params& p, WinState& st,
                 s.e_dst[k - 1] = (uint16_t)k;
                 s.e_next[k - 1] = NONE16;
                 s.e_w[k - 1] = (int32_t)w[k - 1] + (int32_t)w[k];
+                s.e_ord[k - 1] = 0;
             }
         }
     }
@@ -274,14 +278,13 @@ POA_FN_NOINLINE void init_backbone(const Slot& s, const Params& p, WinState& st,
 /* Packed row record (one u32 per row, read 32 rows at a time by the fill and distributed by
  * shuffle):  code[0:8) | sink[8] | profile row[9:12) | pred0-is-previous-row[12] | npred[13:21) |
  * band start / 8 [21:32). */
-POA_FN uint32_t rec_make(int32_t code, bool sink, int32_t prow, bool p0prev, int32_t npred, int32_t bs) {
-    return (uint32_t)code | (sink ? 0x100u : 0u) | ((uint32_t)prow << 9) | (p0prev ? 0x1000u : 0u) |
+POA_FN uint32_t rec_make(int32_t code, bool sink, int32_t prow, int32_t npred, int32_t bs) {
+    return (uint32_t)code | (sink ? 0x100u : 0u) | ((uint32_t)prow << 9) |
            ((uint32_t)npred << 13) | ((uint32_t)(bs >> 3) << 21);
 }
 POA_FN int32_t rec_code(uint32_t r) { return (int32_t)(r & 0xFFu); }
 POA_FN bool rec_sink(uint32_t r) { return (r & 0x100u) != 0; }
 POA_FN int32_t rec_prow(uint32_t r) { return (int32_t)((r >> 9) & 7u); }
-POA_FN bool rec_p0prev(uint32_t r) { return (r & 0x1000u) != 0; }
 POA_FN int32_t rec_npred(uint32_t r) { return (int32_t)((r >> 13) & 0xFFu); }
 POA_FN int32_t rec_bs(uint32_t r) { return (int32_t)(r >> 21) << 3; }
 POA_FN int32_t prof_row_of(int32_t code) { /* A,C,G,T -> 0..3, anything else -> 4 (profile row built on demand) */
@@ -329,56 +332,79 @@ POA_FN int32_t band_start(const ReadGeom& g, int32_t row, int32_t n_rows) {
 }
 
 POA_FN_NOINLINE void build_program(const Slot& s, const Params& p, WinState& st, const ReadGeom& g) {
-    const int32_t N = st.n_nodes;
+    const int32_t N = st.n_nodes, E = st.n_edges;
+    /* pass A, node-parallel, 64 rows per step: row records and CSR offsets (row r+1 <-> node_at[r]) */
     int32_t run = 0; /* running predecessor offset (uniform) */
     POA_LANE0 { s.row_rec[0] = 0; }
     PerLane<int> wide;
     POA_LANES(l) { wide[l] = 0; }
-    for (int32_t base = 0; base < N; base += 32) {
-        PerLane<int> c;
-        POA_LANES(l) {
-            const int32_t r = base + l;
-            c[l] = 0;
-            if (r < N) {
-                const int32_t v = s.node_at[r];
-                const int32_t d = s.nin[v];
-                c[l] = d ? d : 1;
-            }
+    for (int32_t base = 0; base < N; base += 64) {
+        PerLane<int> c0, c1;
+        POA_LANES(l) { /* both rows' loads are independent: two round trips for 64 rows */
+            const int32_t r0 = base + 2 * l, r1 = r0 + 1;
+            const int32_t v0 = r0 < N ? (int32_t)s.node_at[r0] : 0;
+            const int32_t v1 = r1 < N ? (int32_t)s.node_at[r1] : 0;
+            const int32_t d0 = s.nin[v0], d1 = s.nin[v1];
+            const int32_t k0 = s.code[v0], k1 = s.code[v1];
+            const bool s0 = s.nout[v0] == 0, s1 = s.nout[v1] == 0;
+            c0[l] = r0 < N ? (d0 ? d0 : 1) : 0;
+            c1[l] = r1 < N ? (d1 ? d1 : 1) : 0;
+            if (c0[l] > 255 || c1[l] > 255) wide[l] = 1;
+            if (r0 < N) s.row_rec[r0 + 1] = rec_make(k0, s0, prof_row_of(k0), c0[l] & 0xFF, band_start(g, r0 + 1, N));
+            if (r1 < N) s.row_rec[r1 + 1] = rec_make(k1, s1, prof_row_of(k1), c1[l] & 0xFF, band_start(g, r1 + 1, N));
         }
-        PerLane<int> off = c;
+        PerLane<int> off;
+        POA_LANES(l) { off[l] = c0[l] + c1[l]; }
         const int32_t tot = warp_exscan(off);
         POA_LANES(l) {
-            const int32_t r = base + l;
-            if (r >= N) continue;
-            const int32_t v = s.node_at[r];
-            const int32_t o = run + off[l];
-            s.row_poff[r + 1] = (uint32_t)o;
-            const int32_t d = s.nin[v];
-            int32_t first = 0;
-            if (d == 0) {
-                s.row_pred[o] = 0;
-                s.row_pfill[o] = pfill_make(r + 1, 0, 0, p.ring_rows, p.ring_stride);
-            } else {
-                int32_t k = 0;
-                for (uint16_t e = s.in_head[v]; e != NONE16; e = s.e_next[e], ++k) {
-                    const int32_t pr = s.rank_of[s.e_src[e]] + 1;
-                    if (k == 0) first = pr;
-                    const int32_t pbs = band_start(g, pr, N);
-                    s.row_pred[o + k] = (uint32_t)pr | ((uint32_t)pbs << 16);
-                    s.row_pfill[o + k] = pfill_make(r + 1, pr, pbs, p.ring_rows, p.ring_stride);
+            const int32_t r0 = base + 2 * l, r1 = r0 + 1;
+            const int32_t o0 = run + off[l], o1 = o0 + c0[l];
+            if (r0 < N) {
+                s.row_poff[r0 + 1] = (uint32_t)o0;
+                if (s.nin[s.node_at[r0]] == 0) { /* virtual predecessor row 0 (sisd_alignment_engine.cpp:289-290) */
+                    s.row_pred[o0] = 0;
+                    s.row_pfill[o0] = pfill_make(r0 + 1, 0, 0, p.ring_rows, p.ring_stride);
                 }
             }
-            if (c[l] > 255) wide[l] = 1;
-            const int32_t code = s.code[v];
-            s.row_rec[r + 1] = rec_make(code, s.nout[v] == 0, prof_row_of(code), first == r, c[l] & 0xFF,
-                                        band_start(g, r + 1, N));
+            if (r1 < N) {
+                s.row_poff[r1 + 1] = (uint32_t)o1;
+                if (s.nin[s.node_at[r1]] == 0) {
+                    s.row_pred[o1] = 0;
+                    s.row_pfill[o1] = pfill_make(r1 + 1, 0, 0, p.ring_rows, p.ring_stride);
+                }
+            }
         }
         run += tot;
     }
     POA_LANE0 { s.row_poff[N + 1] = (uint32_t)run; }
     if (warp_ballot(wide)) st.status = ST_EDGE_COUNT_EXCEEDED; /* in-degree > 255 does not fit the record */
     POA_SYNC();
-    (void)p;
+    /* pass B, edge-parallel, 64 edges per step: every edge drops its source row into its slot of the
+     * target's predecessor list (slot = e_ord, the edge's position in the in-edge list, fixed when the
+     * edge was created) -- no linked-list walking, three dependent loads per edge. */
+    for (int32_t base = 0; base < E; base += 64) {
+        POA_LANES(l) {
+            const int32_t e0 = base + l, e1 = base + 32 + l;
+            const bool ok0 = e0 < E, ok1 = e1 < E;
+            const int32_t d0 = ok0 ? (int32_t)s.e_dst[e0] : 0, d1 = ok1 ? (int32_t)s.e_dst[e1] : 0;
+            const int32_t u0 = ok0 ? (int32_t)s.e_src[e0] : 0, u1 = ok1 ? (int32_t)s.e_src[e1] : 0;
+            const int32_t q0 = ok0 ? (int32_t)s.e_ord[e0] : 0, q1 = ok1 ? (int32_t)s.e_ord[e1] : 0;
+            const int32_t rd0 = s.rank_of[d0] + 1, rd1 = s.rank_of[d1] + 1;
+            const int32_t ru0 = s.rank_of[u0] + 1, ru1 = s.rank_of[u1] + 1;
+            const int32_t o0 = (int32_t)s.row_poff[rd0] + q0, o1 = (int32_t)s.row_poff[rd1] + q1;
+            if (ok0) {
+                const int32_t pbs = band_start(g, ru0, N);
+                s.row_pred[o0] = (uint32_t)ru0 | ((uint32_t)pbs << 16);
+                s.row_pfill[o0] = pfill_make(rd0, ru0, pbs, p.ring_rows, p.ring_stride);
+            }
+            if (ok1) {
+                const int32_t pbs = band_start(g, ru1, N);
+                s.row_pred[o1] = (uint32_t)ru1 | ((uint32_t)pbs << 16);
+                s.row_pfill[o1] = pfill_make(rd1, ru1, pbs, p.ring_rows, p.ring_stride);
+            }
+        }
+    }
+    POA_SYNC();
 }
 
 /* Score accessor used by the traceback (and by the scalar fill): cells outside the row's band
@@ -426,8 +452,9 @@ struct TbScratch {           /* device: shared memory (the fill's ring area); em
     uint32_t* poff;          /* [TB_ROWS+1] poff[k] = CSR offset of row (r_hi - k); poff[TB_ROWS] unused */
     uint32_t* pred;          /* [TB_PRED_CAP] predecessor entries of the rows, per row at poff - pred_base */
     uint16_t* node;          /* [TB_ROWS]   node id of row (r_hi - k)                   */
+    uint8_t* readc;          /* [TB_COLS + 8] read base under column c at c - c_lo (column c <-> read[c-1]) */
 };
-constexpr int TB_SCRATCH_BYTES = TB_ROWS * TB_COLS * 2 + TB_ROWS * 4 + (TB_ROWS + 1) * 4 + TB_PRED_CAP * 4 + TB_ROWS * 2 + 28;
+constexpr int TB_SCRATCH_BYTES = TB_ROWS * TB_COLS * 2 + TB_ROWS * 4 + (TB_ROWS + 1) * 4 + TB_PRED_CAP * 4 + TB_ROWS * 2 + TB_COLS + 8 + 28;
 
 struct alignas(16) Vec16 { /* 8 int16 cells moved as one 128-bit access */
     uint32_t x, y, z, w;
@@ -450,6 +477,8 @@ POA_FN void tb_bind(TbScratch& t, uint8_t* base) {
     t.pred = reinterpret_cast<uint32_t*>(base);
     base += TB_PRED_CAP * 4;
     t.node = reinterpret_cast<uint16_t*>(base);
+    base += TB_ROWS * 2;
+    t.readc = base;
 }
 
 POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, const ReadGeom& g,
@@ -505,6 +534,8 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
                     t.node[l] = row >= 1 ? s.node_at[row - 1] : (uint16_t)0;
                     cnt[l] = row >= 1 ? rec_npred(rec) : 0;
                 }
+                for (int32_t c = c_lo + l; c < c_lo + TB_COLS; c += 32) /* read bases under the tile's columns */
+                    t.readc[c - c_lo] = (c >= 1 && c <= g.len) ? read[c - 1] : (uint8_t)0;
             }
             POA_SYNC();
             /* CSR entries of rows r_lo..r_hi are contiguous: [poff(r_lo'), poff(r_hi) + np(r_hi)) */
@@ -536,7 +567,7 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
         const uint32_t rec = t.rec[ti];
         const int32_t np = rec_npred(rec);
         const int32_t po = (int32_t)t.poff[ti];
-        const int32_t prof = (j > 0 && rec_code(rec) == (int32_t)read[j - 1]) ? mg : xg;
+        const int32_t prof = (j > 0 && rec_code(rec) == (int32_t)t.readc[j - c_lo]) ? mg : xg;
         bool in_tile = (np <= 32) && (po - pred_base + np <= pred_n);
         int32_t found = 0;
         if (in_tile) {
@@ -651,32 +682,37 @@ POA_FN_NOINLINE void add_alignment(const Slot& s, const Params& p, WinState& st,
     const int32_t N0 = st.n_nodes;
 
     /* (a) resolve every read position: existing node, or a new node (unaligned / aligned to x).
-     *     asg[pos] >= 0 : existing node;  -1 : new, unaligned;  -2-x : new, aligned to node x. */
-    for (int32_t base = tb_begin; base < cap; base += 32) {
+     *     asg[pos] >= 0 : existing node;  -1 : new, unaligned;  -2-x : new, aligned to node x.
+     *     Two alignment entries per lane per step: their dependent loads overlap. */
+    for (int32_t base = tb_begin; base < cap; base += 64) {
         POA_LANES(l) {
-            const int32_t k = base + l;
-            if (k >= cap) continue;
-            const int32_t pos = s.tb_pos[k];
-            if (pos < 0) continue;
-            const int32_t x = s.tb_node[k];
-            const uint8_t letter = read[pos];
-            int32_t a;
-            if (x < 0) {
-                a = -1;
-            } else if (s.code[x] == letter) {
-                a = x;
-            } else {
-                a = -2 - x;
-                const int32_t na = s.aln_cnt[x];
-                for (int32_t q = 0; q < na; ++q) {
-                    const int32_t y = s.aln[x * KA + q];
-                    if (s.code[y] == letter) {
-                        a = y;
-                        break;
+            const int32_t k0 = base + l, k1 = base + 32 + l;
+            const int32_t pos0 = k0 < cap ? (int32_t)s.tb_pos[k0] : -1, pos1 = k1 < cap ? (int32_t)s.tb_pos[k1] : -1;
+            const int32_t x0 = k0 < cap ? (int32_t)s.tb_node[k0] : -1, x1 = k1 < cap ? (int32_t)s.tb_node[k1] : -1;
+            const uint8_t let0 = pos0 >= 0 ? read[pos0] : (uint8_t)0, let1 = pos1 >= 0 ? read[pos1] : (uint8_t)0;
+            const uint8_t cx0 = x0 >= 0 ? s.code[x0] : (uint8_t)0, cx1 = x1 >= 0 ? s.code[x1] : (uint8_t)0;
+            for (int32_t u = 0; u < 2; ++u) {
+                const int32_t pos = u ? pos1 : pos0, x = u ? x1 : x0;
+                const uint8_t letter = u ? let1 : let0, cx = u ? cx1 : cx0;
+                if (pos < 0) continue;
+                int32_t a;
+                if (x < 0) {
+                    a = -1;
+                } else if (cx == letter) {
+                    a = x;
+                } else {
+                    a = -2 - x;
+                    const int32_t na = s.aln_cnt[x];
+                    for (int32_t q = 0; q < na; ++q) {
+                        const int32_t y = s.aln[x * KA + q];
+                        if (s.code[y] == letter) {
+                            a = y;
+                            break;
+                        }
                     }
                 }
+                s.asg[pos] = a;
             }
-            s.asg[pos] = a;
         }
     }
     POA_SYNC();
@@ -711,6 +747,7 @@ POA_FN_NOINLINE void add_alignment(const Slot& s, const Params& p, WinState& st,
             s.cov[v] = 0;
             s.aln_cnt[v] = 0;
             s.cnt[v] = 0;   /* v may become a root itself */
+            s.need[v] = 0;
             s.dirty[v] = 0;
             s.lpos[v] = 0;
             s.root[v] = NONE16; /* resolved in (c) */
@@ -835,6 +872,7 @@ POA_FN_NOINLINE void add_alignment(const Slot& s, const Params& p, WinState& st,
                 s.e_dst[e] = (uint16_t)cur;
                 s.e_next[e] = NONE16;
                 s.e_w[e] = w;
+                s.e_ord[e] = (uint8_t)(s.nin[cur] < 255 ? s.nin[cur] : 255);
                 if (s.in_tail[cur] == NONE16) s.in_head[cur] = (uint16_t)e;
                 else s.e_next[s.in_tail[cur]] = (uint16_t)e;
                 s.in_tail[cur] = (uint16_t)e;
@@ -935,52 +973,73 @@ POA_FN_NOINLINE void topsort_serial(const Slot& s, const Params& p, WinState& st
  * ---------------------------------------------------------------------------------------- */
 POA_FN_NOINLINE void topsort_roots(const Slot& s, const Params& p, WinState& st) {
     const int32_t N = st.n_nodes;
-    for (int32_t base = 0; base < N; base += 32) {
+    /* 1. members of dirty roots: reset DFS marks, accumulate the root's stack bound.  Two nodes per lane
+     *    per step so that the dependent loads (root -> dirty) of both are in flight together. */
+    for (int32_t base = 0; base < N; base += 64) {
         POA_LANES(l) {
-            if (base + l < N) s.need[base + l] = 0;
-        }
-    }
-    POA_SYNC();
-    /* 1. members of dirty roots */
-    for (int32_t base = 0; base < N; base += 32) {
-        POA_LANES(l) {
-            const int32_t v = base + l;
-            if (v >= N) continue;
-            const int32_t r = s.root[v];
-            if (!s.dirty[r]) continue;
-            s.marks[v] = 0;
-            s.check[v] = 1;
-            poa_atomic_add(&s.need[r], (uint32_t)(s.nin[v] + s.aln_cnt[v] + 1));
-        }
-    }
-    POA_SYNC();
-    /* 2a. offsets: prefix-sum the member counts over root ids; collect the dirty multi-node roots
-     *     into a compact work list (so that the DFS below keeps all 32 lanes busy) */
-    int32_t out_run = 0, stk_run = 0, n_work = 0;
-    for (int32_t base = 0; base < N; base += 32) {
-        PerLane<int> c, nd, wk;
-        POA_LANES(l) {
-            const int32_t i = base + l;
-            c[l] = (i < N) ? (int)s.cnt[i] : 0;
-            const int dirty = (i < N && c[l] > 0) ? (int)s.dirty[i] : 0;
-            wk[l] = (dirty && c[l] > 1) ? 1 : 0;
-            nd[l] = wk[l] ? (int)s.need[i] + 1 : 0;
-            if (dirty) {
-                s.dirty[i] = 0;
-                if (c[l] == 1) s.lpos[i] = 0;
+            const int32_t v0 = base + l, v1 = base + 32 + l;
+            const int32_t r0 = v0 < N ? (int32_t)s.root[v0] : 0, r1 = v1 < N ? (int32_t)s.root[v1] : 0;
+            const bool d0 = v0 < N && s.dirty[r0], d1 = v1 < N && s.dirty[r1];
+            if (d0) {
+                s.marks[v0] = 0;
+                s.check[v0] = 1;
+                poa_atomic_add(&s.need[r0], (uint32_t)(s.nin[v0] + s.aln_cnt[v0] + 1));
+            }
+            if (d1) {
+                s.marks[v1] = 0;
+                s.check[v1] = 1;
+                poa_atomic_add(&s.need[r1], (uint32_t)(s.nin[v1] + s.aln_cnt[v1] + 1));
             }
         }
-        PerLane<int> oo = c, so = nd, wo = wk;
+    }
+    POA_SYNC();
+    /* 2a. offsets: prefix-sum the member counts over root ids (two ids per lane per step); collect the
+     *     dirty multi-node roots into a compact work list (so that the DFS below keeps all lanes busy);
+     *     need[] is consumed and zeroed for the next read. */
+    int32_t out_run = 0, stk_run = 0, n_work = 0;
+    for (int32_t base = 0; base < N; base += 64) {
+        PerLane<int> ca, cb, na, nb, wa, wb;
+        POA_LANES(l) {
+            const int32_t i0 = base + 2 * l, i1 = i0 + 1;
+            ca[l] = (i0 < N) ? (int)s.cnt[i0] : 0;
+            cb[l] = (i1 < N) ? (int)s.cnt[i1] : 0;
+            const int da = (i0 < N && ca[l] > 0) ? (int)s.dirty[i0] : 0;
+            const int db = (i1 < N && cb[l] > 0) ? (int)s.dirty[i1] : 0;
+            wa[l] = (da && ca[l] > 1) ? 1 : 0;
+            wb[l] = (db && cb[l] > 1) ? 1 : 0;
+            na[l] = wa[l] ? (int)s.need[i0] + 1 : 0;
+            nb[l] = wb[l] ? (int)s.need[i1] + 1 : 0;
+            if (da) {
+                s.dirty[i0] = 0;
+                s.need[i0] = 0;
+                if (ca[l] == 1) s.lpos[i0] = 0;
+            }
+            if (db) {
+                s.dirty[i1] = 0;
+                s.need[i1] = 0;
+                if (cb[l] == 1) s.lpos[i1] = 0;
+            }
+        }
+        PerLane<int> oo, so, wo;
+        POA_LANES(l) {
+            oo[l] = ca[l] + cb[l];
+            so[l] = na[l] + nb[l];
+            wo[l] = wa[l] + wb[l];
+        }
         const int32_t ctot = warp_exscan(oo);
         const int32_t stot = warp_exscan(so);
         const int32_t wtot = warp_exscan(wo);
         POA_LANES(l) {
-            const int32_t i = base + l;
-            if (i >= N) continue;
-            s.roff[i] = (uint32_t)(out_run + oo[l]);
-            if (wk[l]) { /* work item: root id and where its DFS stack lives (c_score/c_pred are free here) */
-                s.c_score[n_work + wo[l]] = i;
+            const int32_t i0 = base + 2 * l, i1 = i0 + 1;
+            if (i0 < N) s.roff[i0] = (uint32_t)(out_run + oo[l]);
+            if (i1 < N) s.roff[i1] = (uint32_t)(out_run + oo[l] + ca[l]);
+            if (wa[l]) { /* work item: root id and where its DFS stack lives (c_score/c_pred are free here) */
+                s.c_score[n_work + wo[l]] = i0;
                 s.c_pred[n_work + wo[l]] = stk_run + so[l];
+            }
+            if (wb[l]) {
+                s.c_score[n_work + wo[l] + wa[l]] = i1;
+                s.c_pred[n_work + wo[l] + wa[l]] = stk_run + so[l] + na[l];
             }
         }
         out_run += ctot;
@@ -1033,14 +1092,21 @@ POA_FN_NOINLINE void topsort_roots(const Slot& s, const Params& p, WinState& st)
         }
     }
     POA_SYNC();
-    /* 3. ranks */
-    for (int32_t base = 0; base < N; base += 32) {
+    /* 3. ranks (two nodes per lane per step) */
+    for (int32_t base = 0; base < N; base += 64) {
         POA_LANES(l) {
-            const int32_t v = base + l;
-            if (v >= N) continue;
-            const int32_t r = (int32_t)s.roff[s.root[v]] + (int32_t)s.lpos[v];
-            s.rank_of[v] = (uint16_t)r;
-            s.node_at[r] = (uint16_t)v;
+            const int32_t v0 = base + l, v1 = base + 32 + l;
+            const int32_t q0 = v0 < N ? (int32_t)s.root[v0] : 0, q1 = v1 < N ? (int32_t)s.root[v1] : 0;
+            const int32_t p0 = v0 < N ? (int32_t)s.lpos[v0] : 0, p1 = v1 < N ? (int32_t)s.lpos[v1] : 0;
+            const int32_t r0 = (int32_t)s.roff[q0] + p0, r1 = (int32_t)s.roff[q1] + p1;
+            if (v0 < N) {
+                s.rank_of[v0] = (uint16_t)r0;
+                s.node_at[r0] = (uint16_t)v0;
+            }
+            if (v1 < N) {
+                s.rank_of[v1] = (uint16_t)r1;
+                s.node_at[r1] = (uint16_t)v1;
+            }
         }
     }
     POA_SYNC();

@@ -270,7 +270,7 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
 
             if (active) {
                 const uint4 out = make_uint4(a0, a1, a2, a3);
-                *reinterpret_cast<uint4*>(Srow + o0) = out;
+                __stcs(reinterpret_cast<uint4*>(Srow + o0), out); /* streaming: written once, read once by the traceback; keep L2 for the graph */
                 sts128(ring_row_sa + (uint32_t)o0 * 2u, out);
             }
 

@@ -9,7 +9,7 @@ import csv, io, os, re, subprocess, sys, tempfile, collections
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep = sys.argv[1]
 top = int(sys.argv[sys.argv.index("--top") + 1]) if "--top" in sys.argv else 25
-so = os.path.join(ROOT, "racon_gpu_b200", "libb200poa.so")
+so = os.environ.get("B200POA_SO", os.path.join(ROOT, "racon_gpu_b200", "libb200poa.so"))
 
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
