@@ -441,20 +441,23 @@ POA_FN int32_t score_at_bs(const Slot& s, const Params& p, const ReadGeom& g, in
  *   to reading global memory directly.
  *   Output: tb_node/tb_pos filled back to front; returns the index of the first (leftmost) entry.
  * ---------------------------------------------------------------------------------------- */
-constexpr int TB_ROWS = 32;    /* tile rows (one per lane when loading) */
-constexpr int TB_CHUNKS = 7;   /* tile columns in 8-cell chunks */
+constexpr int TB_ROWS = 32;    /* tile rows (one per lane) */
+constexpr int TB_CHUNKS = 5;   /* tile columns in 8-cell chunks */
 constexpr int TB_COLS = TB_CHUNKS * 8;
 constexpr int TB_PRED_CAP = 192; /* predecessor entries a tile can hold */
+constexpr int TB_NPMAX = 12;   /* in-degree a lane resolves inside the tile (more: global fallback) */
 
 struct TbScratch {           /* device: shared memory (the fill's ring area); emulation: heap */
     int16_t* cells;          /* [TB_ROWS * TB_COLS]  row (r_hi - k) at k*TB_COLS, column c at c - c_lo */
     uint32_t* rec;           /* [TB_ROWS]   row records                                 */
-    uint32_t* poff;          /* [TB_ROWS+1] poff[k] = CSR offset of row (r_hi - k); poff[TB_ROWS] unused */
+    uint32_t* poff;          /* [TB_ROWS+1] poff[k] = CSR offset of row (r_hi - k)      */
     uint32_t* pred;          /* [TB_PRED_CAP] predecessor entries of the rows, per row at poff - pred_base */
     uint16_t* node;          /* [TB_ROWS]   node id of row (r_hi - k)                   */
-    uint8_t* readc;          /* [TB_COLS + 8] read base under column c at c - c_lo (column c <-> read[c-1]) */
+    uint8_t* readc;          /* [TB_COLS]   read base under column c at c - c_lo (column c <-> read[c-1]) */
+    uint8_t* dec;            /* [TB_ROWS * TB_COLS] decision per cell: 0 = not computed, else move | row delta << 2 */
 };
-constexpr int TB_SCRATCH_BYTES = TB_ROWS * TB_COLS * 2 + TB_ROWS * 4 + (TB_ROWS + 1) * 4 + TB_PRED_CAP * 4 + TB_ROWS * 2 + TB_COLS + 8 + 28;
+constexpr int TB_SCRATCH_BYTES = TB_ROWS * TB_COLS * 2 + TB_ROWS * 4 + (TB_ROWS + 1) * 4 + TB_PRED_CAP * 4 +
+                                 TB_ROWS * 2 + TB_COLS + TB_ROWS * TB_COLS + 32;
 
 struct alignas(16) Vec16 { /* 8 int16 cells moved as one 128-bit access */
     uint32_t x, y, z, w;
@@ -479,7 +482,11 @@ POA_FN void tb_bind(TbScratch& t, uint8_t* base) {
     t.node = reinterpret_cast<uint16_t*>(base);
     base += TB_ROWS * 2;
     t.readc = base;
+    base += TB_COLS;
+    t.dec = base;
 }
+
+enum { TB_DIAG = 1, TB_VERT = 2, TB_HORZ = 3 };
 
 POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, const ReadGeom& g,
                          const uint8_t* read, int32_t end_row, const TbScratch& t) {
@@ -488,11 +495,8 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
     int32_t i = end_row, j = g.len;
     const int32_t mg = p.match - p.gap, xg = p.mismatch - p.gap;
     int32_t guard = p.max_nodes + p.max_len + 4;
-    int32_t cur = score_at(s, p, g, i, j);
-    /* tile state (uniform) */
-    int32_t r_hi = -1, r_lo = 0, c_lo = 0, c_hi = -1, pred_base = 0, pred_n = 0;
     while (!(i == 0 && j == 0)) {
-        if (--guard < 0 || w <= 32) {
+        if (--guard < 0 || w <= 40) {
             st.status = ST_TRACEBACK_LOST;
             return cap;
         }
@@ -514,119 +518,120 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
             }
             break;
         }
-        /* ---- make sure row i and columns j-1..j are in the tile ---- */
-        bool reloaded = false;
-        if (i > r_hi || i < r_lo || j > c_hi || j - 1 < c_lo) {
-            r_hi = i;
-            r_lo = i - (TB_ROWS - 1) < 0 ? 0 : i - (TB_ROWS - 1);
-            c_hi = j;
-            c_lo = ((j + 1 - TB_COLS) < 0 ? 0 : (j + 1 - TB_COLS + 7)) & ~7; /* 8-aligned, covers j */
-            POA_SYNC();
-            /* level 1: per-row metadata (lane k <-> row r_hi - k) */
-            PerLane<int> cnt;
-            POA_LANES(l) {
-                const int32_t row = r_hi - l;
-                cnt[l] = 0;
-                if (row >= r_lo) {
-                    const uint32_t rec = s.row_rec[row];
-                    t.rec[l] = rec;
-                    t.poff[l] = row >= 1 ? s.row_poff[row] : 0u;
-                    t.node[l] = row >= 1 ? s.node_at[row - 1] : (uint16_t)0;
-                    cnt[l] = row >= 1 ? rec_npred(rec) : 0;
-                }
-                for (int32_t c = c_lo + l; c < c_lo + TB_COLS; c += 32) /* read bases under the tile's columns */
-                    t.readc[c - c_lo] = (c >= 1 && c <= g.len) ? read[c - 1] : (uint8_t)0;
+        /* ================= tile anchored at (i, j): rows i-31..i, columns c_lo..c_lo+39 ================= */
+        const int32_t r_hi = i;
+        const int32_t r_lo = i - (TB_ROWS - 1) < 0 ? 0 : i - (TB_ROWS - 1);
+        const int32_t c_lo = ((j + 1 - TB_COLS) < 0 ? 0 : (j + 1 - TB_COLS + 7)) & ~7; /* 8-aligned, covers j */
+        POA_SYNC();
+        /* level 1: per-row metadata (lane k <-> row r_hi - k), read bases under the tile's columns */
+        POA_LANES(l) {
+            const int32_t row = r_hi - l;
+            if (row >= r_lo) {
+                t.rec[l] = s.row_rec[row];
+                t.poff[l] = row >= 1 ? s.row_poff[row] : 0u;
+                t.node[l] = row >= 1 ? s.node_at[row - 1] : (uint16_t)0;
             }
-            POA_SYNC();
-            /* CSR entries of rows r_lo..r_hi are contiguous: [poff(r_lo'), poff(r_hi) + np(r_hi)) */
-            const int32_t lo_row = r_lo < 1 ? 1 : r_lo;
-            pred_base = (int32_t)t.poff[r_hi - lo_row];
-            pred_n = (int32_t)t.poff[0] + rec_npred(t.rec[0]) - pred_base;
-            if (pred_n > TB_PRED_CAP) pred_n = TB_PRED_CAP; /* rows beyond the cap fall back to global */
-            /* level 2: score chunks and predecessor entries */
-            POA_LANES(l) {
-                const int32_t row = r_hi - l;
-                if (row >= r_lo) {
-                    const int32_t bs = rec_bs(t.rec[l]);
-                    for (int32_t k = 0; k < TB_CHUNKS; ++k) {
-                        const int32_t c = c_lo + 8 * k; /* 8-aligned, bs is 8-aligned: whole chunk in or out */
-                        const int32_t o = c - bs;
-                        int16_t* dst = t.cells + l * TB_COLS + 8 * k;
-                        if (o >= 0 && o + 8 <= g.bw) copy8(dst, s.S + (size_t)row * p.stride + o);
-                        else fill8(dst, NEG);
-                    }
-                }
-                for (int32_t e = l; e < pred_n; e += 32) t.pred[e] = s.row_pred[pred_base + e];
-            }
-            POA_SYNC();
-            reloaded = true;
+            for (int32_t c = c_lo + l; c < c_lo + TB_COLS; c += 32)
+                t.readc[c - c_lo] = (c >= 1 && c <= g.len) ? read[c - 1] : (uint8_t)0;
         }
-        /* ---- one step at (i, j) ---- */
-        int32_t ni = i, nj = j, ncur = cur;
-        const int32_t ti = r_hi - i; /* tile row index of row i */
-        const uint32_t rec = t.rec[ti];
-        const int32_t np = rec_npred(rec);
-        const int32_t po = (int32_t)t.poff[ti];
-        const int32_t prof = (j > 0 && rec_code(rec) == (int32_t)t.readc[j - c_lo]) ? mg : xg;
-        bool in_tile = (np <= 32) && (po - pred_base + np <= pred_n);
-        int32_t found = 0;
-        if (in_tile) {
-            PerLane<int> dm, vm, pr, miss;
-            POA_LANES(l) {
-                dm[l] = 0;
-                vm[l] = 0;
-                pr[l] = 0;
-                miss[l] = 0;
-                if (l < np) {
-                    const uint32_t pe = t.pred[po - pred_base + l];
-                    const int32_t pi = (int32_t)(pe & 0xFFFFu);
-                    pr[l] = pi;
-                    if (pi < r_lo) {
-                        miss[l] = 1;
-                    } else {
-                        const int16_t* cells = t.cells + (r_hi - pi) * TB_COLS - c_lo;
-                        dm[l] = (j > 0) && ((int32_t)cells[j - 1] + prof == cur);
-                        vm[l] = ((int32_t)cells[j] + p.gap == cur);
-                    }
+        POA_SYNC();
+        /* CSR entries of rows r_lo..r_hi are contiguous: [poff(lowest row), poff(r_hi) + np(r_hi)) */
+        const int32_t lo_row = r_lo < 1 ? 1 : r_lo;
+        const int32_t pred_base = (int32_t)t.poff[r_hi - lo_row];
+        int32_t pred_n = (int32_t)t.poff[0] + rec_npred(t.rec[0]) - pred_base;
+        if (pred_n > TB_PRED_CAP) pred_n = TB_PRED_CAP; /* rows beyond the cap stay undecided -> global fallback */
+        /* level 2: score chunks and predecessor entries */
+        POA_LANES(l) {
+            const int32_t row = r_hi - l;
+            if (row >= r_lo) {
+                const int32_t bs = rec_bs(t.rec[l]);
+                for (int32_t k = 0; k < TB_CHUNKS; ++k) {
+                    const int32_t c = c_lo + 8 * k; /* 8-aligned, bs is 8-aligned: whole chunk in or out */
+                    const int32_t o = c - bs;
+                    int16_t* dst = t.cells + l * TB_COLS + 8 * k;
+                    if (o >= 0 && o + 8 <= g.bw) copy8(dst, s.S + (size_t)row * p.stride + o);
+                    else fill8(dst, NEG);
                 }
             }
-            if (warp_ballot(miss)) {
-                in_tile = false;
-            } else {
-                const unsigned dmask = warp_ballot(dm);
-                if (dmask) {
-                    ni = warp_get(pr, poa_ffs(dmask));
-                    nj = j - 1;
-                    ncur = cur - prof;
-                    found = 1;
-                } else {
-                    const unsigned vmask = warp_ballot(vm);
-                    if (vmask) {
-                        ni = warp_get(pr, poa_ffs(vmask));
-                        nj = j;
-                        ncur = cur - p.gap;
-                        found = 1;
-                    }
-                }
-                if (!found) {
-                    if (j > 0 && (int32_t)t.cells[ti * TB_COLS + (j - 1 - c_lo)] == cur) {
-                        nj = j - 1;
-                        found = 1;
-                    } else {
-                        st.status = ST_TRACEBACK_LOST;
-                        return cap;
-                    }
-                }
+            for (int32_t e = l; e < pred_n; e += 32) t.pred[e] = s.row_pred[pred_base + e];
+        }
+        POA_SYNC();
+        /* ---- decisions: lane l decides every cell of its row inside the diagonal band the path can
+         *      reach, with spoa's priority (diagonal over in-edges in order, vertical, horizontal).
+         *      All lanes work in parallel out of shared memory; nothing here is on a serial chain. ---- */
+        POA_LANES(l) {
+            const int32_t row = r_hi - l;
+            uint8_t* dec = t.dec + l * TB_COLS;
+            for (int32_t x = 0; x < TB_COLS; ++x) dec[x] = 0;
+            if (row < 1 || row < r_lo) continue;
+            const uint32_t rec = t.rec[l];
+            const int32_t np = rec_npred(rec);
+            const int32_t po = (int32_t)t.poff[l] - pred_base;
+            if (np > TB_NPMAX || po + np > pred_n) continue; /* undecided row */
+            int32_t tq[TB_NPMAX]; /* tile row index of each predecessor, -1 = outside the tile */
+            bool all_in = true;
+            for (int32_t q = 0; q < np; ++q) {
+                const int32_t pi = (int32_t)(t.pred[po + q] & 0xFFFFu);
+                tq[q] = r_hi - pi;
+                if (pi < r_lo) all_in = false;
+            }
+            if (!all_in) continue; /* a predecessor is below the tile: the walk re-anchors when it gets here */
+            /* columns the path can have on this row: it moves at most one column left per step */
+            int32_t x_hi = j - c_lo - (l >> 2);
+            int32_t x_lo = j - c_lo - l - 10;
+            if (x_lo < 1) x_lo = 1; /* x - 1 must be inside the tile */
+            if (c_lo == 0 && x_lo < 1) x_lo = 1;
+            const int16_t* mine = t.cells + l * TB_COLS;
+            const int32_t code = rec_code(rec);
+            for (int32_t x = x_hi; x >= x_lo; --x) {
+                const int32_t cur = mine[x];
+                const int32_t prof = (code == (int32_t)t.readc[x]) ? mg : xg;
+                int32_t d = (mine[x - 1] == cur) ? TB_HORZ : 0;
+                for (int32_t q = np - 1; q >= 0; --q) /* reverse order: the lowest in-edge index wins */
+                    if ((int32_t)t.cells[tq[q] * TB_COLS + x] + p.gap == cur) d = TB_VERT | ((tq[q] - l) << 2);
+                for (int32_t q = np - 1; q >= 0; --q)
+                    if ((int32_t)t.cells[tq[q] * TB_COLS + x - 1] + prof == cur) d = TB_DIAG | ((tq[q] - l) << 2);
+                dec[x] = (uint8_t)d;
+            }
+            if (c_lo == 0 && x_lo == 1 && x_hi >= 0) { /* column 0: no diagonal, no horizontal */
+                const int32_t cur = mine[0];
+                int32_t d = 0;
+                for (int32_t q = np - 1; q >= 0; --q)
+                    if ((int32_t)t.cells[tq[q] * TB_COLS] + p.gap == cur) d = TB_VERT | ((tq[q] - l) << 2);
+                dec[0] = (uint8_t)d;
             }
         }
-        if (!in_tile) {
-            if (!reloaded) { /* a predecessor fell off the tile: re-anchor the tile at (i, j) and retry */
-                r_hi = -1;
-                ++guard;
-                continue;
+        POA_SYNC();
+        /* ---- walk the decisions (uniform): one shared-memory byte per step ---- */
+        int32_t steps = 0;
+        while (i >= 1 && i >= r_lo) {
+            const int32_t ti = r_hi - i, x = j - c_lo;
+            if (x < 0 || x >= TB_COLS) break;
+            const int32_t d = t.dec[ti * TB_COLS + x];
+            if (d == 0) break;
+            const int32_t mv = d & 3, dl = d >> 2;
+            --w;
+            POA_LANE0 {
+                s.tb_node[w] = (int16_t)(mv == TB_HORZ ? -1 : (int32_t)t.node[ti]);
+                s.tb_pos[w] = (int16_t)(mv == TB_VERT ? -1 : (j - 1));
             }
-            /* even a tile anchored here does not hold the step: read global memory directly */
+            if (mv != TB_HORZ) i -= dl;
+            if (mv != TB_VERT) j -= 1;
+            ++steps;
+            if (w <= 40) break;
+        }
+        guard -= steps > 0 ? steps - 1 : 0;
+        if (steps > 0) continue;
+        if (i == 0) continue;
+        /* ---- the tile anchored HERE cannot decide (i, j): in-degree > TB_NPMAX, a predecessor more than
+         *      31 rows back, or a band hole.  One step straight from global memory. ---- */
+        {
+            const uint32_t rec = s.row_rec[i];
+            const int32_t np = rec_npred(rec);
             const int32_t gpo = (int32_t)s.row_poff[i];
+            const int32_t cur = score_at_bs(s, p, g, i, rec_bs(rec), j);
+            const int32_t prof = (j > 0 && rec_code(rec) == (int32_t)read[j - 1]) ? mg : xg;
+            int32_t ni = i, nj = j, found = 0;
             for (int pass = 0; pass < 2 && !found; ++pass) { /* pass 0: diagonal, pass 1: vertical */
                 for (int32_t b = 0; b < np && !found; b += 32) {
                     PerLane<int> hit, pr;
@@ -646,7 +651,6 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
                     if (m) {
                         ni = warp_get(pr, poa_ffs(m));
                         nj = pass == 0 ? j - 1 : j;
-                        ncur = pass == 0 ? cur - prof : cur - p.gap;
                         found = 1;
                     }
                 }
@@ -659,15 +663,14 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
                     return cap;
                 }
             }
+            --w;
+            POA_LANE0 {
+                s.tb_node[w] = (int16_t)((i == ni) ? -1 : (int32_t)s.node_at[i - 1]);
+                s.tb_pos[w] = (int16_t)((j == nj) ? -1 : (j - 1));
+            }
+            i = ni;
+            j = nj;
         }
-        --w;
-        POA_LANE0 {
-            s.tb_node[w] = (int16_t)((i == ni) ? -1 : (int32_t)t.node[ti]);
-            s.tb_pos[w] = (int16_t)((j == nj) ? -1 : (j - 1));
-        }
-        i = ni;
-        j = nj;
-        cur = ncur;
     }
     POA_SYNC();
     return w;
