@@ -283,6 +283,14 @@ POA_FN uint32_t rec_make(int32_t code, bool sink, int32_t prow, int32_t npred, i
            ((uint32_t)npred << 13) | ((uint32_t)(bs >> 3) << 21);
 }
 POA_FN int32_t rec_code(uint32_t r) { return (int32_t)(r & 0xFFu); }
+POA_FN bool rec_far(uint32_t r) { return (r & 0x1000u) != 0; }
+POA_FN void poa_atomic_or(uint32_t* p, uint32_t v) {
+#if POA_DEVICE
+    atomicOr(p, v);
+#else
+    *p |= v;
+#endif
+}
 POA_FN bool rec_sink(uint32_t r) { return (r & 0x100u) != 0; }
 POA_FN int32_t rec_prow(uint32_t r) { return (int32_t)((r >> 9) & 7u); }
 POA_FN int32_t rec_npred(uint32_t r) { return (int32_t)((r >> 13) & 0xFFu); }
@@ -364,6 +372,7 @@ POA_FN_NOINLINE void build_program(const Slot& s, const Params& p, WinState& st,
                 if (s.nin[s.node_at[r0]] == 0) { /* virtual predecessor row 0 (sisd_alignment_engine.cpp:289-290) */
                     s.row_pred[o0] = 0;
                     s.row_pfill[o0] = pfill_make(r0 + 1, 0, 0, p.ring_rows, p.ring_stride);
+                    if (r0 + 1 >= p.ring_rows) s.row_rec[r0 + 1] |= 0x1000u;
                 }
             }
             if (r1 < N) {
@@ -371,6 +380,7 @@ POA_FN_NOINLINE void build_program(const Slot& s, const Params& p, WinState& st,
                 if (s.nin[s.node_at[r1]] == 0) {
                     s.row_pred[o1] = 0;
                     s.row_pfill[o1] = pfill_make(r1 + 1, 0, 0, p.ring_rows, p.ring_stride);
+                    if (r1 + 1 >= p.ring_rows) s.row_rec[r1 + 1] |= 0x1000u;
                 }
             }
         }
@@ -396,11 +406,13 @@ POA_FN_NOINLINE void build_program(const Slot& s, const Params& p, WinState& st,
                 const int32_t pbs = band_start(g, ru0, N);
                 s.row_pred[o0] = (uint32_t)ru0 | ((uint32_t)pbs << 16);
                 s.row_pfill[o0] = pfill_make(rd0, ru0, pbs, p.ring_rows, p.ring_stride);
+                if (rd0 - ru0 >= p.ring_rows) poa_atomic_or(&s.row_rec[rd0], 0x1000u); /* rare */
             }
             if (ok1) {
                 const int32_t pbs = band_start(g, ru1, N);
                 s.row_pred[o1] = (uint32_t)ru1 | ((uint32_t)pbs << 16);
                 s.row_pfill[o1] = pfill_make(rd1, ru1, pbs, p.ring_rows, p.ring_stride);
+                if (rd1 - ru1 >= p.ring_rows) poa_atomic_or(&s.row_rec[rd1], 0x1000u);
             }
         }
     }
@@ -556,49 +568,47 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
             for (int32_t e = l; e < pred_n; e += 32) t.pred[e] = s.row_pred[pred_base + e];
         }
         POA_SYNC();
-        /* ---- decisions: lane l decides every cell of its row inside the diagonal band the path can
-         *      reach, with spoa's priority (diagonal over in-edges in order, vertical, horizontal).
-         *      All lanes work in parallel out of shared memory; nothing here is on a serial chain. ---- */
+        /* ---- decisions, row by row: lane l decides the cell of the row that lies l columns left of the
+         *      right-most column the path can have there (it moves at most one column left per step),
+         *      with spoa's priority (diagonal over in-edges in order, vertical, horizontal).  The row's
+         *      predecessor list is uniform across lanes, neighbouring lanes read neighbouring cells. ---- */
         POA_LANES(l) {
-            const int32_t row = r_hi - l;
-            uint8_t* dec = t.dec + l * TB_COLS;
-            for (int32_t x = 0; x < TB_COLS; ++x) dec[x] = 0;
-            if (row < 1 || row < r_lo) continue;
-            const uint32_t rec = t.rec[l];
+            for (int32_t e = l; e < TB_ROWS * TB_COLS / 4; e += 32) reinterpret_cast<uint32_t*>(t.dec)[e] = 0u;
+        }
+        POA_SYNC();
+        for (int32_t k = 0; k < TB_ROWS; ++k) {
+            const int32_t row = r_hi - k;
+            if (row < 1 || row < r_lo) break;
+            const uint32_t rec = t.rec[k];
             const int32_t np = rec_npred(rec);
-            const int32_t po = (int32_t)t.poff[l] - pred_base;
-            if (np > TB_NPMAX || po + np > pred_n) continue; /* undecided row */
-            int32_t tq[TB_NPMAX]; /* tile row index of each predecessor, -1 = outside the tile */
+            const int32_t po = (int32_t)t.poff[k] - pred_base;
+            if (po + np > pred_n) continue; /* undecided row: its entries did not fit the tile */
             bool all_in = true;
-            for (int32_t q = 0; q < np; ++q) {
-                const int32_t pi = (int32_t)(t.pred[po + q] & 0xFFFFu);
-                tq[q] = r_hi - pi;
-                if (pi < r_lo) all_in = false;
-            }
+            for (int32_t q = 0; q < np; ++q)
+                if ((int32_t)(t.pred[po + q] & 0xFFFFu) < r_lo) all_in = false;
             if (!all_in) continue; /* a predecessor is below the tile: the walk re-anchors when it gets here */
-            /* columns the path can have on this row: it moves at most one column left per step */
-            int32_t x_hi = j - c_lo - (l >> 2);
-            int32_t x_lo = j - c_lo - l - 10;
-            if (x_lo < 1) x_lo = 1; /* x - 1 must be inside the tile */
-            if (c_lo == 0 && x_lo < 1) x_lo = 1;
-            const int16_t* mine = t.cells + l * TB_COLS;
+            const int32_t x_hi = j - c_lo - (k >> 2);
+            int32_t x_lo = j - c_lo - k - 10;
+            if (x_lo < x_hi - 31) x_lo = x_hi - 31;
+            const int32_t x_min = c_lo == 0 ? 0 : 1; /* column c_lo-1 is not in the tile: c_lo itself cannot be decided */
+            if (x_lo < x_min) x_lo = x_min;
             const int32_t code = rec_code(rec);
-            for (int32_t x = x_hi; x >= x_lo; --x) {
+            const int16_t* mine = t.cells + k * TB_COLS;
+            POA_LANES(l) {
+                const int32_t x = x_hi - l;
+                if (x < x_lo || x < 0) continue;
                 const int32_t cur = mine[x];
                 const int32_t prof = (code == (int32_t)t.readc[x]) ? mg : xg;
-                int32_t d = (mine[x - 1] == cur) ? TB_HORZ : 0;
-                for (int32_t q = np - 1; q >= 0; --q) /* reverse order: the lowest in-edge index wins */
-                    if ((int32_t)t.cells[tq[q] * TB_COLS + x] + p.gap == cur) d = TB_VERT | ((tq[q] - l) << 2);
-                for (int32_t q = np - 1; q >= 0; --q)
-                    if ((int32_t)t.cells[tq[q] * TB_COLS + x - 1] + prof == cur) d = TB_DIAG | ((tq[q] - l) << 2);
-                dec[x] = (uint8_t)d;
-            }
-            if (c_lo == 0 && x_lo == 1 && x_hi >= 0) { /* column 0: no diagonal, no horizontal */
-                const int32_t cur = mine[0];
-                int32_t d = 0;
-                for (int32_t q = np - 1; q >= 0; --q)
-                    if ((int32_t)t.cells[tq[q] * TB_COLS] + p.gap == cur) d = TB_VERT | ((tq[q] - l) << 2);
-                dec[0] = (uint8_t)d;
+                int32_t dd = 0, dv = 0;
+                for (int32_t q = np - 1; q >= 0; --q) { /* descending: the lowest in-edge index wins */
+                    const int32_t tq = r_hi - (int32_t)(t.pred[po + q] & 0xFFFFu);
+                    const int16_t* pc = t.cells + tq * TB_COLS + x;
+                    if ((int32_t)pc[0] + p.gap == cur) dv = TB_VERT | ((tq - k) << 2);
+                    if (x >= 1 && (int32_t)pc[-1] + prof == cur) dd = TB_DIAG | ((tq - k) << 2);
+                }
+                int32_t d = dd ? dd : dv;
+                if (d == 0 && x >= 1 && mine[x - 1] == cur) d = TB_HORZ;
+                t.dec[k * TB_COLS + x] = (uint8_t)d;
             }
         }
         POA_SYNC();

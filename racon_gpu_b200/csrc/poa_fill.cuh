@@ -213,35 +213,52 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
             const unsigned lim_l = active ? (unsigned)bw : 0u;       /* off - 1 < lim_l */
             const uint32_t c0_sa = ring_sa + (uint32_t)c0 * 2u;
 
+/* one predecessor term: V = its 8 cells under this lane, leftw = its cell under column c0-1 */
+#define POA_FILL_ACCUMULATE()                                                                              \
+    do {                                                                                                   \
+        const uint4 V = lds128((unsigned)off <= lim_v ? cell_sa : neg_sa);                                 \
+        const uint32_t leftw = lds_u16((unsigned)(off - 1) < lim_l ? cell_sa - 2u : neg_sa) << 16;         \
+        const uint32_t d0 = __funnelshift_l(leftw, V.x, 16);                                               \
+        const uint32_t d1 = __funnelshift_l(V.x, V.y, 16);                                                 \
+        const uint32_t d2 = __funnelshift_l(V.y, V.z, 16);                                                 \
+        const uint32_t d3 = __funnelshift_l(V.z, V.w, 16);                                                 \
+        a0 = __viaddmax_s16x2(d0, P.x, a0);                                                                \
+        a1 = __viaddmax_s16x2(d1, P.y, a1);                                                                \
+        a2 = __viaddmax_s16x2(d2, P.z, a2);                                                                \
+        a3 = __viaddmax_s16x2(d3, P.w, a3);                                                                \
+        a0 = __viaddmax_s16x2(V.x, G2, a0);                                                                \
+        a1 = __viaddmax_s16x2(V.y, G2, a1);                                                                \
+        a2 = __viaddmax_s16x2(V.z, G2, a2);                                                                \
+        a3 = __viaddmax_s16x2(V.w, G2, a3);                                                                \
+    } while (0)
+
+            if (!rec_far(rec) && np <= 32) {
+                /* the common row: every predecessor is in the ring and its stream entry is in predA
+                 * (out-of-band loads are redirected to the NEG cells: no branches, no predicates) */
 #pragma unroll 1
-            for (int q = 0; q < np; ++q) {
-                /* predecessor entry from the register-resident CSR stream (pre-digested by build_program) */
-                uint32_t pe;
-                if (rel + q < 32) pe = __shfl_sync(0xffffffffu, predA, rel + q);
-                else pe = row_pfill[po + q]; /* in-degree > 32: straight from memory */
-                const int off = c0 - (int)((pe & 0xFFEu) << 2); /* offset of column c0 in the predecessor row */
-                uint32_t cell_sa = c0_sa + (uint32_t)((int)pe >> 12);
-                if (pe & 1u) { /* rare: predecessor older than the ring */
-                    const int pr = (int)(row_pred[po + q] & 0xFFFFu);
-                    fill_stage_far_row(S + (size_t)pr * stride, far_sa, bw);
-                    cell_sa = far_sa + (uint32_t)off * 2u;
+                for (int q = 0; q < np; ++q) {
+                    const uint32_t pe = __shfl_sync(0xffffffffu, predA, rel + q);
+                    const int off = c0 - (int)((pe & 0xFFEu) << 2); /* offset of column c0 in the predecessor row */
+                    const uint32_t cell_sa = c0_sa + (uint32_t)((int)pe >> 12);
+                    POA_FILL_ACCUMULATE();
                 }
-                /* out-of-band loads are redirected to the NEG cells: no branches, no predicates */
-                const uint4 V = lds128((unsigned)off <= lim_v ? cell_sa : neg_sa);
-                const uint32_t leftw = lds_u16((unsigned)(off - 1) < lim_l ? cell_sa - 2u : neg_sa) << 16; /* cell (pr, c0-1) */
-                const uint32_t d0 = __funnelshift_l(leftw, V.x, 16);
-                const uint32_t d1 = __funnelshift_l(V.x, V.y, 16);
-                const uint32_t d2 = __funnelshift_l(V.y, V.z, 16);
-                const uint32_t d3 = __funnelshift_l(V.z, V.w, 16);
-                a0 = __viaddmax_s16x2(d0, P.x, a0);
-                a1 = __viaddmax_s16x2(d1, P.y, a1);
-                a2 = __viaddmax_s16x2(d2, P.z, a2);
-                a3 = __viaddmax_s16x2(d3, P.w, a3);
-                a0 = __viaddmax_s16x2(V.x, G2, a0);
-                a1 = __viaddmax_s16x2(V.y, G2, a1);
-                a2 = __viaddmax_s16x2(V.z, G2, a2);
-                a3 = __viaddmax_s16x2(V.w, G2, a3);
+            } else {
+#pragma unroll 1
+                for (int q = 0; q < np; ++q) {
+                    uint32_t pe;
+                    if (rel + q < 32) pe = __shfl_sync(0xffffffffu, predA, rel + q);
+                    else pe = row_pfill[po + q]; /* in-degree > 32: straight from memory */
+                    const int off = c0 - (int)((pe & 0xFFEu) << 2);
+                    uint32_t cell_sa = c0_sa + (uint32_t)((int)pe >> 12);
+                    if (pe & 1u) { /* predecessor older than the ring: stage its row in the spare slot */
+                        const int pr = (int)(row_pred[po + q] & 0xFFFFu);
+                        fill_stage_far_row(S + (size_t)pr * stride, far_sa, bw);
+                        cell_sa = far_sa + (uint32_t)off * 2u;
+                    }
+                    POA_FILL_ACCUMULATE();
+                }
             }
+#undef POA_FILL_ACCUMULATE
 
             /* horizontal: inclusive prefix max over the 8 cells of the lane ... */
             a0 = __vmaxs2(a0, __byte_perm(a0, NEG2, 0x1054));
