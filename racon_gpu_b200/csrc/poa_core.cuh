@@ -230,8 +230,10 @@ struct PhaseTimer {
 /* ------------------------------------------------------------------------------------------
  * Phase 0: backbone chain  (graph.cpp:274-292 add_sequence + :177-185; window.cpp:73-76)
  * ---------------------------------------------------------------------------------------- */
-POA_FN_NOINLINE void init_backbone(const Slot& s, const Params& p, WinState& st, const uint8_t* seq,
+POA_FN_NOINLINE void init_backbone(const Slot& s_ref, const Params& p_ref, WinState& st, const uint8_t* seq,
                           const int8_t* w, int32_t len) {
+    const Slot s = s_ref;     /* local copies: no reloads of the descriptor after every store */
+    const Params p = p_ref;
     if (len > p.max_nodes || len - 1 > p.max_edges) {
         st.status = ST_SEQ_LEN_EXCEEDED_MAX_NODES;
         return;
@@ -339,7 +341,9 @@ POA_FN int32_t band_start(const ReadGeom& g, int32_t row, int32_t n_rows) {
     return bs & ~7;
 }
 
-POA_FN_NOINLINE void build_program(const Slot& s, const Params& p, WinState& st, const ReadGeom& g) {
+POA_FN_NOINLINE void build_program(const Slot& s_ref, const Params& p_ref, WinState& st, const ReadGeom& g) {
+    const Slot s = s_ref;     /* local copies: no reloads of the descriptor after every store */
+    const Params p = p_ref;
     const int32_t N = st.n_nodes, E = st.n_edges;
     /* pass A, node-parallel, 64 rows per step: row records and CSR offsets (row r+1 <-> node_at[r]) */
     int32_t run = 0; /* running predecessor offset (uniform) */
@@ -453,23 +457,20 @@ POA_FN int32_t score_at_bs(const Slot& s, const Params& p, const ReadGeom& g, in
  *   to reading global memory directly.
  *   Output: tb_node/tb_pos filled back to front; returns the index of the first (leftmost) entry.
  * ---------------------------------------------------------------------------------------- */
-constexpr int TB_ROWS = 32;    /* tile rows (one per lane) */
-constexpr int TB_CHUNKS = 5;   /* tile columns in 8-cell chunks */
+constexpr int TB_ROWS = 32;    /* tile rows (one per lane when loading) */
+constexpr int TB_CHUNKS = 7;   /* tile columns in 8-cell chunks */
 constexpr int TB_COLS = TB_CHUNKS * 8;
 constexpr int TB_PRED_CAP = 192; /* predecessor entries a tile can hold */
-constexpr int TB_NPMAX = 12;   /* in-degree a lane resolves inside the tile (more: global fallback) */
 
 struct TbScratch {           /* device: shared memory (the fill's ring area); emulation: heap */
     int16_t* cells;          /* [TB_ROWS * TB_COLS]  row (r_hi - k) at k*TB_COLS, column c at c - c_lo */
     uint32_t* rec;           /* [TB_ROWS]   row records                                 */
-    uint32_t* poff;          /* [TB_ROWS+1] poff[k] = CSR offset of row (r_hi - k)      */
+    uint32_t* poff;          /* [TB_ROWS+1] poff[k] = CSR offset of row (r_hi - k); poff[TB_ROWS] unused */
     uint32_t* pred;          /* [TB_PRED_CAP] predecessor entries of the rows, per row at poff - pred_base */
     uint16_t* node;          /* [TB_ROWS]   node id of row (r_hi - k)                   */
-    uint8_t* readc;          /* [TB_COLS]   read base under column c at c - c_lo (column c <-> read[c-1]) */
-    uint8_t* dec;            /* [TB_ROWS * TB_COLS] decision per cell: 0 = not computed, else move | row delta << 2 */
+    uint8_t* readc;          /* [TB_COLS + 8] read base under column c at c - c_lo (column c <-> read[c-1]) */
 };
-constexpr int TB_SCRATCH_BYTES = TB_ROWS * TB_COLS * 2 + TB_ROWS * 4 + (TB_ROWS + 1) * 4 + TB_PRED_CAP * 4 +
-                                 TB_ROWS * 2 + TB_COLS + TB_ROWS * TB_COLS + 32;
+constexpr int TB_SCRATCH_BYTES = TB_ROWS * TB_COLS * 2 + TB_ROWS * 4 + (TB_ROWS + 1) * 4 + TB_PRED_CAP * 4 + TB_ROWS * 2 + TB_COLS + 8 + 28;
 
 struct alignas(16) Vec16 { /* 8 int16 cells moved as one 128-bit access */
     uint32_t x, y, z, w;
@@ -494,21 +495,36 @@ POA_FN void tb_bind(TbScratch& t, uint8_t* base) {
     t.node = reinterpret_cast<uint16_t*>(base);
     base += TB_ROWS * 2;
     t.readc = base;
-    base += TB_COLS;
-    t.dec = base;
 }
-
-enum { TB_DIAG = 1, TB_VERT = 2, TB_HORZ = 3 };
 
 POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, const ReadGeom& g,
                          const uint8_t* read, int32_t end_row, const TbScratch& t) {
+    /* everything the loop touches is copied into locals first: `s`, `t`, `p`, `g` are references into
+     * memory, and after each store the compiler would otherwise reload every pointer it needs */
     const int32_t cap = p.max_nodes + p.max_len + 2;
+    int16_t* const T_cells = t.cells;
+    uint32_t* const T_rec = t.rec;
+    uint32_t* const T_poff = t.poff;
+    uint32_t* const T_pred = t.pred;
+    uint16_t* const T_node = t.node;
+    uint8_t* const T_readc = t.readc;
+    int16_t* const tb_node = s.tb_node;
+    int16_t* const tb_pos = s.tb_pos;
+    const uint32_t* const row_rec = s.row_rec;
+    const uint32_t* const row_poff = s.row_poff;
+    const uint32_t* const row_pred = s.row_pred;
+    const uint16_t* const node_at = s.node_at;
+    const int16_t* const S = s.S;
+    const int32_t stride = p.stride, gap = p.gap, bw = g.bw, rlen = g.len;
     int32_t w = cap; /* write cursor (uniform) */
-    int32_t i = end_row, j = g.len;
-    const int32_t mg = p.match - p.gap, xg = p.mismatch - p.gap;
+    int32_t i = end_row, j = rlen;
+    const int32_t mg = p.match - gap, xg = p.mismatch - gap;
     int32_t guard = p.max_nodes + p.max_len + 4;
+    int32_t cur = score_at(s, p, g, i, j);
+    /* tile state (uniform) */
+    int32_t r_hi = -1, r_lo = 0, c_lo = 0, c_hi = -1, pred_base = 0, pred_n = 0;
     while (!(i == 0 && j == 0)) {
-        if (--guard < 0 || w <= 40) {
+        if (--guard < 0 || w <= 32) {
             st.status = ST_TRACEBACK_LOST;
             return cap;
         }
@@ -517,8 +533,8 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
                 POA_LANES(l) {
                     const int32_t jj = j - b - l;
                     if (jj >= 1 && w - 1 - b - l >= 0) {
-                        s.tb_node[w - 1 - b - l] = -1;
-                        s.tb_pos[w - 1 - b - l] = (int16_t)(jj - 1);
+                        tb_node[w - 1 - b - l] = -1;
+                        tb_pos[w - 1 - b - l] = (int16_t)(jj - 1);
                     }
                 }
             }
@@ -530,118 +546,119 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
             }
             break;
         }
-        /* ================= tile anchored at (i, j): rows i-31..i, columns c_lo..c_lo+39 ================= */
-        const int32_t r_hi = i;
-        const int32_t r_lo = i - (TB_ROWS - 1) < 0 ? 0 : i - (TB_ROWS - 1);
-        const int32_t c_lo = ((j + 1 - TB_COLS) < 0 ? 0 : (j + 1 - TB_COLS + 7)) & ~7; /* 8-aligned, covers j */
-        POA_SYNC();
-        /* level 1: per-row metadata (lane k <-> row r_hi - k), read bases under the tile's columns */
-        POA_LANES(l) {
-            const int32_t row = r_hi - l;
-            if (row >= r_lo) {
-                t.rec[l] = s.row_rec[row];
-                t.poff[l] = row >= 1 ? s.row_poff[row] : 0u;
-                t.node[l] = row >= 1 ? s.node_at[row - 1] : (uint16_t)0;
-            }
-            for (int32_t c = c_lo + l; c < c_lo + TB_COLS; c += 32)
-                t.readc[c - c_lo] = (c >= 1 && c <= g.len) ? read[c - 1] : (uint8_t)0;
-        }
-        POA_SYNC();
-        /* CSR entries of rows r_lo..r_hi are contiguous: [poff(lowest row), poff(r_hi) + np(r_hi)) */
-        const int32_t lo_row = r_lo < 1 ? 1 : r_lo;
-        const int32_t pred_base = (int32_t)t.poff[r_hi - lo_row];
-        int32_t pred_n = (int32_t)t.poff[0] + rec_npred(t.rec[0]) - pred_base;
-        if (pred_n > TB_PRED_CAP) pred_n = TB_PRED_CAP; /* rows beyond the cap stay undecided -> global fallback */
-        /* level 2: score chunks and predecessor entries */
-        POA_LANES(l) {
-            const int32_t row = r_hi - l;
-            if (row >= r_lo) {
-                const int32_t bs = rec_bs(t.rec[l]);
-                for (int32_t k = 0; k < TB_CHUNKS; ++k) {
-                    const int32_t c = c_lo + 8 * k; /* 8-aligned, bs is 8-aligned: whole chunk in or out */
-                    const int32_t o = c - bs;
-                    int16_t* dst = t.cells + l * TB_COLS + 8 * k;
-                    if (o >= 0 && o + 8 <= g.bw) copy8(dst, s.S + (size_t)row * p.stride + o);
-                    else fill8(dst, NEG);
-                }
-            }
-            for (int32_t e = l; e < pred_n; e += 32) t.pred[e] = s.row_pred[pred_base + e];
-        }
-        POA_SYNC();
-        /* ---- decisions, row by row: lane l decides the cell of the row that lies l columns left of the
-         *      right-most column the path can have there (it moves at most one column left per step),
-         *      with spoa's priority (diagonal over in-edges in order, vertical, horizontal).  The row's
-         *      predecessor list is uniform across lanes, neighbouring lanes read neighbouring cells. ---- */
-        POA_LANES(l) {
-            for (int32_t e = l; e < TB_ROWS * TB_COLS / 4; e += 32) reinterpret_cast<uint32_t*>(t.dec)[e] = 0u;
-        }
-        POA_SYNC();
-        for (int32_t k = 0; k < TB_ROWS; ++k) {
-            const int32_t row = r_hi - k;
-            if (row < 1 || row < r_lo) break;
-            const uint32_t rec = t.rec[k];
-            const int32_t np = rec_npred(rec);
-            const int32_t po = (int32_t)t.poff[k] - pred_base;
-            if (po + np > pred_n) continue; /* undecided row: its entries did not fit the tile */
-            bool all_in = true;
-            for (int32_t q = 0; q < np; ++q)
-                if ((int32_t)(t.pred[po + q] & 0xFFFFu) < r_lo) all_in = false;
-            if (!all_in) continue; /* a predecessor is below the tile: the walk re-anchors when it gets here */
-            const int32_t x_hi = j - c_lo - (k >> 2);
-            int32_t x_lo = j - c_lo - k - 10;
-            if (x_lo < x_hi - 31) x_lo = x_hi - 31;
-            const int32_t x_min = c_lo == 0 ? 0 : 1; /* column c_lo-1 is not in the tile: c_lo itself cannot be decided */
-            if (x_lo < x_min) x_lo = x_min;
-            const int32_t code = rec_code(rec);
-            const int16_t* mine = t.cells + k * TB_COLS;
+        /* ---- make sure row i and columns j-1..j are in the tile ---- */
+        bool reloaded = false;
+        if (i > r_hi || i < r_lo || j > c_hi || j - 1 < c_lo) {
+            r_hi = i;
+            r_lo = i - (TB_ROWS - 1) < 0 ? 0 : i - (TB_ROWS - 1);
+            c_hi = j;
+            c_lo = ((j + 1 - TB_COLS) < 0 ? 0 : (j + 1 - TB_COLS + 7)) & ~7; /* 8-aligned, covers j */
+            POA_SYNC();
+            /* level 1: per-row metadata (lane k <-> row r_hi - k) */
+            PerLane<int> cnt;
             POA_LANES(l) {
-                const int32_t x = x_hi - l;
-                if (x < x_lo || x < 0) continue;
-                const int32_t cur = mine[x];
-                const int32_t prof = (code == (int32_t)t.readc[x]) ? mg : xg;
-                int32_t dd = 0, dv = 0;
-                for (int32_t q = np - 1; q >= 0; --q) { /* descending: the lowest in-edge index wins */
-                    const int32_t tq = r_hi - (int32_t)(t.pred[po + q] & 0xFFFFu);
-                    const int16_t* pc = t.cells + tq * TB_COLS + x;
-                    if ((int32_t)pc[0] + p.gap == cur) dv = TB_VERT | ((tq - k) << 2);
-                    if (x >= 1 && (int32_t)pc[-1] + prof == cur) dd = TB_DIAG | ((tq - k) << 2);
+                const int32_t row = r_hi - l;
+                cnt[l] = 0;
+                if (row >= r_lo) {
+                    const uint32_t rec = row_rec[row];
+                    T_rec[l] = rec;
+                    T_poff[l] = row >= 1 ? row_poff[row] : 0u;
+                    T_node[l] = row >= 1 ? node_at[row - 1] : (uint16_t)0;
+                    cnt[l] = row >= 1 ? rec_npred(rec) : 0;
                 }
-                int32_t d = dd ? dd : dv;
-                if (d == 0 && x >= 1 && mine[x - 1] == cur) d = TB_HORZ;
-                t.dec[k * TB_COLS + x] = (uint8_t)d;
+                for (int32_t c = c_lo + l; c < c_lo + TB_COLS; c += 32) /* read bases under the tile's columns */
+                    T_readc[c - c_lo] = (c >= 1 && c <= rlen) ? read[c - 1] : (uint8_t)0;
+            }
+            POA_SYNC();
+            /* CSR entries of rows r_lo..r_hi are contiguous: [poff(r_lo'), poff(r_hi) + np(r_hi)) */
+            const int32_t lo_row = r_lo < 1 ? 1 : r_lo;
+            pred_base = (int32_t)T_poff[r_hi - lo_row];
+            pred_n = (int32_t)T_poff[0] + rec_npred(T_rec[0]) - pred_base;
+            if (pred_n > TB_PRED_CAP) pred_n = TB_PRED_CAP; /* rows beyond the cap fall back to global */
+            /* level 2: score chunks and predecessor entries */
+            POA_LANES(l) {
+                const int32_t row = r_hi - l;
+                if (row >= r_lo) {
+                    const int32_t bs = rec_bs(T_rec[l]);
+                    for (int32_t k = 0; k < TB_CHUNKS; ++k) {
+                        const int32_t c = c_lo + 8 * k; /* 8-aligned, bs is 8-aligned: whole chunk in or out */
+                        const int32_t o = c - bs;
+                        int16_t* dst = T_cells + l * TB_COLS + 8 * k;
+                        if (o >= 0 && o + 8 <= bw) copy8(dst, S + (size_t)row * stride + o);
+                        else fill8(dst, NEG);
+                    }
+                }
+                for (int32_t e = l; e < pred_n; e += 32) T_pred[e] = row_pred[pred_base + e];
+            }
+            POA_SYNC();
+            reloaded = true;
+        }
+        /* ---- one step at (i, j) ---- */
+        int32_t ni = i, nj = j, ncur = cur;
+        const int32_t ti = r_hi - i; /* tile row index of row i */
+        const uint32_t rec = T_rec[ti];
+        const int32_t np = rec_npred(rec);
+        const int32_t po = (int32_t)T_poff[ti];
+        const int32_t prof = (j > 0 && rec_code(rec) == (int32_t)T_readc[j - c_lo]) ? mg : xg;
+        bool in_tile = (np <= 32) && (po - pred_base + np <= pred_n);
+        int32_t found = 0;
+        if (in_tile) {
+            PerLane<int> dm, vm, pr, miss;
+            POA_LANES(l) {
+                dm[l] = 0;
+                vm[l] = 0;
+                pr[l] = 0;
+                miss[l] = 0;
+                if (l < np) {
+                    const uint32_t pe = T_pred[po - pred_base + l];
+                    const int32_t pi = (int32_t)(pe & 0xFFFFu);
+                    pr[l] = pi;
+                    if (pi < r_lo) {
+                        miss[l] = 1;
+                    } else {
+                        const int16_t* cells = T_cells + (r_hi - pi) * TB_COLS - c_lo;
+                        dm[l] = (j > 0) && ((int32_t)cells[j - 1] + prof == cur);
+                        vm[l] = ((int32_t)cells[j] + gap == cur);
+                    }
+                }
+            }
+            if (warp_ballot(miss)) {
+                in_tile = false;
+            } else {
+                const unsigned dmask = warp_ballot(dm);
+                if (dmask) {
+                    ni = warp_get(pr, poa_ffs(dmask));
+                    nj = j - 1;
+                    ncur = cur - prof;
+                    found = 1;
+                } else {
+                    const unsigned vmask = warp_ballot(vm);
+                    if (vmask) {
+                        ni = warp_get(pr, poa_ffs(vmask));
+                        nj = j;
+                        ncur = cur - gap;
+                        found = 1;
+                    }
+                }
+                if (!found) {
+                    if (j > 0 && (int32_t)T_cells[ti * TB_COLS + (j - 1 - c_lo)] == cur) {
+                        nj = j - 1;
+                        found = 1;
+                    } else {
+                        st.status = ST_TRACEBACK_LOST;
+                        return cap;
+                    }
+                }
             }
         }
-        POA_SYNC();
-        /* ---- walk the decisions (uniform): one shared-memory byte per step ---- */
-        int32_t steps = 0;
-        while (i >= 1 && i >= r_lo) {
-            const int32_t ti = r_hi - i, x = j - c_lo;
-            if (x < 0 || x >= TB_COLS) break;
-            const int32_t d = t.dec[ti * TB_COLS + x];
-            if (d == 0) break;
-            const int32_t mv = d & 3, dl = d >> 2;
-            --w;
-            POA_LANE0 {
-                s.tb_node[w] = (int16_t)(mv == TB_HORZ ? -1 : (int32_t)t.node[ti]);
-                s.tb_pos[w] = (int16_t)(mv == TB_VERT ? -1 : (j - 1));
+        if (!in_tile) {
+            if (!reloaded) { /* a predecessor fell off the tile: re-anchor the tile at (i, j) and retry */
+                r_hi = -1;
+                ++guard;
+                continue;
             }
-            if (mv != TB_HORZ) i -= dl;
-            if (mv != TB_VERT) j -= 1;
-            ++steps;
-            if (w <= 40) break;
-        }
-        guard -= steps > 0 ? steps - 1 : 0;
-        if (steps > 0) continue;
-        if (i == 0) continue;
-        /* ---- the tile anchored HERE cannot decide (i, j): in-degree > TB_NPMAX, a predecessor more than
-         *      31 rows back, or a band hole.  One step straight from global memory. ---- */
-        {
-            const uint32_t rec = s.row_rec[i];
-            const int32_t np = rec_npred(rec);
-            const int32_t gpo = (int32_t)s.row_poff[i];
-            const int32_t cur = score_at_bs(s, p, g, i, rec_bs(rec), j);
-            const int32_t prof = (j > 0 && rec_code(rec) == (int32_t)read[j - 1]) ? mg : xg;
-            int32_t ni = i, nj = j, found = 0;
+            /* even a tile anchored here does not hold the step: read global memory directly */
+            const int32_t gpo = (int32_t)row_poff[i];
             for (int pass = 0; pass < 2 && !found; ++pass) { /* pass 0: diagonal, pass 1: vertical */
                 for (int32_t b = 0; b < np && !found; b += 32) {
                     PerLane<int> hit, pr;
@@ -649,18 +666,19 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
                         hit[l] = 0;
                         pr[l] = 0;
                         if (b + l < np) {
-                            const uint32_t pe = s.row_pred[gpo + b + l];
+                            const uint32_t pe = row_pred[gpo + b + l];
                             const int32_t pi = (int32_t)(pe & 0xFFFFu);
                             const int32_t pbs = (int32_t)(pe >> 16);
                             pr[l] = pi;
                             hit[l] = pass == 0 ? ((j > 0) && (score_at_bs(s, p, g, pi, pbs, j - 1) + prof == cur))
-                                               : (score_at_bs(s, p, g, pi, pbs, j) + p.gap == cur);
+                                               : (score_at_bs(s, p, g, pi, pbs, j) + gap == cur);
                         }
                     }
                     const unsigned m = warp_ballot(hit);
                     if (m) {
                         ni = warp_get(pr, poa_ffs(m));
                         nj = pass == 0 ? j - 1 : j;
+                        ncur = pass == 0 ? cur - prof : cur - gap;
                         found = 1;
                     }
                 }
@@ -673,14 +691,15 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
                     return cap;
                 }
             }
-            --w;
-            POA_LANE0 {
-                s.tb_node[w] = (int16_t)((i == ni) ? -1 : (int32_t)s.node_at[i - 1]);
-                s.tb_pos[w] = (int16_t)((j == nj) ? -1 : (j - 1));
-            }
-            i = ni;
-            j = nj;
         }
+        --w;
+        POA_LANE0 {
+            tb_node[w] = (int16_t)((i == ni) ? -1 : (int32_t)T_node[ti]);
+            tb_pos[w] = (int16_t)((j == nj) ? -1 : (j - 1));
+        }
+        i = ni;
+        j = nj;
+        cur = ncur;
     }
     POA_SYNC();
     return w;
@@ -689,8 +708,10 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
 /* ------------------------------------------------------------------------------------------
  * Phase 4: add the alignment to the graph  (graph.cpp:155-272, 94-116)
  * ---------------------------------------------------------------------------------------- */
-POA_FN_NOINLINE void add_alignment(const Slot& s, const Params& p, WinState& st, const uint8_t* read,
+POA_FN_NOINLINE void add_alignment(const Slot& s_ref, const Params& p_ref, WinState& st, const uint8_t* read,
                           const int8_t* wt, int32_t len, int32_t tb_begin) {
+    const Slot s = s_ref;     /* local copies: no reloads of the descriptor after every store */
+    const Params p = p_ref;
     const int32_t cap = p.max_nodes + p.max_len + 2;
     const int32_t N0 = st.n_nodes;
 
@@ -908,7 +929,9 @@ POA_FN_NOINLINE void add_alignment(const Slot& s, const Params& p, WinState& st,
  * Phase 5a: serial topological sort, the literal restatement of graph.cpp:294-354.
  * Kept for the test-suite (Params::serial_topsort) as the cross-check of the per-root sort.
  * ---------------------------------------------------------------------------------------- */
-POA_FN_NOINLINE void topsort_serial(const Slot& s, const Params& p, WinState& st) {
+POA_FN_NOINLINE void topsort_serial(const Slot& s_ref, const Params& p_ref, WinState& st) {
+    const Slot s = s_ref;     /* local copies: no reloads of the descriptor after every store */
+    const Params p = p_ref;
     const int32_t N = st.n_nodes;
     for (int32_t base = 0; base < N; base += 32) {
         POA_LANES(l) {
@@ -984,7 +1007,9 @@ POA_FN_NOINLINE void topsort_serial(const Slot& s, const Params& p, WinState& st
  *        members and store each member's position (lpos);
  *     3. every node: rank = offset[root] + lpos.
  * ---------------------------------------------------------------------------------------- */
-POA_FN_NOINLINE void topsort_roots(const Slot& s, const Params& p, WinState& st) {
+POA_FN_NOINLINE void topsort_roots(const Slot& s_ref, const Params& p_ref, WinState& st) {
+    const Slot s = s_ref;     /* local copies: no reloads of the descriptor after every store */
+    const Params p = p_ref;
     const int32_t N = st.n_nodes;
     /* 1. members of dirty roots: reset DFS marks, accumulate the root's stack bound.  Two nodes per lane
      *    per step so that the dependent loads (root -> dirty) of both are in flight together. */
@@ -1157,8 +1182,10 @@ POA_FN void consensus_scores_from(const Slot& s, int32_t N, int32_t first_rank, 
     }
 }
 
-POA_FN_NOINLINE void generate_consensus(const Slot& s, const Params& p, WinState& st, uint8_t* out_cons,
+POA_FN_NOINLINE void generate_consensus(const Slot& s_ref, const Params& p_ref, WinState& st, uint8_t* out_cons,
                                uint16_t* out_cov, int32_t* out_len) {
+    const Slot s = s_ref;     /* local copies: no reloads of the descriptor after every store */
+    const Params p = p_ref;
     const int32_t N = st.n_nodes;
     int32_t len = 0;
     POA_LANE0 {
