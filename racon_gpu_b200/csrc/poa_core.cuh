@@ -483,6 +483,40 @@ POA_FN void fill8(int16_t* dst, int32_t v) {
     *reinterpret_cast<Vec16*>(dst) = q;
 }
 
+/* Reads of the tile on the serial path: real shared-memory loads on the device (the tile pointers are
+ * generic; a generic load pays the address-space resolution on every step of the dependent chain). */
+#if POA_DEVICE
+typedef uint32_t tile_addr;
+POA_FN tile_addr tile_base(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+POA_FN uint32_t tile_u32(tile_addr a, int32_t i) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a + 4u * (uint32_t)i));
+    return v;
+}
+POA_FN int32_t tile_s16(tile_addr a, int32_t i) {
+    int32_t v;
+    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(a + 2u * (uint32_t)i));
+    return v;
+}
+POA_FN uint32_t tile_u16(tile_addr a, int32_t i) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a + 2u * (uint32_t)i));
+    return v;
+}
+POA_FN uint32_t tile_u8(tile_addr a, int32_t i) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a + (uint32_t)i));
+    return v;
+}
+#else
+typedef const uint8_t* tile_addr;
+POA_FN tile_addr tile_base(const void* p) { return reinterpret_cast<const uint8_t*>(p); }
+POA_FN uint32_t tile_u32(tile_addr a, int32_t i) { return reinterpret_cast<const uint32_t*>(a)[i]; }
+POA_FN int32_t tile_s16(tile_addr a, int32_t i) { return reinterpret_cast<const int16_t*>(a)[i]; }
+POA_FN uint32_t tile_u16(tile_addr a, int32_t i) { return reinterpret_cast<const uint16_t*>(a)[i]; }
+POA_FN uint32_t tile_u8(tile_addr a, int32_t i) { return a[i]; }
+#endif
+
 POA_FN void tb_bind(TbScratch& t, uint8_t* base) {
     t.cells = reinterpret_cast<int16_t*>(base);
     base += TB_ROWS * TB_COLS * 2;
@@ -516,6 +550,8 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
     const uint16_t* const node_at = s.node_at;
     const int16_t* const S = s.S;
     const int32_t stride = p.stride, gap = p.gap, bw = g.bw, rlen = g.len;
+    const tile_addr A_cells = tile_base(t.cells), A_rec = tile_base(t.rec), A_poff = tile_base(t.poff),
+                    A_pred = tile_base(t.pred), A_node = tile_base(t.node), A_readc = tile_base(t.readc);
     int32_t w = cap; /* write cursor (uniform) */
     int32_t i = end_row, j = rlen;
     const int32_t mg = p.match - gap, xg = p.mismatch - gap;
@@ -596,59 +632,50 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
         /* ---- one step at (i, j) ---- */
         int32_t ni = i, nj = j, ncur = cur;
         const int32_t ti = r_hi - i; /* tile row index of row i */
-        const uint32_t rec = T_rec[ti];
+        const uint32_t rec = tile_u32(A_rec, ti);
         const int32_t np = rec_npred(rec);
-        const int32_t po = (int32_t)T_poff[ti];
-        const int32_t prof = (j > 0 && rec_code(rec) == (int32_t)T_readc[j - c_lo]) ? mg : xg;
+        const int32_t po = (int32_t)tile_u32(A_poff, ti);
+        const int32_t prof = (j > 0 && rec_code(rec) == (int32_t)tile_u8(A_readc, j - c_lo)) ? mg : xg;
         bool in_tile = (np <= 32) && (po - pred_base + np <= pred_n);
         int32_t found = 0;
         if (in_tile) {
-            PerLane<int> dm, vm, pr, miss;
+            /* every lane rates its predecessor; ONE warp-min picks spoa's choice:
+             *   0 = predecessor below the tile, 1+l = diagonal via in-edge l, 64+l = vertical via in-edge l */
+            PerLane<int> key, pr;
             POA_LANES(l) {
-                dm[l] = 0;
-                vm[l] = 0;
+                key[l] = 255;
                 pr[l] = 0;
-                miss[l] = 0;
                 if (l < np) {
-                    const uint32_t pe = T_pred[po - pred_base + l];
-                    const int32_t pi = (int32_t)(pe & 0xFFFFu);
+                    const int32_t pi = (int32_t)(tile_u32(A_pred, po - pred_base + l) & 0xFFFFu);
                     pr[l] = pi;
                     if (pi < r_lo) {
-                        miss[l] = 1;
+                        key[l] = 0;
                     } else {
-                        const int16_t* cells = T_cells + (r_hi - pi) * TB_COLS - c_lo;
-                        dm[l] = (j > 0) && ((int32_t)cells[j - 1] + prof == cur);
-                        vm[l] = ((int32_t)cells[j] + gap == cur);
+                        const int32_t cb = (r_hi - pi) * TB_COLS - c_lo + j;
+                        if (tile_s16(A_cells, cb) + gap == cur) key[l] = 64 + l;
+                        if (j > 0 && tile_s16(A_cells, cb - 1) + prof == cur) key[l] = 1 + l;
                     }
                 }
             }
-            if (warp_ballot(miss)) {
+            const int32_t best = warp_min(key);
+            if (best == 0) {
                 in_tile = false;
+            } else if (best < 64) {
+                ni = warp_get(pr, best - 1);
+                nj = j - 1;
+                ncur = cur - prof;
+                found = 1;
+            } else if (best < 128) {
+                ni = warp_get(pr, best - 64);
+                nj = j;
+                ncur = cur - gap;
+                found = 1;
+            } else if (j > 0 && tile_s16(A_cells, ti * TB_COLS + (j - 1 - c_lo)) == cur) {
+                nj = j - 1;
+                found = 1;
             } else {
-                const unsigned dmask = warp_ballot(dm);
-                if (dmask) {
-                    ni = warp_get(pr, poa_ffs(dmask));
-                    nj = j - 1;
-                    ncur = cur - prof;
-                    found = 1;
-                } else {
-                    const unsigned vmask = warp_ballot(vm);
-                    if (vmask) {
-                        ni = warp_get(pr, poa_ffs(vmask));
-                        nj = j;
-                        ncur = cur - gap;
-                        found = 1;
-                    }
-                }
-                if (!found) {
-                    if (j > 0 && (int32_t)T_cells[ti * TB_COLS + (j - 1 - c_lo)] == cur) {
-                        nj = j - 1;
-                        found = 1;
-                    } else {
-                        st.status = ST_TRACEBACK_LOST;
-                        return cap;
-                    }
-                }
+                st.status = ST_TRACEBACK_LOST;
+                return cap;
             }
         }
         if (!in_tile) {
@@ -694,7 +721,7 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
         }
         --w;
         POA_LANE0 {
-            tb_node[w] = (int16_t)((i == ni) ? -1 : (int32_t)T_node[ti]);
+            tb_node[w] = (int16_t)((i == ni) ? -1 : (int32_t)tile_u16(A_node, ti));
             tb_pos[w] = (int16_t)((j == nj) ? -1 : (j - 1));
         }
         i = ni;
