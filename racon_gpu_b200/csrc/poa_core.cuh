@@ -1280,6 +1280,8 @@ POA_FN bool score_range_ok(const Params& p, int32_t n_nodes, int32_t len) {
     const int64_t steps = (int64_t)n_nodes + len + 1;
     const int64_t lo = (int64_t)mn * steps - (p.gap > 0 ? (int64_t)p.gap * (len + 1) : 0);
     const int64_t hi = (int64_t)mx * steps + (p.gap < 0 ? (int64_t)(-p.gap) * (len + 1) : 0);
+    const int32_t mg = p.match - p.gap, xg = p.mismatch - p.gap; /* the fill keeps them as int8 */
+    if (mg < -128 || mg > 127 || xg < -128 || xg > 127) return false;
     return lo > NEG + 512 && hi < 32000;
 }
 

@@ -57,6 +57,14 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts8(uint32_t addr, int v) {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void sts16(uint32_t addr, int v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
@@ -65,7 +73,8 @@ __device__ __forceinline__ void sts16(uint32_t addr, int v) {
  * Shared memory of one block (one warp), in int16 cells:
  *   [0, 8)                                  eight NEG cells: where out-of-band lanes point their loads
  *   [8, 16)                                 eight zero cells: profile of lanes beyond the band
- *   [16, 16 + PROF_ROWS*prof_stride)        profile rows
+ *   [16, 16 + PROF_ROWS*prof_stride/2)      profile rows, ONE BYTE per column (s - gap fits int8), widened
+ *                                           to int16 pairs with two sign-replicating PRMTs per 4 cells
  *   [.., + (ring_rows+1)*ring_stride)       ring of score rows + one spare row for old predecessors
  */
 struct FillArgs { /* everything the row loop needs, and nothing else (keeps its register set small) */
@@ -101,7 +110,7 @@ __device__ __noinline__ void fill_build_dyn_prof_row(uint32_t row_sa, int c, con
     for (int col = lane; col < colsP; col += 32) {
         int v = xg;
         if (col >= 1 && col <= len && (int)read[col - 1] == c) v = mg;
-        sts16(row_sa + (uint32_t)col * 2u, v);
+        sts8(row_sa + (uint32_t)col, v);
     }
     __syncwarp();
 }
@@ -132,7 +141,7 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
     const uint32_t neg_sa = fa.smem_sa;
     const uint32_t zero_sa = fa.smem_sa + 16u;
     const uint32_t prof_sa = fa.smem_sa + 32u;
-    const uint32_t ring_sa = prof_sa + (uint32_t)(PROF_ROWS * prof_stride) * 2u;
+    const uint32_t ring_sa = prof_sa + (((uint32_t)(PROF_ROWS * prof_stride) + 15u) & ~15u); /* profile: 1 byte per column */
     const uint32_t ring_row_bytes = (uint32_t)fa.ring_stride * 2u;
     const uint32_t far_sa = ring_sa + (uint32_t)R * ring_row_bytes;
     const int lane8 = lane * 8;
@@ -144,10 +153,10 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
 #pragma unroll 1
     for (int col = lane; col < fa.colsP; col += 32) { /* the four fixed profile rows in one pass */
         const int ch = (col >= 1 && col <= fa.len) ? (int)read[col - 1] : -1;
-        sts16(prof_sa + (uint32_t)(0 * prof_stride + col) * 2u, ch == 'A' ? mg : xg);
-        sts16(prof_sa + (uint32_t)(1 * prof_stride + col) * 2u, ch == 'C' ? mg : xg);
-        sts16(prof_sa + (uint32_t)(2 * prof_stride + col) * 2u, ch == 'G' ? mg : xg);
-        sts16(prof_sa + (uint32_t)(3 * prof_stride + col) * 2u, ch == 'T' ? mg : xg);
+        sts8(prof_sa + (uint32_t)(0 * prof_stride + col), ch == 'A' ? mg : xg);
+        sts8(prof_sa + (uint32_t)(1 * prof_stride + col), ch == 'C' ? mg : xg);
+        sts8(prof_sa + (uint32_t)(2 * prof_stride + col), ch == 'G' ? mg : xg);
+        sts8(prof_sa + (uint32_t)(3 * prof_stride + col), ch == 'T' ? mg : xg);
     }
     /* row 0: H[0][j] = j*gap  =>  S = 0 (global copy for the traceback, ring slot 0 for the fill) */
 #pragma unroll 1
@@ -181,11 +190,11 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
         if (prow == 4) {
             const int code = rec_code(rec);
             if (dyn_code != code) {
-                fill_build_dyn_prof_row(prof_sa + (uint32_t)(4 * prof_stride) * 2u, code, read, fa.len, fa.colsP, mg, xg);
+                fill_build_dyn_prof_row(prof_sa + (uint32_t)(4 * prof_stride), code, read, fa.len, fa.colsP, mg, xg);
                 dyn_code = code;
             }
         }
-        const uint32_t prof_row_sa = prof_sa + (uint32_t)(prow * prof_stride + bs + lane8) * 2u;
+        const uint32_t prof_row_sa = prof_sa + (uint32_t)(prow * prof_stride + bs + lane8);
         int16_t* Srow = S + (size_t)i * stride;
         const uint32_t ring_row_sa = ring_sa + (uint32_t)(i & ring_mask) * ring_row_bytes;
         uint32_t carry = NEG2; /* S[i][last column of the previous chunk], both halves */
@@ -206,7 +215,12 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
             const int o0 = FULLW ? lane8 : k * CHUNK + lane8; /* offset of this lane's cells in the row */
             const bool active = FULLW ? true : (o0 < bw);
             const int c0 = bs + o0;                            /* first column of this lane */
-            const uint4 P = lds128(active ? prof_row_sa + (uint32_t)(FULLW ? 0 : k * CHUNK) * 2u : zero_sa);
+            const uint2 Pb = lds64(active ? prof_row_sa + (uint32_t)(FULLW ? 0 : k * CHUNK) : zero_sa); /* 8 int8 */
+            uint4 P; /* widen to 8 int16: byte b -> (b, sign(b)) */
+            P.x = __byte_perm(Pb.x, 0u, 0x9180);
+            P.y = __byte_perm(Pb.x, 0u, 0xB3A2);
+            P.z = __byte_perm(Pb.y, 0u, 0x9180);
+            P.w = __byte_perm(Pb.y, 0u, 0xB3A2);
             uint32_t a0 = NEG2, a1 = NEG2, a2 = NEG2, a3 = NEG2;
             /* per-chunk constants of the band tests: an inactive lane can never be "in band" */
             const unsigned lim_v = active ? (unsigned)(bw - 8) : 0u; /* off <= lim_v; inactive lanes have off >= bw > 0 */
