@@ -62,6 +62,11 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint32_t prmt_sext(uint32_t a, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0u), "r"(sel));
+    return d;
+}
 __device__ __forceinline__ void sts8(uint32_t addr, int v) {
     asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
@@ -217,10 +222,10 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
             const int c0 = bs + o0;                            /* first column of this lane */
             const uint2 Pb = lds64(active ? prof_row_sa + (uint32_t)(FULLW ? 0 : k * CHUNK) : zero_sa); /* 8 int8 */
             uint4 P; /* widen to 8 int16: byte b -> (b, sign(b)) */
-            P.x = __byte_perm(Pb.x, 0u, 0x9180);
-            P.y = __byte_perm(Pb.x, 0u, 0xB3A2);
-            P.z = __byte_perm(Pb.y, 0u, 0x9180);
-            P.w = __byte_perm(Pb.y, 0u, 0xB3A2);
+            P.x = prmt_sext(Pb.x, 0x9180u); /* PTX prmt: selector bit 3 replicates the byte's sign */
+            P.y = prmt_sext(Pb.x, 0xB3A2u); /* (__byte_perm() only honours 3 selector bits) */
+            P.z = prmt_sext(Pb.y, 0x9180u);
+            P.w = prmt_sext(Pb.y, 0xB3A2u);
             uint32_t a0 = NEG2, a1 = NEG2, a2 = NEG2, a3 = NEG2;
             /* per-chunk constants of the band tests: an inactive lane can never be "in band" */
             const unsigned lim_v = active ? (unsigned)(bw - 8) : 0u; /* off <= lim_v; inactive lanes have off >= bw > 0 */
