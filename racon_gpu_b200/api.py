@@ -19,7 +19,7 @@ import numpy as np
 from .windows import WindowBatch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libb200poa.so")
+_LIB_PATH = os.environ.get("B200POA_LIB", os.path.join(_HERE, "libb200poa.so"))  # B200POA_LIB: experiments only
 
 SUCCESS = 0
 EXCEEDED_MAXIMUM_POAS = 1

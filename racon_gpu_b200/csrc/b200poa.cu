@@ -55,7 +55,10 @@ struct KernelArgs {
     unsigned long long* phase_cycles; /* diagnostics: [PH_COUNT] or nullptr */
 };
 
-__global__ void __launch_bounds__(32, 24) poa_window_kernel(const KernelArgs a) {
+#ifndef POA_MIN_BLOCKS_PER_SM
+#define POA_MIN_BLOCKS_PER_SM 24 /* 24 warps/SM => <= 80 registers per thread */
+#endif
+__global__ void __launch_bounds__(32, POA_MIN_BLOCKS_PER_SM) poa_window_kernel(const KernelArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     /* The workspace descriptor is pure arithmetic on kernel parameters (constant bank): the
      * compiler rematerialises the few pointers a phase needs instead of pinning 33 of them. */

@@ -393,30 +393,35 @@ POA_FN_NOINLINE void build_program(const Slot& s_ref, const Params& p_ref, WinSt
     POA_LANE0 { s.row_poff[N + 1] = (uint32_t)run; }
     if (warp_ballot(wide)) st.status = ST_EDGE_COUNT_EXCEEDED; /* in-degree > 255 does not fit the record */
     POA_SYNC();
-    /* pass B, edge-parallel, 64 edges per step: every edge drops its source row into its slot of the
+    /* pass B, edge-parallel, 128 edges per step: every edge drops its source row into its slot of the
      * target's predecessor list (slot = e_ord, the edge's position in the in-edge list, fixed when the
      * edge was created) -- no linked-list walking, three dependent loads per edge. */
-    for (int32_t base = 0; base < E; base += 64) {
+    for (int32_t base = 0; base < E; base += 128) {
         POA_LANES(l) {
-            const int32_t e0 = base + l, e1 = base + 32 + l;
-            const bool ok0 = e0 < E, ok1 = e1 < E;
-            const int32_t d0 = ok0 ? (int32_t)s.e_dst[e0] : 0, d1 = ok1 ? (int32_t)s.e_dst[e1] : 0;
-            const int32_t u0 = ok0 ? (int32_t)s.e_src[e0] : 0, u1 = ok1 ? (int32_t)s.e_src[e1] : 0;
-            const int32_t q0 = ok0 ? (int32_t)s.e_ord[e0] : 0, q1 = ok1 ? (int32_t)s.e_ord[e1] : 0;
-            const int32_t rd0 = s.rank_of[d0] + 1, rd1 = s.rank_of[d1] + 1;
-            const int32_t ru0 = s.rank_of[u0] + 1, ru1 = s.rank_of[u1] + 1;
-            const int32_t o0 = (int32_t)s.row_poff[rd0] + q0, o1 = (int32_t)s.row_poff[rd1] + q1;
-            if (ok0) {
-                const int32_t pbs = band_start(g, ru0, N);
-                s.row_pred[o0] = (uint32_t)ru0 | ((uint32_t)pbs << 16);
-                s.row_pfill[o0] = pfill_make(rd0, ru0, pbs, p.ring_rows, p.ring_stride);
-                if (rd0 - ru0 >= p.ring_rows) poa_atomic_or(&s.row_rec[rd0], 0x1000u); /* rare */
+            int32_t d[4], u[4], q[4], rd[4], ru[4], o[4];
+            bool ok[4];
+#pragma unroll
+            for (int32_t k = 0; k < 4; ++k) { /* level 1: the edge itself (independent loads) */
+                const int32_t e = base + 32 * k + l;
+                ok[k] = e < E;
+                d[k] = ok[k] ? (int32_t)s.e_dst[e] : 0;
+                u[k] = ok[k] ? (int32_t)s.e_src[e] : 0;
+                q[k] = ok[k] ? (int32_t)s.e_ord[e] : 0;
             }
-            if (ok1) {
-                const int32_t pbs = band_start(g, ru1, N);
-                s.row_pred[o1] = (uint32_t)ru1 | ((uint32_t)pbs << 16);
-                s.row_pfill[o1] = pfill_make(rd1, ru1, pbs, p.ring_rows, p.ring_stride);
-                if (rd1 - ru1 >= p.ring_rows) poa_atomic_or(&s.row_rec[rd1], 0x1000u);
+#pragma unroll
+            for (int32_t k = 0; k < 4; ++k) { /* level 2: ranks */
+                rd[k] = s.rank_of[d[k]] + 1;
+                ru[k] = s.rank_of[u[k]] + 1;
+            }
+#pragma unroll
+            for (int32_t k = 0; k < 4; ++k) o[k] = (int32_t)s.row_poff[rd[k]] + q[k]; /* level 3: slot */
+#pragma unroll
+            for (int32_t k = 0; k < 4; ++k) {
+                if (!ok[k]) continue;
+                const int32_t pbs = band_start(g, ru[k], N);
+                s.row_pred[o[k]] = (uint32_t)ru[k] | ((uint32_t)pbs << 16);
+                s.row_pfill[o[k]] = pfill_make(rd[k], ru[k], pbs, p.ring_rows, p.ring_stride);
+                if (rd[k] - ru[k] >= p.ring_rows) poa_atomic_or(&s.row_rec[rd[k]], 0x1000u); /* rare */
             }
         }
     }
@@ -1157,20 +1162,25 @@ POA_FN_NOINLINE void topsort_roots(const Slot& s_ref, const Params& p_ref, WinSt
         }
     }
     POA_SYNC();
-    /* 3. ranks (two nodes per lane per step) */
-    for (int32_t base = 0; base < N; base += 64) {
+    /* 3. ranks (four nodes per lane per step, loads staged by dependency level) */
+    for (int32_t base = 0; base < N; base += 128) {
         POA_LANES(l) {
-            const int32_t v0 = base + l, v1 = base + 32 + l;
-            const int32_t q0 = v0 < N ? (int32_t)s.root[v0] : 0, q1 = v1 < N ? (int32_t)s.root[v1] : 0;
-            const int32_t p0 = v0 < N ? (int32_t)s.lpos[v0] : 0, p1 = v1 < N ? (int32_t)s.lpos[v1] : 0;
-            const int32_t r0 = (int32_t)s.roff[q0] + p0, r1 = (int32_t)s.roff[q1] + p1;
-            if (v0 < N) {
-                s.rank_of[v0] = (uint16_t)r0;
-                s.node_at[r0] = (uint16_t)v0;
+            int32_t q[4], lp[4], r[4];
+#pragma unroll
+            for (int32_t k = 0; k < 4; ++k) {
+                const int32_t v = base + 32 * k + l;
+                q[k] = v < N ? (int32_t)s.root[v] : 0;
+                lp[k] = v < N ? (int32_t)s.lpos[v] : 0;
             }
-            if (v1 < N) {
-                s.rank_of[v1] = (uint16_t)r1;
-                s.node_at[r1] = (uint16_t)v1;
+#pragma unroll
+            for (int32_t k = 0; k < 4; ++k) r[k] = (int32_t)s.roff[q[k]] + lp[k];
+#pragma unroll
+            for (int32_t k = 0; k < 4; ++k) {
+                const int32_t v = base + 32 * k + l;
+                if (v < N) {
+                    s.rank_of[v] = (uint16_t)r[k];
+                    s.node_at[r[k]] = (uint16_t)v;
+                }
             }
         }
     }
