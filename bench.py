@@ -224,12 +224,12 @@ def main():
         raise SystemExit(f"bench.py: batch accepted {n_added}/{nwin} windows; raise the memory budget")
     pb.upload()
     info = pb.info()
+    sampler = ClockSampler(local_rank)
+    sampler.start()  # started before the warm-up: nvidia-smi needs ~1 s to deliver its first sample
     with torch.cuda.stream(stream):
         for _ in range(warmup):
             pb.launch()
         barrier()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         t0 = time.perf_counter()
         for a, b in ev:
@@ -249,7 +249,7 @@ def main():
     # ---------------- e2e: host buffers through the public API -------------------------------------
     pol = api.Polisher(devices=[local_rank], batches_per_device=args.batches, mem_per_batch=mem // args.batches,
                        banded=banded, match=M, mismatch=X, gap=G)
-    chunk = max(256, nwin // (args.batches * 4))
+    chunk = max(256, -(-nwin // (args.batches * 2)))  # two rounds per batch processor: each launch fills the GPU
     out = None
     for _ in range(warmup):
         out_t = pol.polish(batch, tgs=True, trim=True, max_windows_per_round=chunk)
