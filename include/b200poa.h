@@ -55,7 +55,7 @@ enum {
     B200POA_ALIGNED_COUNT_EXCEEDED = 11, /* more than 8 mutually aligned nodes in one column */
     B200POA_SCORE_RANGE_EXCEEDED = 12,   /* alignment does not fit int16 cells */
     B200POA_TRACEBACK_LOST = 13,         /* static band did not contain a consistent path */
-    B200POA_PARTIAL_SPAN_UNSUPPORTED = 14, /* layer does not span the window (window.cpp:92-103 subgraph path) */
+    B200POA_PARTIAL_SPAN_UNSUPPORTED = 14, /* reserved (partial-span layers are aligned on the device since r01) */
     B200POA_INVALID_ARGUMENT = 15,       /* what the C++ API reports by throwing std::invalid_argument */
     B200POA_CUDA_ERROR = 16              /* what the C++ API reports by aborting in GW_CU_CHECK_ERR */
 };

@@ -45,6 +45,8 @@ struct KernelArgs {
     const int64_t* seq_off;     /* [n_seqs+1] */
     const int32_t* win_seq_off; /* [n_windows+1] */
     const int32_t* win_flags;   /* per window: pre-set status (!= 0 => skip) */
+    const int32_t* seq_begin;   /* [n_seqs] layer span (-1 = spans the window)  */
+    const int32_t* seq_end;     /* [n_seqs] */
     uint8_t* out_cons;
     uint16_t* out_cov;
     int32_t* out_len;
@@ -93,6 +95,8 @@ __global__ void __launch_bounds__(32, POA_MIN_BLOCKS_PER_SM) poa_window_kernel(c
         wv.bases = a.bases;
         wv.weights = a.weights;
         wv.seq_off = a.seq_off + s0;
+        wv.seq_begin = a.seq_begin + s0;
+        wv.seq_end = a.seq_end + s0;
         process_window(s, a.p, wv, fill, tbs, a.out_cons + orow, a.out_cov + orow, a.out_len + w,
                        a.out_status + w, PhaseTimer{a.phase_cycles, 0});
     }
@@ -154,6 +158,8 @@ struct b200poa_batch {
     uint8_t* h_bases = nullptr;
     int8_t* h_weights = nullptr;
     int64_t* h_seq_off = nullptr;
+    int32_t* h_seq_begin = nullptr;
+    int32_t* h_seq_end = nullptr;
     int32_t* h_win_seq_off = nullptr;
     int32_t* h_win_flags = nullptr;
     int32_t* h_work = nullptr;
@@ -166,6 +172,8 @@ struct b200poa_batch {
     uint8_t* d_bases = nullptr;
     int8_t* d_weights = nullptr;
     int64_t* d_seq_off = nullptr;
+    int32_t* d_seq_begin = nullptr;
+    int32_t* d_seq_end = nullptr;
     int32_t* d_win_seq_off = nullptr;
     int32_t* d_win_flags = nullptr;
     int32_t* d_work = nullptr;
@@ -190,6 +198,8 @@ static void free_batch(b200poa_batch* b) {
     cudaFreeHost(b->h_bases);
     cudaFreeHost(b->h_weights);
     cudaFreeHost(b->h_seq_off);
+    cudaFreeHost(b->h_seq_begin);
+    cudaFreeHost(b->h_seq_end);
     cudaFreeHost(b->h_win_seq_off);
     cudaFreeHost(b->h_win_flags);
     cudaFreeHost(b->h_work);
@@ -201,6 +211,8 @@ static void free_batch(b200poa_batch* b) {
     cudaFree(b->d_bases);
     cudaFree(b->d_weights);
     cudaFree(b->d_seq_off);
+    cudaFree(b->d_seq_begin);
+    cudaFree(b->d_seq_end);
     cudaFree(b->d_win_seq_off);
     cudaFree(b->d_win_flags);
     cudaFree(b->d_work);
@@ -246,14 +258,22 @@ static int32_t stage_window(b200poa_batch* b, int32_t n, Get get, int32_t* per_s
         else if (added >= b->cfg.max_sequences_per_poa) st = B200POA_EXCEEDED_MAXIMUM_SEQUENCES_PER_POA; /* :513-516 */
         if (per_seq_status) per_seq_status[i] = st;
         if (st != B200POA_SUCCESS) continue;
+        int32_t sp_b = -1, sp_e = -1; /* -1: the layer spans the window */
         if (added == 0) {
             bb_len = len;
         } else if (!(bg == -1 && en == -1)) {
-            /* window.cpp:87,92-93: does the layer span the whole window? */
+            /* window.cpp:87,92-93: does the layer span the whole window?  If not it is aligned to the
+             * subgraph between its begin and end backbone positions (window.cpp:96-103). */
             const uint32_t L = (uint32_t)bb_len;
             const uint32_t offset = (uint32_t)(0.01 * L);
-            if (!((uint32_t)bg < offset && (uint32_t)en > L - offset)) flag = B200POA_PARTIAL_SPAN_UNSUPPORTED;
+            if (!((uint32_t)bg < offset && (uint32_t)en > L - offset)) {
+                sp_b = bg;
+                sp_e = en;
+                if (bg < 0 || en >= bb_len || bg >= en) flag = B200POA_INVALID_ARGUMENT; /* window.cpp:55-59 rejects it */
+            }
         }
+        b->h_seq_begin[b->seq_count] = sp_b;
+        b->h_seq_end[b->seq_count] = sp_e;
         if (len > b->max_len_staged) b->max_len_staged = len;
         std::memcpy(b->h_bases + b->base_count, seq, (size_t)len);
         if (w) std::memcpy(b->h_weights + b->base_count, w, (size_t)len);
@@ -280,6 +300,8 @@ static int32_t alloc_batch_memory(b200poa_batch* b) {
     CU_TRY(cudaMalloc(&b->d_bases, AC));
     CU_TRY(cudaMalloc(&b->d_weights, AC));
     CU_TRY(cudaMalloc(&b->d_seq_off, (MS + 1) * sizeof(int64_t)));
+    CU_TRY(cudaMalloc(&b->d_seq_begin, (MS + 1) * sizeof(int32_t)));
+    CU_TRY(cudaMalloc(&b->d_seq_end, (MS + 1) * sizeof(int32_t)));
     CU_TRY(cudaMalloc(&b->d_win_seq_off, (MP + 1) * sizeof(int32_t)));
     CU_TRY(cudaMalloc(&b->d_win_flags, MP * sizeof(int32_t)));
     CU_TRY(cudaMalloc(&b->d_work, MP * sizeof(int32_t)));
@@ -296,6 +318,8 @@ static int32_t alloc_batch_memory(b200poa_batch* b) {
     CU_TRY(cudaHostAlloc(&b->h_bases, AC, cudaHostAllocDefault));
     CU_TRY(cudaHostAlloc(&b->h_weights, AC, cudaHostAllocDefault));
     CU_TRY(cudaHostAlloc(&b->h_seq_off, (MS + 1) * sizeof(int64_t), cudaHostAllocDefault));
+    CU_TRY(cudaHostAlloc(&b->h_seq_begin, (MS + 1) * sizeof(int32_t), cudaHostAllocDefault));
+    CU_TRY(cudaHostAlloc(&b->h_seq_end, (MS + 1) * sizeof(int32_t), cudaHostAllocDefault));
     CU_TRY(cudaHostAlloc(&b->h_win_seq_off, (MP + 1) * sizeof(int32_t), cudaHostAllocDefault));
     CU_TRY(cudaHostAlloc(&b->h_win_flags, MP * sizeof(int32_t), cudaHostAllocDefault));
     CU_TRY(cudaHostAlloc(&b->h_work, MP * sizeof(int32_t), cudaHostAllocDefault));
@@ -520,6 +544,8 @@ int32_t b200poa_batch_upload(b200poa_batch* b) {
     CU_TRY(cudaMemcpyAsync(b->d_bases, b->h_bases, (size_t)b->base_count, cudaMemcpyHostToDevice, b->stream));
     CU_TRY(cudaMemcpyAsync(b->d_weights, b->h_weights, (size_t)b->base_count, cudaMemcpyHostToDevice, b->stream));
     CU_TRY(cudaMemcpyAsync(b->d_seq_off, b->h_seq_off, ((size_t)b->seq_count + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, b->stream));
+    CU_TRY(cudaMemcpyAsync(b->d_seq_begin, b->h_seq_begin, (size_t)b->seq_count * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream));
+    CU_TRY(cudaMemcpyAsync(b->d_seq_end, b->h_seq_end, (size_t)b->seq_count * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream));
     CU_TRY(cudaMemcpyAsync(b->d_win_seq_off, b->h_win_seq_off, (W + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream));
     CU_TRY(cudaMemcpyAsync(b->d_win_flags, b->h_win_flags, W * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream));
     CU_TRY(cudaMemcpyAsync(b->d_work, b->h_work, W * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream));
@@ -545,6 +571,8 @@ int32_t b200poa_batch_launch(b200poa_batch* b) {
     a.seq_off = b->d_seq_off;
     a.win_seq_off = b->d_win_seq_off;
     a.win_flags = b->d_win_flags;
+    a.seq_begin = b->d_seq_begin;
+    a.seq_end = b->d_seq_end;
     a.out_cons = b->d_cons;
     a.out_cov = b->d_cov;
     a.out_len = b->d_len;

@@ -97,6 +97,8 @@ struct Slot {
     uint16_t* lpos;     /* [MN] position of the node inside its root's DFS order */
     uint16_t* rank_of;  /* [MN] node -> rank                                 */
     uint16_t* node_at;  /* [MN] rank -> node                                 */
+    uint16_t* sub_at;   /* [MN] partial-span layers: subgraph rank -> node     */
+    uint16_t* sub_rank; /* [MN] node -> subgraph rank, NONE16 = not a member   */
     uint16_t* e_src;    /* [ME] */
     uint16_t* e_dst;    /* [ME] */
     uint16_t* e_next;   /* [ME] next in-edge of e_dst, insertion order       */
@@ -160,6 +162,8 @@ void slot_bind(Slot& s, uint8_t* base, const Params& p, size_t* total_out) {
     POA_CARVE(lpos, uint16_t, MN);
     POA_CARVE(rank_of, uint16_t, MN);
     POA_CARVE(node_at, uint16_t, MN);
+    POA_CARVE(sub_at, uint16_t, MN);
+    POA_CARVE(sub_rank, uint16_t, MN);
     POA_CARVE(e_src, uint16_t, ME);
     POA_CARVE(e_dst, uint16_t, ME);
     POA_CARVE(e_next, uint16_t, ME);
@@ -195,6 +199,8 @@ struct WindowView {
     const uint8_t* bases;    /* batch arena */
     const int8_t* weights;   /* batch arena (always materialised; 1 when racon has no quality) */
     const int64_t* seq_off;  /* [n_seqs+1] offsets of this window's sequences in the arenas */
+    const int32_t* seq_begin; /* [n_seqs] layer span on the backbone, or -1 when the layer spans the window */
+    const int32_t* seq_end;   /* (window.cpp:87,92-93 decides which; the host applies that rule)           */
 };
 
 /* Mutable per-window state (warp-uniform scalars). */
@@ -321,11 +327,13 @@ struct ReadGeom {
     int32_t colsP;  /* (len+1) rounded up to a multiple of 8          */
     int32_t bw;     /* cells per row actually computed (multiple of 8) */
     int32_t banded; /* 1 if bw < colsP                                 */
+    int32_t n_rows; /* graph rows of this alignment (whole graph, or the subgraph of a partial-span layer) */
 };
 
-POA_FN ReadGeom read_geometry(const Params& p, int32_t len) {
+POA_FN ReadGeom read_geometry(const Params& p, int32_t len, int32_t n_rows) {
     ReadGeom g;
     g.len = len;
+    g.n_rows = n_rows;
     g.colsP = (len + 1 + 7) & ~7;
     g.banded = (p.band_width > 0 && g.colsP > p.band_width) ? 1 : 0;
     g.bw = g.banded ? p.band_width : g.colsP;
@@ -425,6 +433,172 @@ POA_FN_NOINLINE void build_program(const Slot& s_ref, const Params& p_ref, WinSt
             }
         }
     }
+    POA_SYNC();
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Partial-span layers (window.cpp:96-103): the read is aligned to the SUBGRAPH of nodes from which the
+ * backbone node `end` can be reached backwards without passing a node with id < begin
+ * (graph.cpp:592-615 extract_subgraph_nodes), in the topological order spoa computes for that
+ * subgraph (graph.cpp:617-673: nodes relabelled in increasing id, in-edges and aligned lists filtered,
+ * then Graph::topological_sort).  Relabelling is monotone, so that order is spoa's DFS run on the
+ * original ids restricted to the members.  Serial on lane 0: only layers that do not span the window
+ * take this path, and the member set is a fraction of the graph.
+ * Outputs: sub_at[0..n_sub), sub_rank[] (NONE16 for non-members), roff[v] = out-degree inside the
+ * subgraph.  Returns n_sub.
+ * ---------------------------------------------------------------------------------------- */
+POA_FN_NOINLINE int32_t mark_subgraph(const Slot& s_ref, const Params& p_ref, WinState& st, int32_t begin, int32_t end) {
+    const Slot s = s_ref;
+    const Params p = p_ref;
+    const int32_t N = st.n_nodes;
+    for (int32_t base = 0; base < N; base += 32) {
+        POA_LANES(l) {
+            if (base + l < N) {
+                s.sub_rank[base + l] = NONE16;
+                s.marks[base + l] = 0; /* 1 = member (then DFS marks 0/1/2 live in check[]) */
+                s.roff[base + l] = 0;
+            }
+        }
+    }
+    POA_SYNC();
+    int32_t n_sub = 0;
+    POA_LANE0 {
+        /* membership: graph.cpp:592-615 */
+        int32_t sp = 0;
+        s.stack[sp++] = (uint16_t)end;
+        while (sp != 0) {
+            const int32_t id = s.stack[--sp];
+            if (s.marks[id] == 0 && id >= begin) {
+                for (uint16_t e = s.in_head[id]; e != NONE16; e = s.e_next[e]) s.stack[sp++] = s.e_src[e];
+                for (int32_t q = 0; q < s.aln_cnt[id]; ++q) s.stack[sp++] = s.aln[id * KA + q];
+                s.marks[id] = 1;
+            }
+        }
+        /* order: graph.cpp:294-354 on the members (c_pred[]: 0 unmarked / 1 temporary / 2 permanent,
+         * c_score[]: check_aligned flag; both arrays are free during the alignment of a read) */
+        for (int32_t i = 0; i < N; ++i) {
+            s.c_pred[i] = 0;
+            s.c_score[i] = 1;
+        }
+        int32_t out = 0;
+        for (int32_t i = 0; i < N; ++i) {
+            if (!s.marks[i] || s.c_pred[i] != 0) continue;
+            sp = 0;
+            s.stack[sp++] = (uint16_t)i;
+            while (sp != 0) {
+                const int32_t id = s.stack[sp - 1];
+                bool valid = true;
+                if (s.c_pred[id] != 2) {
+                    for (uint16_t e = s.in_head[id]; e != NONE16; e = s.e_next[e]) {
+                        const int32_t u = s.e_src[e];
+                        if (s.marks[u] && s.c_pred[u] != 2) {
+                            s.stack[sp++] = (uint16_t)u;
+                            valid = false;
+                        }
+                    }
+                    const int32_t na = s.aln_cnt[id];
+                    if (s.c_score[id]) {
+                        for (int32_t q = 0; q < na; ++q) {
+                            const int32_t a = s.aln[id * KA + q];
+                            if (s.marks[a] && s.c_pred[a] != 2) {
+                                s.stack[sp++] = (uint16_t)a;
+                                s.c_score[a] = 0;
+                                valid = false;
+                            }
+                        }
+                    }
+                    if (valid) {
+                        s.c_pred[id] = 2;
+                        if (s.c_score[id]) {
+                            s.sub_at[out] = (uint16_t)id;
+                            s.sub_rank[id] = (uint16_t)out;
+                            ++out;
+                            for (int32_t q = 0; q < na; ++q) {
+                                const int32_t a = s.aln[id * KA + q];
+                                if (!s.marks[a]) continue; /* aligned list filtered to members (graph.cpp:660-666) */
+                                s.sub_at[out] = (uint16_t)a;
+                                s.sub_rank[a] = (uint16_t)out;
+                                ++out;
+                            }
+                        }
+                    } else {
+                        s.c_pred[id] = 1;
+                    }
+                }
+                if (valid) --sp;
+            }
+        }
+        /* out-degree inside the subgraph (a member without member successors is a sink of the alignment) */
+        for (int32_t r = 0; r < out; ++r) {
+            const int32_t v = s.sub_at[r];
+            for (uint16_t e = s.in_head[v]; e != NONE16; e = s.e_next[e])
+                if (s.marks[s.e_src[e]]) s.roff[s.e_src[e]] += 1;
+        }
+        n_sub = out;
+    }
+    POA_SYNC();
+    n_sub = warp_bcast0(n_sub);
+    (void)p;
+    return n_sub;
+}
+
+/* Row program of a subgraph alignment: rows follow sub_at[], predecessor lists keep only member
+ * sources (in in-edge order), a row without member sources gets the virtual predecessor row 0. */
+POA_FN_NOINLINE void build_program_sub(const Slot& s_ref, const Params& p_ref, WinState& st, const ReadGeom& g) {
+    const Slot s = s_ref;
+    const Params p = p_ref;
+    const int32_t N = g.n_rows;
+    int32_t run = 0;
+    POA_LANE0 { s.row_rec[0] = 0; }
+    PerLane<int> wide;
+    POA_LANES(l) { wide[l] = 0; }
+    for (int32_t base = 0; base < N; base += 32) {
+        PerLane<int> c;
+        POA_LANES(l) {
+            const int32_t r = base + l;
+            c[l] = 0;
+            if (r < N) {
+                const int32_t v = s.sub_at[r];
+                int32_t d = 0;
+                for (uint16_t e = s.in_head[v]; e != NONE16; e = s.e_next[e])
+                    if (s.sub_rank[s.e_src[e]] != NONE16) ++d;
+                c[l] = d ? d : 1;
+            }
+        }
+        PerLane<int> off = c;
+        const int32_t tot = warp_exscan(off);
+        POA_LANES(l) {
+            const int32_t r = base + l;
+            if (r >= N) continue;
+            const int32_t v = s.sub_at[r];
+            const int32_t o = run + off[l];
+            s.row_poff[r + 1] = (uint32_t)o;
+            int32_t k = 0;
+            bool far = false;
+            for (uint16_t e = s.in_head[v]; e != NONE16; e = s.e_next[e]) {
+                const int32_t sr = s.sub_rank[s.e_src[e]];
+                if (sr == NONE16) continue;
+                const int32_t pr = sr + 1;
+                const int32_t pbs = band_start(g, pr, N);
+                s.row_pred[o + k] = (uint32_t)pr | ((uint32_t)pbs << 16);
+                s.row_pfill[o + k] = pfill_make(r + 1, pr, pbs, p.ring_rows, p.ring_stride);
+                if (r + 1 - pr >= p.ring_rows) far = true;
+                ++k;
+            }
+            if (k == 0) {
+                s.row_pred[o] = 0;
+                s.row_pfill[o] = pfill_make(r + 1, 0, 0, p.ring_rows, p.ring_stride);
+                if (r + 1 >= p.ring_rows) far = true;
+            }
+            if (c[l] > 255) wide[l] = 1;
+            const int32_t code = s.code[v];
+            s.row_rec[r + 1] = rec_make(code, s.roff[v] == 0, prof_row_of(code), c[l] & 0xFF, band_start(g, r + 1, N)) |
+                               (far ? 0x1000u : 0u);
+        }
+        run += tot;
+    }
+    POA_LANE0 { s.row_poff[N + 1] = (uint32_t)run; }
+    if (warp_ballot(wide)) st.status = ST_EDGE_COUNT_EXCEEDED;
     POA_SYNC();
 }
 
@@ -537,7 +711,7 @@ POA_FN void tb_bind(TbScratch& t, uint8_t* base) {
 }
 
 POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, const ReadGeom& g,
-                         const uint8_t* read, int32_t end_row, const TbScratch& t) {
+                         const uint8_t* read, int32_t end_row, const TbScratch& t, const uint16_t* row_node) {
     /* everything the loop touches is copied into locals first: `s`, `t`, `p`, `g` are references into
      * memory, and after each store the compiler would otherwise reload every pointer it needs */
     const int32_t cap = p.max_nodes + p.max_len + 2;
@@ -552,7 +726,7 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
     const uint32_t* const row_rec = s.row_rec;
     const uint32_t* const row_poff = s.row_poff;
     const uint32_t* const row_pred = s.row_pred;
-    const uint16_t* const node_at = s.node_at;
+    const uint16_t* const node_at = row_node; /* rank -> node of THIS alignment's rows (graph or subgraph) */
     const int16_t* const S = s.S;
     const int32_t stride = p.stride, gap = p.gap, bw = g.bw, rlen = g.len;
     const tile_addr A_cells = tile_base(t.cells), A_rec = tile_base(t.rec), A_poff = tile_base(t.poff),
@@ -1319,9 +1493,22 @@ POA_FN void process_window(const Slot& s, const Params& p, const WindowView& wv,
             st.status = ST_SCORE_RANGE_EXCEEDED;
             break;
         }
-        const ReadGeom g = read_geometry(p, len);
+        /* window.cpp:92-103: a layer that does not span the window is aligned to a subgraph */
+        const int32_t sp_begin = wv.seq_begin ? wv.seq_begin[r] : -1;
+        const int32_t sp_end = wv.seq_end ? wv.seq_end[r] : -1;
+        const bool partial = sp_begin >= 0;
+        int32_t n_rows = st.n_nodes;
+        if (partial) {
+            if (sp_end >= len0 || sp_begin >= sp_end) { /* racon's add_layer guarantees begin < end <= backbone */
+                st.status = ST_GENERIC_ERROR;
+                break;
+            }
+            n_rows = mark_subgraph(s, p, st, sp_begin, sp_end);
+        }
+        const ReadGeom g = read_geometry(p, len, n_rows);
         tm.lap(PH_OTHER);
-        build_program(s, p, st, g);
+        if (partial) build_program_sub(s, p, st, g);
+        else build_program(s, p, st, g);
         tm.lap(PH_PROGRAM);
         if (st.status != ST_SUCCESS) break;
         const int32_t end_row = fill(s, p, st, g, read);
@@ -1330,7 +1517,7 @@ POA_FN void process_window(const Slot& s, const Params& p, const WindowView& wv,
             st.status = ST_TRACEBACK_LOST;
             break;
         }
-        const int32_t tb = traceback(s, p, st, g, read, end_row, tbs);
+        const int32_t tb = traceback(s, p, st, g, read, end_row, tbs, partial ? s.sub_at : s.node_at);
         tm.lap(PH_TRACEBACK);
         if (st.status != ST_SUCCESS) break;
         add_alignment(s, p, st, read, wt, len, tb);

@@ -349,7 +349,7 @@ struct CudaFill {
         fa.prof_stride = prof_stride;
         fa.ring_stride = ring_stride;
         fa.ring_mask = ring_mask;
-        fa.N = st.n_nodes;
+        fa.N = g.n_rows;
         fa.len = g.len;
         fa.colsP = g.colsP;
         fa.bw = g.bw;

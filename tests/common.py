@@ -55,3 +55,26 @@ def identity_order(batch: WindowBatch) -> np.ndarray:
         s0, s1 = int(batch.win_seq_off[w]), int(batch.win_seq_off[w + 1])
         order[s0:s1] = np.arange(s1 - s0)
     return order
+
+
+def partial_span_windows(n: int = 12, length: int = 400, depth: int = 14, seed: int = 77) -> WindowBatch:
+    """Windows in which every other layer covers only part of the backbone (window.cpp:96-103:
+    such layers are aligned to a subgraph), like real racon windows at read ends."""
+    rng = np.random.default_rng(5)
+    b = synth_windows(n, length, depth, 0.1, seed=seed)
+    wins = []
+    for w in range(b.n_windows):
+        seqs, wts, _, _ = b.window(w)
+        L = len(seqs[0])
+        win = [(seqs[0], wts[0], 0, 0)]
+        for i in range(1, len(seqs)):
+            if i % 2 == 0:
+                lo, hi = sorted(rng.integers(0, L, size=2).tolist())
+                if hi - lo < 40:
+                    lo, hi = 10, L - 10
+                s = seqs[i][int(lo / L * len(seqs[i])):int(hi / L * len(seqs[i]))]
+                win.append((s, None, lo, hi))
+            else:
+                win.append((seqs[i], None, 0, L - 1))
+        wins.append(win)
+    return WindowBatch.from_lists(wins)

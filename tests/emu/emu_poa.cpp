@@ -27,7 +27,8 @@ struct ScalarFill {
     int64_t cells = 0;
     int32_t operator()(const Slot& s, const Params& p, WinState& st, const ReadGeom& g,
                        const uint8_t* read) {
-        const int32_t N = st.n_nodes;
+        const int32_t N = g.n_rows;
+        (void)st;
         const int32_t mg = p.match - p.gap, xg = p.mismatch - p.gap;
         for (int32_t c = 0; c < g.bw; ++c) s.S[c] = 0; /* row 0: H = j*gap  =>  S = 0 */
         int32_t best = NEG, end_row = 0;
@@ -77,7 +78,7 @@ extern "C" {
  * n_windows x max_nodes final rank_to_node order, n_nodes_out (nullable) node counts. */
 void emu_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int64_t* seq_off,
                         const uint8_t* bases, const int8_t* weights, const uint8_t* has_weights,
-                        const int32_t* order, int32_t m, int32_t x, int32_t gap,
+                        const int32_t* begins, const int32_t* ends, const int32_t* order, int32_t m, int32_t x, int32_t gap,
                         int32_t max_nodes, int32_t max_edges, int32_t max_len, int32_t band_width,
                         int32_t serial_topsort, int32_t n_threads, uint8_t* cons_out,
                         uint16_t* cov_out, int32_t stride_out, int32_t* cons_len, int32_t* status,
@@ -109,6 +110,7 @@ void emu_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int
         std::vector<uint8_t> wbases;
         std::vector<int8_t> wweights;
         std::vector<int64_t> woff;
+        std::vector<int32_t> wbeg, wend;
         ScalarFill fill;
         std::vector<uint8_t> tb_mem(TB_SCRATCH_BYTES + 64);
         TbScratch tbs;
@@ -121,6 +123,10 @@ void emu_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int
             wbases.clear();
             wweights.clear();
             woff.assign(1, 0);
+            wbeg.clear();
+            wend.clear();
+            const uint32_t L0 = (uint32_t)(seq_off[s0 + order[s0] + 1] - seq_off[s0 + order[s0]]);
+            const uint32_t offset = (uint32_t)(0.01 * L0); /* window.cpp:87 */
             bool too_long = false;
             for (int32_t k = 0; k < n; ++k) {
                 const int64_t sq = s0 + order[s0 + k];
@@ -130,6 +136,11 @@ void emu_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int
                 if (has_weights[sq]) wweights.insert(wweights.end(), weights + a, weights + b);
                 else wweights.insert(wweights.end(), (size_t)(b - a), (int8_t)1);
                 woff.push_back((int64_t)wbases.size());
+                /* window.cpp:92-93: full-span test (the product's host library applies the same rule) */
+                const bool full = k == 0 || !begins ||
+                                  ((uint32_t)begins[sq] < offset && (uint32_t)ends[sq] > L0 - offset);
+                wbeg.push_back(full ? -1 : begins[sq]);
+                wend.push_back(full ? -1 : ends[sq]);
             }
             if (too_long) {
                 cons_len[w] = 0;
@@ -141,6 +152,8 @@ void emu_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int
             wv.bases = wbases.data();
             wv.weights = wweights.data();
             wv.seq_off = woff.data();
+            wv.seq_begin = wbeg.data();
+            wv.seq_end = wend.data();
             /* process_window writes its node count nowhere; recover it from the slot afterwards */
             process_window(s, p, wv, fill, tbs, cons_out + w * (int64_t)stride_out,
                            cov_out + w * (int64_t)stride_out, &cons_len[w], &status[w]);

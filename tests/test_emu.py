@@ -51,6 +51,19 @@ def test_spoa_known_answers(emu):
         assert st[0] == 0 and ec[0].decode() == gold[key]
 
 
+def test_partial_span_layers_go_through_the_subgraph_path(emu, oracle):
+    """window.cpp:96-103 / graph.cpp:592-683: layers that do not span the window."""
+    from common import partial_span_windows
+    pb = partial_span_windows()
+    order = api.processing_order(pb)
+    oc, ocov, _ = oracle.polish(pb, order, M, X, G, tgs=False, trim=False, threads=8)
+    for band in (0, 256):
+        for serial in (True, False):
+            ec, ecov, st, _ = emu.polish(pb, order, M, X, G, band=band, serial_topsort=serial)
+            assert (st == 0).all() and ec == oc
+            assert all((a == c).all() for a, c in zip(ecov, ocov))
+
+
 def test_static_band_256_tolerance(emu, oracle):
     """Banded mode is compared with the UNBANDED oracle.  Stated tolerance: >= 99% of
     windows identical, per-window edit distance <= 2."""

@@ -126,16 +126,28 @@ def test_edge_cases_follow_the_reference_contract():
     pb.close()
 
 
-def test_short_windows_and_partial_spans_are_reported_not_guessed():
-    """< 3 sequences: backbone + false (window.cpp:68-71).  Partial-span layers (window.cpp:96-103)
-    are not aligned on the device yet: the window is handed back to the caller's CPU path."""
+def test_short_windows_and_partial_span_layers(oracle):
+    """< 3 sequences: backbone + false (window.cpp:68-71).  Layers that do not span the window are aligned
+    to the subgraph between their begin and end (window.cpp:96-103, graph.cpp:592-683) -- on the device."""
+    from common import partial_span_windows
     two = [(b"ACGTACGTAC", None, 0, 0), (b"ACGTTCGTAC", None, 0, 9)]
-    bb = b"ACGTACGTACGGTTAACCGGTTAACCGGTTAAACGTACGTACGGTTAACCGGTTAACCGGTTAAACGTACGTACGGTTAACCGGTTAACCGGTTAAACGTACGTACGGTTAACCGGTTAACCGGTTAA"
-    partial = [(bb, None, 0, 0), (bb, None, 0, len(bb) - 1), (bb[10:60], None, 10, 60), (bb, None, 0, len(bb) - 1)]
-    b = WindowBatch.from_lists([two, partial])
+    b = WindowBatch.from_lists([two])
     cons, clen, pol, status, _ = api.polish_windows(b, M, X, G, mem_per_batch=MEM)
     assert not pol[0] and api.consensus_list(cons, clen)[0] == b"ACGTACGTAC"
-    assert not pol[1] and status[1] == api.PARTIAL_SPAN_UNSUPPORTED
+    pb = partial_span_windows()
+    order = api.processing_order(pb)
+    for trim in (False, True):
+        oc, _, _ = oracle.polish(pb, order, M, X, G, tgs=trim, trim=trim, threads=16)
+        for via_adapter in (False, True):
+            cons, clen, pol, status, _ = api.polish_windows(pb, M, X, G, tgs=trim, trim=trim, mem_per_batch=MEM,
+                                                            via_adapter=via_adapter)
+            assert pol.all() and api.consensus_list(cons, clen) == oc
+    # untrimmed consensus AND coverage through the batch API, banded too
+    oc, ocov, _ = oracle.polish(pb, order, M, X, G, tgs=False, trim=False, threads=16)
+    for banded in (False, True):
+        gc, gcov, st = gpu_untrimmed(pb, banded=banded)
+        assert (st == 0).all() and gc == oc
+        assert all((a == c).all() for a, c in zip(gcov, ocov))
 
 
 def test_batch_full_backpressure_and_multi_batch_concurrency(oracle):

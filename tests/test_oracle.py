@@ -56,27 +56,8 @@ def test_partial_span_layers_use_the_subgraph_path(oracle, ref):
     """window.cpp:92-103: layers that do not span the window are aligned to a subgraph."""
     if not ref.available:
         pytest.skip("oracle/_ref not built")
-    rng = np.random.default_rng(5)
-    b = synth_windows(12, 400, 14, 0.1, seed=77)
-    # turn every other layer into a partial-span layer by cropping it and its span
-    wins = []
-    for w in range(b.n_windows):
-        seqs, wts, bg, en = b.window(w)
-        L = len(seqs[0])
-        win = [(seqs[0], wts[0], 0, 0)]
-        for i in range(1, len(seqs)):
-            if i % 2 == 0:
-                lo, hi = sorted(rng.integers(0, L, size=2).tolist())
-                if hi - lo < 40:
-                    lo, hi = 10, L - 10
-                frac0, frac1 = lo / L, hi / L
-                s = seqs[i][int(frac0 * len(seqs[i])):int(frac1 * len(seqs[i]))]
-                win.append((s, None, lo, hi))
-            else:
-                win.append((seqs[i], None, 0, L - 1))
-        wins.append(win)
-    from racon_gpu_b200.windows import WindowBatch
-    pb = WindowBatch.from_lists(wins)
+    from common import partial_span_windows
+    pb = partial_span_windows()
     order = processing_order(pb, ref.layer_order)
     oc, _, _ = oracle.polish(pb, order, M, X, G, tgs=True, trim=True, threads=8)
     rc, _ = ref.polish(pb, M, X, G, tgs=True, trim=True, threads=8, window_length=400)
