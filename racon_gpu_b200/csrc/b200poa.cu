@@ -71,9 +71,9 @@ __global__ void __launch_bounds__(32, POA_MIN_BLOCKS_PER_SM) poa_window_kernel(c
     fill.prof_stride = a.prof_stride;
     fill.ring_stride = a.ring_stride;
     fill.ring_mask = a.ring_rows - 1;
-    /* the traceback tile reuses the score-row ring (idle during the traceback) */
+    /* the traceback tile overlays the query profile and the score-row ring: the fill rebuilds both per read */
     TbScratch tbs;
-    tb_bind(tbs, smem_raw + 32 + (((size_t)PROF_ROWS * a.prof_stride + 15) & ~(size_t)15));
+    tb_bind(tbs, smem_raw + 32);
     const int lane = threadIdx.x & 31;
     for (;;) {
         int32_t t = 0;
@@ -590,8 +590,9 @@ int32_t b200poa_batch_launch(b200poa_batch* b) {
     int32_t rows = 2;
     while (rows < 32 && rows * 2 * b->ring_stride * (int32_t)sizeof(int16_t) <= ring_bytes) rows *= 2;
     b->ring_rows = rows;
-    b->smem_bytes = 32 + ((PROF_ROWS * b->prof_stride + 15) & ~15) +
-                    std::max((b->ring_rows + 1) * b->ring_stride * (int32_t)sizeof(int16_t), (int32_t)TB_SCRATCH_BYTES);
+    b->smem_bytes = 32 + std::max(((PROF_ROWS * b->prof_stride + 15) & ~15) +
+                                      (b->ring_rows + 1) * b->ring_stride * (int32_t)sizeof(int16_t),
+                                  (int32_t)TB_SCRATCH_BYTES);
     int occ = 0;
     CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, poa_window_kernel, 32, (size_t)b->smem_bytes));
     if (occ < 1) return B200POA_INVALID_ARGUMENT;

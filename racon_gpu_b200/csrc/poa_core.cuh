@@ -626,20 +626,27 @@ POA_FN int32_t score_at_bs(const Slot& s, const Params& p, const ReadGeom& g, in
  *
  *   The score matrix lives in HBM and a step needs 3 dependent reads of it (row record ->
  *   predecessor list -> cells), ~600 steps per read: done naively that is ~2000 serial
- *   round-trips to memory per read.  Instead the path is followed through a TILE: the 32 rows
- *   below the current cell x 56 columns left of it are fetched in ONE round of independent loads
- *   (lane l fetches row i-l: its record, its predecessor list, seven 16-byte score chunks) into
- *   on-chip scratch (shared memory on the device), and ~25 steps are then resolved from the tile.
+ *   round-trips to memory per read.  Instead the path is followed through a TILE: the TB_ROWS rows
+ *   below the current cell x TB_COLS columns left of it are fetched in ONE round of independent
+ *   asynchronous copies (lane l fetches rows i-l, i-l-32: record, CSR offset, 16-byte score chunks) into
+ *   on-chip scratch (shared memory on the device), and ~30 steps are then resolved from the tile.
  *   Predecessors of a step are tested by different lanes and the first match (spoa's priority) is
  *   taken by ballot.  The current cell value is carried along, never re-read.
  *   A step whose data is not in the tile (predecessor > 31 rows back, in-degree > 32) falls back
  *   to reading global memory directly.
  *   Output: tb_node/tb_pos filled back to front; returns the index of the first (leftmost) entry.
  * ---------------------------------------------------------------------------------------- */
-constexpr int TB_ROWS = 32;    /* tile rows (one per lane when loading) */
-constexpr int TB_CHUNKS = 7;   /* tile columns in 8-cell chunks */
+#ifndef POA_TB_RPL
+#define POA_TB_RPL 1
+#endif
+#ifndef POA_TB_CHUNKS
+#define POA_TB_CHUNKS 7
+#endif
+constexpr int TB_RPL = POA_TB_RPL;       /* tile rows loaded per lane */
+constexpr int TB_ROWS = 32 * TB_RPL;     /* tile rows */
+constexpr int TB_CHUNKS = POA_TB_CHUNKS; /* tile columns in 8-cell chunks */
 constexpr int TB_COLS = TB_CHUNKS * 8;
-constexpr int TB_PRED_CAP = 192; /* predecessor entries a tile can hold */
+constexpr int TB_PRED_CAP = 192 * TB_RPL; /* predecessor entries a tile can hold */
 
 struct TbScratch {           /* device: shared memory (the fill's ring area); emulation: heap */
     int16_t* cells;          /* [TB_ROWS * TB_COLS]  row (r_hi - k) at k*TB_COLS, column c at c - c_lo */
@@ -687,7 +694,18 @@ POA_FN uint32_t tile_u8(tile_addr a, int32_t i) {
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a + (uint32_t)i));
     return v;
 }
+/* asynchronous global -> shared copies used by the tile load (LDGSTS: no register staging, all in flight) */
+POA_FN void tile_copy16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+POA_FN void tile_copy4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+POA_FN void tile_copy_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 #else
+POA_FN void tile_copy16(void* dst, const void* src) { *reinterpret_cast<Vec16*>(dst) = *reinterpret_cast<const Vec16*>(src); }
+POA_FN void tile_copy4(void* dst, const void* src) { *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(src); }
+POA_FN void tile_copy_wait() {}
 typedef const uint8_t* tile_addr;
 POA_FN tile_addr tile_base(const void* p) { return reinterpret_cast<const uint8_t*>(p); }
 POA_FN uint32_t tile_u32(tile_addr a, int32_t i) { return reinterpret_cast<const uint32_t*>(a)[i]; }
@@ -729,6 +747,7 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
     const uint16_t* const node_at = row_node; /* rank -> node of THIS alignment's rows (graph or subgraph) */
     const int16_t* const S = s.S;
     const int32_t stride = p.stride, gap = p.gap, bw = g.bw, rlen = g.len;
+    const ReadGeom gg = g;
     const tile_addr A_cells = tile_base(t.cells), A_rec = tile_base(t.rec), A_poff = tile_base(t.poff),
                     A_pred = tile_base(t.pred), A_node = tile_base(t.node), A_readc = tile_base(t.readc);
     int32_t w = cap; /* write cursor (uniform) */
@@ -769,42 +788,48 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
             c_hi = j;
             c_lo = ((j + 1 - TB_COLS) < 0 ? 0 : (j + 1 - TB_COLS + 7)) & ~7; /* 8-aligned, covers j */
             POA_SYNC();
-            /* level 1: per-row metadata (lane k <-> row r_hi - k) */
-            PerLane<int> cnt;
+            /* ONE round of independent loads.  The band start of a row is recomputed (same formula as the
+             * row program) instead of read from its record, so the score chunks -- the loads that go to HBM --
+             * depend on nothing; they are asynchronous global->shared copies, no registers in between.  Only
+             * the predecessor entries need a second, short level (two CSR offsets, cache-resident). */
+            const int32_t lo_row = r_lo < 1 ? 1 : r_lo;
+            const int32_t p_lo = (int32_t)row_poff[lo_row];                           /* uniform loads (i >= 1 here) */
+            const int32_t p_hi = (int32_t)row_poff[r_hi] + rec_npred(row_rec[r_hi]);
             POA_LANES(l) {
-                const int32_t row = r_hi - l;
-                cnt[l] = 0;
-                if (row >= r_lo) {
-                    const uint32_t rec = row_rec[row];
-                    T_rec[l] = rec;
-                    T_poff[l] = row >= 1 ? row_poff[row] : 0u;
-                    T_node[l] = row >= 1 ? node_at[row - 1] : (uint16_t)0;
-                    cnt[l] = row >= 1 ? rec_npred(rec) : 0;
+#pragma unroll
+                for (int32_t rr = 0; rr < TB_RPL; ++rr) {
+                    const int32_t k = l + 32 * rr;
+                    const int32_t row = r_hi - k;
+                    if (row < r_lo) continue;
+                    const int32_t bs = band_start(gg, row, gg.n_rows);
+#pragma unroll
+                    for (int32_t q = 0; q < TB_CHUNKS; ++q) {
+                        const int32_t o = c_lo + 8 * q - bs; /* 8-aligned both: whole chunk in the band or out */
+                        int16_t* dst = T_cells + k * TB_COLS + 8 * q;
+                        if (o >= 0 && o + 8 <= bw) tile_copy16(dst, S + (size_t)row * stride + o);
+                        else fill8(dst, NEG);
+                    }
+                    if (row >= 1) {
+                        tile_copy4(T_rec + k, row_rec + row);
+                        tile_copy4(T_poff + k, row_poff + row);
+                        T_node[k] = node_at[row - 1];
+                    } else {
+                        T_rec[k] = 0u;
+                        T_poff[k] = 0u;
+                        T_node[k] = 0;
+                    }
                 }
                 for (int32_t c = c_lo + l; c < c_lo + TB_COLS; c += 32) /* read bases under the tile's columns */
                     T_readc[c - c_lo] = (c >= 1 && c <= rlen) ? read[c - 1] : (uint8_t)0;
             }
-            POA_SYNC();
             /* CSR entries of rows r_lo..r_hi are contiguous: [poff(r_lo'), poff(r_hi) + np(r_hi)) */
-            const int32_t lo_row = r_lo < 1 ? 1 : r_lo;
-            pred_base = (int32_t)T_poff[r_hi - lo_row];
-            pred_n = (int32_t)T_poff[0] + rec_npred(T_rec[0]) - pred_base;
+            pred_base = p_lo;
+            pred_n = p_hi - p_lo;
             if (pred_n > TB_PRED_CAP) pred_n = TB_PRED_CAP; /* rows beyond the cap fall back to global */
-            /* level 2: score chunks and predecessor entries */
             POA_LANES(l) {
-                const int32_t row = r_hi - l;
-                if (row >= r_lo) {
-                    const int32_t bs = rec_bs(T_rec[l]);
-                    for (int32_t k = 0; k < TB_CHUNKS; ++k) {
-                        const int32_t c = c_lo + 8 * k; /* 8-aligned, bs is 8-aligned: whole chunk in or out */
-                        const int32_t o = c - bs;
-                        int16_t* dst = T_cells + l * TB_COLS + 8 * k;
-                        if (o >= 0 && o + 8 <= bw) copy8(dst, S + (size_t)row * stride + o);
-                        else fill8(dst, NEG);
-                    }
-                }
-                for (int32_t e = l; e < pred_n; e += 32) T_pred[e] = row_pred[pred_base + e];
+                for (int32_t e = l; e < pred_n; e += 32) tile_copy4(T_pred + e, row_pred + pred_base + e);
             }
+            tile_copy_wait();
             POA_SYNC();
             reloaded = true;
         }

@@ -20,9 +20,16 @@ pb = api.PoaBatch(max_gpu_mem=int(args.mem_gb * (1 << 30)), banded=bool(args.ban
 n, _ = pb.add_windows(b)
 assert n == args.windows
 pb.upload()
-for _ in range(args.launches):
-    pb.launch()
 torch.cuda.synchronize()
+ms = []
+for _ in range(args.launches):   # the batch runs on the legacy default stream here, torch's events see it
+    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    pb.launch()
+    b_.record()
+    torch.cuda.synchronize()
+    ms.append(round(a.elapsed_time(b_), 2))
+print("launch ms", ms, "windows/s", round(args.windows / (min(ms) / 1e3)))
 pb.download()
 cons, cov, st = pb.get_consensus()
 print("windows", n, "failed", int((st != 0).sum()), "info", pb.info())
