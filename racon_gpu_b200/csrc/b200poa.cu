@@ -580,7 +580,7 @@ int32_t b200poa_batch_launch(b200poa_batch* b) {
     /* shared memory geometry follows the longest read actually staged */
     const int32_t colsP = (b->max_len_staged + 1 + 7) & ~7;
     b->prof_stride = colsP;
-    b->ring_stride = (b->p.band_width > 0 && b->p.band_width < colsP) ? b->p.band_width : colsP;
+    b->ring_stride = ((b->p.band_width > 0 && b->p.band_width < colsP) ? b->p.band_width : colsP) + RING_PAD_FRONT + RING_PAD_BACK;
     int32_t ring_bytes = 4096;
     {   /* at least 8 ring rows: a predecessor more than 7 ranks back is rare (0.6%), more than 3 is not (19%) */
         const int32_t need8 = 8 * b->ring_stride * (int32_t)sizeof(int16_t);

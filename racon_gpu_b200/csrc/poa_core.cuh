@@ -316,10 +316,20 @@ POA_FN int32_t prof_row_of(int32_t code) { /* A,C,G,T -> 0..3, anything else -> 
 /* Predecessor entry as the fill consumes it:  far[0] | band start/8 [1:12) | delta[12:32) (signed), with
  * delta = (ring slot of the predecessor row) * ring_row_bytes - band_start * 2, so that the shared-memory
  * address of the predecessor cell under column c is  ring_base + c*2 + delta  (one add per predecessor). */
+/* Every ring row carries RING_PAD_FRONT cells before and RING_PAD_BACK cells after its band cells, all NEG:
+ * the fill reads a predecessor row at a small forward shift (its band starts at or before ours) and one cell
+ * to the left, and lands in the pads instead of testing the band limits. */
+constexpr int RING_PAD_FRONT = 8;
+constexpr int RING_PAD_BACK = 24;
 POA_FN uint32_t pfill_make(int32_t row, int32_t pr, int32_t bsp, int32_t ring_rows, int32_t ring_stride) {
     const int32_t far = (row - pr >= ring_rows) ? 1 : 0;
-    const int32_t delta = (pr & (ring_rows - 1)) * ring_stride * 2 - bsp * 2;
+    const int32_t delta = (pr & (ring_rows - 1)) * ring_stride * 2 + RING_PAD_FRONT * 2 - bsp * 2;
     return (uint32_t)far | ((uint32_t)(bsp >> 3) << 1) | ((uint32_t)delta << 12);
+}
+/* a row takes the fill's general path (record bit 12) if a predecessor is older than the ring or its band
+ * starts more than the back pad before the row's own */
+POA_FN bool pred_needs_general_path(int32_t row, int32_t bs_row, int32_t pr, int32_t bsp, int32_t ring_rows) {
+    return row - pr >= ring_rows || bs_row - bsp > RING_PAD_BACK;
 }
 
 struct ReadGeom {
@@ -328,6 +338,7 @@ struct ReadGeom {
     int32_t bw;     /* cells per row actually computed (multiple of 8) */
     int32_t banded; /* 1 if bw < colsP                                 */
     int32_t n_rows; /* graph rows of this alignment (whole graph, or the subgraph of a partial-span layer) */
+    uint32_t step;  /* band centre advance per row, 16.16 fixed point: (len << 16) / n_rows */
 };
 
 POA_FN ReadGeom read_geometry(const Params& p, int32_t len, int32_t n_rows) {
@@ -337,12 +348,16 @@ POA_FN ReadGeom read_geometry(const Params& p, int32_t len, int32_t n_rows) {
     g.colsP = (len + 1 + 7) & ~7;
     g.banded = (p.band_width > 0 && g.colsP > p.band_width) ? 1 : 0;
     g.bw = g.banded ? p.band_width : g.colsP;
+    g.step = ((uint32_t)len << 16) / (uint32_t)(n_rows > 0 ? n_rows : 1); /* len < 2^15 by the config limits */
     return g;
 }
 
+/* Static band: centred on the (0,0)-(n_rows,len) diagonal.  One division per read (ReadGeom::step), a multiply per
+ * row: every phase recomputes a row's band start with this function instead of loading it. */
 POA_FN int32_t band_start(const ReadGeom& g, int32_t row, int32_t n_rows) {
+    (void)n_rows; /* == g.n_rows */
     if (!g.banded) return 0;
-    const int32_t center = (int32_t)(((uint32_t)row * (uint32_t)g.len) / (uint32_t)n_rows); /* < 2^31 by the config limits */
+    const int32_t center = (int32_t)(((uint32_t)row * g.step) >> 16); /* row <= n_rows: row * step <= len << 16 < 2^31 */
     int32_t bs = center - g.bw / 2;
     if (bs > g.colsP - g.bw) bs = g.colsP - g.bw;
     if (bs < 0) bs = 0;
@@ -384,7 +399,7 @@ POA_FN_NOINLINE void build_program(const Slot& s_ref, const Params& p_ref, WinSt
                 if (s.nin[s.node_at[r0]] == 0) { /* virtual predecessor row 0 (sisd_alignment_engine.cpp:289-290) */
                     s.row_pred[o0] = 0;
                     s.row_pfill[o0] = pfill_make(r0 + 1, 0, 0, p.ring_rows, p.ring_stride);
-                    if (r0 + 1 >= p.ring_rows) s.row_rec[r0 + 1] |= 0x1000u;
+                    if (pred_needs_general_path(r0 + 1, band_start(g, r0 + 1, N), 0, 0, p.ring_rows)) s.row_rec[r0 + 1] |= 0x1000u;
                 }
             }
             if (r1 < N) {
@@ -392,7 +407,7 @@ POA_FN_NOINLINE void build_program(const Slot& s_ref, const Params& p_ref, WinSt
                 if (s.nin[s.node_at[r1]] == 0) {
                     s.row_pred[o1] = 0;
                     s.row_pfill[o1] = pfill_make(r1 + 1, 0, 0, p.ring_rows, p.ring_stride);
-                    if (r1 + 1 >= p.ring_rows) s.row_rec[r1 + 1] |= 0x1000u;
+                    if (pred_needs_general_path(r1 + 1, band_start(g, r1 + 1, N), 0, 0, p.ring_rows)) s.row_rec[r1 + 1] |= 0x1000u;
                 }
             }
         }
@@ -429,7 +444,8 @@ POA_FN_NOINLINE void build_program(const Slot& s_ref, const Params& p_ref, WinSt
                 const int32_t pbs = band_start(g, ru[k], N);
                 s.row_pred[o[k]] = (uint32_t)ru[k] | ((uint32_t)pbs << 16);
                 s.row_pfill[o[k]] = pfill_make(rd[k], ru[k], pbs, p.ring_rows, p.ring_stride);
-                if (rd[k] - ru[k] >= p.ring_rows) poa_atomic_or(&s.row_rec[rd[k]], 0x1000u); /* rare */
+                if (pred_needs_general_path(rd[k], band_start(g, rd[k], N), ru[k], pbs, p.ring_rows))
+                    poa_atomic_or(&s.row_rec[rd[k]], 0x1000u); /* rare */
             }
         }
     }
@@ -582,13 +598,13 @@ POA_FN_NOINLINE void build_program_sub(const Slot& s_ref, const Params& p_ref, W
                 const int32_t pbs = band_start(g, pr, N);
                 s.row_pred[o + k] = (uint32_t)pr | ((uint32_t)pbs << 16);
                 s.row_pfill[o + k] = pfill_make(r + 1, pr, pbs, p.ring_rows, p.ring_stride);
-                if (r + 1 - pr >= p.ring_rows) far = true;
+                if (pred_needs_general_path(r + 1, band_start(g, r + 1, N), pr, pbs, p.ring_rows)) far = true;
                 ++k;
             }
             if (k == 0) {
                 s.row_pred[o] = 0;
                 s.row_pfill[o] = pfill_make(r + 1, 0, 0, p.ring_rows, p.ring_stride);
-                if (r + 1 >= p.ring_rows) far = true;
+                if (pred_needs_general_path(r + 1, band_start(g, r + 1, N), 0, 0, p.ring_rows)) far = true;
             }
             if (c[l] > 255) wide[l] = 1;
             const int32_t code = s.code[v];
@@ -1096,57 +1112,79 @@ POA_FN_NOINLINE void add_alignment(const Slot& s_ref, const Params& p_ref, WinSt
     /* (d) edges prev -> cur for consecutive read positions (graph.cpp:248-259, 94-116), and
      * (e) coverage: every node on the read's path carries this sequence's label. */
     int32_t n_edges = st.n_edges;
-    for (int32_t base = 0; base < len; base += 32) {
-        PerLane<int> need;
-        PerLane<int> hit;
+    /* Two read positions per lane per step (pos, pos + 32): the walk over a node's in-edge list is a chain of
+     * dependent loads, the two walks are interleaved so that their round trips overlap.  New edge ids still
+     * follow read order: all of the first 32 positions, then the next 32. */
+    for (int32_t base = 0; base < len; base += 64) {
+        PerLane<int> need0, need1, hit0, hit1;
         POA_LANES(l) {
-            const int32_t pos = base + l;
-            need[l] = 0;
-            hit[l] = -1;
-            if (pos >= len) continue;
-            const int32_t cur = s.asg[pos];
-            if (len >= 2) s.cov[cur] = (uint16_t)(s.cov[cur] + 1);
-            if (pos == 0) continue;
-            const int32_t prev = s.asg[pos - 1];
-            int32_t found = -1;
-            for (uint16_t e = s.in_head[cur]; e != NONE16; e = s.e_next[e]) {
-                if (s.e_src[e] == prev) {
-                    found = e;
-                    break;
+            const int32_t pos0 = base + l, pos1 = base + 32 + l;
+            need0[l] = need1[l] = 0;
+            hit0[l] = hit1[l] = -1;
+            const bool in0 = pos0 < len, in1 = pos1 < len;
+            const int32_t cur0 = in0 ? s.asg[pos0] : 0, cur1 = in1 ? s.asg[pos1] : 0;
+            const int32_t prev0 = (in0 && pos0 > 0) ? s.asg[pos0 - 1] : -1, prev1 = in1 ? s.asg[pos1 - 1] : -1;
+            if (len >= 2) {
+                if (in0) s.cov[cur0] = (uint16_t)(s.cov[cur0] + 1);
+                if (in1) s.cov[cur1] = (uint16_t)(s.cov[cur1] + 1);
+            }
+            uint16_t e0 = (in0 && pos0 > 0) ? s.in_head[cur0] : NONE16;
+            uint16_t e1 = in1 ? s.in_head[cur1] : NONE16;
+            int32_t f0 = -1, f1 = -1;
+            while (e0 != NONE16 || e1 != NONE16) {
+                const int32_t s0 = e0 != NONE16 ? (int32_t)s.e_src[e0] : -2, s1 = e1 != NONE16 ? (int32_t)s.e_src[e1] : -2;
+                const uint16_t n0 = e0 != NONE16 ? s.e_next[e0] : NONE16, n1 = e1 != NONE16 ? s.e_next[e1] : NONE16;
+                if (s0 == prev0) {
+                    f0 = e0;
+                    e0 = NONE16;
+                } else {
+                    e0 = n0;
+                }
+                if (s1 == prev1) {
+                    f1 = e1;
+                    e1 = NONE16;
+                } else {
+                    e1 = n1;
                 }
             }
-            hit[l] = found;
-            need[l] = (found < 0) ? 1 : 0;
+            hit0[l] = f0;
+            hit1[l] = f1;
+            need0[l] = (in0 && pos0 > 0 && f0 < 0) ? 1 : 0;
+            need1[l] = (in1 && f1 < 0) ? 1 : 0;
         }
-        PerLane<int> off = need;
-        const int32_t tot = warp_exscan(off);
-        if (n_edges + tot > p.max_edges) {
+        PerLane<int> off0 = need0, off1 = need1;
+        const int32_t tot0 = warp_exscan(off0);
+        const int32_t tot1 = warp_exscan(off1);
+        if (n_edges + tot0 + tot1 > p.max_edges) {
             fail = ST_EDGE_COUNT_EXCEEDED;
             break;
         }
         POA_LANES(l) {
-            const int32_t pos = base + l;
-            if (pos >= len || pos == 0) continue;
-            const int32_t cur = s.asg[pos], prev = s.asg[pos - 1];
-            const int32_t w = (int32_t)wt[pos - 1] + (int32_t)wt[pos];
-            if (hit[l] >= 0) {
-                s.e_w[hit[l]] += w;
-            } else {
-                const int32_t e = n_edges + off[l];
-                s.e_src[e] = (uint16_t)prev;
-                s.e_dst[e] = (uint16_t)cur;
-                s.e_next[e] = NONE16;
-                s.e_w[e] = w;
-                s.e_ord[e] = (uint8_t)(s.nin[cur] < 255 ? s.nin[cur] : 255);
-                if (s.in_tail[cur] == NONE16) s.in_head[cur] = (uint16_t)e;
-                else s.e_next[s.in_tail[cur]] = (uint16_t)e;
-                s.in_tail[cur] = (uint16_t)e;
-                s.nin[cur] = (uint16_t)(s.nin[cur] + 1);
-                s.nout[prev] = (uint16_t)(s.nout[prev] + 1);
-                if (s.root[prev] == s.root[cur]) s.dirty[s.root[cur]] = 1;
+            for (int32_t u = 0; u < 2; ++u) {
+                const int32_t pos = base + 32 * u + l;
+                if (pos >= len || pos == 0) continue;
+                const int32_t cur = s.asg[pos], prev = s.asg[pos - 1];
+                const int32_t w = (int32_t)wt[pos - 1] + (int32_t)wt[pos];
+                const int32_t h = u ? hit1[l] : hit0[l];
+                if (h >= 0) {
+                    s.e_w[h] += w;
+                } else {
+                    const int32_t e = n_edges + (u ? tot0 + off1[l] : off0[l]);
+                    s.e_src[e] = (uint16_t)prev;
+                    s.e_dst[e] = (uint16_t)cur;
+                    s.e_next[e] = NONE16;
+                    s.e_w[e] = w;
+                    s.e_ord[e] = (uint8_t)(s.nin[cur] < 255 ? s.nin[cur] : 255);
+                    if (s.in_tail[cur] == NONE16) s.in_head[cur] = (uint16_t)e;
+                    else s.e_next[s.in_tail[cur]] = (uint16_t)e;
+                    s.in_tail[cur] = (uint16_t)e;
+                    s.nin[cur] = (uint16_t)(s.nin[cur] + 1);
+                    s.nout[prev] = (uint16_t)(s.nout[prev] + 1);
+                    if (s.root[prev] == s.root[cur]) s.dirty[s.root[cur]] = 1;
+                }
             }
         }
-        n_edges += tot;
+        n_edges += tot0 + tot1;
     }
     POA_SYNC();
     if (fail) {

@@ -80,7 +80,8 @@ __device__ __forceinline__ void sts16(uint32_t addr, int v) {
  *   [8, 16)                                 eight zero cells: profile of lanes beyond the band
  *   [16, 16 + PROF_ROWS*prof_stride/2)      profile rows, ONE BYTE per column (s - gap fits int8), widened
  *                                           to int16 pairs with two sign-replicating PRMTs per 4 cells
- *   [.., + (ring_rows+1)*ring_stride)       ring of score rows + one spare row for old predecessors
+ *   [.., + (ring_rows+1)*ring_stride)       ring of score rows + one spare row for old predecessors; every row is
+ *                                           RING_PAD_FRONT NEG cells | band cells | RING_PAD_BACK NEG cells
  */
 struct FillArgs { /* everything the row loop needs, and nothing else (keeps its register set small) */
     int16_t* S;
@@ -148,7 +149,7 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
     const uint32_t prof_sa = fa.smem_sa + 32u;
     const uint32_t ring_sa = prof_sa + (((uint32_t)(PROF_ROWS * prof_stride) + 15u) & ~15u); /* profile: 1 byte per column */
     const uint32_t ring_row_bytes = (uint32_t)fa.ring_stride * 2u;
-    const uint32_t far_sa = ring_sa + (uint32_t)R * ring_row_bytes;
+    const uint32_t far_sa = ring_sa + (uint32_t)R * ring_row_bytes + RING_PAD_FRONT * 2u; /* band cells of the spare row */
     const int lane8 = lane * 8;
     int dyn_code = -1; /* letter currently held by the on-demand profile row */
 
@@ -163,11 +164,18 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
         sts8(prof_sa + (uint32_t)(2 * prof_stride + col), ch == 'G' ? mg : xg);
         sts8(prof_sa + (uint32_t)(3 * prof_stride + col), ch == 'T' ? mg : xg);
     }
+    /* NEG pads of every ring row (the traceback tile overlays this memory between two fills) */
+#pragma unroll 1
+    for (int idx = lane; idx < (R + 1) * (1 + RING_PAD_BACK / 8); idx += 32) {
+        const int row = idx / (1 + RING_PAD_BACK / 8), part = idx % (1 + RING_PAD_BACK / 8);
+        const uint32_t cell = part == 0 ? 0u : (uint32_t)(fa.ring_stride - RING_PAD_BACK + 8 * (part - 1));
+        sts128(ring_sa + (uint32_t)row * ring_row_bytes + cell * 2u, make_uint4(NEG2, NEG2, NEG2, NEG2));
+    }
     /* row 0: H[0][j] = j*gap  =>  S = 0 (global copy for the traceback, ring slot 0 for the fill) */
 #pragma unroll 1
     for (int o = lane8; o < bw; o += CHUNK) {
         *reinterpret_cast<uint4*>(S + o) = make_uint4(0u, 0u, 0u, 0u);
-        sts128(ring_sa + (uint32_t)o * 2u, make_uint4(0u, 0u, 0u, 0u));
+        sts128(ring_sa + (uint32_t)(RING_PAD_FRONT + o) * 2u, make_uint4(0u, 0u, 0u, 0u));
     }
     /* register-resident streams: lane l holds entry (base + l); the next 32 are prefetched.
      * predA always starts at or before the current row's first entry and is re-aligned (two shuffles)
@@ -182,6 +190,7 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
 
     int best = NEG, end_row = 0;
     int po = 0; /* running offset into row_pfill (CSR is contiguous in row order) */
+    int16_t* Srow = S; /* global score row of the current graph row */
 #pragma unroll 1
     for (int i = 1; i <= N; ++i) {
         if ((i & 31) == 0) {
@@ -200,8 +209,8 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
             }
         }
         const uint32_t prof_row_sa = prof_sa + (uint32_t)(prow * prof_stride + bs + lane8);
-        int16_t* Srow = S + (size_t)i * stride;
-        const uint32_t ring_row_sa = ring_sa + (uint32_t)(i & ring_mask) * ring_row_bytes;
+        Srow += stride;
+        const uint32_t ring_row_sa = ring_sa + RING_PAD_FRONT * 2u + (uint32_t)(i & ring_mask) * ring_row_bytes;
         uint32_t carry = NEG2; /* S[i][last column of the previous chunk], both halves */
         int rel = po - pbase;  /* lane of predA holding this row's first entry */
         if (rel + np > 32) {   /* re-align the stream so that predA starts at this row (uniform, ~1 row in 18) */
@@ -237,6 +246,10 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
     do {                                                                                                   \
         const uint4 V = lds128((unsigned)off <= lim_v ? cell_sa : neg_sa);                                 \
         const uint32_t leftw = lds_u16((unsigned)(off - 1) < lim_l ? cell_sa - 2u : neg_sa) << 16;         \
+        POA_FILL_TERM();                                                                                   \
+    } while (0)
+#define POA_FILL_TERM()                                                                                    \
+    do {                                                                                                   \
         const uint32_t d0 = __funnelshift_l(leftw, V.x, 16);                                               \
         const uint32_t d1 = __funnelshift_l(V.x, V.y, 16);                                                 \
         const uint32_t d2 = __funnelshift_l(V.y, V.z, 16);                                                 \
@@ -251,8 +264,20 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
         a3 = __viaddmax_s16x2(V.w, G2, a3);                                                                \
     } while (0)
 
-            if (!rec_far(rec) && np <= 32) {
-                /* the common row: every predecessor is in the ring and its stream entry is in predA
+            if (FULLW && !rec_far(rec) && np <= 32) {
+                /* the common row of the banded configuration: every predecessor is in the ring, its band starts
+                 * 0..RING_PAD_BACK columns before ours, its stream entry is in predA.  Whatever falls outside the
+                 * predecessor's band lands in the row's NEG pads: no tests at all. */
+#pragma unroll 1
+                for (int q = 0; q < np; ++q) {
+                    const uint32_t pe = __shfl_sync(0xffffffffu, predA, rel + q);
+                    const uint32_t cell_sa = c0_sa + (uint32_t)((int)pe >> 12);
+                    const uint4 V = lds128(cell_sa);
+                    const uint32_t leftw = lds_u16(cell_sa - 2u) << 16;
+                    POA_FILL_TERM();
+                }
+            } else if (!rec_far(rec) && np <= 32) {
+                /* every predecessor is in the ring and its stream entry is in predA
                  * (out-of-band loads are redirected to the NEG cells: no branches, no predicates) */
 #pragma unroll 1
                 for (int q = 0; q < np; ++q) {
@@ -278,6 +303,7 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
                 }
             }
 #undef POA_FILL_ACCUMULATE
+#undef POA_FILL_TERM
 
             /* horizontal: inclusive prefix max over the 8 cells of the lane ... */
             a0 = __vmaxs2(a0, __byte_perm(a0, NEG2, 0x1054));
