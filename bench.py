@@ -254,6 +254,8 @@ def main():
     for _ in range(warmup):
         out_t = pol.polish(batch, tgs=True, trim=True, max_windows_per_round=chunk)
         out = (out_t[0], out_t[1], out_t[2].astype(np.uint8), out_t[3])
+        if world > 1:
+            gather_consensus(out_t[0], out_t[1], device)
     barrier()
     t0 = time.perf_counter()
     e2e_launches = 0

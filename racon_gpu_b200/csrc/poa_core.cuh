@@ -858,7 +858,32 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
         const int32_t prof = (j > 0 && rec_code(rec) == (int32_t)tile_u8(A_readc, j - c_lo)) ? mg : xg;
         bool in_tile = (np <= 32) && (po - pred_base + np <= pred_n);
         int32_t found = 0;
-        if (in_tile) {
+        if (in_tile && np == 1) {
+            /* the common row (one in-edge): the whole step is warp-uniform scalar code, no votes */
+            const int32_t pi = (int32_t)(tile_u32(A_pred, po - pred_base) & 0xFFFFu);
+            if (pi < r_lo) {
+                in_tile = false;
+            } else {
+                const int32_t cb = (r_hi - pi) * TB_COLS - c_lo + j;
+                const int32_t vv = tile_s16(A_cells, cb);
+                const int32_t vd = j > 0 ? tile_s16(A_cells, cb - 1) : 0;
+                const int32_t vh = j > 0 ? tile_s16(A_cells, ti * TB_COLS + (j - 1 - c_lo)) : 0;
+                if (j > 0 && vd + prof == cur) {
+                    ni = pi;
+                    nj = j - 1;
+                    ncur = cur - prof;
+                } else if (vv + gap == cur) {
+                    ni = pi;
+                    ncur = cur - gap;
+                } else if (j > 0 && vh == cur) {
+                    nj = j - 1;
+                } else {
+                    st.status = ST_TRACEBACK_LOST;
+                    return cap;
+                }
+                found = 1;
+            }
+        } else if (in_tile) {
             /* every lane rates its predecessor; ONE warp-min picks spoa's choice:
              *   0 = predecessor below the tile, 1+l = diagonal via in-edge l, 64+l = vertical via in-edge l */
             PerLane<int> key, pr;

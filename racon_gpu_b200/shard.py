@@ -20,24 +20,29 @@ def shard_range(n_windows: int, rank: int, world: int):
 
 
 def gather_consensus(cons: np.ndarray, clen: np.ndarray, device: torch.device):
-    """Gather every rank's padded consensus rows [w_r, stride] and lengths to rank 0 in rank order.
+    """Gather every rank's consensus rows and lengths to rank 0 in rank order (the one collective of the
+    path: windows are independent, cudapolisher.cpp:228-345 has no exchange step).
 
-    Rows are fixed-stride so this is one gather of a [W_max, stride] uint8 tensor plus one of the
-    lengths.  Returns (cons, clen) of the whole job on rank 0 and (None, None) elsewhere.
+    `cons` is [w_r, stride] with row w valid up to clen[w].  Only the first max(clen) columns travel (the
+    rows are padded to the engine's maximum consensus length, ~10x the real one).  Returns (cons, clen) of
+    the whole job on rank 0 -- rows [W, max_len], bytes past a row's length unspecified -- and (None, None)
+    elsewhere.
     """
     world = dist.get_world_size() if dist.is_initialized() else 1
     if world == 1:
         return cons, clen
     rank = dist.get_rank()
-    n_local = torch.tensor([cons.shape[0]], dtype=torch.int64, device=device)
-    counts = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(counts, n_local)
-    counts = [int(c.item()) for c in counts]
-    w_max, stride = max(counts), cons.shape[1]
-    pad_c = torch.zeros((w_max, stride), dtype=torch.uint8, device=device)
+    local_w = int(clen.max()) if clen.size else 0
+    meta = torch.tensor([cons.shape[0], local_w], dtype=torch.int64, device=device)
+    metas = [torch.zeros_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta)
+    counts = [int(m[0].item()) for m in metas]
+    w_max, width = max(counts), max(1, max(int(m[1].item()) for m in metas))
+    pad_c = torch.zeros((w_max, width), dtype=torch.uint8, device=device)
     pad_l = torch.zeros((w_max,), dtype=torch.int32, device=device)
-    pad_c[:cons.shape[0]] = torch.from_numpy(cons).to(device, non_blocking=True)
-    pad_l[:clen.shape[0]] = torch.from_numpy(clen).to(device, non_blocking=True)
+    take = min(width, cons.shape[1])
+    pad_c[:cons.shape[0], :take] = torch.from_numpy(np.ascontiguousarray(cons[:, :take])).to(device, non_blocking=True)
+    pad_l[:clen.shape[0]] = torch.from_numpy(np.ascontiguousarray(clen, dtype=np.int32)).to(device, non_blocking=True)
     out_c = [torch.empty_like(pad_c) for _ in range(world)] if rank == 0 else None
     out_l = [torch.empty_like(pad_l) for _ in range(world)] if rank == 0 else None
     dist.gather(pad_c, out_c, dst=0)
