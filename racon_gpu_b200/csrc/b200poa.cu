@@ -691,3 +691,12 @@ int32_t b200poa_batch_get_info(const b200poa_batch* b, b200poa_batch_info* info)
 }
 
 } // extern "C"
+
+#if defined(B200POA_SUBTIMERS)
+/* experiments only (not part of include/b200poa.h): sub-phase cycle counters since the last call */
+extern "C" int32_t b200poa_debug_subtimers(unsigned long long* out32) {
+    if (cudaMemcpyFromSymbol(out32, b200poa::g_subtimers, sizeof(unsigned long long) * 32) != cudaSuccess) return 1;
+    unsigned long long zero[32] = {0};
+    return cudaMemcpyToSymbol(b200poa::g_subtimers, zero, sizeof(zero)) != cudaSuccess;
+}
+#endif

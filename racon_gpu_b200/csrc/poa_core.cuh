@@ -233,6 +233,22 @@ struct PhaseTimer {
     }
 };
 
+/* Sub-phase cycle counters: compiled in only for experiments (scripts/build_variant.sh ... -DB200POA_SUBTIMERS=1),
+ * read back with b200poa_debug_subtimers(). */
+#if POA_DEVICE && defined(B200POA_SUBTIMERS)
+__device__ unsigned long long g_subtimers[32];
+#define POA_SUB_BEGIN() long long _sub_t = clock64()
+#define POA_SUB_LAP(k)                                                                          \
+    do {                                                                                        \
+        const long long _n = clock64();                                                         \
+        if ((threadIdx.x & 31u) == 0u) atomicAdd(&g_subtimers[k], (unsigned long long)(_n - _sub_t)); \
+        _sub_t = _n;                                                                            \
+    } while (0)
+#else
+#define POA_SUB_BEGIN() ((void)0)
+#define POA_SUB_LAP(k) ((void)0)
+#endif
+
 /* ------------------------------------------------------------------------------------------
  * Phase 0: backbone chain  (graph.cpp:274-292 add_sequence + :177-185; window.cpp:73-76)
  * ---------------------------------------------------------------------------------------- */
@@ -367,6 +383,7 @@ POA_FN int32_t band_start(const ReadGeom& g, int32_t row, int32_t n_rows) {
 POA_FN_NOINLINE void build_program(const Slot& s_ref, const Params& p_ref, WinState& st, const ReadGeom& g) {
     const Slot s = s_ref;     /* local copies: no reloads of the descriptor after every store */
     const Params p = p_ref;
+    POA_SUB_BEGIN();
     const int32_t N = st.n_nodes, E = st.n_edges;
     /* pass A, node-parallel, 64 rows per step: row records and CSR offsets (row r+1 <-> node_at[r]) */
     int32_t run = 0; /* running predecessor offset (uniform) */
@@ -416,6 +433,7 @@ POA_FN_NOINLINE void build_program(const Slot& s_ref, const Params& p_ref, WinSt
     POA_LANE0 { s.row_poff[N + 1] = (uint32_t)run; }
     if (warp_ballot(wide)) st.status = ST_EDGE_COUNT_EXCEEDED; /* in-degree > 255 does not fit the record */
     POA_SYNC();
+    POA_SUB_LAP(0);
     /* pass B, edge-parallel, 128 edges per step: every edge drops its source row into its slot of the
      * target's predecessor list (slot = e_ord, the edge's position in the in-edge list, fixed when the
      * edge was created) -- no linked-list walking, three dependent loads per edge. */
@@ -449,6 +467,7 @@ POA_FN_NOINLINE void build_program(const Slot& s_ref, const Params& p_ref, WinSt
             }
         }
     }
+    POA_SUB_LAP(1);
     POA_SYNC();
 }
 
@@ -674,6 +693,12 @@ struct TbScratch {           /* device: shared memory (the fill's ring area); em
 };
 constexpr int TB_SCRATCH_BYTES = TB_ROWS * TB_COLS * 2 + TB_ROWS * 4 + (TB_ROWS + 1) * 4 + TB_PRED_CAP * 4 + TB_ROWS * 2 + TB_COLS + 8 + 28;
 
+constexpr int TB_OFF_REC = TB_ROWS * TB_COLS * 2;          /* byte offsets of the parts, see tb_bind() */
+constexpr int TB_OFF_POFF = TB_OFF_REC + TB_ROWS * 4;
+constexpr int TB_OFF_PRED = TB_OFF_POFF + (TB_ROWS + 1) * 4;
+constexpr int TB_OFF_NODE = TB_OFF_PRED + TB_PRED_CAP * 4;
+constexpr int TB_OFF_READC = TB_OFF_NODE + TB_ROWS * 2;
+
 struct alignas(16) Vec16 { /* 8 int16 cells moved as one 128-bit access */
     uint32_t x, y, z, w;
 };
@@ -689,7 +714,7 @@ POA_FN void fill8(int16_t* dst, int32_t v) {
  * generic; a generic load pays the address-space resolution on every step of the dependent chain). */
 #if POA_DEVICE
 typedef uint32_t tile_addr;
-POA_FN tile_addr tile_base(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+POA_FN tile_addr tile_base(void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 POA_FN uint32_t tile_u32(tile_addr a, int32_t i) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a + 4u * (uint32_t)i));
@@ -710,20 +735,32 @@ POA_FN uint32_t tile_u8(tile_addr a, int32_t i) {
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a + (uint32_t)i));
     return v;
 }
-/* asynchronous global -> shared copies used by the tile load (LDGSTS: no register staging, all in flight) */
-POA_FN void tile_copy16(void* dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+/* asynchronous global -> shared copies used by the tile load (LDGSTS: no register staging, all in flight);
+ * destinations are shared-window addresses, like every other access to the tile */
+POA_FN void tile_copy16(tile_addr a, int32_t byte_off, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a + (uint32_t)byte_off), "l"(src) : "memory");
 }
-POA_FN void tile_copy4(void* dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+POA_FN void tile_copy4(tile_addr a, int32_t i, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(a + 4u * (uint32_t)i), "l"(src) : "memory");
 }
 POA_FN void tile_copy_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+POA_FN void tile_st_u32(tile_addr a, int32_t i, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a + 4u * (uint32_t)i), "r"(v) : "memory"); }
+POA_FN void tile_st_u16(tile_addr a, int32_t i, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a + 2u * (uint32_t)i), "r"(v) : "memory"); }
+POA_FN void tile_st_u8(tile_addr a, int32_t i, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a + (uint32_t)i), "r"(v) : "memory"); }
+POA_FN void tile_fill8(tile_addr a, int32_t byte_off, int32_t v) { /* 8 int16 cells */
+    const uint32_t pk = ((uint32_t)v & 0xFFFFu) | ((uint32_t)v << 16);
+    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a + (uint32_t)byte_off), "r"(pk) : "memory");
+}
 #else
-POA_FN void tile_copy16(void* dst, const void* src) { *reinterpret_cast<Vec16*>(dst) = *reinterpret_cast<const Vec16*>(src); }
-POA_FN void tile_copy4(void* dst, const void* src) { *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(src); }
+typedef uint8_t* tile_addr;
+POA_FN tile_addr tile_base(void* p) { return reinterpret_cast<uint8_t*>(p); }
+POA_FN void tile_copy16(tile_addr a, int32_t byte_off, const void* src) { *reinterpret_cast<Vec16*>(a + byte_off) = *reinterpret_cast<const Vec16*>(src); }
+POA_FN void tile_copy4(tile_addr a, int32_t i, const void* src) { reinterpret_cast<uint32_t*>(a)[i] = *reinterpret_cast<const uint32_t*>(src); }
 POA_FN void tile_copy_wait() {}
-typedef const uint8_t* tile_addr;
-POA_FN tile_addr tile_base(const void* p) { return reinterpret_cast<const uint8_t*>(p); }
+POA_FN void tile_st_u32(tile_addr a, int32_t i, uint32_t v) { reinterpret_cast<uint32_t*>(a)[i] = v; }
+POA_FN void tile_st_u16(tile_addr a, int32_t i, uint32_t v) { reinterpret_cast<uint16_t*>(a)[i] = (uint16_t)v; }
+POA_FN void tile_st_u8(tile_addr a, int32_t i, uint32_t v) { a[i] = (uint8_t)v; }
+POA_FN void tile_fill8(tile_addr a, int32_t byte_off, int32_t v) { fill8(reinterpret_cast<int16_t*>(a + byte_off), v); }
 POA_FN uint32_t tile_u32(tile_addr a, int32_t i) { return reinterpret_cast<const uint32_t*>(a)[i]; }
 POA_FN int32_t tile_s16(tile_addr a, int32_t i) { return reinterpret_cast<const int16_t*>(a)[i]; }
 POA_FN uint32_t tile_u16(tile_addr a, int32_t i) { return reinterpret_cast<const uint16_t*>(a)[i]; }
@@ -749,12 +786,6 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
     /* everything the loop touches is copied into locals first: `s`, `t`, `p`, `g` are references into
      * memory, and after each store the compiler would otherwise reload every pointer it needs */
     const int32_t cap = p.max_nodes + p.max_len + 2;
-    int16_t* const T_cells = t.cells;
-    uint32_t* const T_rec = t.rec;
-    uint32_t* const T_poff = t.poff;
-    uint32_t* const T_pred = t.pred;
-    uint16_t* const T_node = t.node;
-    uint8_t* const T_readc = t.readc;
     int16_t* const tb_node = s.tb_node;
     int16_t* const tb_pos = s.tb_pos;
     const uint32_t* const row_rec = s.row_rec;
@@ -764,8 +795,11 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
     const int16_t* const S = s.S;
     const int32_t stride = p.stride, gap = p.gap, bw = g.bw, rlen = g.len;
     const ReadGeom gg = g;
-    const tile_addr A_cells = tile_base(t.cells), A_rec = tile_base(t.rec), A_poff = tile_base(t.poff),
-                    A_pred = tile_base(t.pred), A_node = tile_base(t.node), A_readc = tile_base(t.readc);
+    /* the tile is addressed from ONE base (shared-window address on the device); its parts sit at constant offsets */
+    const tile_addr A_cells = tile_base(t.cells);
+    const tile_addr A_rec = A_cells + TB_OFF_REC, A_poff = A_cells + TB_OFF_POFF, A_pred = A_cells + TB_OFF_PRED,
+                    A_node = A_cells + TB_OFF_NODE, A_readc = A_cells + TB_OFF_READC;
+    POA_SUB_BEGIN();
     int32_t w = cap; /* write cursor (uniform) */
     int32_t i = end_row, j = rlen;
     const int32_t mg = p.match - gap, xg = p.mismatch - gap;
@@ -799,6 +833,7 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
         /* ---- make sure row i and columns j-1..j are in the tile ---- */
         bool reloaded = false;
         if (i > r_hi || i < r_lo || j > c_hi || j - 1 < c_lo) {
+            POA_SUB_LAP(11);
             r_hi = i;
             r_lo = i - (TB_ROWS - 1) < 0 ? 0 : i - (TB_ROWS - 1);
             c_hi = j;
@@ -821,32 +856,33 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
 #pragma unroll
                     for (int32_t q = 0; q < TB_CHUNKS; ++q) {
                         const int32_t o = c_lo + 8 * q - bs; /* 8-aligned both: whole chunk in the band or out */
-                        int16_t* dst = T_cells + k * TB_COLS + 8 * q;
-                        if (o >= 0 && o + 8 <= bw) tile_copy16(dst, S + (size_t)row * stride + o);
-                        else fill8(dst, NEG);
+                        const int32_t dst = (k * TB_COLS + 8 * q) * 2; /* byte offset in the tile */
+                        if (o >= 0 && o + 8 <= bw) tile_copy16(A_cells, dst, S + (size_t)row * stride + o);
+                        else tile_fill8(A_cells, dst, NEG);
                     }
                     if (row >= 1) {
-                        tile_copy4(T_rec + k, row_rec + row);
-                        tile_copy4(T_poff + k, row_poff + row);
-                        T_node[k] = node_at[row - 1];
+                        tile_copy4(A_rec, k, row_rec + row);
+                        tile_copy4(A_poff, k, row_poff + row);
+                        tile_st_u16(A_node, k, node_at[row - 1]);
                     } else {
-                        T_rec[k] = 0u;
-                        T_poff[k] = 0u;
-                        T_node[k] = 0;
+                        tile_st_u32(A_rec, k, 0u);
+                        tile_st_u32(A_poff, k, 0u);
+                        tile_st_u16(A_node, k, 0u);
                     }
                 }
                 for (int32_t c = c_lo + l; c < c_lo + TB_COLS; c += 32) /* read bases under the tile's columns */
-                    T_readc[c - c_lo] = (c >= 1 && c <= rlen) ? read[c - 1] : (uint8_t)0;
+                    tile_st_u8(A_readc, c - c_lo, (c >= 1 && c <= rlen) ? read[c - 1] : (uint8_t)0);
             }
             /* CSR entries of rows r_lo..r_hi are contiguous: [poff(r_lo'), poff(r_hi) + np(r_hi)) */
             pred_base = p_lo;
             pred_n = p_hi - p_lo;
             if (pred_n > TB_PRED_CAP) pred_n = TB_PRED_CAP; /* rows beyond the cap fall back to global */
             POA_LANES(l) {
-                for (int32_t e = l; e < pred_n; e += 32) tile_copy4(T_pred + e, row_pred + pred_base + e);
+                for (int32_t e = l; e < pred_n; e += 32) tile_copy4(A_pred, e, row_pred + pred_base + e);
             }
             tile_copy_wait();
             POA_SYNC();
+            POA_SUB_LAP(12);
             reloaded = true;
         }
         /* ---- one step at (i, j) ---- */
@@ -985,6 +1021,7 @@ POA_FN_NOINLINE void add_alignment(const Slot& s_ref, const Params& p_ref, WinSt
     const Slot s = s_ref;     /* local copies: no reloads of the descriptor after every store */
     const Params p = p_ref;
     const int32_t cap = p.max_nodes + p.max_len + 2;
+    POA_SUB_BEGIN();
     const int32_t N0 = st.n_nodes;
 
     /* (a) resolve every read position: existing node, or a new node (unaligned / aligned to x).
@@ -1023,6 +1060,7 @@ POA_FN_NOINLINE void add_alignment(const Slot& s_ref, const Params& p_ref, WinSt
     }
     POA_SYNC();
 
+    POA_SUB_LAP(2);
     /* (b) create the new nodes; ids follow read order exactly like the serial add_node calls. */
     int32_t n_new = 0;
     int32_t fail = 0;
@@ -1090,6 +1128,7 @@ POA_FN_NOINLINE void add_alignment(const Slot& s_ref, const Params& p_ref, WinSt
         return;
     }
 
+    POA_SUB_LAP(3);
     /* (c) roots of new unaligned nodes: root[v] = min(v, root[next node on the read path]); a run
      *     of consecutive new unaligned nodes all see the node that ends the run. */
     for (int32_t base = 0; base < len; base += 32) {
@@ -1134,6 +1173,7 @@ POA_FN_NOINLINE void add_alignment(const Slot& s_ref, const Params& p_ref, WinSt
     POA_SYNC();
     st.n_nodes = N0 + n_new;
 
+    POA_SUB_LAP(4);
     /* (d) edges prev -> cur for consecutive read positions (graph.cpp:248-259, 94-116), and
      * (e) coverage: every node on the read's path carries this sequence's label. */
     int32_t n_edges = st.n_edges;
@@ -1216,6 +1256,7 @@ POA_FN_NOINLINE void add_alignment(const Slot& s_ref, const Params& p_ref, WinSt
         st.status = fail;
         return;
     }
+    POA_SUB_LAP(5);
     st.n_edges = n_edges;
 }
 
@@ -1304,6 +1345,7 @@ POA_FN_NOINLINE void topsort_serial(const Slot& s_ref, const Params& p_ref, WinS
 POA_FN_NOINLINE void topsort_roots(const Slot& s_ref, const Params& p_ref, WinState& st) {
     const Slot s = s_ref;     /* local copies: no reloads of the descriptor after every store */
     const Params p = p_ref;
+    POA_SUB_BEGIN();
     const int32_t N = st.n_nodes;
     /* 1. members of dirty roots: reset DFS marks, accumulate the root's stack bound.  Two nodes per lane
      *    per step so that the dependent loads (root -> dirty) of both are in flight together. */
@@ -1325,6 +1367,7 @@ POA_FN_NOINLINE void topsort_roots(const Slot& s_ref, const Params& p_ref, WinSt
         }
     }
     POA_SYNC();
+    POA_SUB_LAP(6);
     /* 2a. offsets: prefix-sum the member counts over root ids (two ids per lane per step); collect the
      *     dirty multi-node roots into a compact work list (so that the DFS below keeps all lanes busy);
      *     need[] is consumed and zeroed for the next read. */
@@ -1379,6 +1422,7 @@ POA_FN_NOINLINE void topsort_roots(const Slot& s_ref, const Params& p_ref, WinSt
         n_work += wtot;
     }
     POA_SYNC();
+    POA_SUB_LAP(7);
     /* 2b. spoa's DFS restricted to the members of each dirty root, 32 roots at a time */
     for (int32_t base = 0; base < n_work; base += 32) {
         POA_LANES(l) {
@@ -1424,6 +1468,7 @@ POA_FN_NOINLINE void topsort_roots(const Slot& s_ref, const Params& p_ref, WinSt
         }
     }
     POA_SYNC();
+    POA_SUB_LAP(8);
     /* 3. ranks (four nodes per lane per step, loads staged by dependency level) */
     for (int32_t base = 0; base < N; base += 128) {
         POA_LANES(l) {
@@ -1448,6 +1493,7 @@ POA_FN_NOINLINE void topsort_roots(const Slot& s_ref, const Params& p_ref, WinSt
     }
     POA_SYNC();
     (void)p;
+    POA_SUB_LAP(9);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -1481,20 +1527,112 @@ POA_FN void consensus_scores_from(const Slot& s, int32_t N, int32_t first_rank, 
     }
 }
 
+/* The first, full scoring pass (graph.cpp:494-518), 32 ranks at a time.
+ *   gather  (parallel): lane l walks the in-edges of the node at rank r0+l and finds its heaviest in-edge.  Only a
+ *           TIE between equal weights needs predecessor scores to be decided (graph.cpp:505-509); the score of
+ *           a predecessor ranked before this block is final and fetched here.
+ *   resolve (serial over the 32 lanes, but on registers): score = weight + score[pred]; a predecessor inside
+ *           the block is read from its lane by shuffle.  Tied nodes redo the literal walk against memory.
+ * max_id follows the serial rule "first strictly larger score wins" (scores[max_score_id] < scores[id]). */
+POA_FN void consensus_scores_full(const Slot& s, int32_t N, int32_t& max_id_out) {
+    int32_t max_id = 0, max_sc = -1; /* scores[] starts at -1 everywhere */
+    for (int32_t r0 = 0; r0 < N; r0 += 32) {
+        PerLane<int> id, w, pd, prank, pre, tie, score;
+        POA_LANES(l) {
+            const int32_t r = r0 + l;
+            id[l] = 0;
+            w[l] = -1;
+            pd[l] = -1;
+            prank[l] = -1;
+            pre[l] = 0;
+            tie[l] = 0;
+            score[l] = -1;
+            if (r < N) {
+                const int32_t v = s.node_at[r];
+                id[l] = v;
+                int32_t sc = -1, best = -1, t = 0;
+                for (uint16_t e = s.in_head[v]; e != NONE16; e = s.e_next[e]) {
+                    const int32_t ww = s.e_w[e];
+                    if (sc < ww) {
+                        sc = ww;
+                        best = s.e_src[e];
+                        t = 0;
+                    } else if (sc == ww) {
+                        t = 1;
+                    }
+                }
+                w[l] = sc;
+                pd[l] = best;
+                tie[l] = t;
+                if (best >= 0) {
+                    const int32_t pr = s.rank_of[best];
+                    prank[l] = pr;
+                    if (pr < r0) pre[l] = s.c_score[best];
+                }
+            }
+        }
+        const int32_t cnt = N - r0 < 32 ? N - r0 : 32;
+        const unsigned ties = warp_ballot(tie);
+        for (int32_t k = 0; k < cnt; ++k) {
+            if ((ties >> k) & 1u) { /* rare: the literal rule, predecessor scores from memory */
+                POA_SYNC();
+                POA_LANES(l) {
+                    if (l != k) continue;
+                    const int32_t v = id[l];
+                    int32_t sc = -1, best = -1;
+                    for (uint16_t e = s.in_head[v]; e != NONE16; e = s.e_next[e]) {
+                        const int32_t u = s.e_src[e];
+                        const int32_t ww = s.e_w[e];
+                        if (sc < ww || (sc == ww && s.c_score[best] <= s.c_score[u])) {
+                            sc = ww;
+                            best = u;
+                        }
+                    }
+                    if (best != -1) sc += s.c_score[best];
+                    score[l] = sc;
+                    s.c_score[v] = sc;
+                    s.c_pred[v] = best;
+                }
+                POA_SYNC();
+                continue;
+            }
+            const int32_t pk = warp_get(prank, k);
+            const int32_t from_lane = warp_get(score, pk >= r0 ? pk - r0 : 0);
+            POA_LANES(l) {
+                if (l != k) continue;
+                int32_t sc = w[l];
+                if (pd[l] != -1) sc += (pk >= r0) ? from_lane : pre[l];
+                score[l] = sc;
+                s.c_score[id[l]] = sc;
+                s.c_pred[id[l]] = pd[l];
+            }
+        }
+        POA_SYNC(); /* this block's scores are in memory before the next block gathers */
+        PerLane<int> sv;
+        POA_LANES(l) { sv[l] = l < cnt ? score[l] : -2; }
+        const int32_t m = warp_max(sv);
+        if (m > max_sc) {
+            PerLane<int> is;
+            POA_LANES(l) { is[l] = (l < cnt && score[l] == m) ? 1 : 0; }
+            max_id = warp_get(id, poa_ffs(warp_ballot(is)));
+            max_sc = m;
+        }
+    }
+    max_id_out = max_id;
+}
+
 POA_FN_NOINLINE void generate_consensus(const Slot& s_ref, const Params& p_ref, WinState& st, uint8_t* out_cons,
                                uint16_t* out_cov, int32_t* out_len) {
     const Slot s = s_ref;     /* local copies: no reloads of the descriptor after every store */
     const Params p = p_ref;
     const int32_t N = st.n_nodes;
+    POA_SUB_BEGIN();
     int32_t len = 0;
+    int32_t max_id_full = 0;
+    consensus_scores_full(s, N, max_id_full);
     POA_LANE0 {
-        int32_t max_id = 0, dummy = 0;
-        s.c_score[0] = -1; /* scores[max_score_id] is read before node 0 is scored only if rank 0 != node 0 */
-        for (int32_t i = 0; i < N; ++i) {
-            s.c_score[i] = -1;
-            s.c_pred[i] = -1;
-        }
-        consensus_scores_from(s, N, 0, false, max_id, dummy, true);
+        int32_t max_id = max_id_full;
+        POA_SUB_LAP(13);
         int32_t guard = N + 1;
         while (s.nout[max_id] != 0 && guard-- > 0) { /* graph.cpp:520-530 */
             const int32_t node_id = max_id;
@@ -1510,6 +1648,7 @@ POA_FN_NOINLINE void generate_consensus(const Slot& s_ref, const Params& p_ref, 
             max_id = 0;
             consensus_scores_from(s, N, rank + 1, true, max_id, ms, false);
         }
+        POA_SUB_LAP(14);
         /* backtrack into c_score as scratch (path reversed), then emit forward */
         int32_t n = 0;
         int32_t v = max_id;
@@ -1529,6 +1668,7 @@ POA_FN_NOINLINE void generate_consensus(const Slot& s_ref, const Params& p_ref, 
             for (int32_t q = 0; q < s.aln_cnt[id]; ++q) c += s.cov[s.aln[id * KA + q]];
             out_cov[k] = (uint16_t)c;
         }
+        POA_SUB_LAP(15);
         len = n;
         *out_len = n;
     }

@@ -37,3 +37,16 @@ pc = pb.phase_cycles()
 if pc:
     tot = sum(pc.values())
     print("phase cycles per window per launch:", {k: round(v / n / args.launches / 1e6, 2) for k, v in pc.items()}, "Mcycles; total", round(tot / n / args.launches / 1e6, 2))
+
+try:
+    import ctypes
+    lib = ctypes.CDLL(os.environ.get("B200POA_LIB", os.path.join(ROOT, "racon_gpu_b200", "libb200poa.so")))
+    f = lib.b200poa_debug_subtimers
+    buf = (ctypes.c_ulonglong * 32)()
+    f(buf)
+    names = {0: "program.A", 1: "program.B", 2: "add.a", 3: "add.b", 4: "add.c", 5: "add.d", 6: "topsort.1", 7: "topsort.2a",
+             8: "topsort.2b", 9: "topsort.3", 11: "traceback.steps", 12: "traceback.tile_load", 13: "consensus.scores",
+             14: "consensus.branch_completion", 15: "consensus.emit"}
+    print("sub-phase Mcycles per window per launch:", {names.get(i, i): round(buf[i] / n / args.launches / 1e6, 2) for i in range(32) if buf[i]})
+except AttributeError:
+    pass
