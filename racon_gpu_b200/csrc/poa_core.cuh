@@ -380,9 +380,10 @@ POA_FN int32_t band_start(const ReadGeom& g, int32_t row, int32_t n_rows) {
     return bs & ~7;
 }
 
-POA_FN_NOINLINE void build_program(const Slot& s_ref, const Params& p_ref, WinState& st, const ReadGeom& g) {
+POA_FN_NOINLINE void build_program(const Slot& s_ref, const Params& p_ref, WinState& st, const ReadGeom& g_ref) {
     const Slot s = s_ref;     /* local copies: no reloads of the descriptor after every store */
     const Params p = p_ref;
+    const ReadGeom g = g_ref;
     POA_SUB_BEGIN();
     const int32_t N = st.n_nodes, E = st.n_edges;
     /* pass A, node-parallel, 64 rows per step: row records and CSR offsets (row r+1 <-> node_at[r]) */
@@ -579,9 +580,10 @@ POA_FN_NOINLINE int32_t mark_subgraph(const Slot& s_ref, const Params& p_ref, Wi
 
 /* Row program of a subgraph alignment: rows follow sub_at[], predecessor lists keep only member
  * sources (in in-edge order), a row without member sources gets the virtual predecessor row 0. */
-POA_FN_NOINLINE void build_program_sub(const Slot& s_ref, const Params& p_ref, WinState& st, const ReadGeom& g) {
+POA_FN_NOINLINE void build_program_sub(const Slot& s_ref, const Params& p_ref, WinState& st, const ReadGeom& g_ref) {
     const Slot s = s_ref;
     const Params p = p_ref;
+    const ReadGeom g = g_ref;
     const int32_t N = g.n_rows;
     int32_t run = 0;
     POA_LANE0 { s.row_rec[0] = 0; }
@@ -691,13 +693,16 @@ struct TbScratch {           /* device: shared memory (the fill's ring area); em
     uint16_t* node;          /* [TB_ROWS]   node id of row (r_hi - k)                   */
     uint8_t* readc;          /* [TB_COLS + 8] read base under column c at c - c_lo (column c <-> read[c-1]) */
 };
-constexpr int TB_SCRATCH_BYTES = TB_ROWS * TB_COLS * 2 + TB_ROWS * 4 + (TB_ROWS + 1) * 4 + TB_PRED_CAP * 4 + TB_ROWS * 2 + TB_COLS + 8 + 28;
+constexpr int TB_SCRATCH_BYTES = TB_ROWS * TB_COLS * 2 + TB_ROWS * 4 + (TB_ROWS + 1) * 4 + TB_PRED_CAP * 4 + TB_ROWS * 2 + TB_COLS + 8 + 28 +
+                                 TB_ROWS * 4 + 32 * 4 + 4;
 
 constexpr int TB_OFF_REC = TB_ROWS * TB_COLS * 2;          /* byte offsets of the parts, see tb_bind() */
 constexpr int TB_OFF_POFF = TB_OFF_REC + TB_ROWS * 4;
 constexpr int TB_OFF_PRED = TB_OFF_POFF + (TB_ROWS + 1) * 4;
 constexpr int TB_OFF_NODE = TB_OFF_PRED + TB_PRED_CAP * 4;
 constexpr int TB_OFF_READC = TB_OFF_NODE + TB_ROWS * 2;
+constexpr int TB_OFF_INFO = (TB_OFF_READC + TB_COLS + 8 + 3) & ~3; /* [TB_ROWS] u32: node id | predecessor tile row | letter */
+constexpr int TB_OFF_OUT = TB_OFF_INFO + TB_ROWS * 4;              /* [32] u32: buffered alignment entries */
 
 struct alignas(16) Vec16 { /* 8 int16 cells moved as one 128-bit access */
     uint32_t x, y, z, w;
@@ -798,21 +803,38 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
     /* the tile is addressed from ONE base (shared-window address on the device); its parts sit at constant offsets */
     const tile_addr A_cells = tile_base(t.cells);
     const tile_addr A_rec = A_cells + TB_OFF_REC, A_poff = A_cells + TB_OFF_POFF, A_pred = A_cells + TB_OFF_PRED,
-                    A_node = A_cells + TB_OFF_NODE, A_readc = A_cells + TB_OFF_READC;
+                    A_node = A_cells + TB_OFF_NODE, A_readc = A_cells + TB_OFF_READC, A_info = A_cells + TB_OFF_INFO,
+                    A_out = A_cells + TB_OFF_OUT;
     POA_SUB_BEGIN();
     int32_t w = cap; /* write cursor (uniform) */
     int32_t i = end_row, j = rlen;
     const int32_t mg = p.match - gap, xg = p.mismatch - gap;
-    int32_t guard = p.max_nodes + p.max_len + 4;
     int32_t cur = score_at(s, p, g, i, j);
     /* tile state (uniform) */
     int32_t r_hi = -1, r_lo = 0, c_lo = 0, c_hi = -1, pred_base = 0, pred_n = 0;
+    /* alignment entries (node | read position) are collected in the tile and written out 32 at a time, coalesced:
+     * entry b of the buffer belongs to index w + nb - 1 - b */
+    int32_t nb = 0;
+#define POA_TB_FLUSH()                                                                  \
+    do {                                                                                \
+        POA_SYNC();                                                                     \
+        POA_LANES(l) {                                                                  \
+            if (l < nb) {                                                               \
+                const uint32_t e = tile_u32(A_out, l);                                  \
+                tb_node[w + nb - 1 - l] = (int16_t)(e & 0xFFFFu);                       \
+                tb_pos[w + nb - 1 - l] = (int16_t)(e >> 16);                            \
+            }                                                                           \
+        }                                                                               \
+        POA_SYNC();                                                                     \
+        nb = 0;                                                                         \
+    } while (0)
     while (!(i == 0 && j == 0)) {
-        if (--guard < 0 || w <= 32) {
+        if (w <= 32) { /* every step consumes one entry: a path longer than nodes + read length is lost */
             st.status = ST_TRACEBACK_LOST;
             return cap;
         }
         if (i == 0) { /* first row: S[0][*] == 0, only horizontal moves are left */
+            POA_TB_FLUSH();
             for (int32_t b = 0; b < j; b += 32) {
                 POA_LANES(l) {
                     const int32_t jj = j - b - l;
@@ -832,7 +854,7 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
         }
         /* ---- make sure row i and columns j-1..j are in the tile ---- */
         bool reloaded = false;
-        if (i > r_hi || i < r_lo || j > c_hi || j - 1 < c_lo) {
+        if (i > r_hi || i < r_lo || j > c_hi || (j > 0 && j - 1 < c_lo)) {
             POA_SUB_LAP(11);
             r_hi = i;
             r_lo = i - (TB_ROWS - 1) < 0 ? 0 : i - (TB_ROWS - 1);
@@ -882,44 +904,62 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
             }
             tile_copy_wait();
             POA_SYNC();
+            /* digest for the serial walk: a row with ONE in-edge whose source is in the tile takes the short step */
+            POA_LANES(l) {
+#pragma unroll
+                for (int32_t rr = 0; rr < TB_RPL; ++rr) {
+                    const int32_t k = l + 32 * rr;
+                    const int32_t row = r_hi - k;
+                    if (row < r_lo) continue;
+                    const uint32_t rc = tile_u32(A_rec, k);
+                    const int32_t q = (int32_t)tile_u32(A_poff, k) - pred_base;
+                    uint32_t tp = 0xFFu;
+                    if (row >= 1 && rec_npred(rc) == 1 && q < pred_n) {
+                        const int32_t pi = (int32_t)(tile_u32(A_pred, q) & 0xFFFFu);
+                        if (pi >= r_lo) tp = (uint32_t)(r_hi - pi);
+                    }
+                    tile_st_u32(A_info, k, (tile_u16(A_node, k) << 16) | (tp << 8) | (uint32_t)rec_code(rc));
+                }
+            }
+            POA_SYNC();
             POA_SUB_LAP(12);
             reloaded = true;
         }
         /* ---- one step at (i, j) ---- */
         int32_t ni = i, nj = j, ncur = cur;
         const int32_t ti = r_hi - i; /* tile row index of row i */
+        const uint32_t info = tile_u32(A_info, ti);
+        const int32_t tp = (int32_t)((info >> 8) & 0xFFu);
+        uint32_t node_i = info >> 16;
+        if (tp != 0xFF) {
+            /* the common row (one in-edge, source in the tile): warp-uniform scalar code on four tile reads */
+            const int32_t x = j - c_lo; /* >= 1 unless j == 0 */
+            const int32_t cb = tp * TB_COLS + x;
+            const int32_t vv = tile_s16(A_cells, cb);
+            const int32_t vd = tile_s16(A_cells, j > 0 ? cb - 1 : cb);
+            const int32_t vh = tile_s16(A_cells, j > 0 ? ti * TB_COLS + x - 1 : cb);
+            const int32_t prof = (j > 0 && (int32_t)(info & 0xFFu) == (int32_t)tile_u8(A_readc, x)) ? mg : xg;
+            if (j > 0 && vd + prof == cur) {
+                ni = r_hi - tp;
+                nj = j - 1;
+                ncur = cur - prof;
+            } else if (vv + gap == cur) {
+                ni = r_hi - tp;
+                ncur = cur - gap;
+            } else if (j > 0 && vh == cur) {
+                nj = j - 1;
+            } else {
+                st.status = ST_TRACEBACK_LOST;
+                return cap;
+            }
+        } else {
         const uint32_t rec = tile_u32(A_rec, ti);
         const int32_t np = rec_npred(rec);
         const int32_t po = (int32_t)tile_u32(A_poff, ti);
         const int32_t prof = (j > 0 && rec_code(rec) == (int32_t)tile_u8(A_readc, j - c_lo)) ? mg : xg;
         bool in_tile = (np <= 32) && (po - pred_base + np <= pred_n);
         int32_t found = 0;
-        if (in_tile && np == 1) {
-            /* the common row (one in-edge): the whole step is warp-uniform scalar code, no votes */
-            const int32_t pi = (int32_t)(tile_u32(A_pred, po - pred_base) & 0xFFFFu);
-            if (pi < r_lo) {
-                in_tile = false;
-            } else {
-                const int32_t cb = (r_hi - pi) * TB_COLS - c_lo + j;
-                const int32_t vv = tile_s16(A_cells, cb);
-                const int32_t vd = j > 0 ? tile_s16(A_cells, cb - 1) : 0;
-                const int32_t vh = j > 0 ? tile_s16(A_cells, ti * TB_COLS + (j - 1 - c_lo)) : 0;
-                if (j > 0 && vd + prof == cur) {
-                    ni = pi;
-                    nj = j - 1;
-                    ncur = cur - prof;
-                } else if (vv + gap == cur) {
-                    ni = pi;
-                    ncur = cur - gap;
-                } else if (j > 0 && vh == cur) {
-                    nj = j - 1;
-                } else {
-                    st.status = ST_TRACEBACK_LOST;
-                    return cap;
-                }
-                found = 1;
-            }
-        } else if (in_tile) {
+        if (in_tile) {
             /* every lane rates its predecessor; ONE warp-min picks spoa's choice:
              *   0 = predecessor below the tile, 1+l = diagonal via in-edge l, 64+l = vertical via in-edge l */
             PerLane<int> key, pr;
@@ -962,7 +1002,6 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
         if (!in_tile) {
             if (!reloaded) { /* a predecessor fell off the tile: re-anchor the tile at (i, j) and retry */
                 r_hi = -1;
-                ++guard;
                 continue;
             }
             /* even a tile anchored here does not hold the step: read global memory directly */
@@ -1000,15 +1039,17 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
                 }
             }
         }
+        } /* general step */
         --w;
-        POA_LANE0 {
-            tb_node[w] = (int16_t)((i == ni) ? -1 : (int32_t)tile_u16(A_node, ti));
-            tb_pos[w] = (int16_t)((j == nj) ? -1 : (j - 1));
-        }
+        tile_st_u32(A_out, nb, ((i == ni) ? 0xFFFFu : node_i) | ((uint32_t)((j == nj) ? 0xFFFF : (j - 1)) << 16));
+        ++nb;
+        if (nb == 32) POA_TB_FLUSH();
         i = ni;
         j = nj;
         cur = ncur;
     }
+    POA_TB_FLUSH();
+#undef POA_TB_FLUSH
     POA_SYNC();
     return w;
 }
