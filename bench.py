@@ -93,7 +93,8 @@ def recorded_traffic(workload: str):
     if os.path.exists(path):
         rec = json.load(open(path))
         if workload in rec:
-            return rec[workload]
+            r = rec[workload]
+            return float(r["dram_bytes_per_launch"]) if isinstance(r, dict) else float(r)
     return None
 
 

@@ -674,10 +674,10 @@ POA_FN int32_t score_at_bs(const Slot& s, const Params& p, const ReadGeom& g, in
  *   Output: tb_node/tb_pos filled back to front; returns the index of the first (leftmost) entry.
  * ---------------------------------------------------------------------------------------- */
 #ifndef POA_TB_RPL
-#define POA_TB_RPL 1
+#define POA_TB_RPL 2
 #endif
 #ifndef POA_TB_CHUNKS
-#define POA_TB_CHUNKS 7
+#define POA_TB_CHUNKS 4
 #endif
 constexpr int TB_RPL = POA_TB_RPL;       /* tile rows loaded per lane */
 constexpr int TB_ROWS = 32 * TB_RPL;     /* tile rows */
