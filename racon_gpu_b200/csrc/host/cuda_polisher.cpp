@@ -180,15 +180,22 @@ extern "C" int32_t b200poa_polisher_polish(b200poa_polisher* h, int64_t n_window
     const int64_t chunk = max_windows_per_round > 0
                               ? max_windows_per_round
                               : std::max<int64_t>(256, (n_windows + (int64_t)procs.size() * 4 - 1) / ((int64_t)procs.size() * 4));
-    auto worker = [&](FlatProc* p) -> int32_t {
+    const int64_t n_procs = static_cast<int64_t>(procs.size());
+    auto worker = [&](FlatProc* p, int64_t index) -> int32_t {
         cudaSetDevice(p->device);
         int64_t lo = 0, hi = 0; /* claimed but not yet processed windows */
         std::vector<int32_t> seqs_added;
+        /* The processors share the GPU: while one of them downloads, trims and stages, the kernels of the others
+         * must keep it full.  Their first rounds are therefore of different sizes (1/P, 2/P, ... of a round), which
+         * starts the first kernel early and keeps the processors out of step from then on. */
+        bool first_claim = true;
         for (;;) {
             if (lo == hi) {
                 std::lock_guard<std::mutex> g(mu);
+                const int64_t want = first_claim ? std::max<int64_t>(1, chunk * (index + 1) / n_procs) : chunk;
+                first_claim = false;
                 lo = cursor;
-                hi = std::min<int64_t>(n_windows, lo + chunk);
+                hi = std::min<int64_t>(n_windows, lo + want);
                 cursor = hi;
             }
             if (lo == hi) return B200POA_SUCCESS;
@@ -255,7 +262,7 @@ extern "C" int32_t b200poa_polisher_polish(b200poa_polisher* h, int64_t n_window
     };
     std::vector<int32_t> results(procs.size(), B200POA_SUCCESS);
     std::vector<std::thread> th;
-    for (size_t t = 0; t < procs.size(); ++t) th.emplace_back([&, t]() { results[t] = worker(&procs[t]); });
+    for (size_t t = 0; t < procs.size(); ++t) th.emplace_back([&, t]() { results[t] = worker(&procs[t], (int64_t)t); });
     for (auto& t : th) t.join();
     int32_t rc = B200POA_SUCCESS;
     for (int32_t r : results)

@@ -1423,6 +1423,18 @@ POA_FN_NOINLINE void topsort_roots(const Slot& s_ref, const Params& p_ref, WinSt
             const int db = (i1 < N && cb[l] > 0) ? (int)s.dirty[i1] : 0;
             wa[l] = (da && ca[l] > 1) ? 1 : 0;
             wb[l] = (db && cb[l] > 1) ? 1 : 0;
+            /* a root whose members are exactly its own aligned clique (a mismatch bubble, the commonest multi-node
+             * root) needs no DFS: spoa visits the root, pushes the mates, and emits root, mate 0, mate 1, ... */
+            if (wa[l] && ca[l] == 1 + (int)s.aln_cnt[i0]) {
+                s.lpos[i0] = 0;
+                for (int32_t q = 0; q + 1 < ca[l]; ++q) s.lpos[s.aln[i0 * KA + q]] = (uint16_t)(q + 1);
+                wa[l] = 0;
+            }
+            if (wb[l] && cb[l] == 1 + (int)s.aln_cnt[i1]) {
+                s.lpos[i1] = 0;
+                for (int32_t q = 0; q + 1 < cb[l]; ++q) s.lpos[s.aln[i1 * KA + q]] = (uint16_t)(q + 1);
+                wb[l] = 0;
+            }
             na[l] = wa[l] ? (int)s.need[i0] + 1 : 0;
             nb[l] = wb[l] ? (int)s.need[i1] + 1 : 0;
             if (da) {
