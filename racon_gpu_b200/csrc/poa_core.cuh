@@ -1218,64 +1218,83 @@ POA_FN_NOINLINE void add_alignment(const Slot& s_ref, const Params& p_ref, WinSt
     /* (d) edges prev -> cur for consecutive read positions (graph.cpp:248-259, 94-116), and
      * (e) coverage: every node on the read's path carries this sequence's label. */
     int32_t n_edges = st.n_edges;
-    /* Two read positions per lane per step (pos, pos + 32): the walk over a node's in-edge list is a chain of
-     * dependent loads, the two walks are interleaved so that their round trips overlap.  New edge ids still
-     * follow read order: all of the first 32 positions, then the next 32. */
-    for (int32_t base = 0; base < len; base += 64) {
-        PerLane<int> need0, need1, hit0, hit1;
+    /* DU read positions per lane per step (pos, pos + 32, ...): the walk over a node's in-edge list is a chain of
+     * dependent loads to HBM; the DU walks of a lane are interleaved so that their round trips overlap.  New edge
+     * ids follow read order (position = base + 32 u + lane: u-major), computed from ballots. */
+    constexpr int DU = 4;
+    for (int32_t base = 0; base < len; base += 32 * DU) {
+        PerLane<int> hit[DU], need[DU];
         POA_LANES(l) {
-            const int32_t pos0 = base + l, pos1 = base + 32 + l;
-            need0[l] = need1[l] = 0;
-            hit0[l] = hit1[l] = -1;
-            const bool in0 = pos0 < len, in1 = pos1 < len;
-            const int32_t cur0 = in0 ? s.asg[pos0] : 0, cur1 = in1 ? s.asg[pos1] : 0;
-            const int32_t prev0 = (in0 && pos0 > 0) ? s.asg[pos0 - 1] : -1, prev1 = in1 ? s.asg[pos1 - 1] : -1;
-            if (len >= 2) {
-                if (in0) s.cov[cur0] = (uint16_t)(s.cov[cur0] + 1);
-                if (in1) s.cov[cur1] = (uint16_t)(s.cov[cur1] + 1);
+            int32_t cur[DU], prev[DU], f[DU];
+            uint16_t e[DU];
+#pragma unroll
+            for (int32_t u = 0; u < DU; ++u) {
+                const int32_t pos = base + 32 * u + l;
+                const bool in = pos < len;
+                cur[u] = in ? s.asg[pos] : 0;
+                prev[u] = (in && pos > 0) ? s.asg[pos - 1] : -1;
+                f[u] = -1;
             }
-            uint16_t e0 = (in0 && pos0 > 0) ? s.in_head[cur0] : NONE16;
-            uint16_t e1 = in1 ? s.in_head[cur1] : NONE16;
-            int32_t f0 = -1, f1 = -1;
-            while (e0 != NONE16 || e1 != NONE16) {
-                const int32_t s0 = e0 != NONE16 ? (int32_t)s.e_src[e0] : -2, s1 = e1 != NONE16 ? (int32_t)s.e_src[e1] : -2;
-                const uint16_t n0 = e0 != NONE16 ? s.e_next[e0] : NONE16, n1 = e1 != NONE16 ? s.e_next[e1] : NONE16;
-                if (s0 == prev0) {
-                    f0 = e0;
-                    e0 = NONE16;
-                } else {
-                    e0 = n0;
+#pragma unroll
+            for (int32_t u = 0; u < DU; ++u) {
+                const int32_t pos = base + 32 * u + l;
+                const bool in = pos < len;
+                if (in && len >= 2) s.cov[cur[u]] = (uint16_t)(s.cov[cur[u]] + 1);
+                e[u] = (in && pos > 0) ? s.in_head[cur[u]] : NONE16;
+            }
+            for (;;) {
+                bool any = false;
+#pragma unroll
+                for (int32_t u = 0; u < DU; ++u) any = any || e[u] != NONE16;
+                if (!any) break;
+                int32_t src[DU];
+                uint16_t nx[DU];
+#pragma unroll
+                for (int32_t u = 0; u < DU; ++u) {
+                    src[u] = e[u] != NONE16 ? (int32_t)s.e_src[e[u]] : -2;
+                    nx[u] = e[u] != NONE16 ? s.e_next[e[u]] : NONE16;
                 }
-                if (s1 == prev1) {
-                    f1 = e1;
-                    e1 = NONE16;
-                } else {
-                    e1 = n1;
+#pragma unroll
+                for (int32_t u = 0; u < DU; ++u) {
+                    if (src[u] == prev[u]) {
+                        f[u] = e[u];
+                        e[u] = NONE16;
+                    } else {
+                        e[u] = nx[u];
+                    }
                 }
             }
-            hit0[l] = f0;
-            hit1[l] = f1;
-            need0[l] = (in0 && pos0 > 0 && f0 < 0) ? 1 : 0;
-            need1[l] = (in1 && f1 < 0) ? 1 : 0;
+#pragma unroll
+            for (int32_t u = 0; u < DU; ++u) {
+                const int32_t pos = base + 32 * u + l;
+                hit[u][l] = f[u];
+                need[u][l] = (pos < len && pos > 0 && f[u] < 0) ? 1 : 0;
+            }
         }
-        PerLane<int> off0 = need0, off1 = need1;
-        const int32_t tot0 = warp_exscan(off0);
-        const int32_t tot1 = warp_exscan(off1);
-        if (n_edges + tot0 + tot1 > p.max_edges) {
+        unsigned nmask[DU];
+        int32_t first[DU], tot = 0;
+#pragma unroll
+        for (int32_t u = 0; u < DU; ++u) {
+            nmask[u] = warp_ballot(need[u]);
+            first[u] = tot;
+            tot += poa_popc(nmask[u]);
+        }
+        if (n_edges + tot > p.max_edges) {
             fail = ST_EDGE_COUNT_EXCEEDED;
             break;
         }
         POA_LANES(l) {
-            for (int32_t u = 0; u < 2; ++u) {
+#pragma unroll
+            for (int32_t u = 0; u < DU; ++u) {
                 const int32_t pos = base + 32 * u + l;
                 if (pos >= len || pos == 0) continue;
                 const int32_t cur = s.asg[pos], prev = s.asg[pos - 1];
                 const int32_t w = (int32_t)wt[pos - 1] + (int32_t)wt[pos];
-                const int32_t h = u ? hit1[l] : hit0[l];
+                const int32_t h = hit[u][l];
                 if (h >= 0) {
                     s.e_w[h] += w;
                 } else {
-                    const int32_t e = n_edges + (u ? tot0 + off1[l] : off0[l]);
+                    const int32_t e = n_edges + first[u] + poa_popc(nmask[u] & ((1u << l) - 1u));
                     s.e_src[e] = (uint16_t)prev;
                     s.e_dst[e] = (uint16_t)cur;
                     s.e_next[e] = NONE16;
@@ -1290,7 +1309,7 @@ POA_FN_NOINLINE void add_alignment(const Slot& s_ref, const Params& p_ref, WinSt
                 }
             }
         }
-        n_edges += tot0 + tot1;
+        n_edges += tot;
     }
     POA_SYNC();
     if (fail) {
@@ -1388,22 +1407,28 @@ POA_FN_NOINLINE void topsort_roots(const Slot& s_ref, const Params& p_ref, WinSt
     const Params p = p_ref;
     POA_SUB_BEGIN();
     const int32_t N = st.n_nodes;
-    /* 1. members of dirty roots: reset DFS marks, accumulate the root's stack bound.  Two nodes per lane
-     *    per step so that the dependent loads (root -> dirty) of both are in flight together. */
-    for (int32_t base = 0; base < N; base += 64) {
+    /* 1. members of dirty roots: reset DFS marks, accumulate the root's stack bound.  Four nodes per lane
+     *    per step so that the dependent loads (root -> dirty -> in-degree) of all four are in flight together. */
+    for (int32_t base = 0; base < N; base += 128) {
         POA_LANES(l) {
-            const int32_t v0 = base + l, v1 = base + 32 + l;
-            const int32_t r0 = v0 < N ? (int32_t)s.root[v0] : 0, r1 = v1 < N ? (int32_t)s.root[v1] : 0;
-            const bool d0 = v0 < N && s.dirty[r0], d1 = v1 < N && s.dirty[r1];
-            if (d0) {
-                s.marks[v0] = 0;
-                s.check[v0] = 1;
-                poa_atomic_add(&s.need[r0], (uint32_t)(s.nin[v0] + s.aln_cnt[v0] + 1));
+            int32_t r[4], nn[4];
+            bool d[4];
+#pragma unroll
+            for (int32_t u = 0; u < 4; ++u) {
+                const int32_t v = base + 32 * u + l;
+                r[u] = v < N ? (int32_t)s.root[v] : 0;
+                nn[u] = v < N ? (int32_t)s.nin[v] + (int32_t)s.aln_cnt[v] + 1 : 0;
             }
-            if (d1) {
-                s.marks[v1] = 0;
-                s.check[v1] = 1;
-                poa_atomic_add(&s.need[r1], (uint32_t)(s.nin[v1] + s.aln_cnt[v1] + 1));
+#pragma unroll
+            for (int32_t u = 0; u < 4; ++u) d[u] = (base + 32 * u + l < N) && s.dirty[r[u]];
+#pragma unroll
+            for (int32_t u = 0; u < 4; ++u) {
+                const int32_t v = base + 32 * u + l;
+                if (d[u]) {
+                    s.marks[v] = 0;
+                    s.check[v] = 1;
+                    poa_atomic_add(&s.need[r[u]], (uint32_t)nn[u]);
+                }
             }
         }
     }

@@ -122,6 +122,13 @@ POA_FN void warp_shift_down1(const PerLane<int>& x, PerLane<int>& out) {
 
 #endif
 
+POA_FN int poa_popc(unsigned m) {
+#if POA_DEVICE
+    return __popc(m);
+#else
+    return __builtin_popcount(m);
+#endif
+}
 POA_FN int poa_ffs(unsigned m) { /* index of lowest set bit, m != 0 */
 #if POA_DEVICE
     return __ffs((int)m) - 1;

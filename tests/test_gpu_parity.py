@@ -189,3 +189,18 @@ def test_ten_thousand_windows_are_deterministic_across_batch_splits():
     assert p1.all() and p2.all()
     assert (l1 == l2).all() and (c1 == c2).all()
     assert (l1[:5000] == l1[5000:]).all() and (c1[:5000] == c1[5000:]).all()
+
+
+def test_full_size_run_sampled_against_the_oracle(oracle):
+    """BASELINE config 3 at full size: 10k windows, FULL band, every workspace reused by ~3 windows under full
+    occupancy; a random sample of 192 windows must equal the oracle bit for bit, and the failure count is 0."""
+    b = synth_windows(10000, 500, 32, 0.15, seed=53)
+    cons, clen, pol, status, _ = api.polish_windows(b, M, X, G, banded=False, tgs=True, trim=True, mem_per_batch=48 << 30)
+    assert pol.all() and (status == 0).all()
+    rng = np.random.default_rng(7)
+    pick = np.sort(rng.choice(10000, size=192, replace=False))
+    sub = WindowBatch.from_lists([[(s, w, bg, en) for s, w, bg, en in zip(*b.window(int(i)))] for i in pick])
+    order = api.processing_order(sub)
+    oc, _, _ = oracle.polish(sub, order, M, X, G, tgs=True, trim=True, threads=16)
+    got = api.consensus_list(cons, clen)
+    assert [got[int(i)] for i in pick] == oc
