@@ -392,7 +392,7 @@ POA_FN_NOINLINE void build_program(const Slot& s_ref, const Params& p_ref, WinSt
     PerLane<int> wide;
     POA_LANES(l) { wide[l] = 0; }
     for (int32_t base = 0; base < N; base += 64) {
-        PerLane<int> c0, c1;
+        PerLane<int> c0, c1, z0, z1;
         POA_LANES(l) { /* both rows' loads are independent: two round trips for 64 rows */
             const int32_t r0 = base + 2 * l, r1 = r0 + 1;
             const int32_t v0 = r0 < N ? (int32_t)s.node_at[r0] : 0;
@@ -402,6 +402,8 @@ POA_FN_NOINLINE void build_program(const Slot& s_ref, const Params& p_ref, WinSt
             const bool s0 = s.nout[v0] == 0, s1 = s.nout[v1] == 0;
             c0[l] = r0 < N ? (d0 ? d0 : 1) : 0;
             c1[l] = r1 < N ? (d1 ? d1 : 1) : 0;
+            z0[l] = (r0 < N && d0 == 0) ? 1 : 0; /* no in-edge: the virtual predecessor row 0 */
+            z1[l] = (r1 < N && d1 == 0) ? 1 : 0;
             if (c0[l] > 255 || c1[l] > 255) wide[l] = 1;
             if (r0 < N) s.row_rec[r0 + 1] = rec_make(k0, s0, prof_row_of(k0), c0[l] & 0xFF, band_start(g, r0 + 1, N));
             if (r1 < N) s.row_rec[r1 + 1] = rec_make(k1, s1, prof_row_of(k1), c1[l] & 0xFF, band_start(g, r1 + 1, N));
@@ -414,7 +416,7 @@ POA_FN_NOINLINE void build_program(const Slot& s_ref, const Params& p_ref, WinSt
             const int32_t o0 = run + off[l], o1 = o0 + c0[l];
             if (r0 < N) {
                 s.row_poff[r0 + 1] = (uint32_t)o0;
-                if (s.nin[s.node_at[r0]] == 0) { /* virtual predecessor row 0 (sisd_alignment_engine.cpp:289-290) */
+                if (z0[l]) { /* virtual predecessor row 0 (sisd_alignment_engine.cpp:289-290) */
                     s.row_pred[o0] = 0;
                     s.row_pfill[o0] = pfill_make(r0 + 1, 0, 0, p.ring_rows, p.ring_stride);
                     if (pred_needs_general_path(r0 + 1, band_start(g, r0 + 1, N), 0, 0, p.ring_rows)) s.row_rec[r0 + 1] |= 0x1000u;
@@ -422,7 +424,7 @@ POA_FN_NOINLINE void build_program(const Slot& s_ref, const Params& p_ref, WinSt
             }
             if (r1 < N) {
                 s.row_poff[r1 + 1] = (uint32_t)o1;
-                if (s.nin[s.node_at[r1]] == 0) {
+                if (z1[l]) {
                     s.row_pred[o1] = 0;
                     s.row_pfill[o1] = pfill_make(r1 + 1, 0, 0, p.ring_rows, p.ring_stride);
                     if (pred_needs_general_path(r1 + 1, band_start(g, r1 + 1, N), 0, 0, p.ring_rows)) s.row_rec[r1 + 1] |= 0x1000u;
@@ -1235,13 +1237,17 @@ POA_FN_NOINLINE void add_alignment(const Slot& s_ref, const Params& p_ref, WinSt
                 prev[u] = (in && pos > 0) ? s.asg[pos - 1] : -1;
                 f[u] = -1;
             }
+            int32_t cv[DU];
 #pragma unroll
-            for (int32_t u = 0; u < DU; ++u) {
+            for (int32_t u = 0; u < DU; ++u) { /* loads before the stores, see below */
                 const int32_t pos = base + 32 * u + l;
                 const bool in = pos < len;
-                if (in && len >= 2) s.cov[cur[u]] = (uint16_t)(s.cov[cur[u]] + 1);
+                cv[u] = (in && len >= 2) ? (int32_t)s.cov[cur[u]] : 0;
                 e[u] = (in && pos > 0) ? s.in_head[cur[u]] : NONE16;
             }
+#pragma unroll
+            for (int32_t u = 0; u < DU; ++u)
+                if (base + 32 * u + l < len && len >= 2) s.cov[cur[u]] = (uint16_t)(cv[u] + 1);
             for (;;) {
                 bool any = false;
 #pragma unroll
@@ -1284,28 +1290,48 @@ POA_FN_NOINLINE void add_alignment(const Slot& s_ref, const Params& p_ref, WinSt
             break;
         }
         POA_LANES(l) {
+            /* all loads of the DU positions first (their addresses do not depend on each other), then all the
+             * stores: a load placed after a store to the same workspace could not be moved up by the compiler and
+             * would cost a round trip of its own */
+            int32_t cur[DU], prev[DU], w[DU], old_w[DU], nin_c[DU], tail_c[DU], nout_p[DU], root_c[DU], root_p[DU];
+            bool act[DU];
 #pragma unroll
             for (int32_t u = 0; u < DU; ++u) {
                 const int32_t pos = base + 32 * u + l;
-                if (pos >= len || pos == 0) continue;
-                const int32_t cur = s.asg[pos], prev = s.asg[pos - 1];
-                const int32_t w = (int32_t)wt[pos - 1] + (int32_t)wt[pos];
+                act[u] = pos < len && pos != 0;
+                cur[u] = act[u] ? s.asg[pos] : 0;
+                prev[u] = act[u] ? s.asg[pos - 1] : 0;
+                w[u] = act[u] ? (int32_t)wt[pos - 1] + (int32_t)wt[pos] : 0;
+            }
+#pragma unroll
+            for (int32_t u = 0; u < DU; ++u) {
+                const bool is_new = act[u] && hit[u][l] < 0;
+                old_w[u] = (act[u] && !is_new) ? s.e_w[hit[u][l]] : 0;
+                nin_c[u] = is_new ? (int32_t)s.nin[cur[u]] : 0;
+                tail_c[u] = is_new ? (int32_t)s.in_tail[cur[u]] : 0;
+                nout_p[u] = is_new ? (int32_t)s.nout[prev[u]] : 0;
+                root_c[u] = is_new ? (int32_t)s.root[cur[u]] : 0;
+                root_p[u] = is_new ? (int32_t)s.root[prev[u]] : 1;
+            }
+#pragma unroll
+            for (int32_t u = 0; u < DU; ++u) {
+                if (!act[u]) continue;
                 const int32_t h = hit[u][l];
                 if (h >= 0) {
-                    s.e_w[h] += w;
+                    s.e_w[h] = old_w[u] + w[u];
                 } else {
                     const int32_t e = n_edges + first[u] + poa_popc(nmask[u] & ((1u << l) - 1u));
-                    s.e_src[e] = (uint16_t)prev;
-                    s.e_dst[e] = (uint16_t)cur;
+                    s.e_src[e] = (uint16_t)prev[u];
+                    s.e_dst[e] = (uint16_t)cur[u];
                     s.e_next[e] = NONE16;
-                    s.e_w[e] = w;
-                    s.e_ord[e] = (uint8_t)(s.nin[cur] < 255 ? s.nin[cur] : 255);
-                    if (s.in_tail[cur] == NONE16) s.in_head[cur] = (uint16_t)e;
-                    else s.e_next[s.in_tail[cur]] = (uint16_t)e;
-                    s.in_tail[cur] = (uint16_t)e;
-                    s.nin[cur] = (uint16_t)(s.nin[cur] + 1);
-                    s.nout[prev] = (uint16_t)(s.nout[prev] + 1);
-                    if (s.root[prev] == s.root[cur]) s.dirty[s.root[cur]] = 1;
+                    s.e_w[e] = w[u];
+                    s.e_ord[e] = (uint8_t)(nin_c[u] < 255 ? nin_c[u] : 255);
+                    if (tail_c[u] == NONE16) s.in_head[cur[u]] = (uint16_t)e;
+                    else s.e_next[tail_c[u]] = (uint16_t)e;
+                    s.in_tail[cur[u]] = (uint16_t)e;
+                    s.nin[cur[u]] = (uint16_t)(nin_c[u] + 1);
+                    s.nout[prev[u]] = (uint16_t)(nout_p[u] + 1);
+                    if (root_p[u] == root_c[u]) s.dirty[root_c[u]] = 1;
                 }
             }
         }
@@ -1448,18 +1474,6 @@ POA_FN_NOINLINE void topsort_roots(const Slot& s_ref, const Params& p_ref, WinSt
             const int db = (i1 < N && cb[l] > 0) ? (int)s.dirty[i1] : 0;
             wa[l] = (da && ca[l] > 1) ? 1 : 0;
             wb[l] = (db && cb[l] > 1) ? 1 : 0;
-            /* a root whose members are exactly its own aligned clique (a mismatch bubble, the commonest multi-node
-             * root) needs no DFS: spoa visits the root, pushes the mates, and emits root, mate 0, mate 1, ... */
-            if (wa[l] && ca[l] == 1 + (int)s.aln_cnt[i0]) {
-                s.lpos[i0] = 0;
-                for (int32_t q = 0; q + 1 < ca[l]; ++q) s.lpos[s.aln[i0 * KA + q]] = (uint16_t)(q + 1);
-                wa[l] = 0;
-            }
-            if (wb[l] && cb[l] == 1 + (int)s.aln_cnt[i1]) {
-                s.lpos[i1] = 0;
-                for (int32_t q = 0; q + 1 < cb[l]; ++q) s.lpos[s.aln[i1 * KA + q]] = (uint16_t)(q + 1);
-                wb[l] = 0;
-            }
             na[l] = wa[l] ? (int)s.need[i0] + 1 : 0;
             nb[l] = wb[l] ? (int)s.need[i1] + 1 : 0;
             if (da) {
