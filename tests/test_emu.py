@@ -88,3 +88,15 @@ def test_limits_report_status_instead_of_crashing(emu):
     assert (st == 2).all()  # exceeded_maximum_sequence_size
     _, _, st, _ = emu.polish(b, order, 120, -120, -120)
     assert (st == 12).all()  # int16 score range
+
+
+def test_long_window_stress_with_a_larger_sequence_limit(emu, oracle):
+    """BASELINE config 5 (1024 bp x 64 reads, 12 %): half the reads exceed racon's 1023-base BatchConfig; with the
+    limit raised (graph limits scale with it, batch.cu:34-71) full band is bit-exact and band 256 matches."""
+    b = synth_windows(4, 1024, 64, 0.12, seed=5)
+    order = api.processing_order(b)
+    oc, ocov, _ = oracle.polish(b, order, M, X, G, tgs=False, trim=False, threads=8)
+    ec, ecov, st, _ = emu.polish(b, order, M, X, G, band=0, max_len=1279, max_nodes=3840, max_edges=6 * 3840)
+    assert (st == 0).all() and ec == oc and all((a == c).all() for a, c in zip(ecov, ocov))
+    bc, _, st, _ = emu.polish(b, order, M, X, G, band=256, max_len=1279, max_nodes=5116, max_edges=6 * 5116)
+    assert (st == 0).all() and sum(a == c for a, c in zip(bc, oc)) >= 3

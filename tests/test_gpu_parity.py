@@ -204,3 +204,25 @@ def test_full_size_run_sampled_against_the_oracle(oracle):
     oc, _, _ = oracle.polish(sub, order, M, X, G, tgs=True, trim=True, threads=16)
     got = api.consensus_list(cons, clen)
     assert [got[int(i)] for i in pick] == oc
+
+
+def test_long_window_stress_at_true_size(oracle):
+    """BASELINE config 5: 1024 bp x 64 reads, 12 % error.  Half of the reads are longer than racon's hard-coded
+    1023-base limit (cudabatch.cpp:59 BatchConfig(1023, ...)); the engine's limit is a BatchConfig field, so the
+    stress case runs with max_sequence_size = 1279 (graph limits scale with it like batch.cu:34-71): full band
+    bit-exact, static band within the stated tolerance."""
+    b = synth_windows(24, 1024, 64, 0.12, seed=5)
+    assert (np.diff(b.seq_off) > 1023).any()
+    order = api.processing_order(b)
+    oc, ocov, _ = oracle.polish(b, order, M, X, G, tgs=False, trim=False, threads=16)
+    gc, gcov, st = gpu_untrimmed(b, banded=False, max_sequence_size=1279, mem=24 << 30)
+    assert (st == 0).all() and gc == oc
+    assert all((a == c).all() for a, c in zip(gcov, ocov))
+    bc, _, st = gpu_untrimmed(b, banded=True, max_sequence_size=1279, mem=24 << 30)
+    assert (st == 0).all()
+    assert sum(a == c for a, c in zip(bc, oc)) >= 23 and max(edit_distance(a, c) for a, c in zip(bc, oc)) <= 2
+    # with racon's own limit the long reads are dropped and reported per sequence, never silently
+    pb = api.PoaBatch(max_gpu_mem=MEM, banded=True)
+    n, seqs_added = pb.add_windows(b)
+    pb.close()
+    assert n == 24 and (np.asarray(seqs_added) < 64).any()
