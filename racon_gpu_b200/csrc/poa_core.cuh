@@ -24,12 +24,18 @@
  *     ancestor-closure contains v).  root[] is fixed when a node is created, DFS_i for different
  *     roots are independent, so 32 roots are sorted concurrently and concatenated by a prefix sum.
  *     The plain serial DFS is kept (topsort_serial) as the in-kernel cross-check for tests.
- *   - traceback: the predecessors of a cell are tested by different lanes, first-match by ballot.
+ *   - traceback: the path is walked through a shared-memory tile of the score matrix loaded by one round
+ *     of asynchronous copies; rows with one in-edge take a warp-uniform scalar step, rows with several are
+ *     rated by different lanes and decided by one warp-min;
+ *   - consensus: heaviest-bundle scores 32 ranks at a time (parallel gather, in-register resolve).
+ * Every phase is bound by the latency of dependent loads to HBM (a window's graph does not stay in L2 with
+ * 3552 windows in flight), so the loops are shaped to keep many independent loads in flight and to place
+ * loads before stores (a load behind a store to the workspace cannot be hoisted by the compiler).
  *
  * Score cells are int16 in the "skewed" domain S[i][j] = H[i][j] - j*gap so that the horizontal
  * recurrence H[i][j-1]+gap becomes a pure prefix max:
  *   S[i][j] = max( max_p S[p][j-1] + (s(i,j) - gap), max_p S[p][j] + gap, S[i][j-1] ).
- * The DP fill itself is in poa_fill.cuh (CUDA) / emu_fill.hpp (scalar twin for the CPU tests).
+ * The DP fill itself is in poa_fill.cuh (CUDA); tests/emu has its scalar twin for the CPU tests.
  */
 #pragma once
 #include "poa_simt.cuh"
