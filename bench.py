@@ -178,6 +178,7 @@ def main():
     ap.add_argument("--windows", type=int, default=0, help="override windows per GPU")
     ap.add_argument("--seed", type=int, default=12345)
     ap.add_argument("--batches", type=int, default=4, help="batch processors per GPU for the e2e leg (racon -c)")
+    ap.add_argument("--rounds", type=float, default=1.0, help="e2e leg: launches per batch processor per step (chunk = windows / (batches x rounds))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -250,7 +251,7 @@ def main():
     # ---------------- e2e: host buffers through the public API -------------------------------------
     pol = api.Polisher(devices=[local_rank], batches_per_device=args.batches, mem_per_batch=mem // args.batches,
                        banded=banded, match=M, mismatch=X, gap=G)
-    chunk = max(256, -(-nwin // (args.batches * 2)))  # two rounds per batch processor: each launch fills the GPU
+    chunk = max(256, int(-(-nwin // (args.batches * args.rounds))))  # windows per launch of a batch processor
     out = None
     for _ in range(warmup):
         out_t = pol.polish(batch, tgs=True, trim=True, max_windows_per_round=chunk)

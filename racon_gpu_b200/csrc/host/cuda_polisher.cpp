@@ -8,6 +8,8 @@
 #include <cstring>
 #include <mutex>
 #include <stdexcept>
+#include <chrono>
+#include <cstdlib>
 #include <thread>
 
 #include "b200poa.h"
@@ -189,6 +191,11 @@ extern "C" int32_t b200poa_polisher_polish(b200poa_polisher* h, int64_t n_window
          * must keep it full.  Their first rounds are therefore of different sizes (1/P, 2/P, ... of a round), which
          * starts the first kernel early and keeps the processors out of step from then on. */
         bool first_claim = true;
+        const bool timers = std::getenv("B200POA_E2E_TIMERS") != nullptr; /* diagnostics: where a round's wall time goes */
+        double t_stage = 0, t_gpu = 0, t_post = 0;
+        int rounds = 0;
+        auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const double t_begin = now();
         for (;;) {
             if (lo == hi) {
                 std::lock_guard<std::mutex> g(mu);
@@ -198,7 +205,13 @@ extern "C" int32_t b200poa_polisher_polish(b200poa_polisher* h, int64_t n_window
                 hi = std::min<int64_t>(n_windows, lo + want);
                 cursor = hi;
             }
-            if (lo == hi) return B200POA_SUCCESS;
+            if (lo == hi) {
+                if (timers)
+                    std::fprintf(stderr, "[b200poa e2e] proc %lld: %d rounds, stage %.1f ms, upload+kernel+download %.1f ms, trim/copy-out %.1f ms, total %.1f ms\n",
+                                 (long long)index, rounds, 1e3 * t_stage, 1e3 * t_gpu, 1e3 * t_post, 1e3 * (now() - t_begin));
+                return B200POA_SUCCESS;
+            }
+            const double t0 = now();
             b200poa_batch_reset(p->batch);
             int64_t first = lo, n_added = 0;
             seqs_added.resize(static_cast<size_t>(hi - lo));
@@ -207,11 +220,13 @@ extern "C" int32_t b200poa_polisher_polish(b200poa_polisher* h, int64_t n_window
                                                    begins, ends, &n_added, seqs_added.data());
             if (st != B200POA_SUCCESS) return st;
             if (n_added == 0) return B200POA_EXCEEDED_MAXIMUM_POAS; /* a single window larger than the batch */
+            const double t1 = now();
             st = b200poa_batch_generate(p->batch);
             if (st != B200POA_SUCCESS) return st;
             const uint8_t* c; const uint16_t* v; const int32_t* l; const int32_t* s; int32_t bstride;
             st = b200poa_batch_get_consensus(p->batch, &c, &v, &l, &s, &bstride);
             if (st != B200POA_SUCCESS) return st;
+            const double t2 = now();
             b200poa_batch_info info;
             b200poa_batch_get_info(p->batch, &info);
             for (int64_t i = 0; i < n_added; ++i) {
@@ -258,6 +273,10 @@ extern "C" int32_t b200poa_polisher_polish(b200poa_polisher* h, int64_t n_window
                 down_bytes += n_added * (3 * static_cast<int64_t>(bstride) + 8);
             }
             lo = first + n_added;
+            t_stage += t1 - t0;
+            t_gpu += t2 - t1;
+            t_post += now() - t2;
+            ++rounds;
         }
     };
     std::vector<int32_t> results(procs.size(), B200POA_SUCCESS);
