@@ -78,3 +78,30 @@ def partial_span_windows(n: int = 12, length: int = 400, depth: int = 14, seed: 
                 win.append((seqs[i], None, 0, L - 1))
         wins.append(win)
     return WindowBatch.from_lists(wins)
+
+
+def awkward_windows(m: int, x: int, g: int, n: int = 36) -> WindowBatch:
+    """Many small, awkward windows: short and long layers, partial spans, with and without qualities, deep and
+    shallow, up to 30 % error (used by the emulation and the GPU parity tests with several scoring schemes)."""
+    rng = np.random.default_rng(1000 + 7 * m - x - 13 * g)
+    wins = []
+    for _ in range(n):
+        L = int(rng.integers(30, 260))
+        D = int(rng.integers(2, 24))
+        err = float(rng.uniform(0.0, 0.3))
+        b = synth_windows(1, L, D, err, seed=int(rng.integers(1 << 30)), with_quality=bool(rng.integers(2)))
+        seqs, wts, _, _ = b.window(0)
+        Lb = len(seqs[0])
+        win = [(seqs[0], wts[0], 0, 0)]
+        for i in range(1, len(seqs)):
+            if rng.random() < 0.35 and Lb > 60:  # a layer covering part of the backbone only
+                lo, hi = sorted(rng.integers(0, Lb, size=2).tolist())
+                if hi - lo < 20:
+                    lo, hi = 5, Lb - 5
+                a, z = int(lo / Lb * len(seqs[i])), int(hi / Lb * len(seqs[i]))
+                if z - a >= 2:
+                    win.append((seqs[i][a:z], None if wts[i] is None else wts[i][a:z], lo, hi))
+                    continue
+            win.append((seqs[i], wts[i], 0, Lb - 1))
+        wins.append(win)
+    return WindowBatch.from_lists(wins)

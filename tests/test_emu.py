@@ -10,7 +10,7 @@ import pytest
 from common import G, M, X, identity_order, spoa_golden, spoa_window
 from emu_lib import Emu
 from racon_gpu_b200 import api
-from racon_gpu_b200.windows import edit_distance, synth_windows
+from racon_gpu_b200.windows import WindowBatch, edit_distance, synth_windows
 
 
 @pytest.fixture(scope="module")
@@ -100,3 +100,18 @@ def test_long_window_stress_with_a_larger_sequence_limit(emu, oracle):
     assert (st == 0).all() and ec == oc and all((a == c).all() for a, c in zip(ecov, ocov))
     bc, _, st, _ = emu.polish(b, order, M, X, G, band=256, max_len=1279, max_nodes=5116, max_edges=6 * 5116)
     assert (st == 0).all() and sum(a == c for a, c in zip(bc, oc)) >= 3
+
+
+@pytest.mark.parametrize("scoring", [(3, -5, -4), (5, -4, -8), (1, -1, -1), (2, -3, -2)])
+def test_randomized_small_windows_match_the_oracle(emu, oracle, scoring):
+    """Many small, awkward windows (short and long layers, partial spans, with and without qualities, deep and
+    shallow, high error) under several scoring schemes: consensus AND coverage equal the oracle, both sorts."""
+    from common import awkward_windows
+    m, x, g = scoring
+    b = awkward_windows(m, x, g)
+    order = api.processing_order(b)
+    oc, ocov, _ = oracle.polish(b, order, m, x, g, tgs=False, trim=False, threads=8)
+    for serial in (False, True):
+        ec, ecov, st, _ = emu.polish(b, order, m, x, g, band=0, serial_topsort=serial)
+        assert (st == 0).all() and ec == oc
+        assert all((a == c).all() for a, c in zip(ecov, ocov))

@@ -226,3 +226,17 @@ def test_long_window_stress_at_true_size(oracle):
     n, seqs_added = pb.add_windows(b)
     pb.close()
     assert n == 24 and (np.asarray(seqs_added) < 64).any()
+
+
+@pytest.mark.parametrize("scoring", [(3, -5, -4), (5, -4, -8), (1, -1, -1), (2, -3, -2)])
+def test_awkward_windows_under_several_scoring_schemes(oracle, scoring):
+    """Short and long layers, partial spans, qualities, up to 30 % error; full band: consensus and coverage are
+    the oracle's, whatever the (match, mismatch, gap) triple (racon -m/-x/-g)."""
+    from common import awkward_windows
+    m, x, g = scoring
+    b = awkward_windows(m, x, g)
+    order = api.processing_order(b)
+    oc, ocov, _ = oracle.polish(b, order, m, x, g, tgs=False, trim=False, threads=16)
+    gc, gcov, st = gpu_untrimmed(b, banded=False, match=m, mismatch=x, gap=g)
+    assert (st == 0).all() and gc == oc
+    assert all((a == c).all() for a, c in zip(gcov, ocov))
