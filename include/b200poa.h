@@ -199,6 +199,32 @@ int32_t b200poa_polisher_polish(b200poa_polisher* h, int64_t n_windows, const in
                                 int64_t* kernel_launches, int64_t* h2d_bytes, int64_t* d2h_bytes);
 void b200poa_polisher_destroy(b200poa_polisher* h);
 
+/* ---- columnar window construction ------------------------------------------------
+ * Replaces the per-window objects racon builds in Polisher::initialize (src/polisher.cpp:384-457 with
+ * createWindow / Window::add_layer, src/window.cpp:15-63) by ONE arena in the layout b200poa_polisher_polish
+ * consumes.  Same argument checks as the reference (which exits; here: -1 / INVALID_ARGUMENT), layers of
+ * different windows may arrive interleaved, layers of one window keep their add order.  Sequence and quality
+ * pointers are borrowed until b200poa_arena_finalize copies them (quality -> weight = char - 33,
+ * graph.cpp:138-147; nullptr quality -> weight 1, :124-129).  Host-only: no CUDA call is made. */
+typedef struct b200poa_arena b200poa_arena;
+b200poa_arena* b200poa_arena_create(void);
+int64_t b200poa_arena_add_window(b200poa_arena* a, const char* backbone, uint32_t backbone_length,
+                                 const char* quality, uint32_t quality_length); /* window index or -1 */
+int32_t b200poa_arena_add_layer(b200poa_arena* a, int64_t window, const char* sequence, uint32_t sequence_length,
+                                const char* quality, uint32_t quality_length, uint32_t begin, uint32_t end);
+int32_t b200poa_arena_finalize(b200poa_arena* a);
+/* after finalize: pointers stay valid until destroy */
+int32_t b200poa_arena_view(const b200poa_arena* a, int64_t* n_windows, int64_t* n_sequences,
+                           const int64_t** win_seq_off, const int64_t** seq_off, const uint8_t** bases,
+                           const int8_t** weights, const uint8_t** has_weights, const int32_t** begins,
+                           const int32_t** ends);
+/* b200poa_polisher_polish over a finalized arena (same outputs) */
+int32_t b200poa_polisher_polish_arena(b200poa_polisher* h, const b200poa_arena* a, int32_t tgs, int32_t trim,
+                                      int32_t max_windows_per_round, uint8_t* cons_out, int32_t stride,
+                                      int32_t* cons_len, uint8_t* polished, int32_t* status_out,
+                                      int64_t* kernel_launches, int64_t* h2d_bytes, int64_t* d2h_bytes);
+void b200poa_arena_destroy(b200poa_arena* a);
+
 /* The same job driven through the C++ class API that mirrors racon's (racon_b200::createWindow /
  * Window::add_layer / CUDABatchProcessor / polish_windows, racon_gpu_b200/csrc/host/): the path a
  * racon maintainer's code takes.  Same arguments as b200poa_polish_windows. */

@@ -39,6 +39,8 @@ ABI_SYMBOLS = (
     "b200poa_batch_reset", "b200poa_batch_destroy", "b200poa_batch_get_info",
     "b200poa_status_string", "b200poa_batch_phase_cycles", "b200poa_polish_windows", "b200poa_polish_windows_via_adapter",
     "b200poa_polisher_create", "b200poa_polisher_polish", "b200poa_polisher_destroy",
+    "b200poa_arena_create", "b200poa_arena_add_window", "b200poa_arena_add_layer", "b200poa_arena_finalize",
+    "b200poa_arena_view", "b200poa_polisher_polish_arena", "b200poa_arena_destroy",
 )
 
 
@@ -385,9 +387,90 @@ class Polisher:
         self.last = {"kernel_launches": int(launches.value), "h2d_bytes": int(h2d.value), "d2h_bytes": int(d2h.value)}
         return cons, clen, pol.astype(bool), status
 
+    def polish_arena(self, arena: "WindowArena", tgs: bool = True, trim: bool = True, max_windows_per_round: int = 0,
+                     stride: int = 2048):
+        """`polish` over windows built with WindowArena (b200poa_polisher_polish_arena)."""
+        W = arena.n_windows
+        cons, clen = np.zeros((W, stride), dtype=np.uint8), np.zeros(W, dtype=np.int32)
+        pol, status = np.zeros(W, dtype=np.uint8), np.zeros(W, dtype=np.int32)
+        launches, h2d, d2h = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        st = self.lib.b200poa_polisher_polish_arena(
+            self.handle, arena.handle, C.c_int32(int(tgs)), C.c_int32(int(trim)), C.c_int32(max_windows_per_round),
+            _p(cons, C.c_uint8), C.c_int32(stride), _p(clen, C.c_int32), _p(pol, C.c_uint8), _p(status, C.c_int32),
+            C.byref(launches), C.byref(h2d), C.byref(d2h))
+        if st != SUCCESS:
+            raise RuntimeError(f"b200poa_polisher_polish_arena failed: {status_string(st)}")
+        self.last = {"kernel_launches": int(launches.value), "h2d_bytes": int(h2d.value), "d2h_bytes": int(d2h.value)}
+        return cons, clen, pol.astype(bool), status
+
     def close(self):
         if getattr(self, "handle", None) and self.handle.value:
             self.lib.b200poa_polisher_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class WindowArena:
+    """Columnar window construction (b200poa_arena_*): racon's createWindow / Window::add_layer contract
+    (src/window.cpp:15-63) writing into the arena the engine consumes.  Host-only, needs no GPU.
+    Sequences are `bytes`; the object keeps them alive until `finalize` (the C side borrows the pointers)."""
+
+    def __init__(self):
+        self.lib = load_library()
+        self.lib.b200poa_arena_create.restype = C.c_void_p
+        self.lib.b200poa_arena_add_window.restype = C.c_int64
+        self.lib.b200poa_arena_destroy.restype = None
+        self.handle = C.c_void_p(self.lib.b200poa_arena_create())
+        self._keep = []
+        self.n_windows = 0
+
+    def add_window(self, backbone: bytes, quality: bytes) -> int:
+        self._keep += [backbone, quality]
+        w = int(self.lib.b200poa_arena_add_window(self.handle, C.c_char_p(backbone), C.c_uint32(len(backbone)),
+                                                  C.c_char_p(quality), C.c_uint32(len(quality) if quality is not None else 0)))
+        if w >= 0:
+            self.n_windows = w + 1
+        return w
+
+    def add_layer(self, window: int, sequence: bytes, quality, begin: int, end: int) -> bool:
+        self._keep += [sequence, quality]
+        st = self.lib.b200poa_arena_add_layer(self.handle, C.c_int64(window), C.c_char_p(sequence), C.c_uint32(len(sequence)),
+                                              C.c_char_p(quality) if quality is not None else None,
+                                              C.c_uint32(len(quality) if quality is not None else 0),
+                                              C.c_uint32(begin), C.c_uint32(end))
+        return st == SUCCESS
+
+    def finalize(self) -> WindowBatch:
+        """Group and copy; returns the arena as a WindowBatch (copies of the C arrays)."""
+        if self.lib.b200poa_arena_finalize(self.handle) != SUCCESS:
+            raise RuntimeError("b200poa_arena_finalize failed")
+        self._keep = []
+        nw, ns = C.c_int64(0), C.c_int64(0)
+        pw, ps = C.POINTER(C.c_int64)(), C.POINTER(C.c_int64)()
+        pb, pwt, ph = C.POINTER(C.c_uint8)(), C.POINTER(C.c_int8)(), C.POINTER(C.c_uint8)()
+        pbg, pen = C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)()
+        st = self.lib.b200poa_arena_view(self.handle, C.byref(nw), C.byref(ns), C.byref(pw), C.byref(ps), C.byref(pb),
+                                         C.byref(pwt), C.byref(ph), C.byref(pbg), C.byref(pen))
+        if st != SUCCESS:
+            raise RuntimeError("b200poa_arena_view failed")
+        W, S = int(nw.value), int(ns.value)
+
+        def arr(ptr, n, dt):
+            return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dt, copy=True) if n else np.zeros(0, dtype=dt)
+        seq_off = arr(ps, S + 1, np.int64)
+        B = int(seq_off[-1]) if S else 0
+        return WindowBatch(win_seq_off=arr(pw, W + 1, np.int64), seq_off=seq_off, bases=arr(pb, B, np.uint8),
+                           weights=arr(pwt, B, np.int8), has_weights=arr(ph, S, np.uint8),
+                           begins=arr(pbg, S, np.int32), ends=arr(pen, S, np.int32))
+
+    def close(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            self.lib.b200poa_arena_destroy(self.handle)
             self.handle = C.c_void_p()
 
     def __del__(self):

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <new>
 #include <stdexcept>
 #include <chrono>
 #include <cstdlib>
@@ -14,6 +15,7 @@
 
 #include "b200poa.h"
 #include "cuda_batch.hpp"
+#include "window_arena.hpp"
 
 namespace racon_b200 {
 
@@ -374,3 +376,64 @@ extern "C" int32_t b200poa_polish_windows_via_adapter(int64_t n_windows, const i
     }
     return B200POA_SUCCESS;
 }
+
+
+/* ---- columnar window construction: C ABI over racon_b200::WindowArena (window_arena.hpp) ---- */
+struct b200poa_arena {
+    racon_b200::WindowArena arena;
+};
+
+extern "C" b200poa_arena* b200poa_arena_create(void) { return new (std::nothrow) b200poa_arena(); }
+
+extern "C" int64_t b200poa_arena_add_window(b200poa_arena* a, const char* backbone, uint32_t backbone_length,
+                                            const char* quality, uint32_t quality_length) {
+    if (!a || !backbone || !quality) return -1; /* racon always gives the backbone a quality ('!' for FASTA targets) */
+    return a->arena.add_window(backbone, backbone_length, quality, quality_length);
+}
+
+extern "C" int32_t b200poa_arena_add_layer(b200poa_arena* a, int64_t window, const char* sequence,
+                                           uint32_t sequence_length, const char* quality, uint32_t quality_length,
+                                           uint32_t begin, uint32_t end) {
+    if (!a || (!sequence && sequence_length != 0)) return B200POA_INVALID_ARGUMENT;
+    return a->arena.add_layer(window, sequence, sequence_length, quality, quality_length, begin, end)
+               ? B200POA_SUCCESS
+               : B200POA_INVALID_ARGUMENT;
+}
+
+extern "C" int32_t b200poa_arena_finalize(b200poa_arena* a) {
+    if (!a) return B200POA_INVALID_ARGUMENT;
+    a->arena.finalize();
+    return B200POA_SUCCESS;
+}
+
+extern "C" int32_t b200poa_arena_view(const b200poa_arena* a, int64_t* n_windows, int64_t* n_sequences,
+                                      const int64_t** win_seq_off, const int64_t** seq_off, const uint8_t** bases,
+                                      const int8_t** weights, const uint8_t** has_weights, const int32_t** begins,
+                                      const int32_t** ends) {
+    if (!a || !a->arena.finalized()) return B200POA_INVALID_ARGUMENT;
+    const racon_b200::WindowArena& w = a->arena;
+    if (n_windows) *n_windows = w.n_windows();
+    if (n_sequences) *n_sequences = w.n_sequences();
+    if (win_seq_off) *win_seq_off = w.win_seq_off().data();
+    if (seq_off) *seq_off = w.seq_off().data();
+    if (bases) *bases = w.bases().data();
+    if (weights) *weights = w.weights().data();
+    if (has_weights) *has_weights = w.has_weights().data();
+    if (begins) *begins = w.begins().data();
+    if (ends) *ends = w.ends().data();
+    return B200POA_SUCCESS;
+}
+
+extern "C" int32_t b200poa_polisher_polish_arena(b200poa_polisher* h, const b200poa_arena* a, int32_t tgs, int32_t trim,
+                                                 int32_t max_windows_per_round, uint8_t* cons_out, int32_t stride,
+                                                 int32_t* cons_len, uint8_t* polished, int32_t* status_out,
+                                                 int64_t* kernel_launches, int64_t* h2d_bytes, int64_t* d2h_bytes) {
+    if (!a || !a->arena.finalized()) return B200POA_INVALID_ARGUMENT;
+    const racon_b200::WindowArena& w = a->arena;
+    return b200poa_polisher_polish(h, w.n_windows(), w.win_seq_off().data(), w.seq_off().data(), w.bases().data(),
+                                   w.weights().data(), w.has_weights().data(), w.begins().data(), w.ends().data(), tgs,
+                                   trim, max_windows_per_round, cons_out, stride, cons_len, polished, status_out,
+                                   kernel_launches, h2d_bytes, d2h_bytes);
+}
+
+extern "C" void b200poa_arena_destroy(b200poa_arena* a) { delete a; }

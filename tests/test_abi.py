@@ -63,3 +63,41 @@ def test_status_strings_and_invalid_arguments():
     st = lib.b200poa_batch_create(0, None, C.c_size_t(0), 1, C.byref(cfg), C.c_int16(-4), C.c_int16(-5), C.c_int16(3), C.byref(handle))
     assert st == 15 and not handle.value
     assert lib.b200poa_batch_total_poas(None) == 0
+
+
+def test_window_arena_follows_racons_window_contract():
+    """Columnar window construction (b200poa_arena_*): layers of different windows arrive
+    interleaved like in Polisher::initialize; per window they keep their add order; quality -> weight - 33;
+    the argument checks of src/window.cpp:15-28,42-63 reject what racon rejects."""
+    import numpy as np
+    from racon_gpu_b200.windows import WindowBatch, synth_windows
+    b = synth_windows(7, 120, 9, 0.1, seed=3, with_quality=True)
+    per_win = [b.window(w) for w in range(b.n_windows)]
+    arena = api.WindowArena()
+    def qual(w):  # weights back to a PHRED+33 string
+        return bytes((np.asarray(w, dtype=np.int16) + 33).astype(np.uint8))
+    ids = [arena.add_window(bytes(s[0]), qual(w[0])) for s, w, _, _ in per_win]
+    assert ids == list(range(7))
+    # interleave: layer i of every window, then layer i+1 ...; every third layer without quality
+    expect = [[(bytes(s[0]), np.asarray(w[0], dtype=np.int8), 0, 0)] for s, w, _, _ in per_win]
+    for i in range(1, 10):
+        for wid, (s, w, bg, en) in enumerate(per_win):
+            if i >= len(s):
+                continue
+            q = None if i % 3 == 0 else qual(w[i])
+            assert arena.add_layer(wid, bytes(s[i]), q, int(bg[i]), int(en[i]) + 1)
+            expect[wid].append((bytes(s[i]), None if q is None else np.asarray(w[i], dtype=np.int8), int(bg[i]), int(en[i]) + 1))
+    # what racon rejects or skips (window.cpp:44-58)
+    assert arena.add_layer(0, b"", None, 0, 5)                 # empty layer: skipped, not an error
+    assert arena.add_layer(0, b"ACGT", None, 7, 7)             # begin == end: skipped
+    assert not arena.add_layer(0, b"ACGT", b"!!", 0, 4)        # unequal quality size
+    assert not arena.add_layer(0, b"ACGT", None, 9, 3)         # begin >= end
+    assert not arena.add_layer(0, b"ACGT", None, 0, 100000)    # end beyond the backbone
+    assert not arena.add_layer(99, b"ACGT", None, 0, 4)        # no such window
+    assert arena.add_window(b"", b"") == -1 and arena.add_window(b"ACGT", b"!!") == -1
+    got = arena.finalize()
+    want = WindowBatch.from_lists(expect)
+    for f in ("win_seq_off", "seq_off", "bases", "weights", "has_weights", "begins", "ends"):
+        assert (getattr(got, f) == getattr(want, f)).all(), f
+    assert not arena.add_layer(0, b"ACGT", None, 0, 4)         # read-only after finalize
+    arena.close()

@@ -240,3 +240,26 @@ def test_awkward_windows_under_several_scoring_schemes(oracle, scoring):
     gc, gcov, st = gpu_untrimmed(b, banded=False, match=m, mismatch=x, gap=g)
     assert (st == 0).all() and gc == oc
     assert all((a == c).all() for a, c in zip(gcov, ocov))
+
+
+def test_windows_built_in_the_columnar_arena_polish_like_the_oracle(oracle):
+    """windows added through b200poa_arena_* (racon's createWindow/add_layer contract, layers of
+    different windows interleaved) and polished with b200poa_polisher_polish_arena."""
+    b = synth_windows(40, 300, 14, 0.12, seed=61, with_quality=True)
+    order = api.processing_order(b)
+    oc, _, _ = oracle.polish(b, order, M, X, G, tgs=True, trim=True, threads=16)
+    per_win = [b.window(w) for w in range(b.n_windows)]
+    qual = lambda w: bytes((np.asarray(w, dtype=np.int16) + 33).astype(np.uint8))
+    arena = api.WindowArena()
+    for s, w, _, _ in per_win:
+        assert arena.add_window(bytes(s[0]), qual(w[0])) >= 0
+    for i in range(1, 15):
+        for wid, (s, w, bg, en) in enumerate(per_win):
+            assert arena.add_layer(wid, bytes(s[i]), qual(w[i]), int(bg[i]), int(en[i]))
+    built = arena.finalize()
+    assert (built.bases == b.bases).all() and (built.weights == b.weights).all() and (built.begins == b.begins).all()
+    pol = api.Polisher(devices=[0], batches_per_device=2, mem_per_batch=MEM)
+    cons, clen, polished, status = pol.polish_arena(arena, tgs=True, trim=True, max_windows_per_round=16)
+    pol.close()
+    arena.close()
+    assert polished.all() and api.consensus_list(cons, clen) == oc
