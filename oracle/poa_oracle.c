@@ -725,3 +725,48 @@ void poa_oracle_polish_windows(int64_t n_windows, const int64_t* win_seq_off, co
     }
     pthread_mutex_destroy(&job.mu);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Edit distance of two long strings (the metric of racon's end-to-end goldens, test/racon_test.cpp:
+ * 16-25 uses edlib's global alignment distance): Ukkonen's band with a doubling threshold, O(n*k).
+ * Test helper for the stitched-contig checks.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t poa_oracle_edit_distance(const char* a, int64_t la, const char* b, int64_t lb) {
+    if (la < lb) {
+        const char* t = a; a = b; b = t;
+        int64_t tl = la; la = lb; lb = tl;
+    }
+    /* la >= lb; rows over a, columns over b */
+    for (int64_t k = 64;; k *= 2) {
+        if (k > la) k = la;
+        const int64_t W = 2 * k + 1, INF = 1 << 30;
+        int64_t* prev = (int64_t*)malloc(sizeof(int64_t) * (size_t)(W + 2));
+        int64_t* cur = (int64_t*)malloc(sizeof(int64_t) * (size_t)(W + 2));
+        /* cell (i, j) lives at index j - i + k + 1, diagonals -k..k around the main diagonal shifted by 0 */
+        for (int64_t d = 0; d < W + 2; ++d) prev[d] = INF;
+        for (int64_t j = 0; j <= lb && j <= k; ++j) prev[j + k + 1] = j;
+        for (int64_t i = 1; i <= la; ++i) {
+            for (int64_t d = 0; d < W + 2; ++d) cur[d] = INF;
+            int64_t jlo = i - k < 0 ? 0 : i - k, jhi = i + k > lb ? lb : i + k;
+            for (int64_t j = jlo; j <= jhi; ++j) {
+                const int64_t d = j - i + k + 1;
+                int64_t v = INF;
+                if (j == 0) v = i;
+                else {
+                    const int64_t sub = prev[d] + (a[i - 1] != b[j - 1]);  /* (i-1, j-1): same diagonal */
+                    const int64_t del = prev[d + 1] + 1;                     /* (i-1, j) */
+                    const int64_t ins = cur[d - 1] + 1;                      /* (i, j-1) */
+                    v = sub < del ? sub : del;
+                    if (ins < v) v = ins;
+                }
+                cur[d] = v;
+            }
+            int64_t* t = prev; prev = cur; cur = t;
+        }
+        int64_t res = INF;
+        if (lb - la + k + 1 >= 1 && lb - la + k + 1 <= W) res = prev[lb - la + k + 1];
+        free(prev);
+        free(cur);
+        if (res <= k || k >= la) return res;
+    }
+}

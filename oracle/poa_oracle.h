@@ -88,6 +88,10 @@ void poa_oracle_polish_windows(int64_t n_windows, const int64_t* win_seq_off, co
                                uint16_t* cov_out, int32_t stride, int32_t* cons_len,
                                uint8_t* polished, int64_t* stats);
 
+/* Global edit distance of two long strings (banded, doubling threshold); test helper for the stitched-contig
+ * goldens of test/racon_test.cpp:88-130,176-196. */
+int64_t poa_oracle_edit_distance(const char* a, int64_t la, const char* b, int64_t lb);
+
 #ifdef __cplusplus
 }
 #endif

@@ -105,3 +105,90 @@ def awkward_windows(m: int, x: int, g: int, n: int = 36) -> WindowBatch:
             win.append((seqs[i], wts[i], 0, Lb - 1))
         wins.append(win)
     return WindowBatch.from_lists(wins)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Real racon windows (tests/golden/make_lambda_golden.py): the lambda-phage sample of the reference's own
+# end-to-end tests and the 67 deep cudapoa sample windows.
+# ---------------------------------------------------------------------------------------------------
+_ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+_COMP = np.zeros(256, dtype=np.uint8)
+for _a, _b in zip(b"ACGTN", b"TGCAN"):
+    _COMP[_a] = _b
+
+
+def _unpack2(packed: np.ndarray, n: int) -> np.ndarray:
+    c = np.stack([packed & 3, (packed >> 2) & 3, (packed >> 4) & 3, (packed >> 6) & 3], axis=1).reshape(-1)[:n]
+    return _ACGT[c]
+
+
+def _batch_from_columns(bases, seq_len, win_nseq, qual=None, has_q=None, begin=None, end=None) -> WindowBatch:
+    S = seq_len.shape[0]
+    seq_off = np.zeros(S + 1, dtype=np.int64)
+    np.cumsum(seq_len, out=seq_off[1:])
+    win_seq_off = np.zeros(win_nseq.shape[0] + 1, dtype=np.int64)
+    np.cumsum(win_nseq, out=win_seq_off[1:])
+    weights = np.ones(bases.shape[0], dtype=np.int8)
+    if has_q is None:
+        has_q = np.zeros(S, dtype=np.uint8)
+    if qual is not None and qual.shape[0]:
+        mask = np.repeat(has_q.astype(bool), seq_len)
+        weights[mask] = (qual.astype(np.int16) - 33).astype(np.int8)
+    if begin is None:  # all layers span the window (cudapoa sample windows carry no positions)
+        bb_len = np.repeat(seq_len[win_seq_off[:-1]], win_nseq)
+        begin = np.zeros(S, dtype=np.int32)
+        end = (bb_len - 1).astype(np.int32)
+        end[win_seq_off[:-1]] = 0
+    return WindowBatch(win_seq_off=win_seq_off, seq_off=seq_off, bases=np.ascontiguousarray(bases), weights=weights,
+                       has_weights=np.ascontiguousarray(has_q, dtype=np.uint8),
+                       begins=np.ascontiguousarray(begin, dtype=np.int32), ends=np.ascontiguousarray(end, dtype=np.int32))
+
+
+def _split(flat: np.ndarray, lens: np.ndarray):
+    off = np.concatenate([[0], np.cumsum(lens)])
+    return [flat[off[i]:off[i + 1]].tobytes() for i in range(lens.shape[0])]
+
+
+def lambda_fixture(case: str):
+    """Real racon windows of the lambda-phage sample.  case in {fastq_500, fasta_500, fastq_1000}.
+    Returns (WindowBatch in ADD order, racon CPU consensus per window, racon CPU status per window, params dict)."""
+    z = np.load(os.path.join(GOLDEN, "lambda_windows.npz"))
+    g = lambda k: z[f"{case}_{k}"]
+    seq_len = g("seq_len")
+    bases = _unpack2(g("bases"), int(seq_len.sum()))
+    b = _batch_from_columns(bases, seq_len, g("win_nseq"), g("qual"), g("has_q"), g("begin"), g("end"))
+    wl, tgs, trim, m, x, gap, ed, clen = [int(v) for v in g("params")]
+    params = {"window_length": wl, "tgs": bool(tgs), "trim": bool(trim), "m": m, "x": x, "g": gap,
+              "edit_distance": ed, "contig_length": clen}
+    return b, _split(g("cons"), g("cons_len")), g("polished").astype(bool), params
+
+
+def lambda_reference() -> bytes:
+    z = np.load(os.path.join(GOLDEN, "lambda_windows.npz"))
+    return _unpack2(z["reference"], int(z["reference_len"][0])).tobytes()
+
+
+def reverse_complement(s: bytes) -> bytes:
+    return _COMP[np.frombuffer(s, dtype=np.uint8)][::-1].tobytes()
+
+
+def contig_edit_distance(oracle, window_consensus, reference: bytes) -> int:
+    """test/racon_test.cpp:98-107: edit distance of the reverse complement of the stitched contig to the reference."""
+    import ctypes as C
+    q = reverse_complement(b"".join(window_consensus))
+    fn = oracle.lib.poa_oracle_edit_distance
+    fn.restype = C.c_int64
+    return int(fn(C.c_char_p(q), C.c_int64(len(q)), C.c_char_p(reference), C.c_int64(len(reference))))
+
+
+def cudapoa_fixture():
+    """The 67 deep windows of cudapoa's sample-windows.txt (file order = processing order, weight 1, full span).
+    Returns (WindowBatch, reference consensus list, reference coverage list)."""
+    z = np.load(os.path.join(GOLDEN, "cudapoa_windows.npz"))
+    seq_len = z["seq_len"]
+    bases = _unpack2(z["bases"], int(seq_len.sum()))
+    b = _batch_from_columns(bases, seq_len, z["win_nseq"])
+    cons = _split(z["cons"], z["cons_len"])
+    off = np.concatenate([[0], np.cumsum(z["cons_len"])])
+    cov = [z["cov"][off[i]:off[i + 1]] for i in range(len(cons))]
+    return b, cons, cov
