@@ -4,21 +4,24 @@
     python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
     python bench.py --impl reference --gpus N --steps K --warmup W
 
-Workload (config.workload): BASELINE.json configs[1] -- "single B200: 10k windows, 500 bp x 32 reads,
-15% ONT error, banded width 256" -- synthetic windows (racon_gpu_b200/windows.py), per
-GPU (weak scaling).  One step = one pass of the hot path over the whole batch of windows.
+Headline workload (config.workload): BASELINE.json configs[1] -- "single B200: 10k windows, 500 bp x 32 reads,
+15% ONT error, banded width 256" -- synthetic windows (racon_gpu_b200/windows.py), per GPU (weak
+scaling).  One step = one pass of the hot path over the whole batch of windows.
 
   value      windows/s, whole job, inputs ALREADY RESIDENT IN HBM: K back-to-back launches of the POA
              kernel timed with CUDA events on the launching stream, max over ranks.
   e2e        the same metric through the public host API (api.Polisher.polish == racon's GPU window
              scheduler) with HOST buffers: pinned staging + H2D + kernel + D2H + coverage trim every
-             step (+ the NCCL gather of the consensus to rank 0 when N > 1).
-  roofline   the DP-fill kernel against the measured HBM peak: algorithmic bytes = DP cells of the
-             256-column band x 2 B x 2 (one write + one read), SURVEY.md 8(d) / BASELINE.md 4.
+             step (+ the NCCL gather of the consensus to rank 0 when N > 1, overlapped with the next step).
+  roofline   the DP-fill kernel against the measured HBM peak: algorithmic bytes = DP cells
+             x 2 B x 2 (one write + one read), SURVEY.md 8(d) / BASELINE.md 4.
   cpu_baseline  the reference's own CPU path (oracle/_ref: racon::Window + spoa AVX2) timed on this
              box's host cores over a bounded sample of the same windows (rank 0, N=1).
+  extra      (N=1 only, outside the headline timing) the same measurements for BASELINE configs[2]
+             (A_full: full band, the bit-exact mode) and configs[4]'s shape (B_banded: 1024 bp x 64 reads, 12 %,
+             band 256, max_sequence_size 1279).
 
-`--impl reference` times that CPU path as the job itself (all host threads, bounded sample per step).
+`--impl reference` times that CPU path as the job itself (all usable host threads, bounded sample per step).
 """
 from __future__ import annotations
 
@@ -38,11 +41,33 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 M, X, G = 3, -5, -4
 WORKLOADS = {
-    # name: (windows per GPU, backbone length, reads per window, error rate, banded)
-    "A_banded": (10000, 500, 32, 0.15, True),   # BASELINE configs[1]  (headline)
-    "A_full": (10000, 500, 32, 0.15, False),    # BASELINE configs[2]
-    "C_small": (100, 500, 8, 0.05, False),      # BASELINE configs[0] shape
+    # name: (windows per GPU, backbone length, reads per window, error rate, banded, max_sequence_size, BASELINE.json configs[i])
+    "A_banded": (10000, 500, 32, 0.15, True, 1023, 1),   # headline
+    "A_full": (10000, 500, 32, 0.15, False, 1023, 2),
+    "B_banded": (4096, 1024, 64, 0.12, True, 1279, 4),   # long-window stress shape
+    "C_small": (100, 500, 8, 0.05, False, 1023, 0),
 }
+
+
+def usable_cores():
+    """Host cores this process can actually run on: scheduler affinity AND the cgroup CPU quota (a 1-GPU lease of
+    a 128-thread host is a cgroup slice; os.cpu_count() reports the whole host)."""
+    aff = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota = None
+    try:  # cgroup v2
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            quota = float(q) / float(p)
+    except (OSError, ValueError):
+        try:  # cgroup v1
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / p
+        except (OSError, ValueError):
+            pass
+    eff = aff if quota is None else max(1, min(aff, int(quota + 0.5)))
+    return eff, {"os_cpu_count": os.cpu_count(), "sched_affinity": aff, "cgroup_quota": quota}
 
 
 class ClockSampler:
@@ -87,22 +112,23 @@ def measured_hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def recorded_traffic(workload: str):
-    """dram bytes per launch from the committed `ncu --set full` capture, if one matches."""
+def recorded_traffic(workload: str, nwin: int):
+    """DRAM bytes per launch of `nwin` windows, scaled from the committed `ncu --set full` capture of this workload
+    (profiles/traffic.json).  A constant from a profile, not a per-run measurement: see traffic_source."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(path):
         rec = json.load(open(path))
-        if workload in rec:
+        if workload in rec and isinstance(rec[workload], dict):
             r = rec[workload]
-            return float(r["dram_bytes_per_launch"]) if isinstance(r, dict) else float(r)
-    return None
+            return float(r["dram_bytes_per_launch"]) * nwin / float(r["windows_per_launch"]), r.get("source")
+    return None, None
 
 
-def cpu_reference_rate(batch, L, seconds_target, threads):
+def cpu_reference_rate(batch, L, seconds_target, threads, core_info):
     """Times the reference's CPU path on a bounded sample; returns the cpu_baseline dict."""
-    from oracle_lib import Oracle, Ref, processing_order
+    from oracle_lib import Oracle, Ref
     ref = Ref()
-    est = 40.0 * threads  # windows/s guess for config A (SURVEY.md 6: ~50 windows/s/thread)
+    est = 40.0 * threads * (500.0 / L) ** 2  # windows/s guess (SURVEY.md 6: ~50 windows/s/thread on config A)
     n = int(max(threads * 2, min(batch.n_windows, seconds_target * est)))
     sample = batch.slice(0, n)
     t0 = time.perf_counter()
@@ -114,9 +140,9 @@ def cpu_reference_rate(batch, L, seconds_target, threads):
         Oracle().polish(sample, api.processing_order(sample), M, X, G, tgs=True, trim=True, threads=threads)
         kind = "port"
     dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "windows/s", "cores": threads, "kind": kind,
+    return {"value": n / dt, "unit": "windows/s", "cores": threads, "kind": kind, "host": core_info,
             "sample": f"first {n} windows of the workload, {dt:.1f} s, racon::Window::generate_consensus + spoa "
-                      f"(kNW {M}/{X}/{G}), one engine per thread"}
+                      f"(kNW {M}/{X}/{G}, unbanded), one engine per thread, {threads} threads = usable cores"}
 
 
 def algorithmic_bytes_per_window(batch, banded, sample=48):
@@ -125,9 +151,16 @@ def algorithmic_bytes_per_window(batch, banded, sample=48):
     from racon_gpu_b200 import api
     sub = batch.slice(0, min(sample, batch.n_windows))
     _, _, _, st = Oracle().polish(sub, api.processing_order(sub), M, X, G, tgs=False, trim=False,
-                                  threads=min(16, os.cpu_count() or 1), want_stats=True)
+                                  threads=min(16, usable_cores()[0]), want_stats=True)
     cells = st[:, 4].mean() if banded else st[:, 2].mean()
     return float(cells) * 4.0, float(cells)
+
+
+def workload_label(name, nwin):
+    _, L, D, err, banded, max_seq, cfg = WORKLOADS[name]
+    return (f"{name}: {nwin} windows per GPU, {L} bp x {D} reads, {err:.0%} error, "
+            f"{'static band 256' if banded else 'full band'}, m{M}/x{X}/g{G}, max_sequence_size {max_seq} "
+            f"(BASELINE.json configs[{cfg}]{' shape' if name == 'B_banded' else ''})")
 
 
 def run_reference(args, rank, world):
@@ -135,12 +168,13 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from racon_gpu_b200.windows import synth_windows
-    nwin, L, D, err, banded = WORKLOADS[args.workload]
-    threads = os.cpu_count() or 1
-    per_step = int(max(threads * 2, min(nwin, 8.0 * 40.0 * threads)))  # ~8 s of CPU work per step
+    nwin, L, D, err, banded, _, _ = WORKLOADS[args.workload]
+    threads, core_info = usable_cores()
+    per_step = int(max(threads * 2, min(nwin, 6.0 * 40.0 * threads * (500.0 / L) ** 2)))  # ~6 s of CPU work per step
     batch = synth_windows(per_step, L, D, err, seed=args.seed)
-    from oracle_lib import Ref, Oracle
+    from oracle_lib import Oracle, Ref
     ref = Ref()
+
     def step():
         if ref.available:
             ref.polish(batch, M, X, G, tgs=True, trim=True, threads=threads, window_length=L)
@@ -160,12 +194,110 @@ def run_reference(args, rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {L} bp x {D} reads, {err:.0%} error, m{M}/x{X}/g{G}; CPU path is unbanded "
                                f"(spoa has no band); bounded sample of {per_step} windows per step"},
-        "cpu_baseline": {"value": value, "unit": "windows/s", "cores": threads,
+        "cpu_baseline": {"value": value, "unit": "windows/s", "cores": threads, "host": core_info,
                          "kind": "reference" if ref.available else "port",
-                         "sample": f"{per_step} windows per step x {args.steps} steps"},
+                         "sample": f"{per_step} windows per step x {args.steps} steps, {threads} threads = usable cores"},
         "e2e": {"value": value, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+def measure(name, args, rank, world, local_rank, device, steps, warmup, nwin=None, sample_clocks=True):
+    """Kernel-only and end-to-end legs of one workload on this rank.  Returns a dict of per-rank raw numbers."""
+    import torch
+    import torch.distributed as dist
+    from racon_gpu_b200 import api
+    from racon_gpu_b200.shard import ConsensusGather
+    from racon_gpu_b200.windows import synth_windows
+
+    nwin0, L, D, err, banded, max_seq, _ = WORKLOADS[name]
+    nwin = nwin or nwin0
+    batch = synth_windows(nwin, L, D, err, seed=args.seed + 1000003 * rank)  # each rank its own windows
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    free_b, _ = torch.cuda.mem_get_info()
+    mem = int(min(0.6 * free_b, 64 << 30))
+
+    # ---------------- value: kernel with inputs resident in HBM -------------------------------------
+    stream = torch.cuda.Stream(device=device)
+    pb = api.PoaBatch(device=local_rank, stream=stream.cuda_stream, max_gpu_mem=mem, banded=banded,
+                      gap=G, mismatch=X, match=M, max_sequence_size=max_seq)
+    n_added, _ = pb.add_windows(batch)
+    if n_added != nwin:
+        raise SystemExit(f"bench.py: batch accepted {n_added}/{nwin} windows; raise the memory budget")
+    pb.upload()
+    info = pb.info()
+    sampler = ClockSampler(local_rank)
+    if sample_clocks:
+        sampler.start()  # started before the warm-up: nvidia-smi needs ~1 s to deliver its first sample
+    with torch.cuda.stream(stream):
+        for _ in range(warmup):
+            pb.launch()
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        t0 = time.perf_counter()
+        for a, b in ev:
+            a.record(stream)
+            pb.launch()
+            b.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop() if sample_clocks else None
+    dev_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    pb.download()
+    _, _, status_k = pb.get_consensus()
+    n_fail = int((status_k != 0).sum())
+    pb.close()
+
+    # ---------------- e2e: host buffers through the public API -------------------------------------
+    pol = api.Polisher(devices=[local_rank], batches_per_device=args.batches, mem_per_batch=mem // args.batches,
+                       banded=banded, match=M, mismatch=X, gap=G, max_sequence_size=max_seq)
+    chunk = max(256, int(-(-nwin // (args.batches * args.rounds))))  # windows per launch of a batch processor
+    stride = 2 * max_seq + 2
+    bufs = [None, None]  # double-buffered outputs: step k's gather overlaps step k+1's polish
+    gather = ConsensusGather(device, nwin) if world > 1 else None
+    for k in range(warmup):
+        out_t = pol.polish(batch, tgs=True, trim=True, max_windows_per_round=chunk, stride=stride, out=bufs[k % 2])
+        bufs[k % 2] = (out_t[0], out_t[1], out_t[2].astype(np.uint8), out_t[3])
+        if gather:
+            gather.start(out_t[0], out_t[1])
+            gather.wait()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_launches = 0
+    for k in range(steps):
+        cons, clen, polished, status = pol.polish(batch, tgs=True, trim=True, max_windows_per_round=chunk, stride=stride,
+                                                  out=bufs[k % 2])
+        e2e_launches += pol.last["kernel_launches"]
+        if gather:
+            gather.wait()           # the previous step's consensus is on rank 0 (pinned host memory) ...
+            gather.start(cons, clen)  # ... this step's travels while the next one is computed
+    if gather:
+        gather.wait()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d, d2h = pol.last["h2d_bytes"], pol.last["d2h_bytes"]
+    n_unpolished = int((~polished).sum())
+    pol.close()
+    return {"batch": batch, "nwin": nwin, "L": L, "banded": banded, "info": info, "dev_ms": dev_ms, "e2e_s": e2e_s,
+            "wall": wall, "failures": n_fail + n_unpolished, "h2d": h2d, "d2h": d2h, "clocks": clocks,
+            "launches": steps + warmup + e2e_launches, "timed_launches": steps + e2e_launches}
+
+
+def roofline_block(name, m, steps):
+    bytes_per_window, cells = algorithmic_bytes_per_window(m["batch"], m["banded"])
+    peak, peak_src = measured_hbm_peak()
+    launch_s = (m["dev_ms"] / 1e3) / steps
+    achieved = bytes_per_window * m["nwin"] / launch_s / 1e9
+    traffic, tsrc = recorded_traffic(name, m["nwin"])
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "traffic_source": tsrc or "none (no ncu --set full capture committed for this workload)",
+            "kernel": "poa_window_kernel", "algorithmic_bytes_per_window": bytes_per_window,
+            "dp_cells_per_window": cells, "launch_ms": launch_s * 1e3, "peak_source": peak_src}
 
 
 def main():
@@ -180,6 +312,7 @@ def main():
     ap.add_argument("--batches", type=int, default=4, help="batch processors per GPU for the e2e leg (racon -c)")
     ap.add_argument("--rounds", type=float, default=1.0, help="e2e leg: launches per batch processor per step (chunk = windows / (batches x rounds))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the A_full / B_banded block (N=1 only anyway)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -192,9 +325,6 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from racon_gpu_b200 import api
-    from racon_gpu_b200.shard import gather_consensus
-    from racon_gpu_b200.windows import synth_windows
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device visible (the engine has no CPU fallback)")
@@ -204,76 +334,11 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     warmup = max(args.warmup, 3)
 
-    nwin, L, D, err, banded = WORKLOADS[args.workload]
-    if args.windows:
-        nwin = args.windows
-    batch = synth_windows(nwin, L, D, err, seed=args.seed + 1000003 * rank)  # each rank its own windows
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    free_b, _ = torch.cuda.mem_get_info()
-    mem = int(min(0.6 * free_b, 64 << 30))
-
-    # ---------------- value: kernel with inputs resident in HBM -------------------------------------
-    stream = torch.cuda.Stream(device=device)
-    pb = api.PoaBatch(device=local_rank, stream=stream.cuda_stream, max_gpu_mem=mem, banded=banded,
-                      gap=G, mismatch=X, match=M)
-    n_added, _ = pb.add_windows(batch)
-    if n_added != nwin:
-        raise SystemExit(f"bench.py: batch accepted {n_added}/{nwin} windows; raise the memory budget")
-    pb.upload()
-    info = pb.info()
-    sampler = ClockSampler(local_rank)
-    sampler.start()  # started before the warm-up: nvidia-smi needs ~1 s to deliver its first sample
-    with torch.cuda.stream(stream):
-        for _ in range(warmup):
-            pb.launch()
-        barrier()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        t0 = time.perf_counter()
-        for a, b in ev:
-            a.record(stream)
-            pb.launch()
-            b.record(stream)
-        barrier()
-        wall = time.perf_counter() - t0
-        clocks = sampler.stop()
-    kernel_ms = [a.elapsed_time(b) for a, b in ev]
-    dev_ms = float(sum(kernel_ms))
-    pb.download()
-    cons_k, _, status_k = pb.get_consensus()
-    n_fail = int((status_k != 0).sum())
-    pb.close()
-
-    # ---------------- e2e: host buffers through the public API -------------------------------------
-    pol = api.Polisher(devices=[local_rank], batches_per_device=args.batches, mem_per_batch=mem // args.batches,
-                       banded=banded, match=M, mismatch=X, gap=G)
-    chunk = max(256, int(-(-nwin // (args.batches * args.rounds))))  # windows per launch of a batch processor
-    out = None
-    for _ in range(warmup):
-        out_t = pol.polish(batch, tgs=True, trim=True, max_windows_per_round=chunk)
-        out = (out_t[0], out_t[1], out_t[2].astype(np.uint8), out_t[3])
-        if world > 1:
-            gather_consensus(out_t[0], out_t[1], device)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_launches = 0
-    for _ in range(args.steps):
-        cons, clen, polished, status = pol.polish(batch, tgs=True, trim=True, max_windows_per_round=chunk, out=out)
-        e2e_launches += pol.last["kernel_launches"]
-        if world > 1:
-            gather_consensus(cons, clen, device)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    h2d, d2h = pol.last["h2d_bytes"], pol.last["d2h_bytes"]
-    n_unpolished = int((~polished).sum())
-    pol.close()
+    m = measure(args.workload, args, rank, world, local_rank, device, args.steps, warmup, nwin=args.windows or None)
 
     # ---------------- reduce over ranks ---------------------------------------------------------------
-    t = torch.tensor([dev_ms, e2e_s, wall, float(n_fail + n_unpolished)], dtype=torch.float64, device=device)
+    dev_ms, e2e_s, wall, failures = m["dev_ms"], m["e2e_s"], m["wall"], m["failures"]
+    t = torch.tensor([dev_ms, e2e_s, wall, float(failures)], dtype=torch.float64, device=device)
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -281,43 +346,46 @@ def main():
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         dev_ms, e2e_s, wall = float(tmax[0]), float(tmax[1]), float(tmax[2])
         failures = int(tsum[3])
-    else:
-        failures = n_fail + n_unpolished
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
+    nwin, info = m["nwin"], m["info"]
     total_windows = nwin * world
-    value = total_windows * args.steps / (dev_ms / 1e3)
-    e2e_value = total_windows * args.steps / e2e_s
-    bytes_per_window, cells = algorithmic_bytes_per_window(batch, banded)
-    peak, peak_src = measured_hbm_peak()
-    launch_s = (dev_ms / 1e3) / args.steps
-    achieved = bytes_per_window * nwin / launch_s / 1e9
+    m["dev_ms"] = dev_ms
     result = {
-        "metric": "POA windows/sec", "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps,
-        "warmup": warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {nwin} windows per GPU, {L} bp x {D} reads, {err:.0%} error, "
-                               f"{'static band 256' if banded else 'full band'}, m{M}/x{X}/g{G} (BASELINE.json configs[1])",
-                   "windows_per_gpu": nwin, "l2": f"inputs larger than L2: {info['n_slots']} resident window workspaces x "
-                                                  f"{info['slot_bytes'] / 1048576:.1f} MB are rewritten every step",
+        "metric": "POA windows/sec", "value": total_windows * args.steps / (dev_ms / 1e3), "unit": "windows/s",
+        "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+        "config": {"workload": workload_label(args.workload, nwin), "windows_per_gpu": nwin,
+                   "l2": f"inputs larger than L2: {info['n_slots']} resident window workspaces x "
+                         f"{info['slot_bytes'] / 1048576:.1f} MB are rewritten every step",
                    "resident_warps": info["n_slots"], "blocks_per_sm": info["blocks_per_sm"],
                    "e2e_batches_per_gpu": args.batches, "failed_windows": failures},
-        "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        "e2e": {"value": total_windows * args.steps / e2e_s, "unit": "windows/s", "h2d_bytes_per_step": m["h2d"],
+                "d2h_bytes_per_step": m["d2h"],
                 "api": "api.Polisher.polish (b200poa_polisher_polish): staging + H2D + kernel + D2H + trim"
-                       + (" + NCCL gather" if world > 1 else "")},
-        "gpu_launches": args.steps + e2e_launches,
-        "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": recorded_traffic(args.workload), "kernel": "poa_window_kernel",
-                     "algorithmic_bytes_per_window": bytes_per_window, "dp_cells_per_window": cells,
-                     "launch_ms": launch_s * 1e3, "peak_source": peak_src},
+                       + (" + NCCL gather of the compact consensus to rank 0, overlapped with the next step" if world > 1 else "")},
+        "gpu_launches": m["timed_launches"],
+        "clocks": m["clocks"],
+        "roofline": roofline_block(args.workload, m, args.steps),
         "wall_s_timed_region": wall,
     }
     if world == 1 and not args.no_cpu_baseline:
-        result["cpu_baseline"] = cpu_reference_rate(batch, L, 15.0, os.cpu_count() or 1)
+        threads, core_info = usable_cores()
+        result["cpu_baseline"] = cpu_reference_rate(m["batch"], m["L"], 12.0, threads, core_info)
+    if world == 1 and not args.no_extra and args.workload == "A_banded" and not args.windows:
+        extra = {}
+        for name in ("A_full", "B_banded"):
+            x = measure(name, args, rank, world, local_rank, device, 3, 3, sample_clocks=False)
+            extra[name] = {
+                "workload": workload_label(name, x["nwin"]), "steps": 3, "warmup": 3,
+                "value": x["nwin"] * 3 / (x["dev_ms"] / 1e3), "e2e": x["nwin"] * 3 / x["e2e_s"], "unit": "windows/s",
+                "ms_per_step": x["dev_ms"] / 3, "failed_windows": x["failures"],
+                "h2d_bytes_per_step": x["h2d"], "d2h_bytes_per_step": x["d2h"],
+                "resident_warps": x["info"]["n_slots"], "roofline": roofline_block(name, x, 3)}
+        result["extra"] = extra
     print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()

@@ -132,12 +132,24 @@ int32_t b200poa_batch_launch(b200poa_batch* b);
 int32_t b200poa_batch_download(b200poa_batch* b);
 
 /*
- * Synchronises the stream.  Row i of cons/cov (row stride *stride elements) holds window i's
- * UNTRIMMED consensus and per-base coverage, lens[i] its length, status[i] its StatusType.
- * Pointers are into batch-owned pinned host memory, valid until reset/destroy.
+ * Synchronises the stream and completes the download.  Window i's UNTRIMMED consensus is the lens[i] bytes at
+ * cons + offsets[i], its per-base coverage the lens[i] values at cov + offsets[i] (compact arenas: exactly
+ * sum(lens) elements crossed PCIe), status[i] its StatusType.  trim[i] packs the span racon's TGS coverage trim
+ * keeps (src/window.cpp:118-139, threshold (n_seqs - 1) / 2), evaluated on the device: first = trim & 0xFFFF,
+ * last = trim >> 16 (arithmetic; first >= last means "keep the whole consensus", window.cpp:134-137).
+ * Pointers are into batch-owned pinned host memory, valid until reset/destroy.  *cov is NULL when the batch was
+ * told not to download coverage (B200POA_OPT_DOWNLOAD_COVERAGE = 0).
  */
 int32_t b200poa_batch_get_consensus(b200poa_batch* b, const uint8_t** cons, const uint16_t** cov,
-                                    const int32_t** lens, const int32_t** status, int32_t* stride);
+                                    const int32_t** lens, const int32_t** status, const int32_t** offsets,
+                                    const int32_t** trim);
+
+/* Batch options (extensions).  DOWNLOAD_COVERAGE (default 1): 0 = callers that only need the trimmed consensus skip
+ * two thirds of the D2H bytes.  TRIM_COUNTS_STAGED (default 0, set before adding windows): 1 = the trim threshold
+ * counts the sequences actually staged, which is what the reference GPU adapter does when it truncates a deep
+ * window (src/cuda/cudabatch.cpp:134-153, 232-233); 0 = every sequence of the window like the CPU path. */
+enum { B200POA_OPT_DOWNLOAD_COVERAGE = 1, B200POA_OPT_TRIM_COUNTS_STAGED = 2 };
+int32_t b200poa_batch_set_option(b200poa_batch* b, int32_t option, int64_t value);
 
 int32_t b200poa_batch_id(const b200poa_batch* b);
 int32_t b200poa_batch_reset(b200poa_batch* b);
@@ -154,6 +166,8 @@ typedef struct b200poa_batch_info {
     int64_t kernel_launches;  /* kernels launched since creation */
     int32_t smem_bytes;       /* dynamic shared memory per block */
     int32_t blocks_per_sm;    /* occupancy the launch was sized for */
+    int64_t h2d_bytes;        /* bytes the last upload moved host -> device */
+    int64_t d2h_bytes;        /* bytes the last download + get_consensus moved device -> host */
 } b200poa_batch_info;
 int32_t b200poa_batch_get_info(const b200poa_batch* b, b200poa_batch_info* info);
 
@@ -171,8 +185,9 @@ const char* b200poa_status_string(int32_t status);
  *   device_ids NULL / n_devices 0 => every visible device.
  *   mem_per_batch 0 => 0.9 * free / batches_per_device (cudapolisher.cpp:233-236).
  *   cons_out: n_windows rows of `stride` bytes; cons_len[w] the (trimmed) length; polished[w] is
- *   racon's per-window bool (false => the caller's CPU path must polish it: < 3 sequences,
- *   or status_out[w] != success).
+ *   racon's per-window bool.  false => the row holds the window's BACKBONE (window.cpp:68-71 for < 3
+ *   sequences; also when status_out[w] != success or layers were dropped by the batch limits) and the
+ *   caller's CPU path may still polish it, as racon does for the reference's failures (cudapolisher.cpp:354-383).
  */
 int32_t b200poa_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int64_t* seq_off,
                                const uint8_t* bases, const int8_t* weights, const uint8_t* has_weights,
@@ -198,6 +213,32 @@ int32_t b200poa_polisher_polish(b200poa_polisher* h, int64_t n_windows, const in
                                 int32_t stride, int32_t* cons_len, uint8_t* polished, int32_t* status_out,
                                 int64_t* kernel_launches, int64_t* h2d_bytes, int64_t* d2h_bytes);
 void b200poa_polisher_destroy(b200poa_polisher* h);
+
+/* b200poa_polisher_create with every knob: zero fields mean racon's values (cudabatch.cpp:56-59:
+ * BatchConfig(1023, 200, 256, mode)).  accept_truncated = 0 (default): a window whose layers were dropped by
+ * max_sequence_size / max_sequences_per_poa comes back UNPOLISHED (its backbone, polished = 0, status =
+ * the exceeded limit) so that results never silently differ from racon's CPU path; accept_truncated = 1: what the
+ * reference GPU adapter does (src/cuda/cudabatch.cpp:134-153, 232-233) -- polish with the layers that fitted, trim
+ * threshold = staged layers / 2, report polished = 1. */
+typedef struct b200poa_polisher_options {
+    int32_t n_devices;
+    const int32_t* device_ids;
+    int32_t batches_per_device;
+    size_t mem_per_batch;
+    int32_t banded;
+    int32_t match, mismatch, gap;
+    int32_t max_sequence_size;
+    int32_t max_sequences_per_poa;
+    int32_t band_width;
+    int32_t accept_truncated;
+} b200poa_polisher_options;
+int32_t b200poa_polisher_create_ex(const b200poa_polisher_options* opt, b200poa_polisher** out);
+
+/* Pack the rows of a [n_rows x stride] byte matrix (row i valid up to lens[i]) back to back into `flat`
+ * (capacity >= sum(lens)); offsets[i] (n_rows + 1 entries) receives where row i starts.  Host utility for the final
+ * consensus gather (only sum(len) bytes travel).  Returns the number of bytes written. */
+int64_t b200poa_compact_rows(const uint8_t* rows, int64_t n_rows, int64_t stride, const int32_t* lens, uint8_t* flat,
+                             int64_t* offsets);
 
 /* ---- columnar window construction ------------------------------------------------
  * Replaces the per-window objects racon builds in Polisher::initialize (src/polisher.cpp:384-457 with

@@ -36,7 +36,8 @@ ABI_SYMBOLS = (
     "b200poa_layer_order", "b200poa_batch_add_windows", "b200poa_batch_total_poas",
     "b200poa_batch_generate", "b200poa_batch_upload", "b200poa_batch_launch",
     "b200poa_batch_download", "b200poa_batch_get_consensus", "b200poa_batch_id",
-    "b200poa_batch_reset", "b200poa_batch_destroy", "b200poa_batch_get_info",
+    "b200poa_batch_reset", "b200poa_batch_destroy", "b200poa_batch_get_info", "b200poa_batch_set_option",
+    "b200poa_polisher_create_ex", "b200poa_compact_rows",
     "b200poa_status_string", "b200poa_batch_phase_cycles", "b200poa_polish_windows", "b200poa_polish_windows_via_adapter",
     "b200poa_polisher_create", "b200poa_polisher_polish", "b200poa_polisher_destroy",
     "b200poa_arena_create", "b200poa_arena_add_window", "b200poa_arena_add_layer", "b200poa_arena_finalize",
@@ -58,7 +59,15 @@ class Entry(C.Structure):
 class BatchInfo(C.Structure):
     _fields_ = [("n_slots", C.c_int32), ("max_poas", C.c_int32), ("arena_capacity", C.c_int64),
                 ("slot_bytes", C.c_int64), ("device_bytes", C.c_int64), ("staged_bases", C.c_int64),
-                ("kernel_launches", C.c_int64), ("smem_bytes", C.c_int32), ("blocks_per_sm", C.c_int32)]
+                ("kernel_launches", C.c_int64), ("smem_bytes", C.c_int32), ("blocks_per_sm", C.c_int32),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+
+
+class PolisherOptions(C.Structure):
+    _fields_ = [("n_devices", C.c_int32), ("device_ids", C.POINTER(C.c_int32)), ("batches_per_device", C.c_int32),
+                ("mem_per_batch", C.c_size_t), ("banded", C.c_int32), ("match", C.c_int32), ("mismatch", C.c_int32),
+                ("gap", C.c_int32), ("max_sequence_size", C.c_int32), ("max_sequences_per_poa", C.c_int32),
+                ("band_width", C.c_int32), ("accept_truncated", C.c_int32)]
 
 
 _lib = None
@@ -195,27 +204,40 @@ class PoaBatch:
     def download(self):
         self._check(self.lib.b200poa_batch_download(self.handle), "b200poa_batch_download")
 
-    def get_consensus(self):
-        """Synchronises.  Returns (consensus list[bytes], coverage list[np.uint16], status np.int32)."""
+    def get_consensus(self, with_trim: bool = False):
+        """Synchronises.  Returns (consensus list[bytes], coverage list[np.uint16], status np.int32) of the windows
+        in add order (untrimmed); with_trim adds the device-side trim spans [(first, last)] (window.cpp:118-139)."""
         cons = C.POINTER(C.c_uint8)()
         cov = C.POINTER(C.c_uint16)()
         lens = C.POINTER(C.c_int32)()
         stat = C.POINTER(C.c_int32)()
-        stride = C.c_int32(0)
-        self._check(self.lib.b200poa_batch_get_consensus(self.handle, C.byref(cons), C.byref(cov),
-                                                         C.byref(lens), C.byref(stat), C.byref(stride)),
+        offs = C.POINTER(C.c_int32)()
+        trim = C.POINTER(C.c_int32)()
+        self._check(self.lib.b200poa_batch_get_consensus(self.handle, C.byref(cons), C.byref(cov), C.byref(lens),
+                                                         C.byref(stat), C.byref(offs), C.byref(trim)),
                     "b200poa_batch_get_consensus")
         n = self.get_total_poas()
         if n == 0:
-            return [], [], np.zeros(0, dtype=np.int32)
-        s = stride.value
+            return ([], [], np.zeros(0, dtype=np.int32)) + (([],) if with_trim else ())
         lens_a = np.ctypeslib.as_array(lens, shape=(n,)).copy()
         stat_a = np.ctypeslib.as_array(stat, shape=(n,)).copy()
-        cons_a = np.ctypeslib.as_array(cons, shape=(n, s))
-        cov_a = np.ctypeslib.as_array(cov, shape=(n, s))
-        out_c = [cons_a[i, :lens_a[i]].tobytes() for i in range(n)]
-        out_v = [cov_a[i, :lens_a[i]].copy() for i in range(n)]
+        offs_a = np.ctypeslib.as_array(offs, shape=(n,)).copy()
+        trim_a = np.ctypeslib.as_array(trim, shape=(n,)).copy()
+        used = int((offs_a + lens_a).max())
+        cons_a = np.ctypeslib.as_array(cons, shape=(max(used, 1),))
+        out_c = [cons_a[offs_a[i]:offs_a[i] + lens_a[i]].tobytes() for i in range(n)]
+        if cov:
+            cov_a = np.ctypeslib.as_array(cov, shape=(max(used, 1),))
+            out_v = [cov_a[offs_a[i]:offs_a[i] + lens_a[i]].copy() for i in range(n)]
+        else:
+            out_v = [None] * n
+        if with_trim:
+            return out_c, out_v, stat_a, [(int(t) & 0xFFFF, int(t) >> 16) for t in trim_a]
         return out_c, out_v, stat_a
+
+    def set_option(self, option: int, value: int):
+        self._check(self.lib.b200poa_batch_set_option(self.handle, C.c_int32(option), C.c_int64(value)),
+                    "b200poa_batch_set_option")
 
     def batch_id(self) -> int:
         return int(self.lib.b200poa_batch_id(self.handle))
@@ -268,27 +290,33 @@ class CUDABatchProcessor:
                               band_width=256, banded=cuda_banded_alignment, gap=gap,
                               mismatch=mismatch, match=match)
         self.tgs, self.trim = tgs, trim
-        self.n_seqs = []
+        self.n_seqs, self.seqs_added, self.backbones = [], [], []
 
     def add_windows(self, windows: WindowBatch, first: int = 0) -> int:
         """The addWindow loop of cudapolisher.cpp:254-276.  Returns how many windows fitted."""
         n, seqs_added = self.batch.add_windows(windows, first)
         s = windows.win_seq_off
         self.n_seqs.extend((s[first + 1:first + n + 1] - s[first:first + n]).tolist())
+        self.seqs_added.extend(np.asarray(seqs_added).tolist())
+        for w in range(first, first + n):  # the backbone, for windows that come back unpolished
+            a, b = int(windows.seq_off[s[w]]), int(windows.seq_off[s[w] + 1])
+            self.backbones.append(windows.bases[a:b].tobytes())
         return n
 
     def has_windows(self) -> bool:
         return self.batch.get_total_poas() > 0
 
     def generate_consensus(self):
-        """Returns (list of consensus bytes, list of bool status) for the windows in the batch."""
+        """Returns (list of consensus bytes, list of bool status) for the windows in the batch.  A window reported
+        False holds its backbone: fewer than 3 sequences (window.cpp:68-71), a kernel status, or layers dropped by the
+        batch limits (same rule as cuda_polisher.cpp / cuda_batch.cpp: left to the caller's CPU path)."""
         self.batch.generate_poa()
         cons, cov, status = self.batch.get_consensus()
         out, ok = [], []
         for i in range(len(cons)):
-            if status[i] != SUCCESS:
-                out.append(b"")
-                ok.append(False)  # cudabatch.cpp:209-213: left to the caller's CPU path
+            if self.n_seqs[i] < 3 or status[i] != SUCCESS or self.seqs_added[i] != self.n_seqs[i] - 1:
+                out.append(self.backbones[i])
+                ok.append(False)
                 continue
             c = cons[i]
             if self.tgs and self.trim:
@@ -299,7 +327,7 @@ class CUDABatchProcessor:
 
     def reset(self):
         self.batch.reset()
-        self.n_seqs = []
+        self.n_seqs, self.seqs_added, self.backbones = [], [], []
 
 
 def polish_windows(windows: WindowBatch, match: int = 3, mismatch: int = -5, gap: int = -4,
@@ -344,6 +372,21 @@ def polish_windows(windows: WindowBatch, match: int = 3, mismatch: int = -5, gap
     return cons, clen, pol.astype(bool), status, int(launches.value)
 
 
+def compact_rows(cons: np.ndarray, clen: np.ndarray, flat: np.ndarray | None = None):
+    """Rows of a [W, stride] consensus matrix packed back to back (b200poa_compact_rows).  Returns (flat, offsets)."""
+    lib = load_library()
+    lib.b200poa_compact_rows.restype = C.c_int64
+    W, stride = cons.shape
+    clen = np.ascontiguousarray(clen, dtype=np.int32)
+    total = int(np.minimum(clen, stride).sum())
+    if flat is None or flat.shape[0] < total:
+        flat = np.empty(max(total, 1), dtype=np.uint8)
+    off = np.zeros(W + 1, dtype=np.int64)
+    n = lib.b200poa_compact_rows(_p(cons, C.c_uint8), C.c_int64(W), C.c_int64(stride), _p(clen, C.c_int32),
+                                 _p(flat, C.c_uint8), _p(off, C.c_int64))
+    return flat[:n], off
+
+
 def consensus_list(cons: np.ndarray, clen: np.ndarray):
     return [cons[w, :clen[w]].tobytes() for w in range(cons.shape[0])]
 
@@ -353,17 +396,18 @@ class Polisher:
     reused by every `polish` call, like one `CUDAPolisher::polish` run does (cudapolisher.cpp:226-240)."""
 
     def __init__(self, devices=None, batches_per_device: int = 1, mem_per_batch: int = 0, banded: bool = False,
-                 match: int = 3, mismatch: int = -5, gap: int = -4):
+                 match: int = 3, mismatch: int = -5, gap: int = -4, max_sequence_size: int = 0,
+                 max_sequences_per_poa: int = 0, band_width: int = 0, accept_truncated: bool = False):
         self.lib = load_library()
         self.lib.b200poa_polisher_destroy.restype = None
         dev = np.asarray(devices if devices is not None else [], dtype=np.int32)
         self.handle = C.c_void_p()
-        st = self.lib.b200poa_polisher_create(C.c_int32(dev.shape[0]), _p(dev, C.c_int32) if dev.shape[0] else None,
-                                              C.c_int32(batches_per_device), C.c_size_t(mem_per_batch),
-                                              C.c_int32(int(banded)), C.c_int32(match), C.c_int32(mismatch),
-                                              C.c_int32(gap), C.byref(self.handle))
+        opt = PolisherOptions(dev.shape[0], _p(dev, C.c_int32) if dev.shape[0] else None, batches_per_device,
+                              mem_per_batch, int(banded), match, mismatch, gap, max_sequence_size,
+                              max_sequences_per_poa, band_width, int(accept_truncated))
+        st = self.lib.b200poa_polisher_create_ex(C.byref(opt), C.byref(self.handle))
         if st != SUCCESS:
-            raise RuntimeError(f"b200poa_polisher_create failed: {status_string(st)}")
+            raise RuntimeError(f"b200poa_polisher_create_ex failed: {status_string(st)}")
         self.last = {}
 
     def polish(self, windows: WindowBatch, tgs: bool = True, trim: bool = True, max_windows_per_round: int = 0,

@@ -39,19 +39,23 @@ struct KernelArgs {
     size_t slot_bytes;
     int32_t n_windows;
     const int32_t* work; /* window ids, most expensive first */
-    int32_t* cursor;     /* atomic work cursor (zeroed before launch) */
+    int32_t* cursor;     /* [0] atomic work cursor, [1] elements used in the output arenas (both zeroed before launch) */
     const uint8_t* bases;
-    const int8_t* weights;
+    const int8_t* weights;      /* compact: sequences with non-constant weights only */
     const int64_t* seq_off;     /* [n_seqs+1] */
+    const int64_t* w_off;       /* [n_seqs] offset into weights, or -1 - constant */
     const int32_t* win_seq_off; /* [n_windows+1] */
     const int32_t* win_flags;   /* per window: pre-set status (!= 0 => skip) */
+    const int32_t* win_trim_nseq; /* per window: sequences counted by the trim threshold */
     const int32_t* seq_begin;   /* [n_seqs] layer span (-1 = spans the window)  */
     const int32_t* seq_end;     /* [n_seqs] */
-    uint8_t* out_cons;
+    uint8_t* out_cons;          /* compact arenas, see WindowOut */
     uint16_t* out_cov;
     int32_t* out_len;
     int32_t* out_status;
-    int32_t prof_stride; /* int16 cells per profile row  */
+    int32_t* out_off;
+    int32_t* out_trim;
+    int32_t prof_stride; /* bytes per profile row        */
     int32_t ring_stride; /* int16 cells per ring row     */
     int32_t ring_rows;   /* power of two                 */
     unsigned long long* phase_cycles; /* diagnostics: [PH_COUNT] or nullptr */
@@ -81,10 +85,11 @@ __global__ void __launch_bounds__(32, POA_MIN_BLOCKS_PER_SM) poa_window_kernel(c
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= a.n_windows) break;
         const int32_t w = a.work[t];
-        const size_t orow = (size_t)w * (size_t)a.p.max_cons;
         if (a.win_flags[w] != 0) {
             if (lane == 0) {
                 a.out_len[w] = 0;
+                a.out_off[w] = 0;
+                a.out_trim[w] = (int32_t)0xFFFF0000u;
                 a.out_status[w] = a.win_flags[w];
             }
             continue;
@@ -95,10 +100,19 @@ __global__ void __launch_bounds__(32, POA_MIN_BLOCKS_PER_SM) poa_window_kernel(c
         wv.bases = a.bases;
         wv.weights = a.weights;
         wv.seq_off = a.seq_off + s0;
+        wv.w_off = a.w_off + s0;
         wv.seq_begin = a.seq_begin + s0;
         wv.seq_end = a.seq_end + s0;
-        process_window(s, a.p, wv, fill, tbs, a.out_cons + orow, a.out_cov + orow, a.out_len + w,
-                       a.out_status + w, PhaseTimer{a.phase_cycles, 0});
+        WindowOut out;
+        out.cons = a.out_cons;
+        out.cov = a.out_cov;
+        out.cursor = reinterpret_cast<uint32_t*>(a.cursor + 1);
+        out.len = a.out_len + w;
+        out.status = a.out_status + w;
+        out.off = a.out_off + w;
+        out.trim = a.out_trim + w;
+        out.trim_nseq = a.win_trim_nseq[w];
+        process_window(s, a.p, wv, fill, tbs, out, PhaseTimer{a.phase_cycles, 0});
     }
 }
 
@@ -158,39 +172,88 @@ struct b200poa_batch {
     uint8_t* h_bases = nullptr;
     int8_t* h_weights = nullptr;
     int64_t* h_seq_off = nullptr;
+    int64_t* h_w_off = nullptr;
     int32_t* h_seq_begin = nullptr;
     int32_t* h_seq_end = nullptr;
     int32_t* h_win_seq_off = nullptr;
     int32_t* h_win_flags = nullptr;
+    int32_t* h_win_trim_nseq = nullptr;
     int32_t* h_work = nullptr;
     uint8_t* h_cons = nullptr;
     uint16_t* h_cov = nullptr;
     int32_t* h_len = nullptr;
     int32_t* h_status = nullptr;
+    int32_t* h_out_off = nullptr;
+    int32_t* h_trim = nullptr;
+    int32_t* h_cursor = nullptr; /* [2] as on the device */
     /* device */
     uint8_t* d_slab = nullptr;
     uint8_t* d_bases = nullptr;
     int8_t* d_weights = nullptr;
     int64_t* d_seq_off = nullptr;
+    int64_t* d_w_off = nullptr;
     int32_t* d_seq_begin = nullptr;
     int32_t* d_seq_end = nullptr;
     int32_t* d_win_seq_off = nullptr;
     int32_t* d_win_flags = nullptr;
+    int32_t* d_win_trim_nseq = nullptr;
     int32_t* d_work = nullptr;
     int32_t* d_cursor = nullptr;
     uint8_t* d_cons = nullptr;
     uint16_t* d_cov = nullptr;
     int32_t* d_len = nullptr;
     int32_t* d_status = nullptr;
+    int32_t* d_out_off = nullptr;
+    int32_t* d_trim = nullptr;
     unsigned long long* d_phase = nullptr; /* B200POA_PHASE_TIMERS diagnostics */
     /* fill state */
     int32_t poa_count = 0;
     int64_t seq_count = 0;
     int64_t base_count = 0;
+    int64_t weight_count = 0;  /* bytes in the compact weights arena */
+    int64_t out_elems = 0;     /* elements the last downloaded launch used in the output arenas */
+    bool results_fetched = false;
+    int32_t download_coverage = 1; /* B200POA_OPT_DOWNLOAD_COVERAGE */
+    int32_t trim_counts_staged = 0; /* B200POA_OPT_TRIM_COUNTS_STAGED */
+    int64_t h2d_bytes = 0, d2h_bytes = 0; /* PCIe bytes of the last generate / get_consensus */
     std::vector<int64_t> cost; /* per window work estimate for the longest-first work list */
     int64_t launches = 0;
     bool uploaded = false;
 };
+
+/* Shared memory geometry of a launch whose longest staged read has `max_len` bases: profile rows, score-row ring.
+ * Full-band rows are laid out for fill_rows_wide (lane l owns 8*NV consecutive columns): profile and ring rows are
+ * padded to a multiple of 256 columns. */
+struct SmemGeometry {
+    int32_t prof_stride, ring_stride, ring_rows, smem_bytes;
+};
+static SmemGeometry smem_geometry(const Params& p, int32_t max_len) {
+    SmemGeometry g;
+    const int32_t colsP = (max_len + 1 + 7) & ~7;
+    const bool banded = p.band_width > 0 && p.band_width < colsP;
+    /* fill_rows_wide (full-band rows, and reads shorter than the band in banded batches) gives lane l the columns
+     * [l*8*NV, (l+1)*8*NV): lanes past the read still load -- never store -- profile bytes and ring cells up to
+     * column 256*NV.  Rows are therefore sized by the longest read only, and the allocation ends with enough slack
+     * for the loads of the last row. */
+    const int32_t nv = (colsP + 255) / 256;
+    g.prof_stride = banded ? std::max(colsP, 256) : colsP;
+    const int32_t row_cells = banded ? std::max(p.band_width, 256) : colsP;
+    const int32_t slack_cells = banded ? 0 : 256 * nv - colsP;
+    g.ring_stride = row_cells + RING_PAD_FRONT + RING_PAD_BACK;
+    int32_t ring_bytes = 4096;
+    {   /* at least 8 ring rows: a predecessor more than 7 ranks back is rare (0.6%), more than 3 is not (19%) */
+        const int32_t need8 = 8 * g.ring_stride * (int32_t)sizeof(int16_t);
+        if (need8 > ring_bytes && need8 <= 20480) ring_bytes = need8;
+    }
+    if (const char* env = std::getenv("B200POA_RING_BYTES")) ring_bytes = std::atoi(env);
+    int32_t rows = 2;
+    while (rows < 32 && rows * 2 * g.ring_stride * (int32_t)sizeof(int16_t) <= ring_bytes) rows *= 2;
+    g.ring_rows = rows;
+    g.smem_bytes = 32 + std::max(((PROF_ROWS * g.prof_stride + 15) & ~15) +
+                                     ((g.ring_rows + 1) * g.ring_stride + slack_cells) * (int32_t)sizeof(int16_t),
+                                 (int32_t)TB_SCRATCH_BYTES);
+    return g;
+}
 
 static void free_batch(b200poa_batch* b) {
     if (!b) return;
@@ -198,29 +261,38 @@ static void free_batch(b200poa_batch* b) {
     cudaFreeHost(b->h_bases);
     cudaFreeHost(b->h_weights);
     cudaFreeHost(b->h_seq_off);
+    cudaFreeHost(b->h_w_off);
     cudaFreeHost(b->h_seq_begin);
     cudaFreeHost(b->h_seq_end);
     cudaFreeHost(b->h_win_seq_off);
     cudaFreeHost(b->h_win_flags);
+    cudaFreeHost(b->h_win_trim_nseq);
     cudaFreeHost(b->h_work);
     cudaFreeHost(b->h_cons);
     cudaFreeHost(b->h_cov);
     cudaFreeHost(b->h_len);
     cudaFreeHost(b->h_status);
+    cudaFreeHost(b->h_out_off);
+    cudaFreeHost(b->h_trim);
+    cudaFreeHost(b->h_cursor);
     cudaFree(b->d_slab);
     cudaFree(b->d_bases);
     cudaFree(b->d_weights);
     cudaFree(b->d_seq_off);
+    cudaFree(b->d_w_off);
     cudaFree(b->d_seq_begin);
     cudaFree(b->d_seq_end);
     cudaFree(b->d_win_seq_off);
     cudaFree(b->d_win_flags);
+    cudaFree(b->d_win_trim_nseq);
     cudaFree(b->d_work);
     cudaFree(b->d_cursor);
     cudaFree(b->d_cons);
     cudaFree(b->d_cov);
     cudaFree(b->d_len);
     cudaFree(b->d_status);
+    cudaFree(b->d_out_off);
+    cudaFree(b->d_trim);
     cudaFree(b->d_phase);
     delete b;
 }
@@ -250,12 +322,16 @@ static int32_t stage_window(b200poa_batch* b, int32_t n, Get get, int32_t* per_s
     int32_t flag = 0, added = 0;
     int64_t cost = 0;
     int32_t bb_len = 0;
+    bool backbone_rejected = false;
     for (int32_t i = 0; i < n; ++i) {
         const char* seq; const int8_t* w; int32_t len, bg, en;
         get(i, seq, w, len, bg, en);
         int32_t st = B200POA_SUCCESS;
         if (len > b->cfg.max_sequence_size) st = B200POA_EXCEEDED_MAXIMUM_SEQUENCE_SIZE; /* cudapoa_batch.cuh:501-504 */
         else if (added >= b->cfg.max_sequences_per_poa) st = B200POA_EXCEEDED_MAXIMUM_SEQUENCES_PER_POA; /* :513-516 */
+        if (i == 0 && st != B200POA_SUCCESS) backbone_rejected = true;
+        /* a window whose backbone was rejected stages nothing: no layer may take the backbone's place */
+        if (backbone_rejected && st == B200POA_SUCCESS) st = B200POA_EXCEEDED_MAXIMUM_SEQUENCE_SIZE;
         if (per_seq_status) per_seq_status[i] = st;
         if (st != B200POA_SUCCESS) continue;
         int32_t sp_b = -1, sp_e = -1; /* -1: the layer spans the window */
@@ -276,15 +352,30 @@ static int32_t stage_window(b200poa_batch* b, int32_t n, Get get, int32_t* per_s
         b->h_seq_end[b->seq_count] = sp_e;
         if (len > b->max_len_staged) b->max_len_staged = len;
         std::memcpy(b->h_bases + b->base_count, seq, (size_t)len);
-        if (w) std::memcpy(b->h_weights + b->base_count, w, (size_t)len);
-        else std::memset(b->h_weights + b->base_count, 1, (size_t)len); /* cudapoa_batch.cuh:525-530 */
+        /* weights: a sequence whose bases all weigh the same (no quality string => 1, cudapoa_batch.cuh:525-530;
+         * the '!' dummy quality of a FASTA target => 0) ships only that constant */
+        int64_t wo = -1 - 1;
+        if (w) {
+            bool constant = true;
+            for (int32_t k = 1; k < len && constant; ++k) constant = w[k] == w[0];
+            if (constant) {
+                wo = -1 - (int64_t)w[0];
+            } else {
+                wo = b->weight_count;
+                std::memcpy(b->h_weights + b->weight_count, w, (size_t)len);
+                b->weight_count += len;
+            }
+        }
+        b->h_w_off[b->seq_count] = wo;
         b->base_count += len;
         b->seq_count += 1;
         b->h_seq_off[b->seq_count] = b->base_count;
         cost += (int64_t)len * (bb_len + (int64_t)added * (bb_len / 8 + 1));
         ++added;
     }
+    if (backbone_rejected) flag = B200POA_EXCEEDED_MAXIMUM_SEQUENCE_SIZE; /* the kernel skips the window and reports why */
     b->h_win_flags[b->poa_count] = flag;
+    b->h_win_trim_nseq[b->poa_count] = b->trim_counts_staged ? added : n; /* window.cpp:121 counts every sequence */
     b->poa_count += 1;
     b->h_win_seq_off[b->poa_count] = (int32_t)b->seq_count;
     b->cost.push_back(cost);
@@ -300,16 +391,20 @@ static int32_t alloc_batch_memory(b200poa_batch* b) {
     CU_TRY(cudaMalloc(&b->d_bases, AC));
     CU_TRY(cudaMalloc(&b->d_weights, AC));
     CU_TRY(cudaMalloc(&b->d_seq_off, (MS + 1) * sizeof(int64_t)));
+    CU_TRY(cudaMalloc(&b->d_w_off, (MS + 1) * sizeof(int64_t)));
     CU_TRY(cudaMalloc(&b->d_seq_begin, (MS + 1) * sizeof(int32_t)));
     CU_TRY(cudaMalloc(&b->d_seq_end, (MS + 1) * sizeof(int32_t)));
     CU_TRY(cudaMalloc(&b->d_win_seq_off, (MP + 1) * sizeof(int32_t)));
     CU_TRY(cudaMalloc(&b->d_win_flags, MP * sizeof(int32_t)));
+    CU_TRY(cudaMalloc(&b->d_win_trim_nseq, MP * sizeof(int32_t)));
     CU_TRY(cudaMalloc(&b->d_work, MP * sizeof(int32_t)));
-    CU_TRY(cudaMalloc(&b->d_cursor, sizeof(int32_t)));
+    CU_TRY(cudaMalloc(&b->d_cursor, 2 * sizeof(int32_t)));
     CU_TRY(cudaMalloc(&b->d_cons, MP * (size_t)p.max_cons));
     CU_TRY(cudaMalloc(&b->d_cov, MP * (size_t)p.max_cons * sizeof(uint16_t)));
     CU_TRY(cudaMalloc(&b->d_len, MP * sizeof(int32_t)));
     CU_TRY(cudaMalloc(&b->d_status, MP * sizeof(int32_t)));
+    CU_TRY(cudaMalloc(&b->d_out_off, MP * sizeof(int32_t)));
+    CU_TRY(cudaMalloc(&b->d_trim, MP * sizeof(int32_t)));
     if (std::getenv("B200POA_PHASE_TIMERS")) {
         CU_TRY(cudaMalloc(&b->d_phase, PH_COUNT * sizeof(unsigned long long)));
         CU_TRY(cudaMemset(b->d_phase, 0, PH_COUNT * sizeof(unsigned long long)));
@@ -318,15 +413,20 @@ static int32_t alloc_batch_memory(b200poa_batch* b) {
     CU_TRY(cudaHostAlloc(&b->h_bases, AC, cudaHostAllocDefault));
     CU_TRY(cudaHostAlloc(&b->h_weights, AC, cudaHostAllocDefault));
     CU_TRY(cudaHostAlloc(&b->h_seq_off, (MS + 1) * sizeof(int64_t), cudaHostAllocDefault));
+    CU_TRY(cudaHostAlloc(&b->h_w_off, (MS + 1) * sizeof(int64_t), cudaHostAllocDefault));
     CU_TRY(cudaHostAlloc(&b->h_seq_begin, (MS + 1) * sizeof(int32_t), cudaHostAllocDefault));
     CU_TRY(cudaHostAlloc(&b->h_seq_end, (MS + 1) * sizeof(int32_t), cudaHostAllocDefault));
     CU_TRY(cudaHostAlloc(&b->h_win_seq_off, (MP + 1) * sizeof(int32_t), cudaHostAllocDefault));
     CU_TRY(cudaHostAlloc(&b->h_win_flags, MP * sizeof(int32_t), cudaHostAllocDefault));
+    CU_TRY(cudaHostAlloc(&b->h_win_trim_nseq, MP * sizeof(int32_t), cudaHostAllocDefault));
     CU_TRY(cudaHostAlloc(&b->h_work, MP * sizeof(int32_t), cudaHostAllocDefault));
     CU_TRY(cudaHostAlloc(&b->h_cons, MP * (size_t)p.max_cons, cudaHostAllocDefault));
     CU_TRY(cudaHostAlloc(&b->h_cov, MP * (size_t)p.max_cons * sizeof(uint16_t), cudaHostAllocDefault));
     CU_TRY(cudaHostAlloc(&b->h_len, MP * sizeof(int32_t), cudaHostAllocDefault));
     CU_TRY(cudaHostAlloc(&b->h_status, MP * sizeof(int32_t), cudaHostAllocDefault));
+    CU_TRY(cudaHostAlloc(&b->h_out_off, MP * sizeof(int32_t), cudaHostAllocDefault));
+    CU_TRY(cudaHostAlloc(&b->h_trim, MP * sizeof(int32_t), cudaHostAllocDefault));
+    CU_TRY(cudaHostAlloc(&b->h_cursor, 2 * sizeof(int32_t), cudaHostAllocDefault));
     return B200POA_SUCCESS;
 }
 
@@ -427,14 +527,31 @@ int32_t b200poa_batch_create(int32_t device_id, void* stream, size_t max_gpu_mem
     Slot probe;
     slot_bind(probe, nullptr, p, &b->slot_bytes);
     cudaDeviceProp prop;
-    CU_TRY(cudaGetDeviceProperties(&prop, device_id));
+    if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) {
+        delete b;
+        return B200POA_CUDA_ERROR;
+    }
     b->sm_count = prop.multiProcessorCount;
-    /* worst-case shared memory (longest admissible read) must be launchable */
-    CU_TRY(cudaFuncSetAttribute(poa_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                32 + PROF_ROWS * colsP * (int32_t)sizeof(int16_t) + 8192 + 5 * colsP * (int32_t)sizeof(int16_t)));
+    /* worst-case shared memory (longest admissible read) must be launchable; the attribute is per function and per
+     * device, so it is raised to the device's opt-in limit once and never lowered by a later, smaller batch */
+    const SmemGeometry worst = smem_geometry(p, p.max_len);
+    if (worst.smem_bytes > (int32_t)prop.sharedMemPerBlockOptin) {
+        std::fprintf(stderr, "[b200poa] batch %d: max_sequence_size %d needs %d B of shared memory per block (device limit %zu)\n",
+                     b->id, p.max_len, worst.smem_bytes, (size_t)prop.sharedMemPerBlockOptin);
+        delete b;
+        return B200POA_INVALID_ARGUMENT;
+    }
+    if (cudaFuncSetAttribute(poa_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)prop.sharedMemPerBlockOptin) != cudaSuccess) {
+        delete b;
+        return B200POA_CUDA_ERROR;
+    }
     /* slots are sized for the best occupancy a launch can reach (short reads => small profile) */
     int blocks_per_sm = 0;
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, poa_window_kernel, 32, 4096));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, poa_window_kernel, 32, 4096) != cudaSuccess) {
+        delete b;
+        return B200POA_CUDA_ERROR;
+    }
     if (const char* env = std::getenv("B200POA_BLOCKS_PER_SM")) {
         int v = std::atoi(env);
         if (v > 0 && v < blocks_per_sm) blocks_per_sm = v;
@@ -540,15 +657,19 @@ int32_t b200poa_batch_upload(b200poa_batch* b) {
     std::iota(b->h_work, b->h_work + b->poa_count, 0);
     std::stable_sort(b->h_work, b->h_work + b->poa_count,
                      [&](int32_t x, int32_t y) { return b->cost[(size_t)x] > b->cost[(size_t)y]; });
-    const size_t W = (size_t)b->poa_count;
+    const size_t W = (size_t)b->poa_count, S = (size_t)b->seq_count;
     CU_TRY(cudaMemcpyAsync(b->d_bases, b->h_bases, (size_t)b->base_count, cudaMemcpyHostToDevice, b->stream));
-    CU_TRY(cudaMemcpyAsync(b->d_weights, b->h_weights, (size_t)b->base_count, cudaMemcpyHostToDevice, b->stream));
-    CU_TRY(cudaMemcpyAsync(b->d_seq_off, b->h_seq_off, ((size_t)b->seq_count + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, b->stream));
-    CU_TRY(cudaMemcpyAsync(b->d_seq_begin, b->h_seq_begin, (size_t)b->seq_count * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream));
-    CU_TRY(cudaMemcpyAsync(b->d_seq_end, b->h_seq_end, (size_t)b->seq_count * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream));
+    if (b->weight_count > 0) /* only sequences with non-constant weights carry bytes */
+        CU_TRY(cudaMemcpyAsync(b->d_weights, b->h_weights, (size_t)b->weight_count, cudaMemcpyHostToDevice, b->stream));
+    CU_TRY(cudaMemcpyAsync(b->d_seq_off, b->h_seq_off, (S + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, b->stream));
+    CU_TRY(cudaMemcpyAsync(b->d_w_off, b->h_w_off, S * sizeof(int64_t), cudaMemcpyHostToDevice, b->stream));
+    CU_TRY(cudaMemcpyAsync(b->d_seq_begin, b->h_seq_begin, S * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream));
+    CU_TRY(cudaMemcpyAsync(b->d_seq_end, b->h_seq_end, S * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream));
     CU_TRY(cudaMemcpyAsync(b->d_win_seq_off, b->h_win_seq_off, (W + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream));
     CU_TRY(cudaMemcpyAsync(b->d_win_flags, b->h_win_flags, W * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream));
+    CU_TRY(cudaMemcpyAsync(b->d_win_trim_nseq, b->h_win_trim_nseq, W * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream));
     CU_TRY(cudaMemcpyAsync(b->d_work, b->h_work, W * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream));
+    b->h2d_bytes = b->base_count + b->weight_count + (int64_t)((S + 1) * 8 + S * 16 + (W + 1) * 4 + W * 12);
     b->uploaded = true;
     return B200POA_SUCCESS;
 }
@@ -558,7 +679,7 @@ int32_t b200poa_batch_launch(b200poa_batch* b) {
     if (b->poa_count == 0) return B200POA_SUCCESS;
     if (!b->uploaded) return B200POA_INVALID_ARGUMENT;
     DeviceGuard g(b->device);
-    CU_TRY(cudaMemsetAsync(b->d_cursor, 0, sizeof(int32_t), b->stream));
+    CU_TRY(cudaMemsetAsync(b->d_cursor, 0, 2 * sizeof(int32_t), b->stream));
     KernelArgs a;
     a.p = b->p;
     a.slab = b->d_slab;
@@ -569,34 +690,28 @@ int32_t b200poa_batch_launch(b200poa_batch* b) {
     a.bases = b->d_bases;
     a.weights = b->d_weights;
     a.seq_off = b->d_seq_off;
+    a.w_off = b->d_w_off;
     a.win_seq_off = b->d_win_seq_off;
     a.win_flags = b->d_win_flags;
+    a.win_trim_nseq = b->d_win_trim_nseq;
     a.seq_begin = b->d_seq_begin;
     a.seq_end = b->d_seq_end;
     a.out_cons = b->d_cons;
     a.out_cov = b->d_cov;
     a.out_len = b->d_len;
     a.out_status = b->d_status;
+    a.out_off = b->d_out_off;
+    a.out_trim = b->d_trim;
     /* shared memory geometry follows the longest read actually staged */
-    const int32_t colsP = (b->max_len_staged + 1 + 7) & ~7;
-    b->prof_stride = colsP;
-    b->ring_stride = ((b->p.band_width > 0 && b->p.band_width < colsP) ? b->p.band_width : colsP) + RING_PAD_FRONT + RING_PAD_BACK;
-    int32_t ring_bytes = 4096;
-    {   /* at least 8 ring rows: a predecessor more than 7 ranks back is rare (0.6%), more than 3 is not (19%) */
-        const int32_t need8 = 8 * b->ring_stride * (int32_t)sizeof(int16_t);
-        if (need8 > ring_bytes && need8 <= 16384) ring_bytes = need8;
-    }
-    if (const char* env = std::getenv("B200POA_RING_BYTES")) ring_bytes = std::atoi(env);
-    int32_t rows = 2;
-    while (rows < 32 && rows * 2 * b->ring_stride * (int32_t)sizeof(int16_t) <= ring_bytes) rows *= 2;
-    b->ring_rows = rows;
-    b->smem_bytes = 32 + std::max(((PROF_ROWS * b->prof_stride + 15) & ~15) +
-                                      (b->ring_rows + 1) * b->ring_stride * (int32_t)sizeof(int16_t),
-                                  (int32_t)TB_SCRATCH_BYTES);
+    const SmemGeometry sg = smem_geometry(b->p, b->max_len_staged);
+    b->prof_stride = sg.prof_stride;
+    b->ring_stride = sg.ring_stride;
+    b->ring_rows = sg.ring_rows;
+    b->smem_bytes = sg.smem_bytes;
     int occ = 0;
     CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, poa_window_kernel, 32, (size_t)b->smem_bytes));
     if (occ < 1) return B200POA_INVALID_ARGUMENT;
-    b->blocks_per_sm = std::min(occ, b->n_slots / std::max(b->sm_count, 1) > 0 ? occ : occ);
+    b->blocks_per_sm = occ;
     a.prof_stride = b->prof_stride;
     a.ring_stride = b->ring_stride;
     a.ring_rows = b->ring_rows;
@@ -615,18 +730,24 @@ int32_t b200poa_batch_launch(b200poa_batch* b) {
     poa_window_kernel<<<grid, 32, (size_t)b->smem_bytes, b->stream>>>(a);
     CU_TRY(cudaGetLastError());
     b->launches += 1;
+    b->results_fetched = false;
     return B200POA_SUCCESS;
 }
 
+/* D2H, first half: the per-window tables (length, status, arena offset, trim span) and the arena fill level.  The
+ * compact consensus (and coverage) bytes follow in b200poa_batch_get_consensus, once the fill level is known: exactly
+ * sum(len) bytes cross PCIe instead of poa_count full rows (the reference copies max_poas full rows,
+ * cudapoa_batch.cuh:213-222). */
 int32_t b200poa_batch_download(b200poa_batch* b) {
     if (!b) return B200POA_INVALID_ARGUMENT;
     if (b->poa_count == 0) return B200POA_SUCCESS;
     DeviceGuard g(b->device);
     const size_t W = (size_t)b->poa_count;
-    CU_TRY(cudaMemcpyAsync(b->h_cons, b->d_cons, W * (size_t)b->p.max_cons, cudaMemcpyDeviceToHost, b->stream));
-    CU_TRY(cudaMemcpyAsync(b->h_cov, b->d_cov, W * (size_t)b->p.max_cons * sizeof(uint16_t), cudaMemcpyDeviceToHost, b->stream));
     CU_TRY(cudaMemcpyAsync(b->h_len, b->d_len, W * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
     CU_TRY(cudaMemcpyAsync(b->h_status, b->d_status, W * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
+    CU_TRY(cudaMemcpyAsync(b->h_out_off, b->d_out_off, W * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
+    CU_TRY(cudaMemcpyAsync(b->h_trim, b->d_trim, W * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
+    CU_TRY(cudaMemcpyAsync(b->h_cursor, b->d_cursor, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
     return B200POA_SUCCESS;
 }
 
@@ -639,17 +760,43 @@ int32_t b200poa_batch_generate(b200poa_batch* b) {
 }
 
 int32_t b200poa_batch_get_consensus(b200poa_batch* b, const uint8_t** cons, const uint16_t** cov,
-                                    const int32_t** lens, const int32_t** status, int32_t* stride) {
+                                    const int32_t** lens, const int32_t** status, const int32_t** offsets,
+                                    const int32_t** trim) {
     if (!b) return B200POA_INVALID_ARGUMENT;
     if (!(b->output_mask & B200POA_OUTPUT_CONSENSUS)) return B200POA_OUTPUT_TYPE_UNAVAILABLE; /* cudapoa_batch.cuh:205-209 */
     DeviceGuard g(b->device);
     CU_TRY(cudaStreamSynchronize(b->stream));
+    if (b->poa_count > 0 && !b->results_fetched) { /* D2H, second half: the used part of the compact arenas */
+        const size_t used = (size_t)(uint32_t)b->h_cursor[1];
+        b->out_elems = (int64_t)used;
+        if (used > 0) {
+            CU_TRY(cudaMemcpyAsync(b->h_cons, b->d_cons, used, cudaMemcpyDeviceToHost, b->stream));
+            if (b->download_coverage)
+                CU_TRY(cudaMemcpyAsync(b->h_cov, b->d_cov, used * sizeof(uint16_t), cudaMemcpyDeviceToHost, b->stream));
+            CU_TRY(cudaStreamSynchronize(b->stream));
+        }
+        b->d2h_bytes = (int64_t)b->poa_count * 16 + 8 + (int64_t)used * (b->download_coverage ? 3 : 1);
+        b->results_fetched = true;
+    }
     if (cons) *cons = b->h_cons;
-    if (cov) *cov = b->h_cov;
+    if (cov) *cov = b->download_coverage ? b->h_cov : nullptr;
     if (lens) *lens = b->h_len;
     if (status) *status = b->h_status;
-    if (stride) *stride = b->p.max_cons;
+    if (offsets) *offsets = b->h_out_off;
+    if (trim) *trim = b->h_trim;
     return B200POA_SUCCESS;
+}
+
+int32_t b200poa_batch_set_option(b200poa_batch* b, int32_t option, int64_t value) {
+    if (!b) return B200POA_INVALID_ARGUMENT;
+    switch (option) {
+        case B200POA_OPT_DOWNLOAD_COVERAGE: b->download_coverage = value != 0; return B200POA_SUCCESS;
+        case B200POA_OPT_TRIM_COUNTS_STAGED:
+            if (b->poa_count != 0) return B200POA_INVALID_ARGUMENT; /* decided per window at staging */
+            b->trim_counts_staged = value != 0;
+            return B200POA_SUCCESS;
+        default: return B200POA_INVALID_ARGUMENT;
+    }
 }
 
 int32_t b200poa_batch_reset(b200poa_batch* b) {
@@ -657,8 +804,10 @@ int32_t b200poa_batch_reset(b200poa_batch* b) {
     b->poa_count = 0;
     b->seq_count = 0;
     b->base_count = 0;
+    b->weight_count = 0;
     b->cost.clear();
     b->uploaded = false;
+    b->results_fetched = false;
     b->max_len_staged = 0;
     return B200POA_SUCCESS;
 }
@@ -687,6 +836,8 @@ int32_t b200poa_batch_get_info(const b200poa_batch* b, b200poa_batch_info* info)
     info->kernel_launches = b->launches;
     info->smem_bytes = b->smem_bytes;
     info->blocks_per_sm = b->blocks_per_sm;
+    info->h2d_bytes = b->h2d_bytes;
+    info->d2h_bytes = b->d2h_bytes;
     return B200POA_SUCCESS;
 }
 

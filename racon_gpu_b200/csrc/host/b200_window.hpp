@@ -1,5 +1,5 @@
 /*
- * window.hpp -- host-side window container, same data model as racon::Window
+* b200_window.hpp -- host-side window container, same data model as racon::Window
  * (/root/reference/src/window.hpp:23-75, src/window.cpp:15-63): a backbone plus layers, each a
  * borrowed (pointer, length) pair with an optional quality string and a (begin, end) span.
  * The CPU consensus method (Window::generate_consensus, src/window.cpp:65-142) is deliberately

@@ -90,8 +90,8 @@ public:
     }
     StatusType get_consensus(std::vector<std::string>& consensus, std::vector<std::vector<uint16_t>>& coverage,
                              std::vector<StatusType>& output_status) {
-        const uint8_t* c; const uint16_t* v; const int32_t* l; const int32_t* s; int32_t stride;
-        const int32_t r = b200poa_batch_get_consensus(b_, &c, &v, &l, &s, &stride);
+        const uint8_t* c; const uint16_t* v; const int32_t* l; const int32_t* s; const int32_t* off;
+        const int32_t r = b200poa_batch_get_consensus(b_, &c, &v, &l, &s, &off, nullptr);
         if (r != B200POA_SUCCESS) return to_status(r);
         const int32_t n = get_total_poas();
         for (int32_t i = 0; i < n; ++i) {
@@ -101,9 +101,10 @@ public:
                 coverage.emplace_back(std::vector<uint16_t>());
                 continue;
             }
-            const size_t o = static_cast<size_t>(i) * static_cast<size_t>(stride);
+            const size_t o = static_cast<size_t>(off[i]); /* compact arenas: window i lives at its own offset */
             consensus.emplace_back(reinterpret_cast<const char*>(c + o), static_cast<size_t>(l[i]));
-            coverage.emplace_back(v + o, v + o + l[i]);
+            if (v) coverage.emplace_back(v + o, v + o + l[i]);
+            else coverage.emplace_back(std::vector<uint16_t>());
         }
         return success;
     }

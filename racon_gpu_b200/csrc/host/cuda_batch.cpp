@@ -137,7 +137,10 @@ void CUDABatchProcessor::getConsensus() {
             continue;
         }
         if (output_status.at(k) != StatusType::success || dropped_layers_[i]) {
-            window_consensus_status_.emplace_back(false); /* left to the caller's CPU polisher (cudabatch.cpp:209-213) */
+            /* left to the caller's CPU polisher (cudabatch.cpp:209-213); until then the window reads as its
+             * backbone, so a caller without a CPU path stitches unpolished sequence, never a hole */
+            window->consensus_ = std::string(window->sequences_.front().first, window->sequences_.front().second);
+            window_consensus_status_.emplace_back(false);
             continue;
         }
         window->consensus_ = consensuses[k];

@@ -11,7 +11,9 @@
  *   - a chimeric window keeps its untrimmed consensus and reports true (window.cpp:134-137);
  *   - kNGS windows report true;
  *   - a window whose layers were dropped by the batch limits (too long / too deep,
- *     cudabatch.cpp:143-152) reports false so that the caller's CPU path polishes it exactly.
+ *     cudabatch.cpp:143-152) reports false and holds its backbone, so that the caller's CPU path
+ *     polishes it exactly (the columnar polisher can instead accept the truncation like the reference:
+ *     b200poa_polisher_options::accept_truncated).
  */
 #pragma once
 #include <atomic>
@@ -19,7 +21,7 @@
 #include <vector>
 
 #include "b200poa_batch.hpp"
-#include "window.hpp"
+#include "b200_window.hpp"
 
 namespace racon_b200 {
 

@@ -117,6 +117,8 @@ struct FlatProc {
 struct b200poa_polisher {
     std::vector<FlatProc> procs;
     int32_t banded = 0;
+    int32_t accept_truncated = 0;
+    int32_t max_sequences_per_poa = 200;
 };
 
 extern "C" void b200poa_polisher_destroy(b200poa_polisher* h) {
@@ -129,36 +131,43 @@ extern "C" void b200poa_polisher_destroy(b200poa_polisher* h) {
     delete h;
 }
 
-extern "C" int32_t b200poa_polisher_create(int32_t n_devices, const int32_t* device_ids, int32_t batches_per_device,
-                                           size_t mem_per_batch, int32_t banded, int32_t match, int32_t mismatch,
-                                           int32_t gap, b200poa_polisher** out) {
+extern "C" int32_t b200poa_polisher_create_ex(const b200poa_polisher_options* opt, b200poa_polisher** out) {
     using namespace racon_b200;
-    if (!out) return B200POA_INVALID_ARGUMENT;
+    if (!out || !opt) return B200POA_INVALID_ARGUMENT;
     *out = nullptr;
     std::vector<int32_t> devices;
     try {
         std::vector<int32_t> want;
-        for (int32_t i = 0; i < n_devices; ++i) want.push_back(device_ids[i]);
+        for (int32_t i = 0; i < opt->n_devices; ++i) want.push_back(opt->device_ids[i]);
         devices = resolve_devices(want);
     } catch (const std::exception& e) {
         std::fprintf(stderr, "%s\n", e.what());
         return B200POA_CUDA_ERROR;
     }
-    const uint32_t nb = static_cast<uint32_t>(std::max(batches_per_device, 1));
+    const uint32_t nb = static_cast<uint32_t>(std::max(opt->batches_per_device, 1));
     b200poa_polisher* h = new b200poa_polisher();
-    h->banded = banded;
+    h->banded = opt->banded;
+    h->accept_truncated = opt->accept_truncated;
     int32_t rc = B200POA_SUCCESS;
-    b200poa_config cfg;
-    b200poa_config_default(&cfg, 1023, 200, 256, banded ? B200POA_STATIC_BAND : B200POA_FULL_BAND); /* cudabatch.cpp:56-59 */
+    b200poa_config cfg; /* cudabatch.cpp:56-59: BatchConfig(1023, max_depth 200, 256, band mode) unless overridden */
+    b200poa_config_default(&cfg, opt->max_sequence_size > 0 ? opt->max_sequence_size : 1023,
+                           opt->max_sequences_per_poa > 0 ? opt->max_sequences_per_poa : 200,
+                           opt->band_width > 0 ? opt->band_width : 256, opt->banded ? B200POA_STATIC_BAND : B200POA_FULL_BAND);
+    h->max_sequences_per_poa = cfg.max_sequences_per_poa;
     for (int32_t dev : devices) {
-        const size_t mem = batch_memory(dev, nb, mem_per_batch);
+        const size_t mem = batch_memory(dev, nb, opt->mem_per_batch);
         for (uint32_t k = 0; k < nb && rc == B200POA_SUCCESS; ++k) {
             FlatProc p;
             p.device = dev;
             cudaSetDevice(dev);
             if (cudaStreamCreate(&p.stream) != cudaSuccess) rc = B200POA_CUDA_ERROR;
-            else rc = b200poa_batch_create(dev, p.stream, mem, B200POA_OUTPUT_CONSENSUS, &cfg, static_cast<int16_t>(gap),
-                                           static_cast<int16_t>(mismatch), static_cast<int16_t>(match), &p.batch);
+            else rc = b200poa_batch_create(dev, p.stream, mem, B200POA_OUTPUT_CONSENSUS, &cfg, static_cast<int16_t>(opt->gap),
+                                           static_cast<int16_t>(opt->mismatch), static_cast<int16_t>(opt->match), &p.batch);
+            if (rc == B200POA_SUCCESS) {
+                /* the polisher only needs the trimmed consensus: the trim span comes from the device, the coverage stays there */
+                b200poa_batch_set_option(p.batch, B200POA_OPT_DOWNLOAD_COVERAGE, 0);
+                b200poa_batch_set_option(p.batch, B200POA_OPT_TRIM_COUNTS_STAGED, opt->accept_truncated ? 1 : 0);
+            }
             h->procs.push_back(p);
         }
     }
@@ -168,6 +177,22 @@ extern "C" int32_t b200poa_polisher_create(int32_t n_devices, const int32_t* dev
     }
     *out = h;
     return B200POA_SUCCESS;
+}
+
+extern "C" int32_t b200poa_polisher_create(int32_t n_devices, const int32_t* device_ids, int32_t batches_per_device,
+                                           size_t mem_per_batch, int32_t banded, int32_t match, int32_t mismatch,
+                                           int32_t gap, b200poa_polisher** out) {
+    b200poa_polisher_options opt;
+    std::memset(&opt, 0, sizeof(opt));
+    opt.n_devices = n_devices;
+    opt.device_ids = device_ids;
+    opt.batches_per_device = batches_per_device;
+    opt.mem_per_batch = mem_per_batch;
+    opt.banded = banded;
+    opt.match = match;
+    opt.mismatch = mismatch;
+    opt.gap = gap;
+    return b200poa_polisher_create_ex(&opt, out);
 }
 
 extern "C" int32_t b200poa_polisher_polish(b200poa_polisher* h, int64_t n_windows, const int64_t* win_seq_off,
@@ -225,8 +250,8 @@ extern "C" int32_t b200poa_polisher_polish(b200poa_polisher* h, int64_t n_window
             const double t1 = now();
             st = b200poa_batch_generate(p->batch);
             if (st != B200POA_SUCCESS) return st;
-            const uint8_t* c; const uint16_t* v; const int32_t* l; const int32_t* s; int32_t bstride;
-            st = b200poa_batch_get_consensus(p->batch, &c, &v, &l, &s, &bstride);
+            const uint8_t* c; const int32_t* l; const int32_t* s; const int32_t* off; const int32_t* tr;
+            st = b200poa_batch_get_consensus(p->batch, &c, nullptr, &l, &s, &off, &tr);
             if (st != B200POA_SUCCESS) return st;
             const double t2 = now();
             b200poa_batch_info info;
@@ -234,45 +259,40 @@ extern "C" int32_t b200poa_polisher_polish(b200poa_polisher* h, int64_t n_window
             for (int64_t i = 0; i < n_added; ++i) {
                 const int64_t w = first + i;
                 const int64_t nseq = win_seq_off[w + 1] - win_seq_off[w];
-                const size_t o = static_cast<size_t>(i) * static_cast<size_t>(bstride);
                 uint8_t* dst = cons_out + static_cast<size_t>(w) * static_cast<size_t>(stride);
                 if (status_out) status_out[w] = s[i];
-                if (nseq < 3) { /* window.cpp:68-71: backbone, not polished */
+                const bool dropped = seqs_added[static_cast<size_t>(i)] != nseq - 1; /* layers cut by the batch limits */
+                if (nseq < 3 || s[i] != B200POA_SUCCESS || (dropped && !h->accept_truncated)) {
+                    /* window.cpp:68-71 (< 3 sequences), a kernel status, or -- unless the caller accepts the reference
+                     * GPU adapter's depth truncation (cudabatch.cpp:134-153) -- dropped layers: the window comes back
+                     * as its backbone with polished = 0, never as a hole; the caller's CPU path may still polish it */
                     const int64_t a = seq_off[win_seq_off[w]], b = seq_off[win_seq_off[w] + 1];
-                    const int64_t n = std::min<int64_t>(b - a, stride);
-                    std::memcpy(dst, bases + a, static_cast<size_t>(n));
+                    std::memcpy(dst, bases + a, static_cast<size_t>(std::min<int64_t>(b - a, stride)));
                     cons_len[w] = static_cast<int32_t>(b - a);
                     polished[w] = 0;
-                    continue;
-                }
-                if (s[i] != B200POA_SUCCESS || seqs_added[static_cast<size_t>(i)] != nseq - 1) {
-                    /* kernel failure, or layers dropped by the batch limits: the caller's CPU path */
-                    cons_len[w] = 0;
-                    polished[w] = 0;
+                    if (status_out && s[i] == B200POA_SUCCESS && nseq >= 3)
+                        status_out[w] = nseq - 1 > h->max_sequences_per_poa ? B200POA_EXCEEDED_MAXIMUM_SEQUENCES_PER_POA
+                                                                             : B200POA_EXCEEDED_MAXIMUM_SEQUENCE_SIZE;
                     continue;
                 }
                 int32_t begin = 0, end = l[i] - 1;
-                if (tgs && trim) { /* window.cpp:118-139 */
-                    const uint32_t avg = static_cast<uint32_t>(nseq - 1) / 2;
-                    for (; begin < l[i]; ++begin)
-                        if (v[o + begin] >= avg) break;
-                    for (; end >= 0; --end)
-                        if (v[o + end] >= avg) break;
-                    if (begin >= end) {
-                        begin = 0;
-                        end = l[i] - 1;
+                if (tgs && trim) { /* window.cpp:118-139, evaluated on the device (WindowOut::trim) */
+                    const int32_t tb = tr[i] & 0xFFFF, te = tr[i] >> 16;
+                    if (tb < te) {
+                        begin = tb;
+                        end = te;
                     }
                 }
                 const int32_t n = end - begin + 1;
-                std::memcpy(dst, c + o + begin, static_cast<size_t>(std::min(n, stride)));
+                std::memcpy(dst, c + off[i] + begin, static_cast<size_t>(std::min(n, stride)));
                 cons_len[w] = n;
                 polished[w] = 1;
             }
             {
                 std::lock_guard<std::mutex> g(mu);
                 launches += 1;
-                up_bytes += 2 * info.staged_bases + 8 * (win_seq_off[first + n_added] - win_seq_off[first] + 1) + 12 * n_added + 4;
-                down_bytes += n_added * (3 * static_cast<int64_t>(bstride) + 8);
+                up_bytes += info.h2d_bytes;
+                down_bytes += info.d2h_bytes;
             }
             lo = first + n_added;
             t_stage += t1 - t0;
@@ -437,3 +457,16 @@ extern "C" int32_t b200poa_polisher_polish_arena(b200poa_polisher* h, const b200
 }
 
 extern "C" void b200poa_arena_destroy(b200poa_arena* a) { delete a; }
+
+extern "C" int64_t b200poa_compact_rows(const uint8_t* rows, int64_t n_rows, int64_t stride, const int32_t* lens,
+                                        uint8_t* flat, int64_t* offsets) {
+    int64_t o = 0;
+    for (int64_t i = 0; i < n_rows; ++i) {
+        if (offsets) offsets[i] = o;
+        const int64_t n = std::min<int64_t>(lens[i], stride);
+        std::memcpy(flat + o, rows + i * stride, static_cast<size_t>(n));
+        o += n;
+    }
+    if (offsets) offsets[n_rows] = o;
+    return o;
+}

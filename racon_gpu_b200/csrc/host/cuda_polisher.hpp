@@ -11,7 +11,7 @@
 #include <memory>
 #include <vector>
 
-#include "window.hpp"
+#include "b200_window.hpp"
 
 namespace racon_b200 {
 

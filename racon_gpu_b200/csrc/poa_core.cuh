@@ -203,17 +203,53 @@ void slot_bind(Slot& s, uint8_t* base, const Params& p, size_t* total_out) {
 struct WindowView {
     int32_t n_seqs;
     const uint8_t* bases;    /* batch arena */
-    const int8_t* weights;   /* batch arena (always materialised; 1 when racon has no quality) */
-    const int64_t* seq_off;  /* [n_seqs+1] offsets of this window's sequences in the arenas */
+    const int8_t* weights;   /* compact arena: only sequences whose weights are not one constant live here */
+    const int64_t* seq_off;  /* [n_seqs+1] offsets of this window's sequences in the bases arena */
+    const int64_t* w_off;    /* [n_seqs] >= 0: offset of the sequence's weights in `weights`; < 0: every base weighs
+                                -1 - w_off (racon: no quality string => 1, window.cpp:105-107; the '!' dummy quality of
+                                a FASTA target => 0, polisher.cpp:171,392-395) -- such sequences ship no weight bytes */
     const int32_t* seq_begin; /* [n_seqs] layer span on the backbone, or -1 when the layer spans the window */
     const int32_t* seq_end;   /* (window.cpp:87,92-93 decides which; the host applies that rule)           */
 };
+
+/* Where a window's result goes: consensus and coverage are appended to compact arenas (one bump allocation per
+ * window, 16-element granules), the per-window tables say where.  The coverage trim of window.cpp:118-139 is
+ * evaluated here too, so that a caller that only wants the trimmed consensus never downloads the coverage. */
+struct WindowOut {
+    uint8_t* cons;     /* compact consensus arena                          */
+    uint16_t* cov;     /* compact coverage arena, same offsets             */
+    uint32_t* cursor;  /* elements used so far in both arenas              */
+    int32_t* len;      /* this window's slots in the per-window tables ... */
+    int32_t* status;
+    int32_t* off;      /* ... offset of its consensus in the arenas        */
+    int32_t* trim;     /* ... first (low 16 bits) and last (high 16 bits, signed) index whose coverage is
+                          >= (trim_nseq - 1) / 2; first > last: no such base */
+    int32_t trim_nseq; /* sequences the trim threshold counts (window.cpp:121: sequences_.size()) */
+};
+
+POA_FN uint32_t poa_bump(uint32_t* cursor, uint32_t n) {
+#if POA_DEVICE
+    return atomicAdd(cursor, n);
+#else
+    const uint32_t o = *cursor;
+    *cursor += n;
+    return o;
+#endif
+}
+POA_FN int poa_fls(unsigned m) { /* index of highest set bit, m != 0 */
+#if POA_DEVICE
+    return 31 - __clz((int)m);
+#else
+    return 31 - __builtin_clz(m);
+#endif
+}
 
 /* Mutable per-window state (warp-uniform scalars). */
 struct WinState {
     int32_t n_nodes;
     int32_t n_edges;
     int32_t status;
+    int32_t n_columns; /* aligned cliques (a node without aligned mates counts as one): no path visits more nodes */
 };
 
 /* optional per-phase cycle counters (diagnostics: B200POA_PHASE_TIMERS=1), device flavour only */
@@ -259,7 +295,7 @@ __device__ unsigned long long g_subtimers[32];
  * Phase 0: backbone chain  (graph.cpp:274-292 add_sequence + :177-185; window.cpp:73-76)
  * ---------------------------------------------------------------------------------------- */
 POA_FN_NOINLINE void init_backbone(const Slot& s_ref, const Params& p_ref, WinState& st, const uint8_t* seq,
-                          const int8_t* w, int32_t len) {
+                          const int8_t* w, int32_t wconst, int32_t len) {
     const Slot s = s_ref;     /* local copies: no reloads of the descriptor after every store */
     const Params p = p_ref;
     if (len > p.max_nodes || len - 1 > p.max_edges) {
@@ -288,7 +324,7 @@ POA_FN_NOINLINE void init_backbone(const Slot& s_ref, const Params& p_ref, WinSt
                 s.e_src[k - 1] = (uint16_t)(k - 1);
                 s.e_dst[k - 1] = (uint16_t)k;
                 s.e_next[k - 1] = NONE16;
-                s.e_w[k - 1] = (int32_t)w[k - 1] + (int32_t)w[k];
+                s.e_w[k - 1] = w ? (int32_t)w[k - 1] + (int32_t)w[k] : 2 * wconst;
                 s.e_ord[k - 1] = 0;
             }
         }
@@ -296,6 +332,7 @@ POA_FN_NOINLINE void init_backbone(const Slot& s_ref, const Params& p_ref, WinSt
     POA_SYNC();
     st.n_nodes = len;
     st.n_edges = len - 1;
+    st.n_columns = len;
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -1066,7 +1103,7 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
  * Phase 4: add the alignment to the graph  (graph.cpp:155-272, 94-116)
  * ---------------------------------------------------------------------------------------- */
 POA_FN_NOINLINE void add_alignment(const Slot& s_ref, const Params& p_ref, WinState& st, const uint8_t* read,
-                          const int8_t* wt, int32_t len, int32_t tb_begin) {
+                          const int8_t* wt, int32_t wconst, int32_t len, int32_t tb_begin) {
     const Slot s = s_ref;     /* local copies: no reloads of the descriptor after every store */
     const Params p = p_ref;
     const int32_t cap = p.max_nodes + p.max_len + 2;
@@ -1113,6 +1150,7 @@ POA_FN_NOINLINE void add_alignment(const Slot& s_ref, const Params& p_ref, WinSt
     /* (b) create the new nodes; ids follow read order exactly like the serial add_node calls. */
     int32_t n_new = 0;
     int32_t fail = 0;
+    int32_t n_cols = st.n_columns;
     for (int32_t base = 0; base < len; base += 32) {
         PerLane<int> isnew;
         POA_LANES(l) {
@@ -1121,6 +1159,11 @@ POA_FN_NOINLINE void add_alignment(const Slot& s_ref, const Params& p_ref, WinSt
         }
         PerLane<int> off = isnew;
         const int32_t tot = warp_exscan(off);
+        {   /* a new node that is aligned to nothing opens a new column of the graph */
+            PerLane<int> opens;
+            POA_LANES(l) { opens[l] = (isnew[l] && s.asg[base + l] == -1) ? 1 : 0; }
+            n_cols += poa_popc(warp_ballot(opens));
+        }
         if (N0 + n_new + tot > p.max_nodes) {
             fail = ST_NODE_COUNT_EXCEEDED;
             break;
@@ -1221,6 +1264,7 @@ POA_FN_NOINLINE void add_alignment(const Slot& s_ref, const Params& p_ref, WinSt
     }
     POA_SYNC();
     st.n_nodes = N0 + n_new;
+    st.n_columns = n_cols;
 
     POA_SUB_LAP(4);
     /* (d) edges prev -> cur for consecutive read positions (graph.cpp:248-259, 94-116), and
@@ -1307,7 +1351,7 @@ POA_FN_NOINLINE void add_alignment(const Slot& s_ref, const Params& p_ref, WinSt
                 act[u] = pos < len && pos != 0;
                 cur[u] = act[u] ? s.asg[pos] : 0;
                 prev[u] = act[u] ? s.asg[pos - 1] : 0;
-                w[u] = act[u] ? (int32_t)wt[pos - 1] + (int32_t)wt[pos] : 0;
+                w[u] = act[u] ? (wt ? (int32_t)wt[pos - 1] + (int32_t)wt[pos] : 2 * wconst) : 0;
             }
 #pragma unroll
             for (int32_t u = 0; u < DU; ++u) {
@@ -1719,13 +1763,13 @@ POA_FN void consensus_scores_full(const Slot& s, int32_t N, int32_t& max_id_out)
     max_id_out = max_id;
 }
 
-POA_FN_NOINLINE void generate_consensus(const Slot& s_ref, const Params& p_ref, WinState& st, uint8_t* out_cons,
-                               uint16_t* out_cov, int32_t* out_len) {
+POA_FN_NOINLINE void generate_consensus(const Slot& s_ref, const Params& p_ref, WinState& st, const WindowOut& out_ref) {
     const Slot s = s_ref;     /* local copies: no reloads of the descriptor after every store */
     const Params p = p_ref;
+    const WindowOut out = out_ref;
     const int32_t N = st.n_nodes;
     POA_SUB_BEGIN();
-    int32_t len = 0;
+    int32_t n = 0;
     int32_t max_id_full = 0;
     consensus_scores_full(s, N, max_id_full);
     POA_LANE0 {
@@ -1747,51 +1791,80 @@ POA_FN_NOINLINE void generate_consensus(const Slot& s_ref, const Params& p_ref, 
             consensus_scores_from(s, N, rank + 1, true, max_id, ms, false);
         }
         POA_SUB_LAP(14);
-        /* backtrack into c_score as scratch (path reversed), then emit forward */
-        int32_t n = 0;
+        /* backtrack into the stack as scratch (path reversed); emitted forward below */
         int32_t v = max_id;
         while (s.c_pred[v] != -1 && n < N) {
             s.stack[n++] = (uint16_t)v;
             v = s.c_pred[v];
         }
         s.stack[n++] = (uint16_t)v;
-        if (n > p.max_cons) {
-            st.status = ST_GENERIC_ERROR;
-            n = 0;
-        }
-        for (int32_t k = 0; k < n; ++k) {
-            const int32_t id = s.stack[n - 1 - k];
-            out_cons[k] = s.code[id];
-            int32_t c = s.cov[id];
-            for (int32_t q = 0; q < s.aln_cnt[id]; ++q) c += s.cov[s.aln[id * KA + q]];
-            out_cov[k] = (uint16_t)c;
-        }
-        POA_SUB_LAP(15);
-        len = n;
-        *out_len = n;
     }
     POA_SYNC();
-    (void)len;
+    n = warp_bcast0(n);
+    if (n > p.max_cons) {
+        st.status = ST_GENERIC_ERROR;
+        return;
+    }
+    /* one bump allocation in the compact output arenas (16-element granules keep every window 16-byte aligned) */
+    int32_t off = 0;
+    POA_LANE0 { off = (int32_t)poa_bump(out.cursor, ((uint32_t)n + 15u) & ~15u); }
+    off = warp_bcast0(off);
+    /* emit forward, 32 bases per step, and find the span racon's TGS trim keeps (window.cpp:118-139) */
+    const int32_t avg = (out.trim_nseq - 1) / 2;
+    int32_t first = n, last = -1;
+    for (int32_t base = 0; base < n; base += 32) {
+        PerLane<int> ok;
+        POA_LANES(l) {
+            const int32_t k = base + l;
+            ok[l] = 0;
+            if (k < n) {
+                const int32_t id = s.stack[n - 1 - k];
+                int32_t c = s.cov[id];
+                const int32_t na = s.aln_cnt[id];
+                for (int32_t q = 0; q < na; ++q) c += s.cov[s.aln[id * KA + q]];
+                out.cons[off + k] = s.code[id];
+                out.cov[off + k] = (uint16_t)c;
+                ok[l] = c >= avg ? 1 : 0;
+            }
+        }
+        const unsigned m = warp_ballot(ok);
+        if (m) {
+            if (first == n) first = base + poa_ffs(m);
+            last = base + poa_fls(m);
+        }
+    }
+    POA_SUB_LAP(15);
+    POA_LANE0 {
+        *out.len = n;
+        *out.off = off;
+        *out.trim = (int32_t)(((uint32_t)(last & 0xFFFF) << 16) | (uint32_t)(first & 0xFFFF)); /* last < 0 reads back as -1 */
+    }
+    POA_SYNC();
 }
 
 /* ------------------------------------------------------------------------------------------
  * int16 safety: every real cell of the skewed matrix must stay far from NEG and from +32767.
- * (spoa switches to int32 with the rule at simd_alignment_engine.cpp:668-673; cudapoa picks the
- * width statically, cudapoa_limits.hpp:34-53.  We report ST_SCORE_RANGE_EXCEEDED instead and let
- * the caller's CPU path handle such a window, like any other per-window failure.)
+ * In the skewed domain S = H - j*gap a horizontal step costs 0, a diagonal step costs (s - gap), a vertical step
+ * costs gap, and the value of a real cell is the score of SOME path from (0,0): it visits at most `n_columns`
+ * graph nodes (a path crosses every aligned clique at most once) and makes at most min(len, n_columns) diagonal
+ * steps.  Hence
+ *     S >= n_columns * min(gap, match - gap, mismatch - gap, 0)
+ *     S <= min(len, n_columns) * max(match - gap, mismatch - gap, 0) + n_columns * max(gap, 0)
+ * for banded and full-band fills alike.  Inside these limits no cell is ever clamped and the int16 matrix equals
+ * spoa's, whichever width spoa itself picks (its own rule, simd_alignment_engine.cpp:668-673, is the cruder
+ * max|score| * (nodes + len + 17) < 32767; cudapoa picks the width statically, cudapoa_limits.hpp:34-53).
+ * Outside them the window reports ST_SCORE_RANGE_EXCEEDED.
  * ---------------------------------------------------------------------------------------- */
-POA_FN bool score_range_ok(const Params& p, int32_t n_nodes, int32_t len) {
-    int32_t mn = p.match < p.mismatch ? p.match : p.mismatch;
-    if (p.gap < mn) mn = p.gap;
-    if (mn > 0) mn = 0;
-    int32_t mx = p.match > p.mismatch ? p.match : p.mismatch;
-    if (p.gap > mx) mx = p.gap;
-    if (mx < 0) mx = 0;
-    const int64_t steps = (int64_t)n_nodes + len + 1;
-    const int64_t lo = (int64_t)mn * steps - (p.gap > 0 ? (int64_t)p.gap * (len + 1) : 0);
-    const int64_t hi = (int64_t)mx * steps + (p.gap < 0 ? (int64_t)(-p.gap) * (len + 1) : 0);
+POA_FN bool score_range_ok(const Params& p, int32_t n_columns, int32_t len) {
     const int32_t mg = p.match - p.gap, xg = p.mismatch - p.gap; /* the fill keeps them as int8 */
-    if (mg < -128 || mg > 127 || xg < -128 || xg > 127) return false;
+    if (mg < -128 || mg > 127 || xg < -128 || xg > 127 || p.gap < -128 || p.gap > 127) return false;
+    int32_t lo_step = p.gap < 0 ? p.gap : 0;
+    if (mg < lo_step) lo_step = mg;
+    if (xg < lo_step) lo_step = xg;
+    int32_t hi_diag = mg > xg ? mg : xg;
+    if (hi_diag < 0) hi_diag = 0;
+    const int64_t lo = (int64_t)lo_step * n_columns;
+    const int64_t hi = (int64_t)hi_diag * (len < n_columns ? len : n_columns) + (p.gap > 0 ? (int64_t)p.gap * n_columns : 0);
     return lo > NEG + 512 && hi < 32000;
 }
 
@@ -1802,20 +1875,25 @@ POA_FN bool score_range_ok(const Params& p, int32_t n_nodes, int32_t len) {
  * ---------------------------------------------------------------------------------------- */
 template <class Fill>
 POA_FN void process_window(const Slot& s, const Params& p, const WindowView& wv, Fill& fill, const TbScratch& tbs,
-                           uint8_t* out_cons, uint16_t* out_cov, int32_t* out_len,
-                           int32_t* out_status, PhaseTimer tm = PhaseTimer{nullptr, 0}) {
+                           const WindowOut& out, PhaseTimer tm = PhaseTimer{nullptr, 0}) {
     WinState st;
     st.n_nodes = 0;
     st.n_edges = 0;
+    st.n_columns = 0;
     st.status = ST_SUCCESS;
     const int32_t len0 = (int32_t)(wv.seq_off[1] - wv.seq_off[0]);
     tm.start();
-    init_backbone(s, p, st, wv.bases + wv.seq_off[0], wv.weights + wv.seq_off[0], len0);
+    {
+        const int64_t wo = wv.w_off[0];
+        init_backbone(s, p, st, wv.bases + wv.seq_off[0], wo >= 0 ? wv.weights + wo : nullptr, wo >= 0 ? 0 : (int32_t)(-1 - wo), len0);
+    }
     for (int32_t r = 1; r < wv.n_seqs && st.status == ST_SUCCESS; ++r) {
         const uint8_t* read = wv.bases + wv.seq_off[r];
-        const int8_t* wt = wv.weights + wv.seq_off[r];
+        const int64_t wo = wv.w_off[r];
+        const int8_t* wt = wo >= 0 ? wv.weights + wo : nullptr;
+        const int32_t wconst = wo >= 0 ? 0 : (int32_t)(-1 - wo);
         const int32_t len = (int32_t)(wv.seq_off[r + 1] - wv.seq_off[r]);
-        if (!score_range_ok(p, st.n_nodes, len)) {
+        if (!score_range_ok(p, st.n_columns, len)) {
             st.status = ST_SCORE_RANGE_EXCEEDED;
             break;
         }
@@ -1846,18 +1924,22 @@ POA_FN void process_window(const Slot& s, const Params& p, const WindowView& wv,
         const int32_t tb = traceback(s, p, st, g, read, end_row, tbs, partial ? s.sub_at : s.node_at);
         tm.lap(PH_TRACEBACK);
         if (st.status != ST_SUCCESS) break;
-        add_alignment(s, p, st, read, wt, len, tb);
+        add_alignment(s, p, st, read, wt, wconst, len, tb);
         tm.lap(PH_ADD);
         if (st.status != ST_SUCCESS) break;
         if (p.serial_topsort) topsort_serial(s, p, st);
         else topsort_roots(s, p, st);
         tm.lap(PH_TOPSORT);
     }
-    if (st.status == ST_SUCCESS) generate_consensus(s, p, st, out_cons, out_cov, out_len);
+    if (st.status == ST_SUCCESS) generate_consensus(s, p, st, out);
     tm.lap(PH_CONSENSUS);
     POA_LANE0 {
-        if (st.status != ST_SUCCESS) *out_len = 0;
-        *out_status = st.status;
+        if (st.status != ST_SUCCESS) {
+            *out.len = 0;
+            *out.off = 0;
+            *out.trim = (int32_t)0xFFFF0000u; /* first 0, last -1 */
+        }
+        *out.status = st.status;
     }
     POA_SYNC();
 }

@@ -356,6 +356,203 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
     return end_row;
 }
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Full-band rows (every row starts at column 0): ONE pass per row, whatever the read length.
+ * Lane l owns the 8*NV consecutive columns [l*8*NV, (l+1)*8*NV) -- NV 128-bit vectors -- so a row costs one
+ * record decode, one profile load, one in-lane scan over 4*NV packed registers and ONE 5-step warp scan,
+ * instead of NV (and, for reads just over a multiple of 256 columns, NV+1) complete chunk passes.  The only cell a
+ * lane needs from another lane is the one left of its first column (the diagonal operand); inside the lane the
+ * diagonal operand of vector v is carried over from the last cell of vector v-1.  Lanes (and vectors) beyond the
+ * read compute on stale shared memory and are never stored: a prefix max only flows left to right.
+ * All rows have band start 0, so a predecessor is the same lane-private columns of another ring row: no band
+ * tests, no lane shifts.  Must produce exactly the matrix ScalarFill (tests/emu/emu_poa.cpp) produces.
+ * ---------------------------------------------------------------------------------------------- */
+template <int NV>
+__device__ __noinline__ int32_t fill_rows_wide(const FillArgs fa) {
+    int lane;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+    const int N = fa.N;
+    const uint32_t NEG2 = pack2(NEG, NEG);
+    const uint32_t G2 = pack2(fa.gap, fa.gap);
+    const int bw = fa.bw;
+    const size_t stride = (size_t)fa.stride;
+    int16_t* const S = fa.S;
+    const uint32_t* const row_rec = fa.row_rec;
+    const uint32_t* const row_pfill = fa.row_pfill;
+    const int ring_mask = fa.ring_mask;
+    const int R = ring_mask + 1;
+    const int prof_stride = fa.prof_stride;
+    const uint32_t prof_sa = fa.smem_sa + 32u;
+    const uint32_t ring_sa = prof_sa + (((uint32_t)(PROF_ROWS * prof_stride) + 15u) & ~15u);
+    const uint32_t ring_row_bytes = (uint32_t)fa.ring_stride * 2u;
+    const uint32_t far_sa = ring_sa + (uint32_t)R * ring_row_bytes + RING_PAD_FRONT * 2u;
+    const int col0 = lane * (8 * NV);                   /* first column of this lane */
+    const uint32_t c0_sa = ring_sa + (uint32_t)col0 * 2u;
+    const int ring_cols = fa.ring_stride - RING_PAD_FRONT; /* cells a ring row can take after its front pad */
+    int dyn_code = -1;
+
+    __syncwarp();
+    {   /* the four fixed profile rows in one pass; columns beyond the read (up to the lanes' full width) score xg */
+        const int pw = prof_stride;
+#pragma unroll 1
+        for (int col = lane; col < pw; col += 32) {
+            const int ch = (col >= 1 && col <= fa.len) ? (int)fa.read[col - 1] : -1;
+            sts8(prof_sa + (uint32_t)(0 * prof_stride + col), ch == 'A' ? fa.mg : fa.xg);
+            sts8(prof_sa + (uint32_t)(1 * prof_stride + col), ch == 'C' ? fa.mg : fa.xg);
+            sts8(prof_sa + (uint32_t)(2 * prof_stride + col), ch == 'G' ? fa.mg : fa.xg);
+            sts8(prof_sa + (uint32_t)(3 * prof_stride + col), ch == 'T' ? fa.mg : fa.xg);
+        }
+    }
+    /* NEG front pad of every ring row (the cell left of column 0) */
+    if (lane <= R) sts128(ring_sa + (uint32_t)lane * ring_row_bytes, make_uint4(NEG2, NEG2, NEG2, NEG2));
+    /* row 0: S = 0 */
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        const int c = col0 + 8 * v;
+        if (c < bw) *reinterpret_cast<uint4*>(S + c) = make_uint4(0u, 0u, 0u, 0u);
+        if (c + 8 <= ring_cols) sts128(c0_sa + RING_PAD_FRONT * 2u + 16u * v, make_uint4(0u, 0u, 0u, 0u));
+    }
+    uint32_t recA = row_rec[lane];
+    uint32_t recB = row_rec[32 + lane];
+    int pbase = 0;
+    uint32_t predA = row_pfill[lane];
+    uint32_t predB = row_pfill[32 + lane];
+    __syncwarp();
+
+    int best = NEG, end_row = 0;
+    int po = 0;
+    int16_t* Srow = S;
+    const int end_lane = fa.len / (8 * NV), end_cell = fa.len % (8 * NV); /* where column len lives */
+#pragma unroll 1
+    for (int i = 1; i <= N; ++i) {
+        if ((i & 31) == 0) {
+            recA = recB;
+            recB = row_rec[i + 32 + lane];
+        }
+        const uint32_t rec = __shfl_sync(0xffffffffu, recA, i & 31);
+        const int np = rec_npred(rec);
+        const int prow = rec_prow(rec);
+        if (prow == 4) {
+            const int code = rec_code(rec);
+            if (dyn_code != code) {
+                fill_build_dyn_prof_row(prof_sa + (uint32_t)(4 * prof_stride), code, fa.read, fa.len, prof_stride, fa.mg, fa.xg);
+                dyn_code = code;
+            }
+        }
+        Srow += stride;
+        int rel = po - pbase;
+        if (rel + np > 32) {
+            const int src = (lane + rel) & 31;
+            const uint32_t xa = __shfl_sync(0xffffffffu, predA, src);
+            const uint32_t xb = __shfl_sync(0xffffffffu, predB, src);
+            predA = (lane + rel < 32) ? xa : xb;
+            if (rel >= 32) predA = row_pfill[po + lane];
+            pbase = po;
+            predB = row_pfill[po + 32 + lane];
+            rel = 0;
+        }
+        /* profile: 8*NV int8 under this lane's columns, widened to int16 pairs */
+        uint32_t P[4 * NV];
+        {
+            const uint32_t psa = prof_sa + (uint32_t)(prow * prof_stride + col0);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const uint2 Pb = lds64(psa + 8u * v);
+                P[4 * v + 0] = prmt_sext(Pb.x, 0x9180u);
+                P[4 * v + 1] = prmt_sext(Pb.x, 0xB3A2u);
+                P[4 * v + 2] = prmt_sext(Pb.y, 0x9180u);
+                P[4 * v + 3] = prmt_sext(Pb.y, 0xB3A2u);
+            }
+        }
+        uint32_t a[4 * NV];
+#pragma unroll
+        for (int k = 0; k < 4 * NV; ++k) a[k] = NEG2;
+
+#define POA_WIDE_TERM(cell_sa)                                                                         \
+    do {                                                                                               \
+        uint32_t left = lds_u16((cell_sa) - 2u) << 16;                                                 \
+        _Pragma("unroll") for (int v = 0; v < NV; ++v) {                                               \
+            const uint4 V = lds128((cell_sa) + 16u * v);                                               \
+            const uint32_t d0 = __funnelshift_l(left, V.x, 16);                                        \
+            const uint32_t d1 = __funnelshift_l(V.x, V.y, 16);                                         \
+            const uint32_t d2 = __funnelshift_l(V.y, V.z, 16);                                         \
+            const uint32_t d3 = __funnelshift_l(V.z, V.w, 16);                                         \
+            a[4 * v + 0] = __viaddmax_s16x2(d0, P[4 * v + 0], a[4 * v + 0]);                           \
+            a[4 * v + 1] = __viaddmax_s16x2(d1, P[4 * v + 1], a[4 * v + 1]);                           \
+            a[4 * v + 2] = __viaddmax_s16x2(d2, P[4 * v + 2], a[4 * v + 2]);                           \
+            a[4 * v + 3] = __viaddmax_s16x2(d3, P[4 * v + 3], a[4 * v + 3]);                           \
+            a[4 * v + 0] = __viaddmax_s16x2(V.x, G2, a[4 * v + 0]);                                    \
+            a[4 * v + 1] = __viaddmax_s16x2(V.y, G2, a[4 * v + 1]);                                    \
+            a[4 * v + 2] = __viaddmax_s16x2(V.z, G2, a[4 * v + 2]);                                    \
+            a[4 * v + 3] = __viaddmax_s16x2(V.w, G2, a[4 * v + 3]);                                    \
+            left = V.w;                                                                                \
+        }                                                                                              \
+    } while (0)
+
+        if (!rec_far(rec) && np <= 32) {
+#pragma unroll 1
+            for (int q = 0; q < np; ++q) {
+                const uint32_t pe = __shfl_sync(0xffffffffu, predA, rel + q);
+                const uint32_t cell_sa = c0_sa + (uint32_t)((int)pe >> 12);
+                POA_WIDE_TERM(cell_sa);
+            }
+        } else {
+#pragma unroll 1
+            for (int q = 0; q < np; ++q) {
+                uint32_t pe;
+                if (rel + q < 32) pe = __shfl_sync(0xffffffffu, predA, rel + q);
+                else pe = row_pfill[po + q];
+                uint32_t cell_sa = c0_sa + (uint32_t)((int)pe >> 12);
+                if (pe & 1u) { /* predecessor older than the ring: stage its row in the spare slot */
+                    const int pr = (int)(fa.row_pred[po + q] & 0xFFFFu);
+                    fill_stage_far_row(S + (size_t)pr * stride, far_sa, bw);
+                    cell_sa = far_sa + (uint32_t)col0 * 2u;
+                }
+                POA_WIDE_TERM(cell_sa);
+            }
+        }
+#undef POA_WIDE_TERM
+
+        /* inclusive prefix max over the lane's 8*NV cells: inside each register, then register to register */
+        a[0] = __vmaxs2(a[0], __byte_perm(a[0], NEG2, 0x1054));
+#pragma unroll
+        for (int k = 1; k < 4 * NV; ++k)
+            a[k] = __vimax3_s16x2(a[k], __byte_perm(a[k], NEG2, 0x1054), __byte_perm(a[k - 1], a[k - 1], 0x3232));
+        /* ... then across lanes */
+        uint32_t tt = __byte_perm(a[4 * NV - 1], a[4 * NV - 1], 0x3232);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) tt = __vmaxs2(tt, __shfl_up_sync(0xffffffffu, tt, d));
+        uint32_t excl = __shfl_up_sync(0xffffffffu, tt, 1);
+        excl = lane == 0 ? NEG2 : excl;
+#pragma unroll
+        for (int k = 0; k < 4 * NV; ++k) a[k] = __vimax3_s16x2(a[k], excl, NEG2);
+
+        const uint32_t ring_row_sa = c0_sa + RING_PAD_FRONT * 2u + (uint32_t)(i & ring_mask) * ring_row_bytes;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const uint4 out = make_uint4(a[4 * v], a[4 * v + 1], a[4 * v + 2], a[4 * v + 3]);
+            if (col0 + 8 * v < bw) __stcs(reinterpret_cast<uint4*>(Srow + col0 + 8 * v), out);
+            if (col0 + 8 * v + 8 <= ring_cols) sts128(ring_row_sa + 16u * v, out); /* rows are as long as the longest read */
+        }
+        if (rec_sink(rec)) { /* candidate end cell at column len */
+            uint32_t w = a[0];
+#pragma unroll
+            for (int k = 1; k < 4 * NV; ++k)
+                if ((end_cell >> 1) == k) w = a[k];
+            int val = (end_cell & 1) ? ((int)w >> 16) : (int)(int16_t)(w & 0xFFFFu);
+            val = __shfl_sync(0xffffffffu, val, end_lane);
+            if (val > best) {
+                best = val;
+                end_row = i;
+            }
+        }
+        po += np;
+        __syncwarp();
+    }
+    return end_row;
+}
+
 struct CudaFill {
     uint32_t smem_sa;    /* shared-window address of the block's dynamic shared memory */
     int32_t prof_stride;
@@ -382,7 +579,12 @@ struct CudaFill {
         fa.mg = p.match - p.gap;
         fa.xg = p.mismatch - p.gap;
         fa.gap = p.gap;
-        return (g.bw == CHUNK) ? fill_rows<true>(fa) : fill_rows<false>(fa);
+        if (g.banded) return (g.bw == CHUNK) ? fill_rows<true>(fa) : fill_rows<false>(fa);
+        if (g.colsP <= 256) return fill_rows_wide<1>(fa);
+        if (g.colsP <= 512) return fill_rows_wide<2>(fa);
+        if (g.colsP <= 768) return fill_rows_wide<3>(fa);
+        if (g.colsP <= 1024) return fill_rows_wide<4>(fa);
+        return fill_rows<false>(fa); /* longer reads: 256-column chunk passes */
     }
 };
 

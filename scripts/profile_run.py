@@ -14,9 +14,10 @@ ap.add_argument("--length", type=int, default=500)
 ap.add_argument("--depth", type=int, default=32)
 ap.add_argument("--err", type=float, default=0.15)
 ap.add_argument("--mem-gb", type=float, default=24.0)
+ap.add_argument("--max-seq", type=int, default=1023)
 args = ap.parse_args()
 b = synth_windows(args.windows, args.length, args.depth, args.err, seed=12345)
-pb = api.PoaBatch(max_gpu_mem=int(args.mem_gb * (1 << 30)), banded=bool(args.banded))
+pb = api.PoaBatch(max_gpu_mem=int(args.mem_gb * (1 << 30)), banded=bool(args.banded), max_sequence_size=args.max_seq)
 n, _ = pb.add_windows(b)
 assert n == args.windows
 pb.upload()

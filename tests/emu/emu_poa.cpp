@@ -82,7 +82,7 @@ void emu_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int
                         int32_t max_nodes, int32_t max_edges, int32_t max_len, int32_t band_width,
                         int32_t serial_topsort, int32_t n_threads, uint8_t* cons_out,
                         uint16_t* cov_out, int32_t stride_out, int32_t* cons_len, int32_t* status,
-                        int32_t* rank_out, int32_t* n_nodes_out, int64_t* cells_out) {
+                        int32_t* rank_out, int32_t* n_nodes_out, int64_t* cells_out, int32_t* trim_out) {
     Params p;
     p.max_nodes = max_nodes;
     p.max_edges = max_edges;
@@ -109,7 +109,7 @@ void emu_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int
         slot_bind(s, reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(slab.data()) + 255) & ~uintptr_t(255)), p, nullptr);
         std::vector<uint8_t> wbases;
         std::vector<int8_t> wweights;
-        std::vector<int64_t> woff;
+        std::vector<int64_t> woff, wwoff;
         std::vector<int32_t> wbeg, wend;
         ScalarFill fill;
         std::vector<uint8_t> tb_mem(TB_SCRATCH_BYTES + 64);
@@ -123,6 +123,7 @@ void emu_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int
             wbases.clear();
             wweights.clear();
             woff.assign(1, 0);
+            wwoff.clear();
             wbeg.clear();
             wend.clear();
             const uint32_t L0 = (uint32_t)(seq_off[s0 + order[s0] + 1] - seq_off[s0 + order[s0]]);
@@ -133,8 +134,12 @@ void emu_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int
                 const int64_t a = seq_off[sq], b = seq_off[sq + 1];
                 if (b - a > max_len) too_long = true;
                 wbases.insert(wbases.end(), bases + a, bases + b);
-                if (has_weights[sq]) wweights.insert(wweights.end(), weights + a, weights + b);
-                else wweights.insert(wweights.end(), (size_t)(b - a), (int8_t)1);
+                if (has_weights[sq]) { /* explicit weights live in the compact arena ... */
+                    wwoff.push_back((int64_t)wweights.size());
+                    wweights.insert(wweights.end(), weights + a, weights + b);
+                } else {
+                    wwoff.push_back(-1 - 1); /* ... a sequence without quality weighs 1 per base and ships none */
+                }
                 woff.push_back((int64_t)wbases.size());
                 /* window.cpp:92-93: full-span test (the product's host library applies the same rule) */
                 const bool full = k == 0 || !begins ||
@@ -152,11 +157,23 @@ void emu_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int
             wv.bases = wbases.data();
             wv.weights = wweights.data();
             wv.seq_off = woff.data();
+            wv.w_off = wwoff.data();
             wv.seq_begin = wbeg.data();
             wv.seq_end = wend.data();
             /* process_window writes its node count nowhere; recover it from the slot afterwards */
-            process_window(s, p, wv, fill, tbs, cons_out + w * (int64_t)stride_out,
-                           cov_out + w * (int64_t)stride_out, &cons_len[w], &status[w]);
+            uint32_t cursor = 0;
+            int32_t off = 0, trim = 0;
+            WindowOut out;
+            out.cons = cons_out + w * (int64_t)stride_out; /* this window's row is its own arena */
+            out.cov = cov_out + w * (int64_t)stride_out;
+            out.cursor = &cursor;
+            out.len = &cons_len[w];
+            out.status = &status[w];
+            out.off = &off;
+            out.trim = &trim;
+            out.trim_nseq = n;
+            process_window(s, p, wv, fill, tbs, out);
+            if (trim_out) trim_out[w] = trim;
             if (rank_out || n_nodes_out) {
                 /* n_nodes = 1 + max rank_of over nodes is not stored; count nodes via root != unset:
                  * simplest is to re-derive from node_at being a permutation of [0, N). */

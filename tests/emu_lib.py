@@ -27,12 +27,14 @@ class Emu:
         clen = np.zeros(W, dtype=np.int32)
         st = np.zeros(W, dtype=np.int32)
         cells = C.c_int64(0)
+        self.last_trim = np.zeros(W, dtype=np.int32)  # device-side trim interval: first | last << 16
         order = np.ascontiguousarray(order, dtype=np.int32)
         a = _flat_args(b)
         self.lib.emu_polish_windows(
             a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], _p(order, C.c_int32), C.c_int32(m), C.c_int32(x), C.c_int32(g),
             C.c_int32(max_nodes), C.c_int32(max_edges), C.c_int32(max_len), C.c_int32(band),
             C.c_int32(int(serial_topsort)), C.c_int32(threads), _p(cons, C.c_uint8), _p(cov, C.c_uint16),
-            C.c_int32(stride), _p(clen, C.c_int32), _p(st, C.c_int32), None, None, C.byref(cells))
+            C.c_int32(stride), _p(clen, C.c_int32), _p(st, C.c_int32), None, None, C.byref(cells),
+            _p(self.last_trim, C.c_int32))
         return ([cons[w, :clen[w]].tobytes() for w in range(W)], [cov[w, :clen[w]].copy() for w in range(W)],
                 st, cells.value)

@@ -263,3 +263,98 @@ def test_windows_built_in_the_columnar_arena_polish_like_the_oracle(oracle):
     pol.close()
     arena.close()
     assert polished.all() and api.consensus_list(cons, clen) == oc
+
+
+def test_windows_the_batch_limits_cut_come_back_as_backbone_never_as_holes(oracle):
+    """a window with < 3 sequences, or whose layers (or backbone) the batch limits dropped, is reported
+    unpolished and holds its backbone (window.cpp:68-71 / cudapolisher.cpp:354-383 leave it to the CPU path); with
+    accept_truncated the polisher does what the reference GPU adapter does (cudabatch.cpp:134-153, 232-233)."""
+    deep = synth_windows(3, 200, 9, 0.1, seed=71)              # 10 sequences per window
+    seqs, wts, bg, en = deep.window(0)
+    two = [(seqs[0], wts[0], 0, 0), (seqs[1], None, 0, len(seqs[0]) - 1)]
+    long_layer = [(s, w, b, e) for s, w, b, e in zip(*deep.window(1))]
+    long_layer[3] = (long_layer[3][0] * 8, None, long_layer[3][2], long_layer[3][3])      # 1600 bases > 1023
+    plain = [(s, w, b, e) for s, w, b, e in zip(*deep.window(2))]
+    b = WindowBatch.from_lists([two, long_layer, plain])
+    order = api.processing_order(b)
+    oc, _, _ = oracle.polish(b, order, M, X, G, tgs=True, trim=True, threads=4)
+    bb = [b.window(w)[0][0] for w in range(3)]
+    # exact mode (default): only the untouched window is polished
+    pol = api.Polisher(devices=[0], mem_per_batch=MEM)
+    cons, clen, polished, status = pol.polish(b, tgs=True, trim=True)
+    pol.close()
+    got = api.consensus_list(cons, clen)
+    assert polished.tolist() == [False, False, True]
+    assert got[0] == bb[0] and got[1] == bb[1] and got[2] == oc[2]
+    assert status[1] == api.EXCEEDED_MAXIMUM_SEQUENCE_SIZE
+    # depth limit 4 -> every deep window is cut; exact mode returns backbones, reference mode polishes the prefix
+    pol = api.Polisher(devices=[0], mem_per_batch=MEM, max_sequences_per_poa=4)
+    cons, clen, polished, status = pol.polish(b, tgs=True, trim=True)
+    pol.close()
+    assert polished.tolist() == [False, False, False] and api.consensus_list(cons, clen) == bb
+    assert status[2] == api.EXCEEDED_MAXIMUM_SEQUENCES_PER_POA
+    pol = api.Polisher(devices=[0], mem_per_batch=MEM, max_sequences_per_poa=4, accept_truncated=True)
+    cons, clen, polished, status = pol.polish(b, tgs=True, trim=True)
+    pol.close()
+    assert polished.tolist() == [False, True, True]
+    # the truncated result is the consensus of the first 4 sequences in processing order, trimmed at (4 - 1) / 2
+    s0 = int(b.win_seq_off[2])
+    keep = [int(i) for i in order[s0:s0 + 4]]
+    sub = WindowBatch.from_lists([[plain[i] for i in keep]])
+    tc, _, _ = oracle.polish(sub, identity_order(sub), M, X, G, tgs=True, trim=True, threads=1)
+    assert api.consensus_list(cons, clen)[2] == tc[0]
+    # the Python mirror of the adapter applies the same rule
+    proc = api.CUDABatchProcessor(avail_mem=MEM)
+    assert proc.add_windows(b) == 3
+    out, ok = proc.generate_consensus()
+    assert ok == [False, False, True] and out == [bb[0], bb[1], oc[2]]
+    # a backbone longer than the limit: nothing is staged for the window, the status says why
+    pb = api.PoaBatch(max_gpu_mem=MEM)
+    st, per = pb.add_poa_group([(b"ACGT" * 300, None), (b"ACGTACGTAC", None), (b"ACGTACGTAC", None)])
+    assert st == 0 and per == [2, 2, 2]
+    pb.generate_poa()
+    cons, _, status = pb.get_consensus()
+    pb.close()
+    assert status.tolist() == [api.EXCEEDED_MAXIMUM_SEQUENCE_SIZE] and cons == [b""]
+
+
+def test_device_side_trim_and_compact_outputs_match_the_host_rule(oracle):
+    """The trim span computed by the kernel (WindowOut::trim) is window.cpp:118-139's, the compact D2H moves exactly
+    sum(len) elements, and sequences with constant weights ship no weight bytes."""
+    b = synth_windows(64, 300, 12, 0.12, seed=73)             # backbone weight 0 ('!'), reads without quality
+    pb = api.PoaBatch(max_gpu_mem=MEM)
+    n, _ = pb.add_windows(b)
+    pb.generate_poa()
+    cons, cov, st, trim = pb.get_consensus(with_trim=True)
+    info = pb.info()
+    pb.close()
+    assert (st == 0).all()
+    for c, v, (tb, te) in zip(cons, cov, trim):
+        want, chimeric = api.trim_consensus(c, v, 13)
+        assert (c if tb >= te else c[tb:te + 1]) == want
+    n_bases = int(b.seq_off[-1])
+    assert info["h2d_bytes"] < n_bases + 64 * 13 * 40          # bases + tables, no weight bytes
+    assert info["d2h_bytes"] <= 3 * sum((len(c) + 15) // 16 * 16 for c in cons) + 64 * 16 + 8
+    q = synth_windows(16, 300, 12, 0.12, seed=73, with_quality=True)  # real qualities do travel
+    pb = api.PoaBatch(max_gpu_mem=MEM)
+    pb.add_windows(q)
+    pb.generate_poa()
+    pb.get_consensus()
+    assert pb.info()["h2d_bytes"] > 1.8 * int(q.seq_off[-1]) - 16 * 320
+    pb.close()
+
+
+def test_single_process_multi_device_polisher(oracle):
+    """racon's own model: ONE process, batch processors on every device (cudapolisher.cpp:228-240).  Needs >= 2 GPUs."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("one visible device")
+    b = synth_windows(600, 300, 10, 0.1, seed=79)
+    order = api.processing_order(b)
+    oc, _, _ = oracle.polish(b, order, M, X, G, tgs=True, trim=True, threads=16)
+    pol = api.Polisher(devices=list(range(n)), batches_per_device=2, mem_per_batch=MEM)
+    cons, clen, polished, status = pol.polish(b, tgs=True, trim=True, max_windows_per_round=40)
+    launches = pol.last["kernel_launches"]
+    pol.close()
+    assert polished.all() and api.consensus_list(cons, clen) == oc and launches >= 15

@@ -65,10 +65,13 @@ def test_cudapoa_sample_windows(oracle):
     """vendor/GenomeWorks/cudapoa/data/sample-windows.txt: 67 windows, depth 105-170.  Full band: consensus and
     coverage of the unmodified reference's spoa path; static band within the stated tolerance."""
     b, cons, cov = cudapoa_fixture()
+    wins = [b.window(w)[0] for w in range(b.n_windows)]
     for banded in (False, True):
         pb = api.PoaBatch(max_gpu_mem=MEM, banded=banded)
-        n, added = pb.add_windows(b)
-        assert n == 67 and (np.asarray(added) == np.diff(b.win_seq_off) - 1).all()
+        for seqs in wins:  # file order IS the processing order here (cudapoa's add_poa_group contract)
+            st, per = pb.add_poa_group([(s, None) for s in seqs])
+            assert st == 0 and all(x == 0 for x in per)
+        assert pb.get_total_poas() == 67
         pb.generate_poa()
         gc, gcov, st = pb.get_consensus()
         pb.close()

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from racon_gpu_b200.shard import gather_consensus, shard_range
+from racon_gpu_b200.shard import ConsensusGather, assemble, gather_consensus, shard_range
 
 
 def test_shard_ranges_partition_the_windows():
@@ -29,12 +29,27 @@ def _worker(rank, world, port, n_windows, ret):
     rng = np.random.default_rng(1234)  # same stream on every rank: row w is a function of w only
     all_len = rng.integers(1, stride, size=n_windows).astype(np.int32)
     all_rows = rng.integers(65, 90, size=(n_windows, stride)).astype(np.uint8)
-    cons, clen = gather_consensus(all_rows[lo:hi].copy(), all_len[lo:hi].copy(), torch.device("cpu"))
+    want = b"".join(all_rows[w, :all_len[w]].tobytes() for w in range(n_windows))
+    flat, off = gather_consensus(all_rows[lo:hi].copy(), all_len[lo:hi].copy(), torch.device("cpu"))
+    ok = True
     if rank == 0:
-        same = all((cons[w, :all_len[w]] == all_rows[w, :all_len[w]]).all() for w in range(n_windows))
-        ret["ok"] = bool(same and (clen == all_len).all() and cons.shape == (n_windows, int(all_len.max())))
+        ok = flat.tobytes() == want and (np.diff(off) == all_len).all()
     else:
-        assert cons is None and clen is None
+        assert flat is None and off is None
+    # the pipelined form: two steps in flight one after the other, only compact bytes travel
+    g = ConsensusGather(torch.device("cpu"), hi - lo)
+    for step in range(2):
+        rows = np.roll(all_rows, step, axis=1)
+        g.start(rows[lo:hi].copy(), all_len[lo:hi].copy())
+        parts = g.wait()
+        if rank == 0:
+            f2, o2 = assemble(parts)
+            ok = ok and f2.tobytes() == b"".join(rows[w, :all_len[w]].tobytes() for w in range(n_windows))
+            ok = ok and sum(p[1].shape[0] for p in parts) == int(all_len.sum())
+        else:
+            assert parts is None
+    if rank == 0:
+        ret["ok"] = bool(ok)
     dist.barrier()
     dist.destroy_process_group()
 
