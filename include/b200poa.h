@@ -60,8 +60,10 @@ enum {
     B200POA_CUDA_ERROR = 16              /* what the C++ API reports by aborting in GW_CU_CHECK_ERR */
 };
 
-/* cudapoa::BandMode (cudapoa.hpp:47-53); adaptive_band is not selectable from racon (cudabatch.cpp:59) */
-enum { B200POA_FULL_BAND = 0, B200POA_STATIC_BAND = 1 };
+/* cudapoa::BandMode (cudapoa.hpp:47-53).  adaptive_band is not selectable from racon (cudabatch.cpp:59); here it
+ * means: align with alignment_band_width first and re-align a read with twice the width whenever its traceback comes
+ * close to the band's edge (cudapoa's retry protocol, cudapoa_kernels.cuh:257-303), up to the full matrix. */
+enum { B200POA_FULL_BAND = 0, B200POA_STATIC_BAND = 1, B200POA_ADAPTIVE_BAND = 2 };
 
 /* cudapoa::OutputType (cudapoa.hpp:59-63); racon asks for consensus only (cudabatch.cpp:64) */
 enum { B200POA_OUTPUT_CONSENSUS = 0x1, B200POA_OUTPUT_MSA = 0x2 };
@@ -73,7 +75,7 @@ typedef struct b200poa_config {
     int32_t max_nodes_per_graph;   /* 3x (full band) / 4x (static band) max_sequence_size */
     int32_t alignment_band_width;  /* racon: 256 */
     int32_t max_sequences_per_poa; /* racon: 200 (cudapolisher.cpp:226) */
-    int32_t band_mode;             /* B200POA_FULL_BAND | B200POA_STATIC_BAND */
+    int32_t band_mode;             /* B200POA_FULL_BAND | B200POA_STATIC_BAND | B200POA_ADAPTIVE_BAND */
 } b200poa_config;
 
 /* cudapoa::Entry (batch.hpp:45-53) + the layer span racon's Window knows (window.hpp:73) */
@@ -225,7 +227,7 @@ typedef struct b200poa_polisher_options {
     const int32_t* device_ids;
     int32_t batches_per_device;
     size_t mem_per_batch;
-    int32_t banded;
+    int32_t banded;                /* 0 full band, 1 static band (racon -b), 2 adaptive band */
     int32_t match, mismatch, gap;
     int32_t max_sequence_size;
     int32_t max_sequences_per_poa;

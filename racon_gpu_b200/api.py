@@ -28,6 +28,7 @@ EXCEEDED_MAXIMUM_SEQUENCES_PER_POA = 3
 PARTIAL_SPAN_UNSUPPORTED = 14
 FULL_BAND = 0
 STATIC_BAND = 1
+ADAPTIVE_BAND = 2
 OUTPUT_CONSENSUS = 1
 
 #: every symbol include/b200poa.h declares (tests check the library exports all of them)
@@ -94,6 +95,12 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     return lib
 
 
+def _band_mode(banded) -> int:
+    if banded == "adaptive" or banded == ADAPTIVE_BAND and banded is not True:
+        return ADAPTIVE_BAND
+    return STATIC_BAND if banded else FULL_BAND
+
+
 def status_string(st: int) -> str:
     return load_library().b200poa_status_string(C.c_int32(int(st))).decode()
 
@@ -123,13 +130,14 @@ class PoaBatch:
 
     def __init__(self, device: int = 0, stream: int = 0, max_gpu_mem: int = 8 << 30,
                  max_sequence_size: int = 1023, max_sequences_per_poa: int = 200,
-                 band_width: int = 256, banded: bool = False, gap: int = -4, mismatch: int = -5,
+                 band_width: int = 256, banded=False, gap: int = -4, mismatch: int = -5,
                  match: int = 3, output_mask: int = OUTPUT_CONSENSUS):
+        """banded: False = full band, True = static band, "adaptive" = adaptive band (retry with twice the width)."""
         self.lib = load_library()
         self.cfg = Config()
         self.lib.b200poa_config_default(C.byref(self.cfg), C.c_int32(max_sequence_size),
                                         C.c_int32(max_sequences_per_poa), C.c_int32(band_width),
-                                        C.c_int32(STATIC_BAND if banded else FULL_BAND))
+                                        C.c_int32(_band_mode(banded)))
         self.handle = C.c_void_p()
         st = self.lib.b200poa_batch_create(C.c_int32(device), C.c_void_p(stream), C.c_size_t(max_gpu_mem),
                                            C.c_int32(output_mask), C.byref(self.cfg), C.c_int16(gap),
@@ -403,7 +411,7 @@ class Polisher:
         dev = np.asarray(devices if devices is not None else [], dtype=np.int32)
         self.handle = C.c_void_p()
         opt = PolisherOptions(dev.shape[0], _p(dev, C.c_int32) if dev.shape[0] else None, batches_per_device,
-                              mem_per_batch, int(banded), match, mismatch, gap, max_sequence_size,
+                              mem_per_batch, _band_mode(banded), match, mismatch, gap, max_sequence_size,
                               max_sequences_per_poa, band_width, int(accept_truncated))
         st = self.lib.b200poa_polisher_create_ex(C.byref(opt), C.byref(self.handle))
         if st != SUCCESS:

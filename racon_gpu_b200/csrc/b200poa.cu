@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(32, POA_MIN_BLOCKS_PER_SM) poa_window_kernel(c
     for (;;) {
         int32_t t = 0;
         if (lane == 0) t = atomicAdd(a.cursor, 1);
-        t = __shfl_sync(0xffffffffu, t, 0);
+        t = warp_bcast0(t); /* through redux.sync: the work loop is provably warp-uniform (poa_simt.cuh) */
         if (t >= a.n_windows) break;
         const int32_t w = a.work[t];
         if (a.win_flags[w] != 0) {
@@ -92,6 +92,8 @@ __global__ void __launch_bounds__(32, POA_MIN_BLOCKS_PER_SM) poa_window_kernel(c
                 a.out_trim[w] = (int32_t)0xFFFF0000u;
                 a.out_status[w] = a.win_flags[w];
             }
+            __syncwarp(); /* explicit reconvergence before the back edge: without it ptxas assumes a diverged loop head
+                             and gives EVERY collective of the kernel a BRA.DIV slow path (poa_simt.cuh) */
             continue;
         }
         WindowView wv;
@@ -230,7 +232,7 @@ struct SmemGeometry {
 static SmemGeometry smem_geometry(const Params& p, int32_t max_len) {
     SmemGeometry g;
     const int32_t colsP = (max_len + 1 + 7) & ~7;
-    const bool banded = p.band_width > 0 && p.band_width < colsP;
+    const bool banded = !p.adaptive && p.band_width > 0 && p.band_width < colsP;
     /* fill_rows_wide (full-band rows, and reads shorter than the band in banded batches) gives lane l the columns
      * [l*8*NV, (l+1)*8*NV): lanes past the read still load -- never store -- profile bytes and ring cells up to
      * column 256*NV.  Rows are therefore sized by the longest read only, and the allocation ends with enough slack
@@ -490,7 +492,8 @@ int32_t b200poa_batch_create(int32_t device_id, void* stream, size_t max_gpu_mem
     if (cfg->max_sequence_size <= 0 || cfg->max_sequences_per_poa <= 0 || cfg->alignment_band_width < 0 ||
         cfg->max_nodes_per_graph < cfg->max_sequence_size || cfg->max_consensus_size < cfg->max_sequence_size ||
         cfg->max_nodes_per_graph > 32768 || cfg->max_sequence_size > 16380 ||
-        (cfg->band_mode != B200POA_FULL_BAND && cfg->band_mode != B200POA_STATIC_BAND))
+        (cfg->band_mode != B200POA_FULL_BAND && cfg->band_mode != B200POA_STATIC_BAND &&
+         cfg->band_mode != B200POA_ADAPTIVE_BAND))
         return B200POA_INVALID_ARGUMENT;
     if (max_gpu_mem == 0) return B200POA_INVALID_ARGUMENT; /* Test_CudapoaBatch.cu: zero memory throws */
     int ndev = 0;
@@ -507,11 +510,13 @@ int32_t b200poa_batch_create(int32_t device_id, void* stream, size_t max_gpu_mem
 
     Params& p = b->p;
     p.max_nodes = cfg->max_nodes_per_graph;
-    p.max_edges = std::min(6 * cfg->max_nodes_per_graph, 65000);
+    p.max_edges = poa_edge_capacity(cfg->max_nodes_per_graph);
     p.max_len = cfg->max_sequence_size;
     const int32_t colsP = (p.max_len + 1 + 7) & ~7;
-    p.band_width = (cfg->band_mode == B200POA_STATIC_BAND) ? ((cfg->alignment_band_width + 7) & ~7) : 0;
-    p.stride = (p.band_width > 0 && p.band_width < colsP) ? p.band_width : colsP;
+    p.band_width = (cfg->band_mode != B200POA_FULL_BAND) ? ((cfg->alignment_band_width + 7) & ~7) : 0;
+    p.adaptive = cfg->band_mode == B200POA_ADAPTIVE_BAND ? 1 : 0;
+    /* score rows: the band in static mode; whole rows in full and adaptive mode (a retry may widen up to the matrix) */
+    p.stride = (!p.adaptive && p.band_width > 0 && p.band_width < colsP) ? p.band_width : colsP;
     p.max_cons = cfg->max_consensus_size;
     p.match = match_score;
     p.mismatch = mismatch_score;

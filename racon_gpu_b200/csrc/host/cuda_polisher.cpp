@@ -152,7 +152,8 @@ extern "C" int32_t b200poa_polisher_create_ex(const b200poa_polisher_options* op
     b200poa_config cfg; /* cudabatch.cpp:56-59: BatchConfig(1023, max_depth 200, 256, band mode) unless overridden */
     b200poa_config_default(&cfg, opt->max_sequence_size > 0 ? opt->max_sequence_size : 1023,
                            opt->max_sequences_per_poa > 0 ? opt->max_sequences_per_poa : 200,
-                           opt->band_width > 0 ? opt->band_width : 256, opt->banded ? B200POA_STATIC_BAND : B200POA_FULL_BAND);
+                           opt->band_width > 0 ? opt->band_width : 256,
+                           opt->banded == 2 ? B200POA_ADAPTIVE_BAND : opt->banded ? B200POA_STATIC_BAND : B200POA_FULL_BAND);
     h->max_sequences_per_poa = cfg.max_sequences_per_poa;
     for (int32_t dev : devices) {
         const size_t mem = batch_memory(dev, nb, opt->mem_per_batch);

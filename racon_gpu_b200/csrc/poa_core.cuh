@@ -77,7 +77,8 @@ enum Status : int32_t {
 
 struct Params {
     int32_t max_nodes;   /* MN : node capacity of a slot            */
-    int32_t max_edges;   /* ME : edge pool capacity                 */
+    int32_t max_edges;   /* ME : edge pool capacity == poa_edge_capacity(max_nodes): the phases derive it from max_nodes
+                            instead of keeping one more warp-uniform value alive (poa_simt.cuh) */
     int32_t max_len;     /* longest sequence accepted               */
     int32_t stride;      /* int16 cells per score row (multiple of 8) */
     int32_t band_width;  /* 0 = full band, else W (multiple of 8)   */
@@ -86,7 +87,17 @@ struct Params {
     int32_t serial_topsort; /* tests: use the serial DFS instead of the per-root sort */
     int32_t ring_rows;      /* fill: rows in the shared-memory score ring (power of two) */
     int32_t ring_stride;    /* fill: int16 cells per ring row */
+    int32_t adaptive;       /* band_width is only the FIRST try of a read: a traceback that comes close to the band's
+                               edge re-aligns the read with twice the width (cudapoa's retry protocol,
+                               cudapoa_kernels.cuh:257-303, cudapoa_nw_adaptive_banded.cuh:265-281, 462-480) */
 };
+
+#if POA_DEVICE
+__host__ __device__ __forceinline__
+#else
+static inline
+#endif
+int32_t poa_edge_capacity(int32_t max_nodes) { return 6 * max_nodes < 65000 ? 6 * max_nodes : 65000; }
 
 /* Per resident warp workspace.  All pointers are into one device slab (see slot_bytes()). */
 struct Slot {
@@ -250,7 +261,18 @@ struct WinState {
     int32_t n_edges;
     int32_t status;
     int32_t n_columns; /* aligned cliques (a node without aligned mates counts as one): no path visits more nodes */
+    int32_t band_hit;  /* traceback: the path came within TB_EDGE_MARGIN columns of a band edge that is not a matrix edge */
 };
+
+/* After a phase function has updated the state through its reference (local memory, which the compiler must assume
+ * lane-dependent), pass the scalars through poa_uniform() so that the caller's control flow stays provably uniform. */
+POA_FN void winstate_uniform(WinState& st) {
+    st.n_nodes = poa_uniform(st.n_nodes);
+    st.n_edges = poa_uniform(st.n_edges);
+    st.status = poa_uniform(st.status);
+    st.n_columns = poa_uniform(st.n_columns);
+    st.band_hit = poa_uniform(st.band_hit);
+}
 
 /* optional per-phase cycle counters (diagnostics: B200POA_PHASE_TIMERS=1), device flavour only */
 enum Phase { PH_PROGRAM = 0, PH_FILL, PH_TRACEBACK, PH_ADD, PH_TOPSORT, PH_CONSENSUS, PH_OTHER, PH_COUNT };
@@ -294,10 +316,12 @@ __device__ unsigned long long g_subtimers[32];
 /* ------------------------------------------------------------------------------------------
  * Phase 0: backbone chain  (graph.cpp:274-292 add_sequence + :177-185; window.cpp:73-76)
  * ---------------------------------------------------------------------------------------- */
-POA_FN_NOINLINE void init_backbone(const Slot& s_ref, const Params& p_ref, WinState& st, const uint8_t* seq,
+POA_FN_NOINLINE void init_backbone(const Slot& s_ref, const Params p_ref, WinState& st, const uint8_t* seq,
                           const int8_t* w, int32_t wconst, int32_t len) {
     const Slot s = s_ref;     /* local copies: no reloads of the descriptor after every store */
     const Params p = p_ref;
+    len = poa_uniform(len);
+    wconst = poa_uniform(wconst);
     if (len > p.max_nodes || len - 1 > p.max_edges) {
         st.status = ST_SEQ_LEN_EXCEEDED_MAX_NODES;
         return;
@@ -400,17 +424,30 @@ struct ReadGeom {
     uint32_t step;  /* band centre advance per row, 16.16 fixed point: (len << 16) / n_rows */
 };
 
-POA_FN ReadGeom read_geometry(const Params& p, int32_t len, int32_t n_rows) {
+POA_FN ReadGeom read_geometry(const Params& p, int32_t len, int32_t n_rows, int32_t band_width) {
     ReadGeom g;
+    (void)p;
     g.len = len;
     g.n_rows = n_rows;
     g.colsP = (len + 1 + 7) & ~7;
-    g.banded = (p.band_width > 0 && g.colsP > p.band_width) ? 1 : 0;
-    g.bw = g.banded ? p.band_width : g.colsP;
+    g.banded = (band_width > 0 && g.colsP > band_width) ? 1 : 0;
+    g.bw = g.banded ? band_width : g.colsP;
     g.step = ((uint32_t)len << 16) / (uint32_t)(n_rows > 0 ? n_rows : 1); /* len < 2^15 by the config limits */
     return g;
 }
 
+/* Copies of the geometry / parameters a phase function received by reference (i.e. through local memory, which
+ * the compiler must treat as lane-dependent), laundered through poa_uniform(): see poa_simt.cuh. */
+POA_FN ReadGeom geom_uniform(const ReadGeom& r) {
+    ReadGeom g;
+    g.len = poa_uniform(r.len);
+    g.colsP = poa_uniform(r.colsP);
+    g.bw = poa_uniform(r.bw);
+    g.banded = poa_uniform(r.banded);
+    g.n_rows = poa_uniform(r.n_rows);
+    g.step = (uint32_t)poa_uniform((int32_t)r.step); /* < 2^31: len < 2^15 */
+    return g;
+}
 /* Static band: centred on the (0,0)-(n_rows,len) diagonal.  One division per read (ReadGeom::step), a multiply per
  * row: every phase recomputes a row's band start with this function instead of loading it. */
 POA_FN int32_t band_start(const ReadGeom& g, int32_t row, int32_t n_rows) {
@@ -423,12 +460,12 @@ POA_FN int32_t band_start(const ReadGeom& g, int32_t row, int32_t n_rows) {
     return bs & ~7;
 }
 
-POA_FN_NOINLINE void build_program(const Slot& s_ref, const Params& p_ref, WinState& st, const ReadGeom& g_ref) {
+POA_FN_NOINLINE void build_program(const Slot& s_ref, const Params p_ref, WinState& st, const ReadGeom g_ref) {
     const Slot s = s_ref;     /* local copies: no reloads of the descriptor after every store */
     const Params p = p_ref;
-    const ReadGeom g = g_ref;
+    const ReadGeom g = geom_uniform(g_ref);
     POA_SUB_BEGIN();
-    const int32_t N = st.n_nodes, E = st.n_edges;
+    const int32_t N = poa_uniform(st.n_nodes), E = poa_uniform(st.n_edges);
     /* pass A, node-parallel, 64 rows per step: row records and CSR offsets (row r+1 <-> node_at[r]) */
     int32_t run = 0; /* running predecessor offset (uniform) */
     POA_LANE0 { s.row_rec[0] = 0; }
@@ -528,10 +565,12 @@ POA_FN_NOINLINE void build_program(const Slot& s_ref, const Params& p_ref, WinSt
  * Outputs: sub_at[0..n_sub), sub_rank[] (NONE16 for non-members), roff[v] = out-degree inside the
  * subgraph.  Returns n_sub.
  * ---------------------------------------------------------------------------------------- */
-POA_FN_NOINLINE int32_t mark_subgraph(const Slot& s_ref, const Params& p_ref, WinState& st, int32_t begin, int32_t end) {
+POA_FN_NOINLINE int32_t mark_subgraph(const Slot& s_ref, const Params p_ref, WinState& st, int32_t begin, int32_t end) {
     const Slot s = s_ref;
     const Params p = p_ref;
-    const int32_t N = st.n_nodes;
+    const int32_t N = poa_uniform(st.n_nodes);
+    begin = poa_uniform(begin);
+    end = poa_uniform(end);
     for (int32_t base = 0; base < N; base += 32) {
         POA_LANES(l) {
             if (base + l < N) {
@@ -625,10 +664,10 @@ POA_FN_NOINLINE int32_t mark_subgraph(const Slot& s_ref, const Params& p_ref, Wi
 
 /* Row program of a subgraph alignment: rows follow sub_at[], predecessor lists keep only member
  * sources (in in-edge order), a row without member sources gets the virtual predecessor row 0. */
-POA_FN_NOINLINE void build_program_sub(const Slot& s_ref, const Params& p_ref, WinState& st, const ReadGeom& g_ref) {
+POA_FN_NOINLINE void build_program_sub(const Slot& s_ref, const Params p_ref, WinState& st, const ReadGeom g_ref) {
     const Slot s = s_ref;
     const Params p = p_ref;
-    const ReadGeom g = g_ref;
+    const ReadGeom g = geom_uniform(g_ref);
     const int32_t N = g.n_rows;
     int32_t run = 0;
     POA_LANE0 { s.row_rec[0] = 0; }
@@ -729,6 +768,7 @@ constexpr int TB_ROWS = 32 * TB_RPL;     /* tile rows */
 constexpr int TB_CHUNKS = POA_TB_CHUNKS; /* tile columns in 8-cell chunks */
 constexpr int TB_COLS = TB_CHUNKS * 8;
 constexpr int TB_PRED_CAP = 192 * TB_RPL; /* predecessor entries a tile can hold */
+constexpr int TB_EDGE_MARGIN = 24;        /* adaptive band: a tile anchored this close to a band edge asks for a wider band */
 
 struct TbScratch {           /* device: shared memory (the fill's ring area); emulation: heap */
     int16_t* cells;          /* [TB_ROWS * TB_COLS]  row (r_hi - k) at k*TB_COLS, column c at c - c_lo */
@@ -831,11 +871,13 @@ POA_FN void tb_bind(TbScratch& t, uint8_t* base) {
     t.readc = base;
 }
 
-POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, const ReadGeom& g,
+POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params p, WinState& st, const ReadGeom g,
                          const uint8_t* read, int32_t end_row, const TbScratch& t, const uint16_t* row_node) {
     /* everything the loop touches is copied into locals first: `s`, `t`, `p`, `g` are references into
      * memory, and after each store the compiler would otherwise reload every pointer it needs */
-    const int32_t cap = p.max_nodes + p.max_len + 2;
+    const Params pu = p;
+    const int32_t cap = pu.max_nodes + pu.max_len + 2;
+    end_row = poa_uniform(end_row);
     int16_t* const tb_node = s.tb_node;
     int16_t* const tb_pos = s.tb_pos;
     const uint32_t* const row_rec = s.row_rec;
@@ -843,8 +885,8 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
     const uint32_t* const row_pred = s.row_pred;
     const uint16_t* const node_at = row_node; /* rank -> node of THIS alignment's rows (graph or subgraph) */
     const int16_t* const S = s.S;
-    const int32_t stride = p.stride, gap = p.gap, bw = g.bw, rlen = g.len;
-    const ReadGeom gg = g;
+    const ReadGeom gg = geom_uniform(g);
+    const int32_t stride = pu.stride, gap = pu.gap, bw = gg.bw, rlen = gg.len;
     /* the tile is addressed from ONE base (shared-window address on the device); its parts sit at constant offsets */
     const tile_addr A_cells = tile_base(t.cells);
     const tile_addr A_rec = A_cells + TB_OFF_REC, A_poff = A_cells + TB_OFF_POFF, A_pred = A_cells + TB_OFF_PRED,
@@ -852,8 +894,8 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
                     A_out = A_cells + TB_OFF_OUT;
     POA_SUB_BEGIN();
     int32_t w = cap; /* write cursor (uniform) */
-    int32_t i = end_row, j = rlen;
-    const int32_t mg = p.match - gap, xg = p.mismatch - gap;
+    int32_t i = end_row, j = rlen; /* both laundered above */
+    const int32_t mg = pu.match - gap, xg = pu.mismatch - gap;
     int32_t cur = score_at(s, p, g, i, j);
     /* tile state (uniform) */
     int32_t r_hi = -1, r_lo = 0, c_lo = 0, c_hi = -1, pred_base = 0, pred_n = 0;
@@ -873,6 +915,8 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
         POA_SYNC();                                                                     \
         nb = 0;                                                                         \
     } while (0)
+    int32_t lost = 0; /* the band did not contain a consistent path: decided by a vote at the end of the step, so that
+                         the function is never left from lane-dependent control flow (poa_simt.cuh) */
     while (!(i == 0 && j == 0)) {
         if (w <= 32) { /* every step consumes one entry: a path longer than nodes + read length is lost */
             st.status = ST_TRACEBACK_LOST;
@@ -905,6 +949,11 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
             r_lo = i - (TB_ROWS - 1) < 0 ? 0 : i - (TB_ROWS - 1);
             c_hi = j;
             c_lo = ((j + 1 - TB_COLS) < 0 ? 0 : (j + 1 - TB_COLS + 7)) & ~7; /* 8-aligned, covers j */
+            if (gg.banded && pu.adaptive) { /* adaptive band: is the path (sampled once per tile) about to leave the band? */
+                const int32_t bs_i = band_start(gg, i, gg.n_rows);
+                if ((bs_i > 0 && j - bs_i < TB_EDGE_MARGIN) || (bs_i + bw < gg.colsP && bs_i + bw - 1 - j < TB_EDGE_MARGIN))
+                    st.band_hit = 1;
+            }
             POA_SYNC();
             /* ONE round of independent loads.  The band start of a row is recomputed (same formula as the
              * row program) instead of read from its record, so the score chunks -- the loads that go to HBM --
@@ -973,7 +1022,7 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
         /* ---- one step at (i, j) ---- */
         int32_t ni = i, nj = j, ncur = cur;
         const int32_t ti = r_hi - i; /* tile row index of row i */
-        const uint32_t info = tile_u32(A_info, ti);
+        const uint32_t info = (uint32_t)poa_uniform((int32_t)tile_u32(A_info, ti));
         const int32_t tp = (int32_t)((info >> 8) & 0xFFu);
         uint32_t node_i = info >> 16;
         if (tp != 0xFF) {
@@ -994,15 +1043,14 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
             } else if (j > 0 && vh == cur) {
                 nj = j - 1;
             } else {
-                st.status = ST_TRACEBACK_LOST;
-                return cap;
+                lost = 1;
             }
         } else {
         const uint32_t rec = tile_u32(A_rec, ti);
         const int32_t np = rec_npred(rec);
         const int32_t po = (int32_t)tile_u32(A_poff, ti);
         const int32_t prof = (j > 0 && rec_code(rec) == (int32_t)tile_u8(A_readc, j - c_lo)) ? mg : xg;
-        bool in_tile = (np <= 32) && (po - pred_base + np <= pred_n);
+        bool in_tile = poa_uniform_pred((np <= 32) && (po - pred_base + np <= pred_n));
         int32_t found = 0;
         if (in_tile) {
             /* every lane rates its predecessor; ONE warp-min picks spoa's choice:
@@ -1036,12 +1084,12 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
                 nj = j;
                 ncur = cur - gap;
                 found = 1;
-            } else if (j > 0 && tile_s16(A_cells, ti * TB_COLS + (j - 1 - c_lo)) == cur) {
+            } else if (poa_uniform_pred(j > 0 && tile_s16(A_cells, ti * TB_COLS + (j - 1 - c_lo)) == cur)) {
                 nj = j - 1;
                 found = 1;
             } else {
-                st.status = ST_TRACEBACK_LOST;
-                return cap;
+                lost = 1;
+                found = 1;
             }
         }
         if (!in_tile) {
@@ -1079,18 +1127,21 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
                 if (j > 0 && score_at_bs(s, p, g, i, rec_bs(rec), j - 1) == cur) {
                     nj = j - 1;
                 } else {
-                    st.status = ST_TRACEBACK_LOST;
-                    return cap;
+                    lost = 1;
                 }
             }
         }
         } /* general step */
+        if (poa_uniform_pred(lost != 0)) {
+            st.status = ST_TRACEBACK_LOST;
+            return cap;
+        }
         --w;
         tile_st_u32(A_out, nb, ((i == ni) ? 0xFFFFu : node_i) | ((uint32_t)((j == nj) ? 0xFFFF : (j - 1)) << 16));
         ++nb;
         if (nb == 32) POA_TB_FLUSH();
-        i = ni;
-        j = nj;
+        i = poa_uniform(ni); /* the path position steers the loop, tile reloads and flushes (collectives): provably uniform */
+        j = poa_uniform(nj);
         cur = ncur;
     }
     POA_TB_FLUSH();
@@ -1102,13 +1153,19 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params& p, WinState& st, 
 /* ------------------------------------------------------------------------------------------
  * Phase 4: add the alignment to the graph  (graph.cpp:155-272, 94-116)
  * ---------------------------------------------------------------------------------------- */
-POA_FN_NOINLINE void add_alignment(const Slot& s_ref, const Params& p_ref, WinState& st, const uint8_t* read,
+POA_FN_NOINLINE void add_alignment_edges(const Slot& s_ref, const Params p_ref, WinState& st, const int8_t* wt,
+                                         int32_t wconst, int32_t len);
+
+POA_FN_NOINLINE void add_alignment(const Slot& s_ref, const Params p_ref, WinState& st, const uint8_t* read,
                           const int8_t* wt, int32_t wconst, int32_t len, int32_t tb_begin) {
     const Slot s = s_ref;     /* local copies: no reloads of the descriptor after every store */
     const Params p = p_ref;
     const int32_t cap = p.max_nodes + p.max_len + 2;
+    len = poa_uniform(len);
+    tb_begin = poa_uniform(tb_begin);
+    wconst = poa_uniform(wconst);
     POA_SUB_BEGIN();
-    const int32_t N0 = st.n_nodes;
+    const int32_t N0 = poa_uniform(st.n_nodes);
 
     /* (a) resolve every read position: existing node, or a new node (unaligned / aligned to x).
      *     asg[pos] >= 0 : existing node;  -1 : new, unaligned;  -2-x : new, aligned to node x.
@@ -1150,7 +1207,7 @@ POA_FN_NOINLINE void add_alignment(const Slot& s_ref, const Params& p_ref, WinSt
     /* (b) create the new nodes; ids follow read order exactly like the serial add_node calls. */
     int32_t n_new = 0;
     int32_t fail = 0;
-    int32_t n_cols = st.n_columns;
+    int32_t n_cols = poa_uniform(st.n_columns);
     for (int32_t base = 0; base < len; base += 32) {
         PerLane<int> isnew;
         POA_LANES(l) {
@@ -1267,9 +1324,22 @@ POA_FN_NOINLINE void add_alignment(const Slot& s_ref, const Params& p_ref, WinSt
     st.n_columns = n_cols;
 
     POA_SUB_LAP(4);
-    /* (d) edges prev -> cur for consecutive read positions (graph.cpp:248-259, 94-116), and
-     * (e) coverage: every node on the read's path carries this sequence's label. */
-    int32_t n_edges = st.n_edges;
+    add_alignment_edges(s_ref, p_ref, st, wt, wconst, len);
+}
+
+/* (d) edges prev -> cur for consecutive read positions (graph.cpp:248-259, 94-116), and
+ * (e) coverage: every node on the read's path carries this sequence's label.
+ * A function of its own: ptxas proves the warp-uniformity of a function's control flow only while the function stays
+ * small enough (see poa_simt.cuh); the node and the edge stage together were not. */
+POA_FN_NOINLINE void add_alignment_edges(const Slot& s_ref, const Params p_ref, WinState& st, const int8_t* wt,
+                                         int32_t wconst, int32_t len) {
+    const Slot s = s_ref;
+    const Params p = p_ref;
+    len = poa_uniform(len);
+    wconst = poa_uniform(wconst);
+    int32_t fail = 0;
+    POA_SUB_BEGIN();
+    int32_t n_edges = poa_uniform(st.n_edges);
     /* DU read positions per lane per step (pos, pos + 32, ...): the walk over a node's in-edge list is a chain of
      * dependent loads to HBM; the DU walks of a lane are interleaved so that their round trips overlap.  New edge
      * ids follow read order (position = base + 32 u + lane: u-major), computed from ballots. */
@@ -1335,7 +1405,7 @@ POA_FN_NOINLINE void add_alignment(const Slot& s_ref, const Params& p_ref, WinSt
             first[u] = tot;
             tot += poa_popc(nmask[u]);
         }
-        if (n_edges + tot > p.max_edges) {
+        if (n_edges + tot > poa_edge_capacity(p.max_nodes)) {
             fail = ST_EDGE_COUNT_EXCEEDED;
             break;
         }
@@ -1400,10 +1470,10 @@ POA_FN_NOINLINE void add_alignment(const Slot& s_ref, const Params& p_ref, WinSt
  * Phase 5a: serial topological sort, the literal restatement of graph.cpp:294-354.
  * Kept for the test-suite (Params::serial_topsort) as the cross-check of the per-root sort.
  * ---------------------------------------------------------------------------------------- */
-POA_FN_NOINLINE void topsort_serial(const Slot& s_ref, const Params& p_ref, WinState& st) {
+POA_FN_NOINLINE void topsort_serial(const Slot& s_ref, const Params p_ref, WinState& st) {
     const Slot s = s_ref;     /* local copies: no reloads of the descriptor after every store */
     const Params p = p_ref;
-    const int32_t N = st.n_nodes;
+    const int32_t N = poa_uniform(st.n_nodes);
     for (int32_t base = 0; base < N; base += 32) {
         POA_LANES(l) {
             if (base + l < N) {
@@ -1478,11 +1548,11 @@ POA_FN_NOINLINE void topsort_serial(const Slot& s_ref, const Params& p_ref, WinS
  *        members and store each member's position (lpos);
  *     3. every node: rank = offset[root] + lpos.
  * ---------------------------------------------------------------------------------------- */
-POA_FN_NOINLINE void topsort_roots(const Slot& s_ref, const Params& p_ref, WinState& st) {
+POA_FN_NOINLINE void topsort_roots(const Slot& s_ref, const Params p_ref, WinState& st) {
     const Slot s = s_ref;     /* local copies: no reloads of the descriptor after every store */
     const Params p = p_ref;
     POA_SUB_BEGIN();
-    const int32_t N = st.n_nodes;
+    const int32_t N = poa_uniform(st.n_nodes);
     /* 1. members of dirty roots: reset DFS marks, accumulate the root's stack bound.  Four nodes per lane
      *    per step so that the dependent loads (root -> dirty -> in-degree) of all four are in flight together. */
     for (int32_t base = 0; base < N; base += 128) {
@@ -1763,11 +1833,13 @@ POA_FN void consensus_scores_full(const Slot& s, int32_t N, int32_t& max_id_out)
     max_id_out = max_id;
 }
 
-POA_FN_NOINLINE void generate_consensus(const Slot& s_ref, const Params& p_ref, WinState& st, const WindowOut& out_ref) {
+POA_FN_NOINLINE void generate_consensus(const Slot& s_ref, const Params p_ref, WinState& st, const WindowOut& out_ref) {
     const Slot s = s_ref;     /* local copies: no reloads of the descriptor after every store */
     const Params p = p_ref;
-    const WindowOut out = out_ref;
-    const int32_t N = st.n_nodes;
+    WindowOut out = out_ref;
+    out.trim_nseq = poa_uniform(out.trim_nseq);
+    const int32_t N = poa_uniform(st.n_nodes);
+    const int32_t n_edges_total = poa_uniform(st.n_edges);
     POA_SUB_BEGIN();
     int32_t n = 0;
     int32_t max_id_full = 0;
@@ -1780,7 +1852,7 @@ POA_FN_NOINLINE void generate_consensus(const Slot& s_ref, const Params& p_ref, 
             const int32_t node_id = max_id;
             const int32_t rank = s.rank_of[node_id];
             /* invalidate the other sources of every out-neighbour (graph.cpp:547-554) */
-            for (int32_t e = 0; e < st.n_edges; ++e) {
+            for (int32_t e = 0; e < n_edges_total; ++e) {
                 if (s.e_src[e] != node_id) continue;
                 const int32_t d = s.e_dst[e];
                 for (uint16_t f = s.in_head[d]; f != NONE16; f = s.e_next[f])
@@ -1880,12 +1952,14 @@ POA_FN void process_window(const Slot& s, const Params& p, const WindowView& wv,
     st.n_nodes = 0;
     st.n_edges = 0;
     st.n_columns = 0;
+    st.band_hit = 0;
     st.status = ST_SUCCESS;
     const int32_t len0 = (int32_t)(wv.seq_off[1] - wv.seq_off[0]);
     tm.start();
     {
         const int64_t wo = wv.w_off[0];
         init_backbone(s, p, st, wv.bases + wv.seq_off[0], wo >= 0 ? wv.weights + wo : nullptr, wo >= 0 ? 0 : (int32_t)(-1 - wo), len0);
+        winstate_uniform(st);
     }
     for (int32_t r = 1; r < wv.n_seqs && st.status == ST_SUCCESS; ++r) {
         const uint8_t* read = wv.bases + wv.seq_off[r];
@@ -1907,31 +1981,51 @@ POA_FN void process_window(const Slot& s, const Params& p, const WindowView& wv,
                 st.status = ST_GENERIC_ERROR;
                 break;
             }
-            n_rows = mark_subgraph(s, p, st, sp_begin, sp_end);
+            n_rows = poa_uniform(mark_subgraph(s, p, st, sp_begin, sp_end));
         }
-        const ReadGeom g = read_geometry(p, len, n_rows);
-        tm.lap(PH_OTHER);
-        if (partial) build_program_sub(s, p, st, g);
-        else build_program(s, p, st, g);
-        tm.lap(PH_PROGRAM);
-        if (st.status != ST_SUCCESS) break;
-        const int32_t end_row = fill(s, p, st, g, read);
-        tm.lap(PH_FILL);
-        if (end_row <= 0) {
-            st.status = ST_TRACEBACK_LOST;
+        /* static band: one try.  Adaptive band: the configured width is the first try; a traceback that comes close to
+         * a band edge (or loses the path) re-aligns this read with twice the width, up to the full matrix. */
+        int32_t band_w = p.band_width;
+        int32_t tb = 0;
+        for (;;) {
+            const ReadGeom g = read_geometry(p, len, n_rows, band_w);
+            tm.lap(PH_OTHER);
+            if (partial) build_program_sub(s, p, st, g);
+            else build_program(s, p, st, g);
+            winstate_uniform(st);
+            tm.lap(PH_PROGRAM);
+            if (st.status != ST_SUCCESS) break;
+            const int32_t end_row = poa_uniform(fill(s, p, st, g, read));
+            tm.lap(PH_FILL);
+            st.band_hit = 0;
+            if (end_row <= 0) {
+                st.status = ST_TRACEBACK_LOST;
+            } else {
+                tb = poa_uniform(traceback(s, p, st, g, read, end_row, tbs, partial ? s.sub_at : s.node_at));
+                winstate_uniform(st);
+                tm.lap(PH_TRACEBACK);
+            }
+            if (p.adaptive && g.banded && (st.band_hit || st.status == ST_TRACEBACK_LOST)) {
+                st.status = ST_SUCCESS;
+                band_w *= 2;
+                continue;
+            }
             break;
         }
-        const int32_t tb = traceback(s, p, st, g, read, end_row, tbs, partial ? s.sub_at : s.node_at);
-        tm.lap(PH_TRACEBACK);
         if (st.status != ST_SUCCESS) break;
         add_alignment(s, p, st, read, wt, wconst, len, tb);
+        winstate_uniform(st);
         tm.lap(PH_ADD);
         if (st.status != ST_SUCCESS) break;
         if (p.serial_topsort) topsort_serial(s, p, st);
         else topsort_roots(s, p, st);
+        winstate_uniform(st);
         tm.lap(PH_TOPSORT);
     }
-    if (st.status == ST_SUCCESS) generate_consensus(s, p, st, out);
+    if (st.status == ST_SUCCESS) {
+        generate_consensus(s, p, st, out);
+        winstate_uniform(st);
+    }
     tm.lap(PH_CONSENSUS);
     POA_LANE0 {
         if (st.status != ST_SUCCESS) {

@@ -168,7 +168,8 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
 #pragma unroll 1
     for (int idx = lane; idx < (R + 1) * (1 + RING_PAD_BACK / 8); idx += 32) {
         const int row = idx / (1 + RING_PAD_BACK / 8), part = idx % (1 + RING_PAD_BACK / 8);
-        const uint32_t cell = part == 0 ? 0u : (uint32_t)(fa.ring_stride - RING_PAD_BACK + 8 * (part - 1));
+        /* the back pad follows THIS read's band cells (ring rows are sized for the widest band of the batch) */
+        const uint32_t cell = part == 0 ? 0u : (uint32_t)(RING_PAD_FRONT + bw + 8 * (part - 1));
         sts128(ring_sa + (uint32_t)row * ring_row_bytes + cell * 2u, make_uint4(NEG2, NEG2, NEG2, NEG2));
     }
     /* row 0: H[0][j] = j*gap  =>  S = 0 (global copy for the traceback, ring slot 0 for the fill) */
@@ -201,7 +202,7 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
         const int np = rec_npred(rec);
         const int bs = rec_bs(rec);
         const int prow = rec_prow(rec);
-        if (prow == 4) {
+        if (__any_sync(0xffffffffu, prow == 4)) { /* the vote makes the branch provably warp-uniform, see poa_uniform() */
             const int code = rec_code(rec);
             if (dyn_code != code) {
                 fill_build_dyn_prof_row(prof_sa + (uint32_t)(4 * prof_stride), code, read, fa.len, fa.colsP, mg, xg);
@@ -245,12 +246,12 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
 #define POA_FILL_ACCUMULATE()                                                                              \
     do {                                                                                                   \
         const uint4 V = lds128((unsigned)off <= lim_v ? cell_sa : neg_sa);                                 \
-        const uint32_t leftw = lds_u16((unsigned)(off - 1) < lim_l ? cell_sa - 2u : neg_sa) << 16;         \
+        const uint32_t leftw = lds_u16((unsigned)(off - 1) < lim_l ? cell_sa - 2u : neg_sa);               \
         POA_FILL_TERM();                                                                                   \
     } while (0)
 #define POA_FILL_TERM()                                                                                    \
     do {                                                                                                   \
-        const uint32_t d0 = __funnelshift_l(leftw, V.x, 16);                                               \
+        const uint32_t d0 = __byte_perm(leftw, V.x, 0x5410); /* (left cell, first cell): one PRMT */       \
         const uint32_t d1 = __funnelshift_l(V.x, V.y, 16);                                                 \
         const uint32_t d2 = __funnelshift_l(V.y, V.z, 16);                                                 \
         const uint32_t d3 = __funnelshift_l(V.z, V.w, 16);                                                 \
@@ -268,12 +269,20 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
                 /* the common row of the banded configuration: every predecessor is in the ring, its band starts
                  * 0..RING_PAD_BACK columns before ours, its stream entry is in predA.  Whatever falls outside the
                  * predecessor's band lands in the row's NEG pads: no tests at all. */
+                {   /* every row has at least one predecessor (a node without in-edges has the virtual row 0): the first
+                     * one initialises the accumulators */
+                    const uint32_t pe = __shfl_sync(0xffffffffu, predA, rel);
+                    const uint32_t cell_sa = c0_sa + (uint32_t)((int)pe >> 12);
+                    const uint4 V = lds128(cell_sa);
+                    const uint32_t leftw = lds_u16(cell_sa - 2u);
+                    POA_FILL_TERM();
+                }
 #pragma unroll 1
-                for (int q = 0; q < np; ++q) {
+                for (int q = 1; q < np; ++q) {
                     const uint32_t pe = __shfl_sync(0xffffffffu, predA, rel + q);
                     const uint32_t cell_sa = c0_sa + (uint32_t)((int)pe >> 12);
                     const uint4 V = lds128(cell_sa);
-                    const uint32_t leftw = lds_u16(cell_sa - 2u) << 16;
+                    const uint32_t leftw = lds_u16(cell_sa - 2u);
                     POA_FILL_TERM();
                 }
             } else if (!rec_far(rec) && np <= 32) {
@@ -294,7 +303,7 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
                     else pe = row_pfill[po + q]; /* in-degree > 32: straight from memory */
                     const int off = c0 - (int)((pe & 0xFFEu) << 2);
                     uint32_t cell_sa = c0_sa + (uint32_t)((int)pe >> 12);
-                    if (pe & 1u) { /* predecessor older than the ring: stage its row in the spare slot */
+                    if (__any_sync(0xffffffffu, (pe & 1u) != 0)) { /* predecessor older than the ring: stage its row in the spare slot */
                         const int pr = (int)(row_pred[po + q] & 0xFFFFu);
                         fill_stage_far_row(S + (size_t)pr * stride, far_sa, bw);
                         cell_sa = far_sa + (uint32_t)off * 2u;
@@ -433,7 +442,7 @@ __device__ __noinline__ int32_t fill_rows_wide(const FillArgs fa) {
         const uint32_t rec = __shfl_sync(0xffffffffu, recA, i & 31);
         const int np = rec_npred(rec);
         const int prow = rec_prow(rec);
-        if (prow == 4) {
+        if (__any_sync(0xffffffffu, prow == 4)) { /* the vote makes the branch provably warp-uniform, see poa_uniform() */
             const int code = rec_code(rec);
             if (dyn_code != code) {
                 fill_build_dyn_prof_row(prof_sa + (uint32_t)(4 * prof_stride), code, fa.read, fa.len, prof_stride, fa.mg, fa.xg);
@@ -504,7 +513,7 @@ __device__ __noinline__ int32_t fill_rows_wide(const FillArgs fa) {
                 if (rel + q < 32) pe = __shfl_sync(0xffffffffu, predA, rel + q);
                 else pe = row_pfill[po + q];
                 uint32_t cell_sa = c0_sa + (uint32_t)((int)pe >> 12);
-                if (pe & 1u) { /* predecessor older than the ring: stage its row in the spare slot */
+                if (__any_sync(0xffffffffu, (pe & 1u) != 0)) { /* predecessor older than the ring: stage its row in the spare slot */
                     const int pr = (int)(fa.row_pred[po + q] & 0xFFFFu);
                     fill_stage_far_row(S + (size_t)pr * stride, far_sa, bw);
                     cell_sa = far_sa + (uint32_t)col0 * 2u;

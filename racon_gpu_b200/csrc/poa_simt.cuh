@@ -44,7 +44,17 @@ struct PerLane {
 #define POA_LANE0 if ((threadIdx.x & 31u) == 0u)
 #define POA_SYNC() __syncwarp()
 
-/* exclusive prefix sum over lanes, returns the warp total */
+/* Warp-uniform values and the compiler.  Control flow that contains a warp collective (shuffle, vote, __syncwarp) is
+ * cheap only when the compiler can PROVE it warp-uniform: otherwise every collective of the function gets a
+ * "BRA.DIV -> WARPSYNC.COLLECTIVE" slow path, BSSY/BSYNC brackets and the registers to feed them (a quarter of the
+ * fill's instructions before this was understood).  A value read back from a shuffle or from inline-asm memory access
+ * is uniform in fact but not provably; the results of votes and of redux.sync (CREDUX writes a uniform register) are.
+ * poa_uniform() launders a de-facto uniform int through one CREDUX; warp_bcast0() and the scan total use it. */
+POA_FN int poa_uniform(int x) { return __reduce_max_sync(0xffffffffu, x); }
+/* a de-facto uniform predicate made provably uniform by a vote */
+POA_FN bool poa_uniform_pred(bool x) { return __any_sync(0xffffffffu, x) != 0; }
+
+/* exclusive prefix sum over lanes, returns the warp total (provably uniform) */
 POA_FN int warp_exscan(PerLane<int>& x) {
     const int lane = (int)(threadIdx.x & 31u);
     int v = x.v;
@@ -53,7 +63,7 @@ POA_FN int warp_exscan(PerLane<int>& x) {
         int t = __shfl_up_sync(0xffffffffu, v, d);
         if (lane >= d) v += t;
     }
-    int total = __shfl_sync(0xffffffffu, v, 31);
+    const int total = __reduce_add_sync(0xffffffffu, x.v);
     x.v = v - x.v;
     return total;
 }
@@ -64,7 +74,7 @@ POA_FN int warp_sum(const PerLane<int>& x) { return __reduce_add_sync(0xffffffff
 /* value held by lane `src` (src uniform) */
 POA_FN int warp_get(const PerLane<int>& x, int src) { return __shfl_sync(0xffffffffu, x.v, src); }
 /* make a lane-0 scalar uniform across the warp */
-POA_FN int warp_bcast0(int x) { return __shfl_sync(0xffffffffu, x, 0); }
+POA_FN int warp_bcast0(int x) { return __reduce_max_sync(0xffffffffu, (threadIdx.x & 31u) == 0u ? x : (int)0x80000000); }
 /* out[l] = x[l+1] (lane 31 keeps its own value) */
 POA_FN void warp_shift_down1(const PerLane<int>& x, PerLane<int>& out) { out.v = __shfl_down_sync(0xffffffffu, x.v, 1); }
 
@@ -115,6 +125,8 @@ POA_FN int warp_sum(const PerLane<int>& x) {
 }
 POA_FN int warp_get(const PerLane<int>& x, int src) { return x.v[src]; }
 POA_FN int warp_bcast0(int x) { return x; }
+POA_FN int poa_uniform(int x) { return x; }
+POA_FN bool poa_uniform_pred(bool x) { return x; }
 POA_FN void warp_shift_down1(const PerLane<int>& x, PerLane<int>& out) {
     for (int l = 0; l < 31; ++l) out.v[l] = x.v[l + 1];
     out.v[31] = x.v[31];

@@ -85,11 +85,14 @@ void emu_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int
                         int32_t* rank_out, int32_t* n_nodes_out, int64_t* cells_out, int32_t* trim_out) {
     Params p;
     p.max_nodes = max_nodes;
-    p.max_edges = max_edges;
+    p.max_edges = poa_edge_capacity(max_nodes); /* the engine derives the edge pool from the node capacity */
+    (void)max_edges;
     p.max_len = max_len;
     const int32_t colsP = (max_len + 1 + 7) & ~7;
+    p.adaptive = band_width < 0 ? 1 : 0; /* band_width < 0: adaptive band starting at -band_width */
+    if (band_width < 0) band_width = -band_width;
     p.band_width = band_width;
-    p.stride = (band_width > 0 && band_width < colsP) ? band_width : colsP;
+    p.stride = (!p.adaptive && band_width > 0 && band_width < colsP) ? band_width : colsP;
     p.max_cons = stride_out;
     p.match = m;
     p.mismatch = x;

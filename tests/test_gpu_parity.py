@@ -358,3 +358,32 @@ def test_single_process_multi_device_polisher(oracle):
     launches = pol.last["kernel_launches"]
     pol.close()
     assert polished.all() and api.consensus_list(cons, clen) == oc and launches >= 15
+
+
+def test_adaptive_band_on_the_gpu(oracle):
+    """Adaptive band (static band + retry with twice the width when the traceback nears the band edge): exact on the
+    long-deletion windows the static band gets wrong, and bit-identical to its CPU emulation."""
+    from emu_lib import Emu
+    from test_emu import deletion_windows
+    b = deletion_windows()
+    order = identity_order(b)
+    oc, ocov, _ = oracle.polish(b, order, M, X, G, tgs=False, trim=False, threads=16, stride=8192)
+    wins = [b.window(w)[0] for w in range(b.n_windows)]
+    out = {}
+    for mode in (True, "adaptive"):
+        pb = api.PoaBatch(max_gpu_mem=MEM, banded=mode)
+        for seqs in wins:
+            assert pb.add_poa_group([(s, None) for s in seqs])[0] == 0
+        pb.generate_poa()
+        out[mode] = pb.get_consensus()
+        pb.close()
+    gc, gcov, st = out["adaptive"]
+    assert (st == 0).all() and gc == oc and all((a == c).all() for a, c in zip(gcov, ocov))
+    sc, _, sst = out[True]
+    ec, _, est, _ = Emu().polish(b, order, M, X, G, max_nodes=4092, max_edges=24000, band=256, stride=8192)
+    assert (sst == est).all() and sc == ec and sc != oc
+    # on ordinary windows the adaptive band is the static band (no retry): same result, same tolerance
+    a = synth_windows(64, 500, 32, 0.15, seed=83)
+    r_static = gpu_untrimmed(a, banded=True)
+    r_adapt = gpu_untrimmed(a, banded="adaptive")
+    assert r_static[0] == r_adapt[0]
