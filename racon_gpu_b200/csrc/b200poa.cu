@@ -252,7 +252,7 @@ static SmemGeometry smem_geometry(const Params& p, int32_t max_len) {
     while (rows < 32 && rows * 2 * g.ring_stride * (int32_t)sizeof(int16_t) <= ring_bytes) rows *= 2;
     g.ring_rows = rows;
     g.smem_bytes = 32 + std::max(((PROF_ROWS * g.prof_stride + 15) & ~15) +
-                                     ((g.ring_rows + 1) * g.ring_stride + slack_cells) * (int32_t)sizeof(int16_t),
+                                     (g.ring_rows * g.ring_stride + slack_cells) * (int32_t)sizeof(int16_t),
                                  (int32_t)TB_SCRATCH_BYTES);
     return g;
 }

@@ -186,7 +186,7 @@ void slot_bind(Slot& s, uint8_t* base, const Params& p, size_t* total_out) {
     POA_CARVE(e_next, uint16_t, ME);
     POA_CARVE(e_w, int32_t, ME);
     POA_CARVE(e_ord, uint8_t, ME);
-    POA_CARVE(row_rec, uint32_t, MN + 1 + 64); /* +64: the fill prefetches 32-row blocks past the end */
+    POA_CARVE(row_rec, uint32_t, MN + 1 + 128); /* +128: the fill prefetches 32-row blocks up to three blocks past the end */
     POA_CARVE(row_poff, uint32_t, MN + 2);
     POA_CARVE(row_pred, uint32_t, ME + MN + 96);
     POA_CARVE(row_pfill, uint32_t, ME + MN + 96); /* +96: the fill prefetches 32-entry blocks past the end */
@@ -803,43 +803,34 @@ POA_FN void fill8(int16_t* dst, int32_t v) {
 /* Reads of the tile on the serial path: real shared-memory loads on the device (the tile pointers are
  * generic; a generic load pays the address-space resolution on every step of the dependent chain). */
 #if POA_DEVICE
-typedef uint32_t tile_addr;
-POA_FN tile_addr tile_base(void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-POA_FN uint32_t tile_u32(tile_addr a, int32_t i) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a + 4u * (uint32_t)i));
-    return v;
-}
-POA_FN int32_t tile_s16(tile_addr a, int32_t i) {
-    int32_t v;
-    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(a + 2u * (uint32_t)i));
-    return v;
-}
-POA_FN uint32_t tile_u16(tile_addr a, int32_t i) {
-    uint32_t v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a + 2u * (uint32_t)i));
-    return v;
-}
-POA_FN uint32_t tile_u8(tile_addr a, int32_t i) {
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a + (uint32_t)i));
-    return v;
-}
+/* The tile lives at a fixed offset of the block's dynamic shared memory (the kernel binds TbScratch there) and is read
+ * with plain loads from the __shared__ array: the compiler then knows the address space (LDS, no generic resolution)
+ * AND that a load from a warp-uniform address yields a warp-uniform value -- an inline-asm ld.shared would hide both,
+ * and every step of the walk would have to launder what it read (poa_simt.cuh). */
+constexpr uint32_t POA_TB_SMEM_OFFSET = 32;
+extern __shared__ __align__(16) unsigned char poa_smem[];
+typedef uint32_t tile_addr; /* byte offset into poa_smem */
+POA_FN tile_addr tile_base(void*) { return POA_TB_SMEM_OFFSET; }
+POA_FN uint32_t tile_u32(tile_addr a, int32_t i) { return *reinterpret_cast<const uint32_t*>(poa_smem + a + 4u * (uint32_t)i); }
+POA_FN int32_t tile_s16(tile_addr a, int32_t i) { return *reinterpret_cast<const int16_t*>(poa_smem + a + 2u * (uint32_t)i); }
+POA_FN uint32_t tile_u16(tile_addr a, int32_t i) { return *reinterpret_cast<const uint16_t*>(poa_smem + a + 2u * (uint32_t)i); }
+POA_FN uint32_t tile_u8(tile_addr a, int32_t i) { return poa_smem[a + (uint32_t)i]; }
+POA_FN uint32_t tile_sa(tile_addr a) { return (uint32_t)__cvta_generic_to_shared(poa_smem) + a; } /* shared-window address */
 /* asynchronous global -> shared copies used by the tile load (LDGSTS: no register staging, all in flight);
  * destinations are shared-window addresses, like every other access to the tile */
 POA_FN void tile_copy16(tile_addr a, int32_t byte_off, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a + (uint32_t)byte_off), "l"(src) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tile_sa(a) + (uint32_t)byte_off), "l"(src) : "memory");
 }
 POA_FN void tile_copy4(tile_addr a, int32_t i, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(a + 4u * (uint32_t)i), "l"(src) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tile_sa(a) + 4u * (uint32_t)i), "l"(src) : "memory");
 }
 POA_FN void tile_copy_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-POA_FN void tile_st_u32(tile_addr a, int32_t i, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a + 4u * (uint32_t)i), "r"(v) : "memory"); }
-POA_FN void tile_st_u16(tile_addr a, int32_t i, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a + 2u * (uint32_t)i), "r"(v) : "memory"); }
-POA_FN void tile_st_u8(tile_addr a, int32_t i, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a + (uint32_t)i), "r"(v) : "memory"); }
+POA_FN void tile_st_u32(tile_addr a, int32_t i, uint32_t v) { *reinterpret_cast<uint32_t*>(poa_smem + a + 4u * (uint32_t)i) = v; }
+POA_FN void tile_st_u16(tile_addr a, int32_t i, uint32_t v) { *reinterpret_cast<uint16_t*>(poa_smem + a + 2u * (uint32_t)i) = (uint16_t)v; }
+POA_FN void tile_st_u8(tile_addr a, int32_t i, uint32_t v) { poa_smem[a + (uint32_t)i] = (unsigned char)v; }
 POA_FN void tile_fill8(tile_addr a, int32_t byte_off, int32_t v) { /* 8 int16 cells */
     const uint32_t pk = ((uint32_t)v & 0xFFFFu) | ((uint32_t)v << 16);
-    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a + (uint32_t)byte_off), "r"(pk) : "memory");
+    *reinterpret_cast<uint4*>(poa_smem + a + (uint32_t)byte_off) = make_uint4(pk, pk, pk, pk);
 }
 #else
 typedef uint8_t* tile_addr;
@@ -896,7 +887,7 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params p, WinState& st, c
     int32_t w = cap; /* write cursor (uniform) */
     int32_t i = end_row, j = rlen; /* both laundered above */
     const int32_t mg = pu.match - gap, xg = pu.mismatch - gap;
-    int32_t cur = score_at(s, p, g, i, j);
+    int32_t cur = poa_uniform(score_at(s, p, g, i, j)); /* read through generic pointers: launder once */
     /* tile state (uniform) */
     int32_t r_hi = -1, r_lo = 0, c_lo = 0, c_hi = -1, pred_base = 0, pred_n = 0;
     /* alignment entries (node | read position) are collected in the tile and written out 32 at a time, coalesced:
@@ -1022,7 +1013,7 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params p, WinState& st, c
         /* ---- one step at (i, j) ---- */
         int32_t ni = i, nj = j, ncur = cur;
         const int32_t ti = r_hi - i; /* tile row index of row i */
-        const uint32_t info = (uint32_t)poa_uniform((int32_t)tile_u32(A_info, ti));
+        const uint32_t info = tile_u32(A_info, ti);
         const int32_t tp = (int32_t)((info >> 8) & 0xFFu);
         uint32_t node_i = info >> 16;
         if (tp != 0xFF) {
@@ -1131,6 +1122,9 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params p, WinState& st, c
                 }
             }
         }
+        ni = poa_uniform(ni); /* decided through shuffles in the general step: launder (the common step reads only
+                                 warp-uniform tile words, which the compiler proves uniform on its own) */
+        nj = poa_uniform(nj);
         } /* general step */
         if (poa_uniform_pred(lost != 0)) {
             st.status = ST_TRACEBACK_LOST;
@@ -1140,8 +1134,8 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params p, WinState& st, c
         tile_st_u32(A_out, nb, ((i == ni) ? 0xFFFFu : node_i) | ((uint32_t)((j == nj) ? 0xFFFF : (j - 1)) << 16));
         ++nb;
         if (nb == 32) POA_TB_FLUSH();
-        i = poa_uniform(ni); /* the path position steers the loop, tile reloads and flushes (collectives): provably uniform */
-        j = poa_uniform(nj);
+        i = ni;
+        j = nj;
         cur = ncur;
     }
     POA_TB_FLUSH();

@@ -80,7 +80,8 @@ __device__ __forceinline__ void sts16(uint32_t addr, int v) {
  *   [8, 16)                                 eight zero cells: profile of lanes beyond the band
  *   [16, 16 + PROF_ROWS*prof_stride/2)      profile rows, ONE BYTE per column (s - gap fits int8), widened
  *                                           to int16 pairs with two sign-replicating PRMTs per 4 cells
- *   [.., + (ring_rows+1)*ring_stride)       ring of score rows + one spare row for old predecessors; every row is
+ *   [.., + ring_rows*ring_stride)           ring of score rows (an older predecessor is staged in the slot the
+ *                                           current row will take: that slot holds a row out of reach); every row is
  *                                           RING_PAD_FRONT NEG cells | band cells | RING_PAD_BACK NEG cells
  */
 struct FillArgs { /* everything the row loop needs, and nothing else (keeps its register set small) */
@@ -149,7 +150,6 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
     const uint32_t prof_sa = fa.smem_sa + 32u;
     const uint32_t ring_sa = prof_sa + (((uint32_t)(PROF_ROWS * prof_stride) + 15u) & ~15u); /* profile: 1 byte per column */
     const uint32_t ring_row_bytes = (uint32_t)fa.ring_stride * 2u;
-    const uint32_t far_sa = ring_sa + (uint32_t)R * ring_row_bytes + RING_PAD_FRONT * 2u; /* band cells of the spare row */
     const int lane8 = lane * 8;
     int dyn_code = -1; /* letter currently held by the on-demand profile row */
 
@@ -166,7 +166,7 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
     }
     /* NEG pads of every ring row (the traceback tile overlays this memory between two fills) */
 #pragma unroll 1
-    for (int idx = lane; idx < (R + 1) * (1 + RING_PAD_BACK / 8); idx += 32) {
+    for (int idx = lane; idx < R * (1 + RING_PAD_BACK / 8); idx += 32) {
         const int row = idx / (1 + RING_PAD_BACK / 8), part = idx % (1 + RING_PAD_BACK / 8);
         /* the back pad follows THIS read's band cells (ring rows are sized for the widest band of the batch) */
         const uint32_t cell = part == 0 ? 0u : (uint32_t)(RING_PAD_FRONT + bw + 8 * (part - 1));
@@ -192,12 +192,13 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
     int best = NEG, end_row = 0;
     int po = 0; /* running offset into row_pfill (CSR is contiguous in row order) */
     int16_t* Srow = S; /* global score row of the current graph row */
+    /* rows in blocks of 32: the record stream is shifted once per block, not tested once per row */
+    int i = 1;
 #pragma unroll 1
-    for (int i = 1; i <= N; ++i) {
-        if ((i & 31) == 0) {
-            recA = recB;
-            recB = row_rec[i + 32 + lane];
-        }
+    for (int blk_end = 31; i <= N; blk_end += 32) {
+    const int i_end = blk_end < N ? blk_end : N;
+#pragma unroll 1
+    for (; i <= i_end; ++i) {
         const uint32_t rec = __shfl_sync(0xffffffffu, recA, i & 31);
         const int np = rec_npred(rec);
         const int bs = rec_bs(rec);
@@ -303,10 +304,23 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
                     else pe = row_pfill[po + q]; /* in-degree > 32: straight from memory */
                     const int off = c0 - (int)((pe & 0xFFEu) << 2);
                     uint32_t cell_sa = c0_sa + (uint32_t)((int)pe >> 12);
-                    if (__any_sync(0xffffffffu, (pe & 1u) != 0)) { /* predecessor older than the ring: stage its row in the spare slot */
+                    if (__any_sync(0xffffffffu, (pe & 1u) != 0)) { /* predecessor older than the ring */
                         const int pr = (int)(row_pred[po + q] & 0xFFFFu);
-                        fill_stage_far_row(S + (size_t)pr * stride, far_sa, bw);
-                        cell_sa = far_sa + (uint32_t)off * 2u;
+                        if (FULLW) {
+                            /* staged in the ring slot row i itself will take at the end of the row: it holds row i - R,
+                             * which no predecessor within the ring's reach can be */
+                            fill_stage_far_row(S + (size_t)pr * stride, ring_row_sa, bw);
+                            cell_sa = ring_row_sa + (uint32_t)off * 2u;
+                        } else {
+                            /* several chunks per row: the row's own slot already holds the finished chunks, so the
+                             * predecessor's cells come straight from the score matrix (L2/HBM; rare) */
+                            const int16_t* src = S + (size_t)pr * stride;
+                            uint4 V = make_uint4(NEG2, NEG2, NEG2, NEG2);
+                            if ((unsigned)off <= lim_v) V = *reinterpret_cast<const uint4*>(src + off);
+                            const uint32_t leftw = (unsigned)(off - 1) < lim_l ? (uint32_t)(uint16_t)src[off - 1] : (uint32_t)(uint16_t)NEG;
+                            POA_FILL_TERM();
+                            continue;
+                        }
                     }
                     POA_FILL_ACCUMULATE();
                 }
@@ -362,6 +376,9 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
         po += np;
         __syncwarp(); /* row i (ring + global) is visible to every lane before it is read */
     }
+    recA = recB;
+    recB = row_rec[blk_end + 33 + lane]; /* rows of the block after the next one */
+    }
     return end_row;
 }
 
@@ -395,7 +412,6 @@ __device__ __noinline__ int32_t fill_rows_wide(const FillArgs fa) {
     const uint32_t prof_sa = fa.smem_sa + 32u;
     const uint32_t ring_sa = prof_sa + (((uint32_t)(PROF_ROWS * prof_stride) + 15u) & ~15u);
     const uint32_t ring_row_bytes = (uint32_t)fa.ring_stride * 2u;
-    const uint32_t far_sa = ring_sa + (uint32_t)R * ring_row_bytes + RING_PAD_FRONT * 2u;
     const int col0 = lane * (8 * NV);                   /* first column of this lane */
     const uint32_t c0_sa = ring_sa + (uint32_t)col0 * 2u;
     const int ring_cols = fa.ring_stride - RING_PAD_FRONT; /* cells a ring row can take after its front pad */
@@ -414,7 +430,7 @@ __device__ __noinline__ int32_t fill_rows_wide(const FillArgs fa) {
         }
     }
     /* NEG front pad of every ring row (the cell left of column 0) */
-    if (lane <= R) sts128(ring_sa + (uint32_t)lane * ring_row_bytes, make_uint4(NEG2, NEG2, NEG2, NEG2));
+    if (lane < R) sts128(ring_sa + (uint32_t)lane * ring_row_bytes, make_uint4(NEG2, NEG2, NEG2, NEG2));
     /* row 0: S = 0 */
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
@@ -433,12 +449,13 @@ __device__ __noinline__ int32_t fill_rows_wide(const FillArgs fa) {
     int po = 0;
     int16_t* Srow = S;
     const int end_lane = fa.len / (8 * NV), end_cell = fa.len % (8 * NV); /* where column len lives */
+    /* rows in blocks of 32: the record stream is shifted once per block, not tested once per row */
+    int i = 1;
 #pragma unroll 1
-    for (int i = 1; i <= N; ++i) {
-        if ((i & 31) == 0) {
-            recA = recB;
-            recB = row_rec[i + 32 + lane];
-        }
+    for (int blk_end = 31; i <= N; blk_end += 32) {
+    const int i_end = blk_end < N ? blk_end : N;
+#pragma unroll 1
+    for (; i <= i_end; ++i) {
         const uint32_t rec = __shfl_sync(0xffffffffu, recA, i & 31);
         const int np = rec_npred(rec);
         const int prow = rec_prow(rec);
@@ -515,8 +532,10 @@ __device__ __noinline__ int32_t fill_rows_wide(const FillArgs fa) {
                 uint32_t cell_sa = c0_sa + (uint32_t)((int)pe >> 12);
                 if (__any_sync(0xffffffffu, (pe & 1u) != 0)) { /* predecessor older than the ring: stage its row in the spare slot */
                     const int pr = (int)(fa.row_pred[po + q] & 0xFFFFu);
-                    fill_stage_far_row(S + (size_t)pr * stride, far_sa, bw);
-                    cell_sa = far_sa + (uint32_t)col0 * 2u;
+                    /* staged in the ring slot this row takes at its end (it holds row i - R, out of the ring's reach) */
+                    const uint32_t own_sa = ring_sa + RING_PAD_FRONT * 2u + (uint32_t)(i & ring_mask) * ring_row_bytes;
+                    fill_stage_far_row(S + (size_t)pr * stride, own_sa, bw);
+                    cell_sa = own_sa + (uint32_t)col0 * 2u;
                 }
                 POA_WIDE_TERM(cell_sa);
             }
@@ -558,6 +577,9 @@ __device__ __noinline__ int32_t fill_rows_wide(const FillArgs fa) {
         }
         po += np;
         __syncwarp();
+    }
+    recA = recB;
+    recB = row_rec[blk_end + 33 + lane];
     }
     return end_row;
 }

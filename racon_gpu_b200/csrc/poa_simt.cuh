@@ -44,12 +44,24 @@ struct PerLane {
 #define POA_LANE0 if ((threadIdx.x & 31u) == 0u)
 #define POA_SYNC() __syncwarp()
 
-/* Warp-uniform values and the compiler.  Control flow that contains a warp collective (shuffle, vote, __syncwarp) is
- * cheap only when the compiler can PROVE it warp-uniform: otherwise every collective of the function gets a
- * "BRA.DIV -> WARPSYNC.COLLECTIVE" slow path, BSSY/BSYNC brackets and the registers to feed them (a quarter of the
- * fill's instructions before this was understood).  A value read back from a shuffle or from inline-asm memory access
- * is uniform in fact but not provably; the results of votes and of redux.sync (CREDUX writes a uniform register) are.
- * poa_uniform() launders a de-facto uniform int through one CREDUX; warp_bcast0() and the scan total use it. */
+/* Warp-uniform control flow and the compiler (measured on ptxas 12.9 / sm_100a; tests/test_codegen.py pins it).
+ *
+ * A warp collective (shuffle, vote, redux, __syncwarp) is one instruction only where ptxas can PROVE that the whole
+ * warp arrives together.  As soon as ONE collective of the module sits in control flow it cannot prove uniform, EVERY
+ * collective of EVERY function gets a "BRA.DIV -> WARPSYNC.COLLECTIVE" slow path, BSSY/BSYNC brackets and the
+ * registers to feed them: +43 % instructions, 14 % fewer windows/s on this kernel.  The engine is one window per warp,
+ * so its control flow IS uniform; what it takes to make that provable:
+ *   1. Scalars reach a noinline phase function BY VALUE (Params, ReadGeom, lengths).  A value loaded through a
+ *      reference parameter lives in local memory and counts as lane-dependent.
+ *   2. State that must come back through a reference (WinState) is laundered after the call (winstate_uniform) and
+ *      at the function's entry: poa_uniform() = redux.sync, whose result lands in a uniform register (CREDUX).
+ *   3. Values read back from a shuffle, from inline-asm memory accesses or from generic-pointer loads are uniform in
+ *      fact but not provably: launder them (poa_uniform / poa_uniform_pred = vote) before they steer a loop or a branch
+ *      that contains a collective -- the path position in the traceback, the row record in the fill.
+ *   4. Never leave a loop or a function from lane-dependent control flow: set a flag, decide by a vote.
+ *   5. After a lane-0 block that is followed by a loop back edge, reconverge explicitly (__syncwarp).
+ *   6. Keep the number of live uniform values small: derive (edge capacity from node capacity) instead of carrying.
+ * In the proven state __syncwarp() costs no instruction at all and uniform arithmetic moves to the uniform datapath. */
 POA_FN int poa_uniform(int x) { return __reduce_max_sync(0xffffffffu, x); }
 /* a de-facto uniform predicate made provably uniform by a vote */
 POA_FN bool poa_uniform_pred(bool x) { return __any_sync(0xffffffffu, x) != 0; }
