@@ -522,6 +522,10 @@ int32_t b200poa_batch_create(int32_t device_id, void* stream, size_t max_gpu_mem
     p.mismatch = mismatch_score;
     p.gap = gap_score;
     p.serial_topsort = std::getenv("B200POA_SERIAL_TOPSORT") ? 1 : 0;
+    p.force_cells32 = std::getenv("B200POA_FORCE_CELLS32") ? 1 : 0; /* tests only */
+    /* 32-bit score cells: the slots are sized for them only when a read within this batch's limits could
+     * overflow int16 (worst case: a path through max_nodes columns), which racon's scorings and limits never do */
+    p.wide_cells = (p.force_cells32 || !score_range_ok(p, p.max_nodes, p.max_len)) ? 1 : 0;
     p.ring_rows = 8;
     p.ring_stride = p.stride;
     if (p.max_nodes > 65000) {

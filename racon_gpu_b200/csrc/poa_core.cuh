@@ -87,17 +87,21 @@ struct Params {
     int32_t serial_topsort; /* tests: use the serial DFS instead of the per-root sort */
     int32_t ring_rows;      /* fill: rows in the shared-memory score ring (power of two) */
     int32_t ring_stride;    /* fill: int16 cells per ring row */
+    int32_t wide_cells;     /* the score region of a slot is sized for int32 cells: a read whose alignment does not fit
+                               int16 (score_range_ok) is filled and traced with 32-bit cells -- the switch spoa makes,
+                               simd_alignment_engine.cpp:668-673; cudapoa instantiates int32 per batch, batch.cu:114-138 */
+    int32_t force_cells32;  /* tests: every read takes the 32-bit path */
     int32_t adaptive;       /* band_width is only the FIRST try of a read: a traceback that comes close to the band's
                                edge re-aligns the read with twice the width (cudapoa's retry protocol,
                                cudapoa_kernels.cuh:257-303, cudapoa_nw_adaptive_banded.cuh:265-281, 462-480) */
 };
 
 #if POA_DEVICE
-__host__ __device__ __forceinline__
+#define POA_HD __host__ __device__ __forceinline__
 #else
-static inline
+#define POA_HD static inline
 #endif
-int32_t poa_edge_capacity(int32_t max_nodes) { return 6 * max_nodes < 65000 ? 6 * max_nodes : 65000; }
+POA_HD int32_t poa_edge_capacity(int32_t max_nodes) { return 6 * max_nodes < 65000 ? 6 * max_nodes : 65000; }
 
 /* Per resident warp workspace.  All pointers are into one device slab (see slot_bytes()). */
 struct Slot {
@@ -204,7 +208,7 @@ void slot_bind(Slot& s, uint8_t* base, const Params& p, size_t* total_out) {
     POA_CARVE(c_pred, int32_t, MN);
     o = (o + 255) / 256 * 256;
     s.S = base ? reinterpret_cast<int16_t*>(base + o) : nullptr;
-    o += sizeof(int16_t) * (MN + 1) * (size_t)p.stride;
+    o += (p.wide_cells ? sizeof(int32_t) : sizeof(int16_t)) * (MN + 1) * (size_t)p.stride;
     o = (o + 255) / 256 * 256;
 #undef POA_CARVE
     if (total_out) *total_out = o;
@@ -739,6 +743,140 @@ POA_FN int32_t score_at_bs(const Slot& s, const Params& p, const ReadGeom& g, in
     const int32_t o = col - bs;
     if (o < 0 || o >= g.bw) return NEG;
     return s.S[(size_t)row * p.stride + o];
+}
+
+/* ------------------------------------------------------------------------------------------
+ * 32-bit cells: the fallback for alignments that do not fit int16 (score_range_ok), i.e. where spoa switches its
+ * SIMD engine to int32 (simd_alignment_engine.cpp:668-673).  Same recurrence, same row program, same band, same
+ * skewed domain S = H - j*gap, one cell per lane per pass, predecessor rows read back from the score matrix (no
+ * shared-memory ring), and a plain serial walk for the traceback: a correct path for rare, very large windows, not a
+ * fast one.  The matrix overlays the int16 score region (Params::wide_cells: sized for it).
+ * ---------------------------------------------------------------------------------------- */
+constexpr int32_t NEG32 = -(1 << 29);
+
+POA_FN int32_t cell32(const int32_t* S32, int32_t stride, int32_t bw, int32_t row, int32_t bs, int32_t col) {
+    if (col < 0) return NEG32;
+    const int32_t o = col - bs;
+    if (o < 0 || o >= bw) return NEG32;
+    return S32[(size_t)row * stride + o];
+}
+
+POA_FN_NOINLINE int32_t fill_rows_i32(const Slot& s_ref, const Params p, const ReadGeom g, const uint8_t* read) {
+    const Slot s = s_ref;
+    int32_t* const S32 = reinterpret_cast<int32_t*>(s.S);
+    const int32_t N = g.n_rows, bw = g.bw, stride = p.stride;
+    const int32_t mg = p.match - p.gap, xg = p.mismatch - p.gap;
+    for (int32_t o0 = 0; o0 < bw; o0 += 32) {
+        POA_LANES(l) {
+            if (o0 + l < bw) S32[o0 + l] = 0; /* row 0: H = j*gap  =>  S = 0 */
+        }
+    }
+    POA_SYNC();
+    int32_t best = NEG32 - 1, end_row = 0;
+    for (int32_t i = 1; i <= N; ++i) {
+        const uint32_t rec = s.row_rec[i];
+        const int32_t code = rec_code(rec), np = rec_npred(rec), bs = rec_bs(rec);
+        const int32_t po = (int32_t)s.row_poff[i];
+        int32_t carry = NEG32;
+        for (int32_t o0 = 0; o0 < bw; o0 += 32) {
+            PerLane<int> x;
+            POA_LANES(l) {
+                const int32_t o = o0 + l, c = bs + o;
+                int32_t t = NEG32;
+                if (o < bw) {
+                    const int32_t prof = (c >= 1 && c <= g.len && (int32_t)read[c - 1] == code) ? mg : xg;
+                    for (int32_t k = 0; k < np; ++k) {
+                        const uint32_t pe = s.row_pred[po + k];
+                        const int32_t pr = (int32_t)(pe & 0xFFFFu), pbs = (int32_t)(pe >> 16);
+                        const int32_t d = cell32(S32, stride, bw, pr, pbs, c - 1) + prof;
+                        const int32_t v = cell32(S32, stride, bw, pr, pbs, c) + p.gap;
+                        if (d > t) t = d;
+                        if (v > t) t = v;
+                    }
+                }
+                x[l] = t;
+            }
+            warp_incl_max(x);
+            POA_LANES(l) {
+                const int32_t o = o0 + l;
+                int32_t t = x[l] > carry ? x[l] : carry;
+                if (t < NEG32) t = NEG32;
+                x[l] = t;
+                if (o < bw) S32[(size_t)i * stride + o] = t;
+            }
+            carry = poa_uniform(warp_get(x, 31));
+        }
+        POA_SYNC(); /* row i is visible to every lane before it is read as a predecessor */
+        if (rec_sink(rec)) {
+            const int32_t v = cell32(S32, stride, bw, i, bs, g.len);
+            if (v > best) {
+                best = v;
+                end_row = i;
+            }
+        }
+    }
+    return end_row;
+}
+
+/* spoa's traceback priority (sisd_alignment_engine.cpp:366-424) on the int32 matrix: serial on lane 0. */
+POA_FN_NOINLINE int32_t traceback_i32(const Slot& s_ref, const Params p, WinState& st, const ReadGeom g, int32_t end_row,
+                                      const uint8_t* read, const uint16_t* row_node) {
+    const Slot s = s_ref;
+    const int32_t* const S32 = reinterpret_cast<const int32_t*>(s.S);
+    const int32_t cap = p.max_nodes + p.max_len + 2, stride = p.stride, bw = g.bw;
+    const int32_t mg = p.match - p.gap, xg = p.mismatch - p.gap;
+    int32_t w = cap, lost = 0;
+    POA_LANE0 {
+        int32_t i = end_row, j = g.len;
+        while (!(i == 0 && j == 0) && !lost) {
+            if (w <= 0) {
+                lost = 1;
+                break;
+            }
+            int32_t ni = i, nj = j;
+            if (i == 0) {
+                nj = j - 1; /* row 0: only horizontal moves are left */
+            } else {
+                const uint32_t rec = s.row_rec[i];
+                const int32_t np = rec_npred(rec), bs = rec_bs(rec), po = (int32_t)s.row_poff[i];
+                const int32_t cur = cell32(S32, stride, bw, i, bs, j);
+                const int32_t prof = (j > 0 && rec_code(rec) == (int32_t)read[j - 1]) ? mg : xg;
+                bool found = false;
+                for (int32_t k = 0; k < np && !found && j > 0; ++k) { /* diagonal, in-edges in order */
+                    const uint32_t pe = s.row_pred[po + k];
+                    if (cell32(S32, stride, bw, (int32_t)(pe & 0xFFFFu), (int32_t)(pe >> 16), j - 1) + prof == cur) {
+                        ni = (int32_t)(pe & 0xFFFFu);
+                        nj = j - 1;
+                        found = true;
+                    }
+                }
+                for (int32_t k = 0; k < np && !found; ++k) { /* vertical, in-edges in order */
+                    const uint32_t pe = s.row_pred[po + k];
+                    if (cell32(S32, stride, bw, (int32_t)(pe & 0xFFFFu), (int32_t)(pe >> 16), j) + p.gap == cur) {
+                        ni = (int32_t)(pe & 0xFFFFu);
+                        found = true;
+                    }
+                }
+                if (!found) {
+                    if (j > 0 && cell32(S32, stride, bw, i, bs, j - 1) == cur) nj = j - 1; /* horizontal */
+                    else lost = 1;
+                }
+            }
+            if (lost) break;
+            --w;
+            s.tb_node[w] = (int16_t)((i == ni) ? -1 : (int32_t)row_node[i - 1]);
+            s.tb_pos[w] = (int16_t)((j == nj) ? -1 : j - 1);
+            i = ni;
+            j = nj;
+        }
+    }
+    POA_SYNC();
+    w = warp_bcast0(w);
+    if (warp_bcast0(lost)) {
+        st.status = ST_TRACEBACK_LOST;
+        return cap;
+    }
+    return w;
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -1921,7 +2059,7 @@ POA_FN_NOINLINE void generate_consensus(const Slot& s_ref, const Params p_ref, W
  * max|score| * (nodes + len + 17) < 32767; cudapoa picks the width statically, cudapoa_limits.hpp:34-53).
  * Outside them the window reports ST_SCORE_RANGE_EXCEEDED.
  * ---------------------------------------------------------------------------------------- */
-POA_FN bool score_range_ok(const Params& p, int32_t n_columns, int32_t len) {
+POA_HD bool score_range_ok(const Params& p, int32_t n_columns, int32_t len) {
     const int32_t mg = p.match - p.gap, xg = p.mismatch - p.gap; /* the fill keeps them as int8 */
     if (mg < -128 || mg > 127 || xg < -128 || xg > 127 || p.gap < -128 || p.gap > 127) return false;
     int32_t lo_step = p.gap < 0 ? p.gap : 0;
@@ -1961,7 +2099,9 @@ POA_FN void process_window(const Slot& s, const Params& p, const WindowView& wv,
         const int8_t* wt = wo >= 0 ? wv.weights + wo : nullptr;
         const int32_t wconst = wo >= 0 ? 0 : (int32_t)(-1 - wo);
         const int32_t len = (int32_t)(wv.seq_off[r + 1] - wv.seq_off[r]);
-        if (!score_range_ok(p, st.n_columns, len)) {
+        /* int16 cells whenever the alignment provably fits them; else 32-bit cells if the batch was sized for them */
+        const bool cells32 = p.force_cells32 != 0 || !score_range_ok(p, st.n_columns, len);
+        if (cells32 && !p.wide_cells) {
             st.status = ST_SCORE_RANGE_EXCEEDED;
             break;
         }
@@ -1989,13 +2129,14 @@ POA_FN void process_window(const Slot& s, const Params& p, const WindowView& wv,
             winstate_uniform(st);
             tm.lap(PH_PROGRAM);
             if (st.status != ST_SUCCESS) break;
-            const int32_t end_row = poa_uniform(fill(s, p, st, g, read));
+            const int32_t end_row = poa_uniform(cells32 ? fill_rows_i32(s, p, g, read) : fill(s, p, st, g, read));
             tm.lap(PH_FILL);
             st.band_hit = 0;
             if (end_row <= 0) {
                 st.status = ST_TRACEBACK_LOST;
             } else {
-                tb = poa_uniform(traceback(s, p, st, g, read, end_row, tbs, partial ? s.sub_at : s.node_at));
+                tb = poa_uniform(cells32 ? traceback_i32(s, p, st, g, end_row, read, partial ? s.sub_at : s.node_at)
+                                         : traceback(s, p, st, g, read, end_row, tbs, partial ? s.sub_at : s.node_at));
                 winstate_uniform(st);
                 tm.lap(PH_TRACEBACK);
             }

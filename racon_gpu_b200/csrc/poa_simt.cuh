@@ -89,6 +89,17 @@ POA_FN int warp_get(const PerLane<int>& x, int src) { return __shfl_sync(0xfffff
 POA_FN int warp_bcast0(int x) { return __reduce_max_sync(0xffffffffu, (threadIdx.x & 31u) == 0u ? x : (int)0x80000000); }
 /* out[l] = x[l+1] (lane 31 keeps its own value) */
 POA_FN void warp_shift_down1(const PerLane<int>& x, PerLane<int>& out) { out.v = __shfl_down_sync(0xffffffffu, x.v, 1); }
+/* inclusive prefix max over lanes, in place */
+POA_FN void warp_incl_max(PerLane<int>& x) {
+    const int lane = (int)(threadIdx.x & 31u);
+    int v = x.v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d && t > v) v = t;
+    }
+    x.v = v;
+}
 
 #else /* ---------------------------------------------------------------- host emulation */
 
@@ -142,6 +153,10 @@ POA_FN bool poa_uniform_pred(bool x) { return x; }
 POA_FN void warp_shift_down1(const PerLane<int>& x, PerLane<int>& out) {
     for (int l = 0; l < 31; ++l) out.v[l] = x.v[l + 1];
     out.v[31] = x.v[31];
+}
+POA_FN void warp_incl_max(PerLane<int>& x) {
+    for (int l = 1; l < 32; ++l)
+        if (x.v[l - 1] > x.v[l]) x.v[l] = x.v[l - 1];
 }
 
 #endif

@@ -97,7 +97,9 @@ void emu_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int
     p.match = m;
     p.mismatch = x;
     p.gap = gap;
-    p.serial_topsort = serial_topsort;
+    p.force_cells32 = (serial_topsort & 2) ? 1 : 0; /* bit 1 of the flag: every read through the 32-bit path */
+    p.wide_cells = (p.force_cells32 || !score_range_ok(p, p.max_nodes, p.max_len)) ? 1 : 0;
+    p.serial_topsort = serial_topsort & 1;
     p.ring_rows = 8;
     p.ring_stride = p.stride;
     Slot probe;

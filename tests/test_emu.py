@@ -86,8 +86,6 @@ def test_limits_report_status_instead_of_crashing(emu):
     #  poa_edge_capacity(), and a graph runs out of nodes long before it averages six in-edges per node)
     _, _, st, _ = emu.polish(b, order, M, X, G, max_len=400)
     assert (st == 2).all()  # exceeded_maximum_sequence_size
-    _, _, st, _ = emu.polish(b, order, 120, -120, -120)
-    assert (st == 12).all()  # int16 score range
 
 
 def test_long_window_stress_with_a_larger_sequence_limit(emu, oracle):
@@ -155,3 +153,26 @@ def test_adaptive_band_recovers_what_the_static_band_loses(oracle):
     assert (ast == 0).all() and ac == oc and all((a == c).all() for a, c in zip(acov, ocov))
     assert sum(edit_distance(a, c) for a, c in zip(sc, oc)) > 0       # the case is one the static band gets wrong
     assert scells < acells < 0.5 * fcells
+
+
+def test_int32_cells_where_int16_cannot_hold_the_alignment(emu, oracle):
+    """reads whose alignment does not provably fit int16 (score_range_ok) are filled and traced with 32-bit
+    cells, the switch spoa makes (simd_alignment_engine.cpp:668-673).  Forced on ordinary windows the 32-bit path must
+    be exact; an extreme scoring scheme takes it by itself."""
+    b = synth_windows(12, 300, 16, 0.15, seed=9, with_quality=True)
+    order = api.processing_order(b)
+    oc, ocov, _ = oracle.polish(b, order, M, X, G, tgs=False, trim=False, threads=8)
+    ec, ecov, st, _ = emu.polish(b, order, M, X, G, band=0, serial_topsort=2)  # bit 1: force 32-bit cells
+    assert (st == 0).all() and ec == oc and all((a == c).all() for a, c in zip(ecov, ocov))
+    bc, _, st, _ = emu.polish(b, order, M, X, G, band=256, serial_topsort=2)
+    assert (st == 0).all() and bc == oc
+    pb = __import__("common").partial_span_windows()
+    po = api.processing_order(pb)
+    oc, ocov, _ = oracle.polish(pb, po, M, X, G, tgs=False, trim=False, threads=8)
+    ec, ecov, st, _ = emu.polish(pb, po, M, X, G, band=0, serial_topsort=2)
+    assert (st == 0).all() and ec == oc and all((a == c).all() for a, c in zip(ecov, ocov))
+    b = synth_windows(4, 500, 32, 0.15, seed=3)
+    order = api.processing_order(b)
+    oc, _, _ = oracle.polish(b, order, 120, -120, -120, tgs=False, trim=False, threads=8)
+    ec, _, st, _ = emu.polish(b, order, 120, -120, -120)
+    assert (st == 0).all() and ec == oc

@@ -387,3 +387,21 @@ def test_adaptive_band_on_the_gpu(oracle):
     r_static = gpu_untrimmed(a, banded=True)
     r_adapt = gpu_untrimmed(a, banded="adaptive")
     assert r_static[0] == r_adapt[0]
+
+
+def test_int32_cells_on_the_gpu(oracle, monkeypatch):
+    """32-bit score cells (spoa's int32 switch): a scoring scheme int16 cannot hold runs through them on its own, and
+    forced on ordinary windows (B200POA_FORCE_CELLS32, read at batch creation) they are bit-exact too."""
+    b = synth_windows(8, 500, 32, 0.15, seed=3)
+    order = api.processing_order(b)
+    oc, ocov, _ = oracle.polish(b, order, 120, -120, -120, tgs=False, trim=False, threads=16)
+    gc, gcov, st = gpu_untrimmed(b, match=120, mismatch=-120, gap=-120)
+    assert (st == 0).all() and gc == oc and all((a == c).all() for a, c in zip(gcov, ocov))
+    monkeypatch.setenv("B200POA_FORCE_CELLS32", "1")
+    from common import partial_span_windows
+    for w in (synth_windows(24, 300, 16, 0.15, seed=9, with_quality=True), partial_span_windows()):
+        order = api.processing_order(w)
+        oc, ocov, _ = oracle.polish(w, order, M, X, G, tgs=False, trim=False, threads=16)
+        for banded in (False, True):
+            gc, gcov, st = gpu_untrimmed(w, banded=banded)
+            assert (st == 0).all() and gc == oc and all((a == c).all() for a, c in zip(gcov, ocov))
