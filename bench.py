@@ -46,6 +46,8 @@ WORKLOADS = {
     "A_full": (10000, 500, 32, 0.15, False, 1023, 2),
     "B_banded": (4096, 1024, 64, 0.12, True, 1279, 4),   # long-window stress shape
     "C_small": (100, 500, 8, 0.05, False, 1023, 0),
+    # BASELINE configs[3] per GPU: 1M windows over 8 GPUs, cudapoa-batches=8 -> 125k windows and 8 batch processors per GPU
+    "A_banded_1M": (125000, 500, 32, 0.15, True, 1023, 3),
 }
 
 

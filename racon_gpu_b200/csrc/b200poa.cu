@@ -390,6 +390,8 @@ static int32_t alloc_batch_memory(b200poa_batch* b) {
     const Params& p = b->p;
     const size_t MP = (size_t)b->max_poas, MS = (size_t)b->max_seqs, AC = (size_t)b->arena_cap;
     CU_TRY(cudaMalloc(&b->d_slab, (size_t)b->n_slots * b->slot_bytes));
+    if (const char* env = std::getenv("B200POA_SLAB_FILL")) /* debugging: the engine must not depend on what a slot held before */
+        CU_TRY(cudaMemset(b->d_slab, std::atoi(env), (size_t)b->n_slots * b->slot_bytes));
     CU_TRY(cudaMalloc(&b->d_bases, AC));
     CU_TRY(cudaMalloc(&b->d_weights, AC));
     CU_TRY(cudaMalloc(&b->d_seq_off, (MS + 1) * sizeof(int64_t)));

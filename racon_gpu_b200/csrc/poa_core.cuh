@@ -126,6 +126,8 @@ struct Slot {
     int32_t* e_w;       /* [ME] total weight                                 */
     uint8_t* e_ord;     /* [ME] position of the edge in its target's in-edge list (fixed at creation) */
     /* per-read "row program": the graph linearised in rank order (row = rank + 1) */
+    uint32_t* row_meta; /* [MN] by RANK: letter | sink << 8 | in-degree << 16 of the node at that rank.  Written where the
+                           ranks are (topological sort, backbone init), read by the row program: no gather through node_at */
     uint32_t* row_rec;  /* [MN+1] packed row record, see rec_make()                */
     uint32_t* row_poff; /* [MN+2] offset of the row's predecessor list       */
     uint32_t* row_pred; /* [ME+MN] predecessor ROW index (0 = virtual row) | its band start << 16, in in-edge order */
@@ -190,6 +192,7 @@ void slot_bind(Slot& s, uint8_t* base, const Params& p, size_t* total_out) {
     POA_CARVE(e_next, uint16_t, ME);
     POA_CARVE(e_w, int32_t, ME);
     POA_CARVE(e_ord, uint8_t, ME);
+    POA_CARVE(row_meta, uint32_t, MN);
     POA_CARVE(row_rec, uint32_t, MN + 1 + 128); /* +128: the fill prefetches 32-row blocks up to three blocks past the end */
     POA_CARVE(row_poff, uint32_t, MN + 2);
     POA_CARVE(row_pred, uint32_t, ME + MN + 96);
@@ -317,6 +320,11 @@ __device__ unsigned long long g_subtimers[32];
 #define POA_SUB_LAP(k) ((void)0)
 #endif
 
+/* row_meta entry: letter | sink << 8 | in-degree << 16 */
+POA_FN uint32_t meta_make(int32_t code, bool sink, int32_t nin) {
+    return (uint32_t)code | (sink ? 0x100u : 0u) | ((uint32_t)nin << 16);
+}
+
 /* ------------------------------------------------------------------------------------------
  * Phase 0: backbone chain  (graph.cpp:274-292 add_sequence + :177-185; window.cpp:73-76)
  * ---------------------------------------------------------------------------------------- */
@@ -348,6 +356,7 @@ POA_FN_NOINLINE void init_backbone(const Slot& s_ref, const Params p_ref, WinSta
             s.dirty[k] = 0;
             s.rank_of[k] = (uint16_t)k;
             s.node_at[k] = (uint16_t)k;
+            s.row_meta[k] = meta_make(seq[k], k + 1 >= len, k > 0 ? 1 : 0);
             if (k > 0) { /* edge k-1 : (k-1) -> k */
                 s.e_src[k - 1] = (uint16_t)(k - 1);
                 s.e_dst[k - 1] = (uint16_t)k;
@@ -477,13 +486,12 @@ POA_FN_NOINLINE void build_program(const Slot& s_ref, const Params p_ref, WinSta
     POA_LANES(l) { wide[l] = 0; }
     for (int32_t base = 0; base < N; base += 64) {
         PerLane<int> c0, c1, z0, z1;
-        POA_LANES(l) { /* both rows' loads are independent: two round trips for 64 rows */
+        POA_LANES(l) { /* letter, in-degree and sink flag by rank: one coalesced load per row (row_meta) */
             const int32_t r0 = base + 2 * l, r1 = r0 + 1;
-            const int32_t v0 = r0 < N ? (int32_t)s.node_at[r0] : 0;
-            const int32_t v1 = r1 < N ? (int32_t)s.node_at[r1] : 0;
-            const int32_t d0 = s.nin[v0], d1 = s.nin[v1];
-            const int32_t k0 = s.code[v0], k1 = s.code[v1];
-            const bool s0 = s.nout[v0] == 0, s1 = s.nout[v1] == 0;
+            const uint32_t m0 = r0 < N ? s.row_meta[r0] : 0u, m1 = r1 < N ? s.row_meta[r1] : 0u;
+            const int32_t d0 = (int32_t)(m0 >> 16), d1 = (int32_t)(m1 >> 16);
+            const int32_t k0 = (int32_t)(m0 & 0xFFu), k1 = (int32_t)(m1 & 0xFFu);
+            const bool s0 = (m0 & 0x100u) != 0, s1 = (m1 & 0x100u) != 0;
             c0[l] = r0 < N ? (d0 ? d0 : 1) : 0;
             c1[l] = r1 < N ? (d1 ? d1 : 1) : 0;
             z0[l] = (r0 < N && d0 == 0) ? 1 : 0; /* no in-edge: the virtual predecessor row 0 */
@@ -1108,15 +1116,11 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params p, WinState& st, c
                     if (row >= 1) {
                         tile_copy4(A_rec, k, row_rec + row);
                         tile_copy4(A_poff, k, row_poff + row);
-                        tile_st_u16(A_node, k, node_at[row - 1]);
                     } else {
                         tile_st_u32(A_rec, k, 0u);
                         tile_st_u32(A_poff, k, 0u);
-                        tile_st_u16(A_node, k, 0u);
                     }
                 }
-                for (int32_t c = c_lo + l; c < c_lo + TB_COLS; c += 32) /* read bases under the tile's columns */
-                    tile_st_u8(A_readc, c - c_lo, (c >= 1 && c <= rlen) ? read[c - 1] : (uint8_t)0);
             }
             /* CSR entries of rows r_lo..r_hi are contiguous: [poff(r_lo'), poff(r_hi) + np(r_hi)) */
             pred_base = p_lo;
@@ -1124,6 +1128,27 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params p, WinState& st, c
             if (pred_n > TB_PRED_CAP) pred_n = TB_PRED_CAP; /* rows beyond the cap fall back to global */
             POA_LANES(l) {
                 for (int32_t e = l; e < pred_n; e += 32) tile_copy4(A_pred, e, row_pred + pred_base + e);
+            }
+            /* the two items that pass through registers (a 2-byte node id per row, the read bases under the tile) come
+             * last: their round trip overlaps the asynchronous copies already in flight instead of delaying them */
+            POA_LANES(l) {
+                uint32_t nd[TB_RPL];
+#pragma unroll
+                for (int32_t rr = 0; rr < TB_RPL; ++rr) {
+                    const int32_t row = r_hi - (l + 32 * rr);
+                    nd[rr] = row >= 1 ? (uint32_t)node_at[row - 1] : 0u; /* rows below r_lo are never read */
+                }
+                uint32_t rb[(TB_COLS + 31) / 32];
+#pragma unroll
+                for (int32_t u = 0; u < (TB_COLS + 31) / 32; ++u) {
+                    const int32_t c = c_lo + l + 32 * u;
+                    rb[u] = (c >= 1 && c <= rlen) ? (uint32_t)read[c - 1] : 0u;
+                }
+#pragma unroll
+                for (int32_t rr = 0; rr < TB_RPL; ++rr) tile_st_u16(A_node, l + 32 * rr, nd[rr]);
+#pragma unroll
+                for (int32_t u = 0; u < (TB_COLS + 31) / 32; ++u)
+                    if (l + 32 * u < TB_COLS) tile_st_u8(A_readc, l + 32 * u, rb[u]);
             }
             tile_copy_wait();
             POA_SYNC();
@@ -1659,7 +1684,11 @@ POA_FN_NOINLINE void topsort_serial(const Slot& s_ref, const Params p_ref, WinSt
     POA_SYNC();
     for (int32_t base = 0; base < N; base += 32) {
         POA_LANES(l) {
-            if (base + l < N) s.rank_of[s.node_at[base + l]] = (uint16_t)(base + l);
+            if (base + l < N) {
+                const int32_t v = s.node_at[base + l];
+                s.rank_of[v] = (uint16_t)(base + l);
+                s.row_meta[base + l] = meta_make(s.code[v], s.nout[v] == 0, s.nin[v]);
+            }
         }
     }
     POA_SYNC();
@@ -1813,15 +1842,19 @@ POA_FN_NOINLINE void topsort_roots(const Slot& s_ref, const Params p_ref, WinSta
     }
     POA_SYNC();
     POA_SUB_LAP(8);
-    /* 3. ranks (four nodes per lane per step, loads staged by dependency level) */
+    /* 3. ranks (four nodes per lane per step, loads staged by dependency level).  The row program of the NEXT read wants,
+     *    in rank order, each node's letter, in-degree and whether it is a sink: they are read here, where nodes are
+     *    visited in id order (coalesced), and written by rank -- instead of gathered through node_at later. */
     for (int32_t base = 0; base < N; base += 128) {
         POA_LANES(l) {
             int32_t q[4], lp[4], r[4];
+            uint32_t meta[4];
 #pragma unroll
             for (int32_t k = 0; k < 4; ++k) {
                 const int32_t v = base + 32 * k + l;
                 q[k] = v < N ? (int32_t)s.root[v] : 0;
                 lp[k] = v < N ? (int32_t)s.lpos[v] : 0;
+                meta[k] = v < N ? meta_make(s.code[v], s.nout[v] == 0, s.nin[v]) : 0u;
             }
 #pragma unroll
             for (int32_t k = 0; k < 4; ++k) r[k] = (int32_t)s.roff[q[k]] + lp[k];
@@ -1831,6 +1864,7 @@ POA_FN_NOINLINE void topsort_roots(const Slot& s_ref, const Params p_ref, WinSta
                 if (v < N) {
                     s.rank_of[v] = (uint16_t)r[k];
                     s.node_at[r[k]] = (uint16_t)v;
+                    s.row_meta[r[k]] = meta[k];
                 }
             }
         }
@@ -2127,9 +2161,11 @@ POA_FN void process_window(const Slot& s, const Params& p, const WindowView& wv,
             if (partial) build_program_sub(s, p, st, g);
             else build_program(s, p, st, g);
             winstate_uniform(st);
+            POA_FENCE();
             tm.lap(PH_PROGRAM);
             if (st.status != ST_SUCCESS) break;
             const int32_t end_row = poa_uniform(cells32 ? fill_rows_i32(s, p, g, read) : fill(s, p, st, g, read));
+            POA_FENCE(); /* the score rows must be in place before the traceback's asynchronous copies read them */
             tm.lap(PH_FILL);
             st.band_hit = 0;
             if (end_row <= 0) {
@@ -2138,6 +2174,7 @@ POA_FN void process_window(const Slot& s, const Params& p, const WindowView& wv,
                 tb = poa_uniform(cells32 ? traceback_i32(s, p, st, g, end_row, read, partial ? s.sub_at : s.node_at)
                                          : traceback(s, p, st, g, read, end_row, tbs, partial ? s.sub_at : s.node_at));
                 winstate_uniform(st);
+                POA_FENCE();
                 tm.lap(PH_TRACEBACK);
             }
             if (p.adaptive && g.banded && (st.band_hit || st.status == ST_TRACEBACK_LOST)) {
@@ -2150,11 +2187,13 @@ POA_FN void process_window(const Slot& s, const Params& p, const WindowView& wv,
         if (st.status != ST_SUCCESS) break;
         add_alignment(s, p, st, read, wt, wconst, len, tb);
         winstate_uniform(st);
+        POA_FENCE();
         tm.lap(PH_ADD);
         if (st.status != ST_SUCCESS) break;
         if (p.serial_topsort) topsort_serial(s, p, st);
         else topsort_roots(s, p, st);
         winstate_uniform(st);
+        POA_FENCE();
         tm.lap(PH_TOPSORT);
     }
     if (st.status == ST_SUCCESS) {

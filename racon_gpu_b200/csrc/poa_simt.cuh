@@ -43,6 +43,17 @@ struct PerLane {
 #define POA_LANES(l) for (int l = (int)(threadIdx.x & 31u), _poa_once = 1; _poa_once; _poa_once = 0)
 #define POA_LANE0 if ((threadIdx.x & 31u) == 0u)
 #define POA_SYNC() __syncwarp()
+/* Between two phases: what one lane wrote to the workspace (plain, streaming or atomic stores) must be visible to
+ * every access path the other lanes use next (cached loads, L1-bypassing asynchronous copies).  In the proven-uniform
+ * build __syncwarp() is elided altogether, so the ordering is asked for explicitly, once per phase boundary. */
+#ifndef POA_PHASE_FENCE
+#define POA_PHASE_FENCE 1
+#endif
+#if POA_PHASE_FENCE
+#define POA_FENCE() __threadfence_block()
+#else
+#define POA_FENCE() ((void)0)
+#endif
 
 /* Warp-uniform control flow and the compiler (measured on ptxas 12.9 / sm_100a; tests/test_codegen.py pins it).
  *
@@ -113,6 +124,7 @@ struct PerLane {
 #define POA_LANES(l) for (int l = 0; l < 32; ++l)
 #define POA_LANE0
 #define POA_SYNC() ((void)0)
+#define POA_FENCE() ((void)0)
 
 POA_FN int warp_exscan(PerLane<int>& x) {
     int run = 0;
