@@ -368,12 +368,12 @@ def test_adaptive_band_on_the_gpu(oracle):
     b = deletion_windows()
     order = identity_order(b)
     oc, ocov, _ = oracle.polish(b, order, M, X, G, tgs=False, trim=False, threads=16, stride=8192)
-    wins = [b.window(w)[0] for w in range(b.n_windows)]
+    wins = [b.window(w)[:2] for w in range(b.n_windows)]
     out = {}
     for mode in (True, "adaptive"):
         pb = api.PoaBatch(max_gpu_mem=MEM, banded=mode)
-        for seqs in wins:
-            assert pb.add_poa_group([(s, None) for s in seqs])[0] == 0
+        for seqs, wts in wins:  # the backbone carries its weight-0 quality, the reads none: same input as the oracle's
+            assert pb.add_poa_group(list(zip(seqs, wts)))[0] == 0
         pb.generate_poa()
         out[mode] = pb.get_consensus()
         pb.close()
