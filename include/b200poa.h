@@ -122,6 +122,24 @@ int32_t b200poa_batch_add_windows(b200poa_batch* b, int64_t n_windows, int64_t f
                                   const uint8_t* has_weights, const int32_t* begins,
                                   const int32_t* ends, int64_t* n_added, int32_t* seqs_added);
 
+/*
+ * Zero-staging variant of b200poa_batch_add_windows for a columnar arena that lives in PINNED host memory (what
+ * b200poa_arena_finalize produces): nothing is copied on the host; the batch records the byte range of the arena its
+ * windows span and b200poa_batch_generate uploads that range as it is (sequences in add order, the per-sequence tables
+ * carry the processing order).  `weight_mode[s]` (b200poa_weight_modes) says per sequence whether its weights are one
+ * constant (-1 - constant: nothing to ship) or explicit (>= 0: the weights arena range is uploaded too).  The arena
+ * must stay alive and unchanged until the batch's results have been fetched; windows must be added in arena order,
+ * and a batch is either staged or pinned between two resets.
+ */
+int32_t b200poa_batch_add_windows_pinned(b200poa_batch* b, int64_t n_windows, int64_t first,
+                                         const int64_t* win_seq_off, const int64_t* seq_off,
+                                         const uint8_t* bases, const int8_t* weights,
+                                         const uint8_t* has_weights, const int64_t* weight_mode,
+                                         const int32_t* begins, const int32_t* ends, int64_t* n_added,
+                                         int32_t* seqs_added);
+void b200poa_weight_modes(int64_t n_sequences, const int64_t* seq_off, const int8_t* weights,
+                          const uint8_t* has_weights, int64_t* weight_mode);
+
 int32_t b200poa_batch_total_poas(const b200poa_batch* b);
 
 /* Asynchronous on the batch's stream: H2D of the staged arena, the POA kernel, D2H of the results. */
@@ -248,13 +266,19 @@ int64_t b200poa_compact_rows(const uint8_t* rows, int64_t n_rows, int64_t stride
  * consumes.  Same argument checks as the reference (which exits; here: -1 / INVALID_ARGUMENT), layers of
  * different windows may arrive interleaved, layers of one window keep their add order.  Sequence and quality
  * pointers are borrowed until b200poa_arena_finalize copies them (quality -> weight = char - 33,
- * graph.cpp:138-147; nullptr quality -> weight 1, :124-129).  Host-only: no CUDA call is made. */
+ * graph.cpp:138-147; nullptr quality -> weight 1, :124-129).  Building is host-only; finalize additionally page-locks
+ * the arena when a CUDA device is present, so that b200poa_polisher_polish_arena uploads batches straight from it
+ * (b200poa_batch_add_windows_pinned: no per-batch staging copy). */
 typedef struct b200poa_arena b200poa_arena;
 b200poa_arena* b200poa_arena_create(void);
 int64_t b200poa_arena_add_window(b200poa_arena* a, const char* backbone, uint32_t backbone_length,
                                  const char* quality, uint32_t quality_length); /* window index or -1 */
 int32_t b200poa_arena_add_layer(b200poa_arena* a, int64_t window, const char* sequence, uint32_t sequence_length,
                                 const char* quality, uint32_t quality_length, uint32_t begin, uint32_t end);
+/* the same calls for windows that already exist as columns (layout of b200poa_polisher_polish) */
+int32_t b200poa_arena_append_columns(b200poa_arena* a, int64_t n_windows, const int64_t* win_seq_off,
+                                     const int64_t* seq_off, const uint8_t* bases, const int8_t* weights,
+                                     const uint8_t* has_weights, const int32_t* begins, const int32_t* ends);
 int32_t b200poa_arena_finalize(b200poa_arena* a);
 /* after finalize: pointers stay valid until destroy */
 int32_t b200poa_arena_view(const b200poa_arena* a, int64_t* n_windows, int64_t* n_sequences,

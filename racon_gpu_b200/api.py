@@ -38,7 +38,8 @@ ABI_SYMBOLS = (
     "b200poa_batch_generate", "b200poa_batch_upload", "b200poa_batch_launch",
     "b200poa_batch_download", "b200poa_batch_get_consensus", "b200poa_batch_id",
     "b200poa_batch_reset", "b200poa_batch_destroy", "b200poa_batch_get_info", "b200poa_batch_set_option",
-    "b200poa_polisher_create_ex", "b200poa_compact_rows",
+    "b200poa_polisher_create_ex", "b200poa_compact_rows", "b200poa_batch_add_windows_pinned", "b200poa_weight_modes",
+    "b200poa_arena_append_columns",
     "b200poa_status_string", "b200poa_batch_phase_cycles", "b200poa_polish_windows", "b200poa_polish_windows_via_adapter",
     "b200poa_polisher_create", "b200poa_polisher_polish", "b200poa_polisher_destroy",
     "b200poa_arena_create", "b200poa_arena_add_window", "b200poa_arena_add_layer", "b200poa_arena_finalize",
@@ -440,11 +441,14 @@ class Polisher:
         return cons, clen, pol.astype(bool), status
 
     def polish_arena(self, arena: "WindowArena", tgs: bool = True, trim: bool = True, max_windows_per_round: int = 0,
-                     stride: int = 2048):
-        """`polish` over windows built with WindowArena (b200poa_polisher_polish_arena)."""
+                     stride: int = 2048, out=None):
+        """`polish` over windows built with WindowArena (b200poa_polisher_polish_arena).  The finalized arena is
+        page-locked: every batch uploads its byte range straight from it, no staging copy on the host."""
         W = arena.n_windows
-        cons, clen = np.zeros((W, stride), dtype=np.uint8), np.zeros(W, dtype=np.int32)
-        pol, status = np.zeros(W, dtype=np.uint8), np.zeros(W, dtype=np.int32)
+        if out is None:
+            out = (np.zeros((W, stride), dtype=np.uint8), np.zeros(W, dtype=np.int32),
+                   np.zeros(W, dtype=np.uint8), np.zeros(W, dtype=np.int32))
+        cons, clen, pol, status = out
         launches, h2d, d2h = C.c_int64(0), C.c_int64(0), C.c_int64(0)
         st = self.lib.b200poa_polisher_polish_arena(
             self.handle, arena.handle, C.c_int32(int(tgs)), C.c_int32(int(trim)), C.c_int32(max_windows_per_round),
@@ -497,11 +501,28 @@ class WindowArena:
                                               C.c_uint32(begin), C.c_uint32(end))
         return st == SUCCESS
 
-    def finalize(self) -> WindowBatch:
-        """Group and copy; returns the arena as a WindowBatch (copies of the C arrays)."""
+    @classmethod
+    def from_batch(cls, batch: WindowBatch) -> "WindowArena":
+        """An arena holding the windows of a columnar batch (b200poa_arena_append_columns), finalized."""
+        a = cls()
+        st = a.lib.b200poa_arena_append_columns(
+            a.handle, C.c_int64(batch.n_windows), _p(batch.win_seq_off, C.c_int64), _p(batch.seq_off, C.c_int64),
+            _p(batch.bases, C.c_uint8), _p(batch.weights, C.c_int8), _p(batch.has_weights, C.c_uint8),
+            _p(batch.begins, C.c_int32), _p(batch.ends, C.c_int32))
+        if st != SUCCESS:
+            raise RuntimeError(f"b200poa_arena_append_columns failed: {status_string(st)}")
+        a.n_windows = batch.n_windows
+        a.finalize(view=False)
+        return a
+
+    def finalize(self, view: bool = True):
+        """Group and copy (and page-lock, where a CUDA device exists); returns the arena as a WindowBatch (copies of the
+        C arrays) unless view=False."""
         if self.lib.b200poa_arena_finalize(self.handle) != SUCCESS:
             raise RuntimeError("b200poa_arena_finalize failed")
         self._keep = []
+        if not view:
+            return None
         nw, ns = C.c_int64(0), C.c_int64(0)
         pw, ps = C.POINTER(C.c_int64)(), C.POINTER(C.c_int64)()
         pb, pwt, ph = C.POINTER(C.c_uint8)(), C.POINTER(C.c_int8)(), C.POINTER(C.c_uint8)()

@@ -42,7 +42,8 @@ struct KernelArgs {
     int32_t* cursor;     /* [0] atomic work cursor, [1] elements used in the output arenas (both zeroed before launch) */
     const uint8_t* bases;
     const int8_t* weights;      /* compact: sequences with non-constant weights only */
-    const int64_t* seq_off;     /* [n_seqs+1] */
+    const int64_t* seq_off;     /* [n_seqs] start in the bases arena, processing order */
+    const int32_t* seq_len;     /* [n_seqs] */
     const int64_t* w_off;       /* [n_seqs] offset into weights, or -1 - constant */
     const int32_t* win_seq_off; /* [n_windows+1] */
     const int32_t* win_flags;   /* per window: pre-set status (!= 0 => skip) */
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(32, POA_MIN_BLOCKS_PER_SM) poa_window_kernel(c
         wv.bases = a.bases;
         wv.weights = a.weights;
         wv.seq_off = a.seq_off + s0;
+        wv.seq_len = a.seq_len + s0;
         wv.w_off = a.w_off + s0;
         wv.seq_begin = a.seq_begin + s0;
         wv.seq_end = a.seq_end + s0;
@@ -175,6 +177,7 @@ struct b200poa_batch {
     int8_t* h_weights = nullptr;
     int64_t* h_seq_off = nullptr;
     int64_t* h_w_off = nullptr;
+    int32_t* h_seq_len = nullptr;
     int32_t* h_seq_begin = nullptr;
     int32_t* h_seq_end = nullptr;
     int32_t* h_win_seq_off = nullptr;
@@ -194,6 +197,7 @@ struct b200poa_batch {
     int8_t* d_weights = nullptr;
     int64_t* d_seq_off = nullptr;
     int64_t* d_w_off = nullptr;
+    int32_t* d_seq_len = nullptr;
     int32_t* d_seq_begin = nullptr;
     int32_t* d_seq_end = nullptr;
     int32_t* d_win_seq_off = nullptr;
@@ -213,6 +217,12 @@ struct b200poa_batch {
     int64_t seq_count = 0;
     int64_t base_count = 0;
     int64_t weight_count = 0;  /* bytes in the compact weights arena */
+    /* direct mode (b200poa_batch_add_windows_pinned): the batch's device arena mirrors the byte range [ext_lo, ext_hi)
+     * of the caller's pinned host arena -- uploaded straight from there, no staging copy on the host */
+    const uint8_t* ext_bases = nullptr;
+    const int8_t* ext_weights = nullptr;
+    int64_t ext_lo = 0, ext_hi = 0;
+    bool ext_any_weights = false;
     int64_t out_elems = 0;     /* elements the last downloaded launch used in the output arenas */
     bool results_fetched = false;
     int32_t download_coverage = 1; /* B200POA_OPT_DOWNLOAD_COVERAGE */
@@ -264,6 +274,7 @@ static void free_batch(b200poa_batch* b) {
     cudaFreeHost(b->h_weights);
     cudaFreeHost(b->h_seq_off);
     cudaFreeHost(b->h_w_off);
+    cudaFreeHost(b->h_seq_len);
     cudaFreeHost(b->h_seq_begin);
     cudaFreeHost(b->h_seq_end);
     cudaFreeHost(b->h_win_seq_off);
@@ -282,6 +293,7 @@ static void free_batch(b200poa_batch* b) {
     cudaFree(b->d_weights);
     cudaFree(b->d_seq_off);
     cudaFree(b->d_w_off);
+    cudaFree(b->d_seq_len);
     cudaFree(b->d_seq_begin);
     cudaFree(b->d_seq_end);
     cudaFree(b->d_win_seq_off);
@@ -299,35 +311,59 @@ static void free_batch(b200poa_batch* b) {
     delete b;
 }
 
-/* stage one window whose sequences are given in processing order through a getter */
-template <class Get>
-static int32_t stage_window(b200poa_batch* b, int32_t n, Get get, int32_t* per_seq_status, int32_t* n_added_out) {
+/* One sequence as the staging code sees it. */
+struct StagedSeq {
+    const char* seq;
+    const int8_t* w;   /* nullptr: no quality string (weight 1 per base) */
+    int32_t len, bg, en;
+    int64_t host_off;  /* direct mode: offset of the sequence in the caller's pinned arena */
+    int64_t wmode;     /* direct mode: precomputed weight mode (-1 - constant, or >= 0: explicit weights); else INT64_MIN */
+};
+constexpr int64_t WMODE_UNKNOWN = INT64_MIN;
+
+/* Stage one window whose sequences are given in processing order through a getter.
+ * DIRECT = false: bases (and non-constant weights) are copied into the batch's own pinned staging arena.
+ * DIRECT = true : nothing is copied; the tables point into the caller's pinned arena, whose byte range
+ *                 [ext_lo, ext_hi) is uploaded as it is (sequences in add order; the tables carry the processing order). */
+template <bool DIRECT, class Get>
+static int32_t stage_window(b200poa_batch* b, int32_t n, Get get, int32_t* per_seq_status, int32_t* n_added_out,
+                            int64_t win_lo = 0, int64_t win_hi = 0) {
     /* cudapoa_batch.cuh:108-148: the whole group must fit or the batch reports "full" */
     if (b->poa_count >= b->max_poas) return B200POA_EXCEEDED_MAXIMUM_POAS;
     int64_t bytes = 0;
     int32_t n_ok = 0;
     for (int32_t i = 0; i < n; ++i) {
-        const char* seq; const int8_t* w; int32_t len, bg, en;
-        get(i, seq, w, len, bg, en);
-        if (len <= b->cfg.max_sequence_size && n_ok < b->cfg.max_sequences_per_poa) {
-            if (len <= 0) return B200POA_INVALID_ARGUMENT;
-            if (w) /* validate BEFORE anything is staged (cudapoa_batch.cuh:533-537 throws) */
-                for (int32_t k = 0; k < len; ++k)
-                    if (w[k] < 0) return B200POA_INVALID_ARGUMENT;
-            bytes += len;
+        StagedSeq q;
+        get(i, q);
+        if (q.len <= b->cfg.max_sequence_size && n_ok < b->cfg.max_sequences_per_poa) {
+            if (q.len <= 0) return B200POA_INVALID_ARGUMENT;
+            if (q.w && q.wmode == WMODE_UNKNOWN) /* validate BEFORE anything is staged (cudapoa_batch.cuh:533-537 throws) */
+                for (int32_t k = 0; k < q.len; ++k)
+                    if (q.w[k] < 0) return B200POA_INVALID_ARGUMENT;
+            bytes += q.len;
             ++n_ok;
         }
     }
-    if (b->base_count + bytes > b->arena_cap || b->seq_count + n_ok > b->max_seqs)
+    if (DIRECT) { /* the device arena mirrors the contiguous host range of the windows staged so far */
+        const int64_t lo = b->poa_count == 0 ? win_lo : b->ext_lo;
+        if (win_lo < lo || win_hi - lo > b->arena_cap || b->seq_count + n_ok > b->max_seqs) return B200POA_EXCEEDED_MAXIMUM_POAS;
+    } else if (b->base_count + bytes > b->arena_cap || b->seq_count + n_ok > b->max_seqs) {
         return B200POA_EXCEEDED_MAXIMUM_POAS;
+    }
+    if (DIRECT) {
+        if (b->poa_count == 0) b->ext_lo = win_lo;
+        b->ext_hi = win_hi;
+        b->base_count = b->ext_hi - b->ext_lo;
+    }
 
     int32_t flag = 0, added = 0;
     int64_t cost = 0;
     int32_t bb_len = 0;
     bool backbone_rejected = false;
     for (int32_t i = 0; i < n; ++i) {
-        const char* seq; const int8_t* w; int32_t len, bg, en;
-        get(i, seq, w, len, bg, en);
+        StagedSeq q;
+        get(i, q);
+        const int32_t len = q.len, bg = q.bg, en = q.en;
         int32_t st = B200POA_SUCCESS;
         if (len > b->cfg.max_sequence_size) st = B200POA_EXCEEDED_MAXIMUM_SEQUENCE_SIZE; /* cudapoa_batch.cuh:501-504 */
         else if (added >= b->cfg.max_sequences_per_poa) st = B200POA_EXCEEDED_MAXIMUM_SEQUENCES_PER_POA; /* :513-516 */
@@ -353,25 +389,37 @@ static int32_t stage_window(b200poa_batch* b, int32_t n, Get get, int32_t* per_s
         b->h_seq_begin[b->seq_count] = sp_b;
         b->h_seq_end[b->seq_count] = sp_e;
         if (len > b->max_len_staged) b->max_len_staged = len;
-        std::memcpy(b->h_bases + b->base_count, seq, (size_t)len);
         /* weights: a sequence whose bases all weigh the same (no quality string => 1, cudapoa_batch.cuh:525-530;
          * the '!' dummy quality of a FASTA target => 0) ships only that constant */
         int64_t wo = -1 - 1;
-        if (w) {
-            bool constant = true;
-            for (int32_t k = 1; k < len && constant; ++k) constant = w[k] == w[0];
-            if (constant) {
-                wo = -1 - (int64_t)w[0];
-            } else {
-                wo = b->weight_count;
-                std::memcpy(b->h_weights + b->weight_count, w, (size_t)len);
-                b->weight_count += len;
+        if (DIRECT) {
+            b->h_seq_off[b->seq_count] = q.host_off - b->ext_lo;
+            if (q.w) {
+                wo = q.wmode;
+                if (wo >= 0) { /* explicit weights: the weights arena mirrors the same host range */
+                    wo = q.host_off - b->ext_lo;
+                    b->ext_any_weights = true;
+                }
             }
+        } else {
+            b->h_seq_off[b->seq_count] = b->base_count;
+            std::memcpy(b->h_bases + b->base_count, q.seq, (size_t)len);
+            if (q.w) {
+                bool constant = true;
+                for (int32_t k = 1; k < len && constant; ++k) constant = q.w[k] == q.w[0];
+                if (constant) {
+                    wo = -1 - (int64_t)q.w[0];
+                } else {
+                    wo = b->weight_count;
+                    std::memcpy(b->h_weights + b->weight_count, q.w, (size_t)len);
+                    b->weight_count += len;
+                }
+            }
+            b->base_count += len;
         }
         b->h_w_off[b->seq_count] = wo;
-        b->base_count += len;
+        b->h_seq_len[b->seq_count] = len;
         b->seq_count += 1;
-        b->h_seq_off[b->seq_count] = b->base_count;
         cost += (int64_t)len * (bb_len + (int64_t)added * (bb_len / 8 + 1));
         ++added;
     }
@@ -396,6 +444,7 @@ static int32_t alloc_batch_memory(b200poa_batch* b) {
     CU_TRY(cudaMalloc(&b->d_weights, AC));
     CU_TRY(cudaMalloc(&b->d_seq_off, (MS + 1) * sizeof(int64_t)));
     CU_TRY(cudaMalloc(&b->d_w_off, (MS + 1) * sizeof(int64_t)));
+    CU_TRY(cudaMalloc(&b->d_seq_len, (MS + 1) * sizeof(int32_t)));
     CU_TRY(cudaMalloc(&b->d_seq_begin, (MS + 1) * sizeof(int32_t)));
     CU_TRY(cudaMalloc(&b->d_seq_end, (MS + 1) * sizeof(int32_t)));
     CU_TRY(cudaMalloc(&b->d_win_seq_off, (MP + 1) * sizeof(int32_t)));
@@ -418,6 +467,7 @@ static int32_t alloc_batch_memory(b200poa_batch* b) {
     CU_TRY(cudaHostAlloc(&b->h_weights, AC, cudaHostAllocDefault));
     CU_TRY(cudaHostAlloc(&b->h_seq_off, (MS + 1) * sizeof(int64_t), cudaHostAllocDefault));
     CU_TRY(cudaHostAlloc(&b->h_w_off, (MS + 1) * sizeof(int64_t), cudaHostAllocDefault));
+    CU_TRY(cudaHostAlloc(&b->h_seq_len, (MS + 1) * sizeof(int32_t), cudaHostAllocDefault));
     CU_TRY(cudaHostAlloc(&b->h_seq_begin, (MS + 1) * sizeof(int32_t), cudaHostAllocDefault));
     CU_TRY(cudaHostAlloc(&b->h_seq_end, (MS + 1) * sizeof(int32_t), cudaHostAllocDefault));
     CU_TRY(cudaHostAlloc(&b->h_win_seq_off, (MP + 1) * sizeof(int32_t), cudaHostAllocDefault));
@@ -431,6 +481,50 @@ static int32_t alloc_batch_memory(b200poa_batch* b) {
     CU_TRY(cudaHostAlloc(&b->h_out_off, MP * sizeof(int32_t), cudaHostAllocDefault));
     CU_TRY(cudaHostAlloc(&b->h_trim, MP * sizeof(int32_t), cudaHostAllocDefault));
     CU_TRY(cudaHostAlloc(&b->h_cursor, 2 * sizeof(int32_t), cudaHostAllocDefault));
+    return B200POA_SUCCESS;
+}
+
+/* shared body of b200poa_batch_add_windows (staged) and b200poa_batch_add_windows_pinned (direct) */
+template <bool DIRECT>
+static int32_t add_windows_impl(b200poa_batch* b, int64_t n_windows, int64_t first, const int64_t* win_seq_off,
+                                const int64_t* seq_off, const uint8_t* bases, const int8_t* weights,
+                                const uint8_t* has_weights, const int64_t* weight_mode, const int32_t* begins,
+                                const int32_t* ends, int64_t* n_added, int32_t* seqs_added) {
+    if (!b || !n_added) return B200POA_INVALID_ARGUMENT;
+    *n_added = 0;
+    if (DIRECT ? (b->poa_count > 0 && (b->ext_bases != bases || b->ext_weights != weights)) : b->ext_bases != nullptr)
+        return B200POA_INVALID_ARGUMENT; /* a batch is either staged or direct (one arena) until its next reset */
+    std::vector<uint32_t> rank;
+    for (int64_t w = first; w < n_windows; ++w) {
+        const int64_t s0 = win_seq_off[w];
+        const int32_t n = (int32_t)(win_seq_off[w + 1] - s0);
+        /* src/window.cpp:78-85 == src/cuda/cudabatch.cpp:96-104 (see b200poa_layer_order) */
+        rank.resize((size_t)n);
+        for (int32_t i = 0; i < n; ++i) rank[(size_t)i] = (uint32_t)i;
+        if (n > 1)
+            std::sort(rank.begin() + 1, rank.end(),
+                      [&](uint32_t lhs, uint32_t rhs) { return begins[s0 + lhs] < begins[s0 + rhs]; });
+        auto get = [&](int32_t i, StagedSeq& q) {
+            const int64_t s = s0 + rank[(size_t)i];
+            q.seq = reinterpret_cast<const char*>(bases + seq_off[s]);
+            q.w = has_weights[s] ? weights + seq_off[s] : nullptr;
+            q.len = (int32_t)(seq_off[s + 1] - seq_off[s]);
+            q.bg = begins[s];
+            q.en = ends[s];
+            q.host_off = seq_off[s];
+            q.wmode = (DIRECT && weight_mode) ? weight_mode[s] : WMODE_UNKNOWN;
+        };
+        int32_t added = 0;
+        const int32_t st = stage_window<DIRECT>(b, n, get, nullptr, &added, seq_off[s0], seq_off[win_seq_off[w + 1]]);
+        if (st == B200POA_EXCEEDED_MAXIMUM_POAS) break;
+        if (st != B200POA_SUCCESS) return st;
+        if (DIRECT) {
+            b->ext_bases = bases;
+            b->ext_weights = weights;
+        }
+        if (seqs_added) seqs_added[*n_added] = added;
+        ++*n_added;
+    }
     return B200POA_SUCCESS;
 }
 
@@ -616,14 +710,17 @@ int32_t b200poa_batch_create(int32_t device_id, void* stream, size_t max_gpu_mem
 
 int32_t b200poa_batch_add_group(b200poa_batch* b, const b200poa_entry* entries, int32_t n, int32_t* per_seq_status) {
     if (!b || !entries || n <= 0) return B200POA_INVALID_ARGUMENT;
-    auto get = [&](int32_t i, const char*& seq, const int8_t*& w, int32_t& len, int32_t& bg, int32_t& en) {
-        seq = entries[i].seq;
-        w = entries[i].weights;
-        len = entries[i].length;
-        bg = entries[i].begin;
-        en = entries[i].end;
+    if (b->ext_bases) return B200POA_INVALID_ARGUMENT; /* a batch is either staged or direct until its next reset */
+    auto get = [&](int32_t i, StagedSeq& q) {
+        q.seq = entries[i].seq;
+        q.w = entries[i].weights;
+        q.len = entries[i].length;
+        q.bg = entries[i].begin;
+        q.en = entries[i].end;
+        q.host_off = 0;
+        q.wmode = WMODE_UNKNOWN;
     };
-    return stage_window(b, n, get, per_seq_status, nullptr);
+    return stage_window<false>(b, n, get, per_seq_status, nullptr);
 }
 
 int32_t b200poa_batch_add_windows(b200poa_batch* b, int64_t n_windows, int64_t first,
@@ -631,30 +728,34 @@ int32_t b200poa_batch_add_windows(b200poa_batch* b, int64_t n_windows, int64_t f
                                   const uint8_t* bases, const int8_t* weights,
                                   const uint8_t* has_weights, const int32_t* begins,
                                   const int32_t* ends, int64_t* n_added, int32_t* seqs_added) {
-    if (!b || !n_added) return B200POA_INVALID_ARGUMENT;
-    *n_added = 0;
-    std::vector<int32_t> rank;
-    for (int64_t w = first; w < n_windows; ++w) {
-        const int64_t s0 = win_seq_off[w];
-        const int32_t n = (int32_t)(win_seq_off[w + 1] - s0);
-        rank.resize((size_t)n);
-        b200poa_layer_order(n, begins + s0, rank.data());
-        auto get = [&](int32_t i, const char*& seq, const int8_t*& wt, int32_t& len, int32_t& bg, int32_t& en) {
-            const int64_t s = s0 + rank[(size_t)i];
-            seq = reinterpret_cast<const char*>(bases + seq_off[s]);
-            wt = has_weights[s] ? weights + seq_off[s] : nullptr;
-            len = (int32_t)(seq_off[s + 1] - seq_off[s]);
-            bg = begins[s];
-            en = ends[s];
-        };
-        int32_t added = 0;
-        const int32_t st = stage_window(b, n, get, nullptr, &added);
-        if (st == B200POA_EXCEEDED_MAXIMUM_POAS) break;
-        if (st != B200POA_SUCCESS) return st;
-        if (seqs_added) seqs_added[*n_added] = added;
-        ++*n_added;
+    return add_windows_impl<false>(b, n_windows, first, win_seq_off, seq_off, bases, weights, has_weights, nullptr, begins,
+                                   ends, n_added, seqs_added);
+}
+
+int32_t b200poa_batch_add_windows_pinned(b200poa_batch* b, int64_t n_windows, int64_t first,
+                                         const int64_t* win_seq_off, const int64_t* seq_off,
+                                         const uint8_t* bases, const int8_t* weights,
+                                         const uint8_t* has_weights, const int64_t* weight_mode,
+                                         const int32_t* begins, const int32_t* ends, int64_t* n_added,
+                                         int32_t* seqs_added) {
+    if (!weight_mode) return B200POA_INVALID_ARGUMENT;
+    return add_windows_impl<true>(b, n_windows, first, win_seq_off, seq_off, bases, weights, has_weights, weight_mode, begins,
+                                  ends, n_added, seqs_added);
+}
+
+void b200poa_weight_modes(int64_t n_sequences, const int64_t* seq_off, const int8_t* weights, const uint8_t* has_weights,
+                          int64_t* weight_mode) {
+    for (int64_t s = 0; s < n_sequences; ++s) {
+        if (!has_weights[s]) {
+            weight_mode[s] = -1 - 1; /* no quality string: weight 1 (window.cpp:105-107) */
+            continue;
+        }
+        const int8_t* w = weights + seq_off[s];
+        const int64_t len = seq_off[s + 1] - seq_off[s];
+        bool constant = true;
+        for (int64_t k = 1; k < len && constant; ++k) constant = w[k] == w[0];
+        weight_mode[s] = (constant && len > 0) ? -1 - (int64_t)w[0] : 0;
     }
-    return B200POA_SUCCESS;
 }
 
 int32_t b200poa_batch_total_poas(const b200poa_batch* b) { return b ? b->poa_count : 0; }
@@ -669,10 +770,19 @@ int32_t b200poa_batch_upload(b200poa_batch* b) {
     std::stable_sort(b->h_work, b->h_work + b->poa_count,
                      [&](int32_t x, int32_t y) { return b->cost[(size_t)x] > b->cost[(size_t)y]; });
     const size_t W = (size_t)b->poa_count, S = (size_t)b->seq_count;
-    CU_TRY(cudaMemcpyAsync(b->d_bases, b->h_bases, (size_t)b->base_count, cudaMemcpyHostToDevice, b->stream));
-    if (b->weight_count > 0) /* only sequences with non-constant weights carry bytes */
-        CU_TRY(cudaMemcpyAsync(b->d_weights, b->h_weights, (size_t)b->weight_count, cudaMemcpyHostToDevice, b->stream));
-    CU_TRY(cudaMemcpyAsync(b->d_seq_off, b->h_seq_off, (S + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, b->stream));
+    int64_t weight_bytes = b->weight_count;
+    if (b->ext_bases) { /* direct mode: the caller's pinned arena range goes up as it is */
+        CU_TRY(cudaMemcpyAsync(b->d_bases, b->ext_bases + b->ext_lo, (size_t)b->base_count, cudaMemcpyHostToDevice, b->stream));
+        weight_bytes = b->ext_any_weights ? b->base_count : 0;
+        if (weight_bytes > 0)
+            CU_TRY(cudaMemcpyAsync(b->d_weights, b->ext_weights + b->ext_lo, (size_t)weight_bytes, cudaMemcpyHostToDevice, b->stream));
+    } else {
+        CU_TRY(cudaMemcpyAsync(b->d_bases, b->h_bases, (size_t)b->base_count, cudaMemcpyHostToDevice, b->stream));
+        if (weight_bytes > 0) /* only sequences with non-constant weights carry bytes */
+            CU_TRY(cudaMemcpyAsync(b->d_weights, b->h_weights, (size_t)weight_bytes, cudaMemcpyHostToDevice, b->stream));
+    }
+    CU_TRY(cudaMemcpyAsync(b->d_seq_off, b->h_seq_off, S * sizeof(int64_t), cudaMemcpyHostToDevice, b->stream));
+    CU_TRY(cudaMemcpyAsync(b->d_seq_len, b->h_seq_len, S * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream));
     CU_TRY(cudaMemcpyAsync(b->d_w_off, b->h_w_off, S * sizeof(int64_t), cudaMemcpyHostToDevice, b->stream));
     CU_TRY(cudaMemcpyAsync(b->d_seq_begin, b->h_seq_begin, S * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream));
     CU_TRY(cudaMemcpyAsync(b->d_seq_end, b->h_seq_end, S * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream));
@@ -680,7 +790,7 @@ int32_t b200poa_batch_upload(b200poa_batch* b) {
     CU_TRY(cudaMemcpyAsync(b->d_win_flags, b->h_win_flags, W * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream));
     CU_TRY(cudaMemcpyAsync(b->d_win_trim_nseq, b->h_win_trim_nseq, W * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream));
     CU_TRY(cudaMemcpyAsync(b->d_work, b->h_work, W * sizeof(int32_t), cudaMemcpyHostToDevice, b->stream));
-    b->h2d_bytes = b->base_count + b->weight_count + (int64_t)((S + 1) * 8 + S * 16 + (W + 1) * 4 + W * 12);
+    b->h2d_bytes = b->base_count + weight_bytes + (int64_t)(S * 28 + (W + 1) * 4 + W * 12);
     b->uploaded = true;
     return B200POA_SUCCESS;
 }
@@ -701,6 +811,7 @@ int32_t b200poa_batch_launch(b200poa_batch* b) {
     a.bases = b->d_bases;
     a.weights = b->d_weights;
     a.seq_off = b->d_seq_off;
+    a.seq_len = b->d_seq_len;
     a.w_off = b->d_w_off;
     a.win_seq_off = b->d_win_seq_off;
     a.win_flags = b->d_win_flags;
@@ -816,6 +927,10 @@ int32_t b200poa_batch_reset(b200poa_batch* b) {
     b->seq_count = 0;
     b->base_count = 0;
     b->weight_count = 0;
+    b->ext_bases = nullptr;
+    b->ext_weights = nullptr;
+    b->ext_lo = b->ext_hi = 0;
+    b->ext_any_weights = false;
     b->cost.clear();
     b->uploaded = false;
     b->results_fetched = false;

@@ -11,6 +11,7 @@
 #include <stdexcept>
 #include <chrono>
 #include <cstdlib>
+#include <string>
 #include <thread>
 
 #include "b200poa.h"
@@ -196,12 +197,13 @@ extern "C" int32_t b200poa_polisher_create(int32_t n_devices, const int32_t* dev
     return b200poa_polisher_create_ex(&opt, out);
 }
 
-extern "C" int32_t b200poa_polisher_polish(b200poa_polisher* h, int64_t n_windows, const int64_t* win_seq_off,
-                                           const int64_t* seq_off, const uint8_t* bases, const int8_t* weights,
-                                           const uint8_t* has_weights, const int32_t* begins, const int32_t* ends,
-                                           int32_t tgs, int32_t trim, int32_t max_windows_per_round, uint8_t* cons_out,
-                                           int32_t stride, int32_t* cons_len, uint8_t* polished, int32_t* status_out,
-                                           int64_t* kernel_launches, int64_t* h2d_bytes, int64_t* d2h_bytes) {
+/* pinned_weight_mode != nullptr: the arrays are a page-locked arena (b200poa_arena_finalize) -> zero-staging batches */
+static int32_t polisher_polish_impl(b200poa_polisher* h, int64_t n_windows, const int64_t* win_seq_off,
+                                    const int64_t* seq_off, const uint8_t* bases, const int8_t* weights,
+                                    const uint8_t* has_weights, const int64_t* pinned_weight_mode, const int32_t* begins,
+                                    const int32_t* ends, int32_t tgs, int32_t trim, int32_t max_windows_per_round,
+                                    uint8_t* cons_out, int32_t stride, int32_t* cons_len, uint8_t* polished,
+                                    int32_t* status_out, int64_t* kernel_launches, int64_t* h2d_bytes, int64_t* d2h_bytes) {
     if (!h || n_windows < 0 || !win_seq_off || !seq_off || !cons_out || !cons_len || !polished) return B200POA_INVALID_ARGUMENT;
     std::vector<FlatProc>& procs = h->procs;
     std::mutex mu;
@@ -244,8 +246,12 @@ extern "C" int32_t b200poa_polisher_polish(b200poa_polisher* h, int64_t n_window
             int64_t first = lo, n_added = 0;
             seqs_added.resize(static_cast<size_t>(hi - lo));
             /* stage [lo, hi) but stop at the first window that does not fit */
-            int32_t st = b200poa_batch_add_windows(p->batch, hi, first, win_seq_off, seq_off, bases, weights, has_weights,
-                                                   begins, ends, &n_added, seqs_added.data());
+            int32_t st = pinned_weight_mode
+                             ? b200poa_batch_add_windows_pinned(p->batch, hi, first, win_seq_off, seq_off, bases, weights,
+                                                                has_weights, pinned_weight_mode, begins, ends, &n_added,
+                                                                seqs_added.data())
+                             : b200poa_batch_add_windows(p->batch, hi, first, win_seq_off, seq_off, bases, weights, has_weights,
+                                                         begins, ends, &n_added, seqs_added.data());
             if (st != B200POA_SUCCESS) return st;
             if (n_added == 0) return B200POA_EXCEEDED_MAXIMUM_POAS; /* a single window larger than the batch */
             const double t1 = now();
@@ -313,6 +319,17 @@ extern "C" int32_t b200poa_polisher_polish(b200poa_polisher* h, int64_t n_window
     if (h2d_bytes) *h2d_bytes = up_bytes;
     if (d2h_bytes) *d2h_bytes = down_bytes;
     return rc;
+}
+
+extern "C" int32_t b200poa_polisher_polish(b200poa_polisher* h, int64_t n_windows, const int64_t* win_seq_off,
+                                           const int64_t* seq_off, const uint8_t* bases, const int8_t* weights,
+                                           const uint8_t* has_weights, const int32_t* begins, const int32_t* ends,
+                                           int32_t tgs, int32_t trim, int32_t max_windows_per_round, uint8_t* cons_out,
+                                           int32_t stride, int32_t* cons_len, uint8_t* polished, int32_t* status_out,
+                                           int64_t* kernel_launches, int64_t* h2d_bytes, int64_t* d2h_bytes) {
+    return polisher_polish_impl(h, n_windows, win_seq_off, seq_off, bases, weights, has_weights, nullptr, begins, ends, tgs,
+                                trim, max_windows_per_round, cons_out, stride, cons_len, polished, status_out,
+                                kernel_launches, h2d_bytes, d2h_bytes);
 }
 
 extern "C" int32_t b200poa_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int64_t* seq_off,
@@ -402,6 +419,9 @@ extern "C" int32_t b200poa_polish_windows_via_adapter(int64_t n_windows, const i
 /* ---- columnar window construction: C ABI over racon_b200::WindowArena (window_arena.hpp) ---- */
 struct b200poa_arena {
     racon_b200::WindowArena arena;
+    std::vector<int64_t> weight_mode; /* per sequence, b200poa_weight_modes */
+    std::vector<std::string> quality_store; /* b200poa_arena_append_columns: quality strings kept alive until finalize */
+    bool pinned = false;              /* bases/weights are page-locked (cudaHostRegister) */
 };
 
 extern "C" b200poa_arena* b200poa_arena_create(void) { return new (std::nothrow) b200poa_arena(); }
@@ -421,9 +441,52 @@ extern "C" int32_t b200poa_arena_add_layer(b200poa_arena* a, int64_t window, con
                : B200POA_INVALID_ARGUMENT;
 }
 
+/* Convenience for callers that already hold their windows as columns (tests, bench): the same add_window / add_layer
+ * calls as above, one per sequence, qualities rebuilt as PHRED+33 characters from the weights. */
+extern "C" int32_t b200poa_arena_append_columns(b200poa_arena* a, int64_t n_windows, const int64_t* win_seq_off,
+                                                const int64_t* seq_off, const uint8_t* bases, const int8_t* weights,
+                                                const uint8_t* has_weights, const int32_t* begins, const int32_t* ends) {
+    if (!a || a->arena.finalized()) return B200POA_INVALID_ARGUMENT;
+    a->quality_store.emplace_back();
+    std::string& q = a->quality_store.back(); /* add_* borrow the pointers until finalize */
+    q.resize(static_cast<size_t>(seq_off[win_seq_off[n_windows]]));
+    for (size_t i = 0; i < q.size(); ++i) q[i] = static_cast<char>(weights[i] + 33);
+    for (int64_t w = 0; w < n_windows; ++w) {
+        const int64_t s0 = win_seq_off[w], s1 = win_seq_off[w + 1];
+        const uint32_t bl = static_cast<uint32_t>(seq_off[s0 + 1] - seq_off[s0]);
+        const int64_t id = a->arena.add_window(reinterpret_cast<const char*>(bases + seq_off[s0]), bl, q.data() + seq_off[s0], bl);
+        if (id < 0) return B200POA_INVALID_ARGUMENT;
+        for (int64_t s = s0 + 1; s < s1; ++s) {
+            const uint32_t len = static_cast<uint32_t>(seq_off[s + 1] - seq_off[s]);
+            if (!a->arena.add_layer(id, reinterpret_cast<const char*>(bases + seq_off[s]), len,
+                                    has_weights[s] ? q.data() + seq_off[s] : nullptr, has_weights[s] ? len : 0,
+                                    static_cast<uint32_t>(begins[s]), static_cast<uint32_t>(ends[s])))
+                return B200POA_INVALID_ARGUMENT;
+        }
+    }
+    return B200POA_SUCCESS;
+}
+
 extern "C" int32_t b200poa_arena_finalize(b200poa_arena* a) {
     if (!a) return B200POA_INVALID_ARGUMENT;
+    if (a->arena.finalized()) return B200POA_SUCCESS;
     a->arena.finalize();
+    a->quality_store.clear();
+    const racon_b200::WindowArena& w = a->arena;
+    a->weight_mode.assign(static_cast<size_t>(w.n_sequences()), 0);
+    b200poa_weight_modes(w.n_sequences(), w.seq_off().data(), w.weights().data(), w.has_weights().data(), a->weight_mode.data());
+    /* page-lock the arena where a CUDA device exists: batches then upload straight from it.  Without a device (or if
+     * the driver refuses) the arena stays pageable and polishing goes through the staging copy. */
+    int ndev = 0;
+    if (!w.bases().empty() && cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {
+        const bool ok_b = cudaHostRegister(const_cast<uint8_t*>(w.bases().data()), w.bases().size(), cudaHostRegisterPortable) == cudaSuccess;
+        const bool ok_w = ok_b && cudaHostRegister(const_cast<int8_t*>(w.weights().data()), w.weights().size(), cudaHostRegisterPortable) == cudaSuccess;
+        if (ok_b && !ok_w) cudaHostUnregister(const_cast<uint8_t*>(w.bases().data()));
+        a->pinned = ok_b && ok_w;
+        if (!a->pinned) cudaGetLastError(); /* not an error of the caller's */
+    } else {
+        cudaGetLastError();
+    }
     return B200POA_SUCCESS;
 }
 
@@ -451,13 +514,19 @@ extern "C" int32_t b200poa_polisher_polish_arena(b200poa_polisher* h, const b200
                                                  int64_t* kernel_launches, int64_t* h2d_bytes, int64_t* d2h_bytes) {
     if (!a || !a->arena.finalized()) return B200POA_INVALID_ARGUMENT;
     const racon_b200::WindowArena& w = a->arena;
-    return b200poa_polisher_polish(h, w.n_windows(), w.win_seq_off().data(), w.seq_off().data(), w.bases().data(),
-                                   w.weights().data(), w.has_weights().data(), w.begins().data(), w.ends().data(), tgs,
-                                   trim, max_windows_per_round, cons_out, stride, cons_len, polished, status_out,
-                                   kernel_launches, h2d_bytes, d2h_bytes);
+    return polisher_polish_impl(h, w.n_windows(), w.win_seq_off().data(), w.seq_off().data(), w.bases().data(),
+                                w.weights().data(), w.has_weights().data(), a->pinned ? a->weight_mode.data() : nullptr,
+                                w.begins().data(), w.ends().data(), tgs, trim, max_windows_per_round, cons_out, stride,
+                                cons_len, polished, status_out, kernel_launches, h2d_bytes, d2h_bytes);
 }
 
-extern "C" void b200poa_arena_destroy(b200poa_arena* a) { delete a; }
+extern "C" void b200poa_arena_destroy(b200poa_arena* a) {
+    if (a && a->pinned) {
+        cudaHostUnregister(const_cast<uint8_t*>(a->arena.bases().data()));
+        cudaHostUnregister(const_cast<int8_t*>(a->arena.weights().data()));
+    }
+    delete a;
+}
 
 extern "C" int64_t b200poa_compact_rows(const uint8_t* rows, int64_t n_rows, int64_t stride, const int32_t* lens,
                                         uint8_t* flat, int64_t* offsets) {

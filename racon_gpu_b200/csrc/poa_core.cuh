@@ -222,7 +222,9 @@ struct WindowView {
     int32_t n_seqs;
     const uint8_t* bases;    /* batch arena */
     const int8_t* weights;   /* compact arena: only sequences whose weights are not one constant live here */
-    const int64_t* seq_off;  /* [n_seqs+1] offsets of this window's sequences in the bases arena */
+    const int64_t* seq_off;  /* [n_seqs] start of each sequence in the bases arena, in PROCESSING order (the arena itself may hold
+                                the sequences in any order: a pinned host arena is uploaded as it is, add order) */
+    const int32_t* seq_len;  /* [n_seqs] their lengths */
     const int64_t* w_off;    /* [n_seqs] >= 0: offset of the sequence's weights in `weights`; < 0: every base weighs
                                 -1 - w_off (racon: no quality string => 1, window.cpp:105-107; the '!' dummy quality of
                                 a FASTA target => 0, polisher.cpp:171,392-395) -- such sequences ship no weight bytes */
@@ -925,7 +927,7 @@ struct TbScratch {           /* device: shared memory (the fill's ring area); em
     uint8_t* readc;          /* [TB_COLS + 8] read base under column c at c - c_lo (column c <-> read[c-1]) */
 };
 constexpr int TB_SCRATCH_BYTES = TB_ROWS * TB_COLS * 2 + TB_ROWS * 4 + (TB_ROWS + 1) * 4 + TB_PRED_CAP * 4 + TB_ROWS * 2 + TB_COLS + 8 + 28 +
-                                 TB_ROWS * 4 + 32 * 4 + 4;
+                                 TB_ROWS * 4 + 32 * 4 + 4 + 16;
 
 constexpr int TB_OFF_REC = TB_ROWS * TB_COLS * 2;          /* byte offsets of the parts, see tb_bind() */
 constexpr int TB_OFF_POFF = TB_OFF_REC + TB_ROWS * 4;
@@ -934,6 +936,7 @@ constexpr int TB_OFF_NODE = TB_OFF_PRED + TB_PRED_CAP * 4;
 constexpr int TB_OFF_READC = TB_OFF_NODE + TB_ROWS * 2;
 constexpr int TB_OFF_INFO = (TB_OFF_READC + TB_COLS + 8 + 3) & ~3; /* [TB_ROWS] u32: node id | predecessor tile row | letter */
 constexpr int TB_OFF_OUT = TB_OFF_INFO + TB_ROWS * 4;              /* [32] u32: buffered alignment entries */
+constexpr int TB_OFF_MBAR = (TB_OFF_OUT + 32 * 4 + 7) & ~7;        /* 8 bytes: mbarrier of the bulk tile copies (TMA variant) */
 
 struct alignas(16) Vec16 { /* 8 int16 cells moved as one 128-bit access */
     uint32_t x, y, z, w;
@@ -971,6 +974,34 @@ POA_FN void tile_copy4(tile_addr a, int32_t i, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tile_sa(a) + 4u * (uint32_t)i), "l"(src) : "memory");
 }
 POA_FN void tile_copy_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+/* Bulk asynchronous copies (the TMA engine's 1-D form, cp.async.bulk) with mbarrier completion: one 64-byte request per
+ * tile row that lies wholly inside its band instead of four 16-byte LDGSTS.  POA_TB_TMA selects the variant. */
+#ifndef POA_TB_TMA
+#define POA_TB_TMA 0
+#endif
+POA_FN void tile_mbar_init(tile_addr a) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tile_sa(a)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+POA_FN void tile_mbar_inval(tile_addr a) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(tile_sa(a)) : "memory"); }
+POA_FN void tile_mbar_expect(tile_addr a, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tile_sa(a)), "r"(bytes) : "memory");
+}
+POA_FN void tile_async_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+POA_FN void tile_bulk_copy(tile_addr a, int32_t byte_off, const void* src, uint32_t bytes, tile_addr mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     tile_sa(a) + (uint32_t)byte_off),
+                 "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(tile_sa(mbar))
+                 : "memory");
+}
+POA_FN bool tile_mbar_test(tile_addr a, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok)
+                 : "r"(tile_sa(a)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
 POA_FN void tile_st_u32(tile_addr a, int32_t i, uint32_t v) { *reinterpret_cast<uint32_t*>(poa_smem + a + 4u * (uint32_t)i) = v; }
 POA_FN void tile_st_u16(tile_addr a, int32_t i, uint32_t v) { *reinterpret_cast<uint16_t*>(poa_smem + a + 2u * (uint32_t)i) = (uint16_t)v; }
 POA_FN void tile_st_u8(tile_addr a, int32_t i, uint32_t v) { poa_smem[a + (uint32_t)i] = (unsigned char)v; }
@@ -984,6 +1015,7 @@ POA_FN tile_addr tile_base(void* p) { return reinterpret_cast<uint8_t*>(p); }
 POA_FN void tile_copy16(tile_addr a, int32_t byte_off, const void* src) { *reinterpret_cast<Vec16*>(a + byte_off) = *reinterpret_cast<const Vec16*>(src); }
 POA_FN void tile_copy4(tile_addr a, int32_t i, const void* src) { reinterpret_cast<uint32_t*>(a)[i] = *reinterpret_cast<const uint32_t*>(src); }
 POA_FN void tile_copy_wait() {}
+#define POA_TB_TMA 0
 POA_FN void tile_st_u32(tile_addr a, int32_t i, uint32_t v) { reinterpret_cast<uint32_t*>(a)[i] = v; }
 POA_FN void tile_st_u16(tile_addr a, int32_t i, uint32_t v) { reinterpret_cast<uint16_t*>(a)[i] = (uint16_t)v; }
 POA_FN void tile_st_u8(tile_addr a, int32_t i, uint32_t v) { a[i] = (uint8_t)v; }
@@ -1029,6 +1061,15 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params p, WinState& st, c
     const tile_addr A_rec = A_cells + TB_OFF_REC, A_poff = A_cells + TB_OFF_POFF, A_pred = A_cells + TB_OFF_PRED,
                     A_node = A_cells + TB_OFF_NODE, A_readc = A_cells + TB_OFF_READC, A_info = A_cells + TB_OFF_INFO,
                     A_out = A_cells + TB_OFF_OUT;
+#if POA_TB_TMA
+#define POA_TB_EXIT() do { POA_SYNC(); POA_LANE0 { tile_mbar_inval(A_mbar); } POA_SYNC(); } while (0)
+    const tile_addr A_mbar = A_cells + TB_OFF_MBAR;
+    uint32_t tma_parity = 0; /* phase of the mbarrier the bulk copies complete on */
+    POA_LANE0 { tile_mbar_init(A_mbar); }
+    POA_SYNC();
+#else
+#define POA_TB_EXIT() ((void)0)
+#endif
     POA_SUB_BEGIN();
     int32_t w = cap; /* write cursor (uniform) */
     int32_t i = end_row, j = rlen; /* both laundered above */
@@ -1057,6 +1098,7 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params p, WinState& st, c
     while (!(i == 0 && j == 0)) {
         if (w <= 32) { /* every step consumes one entry: a path longer than nodes + read length is lost */
             st.status = ST_TRACEBACK_LOST;
+            POA_TB_EXIT();
             return cap;
         }
         if (i == 0) { /* first row: S[0][*] == 0, only horizontal moves are left */
@@ -1074,7 +1116,8 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params p, WinState& st, c
             j = 0;
             if (w < 0) {
                 st.status = ST_TRACEBACK_LOST;
-                return cap;
+                POA_TB_EXIT();
+            return cap;
             }
             break;
         }
@@ -1096,6 +1139,42 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params p, WinState& st, c
              * row program) instead of read from its record, so the score chunks -- the loads that go to HBM --
              * depend on nothing; they are asynchronous global->shared copies, no registers in between.  Only
              * the predecessor entries need a second, short level (two CSR offsets, cache-resident). */
+#if POA_TB_TMA
+            /* Rows that lie wholly inside their band arrive as ONE 64-byte bulk copy each (cp.async.bulk, completion
+             * counted in bytes on an mbarrier); rows cut by a band edge keep the 16-byte copies + NEG fill below. */
+            int32_t bulk_bytes = 0;
+            {
+                PerLane<int> nb_l;
+                POA_LANES(l) {
+                    int32_t n = 0;
+#pragma unroll
+                    for (int32_t rr = 0; rr < TB_RPL; ++rr) {
+                        const int32_t row = r_hi - (l + 32 * rr);
+                        if (row < r_lo) continue;
+                        const int32_t o = c_lo - band_start(gg, row, gg.n_rows);
+                        if (o >= 0 && o + TB_COLS <= bw) ++n;
+                    }
+                    nb_l[l] = n;
+                }
+                bulk_bytes = warp_sum(nb_l) * TB_COLS * 2;
+            }
+            if (bulk_bytes > 0) {
+                tile_async_fence(); /* the tile was read through the generic proxy; the bulk copies write through the async one */
+                POA_LANE0 { tile_mbar_expect(A_mbar, (uint32_t)bulk_bytes); }
+                POA_SYNC();
+                POA_LANES(l) {
+#pragma unroll
+                    for (int32_t rr = 0; rr < TB_RPL; ++rr) {
+                        const int32_t k = l + 32 * rr;
+                        const int32_t row = r_hi - k;
+                        if (row < r_lo) continue;
+                        const int32_t o = c_lo - band_start(gg, row, gg.n_rows);
+                        if (o >= 0 && o + TB_COLS <= bw)
+                            tile_bulk_copy(A_cells, k * TB_COLS * 2, S + (size_t)row * stride + o, TB_COLS * 2, A_mbar);
+                    }
+                }
+            }
+#endif
             const int32_t lo_row = r_lo < 1 ? 1 : r_lo;
             const int32_t p_lo = (int32_t)row_poff[lo_row];                           /* uniform loads (i >= 1 here) */
             const int32_t p_hi = (int32_t)row_poff[r_hi] + rec_npred(row_rec[r_hi]);
@@ -1106,8 +1185,13 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params p, WinState& st, c
                     const int32_t row = r_hi - k;
                     if (row < r_lo) continue;
                     const int32_t bs = band_start(gg, row, gg.n_rows);
+#if POA_TB_TMA
+                    const bool bulk_row = c_lo - bs >= 0 && c_lo - bs + TB_COLS <= bw; /* whole row in its band: bulk copy below */
+#else
+                    const bool bulk_row = false;
+#endif
 #pragma unroll
-                    for (int32_t q = 0; q < TB_CHUNKS; ++q) {
+                    for (int32_t q = 0; q < TB_CHUNKS && !bulk_row; ++q) {
                         const int32_t o = c_lo + 8 * q - bs; /* 8-aligned both: whole chunk in the band or out */
                         const int32_t dst = (k * TB_COLS + 8 * q) * 2; /* byte offset in the tile */
                         if (o >= 0 && o + 8 <= bw) tile_copy16(A_cells, dst, S + (size_t)row * stride + o);
@@ -1151,6 +1235,14 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params p, WinState& st, c
                     if (l + 32 * u < TB_COLS) tile_st_u8(A_readc, l + 32 * u, rb[u]);
             }
             tile_copy_wait();
+#if POA_TB_TMA
+            if (bulk_bytes > 0) {
+                int32_t spins = 0;
+                while (!tile_mbar_test(A_mbar, tma_parity) && ++spins < (1 << 22)) {}
+                if (spins >= (1 << 22)) lost = 1; /* never expected: a copy that does not complete must not hang the device */
+                tma_parity ^= 1u;
+            }
+#endif
             POA_SYNC();
             /* digest for the serial walk: a row with ONE in-edge whose source is in the tile takes the short step */
             POA_LANES(l) {
@@ -1291,6 +1383,7 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params p, WinState& st, c
         } /* general step */
         if (poa_uniform_pred(lost != 0)) {
             st.status = ST_TRACEBACK_LOST;
+            POA_TB_EXIT();
             return cap;
         }
         --w;
@@ -1304,8 +1397,10 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params p, WinState& st, c
     POA_TB_FLUSH();
 #undef POA_TB_FLUSH
     POA_SYNC();
+    POA_TB_EXIT();
     return w;
 }
+#undef POA_TB_EXIT
 
 /* ------------------------------------------------------------------------------------------
  * Phase 4: add the alignment to the graph  (graph.cpp:155-272, 94-116)
@@ -2120,7 +2215,7 @@ POA_FN void process_window(const Slot& s, const Params& p, const WindowView& wv,
     st.n_columns = 0;
     st.band_hit = 0;
     st.status = ST_SUCCESS;
-    const int32_t len0 = (int32_t)(wv.seq_off[1] - wv.seq_off[0]);
+    const int32_t len0 = wv.seq_len[0];
     tm.start();
     {
         const int64_t wo = wv.w_off[0];
@@ -2132,7 +2227,7 @@ POA_FN void process_window(const Slot& s, const Params& p, const WindowView& wv,
         const int64_t wo = wv.w_off[r];
         const int8_t* wt = wo >= 0 ? wv.weights + wo : nullptr;
         const int32_t wconst = wo >= 0 ? 0 : (int32_t)(-1 - wo);
-        const int32_t len = (int32_t)(wv.seq_off[r + 1] - wv.seq_off[r]);
+        const int32_t len = wv.seq_len[r];
         /* int16 cells whenever the alignment provably fits them; else 32-bit cells if the batch was sized for them */
         const bool cells32 = p.force_cells32 != 0 || !score_range_ok(p, st.n_columns, len);
         if (cells32 && !p.wide_cells) {

@@ -115,6 +115,7 @@ void emu_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int
         std::vector<uint8_t> wbases;
         std::vector<int8_t> wweights;
         std::vector<int64_t> woff, wwoff;
+        std::vector<int32_t> wlen;
         std::vector<int32_t> wbeg, wend;
         ScalarFill fill;
         std::vector<uint8_t> tb_mem(TB_SCRATCH_BYTES + 64);
@@ -127,7 +128,8 @@ void emu_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int
             const int32_t n = (int32_t)(win_seq_off[w + 1] - s0);
             wbases.clear();
             wweights.clear();
-            woff.assign(1, 0);
+            woff.clear();
+            wlen.clear();
             wwoff.clear();
             wbeg.clear();
             wend.clear();
@@ -138,6 +140,8 @@ void emu_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int
                 const int64_t sq = s0 + order[s0 + k];
                 const int64_t a = seq_off[sq], b = seq_off[sq + 1];
                 if (b - a > max_len) too_long = true;
+                woff.push_back((int64_t)wbases.size());
+                wlen.push_back((int32_t)(b - a));
                 wbases.insert(wbases.end(), bases + a, bases + b);
                 if (has_weights[sq]) { /* explicit weights live in the compact arena ... */
                     wwoff.push_back((int64_t)wweights.size());
@@ -145,7 +149,6 @@ void emu_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int
                 } else {
                     wwoff.push_back(-1 - 1); /* ... a sequence without quality weighs 1 per base and ships none */
                 }
-                woff.push_back((int64_t)wbases.size());
                 /* window.cpp:92-93: full-span test (the product's host library applies the same rule) */
                 const bool full = k == 0 || !begins ||
                                   ((uint32_t)begins[sq] < offset && (uint32_t)ends[sq] > L0 - offset);
@@ -162,6 +165,7 @@ void emu_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int
             wv.bases = wbases.data();
             wv.weights = wweights.data();
             wv.seq_off = woff.data();
+            wv.seq_len = wlen.data();
             wv.w_off = wwoff.data();
             wv.seq_begin = wbeg.data();
             wv.seq_end = wend.data();
