@@ -317,7 +317,7 @@ def main():
     ap.add_argument("--workload", default="A_banded", choices=sorted(WORKLOADS))
     ap.add_argument("--windows", type=int, default=0, help="override windows per GPU")
     ap.add_argument("--seed", type=int, default=12345)
-    ap.add_argument("--batches", type=int, default=4, help="batch processors per GPU for the e2e leg (racon -c)")
+    ap.add_argument("--batches", type=int, default=2, help="batch processors per GPU for the e2e leg (racon -c)")
     ap.add_argument("--rounds", type=float, default=1.0, help="e2e leg: launches per batch processor per step (chunk = windows / (batches x rounds))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the A_full / B_banded block (N=1 only anyway)")
