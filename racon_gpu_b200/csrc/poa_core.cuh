@@ -475,6 +475,10 @@ POA_FN int32_t band_start(const ReadGeom& g, int32_t row, int32_t n_rows) {
     return bs & ~7;
 }
 
+#ifndef POA_PB_U
+#define POA_PB_U 4
+#endif
+constexpr int PB_U = POA_PB_U; /* edges per lane per step in the edge-parallel pass of the row program */
 POA_FN_NOINLINE void build_program(const Slot& s_ref, const Params p_ref, WinState& st, const ReadGeom g_ref) {
     const Slot s = s_ref;     /* local copies: no reloads of the descriptor after every store */
     const Params p = p_ref;
@@ -534,12 +538,12 @@ POA_FN_NOINLINE void build_program(const Slot& s_ref, const Params p_ref, WinSta
     /* pass B, edge-parallel, 128 edges per step: every edge drops its source row into its slot of the
      * target's predecessor list (slot = e_ord, the edge's position in the in-edge list, fixed when the
      * edge was created) -- no linked-list walking, three dependent loads per edge. */
-    for (int32_t base = 0; base < E; base += 128) {
+    for (int32_t base = 0; base < E; base += 32 * PB_U) {
         POA_LANES(l) {
-            int32_t d[4], u[4], q[4], rd[4], ru[4], o[4];
-            bool ok[4];
+            int32_t d[PB_U], u[PB_U], q[PB_U], rd[PB_U], ru[PB_U], o[PB_U];
+            bool ok[PB_U];
 #pragma unroll
-            for (int32_t k = 0; k < 4; ++k) { /* level 1: the edge itself (independent loads) */
+            for (int32_t k = 0; k < PB_U; ++k) { /* level 1: the edge itself (independent loads) */
                 const int32_t e = base + 32 * k + l;
                 ok[k] = e < E;
                 d[k] = ok[k] ? (int32_t)s.e_dst[e] : 0;
@@ -547,14 +551,14 @@ POA_FN_NOINLINE void build_program(const Slot& s_ref, const Params p_ref, WinSta
                 q[k] = ok[k] ? (int32_t)s.e_ord[e] : 0;
             }
 #pragma unroll
-            for (int32_t k = 0; k < 4; ++k) { /* level 2: ranks */
+            for (int32_t k = 0; k < PB_U; ++k) { /* level 2: ranks */
                 rd[k] = s.rank_of[d[k]] + 1;
                 ru[k] = s.rank_of[u[k]] + 1;
             }
 #pragma unroll
-            for (int32_t k = 0; k < 4; ++k) o[k] = (int32_t)s.row_poff[rd[k]] + q[k]; /* level 3: slot */
+            for (int32_t k = 0; k < PB_U; ++k) o[k] = (int32_t)s.row_poff[rd[k]] + q[k]; /* level 3: slot */
 #pragma unroll
-            for (int32_t k = 0; k < 4; ++k) {
+            for (int32_t k = 0; k < PB_U; ++k) {
                 if (!ok[k]) continue;
                 const int32_t pbs = band_start(g, ru[k], N);
                 s.row_pred[o[k]] = (uint32_t)ru[k] | ((uint32_t)pbs << 16);
@@ -1804,6 +1808,10 @@ POA_FN_NOINLINE void topsort_serial(const Slot& s_ref, const Params p_ref, WinSt
  *        members and store each member's position (lpos);
  *     3. every node: rank = offset[root] + lpos.
  * ---------------------------------------------------------------------------------------- */
+#ifndef POA_TS_U
+#define POA_TS_U 4
+#endif
+constexpr int TS_U = POA_TS_U; /* nodes per lane per step in the node-parallel passes of the sort */
 POA_FN_NOINLINE void topsort_roots(const Slot& s_ref, const Params p_ref, WinState& st) {
     const Slot s = s_ref;     /* local copies: no reloads of the descriptor after every store */
     const Params p = p_ref;
@@ -1811,20 +1819,20 @@ POA_FN_NOINLINE void topsort_roots(const Slot& s_ref, const Params p_ref, WinSta
     const int32_t N = poa_uniform(st.n_nodes);
     /* 1. members of dirty roots: reset DFS marks, accumulate the root's stack bound.  Four nodes per lane
      *    per step so that the dependent loads (root -> dirty -> in-degree) of all four are in flight together. */
-    for (int32_t base = 0; base < N; base += 128) {
+    for (int32_t base = 0; base < N; base += 32 * TS_U) {
         POA_LANES(l) {
-            int32_t r[4], nn[4];
-            bool d[4];
+            int32_t r[TS_U], nn[TS_U];
+            bool d[TS_U];
 #pragma unroll
-            for (int32_t u = 0; u < 4; ++u) {
+            for (int32_t u = 0; u < TS_U; ++u) {
                 const int32_t v = base + 32 * u + l;
                 r[u] = v < N ? (int32_t)s.root[v] : 0;
                 nn[u] = v < N ? (int32_t)s.nin[v] + (int32_t)s.aln_cnt[v] + 1 : 0;
             }
 #pragma unroll
-            for (int32_t u = 0; u < 4; ++u) d[u] = (base + 32 * u + l < N) && s.dirty[r[u]];
+            for (int32_t u = 0; u < TS_U; ++u) d[u] = (base + 32 * u + l < N) && s.dirty[r[u]];
 #pragma unroll
-            for (int32_t u = 0; u < 4; ++u) {
+            for (int32_t u = 0; u < TS_U; ++u) {
                 const int32_t v = base + 32 * u + l;
                 if (d[u]) {
                     s.marks[v] = 0;
@@ -1940,21 +1948,21 @@ POA_FN_NOINLINE void topsort_roots(const Slot& s_ref, const Params p_ref, WinSta
     /* 3. ranks (four nodes per lane per step, loads staged by dependency level).  The row program of the NEXT read wants,
      *    in rank order, each node's letter, in-degree and whether it is a sink: they are read here, where nodes are
      *    visited in id order (coalesced), and written by rank -- instead of gathered through node_at later. */
-    for (int32_t base = 0; base < N; base += 128) {
+    for (int32_t base = 0; base < N; base += 32 * TS_U) {
         POA_LANES(l) {
-            int32_t q[4], lp[4], r[4];
-            uint32_t meta[4];
+            int32_t q[TS_U], lp[TS_U], r[TS_U];
+            uint32_t meta[TS_U];
 #pragma unroll
-            for (int32_t k = 0; k < 4; ++k) {
+            for (int32_t k = 0; k < TS_U; ++k) {
                 const int32_t v = base + 32 * k + l;
                 q[k] = v < N ? (int32_t)s.root[v] : 0;
                 lp[k] = v < N ? (int32_t)s.lpos[v] : 0;
                 meta[k] = v < N ? meta_make(s.code[v], s.nout[v] == 0, s.nin[v]) : 0u;
             }
 #pragma unroll
-            for (int32_t k = 0; k < 4; ++k) r[k] = (int32_t)s.roff[q[k]] + lp[k];
+            for (int32_t k = 0; k < TS_U; ++k) r[k] = (int32_t)s.roff[q[k]] + lp[k];
 #pragma unroll
-            for (int32_t k = 0; k < 4; ++k) {
+            for (int32_t k = 0; k < TS_U; ++k) {
                 const int32_t v = base + 32 * k + l;
                 if (v < N) {
                     s.rank_of[v] = (uint16_t)r[k];
