@@ -971,8 +971,25 @@ POA_FN uint32_t tile_u8(tile_addr a, int32_t i) { return poa_smem[a + (uint32_t)
 POA_FN uint32_t tile_sa(tile_addr a) { return (uint32_t)__cvta_generic_to_shared(poa_smem) + a; } /* shared-window address */
 /* asynchronous global -> shared copies used by the tile load (LDGSTS: no register staging, all in flight);
  * destinations are shared-window addresses, like every other access to the tile */
-POA_FN void tile_copy16(tile_addr a, int32_t byte_off, const void* src) {
+#ifndef POA_TB_EVICT_FIRST
+#define POA_TB_EVICT_FIRST 1
+#endif
+/* score chunks are read once by the traceback: with POA_TB_EVICT_FIRST they are marked first to leave L2 */
+POA_FN uint64_t tile_stream_policy() {
+    uint64_t pol = 0;
+#if POA_TB_EVICT_FIRST
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+#endif
+    return pol;
+}
+POA_FN void tile_copy16(tile_addr a, int32_t byte_off, const void* src, uint64_t pol) {
+#if POA_TB_EVICT_FIRST
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(tile_sa(a) + (uint32_t)byte_off), "l"(src), "l"(pol)
+                 : "memory");
+#else
+    (void)pol;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tile_sa(a) + (uint32_t)byte_off), "l"(src) : "memory");
+#endif
 }
 POA_FN void tile_copy4(tile_addr a, int32_t i, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tile_sa(a) + 4u * (uint32_t)i), "l"(src) : "memory");
@@ -1016,7 +1033,8 @@ POA_FN void tile_fill8(tile_addr a, int32_t byte_off, int32_t v) { /* 8 int16 ce
 #else
 typedef uint8_t* tile_addr;
 POA_FN tile_addr tile_base(void* p) { return reinterpret_cast<uint8_t*>(p); }
-POA_FN void tile_copy16(tile_addr a, int32_t byte_off, const void* src) { *reinterpret_cast<Vec16*>(a + byte_off) = *reinterpret_cast<const Vec16*>(src); }
+POA_FN uint64_t tile_stream_policy() { return 0; }
+POA_FN void tile_copy16(tile_addr a, int32_t byte_off, const void* src, uint64_t) { *reinterpret_cast<Vec16*>(a + byte_off) = *reinterpret_cast<const Vec16*>(src); }
 POA_FN void tile_copy4(tile_addr a, int32_t i, const void* src) { reinterpret_cast<uint32_t*>(a)[i] = *reinterpret_cast<const uint32_t*>(src); }
 POA_FN void tile_copy_wait() {}
 #define POA_TB_TMA 0
@@ -1074,6 +1092,7 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params p, WinState& st, c
 #else
 #define POA_TB_EXIT() ((void)0)
 #endif
+    const uint64_t stream_pol = tile_stream_policy();
     POA_SUB_BEGIN();
     int32_t w = cap; /* write cursor (uniform) */
     int32_t i = end_row, j = rlen; /* both laundered above */
@@ -1198,7 +1217,7 @@ POA_FN_NOINLINE int32_t traceback(const Slot& s, const Params p, WinState& st, c
                     for (int32_t q = 0; q < TB_CHUNKS && !bulk_row; ++q) {
                         const int32_t o = c_lo + 8 * q - bs; /* 8-aligned both: whole chunk in the band or out */
                         const int32_t dst = (k * TB_COLS + 8 * q) * 2; /* byte offset in the tile */
-                        if (o >= 0 && o + 8 <= bw) tile_copy16(A_cells, dst, S + (size_t)row * stride + o);
+                        if (o >= 0 && o + 8 <= bw) tile_copy16(A_cells, dst, S + (size_t)row * stride + o, stream_pol);
                         else tile_fill8(A_cells, dst, NEG);
                     }
                     if (row >= 1) {
@@ -1599,7 +1618,10 @@ POA_FN_NOINLINE void add_alignment_edges(const Slot& s_ref, const Params p_ref, 
     /* DU read positions per lane per step (pos, pos + 32, ...): the walk over a node's in-edge list is a chain of
      * dependent loads to HBM; the DU walks of a lane are interleaved so that their round trips overlap.  New edge
      * ids follow read order (position = base + 32 u + lane: u-major), computed from ballots. */
-    constexpr int DU = 4;
+#ifndef POA_ADD_DU
+#define POA_ADD_DU 4
+#endif
+    constexpr int DU = POA_ADD_DU;
     for (int32_t base = 0; base < len; base += 32 * DU) {
         PerLane<int> hit[DU], need[DU];
         POA_LANES(l) {
@@ -2214,6 +2236,49 @@ POA_HD bool score_range_ok(const Params& p, int32_t n_columns, int32_t len) {
  * full-span layers; the caller trims).  Fill is the DP-fill functor:
  *     int32_t operator()(slot, params, state, geom, read) -> end row (0 = none)
  * ---------------------------------------------------------------------------------------- */
+/* Experiment (POA_PREFETCH_GRAPH): the graph phases that follow the traceback walk the graph through chains of dependent
+ * loads, each of which is served from HBM when its line has left L2 since the previous read.  Ask for the lines ahead
+ * of time: one prefetch per 128-byte line of the node arrays [0, N) and edge arrays [0, E). */
+#ifndef POA_PREFETCH_GRAPH
+#define POA_PREFETCH_GRAPH 0
+#endif
+#if POA_DEVICE && POA_PREFETCH_GRAPH
+__device__ __forceinline__ void prefetch_span(const void* ptr, size_t bytes) {
+    const char* b = reinterpret_cast<const char*>(ptr);
+    for (size_t o = (size_t)(threadIdx.x & 31u) * 128u; o < bytes; o += 32u * 128u) {
+#if POA_PREFETCH_GRAPH == 2
+        asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(b + o));
+#else
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(b + o));
+#endif
+    }
+}
+__device__ __noinline__ void prefetch_graph(const Slot& s, int32_t N, int32_t E) {
+    const size_t n = (size_t)N, e = (size_t)E;
+    prefetch_span(s.code, n);
+    prefetch_span(s.nin, 2 * n);
+    prefetch_span(s.nout, 2 * n);
+    prefetch_span(s.in_head, 2 * n);
+    prefetch_span(s.in_tail, 2 * n);
+    prefetch_span(s.cov, 2 * n);
+    prefetch_span(s.aln_cnt, n);
+    prefetch_span(s.aln, 2 * KA * n);
+    prefetch_span(s.root, 2 * n);
+    prefetch_span(s.lpos, 2 * n);
+    prefetch_span(s.rank_of, 2 * n);
+    prefetch_span(s.e_src, 2 * e);
+    prefetch_span(s.e_dst, 2 * e);
+    prefetch_span(s.e_next, 2 * e);
+    prefetch_span(s.e_w, 4 * e);
+    prefetch_span(s.e_ord, e);
+    prefetch_span(s.cnt, 4 * n);
+    prefetch_span(s.need, 4 * n);
+    prefetch_span(s.dirty, n);
+    prefetch_span(s.marks, n);
+    prefetch_span(s.check, n);
+}
+#endif
+
 template <class Fill>
 POA_FN void process_window(const Slot& s, const Params& p, const WindowView& wv, Fill& fill, const TbScratch& tbs,
                            const WindowOut& out, PhaseTimer tm = PhaseTimer{nullptr, 0}) {
@@ -2271,6 +2336,9 @@ POA_FN void process_window(const Slot& s, const Params& p, const WindowView& wv,
             POA_FENCE(); /* the score rows must be in place before the traceback's asynchronous copies read them */
             tm.lap(PH_FILL);
             st.band_hit = 0;
+#if POA_DEVICE && POA_PREFETCH_GRAPH && POA_PREFETCH_GRAPH != 3
+            prefetch_graph(s, poa_uniform(st.n_nodes), poa_uniform(st.n_edges));
+#endif
             if (end_row <= 0) {
                 st.status = ST_TRACEBACK_LOST;
             } else {
@@ -2288,6 +2356,9 @@ POA_FN void process_window(const Slot& s, const Params& p, const WindowView& wv,
             break;
         }
         if (st.status != ST_SUCCESS) break;
+#if POA_DEVICE && POA_PREFETCH_GRAPH == 3
+        prefetch_graph(s, poa_uniform(st.n_nodes), poa_uniform(st.n_edges));
+#endif
         add_alignment(s, p, st, read, wt, wconst, len, tb);
         winstate_uniform(st);
         POA_FENCE();
