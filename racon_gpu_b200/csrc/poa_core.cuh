@@ -50,6 +50,10 @@ POA_FN void poa_atomic_add(uint32_t* p, uint32_t v) {
 #endif
 }
 
+#ifndef POA_TS_U
+#define POA_TS_U 4
+#endif
+constexpr int TS_U = POA_TS_U; /* nodes per lane per step in the node-parallel passes of the sort */
 constexpr int KA = 7;                  /* max aligned nodes per node (clique size - 1) */
 constexpr uint16_t NONE16 = 0xFFFFu;
 constexpr int NEG = -30000;            /* "minus infinity" for int16 cells; see DESIGN.md */
@@ -580,10 +584,10 @@ POA_FN_NOINLINE void build_program(const Slot& s_ref, const Params p_ref, WinSta
  * then Graph::topological_sort).  Relabelling is monotone, so that order is spoa's DFS run on the
  * original ids restricted to the members.  Serial on lane 0: only layers that do not span the window
  * take this path, and the member set is a fraction of the graph.
- * Outputs: sub_at[0..n_sub), sub_rank[] (NONE16 for non-members), roff[v] = out-degree inside the
+ * Outputs: sub_at[0..n_sub), sub_rank[] (NONE16 for non-members), roff[v] != 0 iff v has a successor inside the
  * subgraph.  Returns n_sub.
  * ---------------------------------------------------------------------------------------- */
-POA_FN_NOINLINE int32_t mark_subgraph(const Slot& s_ref, const Params p_ref, WinState& st, int32_t begin, int32_t end) {
+POA_FN_NOINLINE int32_t mark_subgraph_serial(const Slot& s_ref, const Params p_ref, WinState& st, int32_t begin, int32_t end) {
     const Slot s = s_ref;
     const Params p = p_ref;
     const int32_t N = poa_uniform(st.n_nodes);
@@ -678,6 +682,239 @@ POA_FN_NOINLINE int32_t mark_subgraph(const Slot& s_ref, const Params p_ref, Win
     n_sub = warp_bcast0(n_sub);
     (void)p;
     return n_sub;
+}
+
+/* The same subgraph and the same order, computed by the whole warp.
+ *   Members.  v is a member iff `end` can be reached from it through edges and aligned-node links without leaving the
+ *   ids >= begin, and spoa's DFS started at member i emits exactly the members whose first such reachable id (in id
+ *   order) is i: sroot(v) = min id reachable from v.  Both come out of ONE sweep over the full graph's ranks from
+ *   `end` downwards: a node passes its sroot to the sources of its in-edges (lower ranks) and to its aligned nodes
+ *   (the ranks next to it: a clique is emitted as one run, topological_sort graph.cpp:294-354).  32 ranks at a time,
+ *   iterated until nothing changes; consecutive chunks overlap by a clique's length so that a clique cut by a chunk
+ *   boundary is settled as a whole.  sroot lives in shared memory (the tile scratch, idle between two alignments).
+ *   Order.  rank(v) = (members with a smaller sroot) + (position of v in the DFS of its sroot restricted to that
+ *   sroot's members): the per-root decomposition of topsort_roots(), run from scratch with every root "dirty".
+ * Scratch that is free while a read is being prepared: the score matrix (counters, marks), stack, c_score/c_pred. */
+POA_FN_NOINLINE void subgraph_members(const Slot& s_ref, int32_t N, int32_t begin, int32_t end, uint16_t* sroot) {
+    const Slot s = s_ref;
+    N = poa_uniform(N);
+    begin = poa_uniform(begin);
+    end = poa_uniform(end);
+    uint32_t* const t_cnt = reinterpret_cast<uint32_t*>(s.S); /* [N] members per sroot */
+    uint32_t* const t_need = t_cnt + N;                       /* [N] DFS stack bound per sroot */
+    for (int32_t base = 0; base < N; base += 32) {
+        POA_LANES(l) {
+            const int32_t v = base + l;
+            if (v < N) {
+                s.sub_rank[v] = NONE16;
+                s.roff[v] = 0;
+                sroot[v] = NONE16;
+                t_cnt[v] = 0;
+                t_need[v] = 0;
+            }
+        }
+    }
+    POA_SYNC();
+    POA_LANE0 { sroot[end] = (uint16_t)end; }
+    int32_t r_top = (int32_t)s.rank_of[end] + KA;
+    if (r_top > N - 1) r_top = N - 1;
+    r_top = poa_uniform(r_top);
+    POA_SYNC();
+    /* ---- members and their sroot ---- */
+    for (int32_t hi = r_top; hi >= 0; hi -= 32 - (KA + 1)) {
+        PerLane<int> vv;
+        POA_LANES(l) {
+            const int32_t r = hi - l;
+            int32_t v = r >= 0 ? (int32_t)s.node_at[r] : -1;
+            if (v < begin) v = -1; /* backbone before `begin`: not a member, passes nothing on */
+            vv[l] = v;
+        }
+        for (;;) {
+            PerLane<int> ch;
+            POA_LANES(l) {
+                ch[l] = 0;
+                const int32_t v = vv[l];
+                if (v < 0) continue;
+                const int32_t x = sroot[v];
+                if (x == NONE16) continue;
+                for (uint16_t e = s.in_head[v]; e != NONE16; e = s.e_next[e]) {
+                    const int32_t u = s.e_src[e];
+                    const int32_t nx = x < u ? x : u;
+                    if (u >= begin && (int32_t)sroot[u] > nx) {
+                        sroot[u] = (uint16_t)nx;
+                        ch[l] = 1;
+                    }
+                }
+                const int32_t na = s.aln_cnt[v];
+                for (int32_t q = 0; q < na; ++q) {
+                    const int32_t a = s.aln[v * KA + q];
+                    const int32_t nx = x < a ? x : a;
+                    if (a >= begin && (int32_t)sroot[a] > nx) {
+                        sroot[a] = (uint16_t)nx;
+                        ch[l] = 1;
+                    }
+                }
+            }
+            POA_SYNC();
+            if (!warp_ballot(ch)) break;
+        }
+        if (hi < 32) break; /* this chunk reached rank 0 */
+    }
+}
+
+/* second half of mark_subgraph(): the order of the members (functions of their own: see poa_simt.cuh on function size) */
+POA_FN_NOINLINE int32_t subgraph_order(const Slot& s_ref, int32_t N, const uint16_t* sroot) {
+    const Slot s = s_ref;
+    N = poa_uniform(N);
+    uint32_t* const t_cnt = reinterpret_cast<uint32_t*>(s.S); /* [N] members per sroot */
+    uint32_t* const t_need = t_cnt + N;                       /* [N] DFS stack bound per sroot */
+    uint32_t* const t_off = t_need + N;                       /* [N] first rank of the sroot's members */
+    uint16_t* const t_lpos = reinterpret_cast<uint16_t*>(t_off + N); /* [N] position inside the sroot's DFS */
+    uint8_t* const t_marks = reinterpret_cast<uint8_t*>(t_lpos + N); /* [N] DFS marks */
+    uint8_t* const t_check = t_marks + N;                            /* [N] check_aligned flags */
+    /* ---- 1. members: DFS flags, members and stack bound per sroot ---- */
+    for (int32_t base = 0; base < N; base += 32 * TS_U) {
+        POA_LANES(l) {
+            int32_t r[TS_U], nn[TS_U];
+#pragma unroll
+            for (int32_t u = 0; u < TS_U; ++u) {
+                const int32_t v = base + 32 * u + l;
+                r[u] = v < N ? (int32_t)sroot[v] : (int32_t)NONE16;
+                nn[u] = (v < N && r[u] != NONE16) ? (int32_t)s.nin[v] + (int32_t)s.aln_cnt[v] + 1 : 0;
+            }
+#pragma unroll
+            for (int32_t u = 0; u < TS_U; ++u) {
+                const int32_t v = base + 32 * u + l;
+                if (v < N && r[u] != NONE16) {
+                    t_marks[v] = 0;
+                    t_check[v] = 1;
+                    poa_atomic_add(&t_cnt[r[u]], 1u);
+                    poa_atomic_add(&t_need[r[u]], (uint32_t)nn[u]);
+                }
+            }
+        }
+    }
+    POA_SYNC();
+    /* ---- 2a. offsets per sroot, work list of the sroots with more than one member ---- */
+    int32_t out_run = 0, stk_run = 0, n_work = 0;
+    for (int32_t base = 0; base < N; base += 64) {
+        PerLane<int> ca, cb, na, nb, wa, wb;
+        POA_LANES(l) {
+            const int32_t i0 = base + 2 * l, i1 = i0 + 1;
+            ca[l] = (i0 < N) ? (int)t_cnt[i0] : 0;
+            cb[l] = (i1 < N) ? (int)t_cnt[i1] : 0;
+            wa[l] = ca[l] > 1 ? 1 : 0;
+            wb[l] = cb[l] > 1 ? 1 : 0;
+            na[l] = wa[l] ? (int)t_need[i0] + 1 : 0;
+            nb[l] = wb[l] ? (int)t_need[i1] + 1 : 0;
+            if (ca[l] == 1) t_lpos[i0] = 0;
+            if (cb[l] == 1) t_lpos[i1] = 0;
+        }
+        PerLane<int> oo, so, wo;
+        POA_LANES(l) {
+            oo[l] = ca[l] + cb[l];
+            so[l] = na[l] + nb[l];
+            wo[l] = wa[l] + wb[l];
+        }
+        const int32_t ctot = warp_exscan(oo);
+        const int32_t stot = warp_exscan(so);
+        const int32_t wtot = warp_exscan(wo);
+        POA_LANES(l) {
+            const int32_t i0 = base + 2 * l, i1 = i0 + 1;
+            if (i0 < N) t_off[i0] = (uint32_t)(out_run + oo[l]);
+            if (i1 < N) t_off[i1] = (uint32_t)(out_run + oo[l] + ca[l]);
+            if (wa[l]) {
+                s.c_score[n_work + wo[l]] = i0;
+                s.c_pred[n_work + wo[l]] = stk_run + so[l];
+            }
+            if (wb[l]) {
+                s.c_score[n_work + wo[l] + wa[l]] = i1;
+                s.c_pred[n_work + wo[l] + wa[l]] = stk_run + so[l] + na[l];
+            }
+        }
+        out_run += ctot;
+        stk_run += stot;
+        n_work += wtot;
+    }
+    POA_SYNC();
+    /* ---- 2b. spoa's DFS inside each sroot (graph.cpp:294-354 on the members), 32 sroots at a time ---- */
+    for (int32_t base = 0; base < n_work; base += 32) {
+        POA_LANES(l) {
+            if (base + l >= n_work) continue;
+            const int32_t i = s.c_score[base + l];
+            uint16_t* stk = s.stack + s.c_pred[base + l];
+            int32_t sp = 0, out = 0;
+            stk[sp++] = (uint16_t)i;
+            while (sp != 0) {
+                const int32_t id = stk[sp - 1];
+                bool valid = true;
+                if (t_marks[id] != 2) {
+                    for (uint16_t e = s.in_head[id]; e != NONE16;) {
+                        const uint16_t nx = s.e_next[e];
+                        const int32_t u = s.e_src[e];
+                        if ((int32_t)sroot[u] == i && t_marks[u] != 2) {
+                            stk[sp++] = (uint16_t)u;
+                            valid = false;
+                        }
+                        e = nx;
+                    }
+                    const int32_t na = s.aln_cnt[id];
+                    if (t_check[id]) {
+                        for (int32_t q = 0; q < na; ++q) {
+                            const int32_t a = s.aln[id * KA + q];
+                            if ((int32_t)sroot[a] == i && t_marks[a] != 2) { /* member clique mates share the sroot */
+                                stk[sp++] = (uint16_t)a;
+                                t_check[a] = 0;
+                                valid = false;
+                            }
+                        }
+                    }
+                    if (valid) {
+                        t_marks[id] = 2;
+                        if (t_check[id]) {
+                            t_lpos[id] = (uint16_t)out++;
+                            for (int32_t q = 0; q < na; ++q) {
+                                const int32_t a = s.aln[id * KA + q];
+                                if ((int32_t)sroot[a] != i) continue; /* aligned list filtered to members (graph.cpp:660-666) */
+                                t_lpos[a] = (uint16_t)out++;
+                            }
+                        }
+                    } else {
+                        t_marks[id] = 1;
+                    }
+                }
+                if (valid) --sp;
+            }
+        }
+    }
+    POA_SYNC();
+    /* ---- 3. subgraph ranks; out-degree inside the subgraph (a member without member successors is a sink) ---- */
+    for (int32_t base = 0; base < N; base += 32) {
+        POA_LANES(l) {
+            const int32_t v = base + l;
+            if (v >= N) continue;
+            const int32_t x = sroot[v];
+            if (x == NONE16) continue;
+            const int32_t r = (int32_t)t_off[x] + (int32_t)t_lpos[v];
+            s.sub_rank[v] = (uint16_t)r;
+            s.sub_at[r] = (uint16_t)v;
+            for (uint16_t e = s.in_head[v]; e != NONE16; e = s.e_next[e]) {
+                const int32_t u = s.e_src[e];
+                if (sroot[u] != NONE16) s.roff[u] = 1u; /* only "has a member successor" is ever asked; an atomic inside a
+                                                           lane-divergent loop would also cost the module its uniformity proof */
+            }
+        }
+    }
+    POA_SYNC();
+    return out_run;
+}
+
+POA_FN int32_t mark_subgraph(const Slot& s, const Params& p, WinState& st, int32_t begin, int32_t end, uint16_t* sroot,
+                             int32_t sroot_cap) {
+    const int32_t N = poa_uniform(st.n_nodes);
+    if (p.serial_topsort || N > sroot_cap) return mark_subgraph_serial(s, p, st, begin, end);
+    subgraph_members(s, N, begin, end, sroot);
+    return subgraph_order(s, N, sroot);
 }
 
 /* Row program of a subgraph alignment: rows follow sub_at[], predecessor lists keep only member
@@ -1830,10 +2067,6 @@ POA_FN_NOINLINE void topsort_serial(const Slot& s_ref, const Params p_ref, WinSt
  *        members and store each member's position (lpos);
  *     3. every node: rank = offset[root] + lpos.
  * ---------------------------------------------------------------------------------------- */
-#ifndef POA_TS_U
-#define POA_TS_U 4
-#endif
-constexpr int TS_U = POA_TS_U; /* nodes per lane per step in the node-parallel passes of the sort */
 POA_FN_NOINLINE void topsort_roots(const Slot& s_ref, const Params p_ref, WinState& st) {
     const Slot s = s_ref;     /* local copies: no reloads of the descriptor after every store */
     const Params p = p_ref;
@@ -1933,12 +2166,14 @@ POA_FN_NOINLINE void topsort_roots(const Slot& s_ref, const Params p_ref, WinSta
                 const int32_t id = stk[sp - 1];
                 bool valid = true;
                 if (s.marks[id] != 2) {
-                    for (uint16_t e = s.in_head[id]; e != NONE16; e = s.e_next[e]) {
+                    for (uint16_t e = s.in_head[id]; e != NONE16;) {
+                        const uint16_t nx = s.e_next[e]; /* next link requested with the source, not after the stores below */
                         const int32_t u = s.e_src[e];
                         if ((int32_t)s.root[u] == i && s.marks[u] != 2) {
                             stk[sp++] = (uint16_t)u;
                             valid = false;
                         }
+                        e = nx;
                     }
                     const int32_t na = s.aln_cnt[id];
                     if (s.check[id]) {
@@ -2317,7 +2552,7 @@ POA_FN void process_window(const Slot& s, const Params& p, const WindowView& wv,
                 st.status = ST_GENERIC_ERROR;
                 break;
             }
-            n_rows = poa_uniform(mark_subgraph(s, p, st, sp_begin, sp_end));
+            n_rows = poa_uniform(mark_subgraph(s, p, st, sp_begin, sp_end, reinterpret_cast<uint16_t*>(tbs.cells), TB_SCRATCH_BYTES / 2));
         }
         /* static band: one try.  Adaptive band: the configured width is the first try; a traceback that comes close to
          * a band edge (or loses the path) re-aligns this read with twice the width, up to the full matrix. */

@@ -99,6 +99,21 @@ struct FillArgs { /* everything the row loop needs, and nothing else (keeps its 
     int32_t mg, xg, gap;
 };
 
+/* A load that stays where it is written: the row loop prefetches its record stream a block ahead, and the compiler would
+ * otherwise sink the load to just before its first use (one register less, one full memory latency more per block). */
+__device__ __forceinline__ uint32_t ldg_pinned(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+/* rare (after a row with more than 32 predecessors): restart the predecessor stream at entry `at`.  A call on purpose:
+ * as a predicated load inside the re-alignment it shared a scoreboard with the prefetch of the next 32 entries, and the
+ * first shuffle of every re-aligned row waited for that prefetch to land. */
+__device__ __noinline__ uint2 fill_restart_pred_stream(const uint32_t* row_pfill, int at) {
+    const int lane = threadIdx.x & 31;
+    return make_uint2(row_pfill[at + lane], row_pfill[at + 32 + lane]);
+}
+
 /* rare: predecessor older than the ring -> copy its row from global memory into the spare row */
 __device__ __noinline__ void fill_stage_far_row(const int16_t* src, uint32_t far_sa, int bw) {
     const int lane8 = (threadIdx.x & 31) * 8;
@@ -183,7 +198,6 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
      * whenever a row's entries would run past it, so a row with <= 32 predecessors reads them all
      * from predA with a single shuffle each. */
     uint32_t recA = row_rec[lane];
-    uint32_t recB = row_rec[32 + lane];
     int pbase = 0; /* row_pfill index held by lane 0 of predA */
     uint32_t predA = row_pfill[lane];
     uint32_t predB = row_pfill[32 + lane];
@@ -197,6 +211,7 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
 #pragma unroll 1
     for (int blk_end = 31; i <= N; blk_end += 32) {
     const int i_end = blk_end < N ? blk_end : N;
+    const uint32_t recN = ldg_pinned(row_rec + blk_end + 1 + lane); /* the next block's records, in flight during this one */
 #pragma unroll 1
     for (; i <= i_end; ++i) {
         const uint32_t rec = __shfl_sync(0xffffffffu, recA, i & 31);
@@ -216,13 +231,18 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
         uint32_t carry = NEG2; /* S[i][last column of the previous chunk], both halves */
         int rel = po - pbase;  /* lane of predA holding this row's first entry */
         if (rel + np > 32) {   /* re-align the stream so that predA starts at this row (uniform, ~1 row in 18) */
-            const int src = (lane + rel) & 31;
-            const uint32_t xa = __shfl_sync(0xffffffffu, predA, src);
-            const uint32_t xb = __shfl_sync(0xffffffffu, predB, src);
-            predA = (lane + rel < 32) ? xa : xb;
-            if (rel >= 32) predA = row_pfill[po + lane]; /* a row with > 32 entries jumped past predB */
+            if (rel > 32) { /* a row with > 32 entries jumped past predB */
+                const uint2 t = fill_restart_pred_stream(row_pfill, po);
+                predA = t.x;
+                predB = t.y;
+            } else {
+                const int src = (lane + rel) & 31;
+                const uint32_t xa = __shfl_sync(0xffffffffu, predA, src);
+                const uint32_t xb = __shfl_sync(0xffffffffu, predB, src);
+                predA = (lane + rel < 32) ? xa : xb;
+                predB = row_pfill[po + 32 + lane];
+            }
             pbase = po;
-            predB = row_pfill[po + 32 + lane];
             rel = 0;
         }
 
@@ -376,8 +396,7 @@ __device__ __noinline__ int32_t fill_rows(const FillArgs fa) {
         po += np;
         __syncwarp(); /* row i (ring + global) is visible to every lane before it is read */
     }
-    recA = recB;
-    recB = row_rec[blk_end + 33 + lane]; /* rows of the block after the next one */
+    recA = recN;
     }
     return end_row;
 }
@@ -439,7 +458,6 @@ __device__ __noinline__ int32_t fill_rows_wide(const FillArgs fa) {
         if (c + 8 <= ring_cols) sts128(c0_sa + RING_PAD_FRONT * 2u + 16u * v, make_uint4(0u, 0u, 0u, 0u));
     }
     uint32_t recA = row_rec[lane];
-    uint32_t recB = row_rec[32 + lane];
     int pbase = 0;
     uint32_t predA = row_pfill[lane];
     uint32_t predB = row_pfill[32 + lane];
@@ -454,6 +472,7 @@ __device__ __noinline__ int32_t fill_rows_wide(const FillArgs fa) {
 #pragma unroll 1
     for (int blk_end = 31; i <= N; blk_end += 32) {
     const int i_end = blk_end < N ? blk_end : N;
+    const uint32_t recN = ldg_pinned(row_rec + blk_end + 1 + lane); /* the next block's records, in flight during this one */
 #pragma unroll 1
     for (; i <= i_end; ++i) {
         const uint32_t rec = __shfl_sync(0xffffffffu, recA, i & 31);
@@ -469,13 +488,18 @@ __device__ __noinline__ int32_t fill_rows_wide(const FillArgs fa) {
         Srow += stride;
         int rel = po - pbase;
         if (rel + np > 32) {
-            const int src = (lane + rel) & 31;
-            const uint32_t xa = __shfl_sync(0xffffffffu, predA, src);
-            const uint32_t xb = __shfl_sync(0xffffffffu, predB, src);
-            predA = (lane + rel < 32) ? xa : xb;
-            if (rel >= 32) predA = row_pfill[po + lane];
+            if (rel > 32) { /* a row with > 32 entries jumped past predB */
+                const uint2 t = fill_restart_pred_stream(row_pfill, po);
+                predA = t.x;
+                predB = t.y;
+            } else {
+                const int src = (lane + rel) & 31;
+                const uint32_t xa = __shfl_sync(0xffffffffu, predA, src);
+                const uint32_t xb = __shfl_sync(0xffffffffu, predB, src);
+                predA = (lane + rel < 32) ? xa : xb;
+                predB = row_pfill[po + 32 + lane];
+            }
             pbase = po;
-            predB = row_pfill[po + 32 + lane];
             rel = 0;
         }
         /* profile: 8*NV int8 under this lane's columns, widened to int16 pairs */
@@ -578,8 +602,7 @@ __device__ __noinline__ int32_t fill_rows_wide(const FillArgs fa) {
         po += np;
         __syncwarp();
     }
-    recA = recB;
-    recB = row_rec[blk_end + 33 + lane];
+    recA = recN;
     }
     return end_row;
 }

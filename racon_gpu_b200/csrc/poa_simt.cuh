@@ -72,6 +72,9 @@ struct PerLane {
  *   4. Never leave a loop or a function from lane-dependent control flow: set a flag, decide by a vote.
  *   5. After a lane-0 block that is followed by a loop back edge, reconverge explicitly (__syncwarp).
  *   6. Keep the number of live uniform values small: derive (edge capacity from node capacity) instead of carrying.
+ *   7. No atomicAdd inside a lane-divergent loop (ptxas aggregates it with a match/vote of its own, which sits in
+ *      divergent flow by construction): use an idempotent plain store where a flag is all that is asked, or hoist the
+ *      atomic into straight-line predicated code (mark_subgraph / topsort_roots).
  * In the proven state __syncwarp() costs no instruction at all and uniform arithmetic moves to the uniform datapath. */
 POA_FN int poa_uniform(int x) { return __reduce_max_sync(0xffffffffu, x); }
 /* a de-facto uniform predicate made provably uniform by a vote */
