@@ -722,13 +722,41 @@ POA_FN_NOINLINE void subgraph_members(const Slot& s_ref, int32_t N, int32_t begi
     POA_SYNC();
     /* ---- members and their sroot ---- */
     for (int32_t hi = r_top; hi >= 0; hi -= 32 - (KA + 1)) {
-        PerLane<int> vv;
+        /* the chunk's topology, read once: up to four in-edge sources and the aligned nodes of every lane's node, packed
+         * two ids per register (a longer in-edge list is walked in memory each time its node has something to pass on) */
+        PerLane<int> vv, n_src, passed, s01, s23, m01, m23, m45, m6;
         POA_LANES(l) {
             const int32_t r = hi - l;
             int32_t v = r >= 0 ? (int32_t)s.node_at[r] : -1;
             if (v < begin) v = -1; /* backbone before `begin`: not a member, passes nothing on */
             vv[l] = v;
+            passed[l] = 0x10000; /* the sroot this lane has last passed on (none yet) */
+            uint32_t sp[4] = {NONE16, NONE16, NONE16, NONE16};
+            uint32_t mt[8] = {NONE16, NONE16, NONE16, NONE16, NONE16, NONE16, NONE16, NONE16};
+            int32_t n = 0;
+            if (v >= 0) {
+                for (uint16_t e = s.in_head[v]; e != NONE16;) {
+                    const uint16_t nx = s.e_next[e];
+                    const uint32_t u = s.e_src[e];
+                    if (n < 4) sp[n] = u;
+                    ++n;
+                    e = nx;
+                }
+                const int32_t na = s.aln_cnt[v];
+#pragma unroll
+                for (int32_t q = 0; q < KA; ++q)
+                    if (q < na) mt[q] = s.aln[v * KA + q];
+            }
+            n_src[l] = n;
+            s01[l] = (int32_t)(sp[0] | (sp[1] << 16));
+            s23[l] = (int32_t)(sp[2] | (sp[3] << 16));
+            m01[l] = (int32_t)(mt[0] | (mt[1] << 16));
+            m23[l] = (int32_t)(mt[2] | (mt[3] << 16));
+            m45[l] = (int32_t)(mt[4] | (mt[5] << 16));
+            m6[l] = (int32_t)mt[6];
         }
+        /* pass sroots on until nothing moves.  Two lanes may write one target in the same step and the larger value
+         * may land last: a lane counts its value as passed on only once every target is seen to hold it (or less). */
         for (;;) {
             PerLane<int> ch;
             POA_LANES(l) {
@@ -736,24 +764,35 @@ POA_FN_NOINLINE void subgraph_members(const Slot& s_ref, int32_t N, int32_t begi
                 const int32_t v = vv[l];
                 if (v < 0) continue;
                 const int32_t x = sroot[v];
-                if (x == NONE16) continue;
-                for (uint16_t e = s.in_head[v]; e != NONE16; e = s.e_next[e]) {
-                    const int32_t u = s.e_src[e];
+                if (x == NONE16 || x >= passed[l]) continue;
+                const uint32_t tg[11] = {(uint32_t)s01[l] & 0xFFFFu, (uint32_t)s01[l] >> 16, (uint32_t)s23[l] & 0xFFFFu,
+                                         (uint32_t)s23[l] >> 16,     (uint32_t)m01[l] & 0xFFFFu, (uint32_t)m01[l] >> 16,
+                                         (uint32_t)m23[l] & 0xFFFFu, (uint32_t)m23[l] >> 16,     (uint32_t)m45[l] & 0xFFFFu,
+                                         (uint32_t)m45[l] >> 16,     (uint32_t)m6[l] & 0xFFFFu};
+                int32_t moved = 0;
+#pragma unroll
+                for (int32_t k = 0; k < 11; ++k) {
+                    const int32_t u = (int32_t)tg[k];
                     const int32_t nx = x < u ? x : u;
-                    if (u >= begin && (int32_t)sroot[u] > nx) {
+                    if (u != NONE16 && u >= begin && (int32_t)sroot[u] > nx) {
                         sroot[u] = (uint16_t)nx;
-                        ch[l] = 1;
+                        moved = 1;
                     }
                 }
-                const int32_t na = s.aln_cnt[v];
-                for (int32_t q = 0; q < na; ++q) {
-                    const int32_t a = s.aln[v * KA + q];
-                    const int32_t nx = x < a ? x : a;
-                    if (a >= begin && (int32_t)sroot[a] > nx) {
-                        sroot[a] = (uint16_t)nx;
-                        ch[l] = 1;
+                if (n_src[l] > 4) { /* rare: the rest of a long in-edge list */
+                    int32_t k = 0;
+                    for (uint16_t e = s.in_head[v]; e != NONE16; e = s.e_next[e], ++k) {
+                        if (k < 4) continue;
+                        const int32_t u = s.e_src[e];
+                        const int32_t nx = x < u ? x : u;
+                        if (u >= begin && (int32_t)sroot[u] > nx) {
+                            sroot[u] = (uint16_t)nx;
+                            moved = 1;
+                        }
                     }
                 }
+                if (moved) ch[l] = 1; /* look again: the stores are checked in the next step */
+                else passed[l] = x;   /* every target already holds it */
             }
             POA_SYNC();
             if (!warp_ballot(ch)) break;
