@@ -37,4 +37,4 @@ def test_the_fill_uses_the_packed_int16_pipeline_and_async_copies(sass):
     for op in ("VIADDMNMX.S16x2", "VIMNMX3.S16x2", "LDGSTS", "CREDUX", "STG.E.EF.128"):
         assert op in sass, op
     n_instr = len(re.findall(r"^\s+/\*[0-9a-f]{4,6}\*/", sass, flags=re.M))
-    assert n_instr < 13000, f"kernel grew to {n_instr} instructions: check for divergence fallbacks or unrolling"
+    assert n_instr < 14500, f"kernel grew to {n_instr} instructions: check for divergence fallbacks or unrolling"
