@@ -52,6 +52,7 @@ struct poa_graph {
     int32_t ne, ecap;
     int32_t num_sequences;
     ivec rank_to_node;
+    ivec begin_nodes; /* spoa::Graph::sequences_begin_nodes_ids_ */
 };
 
 poa_graph* poa_graph_create(void) { return (poa_graph*)calloc(1, sizeof(poa_graph)); }
@@ -67,6 +68,7 @@ void poa_graph_destroy(poa_graph* g) {
     free(g->nodes);
     free(g->edges);
     iv_free(&g->rank_to_node);
+    iv_free(&g->begin_nodes);
     free(g);
 }
 
@@ -183,7 +185,7 @@ void poa_graph_add_alignment(poa_graph* g, const poa_pair* aln, int32_t n_aln, c
                              int32_t len, const uint32_t* w) {
     if (len == 0) return;
     if (n_aln == 0) { /* graph.cpp:177-185 */
-        add_sequence(g, seq, w, 0, len);
+        iv_push(&g->begin_nodes, add_sequence(g, seq, w, 0, len));
         ++g->num_sequences;
         topological_sort(g);
         return;
@@ -196,7 +198,7 @@ void poa_graph_add_alignment(poa_graph* g, const poa_pair* aln, int32_t n_aln, c
         }
     }
     int32_t tmp = g->nn;
-    add_sequence(g, seq, w, 0, first_valid);
+    int32_t begin_node = add_sequence(g, seq, w, 0, first_valid);
     int32_t head = (tmp == g->nn) ? -1 : g->nn - 1;
     int32_t tail = add_sequence(g, seq, w, last_valid + 1, len);
     int32_t new_id = -1;
@@ -233,12 +235,14 @@ void poa_graph_add_alignment(poa_graph* g, const poa_pair* aln, int32_t n_aln, c
                 new_id = aligned_to;
             }
         }
+        if (begin_node == -1) begin_node = new_id; /* graph.cpp:244-246 */
         if (head != -1) add_edge_labelled(g, head, new_id, prev_w + (int64_t)w[aln[i].pos]);
         head = new_id;
         prev_w = (int64_t)w[aln[i].pos];
     }
     if (tail != -1) add_edge_labelled(g, head, tail, prev_w + (int64_t)w[last_valid + 1]);
     ++g->num_sequences;
+    iv_push(&g->begin_nodes, begin_node); /* graph.cpp:269 */
     topological_sort(g);
 }
 
@@ -519,20 +523,10 @@ static poa_graph* subgraph(const poa_graph* g, int32_t begin, int32_t end, int32
     return s;
 }
 
-/* window.cpp:65-142 Window::generate_consensus */
-int32_t poa_oracle_window_consensus(int32_t n_seqs, const char* const* seqs, const int32_t* lens,
-                                    const int8_t* const* weights, const int32_t* begins,
-                                    const int32_t* ends, int32_t tgs, int32_t trim, int32_t m,
-                                    int32_t x, int32_t gap, char* cons_out, uint32_t* cov_out,
-                                    int32_t max_out, int32_t* polished, int64_t* stats) {
-    if (stats) stats[0] = stats[1] = stats[2] = stats[3] = stats[4] = stats[5] = 0;
-    if (n_seqs < 3) { /* window.cpp:68-71 */
-        if (polished) *polished = 0;
-        if (lens[0] > max_out) return -1;
-        memcpy(cons_out, seqs[0], (size_t)lens[0]);
-        if (cov_out) memset(cov_out, 0, sizeof(uint32_t) * (size_t)lens[0]);
-        return lens[0];
-    }
+/* window.cpp:73-116: the graph of one window -- backbone, then every layer aligned (whole graph or subgraph) and added */
+static poa_graph* window_graph(int32_t n_seqs, const char* const* seqs, const int32_t* lens,
+                               const int8_t* const* weights, const int32_t* begins, const int32_t* ends,
+                               int32_t m, int32_t x, int32_t gap, int64_t* stats) {
     int32_t maxlen = 0;
     for (int32_t i = 0; i < n_seqs; ++i)
         if (lens[i] > maxlen) maxlen = lens[i];
@@ -547,7 +541,7 @@ int32_t poa_oracle_window_consensus(int32_t n_seqs, const char* const* seqs, con
     for (int32_t i = 1; i < n_seqs; ++i) {
         poa_pair* aln = NULL;
         int32_t n_aln;
-        if ((uint32_t)begins[i] < offset && (uint32_t)ends[i] > L - offset) { /* window.cpp:92-95 */
+        if (!begins || ((uint32_t)begins[i] < offset && (uint32_t)ends[i] > L - offset)) { /* window.cpp:92-95 */
             if (stats) {
                 stats[2] += (int64_t)g->nn * (lens[i] + 1);
                 stats[4] += (int64_t)g->nn * (lens[i] + 1 < 256 ? lens[i] + 1 : 256);
@@ -571,6 +565,25 @@ int32_t poa_oracle_window_consensus(int32_t n_seqs, const char* const* seqs, con
         free(aln);
         if (stats) stats[3] += 1;
     }
+    free(w);
+    return g;
+}
+
+/* window.cpp:65-142 Window::generate_consensus */
+int32_t poa_oracle_window_consensus(int32_t n_seqs, const char* const* seqs, const int32_t* lens,
+                                    const int8_t* const* weights, const int32_t* begins,
+                                    const int32_t* ends, int32_t tgs, int32_t trim, int32_t m,
+                                    int32_t x, int32_t gap, char* cons_out, uint32_t* cov_out,
+                                    int32_t max_out, int32_t* polished, int64_t* stats) {
+    if (stats) stats[0] = stats[1] = stats[2] = stats[3] = stats[4] = stats[5] = 0;
+    if (n_seqs < 3) { /* window.cpp:68-71 */
+        if (polished) *polished = 0;
+        if (lens[0] > max_out) return -1;
+        memcpy(cons_out, seqs[0], (size_t)lens[0]);
+        if (cov_out) memset(cov_out, 0, sizeof(uint32_t) * (size_t)lens[0]);
+        return lens[0];
+    }
+    poa_graph* g = window_graph(n_seqs, seqs, lens, weights, begins, ends, m, x, gap, stats);
 
     char* cons = NULL;
     uint32_t* cov = NULL;
@@ -602,10 +615,65 @@ int32_t poa_oracle_window_consensus(int32_t n_seqs, const char* const* seqs, con
     if (polished) *polished = 1;
     free(cons);
     free(cov);
-    free(w);
     poa_graph_destroy(g);
     return ret;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Multiple sequence alignment  (graph.cpp:373-389 initialize_multiple_sequence_alignment,
+ * :391-427 generate_multiple_sequence_alignment with include_consensus = false, Node::successor :31-43).
+ * This is what the reference's own MSA test holds cudapoa's Batch::get_msa against
+ * (vendor/GenomeWorks/cudapoa/tests/Test_CudapoaGenerateMSA2.cu:62-79,117-128).
+ * Returns the number of rows (= sequences); *rows_out is ONE malloc'ed block of n_rows x *msa_len bytes.
+ * ---------------------------------------------------------------------------------------- */
+int32_t poa_graph_msa(const poa_graph* g, char** rows_out, int32_t* msa_len) {
+    int32_t* msa_id = (int32_t*)malloc(sizeof(int32_t) * (size_t)(g->nn + 1));
+    int32_t n_cols = 0;
+    for (int32_t i = 0; i < g->nn; ++i) { /* graph.cpp:379-386: a node and its aligned nodes share one column */
+        int32_t id = g->rank_to_node.v[i];
+        msa_id[id] = n_cols;
+        for (int32_t j = 0; j < g->nodes[id].aligned.n; ++j) msa_id[g->rank_to_node.v[++i]] = n_cols;
+        ++n_cols;
+    }
+    char* rows = (char*)malloc((size_t)g->num_sequences * (size_t)n_cols + 1);
+    memset(rows, '-', (size_t)g->num_sequences * (size_t)n_cols);
+    for (int32_t i = 0; i < g->num_sequences; ++i) { /* graph.cpp:400-414 */
+        char* row = rows + (size_t)i * (size_t)n_cols;
+        int32_t id = g->begin_nodes.v[i];
+        for (;;) {
+            row[msa_id[id]] = g->nodes[id].letter;
+            int32_t next = -1; /* Node::successor: first out-edge that carries this sequence's label */
+            for (int32_t k = 0; k < g->nodes[id].out.n && next < 0; ++k) {
+                const edge_t* e = &g->edges[g->nodes[id].out.v[k]];
+                for (int32_t q = 0; q < e->labels.n; ++q)
+                    if (e->labels.v[q] == i) {
+                        next = e->dst;
+                        break;
+                    }
+            }
+            if (next < 0) break;
+            id = next;
+        }
+    }
+    free(msa_id);
+    *rows_out = rows;
+    *msa_len = n_cols;
+    return g->num_sequences;
+}
+
+/* The MSA of one window whose graph is built like window.cpp:73-116 builds it (sequences in processing order; a
+ * cudapoa-style group is the special case "every layer spans the window": begins/ends NULL). */
+int32_t poa_oracle_window_msa(int32_t n_seqs, const char* const* seqs, const int32_t* lens,
+                              const int8_t* const* weights, const int32_t* begins, const int32_t* ends,
+                              int32_t m, int32_t x, int32_t gap, char** rows_out, int32_t* msa_len) {
+    if (!ends) begins = NULL;
+    poa_graph* g = window_graph(n_seqs, seqs, lens, weights, begins, ends, m, x, gap, NULL);
+    int32_t n = poa_graph_msa(g, rows_out, msa_len);
+    poa_graph_destroy(g);
+    return n;
+}
+
+void poa_oracle_free(void* p) { free(p); }
 
 /* ------------------------------------------------------------------------------------------
  * Flat-batch runner: same role as racon::Polisher::polish (src/polisher.cpp:486-548): one task

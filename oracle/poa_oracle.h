@@ -9,6 +9,7 @@
  *   spoa::Graph::topological_sort                /root/reference/vendor/spoa/src/graph.cpp:294-354
  *   spoa::Graph::generate_consensus & friends    /root/reference/vendor/spoa/src/graph.cpp:44-58,440-589
  *   spoa::Graph::subgraph / update_alignment     /root/reference/vendor/spoa/src/graph.cpp:592-683
+ *   spoa::Graph::generate_multiple_sequence_alignment  /root/reference/vendor/spoa/src/graph.cpp:373-427
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
  * may load this library.  The product (racon_gpu_b200/) never links, imports or calls it.
@@ -87,6 +88,17 @@ void poa_oracle_polish_windows(int64_t n_windows, const int64_t* win_seq_off, co
                                int32_t m, int32_t x, int32_t gap, int32_t n_threads, char* cons_out,
                                uint16_t* cov_out, int32_t stride, int32_t* cons_len,
                                uint8_t* polished, int64_t* stats);
+
+/* spoa::Graph::generate_multiple_sequence_alignment(dst, false)  (graph.cpp:373-427): one row per sequence in the
+ * order they were added, '-' where the sequence has no base in a column.  *rows_out is one malloc'ed block of
+ * n_rows x *msa_len bytes (free with poa_oracle_free); returns n_rows. */
+int32_t poa_graph_msa(const poa_graph* g, char** rows_out, int32_t* msa_len);
+/* The same for a window built like racon builds it (sequences in processing order; begins/ends NULL: every layer
+ * spans the window, i.e. a plain cudapoa group). */
+int32_t poa_oracle_window_msa(int32_t n_seqs, const char* const* seqs, const int32_t* lens,
+                              const int8_t* const* weights, const int32_t* begins, const int32_t* ends,
+                              int32_t m, int32_t x, int32_t gap, char** rows_out, int32_t* msa_len);
+void poa_oracle_free(void* p);
 
 /* Global edit distance of two long strings (banded, doubling threshold); test helper for the stitched-contig
  * goldens of test/racon_test.cpp:88-130,176-196. */

@@ -163,4 +163,33 @@ int32_t ref_spoa_window(int32_t n_seqs, const char* const* seqs, const int32_t* 
     return len;
 }
 
+/*
+ * spoa's multiple sequence alignment of one group of sequences, the way the reference's own MSA test produces its
+ * expected value (vendor/GenomeWorks/cudapoa/tests/Test_CudapoaGenerateMSA2.cu:62-79: kNW engine, align + add_alignment
+ * per sequence, Graph::generate_multiple_sequence_alignment).  Rows are written back to back into `out`
+ * (n_seqs x *msa_len bytes) when they fit max_out.  Returns the number of rows.
+ */
+int32_t ref_spoa_window_msa(int32_t n_seqs, const char* const* seqs, const int32_t* lens,
+                            const int8_t* const* weights, int32_t m, int32_t x, int32_t g, char* out,
+                            int64_t max_out, int32_t* msa_len) {
+    auto engine = spoa::createAlignmentEngine(spoa::AlignmentType::kNW, static_cast<int8_t>(m),
+                                              static_cast<int8_t>(x), static_cast<int8_t>(g));
+    auto graph = spoa::createGraph();
+    for (int32_t i = 0; i < n_seqs; ++i) {
+        spoa::Alignment aln;
+        if (i > 0) aln = engine->align(seqs[i], static_cast<uint32_t>(lens[i]), graph);
+        std::vector<uint32_t> w(static_cast<size_t>(lens[i]), 1u);
+        if (weights && weights[i])
+            for (int32_t k = 0; k < lens[i]; ++k) w[static_cast<size_t>(k)] = static_cast<uint32_t>(weights[i][k]);
+        graph->add_alignment(aln, seqs[i], static_cast<uint32_t>(lens[i]), w);
+    }
+    std::vector<std::string> msa;
+    graph->generate_multiple_sequence_alignment(msa);
+    const size_t L = msa.empty() ? 0 : msa[0].size();
+    if (msa_len) *msa_len = static_cast<int32_t>(L);
+    if (static_cast<int64_t>(L * msa.size()) <= max_out)
+        for (size_t i = 0; i < msa.size(); ++i) std::memcpy(out + i * L, msa[i].data(), L);
+    return static_cast<int32_t>(msa.size());
+}
+
 } // extern "C"

@@ -64,6 +64,50 @@ class Oracle:
         return out, covs, pol.astype(bool)
 
 
+def _seq_arrays(seqs, weights):
+    n = len(seqs)
+    arr_s = (C.c_char_p * n)(*[bytes(s) for s in seqs])
+    lens = np.asarray([len(s) for s in seqs], dtype=np.int32)
+    keep = [None if w is None else np.ascontiguousarray(w, dtype=np.int8) for w in weights]
+    arr_w = (C.POINTER(C.c_int8) * n)(*[
+        C.cast(None, C.POINTER(C.c_int8)) if w is None else _p(w, C.c_int8) for w in keep])
+    return n, arr_s, lens, keep, arr_w
+
+
+def window_sequences(batch, order: np.ndarray, w: int):
+    """Window w of a flat batch as (seqs, weights, begins, ends) in PROCESSING order."""
+    s0, s1 = int(batch.win_seq_off[w]), int(batch.win_seq_off[w + 1])
+    seqs, wts, bg, en = [], [], [], []
+    for k in range(s1 - s0):
+        s = s0 + int(order[s0 + k])
+        a, b = int(batch.seq_off[s]), int(batch.seq_off[s + 1])
+        seqs.append(batch.bases[a:b].tobytes())
+        wts.append(batch.weights[a:b].copy() if batch.has_weights[s] else None)
+        bg.append(int(batch.begins[s]))
+        en.append(int(batch.ends[s]))
+    return seqs, wts, bg, en
+
+
+def oracle_window_msa(oracle: "Oracle", seqs, weights, begins, ends, m: int, x: int, g: int):
+    """spoa's MSA (one row per sequence, processing order) of a window built like racon builds it; begins None:
+    every layer spans the window (a plain cudapoa group)."""
+    lib = oracle.lib
+    n, arr_s, lens, keep, arr_w = _seq_arrays(seqs, weights)
+    rows = C.c_void_p()
+    L = C.c_int32(0)
+    lib.poa_oracle_window_msa.restype = C.c_int32
+    bg = None if begins is None else np.ascontiguousarray(begins, dtype=np.int32)
+    en = None if begins is None else np.ascontiguousarray(ends, dtype=np.int32)
+    nr = lib.poa_oracle_window_msa(C.c_int32(n), arr_s, _p(lens, C.c_int32), arr_w,
+                                   None if bg is None else _p(bg, C.c_int32),
+                                   None if en is None else _p(en, C.c_int32),
+                                   C.c_int32(m), C.c_int32(x), C.c_int32(g), C.byref(rows), C.byref(L))
+    buf = C.string_at(rows.value, nr * L.value)
+    lib.poa_oracle_free.argtypes = [C.c_void_p]
+    lib.poa_oracle_free(rows)
+    return [buf[i * L.value:(i + 1) * L.value] for i in range(nr)]
+
+
 class Ref:
     """The unmodified reference.  `available` is False when oracle/_ref was not built/shipped."""
 
@@ -113,6 +157,19 @@ class Ref:
             C.c_int32(g), cons.ctypes.data_as(C.c_char_p), _p(cov, C.c_uint32), C.c_int32(max_out),
             _p(rank, C.c_int32), C.c_int32(max_nodes), C.byref(nn))
         return cons[:ln].tobytes(), cov[:ln].copy(), rank[:nn.value].copy()
+
+
+def ref_window_msa(ref: Ref, seqs, weights, m: int, x: int, g: int):
+    """spoa::Graph::generate_multiple_sequence_alignment of the unmodified reference for one group."""
+    n, arr_s, lens, keep, arr_w = _seq_arrays(seqs, weights)
+    cap = int(lens.sum()) * n + 64
+    out = np.zeros(cap, dtype=np.uint8)
+    L = C.c_int32(0)
+    ref.lib.ref_spoa_window_msa.restype = C.c_int32
+    nr = ref.lib.ref_spoa_window_msa(C.c_int32(n), arr_s, _p(lens, C.c_int32), arr_w, C.c_int32(m), C.c_int32(x),
+                                     C.c_int32(g), out.ctypes.data_as(C.c_char_p), C.c_int64(cap), C.byref(L))
+    assert nr * L.value <= cap
+    return [out[i * L.value:(i + 1) * L.value].tobytes() for i in range(nr)]
 
 
 def processing_order(batch, layer_order_fn) -> np.ndarray:
