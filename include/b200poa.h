@@ -13,6 +13,7 @@
  *   b200poa_batch_total_poas     <- Batch::get_total_poas()                 .../cudapoa/batch.hpp:110
  *   b200poa_batch_generate       <- Batch::generate_poa()                   .../cudapoa/batch.hpp:113
  *   b200poa_batch_get_consensus  <- Batch::get_consensus(consensus, coverage, output_status)  .../cudapoa/batch.hpp:125-127
+ *   b200poa_batch_get_msa        <- Batch::get_msa(msa, output_status)      .../cudapoa/batch.hpp:141-142
  *   b200poa_batch_id             <- Batch::batch_id()                       .../cudapoa/batch.hpp:155
  *   b200poa_batch_reset          <- Batch::reset()                          .../cudapoa/batch.hpp:158
  *   b200poa_batch_destroy        <- Batch::~Batch()
@@ -163,6 +164,22 @@ int32_t b200poa_batch_download(b200poa_batch* b);
 int32_t b200poa_batch_get_consensus(b200poa_batch* b, const uint8_t** cons, const uint16_t** cov,
                                     const int32_t** lens, const int32_t** status, const int32_t** offsets,
                                     const int32_t** trim);
+
+/*
+ * Batch::get_msa (batch.hpp:141-142, cudapoa_batch.cuh:260-313): synchronises and completes the download of the
+ * multiple sequence alignments (the batch must have been created with B200POA_OUTPUT_MSA in its output mask, else
+ * B200POA_OUTPUT_TYPE_UNAVAILABLE).  Window i's alignment is n_rows[i] rows of n_cols[i] bytes, back to back at
+ * msa + offsets[i]; row k belongs to the k-th sequence STAGED for the window (entry order of b200poa_batch_add_group;
+ * processing order for the columnar adds), '-' where the sequence has no base in a column.  Rows and columns are those
+ * of spoa::Graph::generate_multiple_sequence_alignment (vendor/spoa/src/graph.cpp:373-427), which is what the
+ * reference's own test compares cudapoa with (cudapoa/tests/Test_CudapoaGenerateMSA2.cu:117-128).  status[i] is the
+ * window's StatusType; an alignment of max_consensus_size columns or more reports
+ * B200POA_EXCEEDED_MAXIMUM_SEQUENCE_SIZE like the reference (cudapoa_generate_msa.cuh:203-208) and has n_cols 0.
+ * Only the bytes the launch produced cross PCIe (the reference copies max_poas x max_sequences_per_poa x
+ * max_consensus_size).  Pointers are into batch-owned pinned host memory, valid until the next generate / reset.
+ */
+int32_t b200poa_batch_get_msa(b200poa_batch* b, const uint8_t** msa, const int64_t** offsets, const int32_t** n_rows,
+                              const int32_t** n_cols, const int32_t** status);
 
 /* Batch options (extensions).  DOWNLOAD_COVERAGE (default 1): 0 = callers that only need the trimmed consensus skip
  * two thirds of the D2H bytes.  TRIM_COUNTS_STAGED (default 0, set before adding windows): 1 = the trim threshold

@@ -30,13 +30,15 @@ FULL_BAND = 0
 STATIC_BAND = 1
 ADAPTIVE_BAND = 2
 OUTPUT_CONSENSUS = 1
+OUTPUT_MSA = 2
+OUTPUT_TYPE_UNAVAILABLE = 9
 
 #: every symbol include/b200poa.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = (
     "b200poa_init", "b200poa_config_default", "b200poa_batch_create", "b200poa_batch_add_group",
     "b200poa_layer_order", "b200poa_batch_add_windows", "b200poa_batch_total_poas",
     "b200poa_batch_generate", "b200poa_batch_upload", "b200poa_batch_launch",
-    "b200poa_batch_download", "b200poa_batch_get_consensus", "b200poa_batch_id",
+    "b200poa_batch_download", "b200poa_batch_get_consensus", "b200poa_batch_get_msa", "b200poa_batch_id",
     "b200poa_batch_reset", "b200poa_batch_destroy", "b200poa_batch_get_info", "b200poa_batch_set_option",
     "b200poa_polisher_create_ex", "b200poa_compact_rows", "b200poa_batch_add_windows_pinned", "b200poa_weight_modes",
     "b200poa_arena_append_columns",
@@ -243,6 +245,37 @@ class PoaBatch:
         if with_trim:
             return out_c, out_v, stat_a, [(int(t) & 0xFFFF, int(t) >> 16) for t in trim_a]
         return out_c, out_v, stat_a
+
+    def get_msa(self):
+        """Batch::get_msa.  Synchronises.  Returns (msa, status): msa[i] is the list of rows (bytes, one per staged
+        sequence, in the order they were staged) of window i, or None where status[i] != 0."""
+        msa = C.POINTER(C.c_uint8)()
+        offs = C.POINTER(C.c_int64)()
+        rows = C.POINTER(C.c_int32)()
+        cols = C.POINTER(C.c_int32)()
+        stat = C.POINTER(C.c_int32)()
+        st = self.lib.b200poa_batch_get_msa(self.handle, C.byref(msa), C.byref(offs), C.byref(rows), C.byref(cols),
+                                            C.byref(stat))
+        if st == OUTPUT_TYPE_UNAVAILABLE:
+            raise RuntimeError("b200poa_batch_get_msa: output_type_unavailable (create the batch with OUTPUT_MSA)")
+        self._check(st, "b200poa_batch_get_msa")
+        n = self.get_total_poas()
+        if n == 0:
+            return [], np.zeros(0, dtype=np.int32)
+        offs_a = np.ctypeslib.as_array(offs, shape=(n,)).copy()
+        rows_a = np.ctypeslib.as_array(rows, shape=(n,)).copy()
+        cols_a = np.ctypeslib.as_array(cols, shape=(n,)).copy()
+        stat_a = np.ctypeslib.as_array(stat, shape=(n,)).copy()
+        used = int((offs_a + rows_a.astype(np.int64) * cols_a).max())
+        arena = np.ctypeslib.as_array(msa, shape=(max(used, 1),)) if used > 0 else np.zeros(1, dtype=np.uint8)
+        out = []
+        for i in range(n):
+            if stat_a[i] != SUCCESS:
+                out.append(None)
+                continue
+            o, c = int(offs_a[i]), int(cols_a[i])
+            out.append([arena[o + k * c:o + (k + 1) * c].tobytes() for k in range(int(rows_a[i]))])
+        return out, stat_a
 
     def set_option(self, option: int, value: int):
         self._check(self.lib.b200poa_batch_set_option(self.handle, C.c_int32(option), C.c_int64(value)),

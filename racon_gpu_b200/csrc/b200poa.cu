@@ -56,6 +56,14 @@ struct KernelArgs {
     int32_t* out_status;
     int32_t* out_off;
     int32_t* out_trim;
+    /* multiple sequence alignment (output mask has B200POA_OUTPUT_MSA; else all null) */
+    uint16_t* path;               /* [arena] node of every base, parallel to `bases` */
+    uint8_t* out_msa;             /* compact MSA arena */
+    unsigned long long* msa_cursor;
+    unsigned long long msa_cap;
+    long long* out_msa_off;
+    int32_t* out_msa_cols;
+    int32_t* out_msa_status;
     int32_t prof_stride; /* bytes per profile row        */
     int32_t ring_stride; /* int16 cells per ring row     */
     int32_t ring_rows;   /* power of two                 */
@@ -92,6 +100,11 @@ __global__ void __launch_bounds__(32, POA_MIN_BLOCKS_PER_SM) poa_window_kernel(c
                 a.out_off[w] = 0;
                 a.out_trim[w] = (int32_t)0xFFFF0000u;
                 a.out_status[w] = a.win_flags[w];
+                if (a.out_msa) {
+                    a.out_msa_off[w] = 0;
+                    a.out_msa_cols[w] = 0;
+                    a.out_msa_status[w] = a.win_flags[w];
+                }
             }
             __syncwarp(); /* explicit reconvergence before the back edge: without it ptxas assumes a diverged loop head
                              and gives EVERY collective of the kernel a BRA.DIV slow path (poa_simt.cuh) */
@@ -107,6 +120,7 @@ __global__ void __launch_bounds__(32, POA_MIN_BLOCKS_PER_SM) poa_window_kernel(c
         wv.w_off = a.w_off + s0;
         wv.seq_begin = a.seq_begin + s0;
         wv.seq_end = a.seq_end + s0;
+        wv.path = a.path;
         WindowOut out;
         out.cons = a.out_cons;
         out.cov = a.out_cov;
@@ -116,7 +130,17 @@ __global__ void __launch_bounds__(32, POA_MIN_BLOCKS_PER_SM) poa_window_kernel(c
         out.off = a.out_off + w;
         out.trim = a.out_trim + w;
         out.trim_nseq = a.win_trim_nseq[w];
-        process_window(s, a.p, wv, fill, tbs, out, PhaseTimer{a.phase_cycles, 0});
+        const int32_t n_nodes = poa_uniform(process_window(s, a.p, wv, fill, tbs, out, PhaseTimer{a.phase_cycles, 0}));
+        if (a.out_msa) { /* B200POA_OUTPUT_MSA */
+            MsaOut mo;
+            mo.arena = a.out_msa;
+            mo.cursor = a.msa_cursor;
+            mo.cap = a.msa_cap;
+            mo.off = a.out_msa_off + w;
+            mo.cols = a.out_msa_cols + w;
+            mo.status = a.out_msa_status + w;
+            window_msa(s, a.p, n_nodes, poa_uniform(a.out_status[w]), wv, mo);
+        }
     }
 }
 
@@ -212,6 +236,23 @@ struct b200poa_batch {
     int32_t* d_out_off = nullptr;
     int32_t* d_trim = nullptr;
     unsigned long long* d_phase = nullptr; /* B200POA_PHASE_TIMERS diagnostics */
+    /* multiple sequence alignment (output mask has B200POA_OUTPUT_MSA) */
+    uint16_t* d_path = nullptr;            /* [arena_cap] node of every base */
+    uint8_t* d_msa = nullptr;              /* [msa_cap] compact rows */
+    unsigned long long* d_msa_cursor = nullptr;
+    long long* d_msa_off = nullptr;
+    int32_t* d_msa_cols = nullptr;
+    int32_t* d_msa_status = nullptr;
+    uint8_t* h_msa = nullptr;              /* pinned, grown on demand to the bytes a launch used */
+    size_t h_msa_bytes = 0;
+    unsigned long long* h_msa_cursor = nullptr;
+    long long* h_msa_off = nullptr;
+    int32_t* h_msa_cols = nullptr;
+    int32_t* h_msa_status = nullptr;
+    int32_t* h_msa_rows = nullptr;         /* sequences staged per window = rows of its MSA */
+    size_t msa_cap = 0;
+    size_t msa_bound = 0;                  /* worst-case MSA bytes of the windows staged so far */
+    bool msa_fetched = false;
     /* fill state */
     int32_t poa_count = 0;
     int64_t seq_count = 0;
@@ -308,6 +349,18 @@ static void free_batch(b200poa_batch* b) {
     cudaFree(b->d_out_off);
     cudaFree(b->d_trim);
     cudaFree(b->d_phase);
+    cudaFree(b->d_path);
+    cudaFree(b->d_msa);
+    cudaFree(b->d_msa_cursor);
+    cudaFree(b->d_msa_off);
+    cudaFree(b->d_msa_cols);
+    cudaFree(b->d_msa_status);
+    cudaFreeHost(b->h_msa);
+    cudaFreeHost(b->h_msa_cursor);
+    cudaFreeHost(b->h_msa_off);
+    cudaFreeHost(b->h_msa_cols);
+    cudaFreeHost(b->h_msa_status);
+    cudaFreeHost(b->h_msa_rows);
     delete b;
 }
 
@@ -343,6 +396,14 @@ static int32_t stage_window(b200poa_batch* b, int32_t n, Get get, int32_t* per_s
             bytes += q.len;
             ++n_ok;
         }
+    }
+    /* MSA output: n rows of at most min(max_consensus_size, sum of lengths) columns (every base adds at most one node;
+     * longer alignments fail with exceeded_maximum_sequence_size, cudapoa_generate_msa.cuh:203-208): the batch is
+     * "full" when the worst case of its windows would not fit the MSA arena (cudapoa_batch.cuh:122-125's back-pressure) */
+    size_t msa_need = 0;
+    if (b->output_mask & B200POA_OUTPUT_MSA) {
+        msa_need = ((size_t)n_ok * (size_t)std::min<int64_t>(bytes, b->cfg.max_consensus_size) + 15) & ~(size_t)15;
+        if (b->msa_bound + msa_need > b->msa_cap) return B200POA_EXCEEDED_MAXIMUM_POAS;
     }
     if (DIRECT) { /* the device arena mirrors the contiguous host range of the windows staged so far */
         const int64_t lo = b->poa_count == 0 ? win_lo : b->ext_lo;
@@ -426,6 +487,8 @@ static int32_t stage_window(b200poa_batch* b, int32_t n, Get get, int32_t* per_s
     if (backbone_rejected) flag = B200POA_EXCEEDED_MAXIMUM_SEQUENCE_SIZE; /* the kernel skips the window and reports why */
     b->h_win_flags[b->poa_count] = flag;
     b->h_win_trim_nseq[b->poa_count] = b->trim_counts_staged ? added : n; /* window.cpp:121 counts every sequence */
+    if (b->h_msa_rows) b->h_msa_rows[b->poa_count] = added;
+    b->msa_bound += msa_need;
     b->poa_count += 1;
     b->h_win_seq_off[b->poa_count] = (int32_t)b->seq_count;
     b->cost.push_back(cost);
@@ -463,6 +526,20 @@ static int32_t alloc_batch_memory(b200poa_batch* b) {
         CU_TRY(cudaMemset(b->d_phase, 0, PH_COUNT * sizeof(unsigned long long)));
     }
     b->device_bytes = (size_t)b->n_slots * b->slot_bytes + 2 * AC + (MS + 1) * 8 + MP * (16 + 3 * (size_t)p.max_cons);
+    if (b->output_mask & B200POA_OUTPUT_MSA) {
+        CU_TRY(cudaMalloc(&b->d_path, AC * sizeof(uint16_t)));
+        CU_TRY(cudaMalloc(&b->d_msa, b->msa_cap));
+        CU_TRY(cudaMalloc(&b->d_msa_cursor, sizeof(unsigned long long)));
+        CU_TRY(cudaMalloc(&b->d_msa_off, MP * sizeof(long long)));
+        CU_TRY(cudaMalloc(&b->d_msa_cols, MP * sizeof(int32_t)));
+        CU_TRY(cudaMalloc(&b->d_msa_status, MP * sizeof(int32_t)));
+        CU_TRY(cudaHostAlloc(&b->h_msa_cursor, sizeof(unsigned long long), cudaHostAllocDefault));
+        CU_TRY(cudaHostAlloc(&b->h_msa_off, MP * sizeof(long long), cudaHostAllocDefault));
+        CU_TRY(cudaHostAlloc(&b->h_msa_cols, MP * sizeof(int32_t), cudaHostAllocDefault));
+        CU_TRY(cudaHostAlloc(&b->h_msa_status, MP * sizeof(int32_t), cudaHostAllocDefault));
+        CU_TRY(cudaHostAlloc(&b->h_msa_rows, MP * sizeof(int32_t), cudaHostAllocDefault));
+        b->device_bytes += AC * sizeof(uint16_t) + b->msa_cap + MP * 16;
+    }
     CU_TRY(cudaHostAlloc(&b->h_bases, AC, cudaHostAllocDefault));
     CU_TRY(cudaHostAlloc(&b->h_weights, AC, cudaHostAllocDefault));
     CU_TRY(cudaHostAlloc(&b->h_seq_off, (MS + 1) * sizeof(int64_t), cudaHostAllocDefault));
@@ -678,6 +755,20 @@ int32_t b200poa_batch_create(int32_t device_id, void* stream, size_t max_gpu_mem
     }
     b->n_slots = (int32_t)std::min(want_slots, slots_by_mem);
     size_t rest = max_gpu_mem - (size_t)b->n_slots * b->slot_bytes;
+    const bool want_msa = (output_mask & B200POA_OUTPUT_MSA) != 0;
+    if (want_msa) { /* the MSA arena: a quarter of what the slots leave, at most 4 GiB (B200POA_MSA_ARENA_MB overrides);
+                       never less than one worst-case window */
+        size_t cap_msa = std::min<size_t>(rest / 4, (size_t)4 << 30);
+        if (const char* env = std::getenv("B200POA_MSA_ARENA_MB")) cap_msa = (size_t)std::atoll(env) << 20;
+        const size_t one = ((size_t)cfg->max_sequences_per_poa * (size_t)cfg->max_consensus_size + 15) & ~(size_t)15;
+        if (cap_msa < one) cap_msa = one;
+        if (cap_msa >= rest) {
+            delete b;
+            return B200POA_INVALID_ARGUMENT;
+        }
+        b->msa_cap = cap_msa;
+        rest -= cap_msa;
+    }
     /* staging is pinned host memory too: keep it bounded (B200POA_MAX_STAGING_MB, default 3 GiB) */
     size_t cap = 3ull << 30;
     if (const char* env = std::getenv("B200POA_MAX_STAGING_MB")) cap = (size_t)std::atoll(env) << 20;
@@ -688,7 +779,7 @@ int32_t b200poa_batch_create(int32_t device_id, void* stream, size_t max_gpu_mem
     if (max_poas < 1) max_poas = 1;
     if (max_poas > (1 << 22)) max_poas = 1 << 22;
     b->max_poas = (int32_t)max_poas;
-    size_t arena = (rest - (size_t)max_poas * out_per_win) / 2;
+    size_t arena = (rest - (size_t)max_poas * out_per_win) / (want_msa ? 4 : 2); /* bases + weights (+ the 16-bit path arena) */
     arena = arena / 10 * 9; /* 10% of the arena budget goes to the sequence offset table */
     if (arena < (size_t)p.max_len * 4) arena = (size_t)p.max_len * 4;
     b->arena_cap = (int64_t)arena;
@@ -801,6 +892,7 @@ int32_t b200poa_batch_launch(b200poa_batch* b) {
     if (!b->uploaded) return B200POA_INVALID_ARGUMENT;
     DeviceGuard g(b->device);
     CU_TRY(cudaMemsetAsync(b->d_cursor, 0, 2 * sizeof(int32_t), b->stream));
+    if (b->d_msa_cursor) CU_TRY(cudaMemsetAsync(b->d_msa_cursor, 0, sizeof(unsigned long long), b->stream));
     KernelArgs a;
     a.p = b->p;
     a.slab = b->d_slab;
@@ -824,6 +916,14 @@ int32_t b200poa_batch_launch(b200poa_batch* b) {
     a.out_status = b->d_status;
     a.out_off = b->d_out_off;
     a.out_trim = b->d_trim;
+    a.path = b->d_path;
+    a.out_msa = b->d_msa;
+    a.msa_cursor = b->d_msa_cursor;
+    a.msa_cap = (unsigned long long)b->msa_cap;
+    a.out_msa_off = b->d_msa_off;
+    a.out_msa_cols = b->d_msa_cols;
+    a.out_msa_status = b->d_msa_status;
+    a.p.skip_consensus = (b->output_mask & B200POA_OUTPUT_CONSENSUS) ? 0 : 1;
     /* shared memory geometry follows the longest read actually staged */
     const SmemGeometry sg = smem_geometry(b->p, b->max_len_staged);
     b->prof_stride = sg.prof_stride;
@@ -853,6 +953,7 @@ int32_t b200poa_batch_launch(b200poa_batch* b) {
     CU_TRY(cudaGetLastError());
     b->launches += 1;
     b->results_fetched = false;
+    b->msa_fetched = false;
     return B200POA_SUCCESS;
 }
 
@@ -870,6 +971,12 @@ int32_t b200poa_batch_download(b200poa_batch* b) {
     CU_TRY(cudaMemcpyAsync(b->h_out_off, b->d_out_off, W * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
     CU_TRY(cudaMemcpyAsync(b->h_trim, b->d_trim, W * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
     CU_TRY(cudaMemcpyAsync(b->h_cursor, b->d_cursor, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
+    if (b->d_msa) { /* the MSA tables; the rows follow in b200poa_batch_get_msa once the fill level is known */
+        CU_TRY(cudaMemcpyAsync(b->h_msa_off, b->d_msa_off, W * sizeof(long long), cudaMemcpyDeviceToHost, b->stream));
+        CU_TRY(cudaMemcpyAsync(b->h_msa_cols, b->d_msa_cols, W * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
+        CU_TRY(cudaMemcpyAsync(b->h_msa_status, b->d_msa_status, W * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
+        CU_TRY(cudaMemcpyAsync(b->h_msa_cursor, b->d_msa_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, b->stream));
+    }
     return B200POA_SUCCESS;
 }
 
@@ -909,6 +1016,38 @@ int32_t b200poa_batch_get_consensus(b200poa_batch* b, const uint8_t** cons, cons
     return B200POA_SUCCESS;
 }
 
+int32_t b200poa_batch_get_msa(b200poa_batch* b, const uint8_t** msa, const int64_t** offsets, const int32_t** n_rows,
+                              const int32_t** n_cols, const int32_t** status) {
+    if (!b) return B200POA_INVALID_ARGUMENT;
+    if (!(b->output_mask & B200POA_OUTPUT_MSA)) return B200POA_OUTPUT_TYPE_UNAVAILABLE; /* cudapoa_batch.cuh:263-267 */
+    DeviceGuard g(b->device);
+    CU_TRY(cudaStreamSynchronize(b->stream));
+    if (b->poa_count > 0 && !b->msa_fetched) { /* exactly the bytes the launch used (the reference copies
+                                                  max_poas x max_sequences_per_poa x max_consensus_size, :271-275) */
+        const size_t used = (size_t)*b->h_msa_cursor;
+        if (used > b->h_msa_bytes) {
+            cudaFreeHost(b->h_msa);
+            b->h_msa = nullptr;
+            b->h_msa_bytes = 0;
+            CU_TRY(cudaHostAlloc(&b->h_msa, used + used / 4, cudaHostAllocDefault));
+            b->h_msa_bytes = used + used / 4;
+        }
+        if (used > 0) {
+            CU_TRY(cudaMemcpyAsync(b->h_msa, b->d_msa, used, cudaMemcpyDeviceToHost, b->stream));
+            CU_TRY(cudaStreamSynchronize(b->stream));
+        }
+        b->d2h_bytes += (int64_t)used + (int64_t)b->poa_count * 16 + 8;
+        b->msa_fetched = true;
+    }
+    static_assert(sizeof(long long) == sizeof(int64_t), "offset table type");
+    if (msa) *msa = b->h_msa;
+    if (offsets) *offsets = reinterpret_cast<const int64_t*>(b->h_msa_off);
+    if (n_rows) *n_rows = b->h_msa_rows;
+    if (n_cols) *n_cols = b->h_msa_cols;
+    if (status) *status = b->h_msa_status;
+    return B200POA_SUCCESS;
+}
+
 int32_t b200poa_batch_set_option(b200poa_batch* b, int32_t option, int64_t value) {
     if (!b) return B200POA_INVALID_ARGUMENT;
     switch (option) {
@@ -934,6 +1073,8 @@ int32_t b200poa_batch_reset(b200poa_batch* b) {
     b->cost.clear();
     b->uploaded = false;
     b->results_fetched = false;
+    b->msa_fetched = false;
+    b->msa_bound = 0;
     b->max_len_staged = 0;
     return B200POA_SUCCESS;
 }

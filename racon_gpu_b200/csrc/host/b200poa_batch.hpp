@@ -108,6 +108,22 @@ public:
         }
         return success;
     }
+    /* batch.hpp:141-142 / cudapoa_batch.cuh:260-313: one vector of rows per window (empty where the window failed) */
+    StatusType get_msa(std::vector<std::vector<std::string>>& msa, std::vector<StatusType>& output_status) {
+        const uint8_t* m; const int64_t* off; const int32_t* rows; const int32_t* cols; const int32_t* s;
+        const int32_t r = b200poa_batch_get_msa(b_, &m, &off, &rows, &cols, &s);
+        if (r != B200POA_SUCCESS) return to_status(r);
+        const int32_t n = get_total_poas();
+        for (int32_t i = 0; i < n; ++i) {
+            msa.emplace_back(std::vector<std::string>());
+            output_status.emplace_back(to_status(s[i]));
+            if (s[i] != B200POA_SUCCESS) continue;
+            for (int32_t k = 0; k < rows[i]; ++k)
+                msa.back().emplace_back(reinterpret_cast<const char*>(m + off[i] + static_cast<int64_t>(k) * cols[i]),
+                                        static_cast<size_t>(cols[i]));
+        }
+        return success;
+    }
     int32_t batch_id() const { return b200poa_batch_id(b_); }
     void reset() { b200poa_batch_reset(b_); }
     b200poa_batch* raw() { return b_; }

@@ -95,6 +95,7 @@ struct Params {
                                int16 (score_range_ok) is filled and traced with 32-bit cells -- the switch spoa makes,
                                simd_alignment_engine.cpp:668-673; cudapoa instantiates int32 per batch, batch.cu:114-138 */
     int32_t force_cells32;  /* tests: every read takes the 32-bit path */
+    int32_t skip_consensus; /* the output mask has no OutputType::consensus (MSA only, cudapoa_kernels.cuh:198-216) */
     int32_t adaptive;       /* band_width is only the FIRST try of a read: a traceback that comes close to the band's
                                edge re-aligns the read with twice the width (cudapoa's retry protocol,
                                cudapoa_kernels.cuh:257-303, cudapoa_nw_adaptive_banded.cuh:265-281, 462-480) */
@@ -234,6 +235,10 @@ struct WindowView {
                                 a FASTA target => 0, polisher.cpp:171,392-395) -- such sequences ship no weight bytes */
     const int32_t* seq_begin; /* [n_seqs] layer span on the backbone, or -1 when the layer spans the window */
     const int32_t* seq_end;   /* (window.cpp:87,92-93 decides which; the host applies that rule)           */
+    uint16_t* path;           /* MSA output only (else nullptr): arena parallel to `bases` (same seq_off) receiving the node
+                                 every base of every sequence was assigned to -- the sequence's path through the graph,
+                                 which spoa re-derives from edge labels (Node::successor, graph.cpp:31-43) and cudapoa
+                                 from per-edge sequence lists (outgoing_edges_coverage, cudapoa_add_alignment.cuh:245-262) */
 };
 
 /* Where a window's result goes: consensus and coverage are appended to compact arenas (one bump allocation per
@@ -251,11 +256,31 @@ struct WindowOut {
     int32_t trim_nseq; /* sequences the trim threshold counts (window.cpp:121: sequences_.size()) */
 };
 
+/* OutputType::msa: a window's rows are bump-allocated in a compact arena like its consensus (n_seqs rows of `cols`
+ * bytes).  Kept apart from WindowOut: process_window() never sees it, the caller runs generate_msa() afterwards. */
+struct MsaOut {
+    uint8_t* arena;
+    unsigned long long* cursor; /* bytes used so far */
+    unsigned long long cap;     /* arena capacity (the host admits windows by their worst case, this is the backstop) */
+    long long* off;             /* this window's slots in the per-window tables: where its rows start ... */
+    int32_t* cols;              /* ... their length ... */
+    int32_t* status;            /* ... and the status of its MSA */
+};
+
 POA_FN uint32_t poa_bump(uint32_t* cursor, uint32_t n) {
 #if POA_DEVICE
     return atomicAdd(cursor, n);
 #else
     const uint32_t o = *cursor;
+    *cursor += n;
+    return o;
+#endif
+}
+POA_FN unsigned long long poa_bump64(unsigned long long* cursor, unsigned long long n) {
+#if POA_DEVICE
+    return atomicAdd(cursor, n);
+#else
+    const unsigned long long o = *cursor;
     *cursor += n;
     return o;
 #endif
@@ -2480,6 +2505,133 @@ POA_FN_NOINLINE void generate_consensus(const Slot& s_ref, const Params p_ref, W
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Multiple sequence alignment  (spoa: graph.cpp:373-427 generate_multiple_sequence_alignment; cudapoa:
+ * cudapoa_generate_msa.cuh:35-233 getNodeIDToMSAPosDevice / generateMSADevice / generateMSAKernel, one thread per
+ * sequence walking labelled out-edges).  Here a sequence's path is simply the node each of its bases was assigned to
+ * (add_alignment's asg[], kept in WindowView::path), so a row is one parallel scatter.
+ * ---------------------------------------------------------------------------------------- */
+/* after add_alignment: asg[pos] is the node of read position pos (identity: the backbone chain, node k = base k) */
+POA_FN_NOINLINE void record_path(const int32_t* asg, uint16_t* path, int32_t len, int32_t identity) {
+    len = poa_uniform(len);
+    identity = poa_uniform(identity);
+    for (int32_t base = 0; base < len; base += 32) {
+        POA_LANES(l) {
+            const int32_t pos = base + l;
+            if (pos < len) path[pos] = (uint16_t)(identity ? pos : asg[pos]);
+        }
+    }
+    POA_SYNC();
+}
+
+POA_FN void poa_store16_dash(uint8_t* dst) { /* 16 '-' at a 16-byte aligned address */
+#if POA_DEVICE
+    *reinterpret_cast<uint4*>(dst) = make_uint4(0x2D2D2D2Du, 0x2D2D2D2Du, 0x2D2D2D2Du, 0x2D2D2D2Du);
+#else
+    for (int k = 0; k < 16; ++k) dst[k] = (uint8_t)'-';
+#endif
+}
+
+POA_FN_NOINLINE void generate_msa(const Slot& s_ref, const Params p_ref, int32_t n_nodes, const WindowView& wv_ref,
+                                  const MsaOut& out_ref) {
+    const Slot s = s_ref;
+    const Params p = p_ref;
+    const WindowView wv = wv_ref;
+    const MsaOut out = out_ref;
+    const int32_t N = poa_uniform(n_nodes);
+    const int32_t n_seqs = poa_uniform(wv.n_seqs);
+    /* 1. column of every node (graph.cpp:373-389): a node and its aligned nodes share a column, columns follow the
+     *    topological order, and the sort emits a clique as one run of ranks (graph.cpp:334-341) -- so rank r opens a
+     *    column iff no clique mate ranks before it, and column(r) = (#openers among ranks <= r) - 1.  c_score[] is free. */
+    int32_t run = 0;
+    for (int32_t base = 0; base < N; base += 32) {
+        PerLane<int> opens, node;
+        POA_LANES(l) {
+            const int32_t r = base + l;
+            opens[l] = 0;
+            node[l] = 0;
+            if (r < N) {
+                const int32_t v = s.node_at[r];
+                node[l] = v;
+                int32_t first = r;
+                const int32_t na = s.aln_cnt[v];
+                for (int32_t q = 0; q < na; ++q) {
+                    const int32_t rr = s.rank_of[s.aln[v * KA + q]];
+                    if (rr < first) first = rr;
+                }
+                opens[l] = first == r ? 1 : 0;
+            }
+        }
+        PerLane<int> before = opens;
+        const int32_t tot = warp_exscan(before);
+        POA_LANES(l) {
+            if (base + l < N) s.c_score[node[l]] = run + before[l] + opens[l] - 1;
+        }
+        run += tot;
+    }
+    POA_SYNC();
+    const int32_t cols = run;
+    if (cols >= p.max_cons) { /* cudapoa_generate_msa.cuh:203-208: the MSA does not fit max_consensus_size */
+        POA_LANE0 {
+            *out.status = ST_EXCEEDED_MAX_SEQ_SIZE;
+            *out.cols = 0;
+            *out.off = 0;
+        }
+        POA_SYNC();
+        return;
+    }
+    /* 2. one bump allocation for the window's rows (16-byte granules) */
+    const unsigned long long bytes = ((unsigned long long)n_seqs * (unsigned long long)cols + 15ull) & ~15ull;
+    int32_t lo = 0, hi = 0;
+    POA_LANE0 {
+        const unsigned long long o = poa_bump64(out.cursor, bytes);
+        lo = (int32_t)(o & 0xFFFFFFFFull);
+        hi = (int32_t)(o >> 32);
+    }
+    const unsigned long long off = ((unsigned long long)(uint32_t)warp_bcast0(hi) << 32) | (unsigned long long)(uint32_t)warp_bcast0(lo);
+    if (poa_uniform_pred(off + bytes > out.cap)) { /* cap arrives through a reference: laundered (poa_simt.cuh) */
+        POA_LANE0 {
+            *out.status = ST_GENERIC_ERROR;
+            *out.cols = 0;
+            *out.off = 0;
+        }
+        POA_SYNC();
+        return;
+    }
+    uint8_t* rows = out.arena + off;
+    /* 3. gaps everywhere (graph.cpp:401), then every base into its node's column (:404-410) */
+    for (unsigned long long o = 0; o < bytes; o += 32 * 16) {
+        POA_LANES(l) {
+            const unsigned long long q = o + (unsigned long long)l * 16ull;
+            if (q < bytes) poa_store16_dash(rows + q);
+        }
+    }
+    POA_SYNC();
+    POA_FENCE();
+    for (int32_t r = 0; r < n_seqs; ++r) {
+        const int64_t so = wv.seq_off[r];
+        const int32_t len = poa_uniform(wv.seq_len[r]);
+        uint8_t* row = rows + (size_t)r * (size_t)cols;
+        for (int32_t base = 0; base < len; base += 64) {
+            POA_LANES(l) {
+                const int32_t p0 = base + l, p1 = base + 32 + l;
+                const int32_t v0 = p0 < len ? (int32_t)wv.path[so + p0] : 0, v1 = p1 < len ? (int32_t)wv.path[so + p1] : 0;
+                const uint8_t b0 = p0 < len ? wv.bases[so + p0] : (uint8_t)0, b1 = p1 < len ? wv.bases[so + p1] : (uint8_t)0;
+                const int32_t c0 = s.c_score[v0], c1 = s.c_score[v1];
+                if (p0 < len) row[c0] = b0;
+                if (p1 < len) row[c1] = b1;
+            }
+        }
+    }
+    POA_SYNC();
+    POA_LANE0 {
+        *out.status = ST_SUCCESS;
+        *out.cols = cols;
+        *out.off = (long long)off;
+    }
+    POA_SYNC();
+}
+
+/* ------------------------------------------------------------------------------------------
  * int16 safety: every real cell of the skewed matrix must stay far from NEG and from +32767.
  * In the skewed domain S = H - j*gap a horizontal step costs 0, a diagonal step costs (s - gap), a vertical step
  * costs gap, and the value of a real cell is the score of SOME path from (0,0): it visits at most `n_columns`
@@ -2554,8 +2706,8 @@ __device__ __noinline__ void prefetch_graph(const Slot& s, int32_t N, int32_t E)
 #endif
 
 template <class Fill>
-POA_FN void process_window(const Slot& s, const Params& p, const WindowView& wv, Fill& fill, const TbScratch& tbs,
-                           const WindowOut& out, PhaseTimer tm = PhaseTimer{nullptr, 0}) {
+POA_FN int32_t process_window(const Slot& s, const Params& p, const WindowView& wv, Fill& fill, const TbScratch& tbs,
+                              const WindowOut& out, PhaseTimer tm = PhaseTimer{nullptr, 0}) {
     WinState st;
     st.n_nodes = 0;
     st.n_edges = 0;
@@ -2568,6 +2720,7 @@ POA_FN void process_window(const Slot& s, const Params& p, const WindowView& wv,
         const int64_t wo = wv.w_off[0];
         init_backbone(s, p, st, wv.bases + wv.seq_off[0], wo >= 0 ? wv.weights + wo : nullptr, wo >= 0 ? 0 : (int32_t)(-1 - wo), len0);
         winstate_uniform(st);
+        if (wv.path && st.status == ST_SUCCESS) record_path(s.asg, wv.path + wv.seq_off[0], len0, 1);
     }
     for (int32_t r = 1; r < wv.n_seqs && st.status == ST_SUCCESS; ++r) {
         const uint8_t* read = wv.bases + wv.seq_off[r];
@@ -2638,19 +2791,20 @@ POA_FN void process_window(const Slot& s, const Params& p, const WindowView& wv,
         POA_FENCE();
         tm.lap(PH_ADD);
         if (st.status != ST_SUCCESS) break;
+        if (wv.path) record_path(s.asg, wv.path + wv.seq_off[r], len, 0);
         if (p.serial_topsort) topsort_serial(s, p, st);
         else topsort_roots(s, p, st);
         winstate_uniform(st);
         POA_FENCE();
         tm.lap(PH_TOPSORT);
     }
-    if (st.status == ST_SUCCESS) {
+    if (st.status == ST_SUCCESS && !p.skip_consensus) {
         generate_consensus(s, p, st, out);
         winstate_uniform(st);
     }
     tm.lap(PH_CONSENSUS);
     POA_LANE0 {
-        if (st.status != ST_SUCCESS) {
+        if (st.status != ST_SUCCESS || p.skip_consensus) {
             *out.len = 0;
             *out.off = 0;
             *out.trim = (int32_t)0xFFFF0000u; /* first 0, last -1 */
@@ -2658,6 +2812,22 @@ POA_FN void process_window(const Slot& s, const Params& p, const WindowView& wv,
         *out.status = st.status;
     }
     POA_SYNC();
+    return st.status == ST_SUCCESS ? st.n_nodes : -1; /* the graph stays in the slot: generate_msa() may follow */
+}
+
+/* The MSA of the window process_window() just finished (n_nodes = its return value, status = what it reported);
+ * runs after the consensus because the column table takes over the consensus' score array. */
+POA_FN void window_msa(const Slot& s, const Params& p, int32_t n_nodes, int32_t status, const WindowView& wv, const MsaOut& mo) {
+    if (n_nodes >= 0) {
+        generate_msa(s, p, n_nodes, wv, mo);
+    } else {
+        POA_LANE0 {
+            *mo.status = status;
+            *mo.cols = 0;
+            *mo.off = 0;
+        }
+        POA_SYNC();
+    }
 }
 
 } // namespace b200poa

@@ -82,7 +82,9 @@ void emu_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int
                         int32_t max_nodes, int32_t max_edges, int32_t max_len, int32_t band_width,
                         int32_t serial_topsort, int32_t n_threads, uint8_t* cons_out,
                         uint16_t* cov_out, int32_t stride_out, int32_t* cons_len, int32_t* status,
-                        int32_t* rank_out, int32_t* n_nodes_out, int64_t* cells_out, int32_t* trim_out) {
+                        int32_t* rank_out, int32_t* n_nodes_out, int64_t* cells_out, int32_t* trim_out,
+                        /* MSA (all nullable): compact arena of msa_cap bytes + per-window offset / columns / status */
+                        uint8_t* msa_out, int64_t msa_cap, int64_t* msa_off, int32_t* msa_cols, int32_t* msa_status) {
     Params p;
     p.max_nodes = max_nodes;
     p.max_edges = poa_edge_capacity(max_nodes); /* the engine derives the edge pool from the node capacity */
@@ -100,6 +102,7 @@ void emu_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int
     p.force_cells32 = (serial_topsort & 2) ? 1 : 0; /* bit 1 of the flag: every read through the 32-bit path */
     p.wide_cells = (p.force_cells32 || !score_range_ok(p, p.max_nodes, p.max_len)) ? 1 : 0;
     p.serial_topsort = serial_topsort & 1;
+    p.skip_consensus = 0;
     p.ring_rows = 8;
     p.ring_stride = p.stride;
     Slot probe;
@@ -108,6 +111,8 @@ void emu_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int
 
     std::atomic<int64_t> cursor{0};
     std::atomic<int64_t> total_cells{0};
+    unsigned long long msa_cursor = 0;
+    if (msa_out) n_threads = 1; /* the host flavour of the bump allocator is not atomic */
     auto worker = [&]() {
         std::vector<uint8_t> slab(slot_bytes + 512);
         Slot s;
@@ -158,6 +163,11 @@ void emu_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int
             if (too_long) {
                 cons_len[w] = 0;
                 status[w] = ST_EXCEEDED_MAX_SEQ_SIZE;
+                if (msa_out) {
+                    msa_off[w] = 0;
+                    msa_cols[w] = 0;
+                    msa_status[w] = ST_EXCEEDED_MAX_SEQ_SIZE;
+                }
                 continue;
             }
             WindowView wv;
@@ -169,6 +179,8 @@ void emu_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int
             wv.w_off = wwoff.data();
             wv.seq_begin = wbeg.data();
             wv.seq_end = wend.data();
+            std::vector<uint16_t> wpath(msa_out ? wbases.size() + 1 : 0);
+            wv.path = msa_out ? wpath.data() : nullptr;
             /* process_window writes its node count nowhere; recover it from the slot afterwards */
             uint32_t cursor = 0;
             int32_t off = 0, trim = 0;
@@ -181,8 +193,25 @@ void emu_polish_windows(int64_t n_windows, const int64_t* win_seq_off, const int
             out.off = &off;
             out.trim = &trim;
             out.trim_nseq = n;
-            process_window(s, p, wv, fill, tbs, out);
+            long long moff = 0;
+            int32_t mcols = 0, mst = 0;
+            const int32_t n_final = process_window(s, p, wv, fill, tbs, out);
+            if (msa_out) {
+                MsaOut mo;
+                mo.arena = msa_out;
+                mo.cursor = &msa_cursor;
+                mo.cap = (unsigned long long)msa_cap;
+                mo.off = &moff;
+                mo.cols = &mcols;
+                mo.status = &mst;
+                window_msa(s, p, n_final, status[w], wv, mo);
+            }
             if (trim_out) trim_out[w] = trim;
+            if (msa_out) {
+                msa_off[w] = moff;
+                msa_cols[w] = mcols;
+                msa_status[w] = mst;
+            }
             if (rank_out || n_nodes_out) {
                 /* n_nodes = 1 + max rank_of over nodes is not stored; count nodes via root != unset:
                  * simplest is to re-derive from node_at being a permutation of [0, N). */

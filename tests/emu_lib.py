@@ -19,7 +19,7 @@ class Emu:
         self.lib = C.CDLL(os.path.join(HERE, "emu", "libpoa_emu.so"))
 
     def polish(self, b, order, m, x, g, max_nodes=4096, max_edges=24576, max_len=1023, band=0,
-               serial_topsort=False, threads=8, stride=4096):
+               serial_topsort=False, threads=8, stride=4096, msa_cap=0):
         """Untrimmed consensus, coverage, status and DP cell count of the emulated engine."""
         W = b.n_windows
         cons = np.zeros((W, stride), dtype=np.uint8)
@@ -35,6 +35,21 @@ class Emu:
             C.c_int32(max_nodes), C.c_int32(max_edges), C.c_int32(max_len), C.c_int32(band),
             C.c_int32(int(serial_topsort)), C.c_int32(threads), _p(cons, C.c_uint8), _p(cov, C.c_uint16),
             C.c_int32(stride), _p(clen, C.c_int32), _p(st, C.c_int32), None, None, C.byref(cells),
-            _p(self.last_trim, C.c_int32))
+            _p(self.last_trim, C.c_int32), *self._msa_args(W, msa_cap))
+        self.last_msa = None
+        if msa_cap:  # per window: list of rows (processing order), or the status when the MSA failed
+            arena, off, cols, mst = self._msa
+            nseq = np.diff(b.win_seq_off)
+            self.last_msa = [[arena[off[w] + k * cols[w]:off[w] + (k + 1) * cols[w]].tobytes() for k in range(int(nseq[w]))]
+                             if mst[w] == 0 else int(mst[w]) for w in range(W)]
         return ([cons[w, :clen[w]].tobytes() for w in range(W)], [cov[w, :clen[w]].copy() for w in range(W)],
                 st, cells.value)
+
+    def _msa_args(self, W, msa_cap):
+        if not msa_cap:
+            self._msa = None
+            return (None, C.c_int64(0), None, None, None)
+        self._msa = (np.zeros(msa_cap, dtype=np.uint8), np.zeros(W, dtype=np.int64), np.zeros(W, dtype=np.int32),
+                     np.zeros(W, dtype=np.int32))
+        a, o, c, s = self._msa
+        return (_p(a, C.c_uint8), C.c_int64(msa_cap), _p(o, C.c_int64), _p(c, C.c_int32), _p(s, C.c_int32))
