@@ -19,7 +19,7 @@ scaling).  One step = one pass of the hot path over the whole batch of windows.
              box's host cores over a bounded sample of the same windows (rank 0, N=1).
   extra      (N=1 only, outside the headline timing) the same measurements for BASELINE configs[2]
              (A_full: full band, the bit-exact mode) and configs[4]'s shape (B_banded: 1024 bp x 64 reads, 12 %,
-             band 256, max_sequence_size 1279).
+             band 256, max_sequence_size 1279), and the headline workload with the MSA output switched on.
 
 `--impl reference` times that CPU path as the job itself (all usable host threads, bounded sample per step).
 """
@@ -296,6 +296,46 @@ def measure(name, args, rank, world, local_rank, device, steps, warmup, nwin=Non
             "launches": steps + warmup + e2e_launches, "timed_launches": steps + e2e_launches}
 
 
+def measure_msa(args, local_rank, device, steps=3, warmup=3):
+    """extra: the headline workload with OutputType::msa added to the output mask (Batch::get_msa): kernel rate with the
+    inputs resident, and the bytes / time of the compact MSA download."""
+    import torch
+    from racon_gpu_b200 import api
+    from racon_gpu_b200.windows import synth_windows
+    nwin, L, D, err, banded, max_seq, _ = WORKLOADS["A_banded"]
+    batch = synth_windows(nwin, L, D, err, seed=args.seed)
+    free_b, _ = torch.cuda.mem_get_info()
+    stream = torch.cuda.Stream(device=device)
+    pb = api.PoaBatch(device=local_rank, stream=stream.cuda_stream, max_gpu_mem=int(min(0.6 * free_b, 64 << 30)),
+                      banded=banded, gap=G, mismatch=X, match=M, max_sequence_size=max_seq,
+                      output_mask=api.OUTPUT_CONSENSUS | api.OUTPUT_MSA)
+    n_added, _ = pb.add_windows(batch)
+    pb.upload()
+    with torch.cuda.stream(stream):
+        for _ in range(warmup):
+            pb.launch()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(steps):
+            pb.launch()
+        b.record(stream)
+        torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    pb.download()
+    t0 = time.perf_counter()
+    msa, status = pb.get_msa()
+    dt = time.perf_counter() - t0
+    ok = [m for m in msa if m is not None]
+    msa_bytes = sum(len(m) * len(m[0]) for m in ok)
+    pb.close()
+    return {"workload": workload_label("A_banded", n_added) + " + OutputType::msa", "steps": steps, "warmup": warmup,
+            "value": n_added / (ms / 1e3), "unit": "windows/s", "ms_per_step": ms, "windows": n_added,
+            "failed_windows": int((status != 0).sum()), "msa_bytes_per_window": msa_bytes / max(len(ok), 1),
+            "msa_d2h_and_unpack_s": dt,
+            "note": "kernel with consensus + MSA, inputs resident; the MSA download moves exactly the bytes produced"}
+
+
 def roofline_block(name, m, steps):
     bytes_per_window, cells = algorithmic_bytes_per_window(m["batch"], m["banded"])
     peak, peak_src = measured_hbm_peak()
@@ -393,6 +433,7 @@ def main():
                 "ms_per_step": x["dev_ms"] / 3, "failed_windows": x["failures"],
                 "h2d_bytes_per_step": x["h2d"], "d2h_bytes_per_step": x["d2h"],
                 "resident_warps": x["info"]["n_slots"], "roofline": roofline_block(name, x, 3)}
+        extra["A_banded_msa"] = measure_msa(args, local_rank, device)
         result["extra"] = extra
     print(json.dumps(result))
     if world > 1:
