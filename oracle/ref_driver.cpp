@@ -4,6 +4,7 @@
  * Compiled by oracle/Makefile together with, by path and never copied,
  *   /root/reference/src/window.cpp
  *   /root/reference/vendor/spoa/src/{alignment_engine,graph,simd_alignment_engine,sisd_alignment_engine}.cpp
+ *   /root/reference/vendor/edlib/edlib/src/edlib.cpp
  * into oracle/_ref/libracon_ref.so.  It drives racon::Window exactly the way
  * racon::Polisher::polish does (src/polisher.cpp:181-185, 491-504): one spoa NW engine per
  * thread, prealloc(window_length, 5), one generate_consensus call per window.
@@ -14,12 +15,14 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
 #include <thread>
 #include <vector>
 
+#include "edlib.h"
 #include "spoa/spoa.hpp"
 #include "window.hpp"
 
@@ -190,6 +193,37 @@ int32_t ref_spoa_window_msa(int32_t n_seqs, const char* const* seqs, const int32
     if (static_cast<int64_t>(L * msa.size()) <= max_out)
         for (size_t i = 0; i < msa.size(); ++i) std::memcpy(out + i * L, msa[i].data(), L);
     return static_cast<int32_t>(msa.size());
+}
+
+/*
+ * The overlap alignment of racon's CPU path, verbatim: Overlap::align_overlaps (src/overlap.cpp:205-224) =
+ * edlibAlign(q, q_length, t, t_length, edlibNewAlignConfig(-1, EDLIB_MODE_NW, EDLIB_TASK_PATH, nullptr, 0)) followed by
+ * edlibAlignmentToCigar(..., EDLIB_CIGAR_STANDARD).  ops_out (nullable, capacity cap) receives edlib's edit operations
+ * (0 match, 1 insertion = a query base without partner, 2 deletion = a target base without partner, 3 mismatch),
+ * cigar_out (nullable, capacity cigar_cap incl. NUL) the CIGAR string racon stores.  Returns the number of operations,
+ * or -1 when edlib fails / a buffer is too small; *score receives the edit distance.
+ */
+int64_t ref_edlib_nw(const char* q, int32_t q_len, const char* t, int32_t t_len, uint8_t* ops_out, int64_t cap,
+                     char* cigar_out, int64_t cigar_cap, int32_t* score) {
+    EdlibAlignResult r = edlibAlign(q, q_len, t, t_len, edlibNewAlignConfig(-1, EDLIB_MODE_NW, EDLIB_TASK_PATH, nullptr, 0));
+    int64_t n = -1;
+    if (r.status == EDLIB_STATUS_OK) {
+        if (score) *score = r.editDistance;
+        n = r.alignmentLength;
+        if (ops_out) {
+            if (n <= cap) std::memcpy(ops_out, r.alignment, static_cast<size_t>(n));
+            else n = -1;
+        }
+        if (cigar_out && n >= 0) {
+            char* c = edlibAlignmentToCigar(r.alignment, r.alignmentLength, EDLIB_CIGAR_STANDARD);
+            const size_t L = std::strlen(c);
+            if (static_cast<int64_t>(L) + 1 <= cigar_cap) std::memcpy(cigar_out, c, L + 1);
+            else n = -1;
+            std::free(c);
+        }
+    }
+    edlibFreeAlignResult(r);
+    return n;
 }
 
 } // extern "C"

@@ -192,3 +192,39 @@ def cudapoa_fixture():
     off = np.concatenate([[0], np.cumsum(z["cons_len"])])
     cov = [z["cov"][off[i]:off[i + 1]] for i in range(len(cons))]
     return b, cons, cov
+
+
+def overlap_fixture():
+    """The 181 real overlap alignment inputs of the lambda-phage sample (tests/golden/make_overlap_golden.py).
+    Returns a list of dicts {q, t, score, n_ops, cigar_sha} (edlib's result as racon's CPU path obtains it)."""
+    z = np.load(os.path.join(GOLDEN, "lambda_overlaps.npz"))
+    ql, tl = z["q_len"], z["t_len"]
+    qs = _split(_unpack2(z["q_bases"], int(ql.sum())), ql)
+    ts = _split(_unpack2(z["t_bases"], int(tl.sum())), tl)
+    meta = [l.split() for l in z["cigar_sha"].tobytes().decode().strip().split("\n")]
+    return [{"q": qs[i], "t": ts[i], "score": int(z["score"][i]), "n_ops": int(meta[i][0]), "cigar_sha": meta[i][1]}
+            for i in range(len(qs))]
+
+
+def random_pairs(seed: int, shapes):
+    """(q, t) pairs: t random over ACGT, q a mutated copy (substitutions, insertions, deletions at rate e)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for n, e in shapes:
+        t = rng.choice(_ACGT, size=n)
+        keep = rng.random(n)
+        parts = []
+        for k in range(n):
+            x = keep[k]
+            if x < e / 3:
+                parts.append(_ACGT[rng.integers(4)])
+            elif x < 2 * e / 3:
+                continue
+            elif x < e:
+                parts.append(t[k])
+                parts.append(_ACGT[rng.integers(4)])
+            else:
+                parts.append(t[k])
+        q = np.asarray(parts, dtype=np.uint8).tobytes() if parts else b"A"
+        out.append((q, t.tobytes()))
+    return out

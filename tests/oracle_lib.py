@@ -179,3 +179,42 @@ def processing_order(batch, layer_order_fn) -> np.ndarray:
         s0, s1 = int(batch.win_seq_off[w]), int(batch.win_seq_off[w + 1])
         order[s0:s1] = layer_order_fn(batch.begins[s0:s1])
     return order
+
+
+# ---------------------------------------------------------------------------------------------------
+# overlap alignment (edlib NW path): oracle/aln_oracle.c restatement and the unmodified edlib in oracle/_ref
+# ---------------------------------------------------------------------------------------------------
+def oracle_align(oracle: "Oracle", q: bytes, t: bytes):
+    """(ops uint8 array, edit distance) of the restatement; ops: 0 match, 1 insertion, 2 deletion, 3 mismatch."""
+    cap = len(q) + len(t) + 8
+    ops = np.zeros(cap, dtype=np.uint8)
+    score = C.c_int32(0)
+    oracle.lib.aln_oracle_nw.restype = C.c_int64
+    n = oracle.lib.aln_oracle_nw(C.c_char_p(q), C.c_int32(len(q)), C.c_char_p(t), C.c_int32(len(t)), _p(ops, C.c_uint8),
+                                 C.c_int64(cap), C.byref(score))
+    assert n >= 0
+    return ops[:n].copy(), int(score.value)
+
+
+def ops_to_cigar(oracle: "Oracle", ops: np.ndarray) -> bytes:
+    ops = np.ascontiguousarray(ops, dtype=np.uint8)
+    cap = 16 * ops.shape[0] + 16
+    buf = C.create_string_buffer(cap)
+    oracle.lib.aln_oracle_cigar.restype = C.c_int64
+    n = oracle.lib.aln_oracle_cigar(_p(ops, C.c_uint8), C.c_int64(ops.shape[0]), buf, C.c_int64(cap))
+    assert n >= 0
+    return buf.raw[:n]
+
+
+def ref_align(ref: "Ref", q: bytes, t: bytes):
+    """(ops, edit distance, CIGAR) of the unmodified edlib called like racon calls it (src/overlap.cpp:205-224)."""
+    cap = len(q) + len(t) + 8
+    ops = np.zeros(cap, dtype=np.uint8)
+    ccap = 16 * cap
+    cig = C.create_string_buffer(ccap)
+    score = C.c_int32(0)
+    ref.lib.ref_edlib_nw.restype = C.c_int64
+    n = ref.lib.ref_edlib_nw(C.c_char_p(q), C.c_int32(len(q)), C.c_char_p(t), C.c_int32(len(t)), _p(ops, C.c_uint8),
+                             C.c_int64(cap), cig, C.c_int64(ccap), C.byref(score))
+    assert n >= 0
+    return ops[:n].copy(), int(score.value), cig.value

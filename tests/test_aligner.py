@@ -1,0 +1,44 @@
+"""CPU: the overlap alignment path (CUDABatchAligner / src/overlap.cpp:205-224).
+
+Parity target = the CIGAR racon's CPU path gets from edlib (NW, path).  Here: the oracle's restatement
+(oracle/aln_oracle.c) against the committed digests of the unmodified edlib on REAL overlaps
+(tests/golden/lambda_overlaps.npz), live against oracle/_ref on random pairs around every threshold of edlib's
+recursion, and the engine's lane emulation against the oracle.  GPU: tests/test_gpu_aligner.py."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from common import overlap_fixture, random_pairs
+from oracle_lib import ops_to_cigar, oracle_align, ref_align
+
+SHAPES = [(1, 0.5), (2, 0.5), (5, 0.3), (63, 0.2), (64, 0.2), (65, 0.2), (129, 0.25), (200, 0.15), (700, 0.15),
+          (1500, 0.1), (1800, 0.15), (1850, 0.15), (2000, 0.15), (2600, 0.2), (4000, 0.12), (5000, 0.3)]
+
+
+def test_restatement_matches_edlib_digests_on_real_overlaps(oracle):
+    fx = overlap_fixture()
+    assert len(fx) == 181
+    order = np.argsort([len(f["q"]) * len(f["t"]) for f in fx])
+    for i in list(order[:70]) + list(order[-2:]):  # the 70 smallest (1.4 - 4 kb) and the two largest (11 kb)
+        f = fx[i]
+        ops, score = oracle_align(oracle, f["q"], f["t"])
+        assert score == f["score"] and ops.shape[0] == f["n_ops"]
+        assert hashlib.sha256(ops_to_cigar(oracle, ops)).hexdigest() == f["cigar_sha"], i
+
+
+def test_restatement_matches_live_edlib(oracle, ref):
+    if not ref.available:
+        pytest.skip("oracle/_ref not built (no /root/reference on this box)")
+    pairs = []
+    for rep in range(6):
+        pairs += random_pairs(100 + rep, [s for s in SHAPES if s[0] < 300 or rep < 2])
+    rng = np.random.default_rng(7)
+    for n, m in [(100, 3000), (3000, 100), (1, 5000), (5000, 1), (2500, 2500), (700, 9000), (9000, 700)]:
+        pairs.append((rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=n).tobytes(),
+                      rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=m).tobytes()))
+    for q, t in pairs:
+        a, sa = oracle_align(oracle, q, t)
+        b, sb, cigar = ref_align(ref, q, t)
+        assert sa == sb and a.shape == b.shape and (a == b).all()
+        assert ops_to_cigar(oracle, a) == cigar
