@@ -1,0 +1,384 @@
+/*
+ * aln_core.cuh -- batched global (Needleman-Wunsch, unit cost) alignment of overlaps with path, one warp per
+ * sub-problem, written against poa_simt.cuh (CUDA flavour = the product, lane emulation = tests/emu).
+ *
+ * Replaces, for racon's overlap alignment step (src/cuda/cudapolisher.cpp:74-214, src/cuda/cudaaligner.cpp:50-98), what
+ * the reference runs in vendor/GenomeWorks/cudaaligner (Aligner::align_all: Myers / Hirschberg-Myers kernels) -- but
+ * with the RESULT of racon's CPU path, which is the parity target: the alignment edlib returns
+ * (src/overlap.cpp:205-224; vendor/edlib/edlib/src/edlib.cpp).  Which optimal alignment that is follows from rules on
+ * the plain distance matrix D (oracle/aln_oracle.c restates and pins them):
+ *   - a sub-problem (n query x m target characters) is trivial (n == 0 or m == 0), traced back directly when
+ *     20 * ceil(n / 64) * m + 8 * m < 2^20 (edlib.cpp:1155-1157), or split by Hirschberg at lh = m / 2 otherwise;
+ *   - traceback: first possible move of up (query character alone), left (target character alone), diagonal
+ *     (edlib.cpp:983-1093);
+ *   - split: first query index r = 0..n-2 with L[r] + R[r+1] == optimum, else r = -1, else r = n-1 (:1282-1308).
+ *
+ * Design (not a port of either library):
+ *   - the recursion is LEVEL-SYNCHRONOUS over the whole batch: the host keeps the list of open sub-problems, one launch
+ *     of aln_split_kernel resolves every sub-problem of a level (one warp each: a forward and a backward bit-vector pass
+ *     to the middle column, then the split rule), and ONE launch of aln_leaf_kernel traces back all leaves of all levels;
+ *   - bit-vector passes (Myers 1999 / Hyyro 2003 block recurrence, 64 rows per word) run as a WAVEFRONT across the
+ *     warp: lane l owns block l of a 32-block stripe (2048 rows) and works on column (step - l); the horizontal delta
+ *     of its last row and the column's target character travel to lane l + 1 in one packed shuffle per step.  Taller
+ *     sub-problems take several stripes; the last lane's deltas spill to a per-warp byte row in between;
+ *   - no band: every cell is exact, 64 cells per word operation, so the choice rules above need no band bookkeeping;
+ *   - a leaf stores (Pv, Mv, bottom score) per block and column -- 20 bytes, the record edlib keeps, which is why the
+ *     1 MB rule bounds a leaf's workspace -- in wavefront order (coalesced), and any cell's value is
+ *     bottom - popc(Pv & below) + popc(Mv & below);
+ *   - edit operations go to ops[r0 + c0 ...] of the alignment's (n + m)-byte region: sub-problems never overlap there,
+ *     holes stay 0xFF and are dropped when the CIGAR is formed.
+ */
+#pragma once
+#include "poa_simt.cuh"
+
+namespace b200aln {
+using b200poa::PerLane;
+using b200poa::poa_ffs;
+using b200poa::poa_uniform;
+using b200poa::poa_uniform_pred;
+using b200poa::warp_ballot;
+using b200poa::warp_bcast0;
+using b200poa::warp_get;
+using b200poa::warp_min;
+using b200poa::warp_shift_up1;
+
+enum : uint8_t { OP_MATCH = 0, OP_INSERT = 1, OP_DELETE = 2, OP_MISMATCH = 3, OP_NONE = 0xFF }; /* edlib.h EDLIB_EDOP_* */
+
+#if POA_DEVICE
+#define ALN_HD __host__ __device__ __forceinline__
+#else
+#define ALN_HD static inline
+#endif
+
+constexpr int64_t ALN_LEAF_DATA_LIMIT = 1024 * 1024; /* edlib.cpp:1157 */
+
+/* edlib.cpp:1135-1157: is this sub-problem traced back directly? */
+ALN_HD bool aln_is_leaf(int32_t n, int32_t m) {
+    if (n == 0 || m == 0) return true;
+    const int64_t blocks = (n + 63) / 64;
+    return (2 * 8 + 4) * blocks * (int64_t)m + 2 * 4 * (int64_t)m < ALN_LEAF_DATA_LIMIT;
+}
+
+/* one open sub-problem: rows [r0, r0 + n) of the query, columns [c0, c0 + m) of the target */
+struct AlnRect {
+    int32_t aln;
+    int32_t r0, n, c0, m;
+    int32_t top; /* 1: the whole alignment (its optimum is reported as the edit distance) */
+};
+struct AlnSplit { /* result of one Hirschberg step */
+    int32_t r;      /* split query index relative to the rect, -1 .. n-1; -2: inconsistent */
+    int32_t ls, rs; /* optima of the upper-left and lower-right sub-problems */
+    int32_t best;
+};
+
+/* per resident warp workspace */
+struct AlnSlot {
+    int8_t* hbuf;  /* [max_len + 64]  horizontal deltas of the row between two stripes */
+    int32_t* Lc;   /* [max_len + 2]   last column of the forward pass:  Lc[i] = D(q[0..i), left half)        */
+    int32_t* Rr;   /* [max_len + 2]   last column of the backward pass: Rr[i] = D(q[n-i..n), right half)    */
+    uint64_t* P;   /* [leaf entries]  leaf records in wavefront order, see leaf_entry() */
+    uint64_t* M;
+    int32_t* S;
+};
+ALN_HD int64_t aln_leaf_entries(int32_t max_len) { return ALN_LEAF_DATA_LIMIT / 20 + 31 * (int64_t)((max_len + 63) / 64) + 64; }
+ALN_HD void aln_slot_bind(AlnSlot& s, uint8_t* base, int32_t max_len, size_t* total_out) {
+    size_t o = 0;
+    const size_t E = (size_t)aln_leaf_entries(max_len);
+#define ALN_CARVE(field, type, count)                                  \
+    do {                                                               \
+        o = (o + 255) / 256 * 256;                                     \
+        s.field = base ? reinterpret_cast<type*>(base + o) : nullptr;  \
+        o += sizeof(type) * (size_t)(count);                           \
+    } while (0)
+    ALN_CARVE(hbuf, int8_t, (size_t)max_len + 64);
+    ALN_CARVE(Lc, int32_t, (size_t)max_len + 2);
+    ALN_CARVE(Rr, int32_t, (size_t)max_len + 2);
+    ALN_CARVE(P, uint64_t, E);
+    ALN_CARVE(M, uint64_t, E);
+    ALN_CARVE(S, int32_t, E);
+#undef ALN_CARVE
+    o = (o + 255) / 256 * 256;
+    if (total_out) *total_out = o;
+}
+
+/* a sequence read forwards (step +1) or backwards (step -1): element k = p[k * step] */
+struct SeqView {
+    const uint8_t* p;
+    int32_t step;
+};
+POA_FN uint8_t seq_at(const SeqView s, int32_t k) { return s.p[(int64_t)k * s.step]; }
+
+POA_FN int aln_popc64(uint64_t x) {
+#if POA_DEVICE
+    return __popcll(x);
+#else
+    return __builtin_popcountll(x);
+#endif
+}
+POA_FN int aln_code(uint8_t c) { /* A C G T -> 0..3, anything else -> 4 */
+    return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 4;
+}
+
+/* where the record of (block b, column j) of a leaf with B blocks and `cols` columns lives: stripes of 32 blocks one
+ * after the other, inside a stripe in wavefront order (step = j + lane, nb lanes per step) */
+POA_FN int64_t leaf_entry(int32_t b, int32_t j, int32_t B, int32_t cols) {
+    const int32_t s0 = b & ~31, l = b & 31;
+    const int32_t nb = B - s0 < 32 ? B - s0 : 32;
+    return (int64_t)s0 * (cols + 31) + (int64_t)(j + l) * nb + l;
+}
+
+/*
+ * One bit-vector pass: the distance matrix of q[0..n) against t[0..cols), boundary D[i][0] = i, D[0][j] = j.
+ *   out_col (nullable): receives the last column, out_col[i] = D[i][cols], i = 0..n
+ *   P/M/S   (nullable): receive the record of every (block, column), leaf_entry() order
+ * Myers' block recurrence in Hyyro's formulation (64 rows per word): with Pv/Mv the +1/-1 vertical deltas of the previous
+ * column, Eq the rows whose character equals the column's and hin the horizontal delta entering from above,
+ *   Xv = Eq | Mv;  Eq |= (hin < 0);  Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;  Ph = Mv | ~(Xh | Pv);  Mh = Pv & Xh;
+ *   hout = bit63(Ph) - bit63(Mh);  Ph = Ph << 1 | (hin > 0);  Mh = Mh << 1 | (hin < 0);
+ *   Pv' = Mh | ~(Xv | Ph);  Mv' = Ph & Xv.
+ */
+POA_FN_NOINLINE void myers_pass(const SeqView q, int32_t n, const SeqView t, int32_t cols, int8_t* hbuf, int32_t* out_col,
+                                uint64_t* P, uint64_t* M, int32_t* S) {
+    n = poa_uniform(n);
+    cols = poa_uniform(cols);
+    const int32_t B = (n + 63) / 64;
+    if (out_col) {
+        POA_LANE0 { out_col[0] = cols; }
+    }
+    for (int32_t s0 = 0; s0 < B; s0 += 32) {
+        const int32_t nb = B - s0 < 32 ? B - s0 : 32;
+        const bool more = s0 + 32 < B; /* another stripe follows: the last lane's horizontal deltas are kept */
+        PerLane<uint64_t> Pv, Mv, E0, E1, E2, E3;
+        PerLane<int> bot, link, tcur, tnext, hcur, hnext;
+        POA_LANES(l) {
+            const int32_t b = s0 + l;
+            uint64_t e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+            if (l < nb) {
+                const int32_t row0 = 64 * b;
+                const int32_t cnt = n - row0 < 64 ? n - row0 : 64;
+                for (int32_t k = 0; k < cnt; ++k) {
+                    const int c = aln_code(seq_at(q, row0 + k));
+                    const uint64_t bit = (uint64_t)1 << k;
+                    if (c == 0) e0 |= bit;
+                    else if (c == 1) e1 |= bit;
+                    else if (c == 2) e2 |= bit;
+                    else if (c == 3) e3 |= bit;
+                }
+            }
+            E0[l] = e0;
+            E1[l] = e1;
+            E2[l] = e2;
+            E3[l] = e3;
+            Pv[l] = ~(uint64_t)0;
+            Mv[l] = 0;
+            bot[l] = 64 * (b + 1);
+            link[l] = 0;
+            /* the column stream (target character, entering delta) is fetched 32 columns at a time, one per lane, a block
+             * ahead, and handed to lane 0 by a shuffle */
+            tcur[l] = l < cols ? (int)seq_at(t, l) : 0;
+            tnext[l] = 32 + l < cols ? (int)seq_at(t, 32 + l) : 0;
+            hcur[l] = (s0 > 0 && l < cols) ? (int)hbuf[l] : 1;
+            hnext[l] = (s0 > 0 && 32 + l < cols) ? (int)hbuf[32 + l] : 1;
+        }
+        const int32_t steps = cols + nb - 1;
+        for (int32_t step = 0; step < steps; ++step) {
+            if (step > 0 && (step & 31) == 0) {
+                POA_LANES(l) {
+                    tcur[l] = tnext[l];
+                    hcur[l] = hnext[l];
+                    const int32_t c = step + 32 + l;
+                    tnext[l] = c < cols ? (int)seq_at(t, c) : 0;
+                    hnext[l] = (s0 > 0 && c < cols) ? (int)hbuf[c] : 1;
+                }
+            }
+            const int tch0 = warp_get(tcur, step & 31);
+            const int hin0 = warp_get(hcur, step & 31);
+            PerLane<int> in;
+            warp_shift_up1(link, in); /* in[l] = what lane l - 1 produced in the previous step */
+            POA_LANES(l) {
+                const int32_t j = step - l;
+                int v = in[l];
+                if (l == 0) v = step < cols ? ((hin0 + 1) | (tch0 << 8) | 0x10000) : 0;
+                int nl = 0;
+                if (l < nb && (v & 0x10000)) { /* lane l works on column j = step - l */
+                    const int hin = (v & 0xFF) - 1;
+                    const int tc = (v >> 8) & 0xFF;
+                    uint64_t Eq;
+                    if (tc == 'A') Eq = E0[l];
+                    else if (tc == 'C') Eq = E1[l];
+                    else if (tc == 'G') Eq = E2[l];
+                    else if (tc == 'T') Eq = E3[l];
+                    else { /* any other character equals only itself (edlib's alphabet is the set of bytes seen) */
+                        Eq = 0;
+                        const int32_t row0 = 64 * (s0 + l);
+                        const int32_t cnt = n - row0 < 64 ? n - row0 : 64;
+                        for (int32_t k = 0; k < cnt; ++k)
+                            if ((int)seq_at(q, row0 + k) == tc) Eq |= (uint64_t)1 << k;
+                    }
+                    const uint64_t pv = Pv[l], mv = Mv[l];
+                    const uint64_t neg = hin < 0 ? 1u : 0u, pos = hin > 0 ? 1u : 0u;
+                    const uint64_t Xv = Eq | mv;
+                    const uint64_t Eh = Eq | neg;
+                    const uint64_t Xh = (((Eh & pv) + pv) ^ pv) | Eh;
+                    uint64_t Ph = mv | ~(Xh | pv);
+                    uint64_t Mh = pv & Xh;
+                    const int hout = (int)(Ph >> 63) - (int)(Mh >> 63);
+                    Ph = (Ph << 1) | pos;
+                    Mh = (Mh << 1) | neg;
+                    const uint64_t npv = Mh | ~(Xv | Ph);
+                    const uint64_t nmv = Ph & Xv;
+                    Pv[l] = npv;
+                    Mv[l] = nmv;
+                    bot[l] = bot[l] + hout;
+                    if (P) {
+                        const int64_t e = (int64_t)s0 * (cols + 31) + (int64_t)step * nb + l;
+                        P[e] = npv;
+                        M[e] = nmv;
+                        S[e] = bot[l];
+                    }
+                    if (more && l == 31) hbuf[j] = (int8_t)hout; /* column j was consumed by lane 0 at step j <= step */
+                    nl = (hout + 1) | (tc << 8) | 0x10000;
+                }
+                link[l] = nl;
+            }
+        }
+        if (out_col) { /* the last column, row by row: D = (score above the block) + running sum of the vertical deltas */
+            POA_LANES(l) {
+                if (l < nb) {
+                    const int32_t row0 = 64 * (s0 + l);
+                    const int32_t cnt = n - row0 < 64 ? n - row0 : 64;
+                    const uint64_t pv = Pv[l], mv = Mv[l];
+                    int run = bot[l] - aln_popc64(pv) + aln_popc64(mv);
+                    for (int32_t k = 0; k < cnt; ++k) {
+                        run += (int)((pv >> k) & 1u) - (int)((mv >> k) & 1u);
+                        out_col[row0 + k + 1] = run;
+                    }
+                }
+            }
+        }
+        POA_SYNC();
+        POA_FENCE(); /* hbuf / out_col written by one lane are read by others next */
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * One Hirschberg step (edlib.cpp:1198-1344)
+ * ---------------------------------------------------------------------------------------- */
+POA_FN_NOINLINE void aln_split(const AlnSlot& s_ref, const uint8_t* q, const uint8_t* t, int32_t n, int32_t m, AlnSplit* out) {
+    const AlnSlot s = s_ref;
+    n = poa_uniform(n);
+    m = poa_uniform(m);
+    const int32_t lh = m / 2, rh = m - lh; /* edlib.cpp:1216-1217 */
+    myers_pass(SeqView{q, 1}, n, SeqView{t, 1}, lh, s.hbuf, s.Lc, nullptr, nullptr, nullptr);
+    myers_pass(SeqView{q + (n - 1), -1}, n, SeqView{t + (m - 1), -1}, rh, s.hbuf, s.Rr, nullptr, nullptr, nullptr);
+    /* the optimum of the sub-problem is the smallest left + right sum over all crossing points of the middle */
+    PerLane<int> acc;
+    POA_LANES(l) { acc[l] = 0x7FFFFFFF; }
+    for (int32_t base = 0; base <= n - 2; base += 32) {
+        POA_LANES(l) {
+            const int32_t idx = base + l;
+            if (idx <= n - 2) {
+                const int v = s.Lc[idx + 1] + s.Rr[n - idx - 1];
+                if (v < acc[l]) acc[l] = v;
+            }
+        }
+    }
+    int32_t best = warp_min(acc);
+    const int32_t top_sum = poa_uniform(lh + s.Rr[n]);    /* r = -1: the left half is all deletions  (:1292-1299) */
+    const int32_t bot_sum = poa_uniform(s.Lc[n] + rh);    /* r = n-1: the right half is all deletions (:1300-1308) */
+    if (top_sum < best) best = top_sum;
+    if (bot_sum < best) best = bot_sum;
+    int32_t r = -2;
+    for (int32_t base = 0; base <= n - 2 && r == -2; base += 32) { /* first index wins (:1282-1290) */
+        PerLane<int> hit;
+        POA_LANES(l) {
+            const int32_t idx = base + l;
+            hit[l] = (idx <= n - 2 && s.Lc[idx + 1] + s.Rr[n - idx - 1] == best) ? 1 : 0;
+        }
+        const unsigned mask = warp_ballot(hit);
+        if (mask) r = base + poa_ffs(mask);
+    }
+    int32_t ls = 0, rs = 0;
+    if (r >= 0) {
+        ls = poa_uniform(s.Lc[r + 1]);
+        rs = poa_uniform(s.Rr[n - r - 1]);
+    } else if (top_sum == best) {
+        r = -1;
+        ls = lh;
+        rs = best - lh;
+    } else if (bot_sum == best) {
+        r = n - 1;
+        rs = rh;
+        ls = best - rh;
+    }
+    POA_LANE0 {
+        out->r = r;
+        out->ls = ls;
+        out->rs = rs;
+        out->best = best;
+    }
+    POA_SYNC();
+}
+
+/* ------------------------------------------------------------------------------------------
+ * A leaf: store the whole matrix as block records, walk back from the last cell (edlib.cpp:909-1126)
+ * ---------------------------------------------------------------------------------------- */
+POA_FN int32_t leaf_cell(const AlnSlot& s, int32_t i, int32_t j, int32_t B, int32_t cols) {
+    if (i < 0) return j + 1;
+    if (j < 0) return i + 1;
+    const int32_t k = i & 63;
+    const int64_t e = leaf_entry(i >> 6, j, B, cols);
+    const uint64_t below = k == 63 ? (uint64_t)0 : (~(uint64_t)0 << (k + 1));
+    return s.S[e] - aln_popc64(s.P[e] & below) + aln_popc64(s.M[e] & below);
+}
+
+/* ops: the (n + m)-byte region of this sub-problem, filled from its END backwards (holes stay OP_NONE in front) */
+POA_FN_NOINLINE void aln_leaf(const AlnSlot& s_ref, const uint8_t* q, const uint8_t* t, int32_t n, int32_t m, uint8_t* ops,
+                              int32_t* score_out) {
+    const AlnSlot s = s_ref;
+    n = poa_uniform(n);
+    m = poa_uniform(m);
+    if (n == 0 || m == 0) { /* edlib.cpp:1135-1142 */
+        const int32_t len = n + m;
+        const uint8_t op = n == 0 ? OP_DELETE : OP_INSERT;
+        for (int32_t base = 0; base < len; base += 32) {
+            POA_LANES(l) {
+                if (base + l < len) ops[base + l] = op;
+            }
+        }
+        POA_SYNC();
+        return;
+    }
+    myers_pass(SeqView{q, 1}, n, SeqView{t, 1}, m, s.hbuf, nullptr, s.P, s.M, s.S);
+    const int32_t B = (n + 63) / 64;
+    POA_LANE0 {
+        int32_t i = n - 1, j = m - 1;
+        int32_t cur = leaf_cell(s, i, j, B, m);
+        if (score_out) *score_out = cur;
+        int32_t w = n + m; /* next write position + 1 */
+        while (i >= 0 && j >= 0) {
+            const int32_t u = leaf_cell(s, i - 1, j, B, m);
+            const int32_t lf = leaf_cell(s, i, j - 1, B, m);
+            const int32_t ul = leaf_cell(s, i - 1, j - 1, B, m);
+            if (u + 1 == cur) { /* up: the query character stands alone (edlib.cpp:983-1013) */
+                ops[--w] = OP_INSERT;
+                --i;
+                cur = u;
+            } else if (lf + 1 == cur) { /* left: the target character stands alone (:1015-1044) */
+                ops[--w] = OP_DELETE;
+                --j;
+                cur = lf;
+            } else { /* diagonal (:1046-1093) */
+                ops[--w] = ul == cur ? OP_MATCH : OP_MISMATCH;
+                --i;
+                --j;
+                cur = ul;
+            }
+        }
+        for (; i >= 0; --i) ops[--w] = OP_INSERT; /* along the left border */
+        for (; j >= 0; --j) ops[--w] = OP_DELETE; /* along the top border  */
+    }
+    POA_SYNC();
+}
+
+} // namespace b200aln

@@ -115,6 +115,9 @@ POA_FN void warp_incl_max(PerLane<int>& x) {
     x.v = v;
 }
 
+/* out[l] = x[l-1] (lane 0 keeps its own value) */
+POA_FN void warp_shift_up1(const PerLane<int>& x, PerLane<int>& out) { out.v = __shfl_up_sync(0xffffffffu, x.v, 1); }
+
 #else /* ---------------------------------------------------------------- host emulation */
 
 template <class T>
@@ -172,6 +175,10 @@ POA_FN void warp_shift_down1(const PerLane<int>& x, PerLane<int>& out) {
 POA_FN void warp_incl_max(PerLane<int>& x) {
     for (int l = 1; l < 32; ++l)
         if (x.v[l - 1] > x.v[l]) x.v[l] = x.v[l - 1];
+}
+POA_FN void warp_shift_up1(const PerLane<int>& x, PerLane<int>& out) {
+    for (int l = 31; l > 0; --l) out.v[l] = x.v[l - 1];
+    out.v[0] = x.v[0];
 }
 
 #endif

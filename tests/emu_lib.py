@@ -53,3 +53,21 @@ class Emu:
                      np.zeros(W, dtype=np.int32))
         a, o, c, s = self._msa
         return (_p(a, C.c_uint8), C.c_int64(msa_cap), _p(o, C.c_int64), _p(c, C.c_int32), _p(s, C.c_int32))
+
+
+class EmuAligner:
+    """Host-flavour build of the overlap aligner (tests/emu/libaln_emu.so)."""
+
+    def __init__(self):
+        subprocess.run(["make", "-s", "-C", os.path.join(HERE, "emu")], check=True, stdout=subprocess.DEVNULL)
+        self.lib = C.CDLL(os.path.join(HERE, "emu", "libaln_emu.so"))
+        self.lib.emu_align.restype = C.c_int64
+
+    def align(self, q: bytes, t: bytes):
+        """(ops, edit distance, recursion depth, leaves)"""
+        ops = np.zeros(len(q) + len(t) + 8, dtype=np.uint8)
+        score, levels, leaves = C.c_int32(-1), C.c_int32(0), C.c_int32(0)
+        n = self.lib.emu_align(C.c_char_p(q), C.c_int32(len(q)), C.c_char_p(t), C.c_int32(len(t)), _p(ops, C.c_uint8),
+                               C.byref(score), C.byref(levels), C.byref(leaves))
+        assert n >= 0, "inconsistent split"
+        return ops[:n].copy(), int(score.value), int(levels.value), int(leaves.value)

@@ -42,3 +42,46 @@ def test_restatement_matches_live_edlib(oracle, ref):
         b, sb, cigar = ref_align(ref, q, t)
         assert sa == sb and a.shape == b.shape and (a == b).all()
         assert ops_to_cigar(oracle, a) == cigar
+
+
+@pytest.fixture(scope="module")
+def emu():
+    from emu_lib import EmuAligner
+    return EmuAligner()
+
+
+def test_emulated_aligner_equals_oracle_on_random_pairs(oracle, emu):
+    """Wavefront bit-vector passes, split rule, leaf records and traceback of the engine (lane emulation)."""
+    pairs = []
+    for rep in range(3):
+        pairs += random_pairs(300 + rep, [s for s in SHAPES if s[0] < 300 or rep < 1])
+    rng = np.random.default_rng(11)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    # unrelated sequences and extreme shapes: tall leaves span several 32-block stripes, 1-row / 1-column problems
+    for n, m in [(100, 3000), (3000, 100), (1, 5000), (5000, 1), (2500, 2500), (300, 9000), (9000, 300), (4200, 130)]:
+        pairs.append((rng.choice(acgt, size=n).tobytes(), rng.choice(acgt, size=m).tobytes()))
+    # characters outside ACGT equal only themselves (edlib builds its alphabet from the bytes it sees)
+    q, t = random_pairs(17, [(900, 0.1)])[0]
+    qa, ta = bytearray(q), bytearray(t)
+    for k in range(0, len(qa), 37):
+        qa[k] = ord("N")
+    for k in range(5, len(ta), 41):
+        ta[k] = ord("N") if k % 2 else ord("R")
+    pairs.append((bytes(qa), bytes(ta)))
+    depths = set()
+    for q, t in pairs:
+        a, sa = oracle_align(oracle, q, t)
+        b, sb, depth, leaves = emu.align(q, t)
+        assert sa == sb and a.shape == b.shape and (a == b).all(), (len(q), len(t))
+        depths.add(depth)
+    assert 0 in depths and max(depths) >= 2  # direct tracebacks and Hirschberg recursions both occurred
+
+
+def test_emulated_aligner_on_real_overlaps(oracle, emu):
+    fx = overlap_fixture()
+    order = np.argsort([len(f["q"]) * len(f["t"]) for f in fx])
+    for i in list(order[:12]) + [order[90], order[-1]]:
+        f = fx[i]
+        ops, score, depth, leaves = emu.align(f["q"], f["t"])
+        assert score == f["score"] and ops.shape[0] == f["n_ops"]
+        assert hashlib.sha256(ops_to_cigar(oracle, ops)).hexdigest() == f["cigar_sha"], i
