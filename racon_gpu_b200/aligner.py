@@ -1,0 +1,155 @@
+"""ctypes binding of the overlap aligner's C ABI (include/b200aln.h) -- for tests and bench.py only.
+
+Mirrors racon's adapter for this step, racon::CUDABatchAligner (/root/reference/src/cuda/cudaaligner.hpp:24-96:
+addOverlap / alignAll / generate_cigar_strings / reset) one level below racon's Overlap objects: a pair is
+(query = read segment, target = contig segment) exactly as Overlap::align_overlaps hands them to edlib
+(src/overlap.cpp:205-209).  The product is the CUDA library; there is no CPU fallback here."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from .api import load_library
+
+#: every symbol include/b200aln.h declares (tests check the library exports all of them)
+ALN_ABI_SYMBOLS = (
+    "b200aln_init", "b200aln_batch_create", "b200aln_batch_add_alignment", "b200aln_batch_align_all",
+    "b200aln_batch_sync", "b200aln_batch_num_alignments", "b200aln_batch_get_alignment", "b200aln_batch_get_cigar",
+    "b200aln_batch_get_ops", "b200aln_batch_reset", "b200aln_batch_destroy", "b200aln_batch_get_info",
+    "b200aln_status_string", "b200aln_align_pairs",
+)
+
+SUCCESS, UNINITIALIZED, EXCEEDED_MAX_ALIGNMENTS, EXCEEDED_MAX_LENGTH = 0, 1, 2, 3
+GENERIC_ERROR, INVALID_ARGUMENT, CUDA_ERROR = 5, 6, 7
+
+
+class AlnBatchInfo(C.Structure):
+    _fields_ = [("device_id", C.c_int32), ("n_slots", C.c_int32), ("levels", C.c_int32), ("kernel_launches", C.c_int32),
+                ("n_open", C.c_int64), ("n_leaves", C.c_int64), ("cells", C.c_int64), ("h2d_bytes", C.c_int64),
+                ("d2h_bytes", C.c_int64), ("kernel_ms", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def _lib():
+    lib = load_library()
+    if not getattr(lib, "_aln_typed", False):
+        lib.b200aln_status_string.restype = C.c_char_p
+        lib.b200aln_batch_destroy.restype = None
+        lib.b200aln_batch_get_cigar.restype = C.c_int64
+        lib.b200aln_batch_get_ops.restype = C.c_int64
+        lib._aln_typed = True
+    return lib
+
+
+def status_string(st: int) -> str:
+    return _lib().b200aln_status_string(C.c_int32(int(st))).decode()
+
+
+class CUDABatchAligner:
+    """One aligner batch on one device (createCUDABatchAligner(max_bandwidth, device_id, max_gpu_memory),
+    src/cuda/cudaaligner.cpp:18-45)."""
+
+    def __init__(self, device_id: int = 0, max_gpu_memory: int = 0, max_bandwidth: int = 0, stream=None):
+        self.lib = _lib()
+        self.h = C.c_void_p()
+        st = self.lib.b200aln_batch_create(C.c_int32(device_id), C.c_void_p(stream), C.c_int64(int(max_gpu_memory)),
+                                           C.c_int32(max_bandwidth), C.byref(self.h))
+        if st != SUCCESS:
+            raise RuntimeError(f"b200aln_batch_create: {status_string(st)}")
+
+    def close(self):
+        if self.h:
+            self.lib.b200aln_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_overlap(self, query: bytes, target: bytes) -> bool:
+        """CUDABatchAligner::addOverlap (cudaaligner.cpp:50-81): False = the batch is full (align, reset, add again)."""
+        st = self.lib.b200aln_batch_add_alignment(self.h, C.c_char_p(query), C.c_int32(len(query)), C.c_char_p(target),
+                                                  C.c_int32(len(target)))
+        if st == EXCEEDED_MAX_ALIGNMENTS:
+            return False
+        if st != SUCCESS:
+            raise RuntimeError(f"b200aln_batch_add_alignment: {status_string(st)}")
+        return True
+
+    def has_overlaps(self) -> bool:
+        return self.lib.b200aln_batch_num_alignments(self.h) > 0
+
+    def align_all(self):
+        """CUDABatchAligner::alignAll (cudaaligner.cpp:83-86)"""
+        st = self.lib.b200aln_batch_align_all(self.h)
+        if st != SUCCESS:
+            raise RuntimeError(f"b200aln_batch_align_all: {status_string(st)}")
+
+    def generate_cigar_strings(self):
+        """CUDABatchAligner::generate_cigar_strings (cudaaligner.cpp:88-103): list of (cigar bytes, edit distance)."""
+        st = self.lib.b200aln_batch_sync(self.h)
+        if st != SUCCESS:
+            raise RuntimeError(f"b200aln_batch_sync: {status_string(st)}")
+        out = []
+        for k in range(self.lib.b200aln_batch_num_alignments(self.h)):
+            ed, ast = C.c_int32(-1), C.c_int32(-1)
+            self.lib.b200aln_batch_get_alignment(self.h, C.c_int32(k), None, None, None, C.byref(ed), C.byref(ast))
+            if ast.value != SUCCESS:
+                raise RuntimeError(f"alignment {k}: {status_string(ast.value)}")
+            n = self.lib.b200aln_batch_get_cigar(self.h, C.c_int32(k), None, C.c_int64(0))
+            buf = C.create_string_buffer(int(n) + 1)
+            self.lib.b200aln_batch_get_cigar(self.h, C.c_int32(k), buf, C.c_int64(int(n) + 1))
+            out.append((buf.value, int(ed.value)))
+        return out
+
+    def ops(self, k: int) -> np.ndarray:
+        """Alignment::get_alignment() of alignment k as edlib operation codes (0 match, 1 insert, 2 delete, 3 mismatch)."""
+        n = self.lib.b200aln_batch_get_ops(self.h, C.c_int32(k), None, C.c_int64(0))
+        if n < 0:
+            raise RuntimeError(f"alignment {k}: {status_string(-n)}")
+        out = np.zeros(int(n) + 1, dtype=np.uint8)
+        self.lib.b200aln_batch_get_ops(self.h, C.c_int32(k), out.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_int64(int(n)))
+        return out[:int(n)]
+
+    def info(self) -> dict:
+        bi = AlnBatchInfo()
+        self.lib.b200aln_batch_get_info(self.h, C.byref(bi))
+        return bi.as_dict()
+
+    def reset(self):
+        self.lib.b200aln_batch_reset(self.h)
+
+
+def pack_pairs(pairs):
+    """[(query, target)] -> the columnar form b200aln_align_pairs takes."""
+    q = np.frombuffer(b"".join(p[0] for p in pairs), dtype=np.uint8)
+    t = np.frombuffer(b"".join(p[1] for p in pairs), dtype=np.uint8)
+    q_off = np.zeros(len(pairs) + 1, dtype=np.int64)
+    t_off = np.zeros(len(pairs) + 1, dtype=np.int64)
+    np.cumsum([len(p[0]) for p in pairs], out=q_off[1:])
+    np.cumsum([len(p[1]) for p in pairs], out=t_off[1:])
+    return np.ascontiguousarray(q), q_off, np.ascontiguousarray(t), t_off
+
+
+def align_pairs(q, q_off, t, t_off, device_id: int = 0, max_gpu_memory: int = 0, cigar_cap: int | None = None):
+    """b200aln_align_pairs: (edit distances, cigar bytes, cigar offsets, info dict)."""
+    lib = _lib()
+    n = len(q_off) - 1
+    if cigar_cap is None:
+        cigar_cap = int(q_off[-1] + t_off[-1]) * 2 + 16 * n + 64
+    ed = np.zeros(max(n, 1), dtype=np.int32)
+    cigars = np.zeros(cigar_cap, dtype=np.uint8)
+    coff = np.zeros(n + 1, dtype=np.int64)
+    bi = AlnBatchInfo()
+    p = lambda a, ty: a.ctypes.data_as(C.POINTER(ty))
+    st = lib.b200aln_align_pairs(C.c_int32(device_id), C.c_int64(int(max_gpu_memory)), C.c_int64(n), p(q, C.c_uint8),
+                                 p(q_off, C.c_int64), p(t, C.c_uint8), p(t_off, C.c_int64), p(ed, C.c_int32),
+                                 p(cigars, C.c_char), C.c_int64(cigar_cap), p(coff, C.c_int64), C.byref(bi))
+    if st != SUCCESS:
+        raise RuntimeError(f"b200aln_align_pairs: {status_string(st)}")
+    return ed[:n], cigars, coff, bi.as_dict()

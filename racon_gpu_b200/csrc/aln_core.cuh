@@ -14,9 +14,11 @@
  *   - split: first query index r = 0..n-2 with L[r] + R[r+1] == optimum, else r = -1, else r = n-1 (:1282-1308).
  *
  * Design (not a port of either library):
- *   - the recursion is LEVEL-SYNCHRONOUS over the whole batch: the host keeps the list of open sub-problems, one launch
- *     of aln_split_kernel resolves every sub-problem of a level (one warp each: a forward and a backward bit-vector pass
- *     to the middle column, then the split rule), and ONE launch of aln_leaf_kernel traces back all leaves of all levels;
+ *   - the recursion is LEVEL-SYNCHRONOUS over the whole batch: the list of open sub-problems lives on the device, one
+ *     launch of aln_split_kernel resolves every sub-problem of a level (one warp each: a forward and a backward bit-vector
+ *     pass to the middle column, then the split rule) and appends its two children to the next level's list or to the
+ *     leaf list (aln_push); the host only reads one counter per level.  ONE launch of aln_leaf_kernel then traces back
+ *     all leaves of all levels, one of aln_runs_kernel turns every alignment's operations into run starts;
  *   - bit-vector passes (Myers 1999 / Hyyro 2003 block recurrence, 64 rows per word) run as a WAVEFRONT across the
  *     warp: lane l owns block l of a 32-block stripe (2048 rows) and works on column (step - l); the horizontal delta
  *     of its last row and the column's target character travel to lane l + 1 in one packed shuffle per step.  Taller
@@ -71,6 +73,17 @@ struct AlnSplit { /* result of one Hirschberg step */
     int32_t best;
 };
 
+/* the open list of the next level, the leaf list, and where an overflow of either is reported */
+struct AlnLists {
+    AlnRect* open;
+    int32_t* n_open;
+    int32_t cap_open;
+    AlnRect* leaves;
+    int32_t* n_leaves;
+    int32_t cap_leaves;
+    int32_t* overflow;
+};
+
 /* per resident warp workspace */
 struct AlnSlot {
     int8_t* hbuf;  /* [max_len + 64]  horizontal deltas of the row between two stripes */
@@ -99,6 +112,30 @@ ALN_HD void aln_slot_bind(AlnSlot& s, uint8_t* base, int32_t max_len, size_t* to
 #undef ALN_CARVE
     o = (o + 255) / 256 * 256;
     if (total_out) *total_out = o;
+}
+
+POA_FN int32_t aln_take(int32_t* counter) { /* called by ONE lane */
+#if POA_DEVICE
+    return atomicAdd(counter, 1);
+#else
+    return (*counter)++;
+#endif
+}
+/* files a sub-problem: empty ones vanish, leaves (edlib.cpp:1135-1157) go to the leaf list, the rest stays open.  ONE lane. */
+POA_FN void aln_push(const AlnLists& L, const AlnRect r) {
+    if (r.n == 0 && r.m == 0) return;
+    const bool leaf = aln_is_leaf(r.n, r.m);
+    const int32_t k = aln_take(leaf ? L.n_leaves : L.n_open);
+    if (k < (leaf ? L.cap_leaves : L.cap_open)) (leaf ? L.leaves : L.open)[k] = r;
+    else *L.overflow = 1;
+}
+/* upper-left and lower-right sub-problems of `r` split at query index sr (relative, -1 .. n-1), edlib.cpp:1321-1333 */
+POA_FN bool aln_children(const AlnRect r, int32_t sr, AlnRect& ul, AlnRect& lr) {
+    if (sr < -1 || sr > r.n - 1) return false;
+    const int32_t lh = r.m / 2, uh = sr + 1;
+    ul = AlnRect{r.aln, r.r0, uh, r.c0, lh, 0};
+    lr = AlnRect{r.aln, r.r0 + uh, r.n - uh, r.c0 + lh, r.m - lh, 0};
+    return true;
 }
 
 /* a sequence read forwards (step +1) or backwards (step -1): element k = p[k * step] */
@@ -323,16 +360,48 @@ POA_FN_NOINLINE void aln_split(const AlnSlot& s_ref, const uint8_t* q, const uin
 /* ------------------------------------------------------------------------------------------
  * A leaf: store the whole matrix as block records, walk back from the last cell (edlib.cpp:909-1126)
  * ---------------------------------------------------------------------------------------- */
-POA_FN int32_t leaf_cell(const AlnSlot& s, int32_t i, int32_t j, int32_t B, int32_t cols) {
-    if (i < 0) return j + 1;
-    if (j < 0) return i + 1;
-    const int32_t k = i & 63;
-    const int64_t e = leaf_entry(i >> 6, j, B, cols);
-    const uint64_t below = k == 63 ? (uint64_t)0 : (~(uint64_t)0 << (k + 1));
-    return s.S[e] - aln_popc64(s.P[e] & below) + aln_popc64(s.M[e] & below);
+POA_FN uint64_t warp_get64(const PerLane<uint64_t>& x, int src) {
+#if POA_DEVICE
+    return __shfl_sync(0xffffffffu, x.v, src);
+#else
+    return x.v[src];
+#endif
+}
+POA_FN uint64_t aln_below(int32_t k) { return k == 63 ? (uint64_t)0 : (~(uint64_t)0 << (k + 1)); } /* rows under row k */
+POA_FN int aln_bit(uint64_t x, int32_t k) { return (int)((x >> k) & 1u); }
+
+/* The records of block b for the 32 columns jw, jw-1, .. jw-31 (lane l holds column jw - l): one strided load per field
+ * instead of a dependent round trip per traceback step */
+struct LeafWindow {
+    PerLane<uint64_t> P, M;
+    PerLane<int> S;
+};
+POA_FN void leaf_window_load(const AlnSlot& s, LeafWindow& w, int32_t b, int32_t jw, int32_t B, int32_t cols) {
+    POA_LANES(l) {
+        const int32_t c = jw - l;
+        uint64_t p = 0, m = 0;
+        int sc = 0;
+        if (c >= 0) {
+            const int64_t e = leaf_entry(b, c, B, cols);
+            p = s.P[e];
+            m = s.M[e];
+            sc = s.S[e];
+        }
+        w.P[l] = p;
+        w.M[l] = m;
+        w.S[l] = sc;
+    }
 }
 
-/* ops: the (n + m)-byte region of this sub-problem, filled from its END backwards (holes stay OP_NONE in front) */
+/*
+ * ops: the (n + m)-byte region of this sub-problem, filled from its END backwards (holes stay OP_NONE in front).
+ * The walk is executed by the whole warp in lock step (every lane holds the same position); cell (i, j) stands for
+ * D[i + 1][j + 1].  With (Pj, Mj) the record of (block of i, column j) and (Pl, Ml, Sl) that of column j - 1:
+ *   up        = cur - bit_k(Pj) + bit_k(Mj)                      (the vertical delta of row i, k = i mod 64)
+ *   left      = Sl - popc(Pl & below k) + popc(Ml & below k)      (bottom of the block minus the deltas under row i)
+ *   diagonal  = left - bit_k(Pl) + bit_k(Ml)
+ * so a step costs no memory access; a new window is loaded every 31 columns or when the path enters the block above.
+ */
 POA_FN_NOINLINE void aln_leaf(const AlnSlot& s_ref, const uint8_t* q, const uint8_t* t, int32_t n, int32_t m, uint8_t* ops,
                               int32_t* score_out) {
     const AlnSlot s = s_ref;
@@ -346,39 +415,151 @@ POA_FN_NOINLINE void aln_leaf(const AlnSlot& s_ref, const uint8_t* q, const uint
                 if (base + l < len) ops[base + l] = op;
             }
         }
+        if (score_out) {
+            POA_LANE0 { *score_out = len; }
+        }
         POA_SYNC();
         return;
     }
     myers_pass(SeqView{q, 1}, n, SeqView{t, 1}, m, s.hbuf, nullptr, s.P, s.M, s.S);
     const int32_t B = (n + 63) / 64;
-    POA_LANE0 {
-        int32_t i = n - 1, j = m - 1;
-        int32_t cur = leaf_cell(s, i, j, B, m);
-        if (score_out) *score_out = cur;
-        int32_t w = n + m; /* next write position + 1 */
-        while (i >= 0 && j >= 0) {
-            const int32_t u = leaf_cell(s, i - 1, j, B, m);
-            const int32_t lf = leaf_cell(s, i, j - 1, B, m);
-            const int32_t ul = leaf_cell(s, i - 1, j - 1, B, m);
-            if (u + 1 == cur) { /* up: the query character stands alone (edlib.cpp:983-1013) */
-                ops[--w] = OP_INSERT;
-                --i;
-                cur = u;
-            } else if (lf + 1 == cur) { /* left: the target character stands alone (:1015-1044) */
-                ops[--w] = OP_DELETE;
-                --j;
-                cur = lf;
-            } else { /* diagonal (:1046-1093) */
-                ops[--w] = ul == cur ? OP_MATCH : OP_MISMATCH;
-                --i;
-                --j;
-                cur = ul;
+    LeafWindow win;
+    int32_t i = n - 1, j = m - 1, jw = j;
+    leaf_window_load(s, win, i >> 6, jw, B, m);
+    uint64_t Pj = warp_get64(win.P, 0), Mj = warp_get64(win.M, 0);
+    uint64_t Pl = warp_get64(win.P, 1), Ml = warp_get64(win.M, 1);
+    int32_t Sl = warp_get(win.S, 1);
+    int32_t cur = warp_get(win.S, 0) - aln_popc64(Pj & aln_below(i & 63)) + aln_popc64(Mj & aln_below(i & 63));
+    if (score_out) {
+        POA_LANE0 { *score_out = cur; }
+    }
+    int32_t w = n + m; /* next write position + 1 */
+    while (i >= 0 && j >= 0) {
+        const int32_t k = i & 63;
+        const int32_t u = cur - aln_bit(Pj, k) + aln_bit(Mj, k);
+        int32_t lf, ul;
+        if (j > 0) {
+            lf = Sl - aln_popc64(Pl & aln_below(k)) + aln_popc64(Ml & aln_below(k));
+            ul = lf - aln_bit(Pl, k) + aln_bit(Ml, k);
+        } else { /* the left border: D[i + 1][0] = i + 1 */
+            lf = i + 1;
+            ul = i;
+        }
+        uint8_t op;
+        bool row_move, col_move;
+        if (u + 1 == cur) { /* up: the query character stands alone (edlib.cpp:983-1013) */
+            op = OP_INSERT;
+            row_move = true;
+            col_move = false;
+            cur = u;
+        } else if (lf + 1 == cur) { /* left: the target character stands alone (:1015-1044) */
+            op = OP_DELETE;
+            row_move = false;
+            col_move = true;
+            cur = lf;
+        } else { /* diagonal (:1046-1093) */
+            op = ul == cur ? OP_MATCH : OP_MISMATCH;
+            row_move = col_move = true;
+            cur = ul;
+        }
+        --w;
+        POA_LANE0 { ops[w] = op; }
+        if (row_move) --i;
+        if (col_move) --j;
+        if (i < 0 || j < 0) break;
+        if (row_move && k == 0) { /* the path entered the block above: its records, from column j on */
+            jw = j;
+            leaf_window_load(s, win, i >> 6, jw, B, m);
+            Pj = warp_get64(win.P, 0);
+            Mj = warp_get64(win.M, 0);
+            Pl = warp_get64(win.P, 1);
+            Ml = warp_get64(win.M, 1);
+            Sl = warp_get(win.S, 1);
+        } else if (col_move) {
+            Pj = Pl;
+            Mj = Ml;
+            if (j > 0) {
+                if (jw - (j - 1) > 31) {
+                    jw = j;
+                    leaf_window_load(s, win, i >> 6, jw, B, m);
+                }
+                const int src = jw - (j - 1);
+                Pl = warp_get64(win.P, src);
+                Ml = warp_get64(win.M, src);
+                Sl = warp_get(win.S, src);
             }
         }
-        for (; i >= 0; --i) ops[--w] = OP_INSERT; /* along the left border */
-        for (; j >= 0; --j) ops[--w] = OP_DELETE; /* along the top border  */
+    }
+    /* along the left border (insertions) or the top border (deletions) */
+    const int32_t rest = (i >= 0 ? i : j) + 1;
+    const uint8_t rop = i >= 0 ? OP_INSERT : OP_DELETE;
+    for (int32_t base = 0; base < rest; base += 32) {
+        POA_LANES(l) {
+            if (base + l < rest) ops[w - rest + base + l] = rop;
+        }
     }
     POA_SYNC();
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Operations -> runs (what a CIGAR is made of).  ops: an alignment's (n + m)-byte region with holes; a run start is a
+ * position whose operation differs from the previous (non-hole) one.  Writes start_index << 2 | op for every run start
+ * to runs[] (nullable: count only) and returns the number of runs; *n_ops = operations in total (the end of the last
+ * run).  The host takes differences (Alignment::convert_to_cigar merges match / mismatch runs into 'M' like
+ * edlibAlignmentToCigar(EDLIB_CIGAR_STANDARD), edlib.cpp:1482-1520).
+ * ---------------------------------------------------------------------------------------- */
+POA_FN int aln_fls(unsigned x) { /* index of the highest set bit, x != 0 */
+#if POA_DEVICE
+    return 31 - __clz((int)x);
+#else
+    return 31 - __builtin_clz(x);
+#endif
+}
+POA_FN_NOINLINE int32_t aln_runs(const uint8_t* ops, int32_t len, uint32_t* runs, int32_t* n_ops_out) {
+    len = poa_uniform(len);
+    int32_t n_runs = 0, n_valid = 0, carry = 4; /* carry: the last operation seen, 4 = none yet */
+    for (int32_t base = 0; base < len; base += 32) {
+        PerLane<int> cls, b0, b1, ok;
+        POA_LANES(l) {
+            const int32_t idx = base + l;
+            const int op = idx < len ? (int)ops[idx] : (int)OP_NONE;
+            cls[l] = op;
+            ok[l] = op != (int)OP_NONE;
+            b0[l] = ok[l] && (op & 1);
+            b1[l] = ok[l] && (op & 2);
+        }
+        const unsigned valid = warp_ballot(ok), m0 = warp_ballot(b0), m1 = warp_ballot(b1);
+        if (valid == 0) continue;
+        PerLane<int> start;
+        POA_LANES(l) {
+            const unsigned under = valid & ((1u << l) - 1u);
+            int prev = carry;
+            if (under) {
+                const int p = aln_fls(under);
+                prev = (int)((m0 >> p) & 1u) | (int)(((m1 >> p) & 1u) << 1);
+            }
+            start[l] = ok[l] && prev != cls[l];
+        }
+        const unsigned sm = warp_ballot(start);
+        if (runs) {
+            POA_LANES(l) {
+                if (start[l]) {
+                    const unsigned under = (1u << l) - 1u;
+                    runs[n_runs + b200poa::poa_popc(sm & under)] =
+                        ((uint32_t)(n_valid + b200poa::poa_popc(valid & under)) << 2) | (uint32_t)cls[l];
+                }
+            }
+        }
+        n_runs += b200poa::poa_popc(sm);
+        n_valid += b200poa::poa_popc(valid);
+        const int p = aln_fls(valid);
+        carry = (int)((m0 >> p) & 1u) | (int)(((m1 >> p) & 1u) << 1);
+    }
+    if (n_ops_out) {
+        POA_LANE0 { *n_ops_out = n_valid; }
+    }
+    POA_SYNC();
+    return n_runs;
 }
 
 } // namespace b200aln

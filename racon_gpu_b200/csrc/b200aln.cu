@@ -1,0 +1,683 @@
+/*
+ * b200aln.cu -- C ABI (include/b200aln.h) + batch runtime + kernel launches of the overlap aligner (aln_core.cuh).
+ *
+ * Replaces what racon's CUDABatchAligner reaches through cudaaligner's Aligner (src/cuda/cudaaligner.cpp:50-98 ->
+ * vendor/GenomeWorks/cudaaligner/src/aligner_global*.cpp, hirschberg_myers_gpu.cu), with the results of racon's CPU
+ * path (edlib, src/overlap.cpp:205-224).  Runtime design:
+ *   - per-RESIDENT-WARP workspaces ("slots": two distance columns, the stripe hand-over row, 1 MB of leaf records),
+ *     reused by every sub-problem the warp takes from the level's list; persistent grids, one atomic cursor per launch;
+ *   - the Hirschberg recursion is level-synchronous over the whole batch and its lists live on the device: per level one
+ *     launch and one 4-byte read-back (how many sub-problems the next level has);
+ *   - results leave the device compact: run starts (4 bytes per run of equal operations) bump-allocated into one arena,
+ *     a 24-byte record per alignment -- not (n + m) bytes per alignment.
+ * Nothing here falls back to a CPU aligner; a CUDA failure is a status, not a different code path.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/b200aln.h"
+#include "aln_core.cuh"
+#include "host/aln_levels.hpp"
+
+using namespace b200aln;
+
+namespace {
+
+struct AlnJob { /* one alignment of the batch */
+    int64_t q_off, t_off; /* into the sequence arena */
+    int64_t ops_off;      /* into the operations arena (n + m bytes) */
+    int32_t n, m;
+};
+struct AlnResult {
+    int32_t score, status, n_runs, n_ops;
+    int64_t runs_off;
+};
+
+enum { /* int32 words of the device counter block */
+    CT_CURSOR = 0,      /* [64] one work cursor per launch                                   */
+    CT_NOPEN = 64,      /* [64] sub-problems open at level k                                 */
+    CT_NLEAVES = 128,
+    CT_OVERFLOW = 129,
+    CT_RUNS = 130,      /* u64: entries used in the runs arena                               */
+    CT_CELLS = 132,     /* u64: distance-matrix cells computed                               */
+    CT_WORDS = 136,
+    MAX_LEVELS = 60
+};
+
+struct AlnKernelArgs {
+    uint8_t* slab;
+    size_t slot_bytes;
+    int32_t max_len;
+    const uint8_t* seq;
+    const AlnJob* jobs;
+    uint8_t* ops;
+    AlnResult* res;
+    int32_t* counters;
+};
+
+constexpr int WARPS_PER_BLOCK = 2;
+
+__device__ __forceinline__ void bind_slot(const AlnKernelArgs& a, AlnSlot& s) {
+    const size_t slot = (size_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    aln_slot_bind(s, a.slab + slot * a.slot_bytes, a.max_len, nullptr);
+}
+__device__ __forceinline__ int32_t take_work(int32_t* cursor) {
+    int32_t t = 0;
+    if ((threadIdx.x & 31u) == 0u) t = atomicAdd(cursor, 1);
+    return __shfl_sync(0xffffffffu, t, 0);
+}
+
+/* one Hirschberg level: every open sub-problem is split, its children are filed for the next level or as leaves */
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) aln_split_kernel(const AlnKernelArgs a, const AlnRect* level,
+                                                                         int32_t n_level, const AlnLists next,
+                                                                         int32_t* cursor) {
+    AlnSlot s;
+    bind_slot(a, s);
+    for (;;) {
+        const int32_t k = take_work(cursor);
+        if (k >= n_level) break;
+        const AlnRect r = level[k];
+        const AlnJob job = a.jobs[r.aln];
+        AlnSplit sp;
+        aln_split(s, a.seq + job.q_off + r.r0, a.seq + job.t_off + r.c0, r.n, r.m, &sp);
+        if ((threadIdx.x & 31u) == 0u) {
+            if (r.top) a.res[r.aln].score = sp.best;
+            AlnRect ul, lr;
+            if (aln_children(r, sp.r, ul, lr)) {
+                aln_push(next, ul);
+                aln_push(next, lr);
+            } else {
+                a.res[r.aln].status = B200ALN_GENERIC_ERROR;
+            }
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + CT_CELLS), (unsigned long long)r.n * (unsigned long long)r.m);
+        }
+        __syncwarp();
+    }
+}
+
+/* all leaves of all levels: the matrix as block records, the walk back, operations into the alignment's region */
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) aln_leaf_kernel(const AlnKernelArgs a, const AlnRect* leaves,
+                                                                        int32_t n_leaves, int32_t* cursor) {
+    AlnSlot s;
+    bind_slot(a, s);
+    for (;;) {
+        const int32_t k = take_work(cursor);
+        if (k >= n_leaves) break;
+        const AlnRect r = leaves[k];
+        const AlnJob job = a.jobs[r.aln];
+        aln_leaf(s, a.seq + job.q_off + r.r0, a.seq + job.t_off + r.c0, r.n, r.m, a.ops + job.ops_off + r.r0 + r.c0,
+                 r.top ? &a.res[r.aln].score : nullptr);
+        if ((threadIdx.x & 31u) == 0u)
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + CT_CELLS), (unsigned long long)r.n * (unsigned long long)r.m);
+        __syncwarp();
+    }
+}
+
+/* operations -> run starts, bump-allocated into the compact runs arena */
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) aln_runs_kernel(const AlnKernelArgs a, int32_t n_alignments,
+                                                                        uint32_t* runs, unsigned long long runs_cap,
+                                                                        int32_t* cursor) {
+    for (;;) {
+        const int32_t k = take_work(cursor);
+        if (k >= n_alignments) break;
+        const AlnJob job = a.jobs[k];
+        const uint8_t* ops = a.ops + job.ops_off;
+        const int32_t n_runs = aln_runs(ops, job.n + job.m, nullptr, nullptr);
+        unsigned long long off = 0;
+        if ((threadIdx.x & 31u) == 0u)
+            off = atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + CT_RUNS), (unsigned long long)n_runs);
+        off = __shfl_sync(0xffffffffu, off, 0);
+        if (off + (unsigned long long)n_runs <= runs_cap) {
+            aln_runs(ops, job.n + job.m, runs + off, &a.res[k].n_ops);
+            if ((threadIdx.x & 31u) == 0u) {
+                a.res[k].n_runs = n_runs;
+                a.res[k].runs_off = (int64_t)off;
+            }
+        } else if ((threadIdx.x & 31u) == 0u) {
+            a.res[k].status = B200ALN_GENERIC_ERROR;
+        }
+        __syncwarp();
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* host side                                                                                   */
+/* ------------------------------------------------------------------------------------------ */
+struct DevBuf { /* grow-only device buffer */
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t need(size_t bytes, bool slack = true) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = bytes + (slack ? bytes / 4 : 0) + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+struct PinnedBuf { /* grow-only page-locked host buffer, contents preserved */
+    uint8_t* p = nullptr;
+    size_t cap = 0, used = 0;
+    bool reserve(size_t bytes) {
+        if (bytes <= cap) return true;
+        size_t want = std::max<size_t>(bytes, cap * 2);
+        want = std::max<size_t>(want, (size_t)1 << 20);
+        uint8_t* q = nullptr;
+        if (cudaHostAlloc(reinterpret_cast<void**>(&q), want, cudaHostAllocDefault) != cudaSuccess) return false;
+        if (used) std::memcpy(q, p, used);
+        if (p) cudaFreeHost(p);
+        p = q;
+        cap = want;
+        return true;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = used = 0;
+    }
+};
+
+} // namespace
+
+struct b200aln_batch {
+    int32_t device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int64_t budget = 0;
+    int32_t sm_count = 0, blocks_per_sm = 0;
+
+    /* host staging */
+    PinnedBuf h_seq;
+    std::vector<AlnJob> jobs;
+    int64_t ops_bytes = 0;
+    int64_t cap_open = 0, cap_leaves = 0; /* list capacities the staged alignments need */
+    int32_t max_len = 0;
+    int64_t var_bytes = 0; /* device bytes the staged alignments need besides the slots */
+
+    /* device */
+    DevBuf d_slab, d_seq, d_jobs, d_ops, d_res, d_runs, d_list[2], d_leaves, d_counters;
+    int32_t n_slots = 0, slot_max_len = 0;
+    size_t slot_bytes = 0;
+
+    /* results */
+    std::vector<AlnResult> res;
+    PinnedBuf h_runs;
+    int32_t* h_counters = nullptr; /* pinned, CT_WORDS */
+    bool aligned = false, synced = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    b200aln_batch_info info{};
+};
+
+namespace {
+
+#define ALN_CU(call)                               \
+    do {                                           \
+        cudaError_t e_ = (call);                   \
+        if (e_ != cudaSuccess) {                   \
+            cudaGetLastError();                    \
+            return B200ALN_CUDA_ERROR;             \
+        }                                          \
+    } while (0)
+
+int64_t slot_bytes_for(int32_t max_len) {
+    size_t total = 0;
+    AlnSlot s;
+    aln_slot_bind(s, nullptr, max_len, &total);
+    return (int64_t)total;
+}
+int32_t round_len(int32_t len) { /* slots are re-made only when the longest sequence outgrows them */
+    int32_t r = 16384;
+    while (r < len + 1 && r < (1 << 30)) r <<= 1;
+    return r;
+}
+/* device bytes one alignment needs besides the slots: sequences, operations, run starts, its share of the lists */
+int64_t var_bytes_for(int32_t n, int32_t m) {
+    const int64_t len = (int64_t)n + m;
+    return 6 * len + 64 + (int64_t)sizeof(AlnJob) + (int64_t)sizeof(AlnResult) +
+           (2 * aln_open_capacity(n, m) + aln_leaf_capacity(n, m)) * (int64_t)sizeof(AlnRect);
+}
+
+int32_t ensure_slots(b200aln_batch* b) {
+    const int32_t want_len = round_len(b->max_len);
+    if (b->n_slots > 0 && want_len <= b->slot_max_len) return B200ALN_SUCCESS;
+    const int64_t sb = slot_bytes_for(want_len);
+    const int64_t resident = (int64_t)b->sm_count * b->blocks_per_sm * WARPS_PER_BLOCK;
+    const int64_t avail = b->budget - b->var_bytes;
+    int64_t n = std::min<int64_t>(resident, avail / sb);
+    n -= n % WARPS_PER_BLOCK;
+    if (n < WARPS_PER_BLOCK) return B200ALN_EXCEEDED_MAX_LENGTH;
+    ALN_CU(b->d_slab.need((size_t)(n * sb), false));
+    b->n_slots = (int32_t)n;
+    b->slot_bytes = (size_t)sb;
+    b->slot_max_len = want_len;
+    return B200ALN_SUCCESS;
+}
+
+} // namespace
+
+extern "C" {
+
+int32_t b200aln_init(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return B200ALN_CUDA_ERROR;
+    }
+    return B200ALN_SUCCESS;
+}
+
+const char* b200aln_status_string(int32_t st) {
+    switch (st) {
+        case B200ALN_SUCCESS: return "success";
+        case B200ALN_UNINITIALIZED: return "uninitialized";
+        case B200ALN_EXCEEDED_MAX_ALIGNMENTS: return "exceeded_max_alignments";
+        case B200ALN_EXCEEDED_MAX_LENGTH: return "exceeded_max_length";
+        case B200ALN_EXCEEDED_MAX_ALIGNMENT_DIFFERENCE: return "exceeded_max_alignment_difference";
+        case B200ALN_GENERIC_ERROR: return "generic_error";
+        case B200ALN_INVALID_ARGUMENT: return "invalid_argument";
+        case B200ALN_CUDA_ERROR: return "cuda_error";
+        default: return "unknown";
+    }
+}
+
+void b200aln_batch_destroy(b200aln_batch* b) {
+    if (!b) return;
+    cudaSetDevice(b->device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    b->d_slab.release();
+    b->d_seq.release();
+    b->d_jobs.release();
+    b->d_ops.release();
+    b->d_res.release();
+    b->d_runs.release();
+    b->d_list[0].release();
+    b->d_list[1].release();
+    b->d_leaves.release();
+    b->d_counters.release();
+    b->h_seq.release();
+    b->h_runs.release();
+    if (b->h_counters) cudaFreeHost(b->h_counters);
+    if (b->ev0) cudaEventDestroy(b->ev0);
+    if (b->ev1) cudaEventDestroy(b->ev1);
+    if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
+    cudaGetLastError();
+    delete b;
+}
+
+int32_t b200aln_batch_create(int32_t device_id, void* stream, int64_t max_gpu_mem, int32_t max_bandwidth,
+                             b200aln_batch** out) {
+    (void)max_bandwidth; /* no band: every cell is exact (b200aln.h) */
+    if (!out) return B200ALN_INVALID_ARGUMENT;
+    *out = nullptr;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess) {
+        cudaGetLastError();
+        return B200ALN_CUDA_ERROR;
+    }
+    if (device_id < 0 || device_id >= n_dev) return B200ALN_INVALID_ARGUMENT;
+    b200aln_batch* b = new (std::nothrow) b200aln_batch();
+    if (!b) return B200ALN_GENERIC_ERROR;
+    b->device = device_id;
+    int32_t st = B200ALN_SUCCESS;
+    do {
+        if (cudaSetDevice(device_id) != cudaSuccess) { st = B200ALN_CUDA_ERROR; break; }
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { st = B200ALN_CUDA_ERROR; break; }
+        b->budget = max_gpu_mem > 0 ? max_gpu_mem : (int64_t)((double)free_b * 0.9);
+        if (b->budget < ((int64_t)4 << 20)) { st = B200ALN_INVALID_ARGUMENT; break; }
+        if (stream) {
+            b->stream = static_cast<cudaStream_t>(stream);
+        } else {
+            if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) { st = B200ALN_CUDA_ERROR; break; }
+            b->own_stream = true;
+        }
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) { st = B200ALN_CUDA_ERROR; break; }
+        b->sm_count = prop.multiProcessorCount;
+        int bps_split = 0, bps_leaf = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_split, aln_split_kernel, 32 * WARPS_PER_BLOCK, 0) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_leaf, aln_leaf_kernel, 32 * WARPS_PER_BLOCK, 0) != cudaSuccess) {
+            st = B200ALN_CUDA_ERROR;
+            break;
+        }
+        b->blocks_per_sm = std::max(1, std::min(bps_split, bps_leaf));
+        if (cudaHostAlloc(reinterpret_cast<void**>(&b->h_counters), CT_WORDS * sizeof(int32_t), cudaHostAllocDefault) != cudaSuccess ||
+            cudaEventCreate(&b->ev0) != cudaSuccess || cudaEventCreate(&b->ev1) != cudaSuccess) {
+            st = B200ALN_CUDA_ERROR;
+            break;
+        }
+        b->info.device_id = device_id;
+    } while (0);
+    if (st != B200ALN_SUCCESS) {
+        cudaGetLastError();
+        b200aln_batch_destroy(b);
+        return st;
+    }
+    *out = b;
+    return B200ALN_SUCCESS;
+}
+
+int32_t b200aln_batch_add_alignment(b200aln_batch* b, const char* query, int32_t n, const char* target, int32_t m) {
+    if (!b || n < 0 || m < 0 || (n > 0 && !query) || (m > 0 && !target)) return B200ALN_INVALID_ARGUMENT;
+    if (b->aligned) return B200ALN_GENERIC_ERROR; /* reset() first, like a cudaaligner batch after align_all */
+    if ((int64_t)n + m >= ((int64_t)1 << 30)) return B200ALN_EXCEEDED_MAX_LENGTH; /* run starts are 30-bit */
+    const int64_t vb = var_bytes_for(n, m);
+    const int32_t new_max = std::max(b->max_len, std::max(n, m));
+    /* the slots get what the alignments leave; at least one block's worth must remain */
+    const int64_t min_slots = WARPS_PER_BLOCK * slot_bytes_for(round_len(new_max));
+    if (vb + min_slots > b->budget) return B200ALN_EXCEEDED_MAX_LENGTH;
+    if (b->var_bytes + vb + min_slots > b->budget) return B200ALN_EXCEEDED_MAX_ALIGNMENTS;
+    if (b->jobs.size() >= (size_t)0x7FFFFF00) return B200ALN_EXCEEDED_MAX_ALIGNMENTS;
+    if (!b->h_seq.reserve(b->h_seq.used + (size_t)n + (size_t)m)) return B200ALN_GENERIC_ERROR;
+    AlnJob j;
+    j.q_off = (int64_t)b->h_seq.used;
+    if (n) std::memcpy(b->h_seq.p + b->h_seq.used, query, (size_t)n);
+    b->h_seq.used += (size_t)n;
+    j.t_off = (int64_t)b->h_seq.used;
+    if (m) std::memcpy(b->h_seq.p + b->h_seq.used, target, (size_t)m);
+    b->h_seq.used += (size_t)m;
+    j.ops_off = b->ops_bytes;
+    j.n = n;
+    j.m = m;
+    b->ops_bytes += (int64_t)n + m;
+    b->cap_open += aln_open_capacity(n, m);
+    b->cap_leaves += aln_leaf_capacity(n, m);
+    b->var_bytes += vb;
+    b->max_len = new_max;
+    b->jobs.push_back(j);
+    return B200ALN_SUCCESS;
+}
+
+int32_t b200aln_batch_num_alignments(const b200aln_batch* b) { return b ? (int32_t)b->jobs.size() : 0; }
+
+int32_t b200aln_batch_align_all(b200aln_batch* b) {
+    if (!b) return B200ALN_INVALID_ARGUMENT;
+    if (b->aligned) return B200ALN_SUCCESS;
+    const int32_t n_aln = (int32_t)b->jobs.size();
+    b->info.levels = 0;
+    b->info.kernel_launches = 0;
+    b->info.n_open = b->info.n_leaves = b->info.cells = 0;
+    b->info.h2d_bytes = b->info.d2h_bytes = 0;
+    b->info.kernel_ms = 0.f;
+    b->res.assign((size_t)n_aln, AlnResult{0, 0, 0, 0, 0});
+    if (n_aln == 0) {
+        b->aligned = b->synced = true;
+        return B200ALN_SUCCESS;
+    }
+    ALN_CU(cudaSetDevice(b->device));
+    int32_t st = ensure_slots(b);
+    if (st != B200ALN_SUCCESS) return st;
+    b->info.n_slots = b->n_slots;
+
+    /* the first level, classified on the host: largest first, so the persistent grid starts with the long ones */
+    std::vector<AlnRect> first, leaves0;
+    for (int32_t k = 0; k < n_aln; ++k) {
+        const AlnJob& j = b->jobs[(size_t)k];
+        if (j.n == 0 && j.m == 0) continue;
+        (aln_is_leaf(j.n, j.m) ? leaves0 : first).push_back(AlnRect{k, 0, j.n, 0, j.m, 1});
+    }
+    std::stable_sort(first.begin(), first.end(),
+                     [](const AlnRect& x, const AlnRect& y) { return (int64_t)x.n * x.m > (int64_t)y.n * y.m; });
+    const int64_t cap_open = std::max<int64_t>(b->cap_open, (int64_t)first.size()) + 16;
+    const int64_t cap_leaves = std::max<int64_t>(b->cap_leaves, (int64_t)leaves0.size()) + 16;
+    if (cap_open >= 0x7FFFFFFF || cap_leaves >= 0x7FFFFFFF) return B200ALN_EXCEEDED_MAX_ALIGNMENTS;
+
+    ALN_CU(b->d_seq.need(b->h_seq.used + 64));
+    ALN_CU(b->d_jobs.need(sizeof(AlnJob) * (size_t)n_aln));
+    ALN_CU(b->d_ops.need((size_t)b->ops_bytes + 64));
+    ALN_CU(b->d_res.need(sizeof(AlnResult) * (size_t)n_aln));
+    ALN_CU(b->d_runs.need(sizeof(uint32_t) * ((size_t)b->ops_bytes + 64)));
+    ALN_CU(b->d_list[0].need(sizeof(AlnRect) * (size_t)cap_open));
+    ALN_CU(b->d_list[1].need(sizeof(AlnRect) * (size_t)cap_open));
+    ALN_CU(b->d_leaves.need(sizeof(AlnRect) * (size_t)cap_leaves));
+    ALN_CU(b->d_counters.need(sizeof(int32_t) * CT_WORDS));
+
+    cudaStream_t s = b->stream;
+    int32_t* ct = static_cast<int32_t*>(b->d_counters.p);
+    std::memset(b->h_counters, 0, sizeof(int32_t) * CT_WORDS);
+    b->h_counters[CT_NOPEN] = (int32_t)first.size();
+    b->h_counters[CT_NLEAVES] = (int32_t)leaves0.size();
+    ALN_CU(cudaMemcpyAsync(ct, b->h_counters, sizeof(int32_t) * CT_WORDS, cudaMemcpyHostToDevice, s));
+    ALN_CU(cudaMemcpyAsync(b->d_seq.p, b->h_seq.p, b->h_seq.used, cudaMemcpyHostToDevice, s));
+    ALN_CU(cudaMemcpyAsync(b->d_jobs.p, b->jobs.data(), sizeof(AlnJob) * (size_t)n_aln, cudaMemcpyHostToDevice, s));
+    if (!first.empty())
+        ALN_CU(cudaMemcpyAsync(b->d_list[0].p, first.data(), sizeof(AlnRect) * first.size(), cudaMemcpyHostToDevice, s));
+    if (!leaves0.empty())
+        ALN_CU(cudaMemcpyAsync(b->d_leaves.p, leaves0.data(), sizeof(AlnRect) * leaves0.size(), cudaMemcpyHostToDevice, s));
+    ALN_CU(cudaMemsetAsync(b->d_ops.p, 0xFF, (size_t)b->ops_bytes + 64, s));
+    ALN_CU(cudaMemsetAsync(b->d_res.p, 0, sizeof(AlnResult) * (size_t)n_aln, s));
+    /* the pageable vectors above (jobs, first, leaves0) must not be touched before the copies were issued from them:
+     * cudaMemcpyAsync from pageable memory stages them before returning */
+    b->info.h2d_bytes = (int64_t)(b->h_seq.used + sizeof(AlnJob) * (size_t)n_aln + sizeof(AlnRect) * (first.size() + leaves0.size()) +
+                                  sizeof(int32_t) * CT_WORDS);
+
+    AlnKernelArgs a;
+    a.slab = static_cast<uint8_t*>(b->d_slab.p);
+    a.slot_bytes = b->slot_bytes;
+    a.max_len = b->slot_max_len;
+    a.seq = static_cast<const uint8_t*>(b->d_seq.p);
+    a.jobs = static_cast<const AlnJob*>(b->d_jobs.p);
+    a.ops = static_cast<uint8_t*>(b->d_ops.p);
+    a.res = static_cast<AlnResult*>(b->d_res.p);
+    a.counters = ct;
+    const int32_t max_blocks = b->n_slots / WARPS_PER_BLOCK;
+    auto grid_for = [&](int64_t items) {
+        return (unsigned)std::max<int64_t>(1, std::min<int64_t>(max_blocks, (items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK));
+    };
+
+    ALN_CU(cudaEventRecord(b->ev0, s));
+    int32_t n_level = (int32_t)first.size();
+    int32_t level = 0, launch = 0;
+    while (n_level > 0) {
+        if (level + 1 >= MAX_LEVELS) return B200ALN_GENERIC_ERROR;
+        AlnLists next;
+        next.open = static_cast<AlnRect*>(b->d_list[(level + 1) & 1].p);
+        next.n_open = ct + CT_NOPEN + level + 1;
+        next.cap_open = (int32_t)cap_open;
+        next.leaves = static_cast<AlnRect*>(b->d_leaves.p);
+        next.n_leaves = ct + CT_NLEAVES;
+        next.cap_leaves = (int32_t)cap_leaves;
+        next.overflow = ct + CT_OVERFLOW;
+        aln_split_kernel<<<grid_for(n_level), 32 * WARPS_PER_BLOCK, 0, s>>>(
+            a, static_cast<const AlnRect*>(b->d_list[level & 1].p), n_level, next, ct + CT_CURSOR + launch);
+        ALN_CU(cudaGetLastError());
+        ++launch;
+        b->info.n_open += n_level;
+        ALN_CU(cudaMemcpyAsync(b->h_counters + CT_NOPEN + level + 1, ct + CT_NOPEN + level + 1, sizeof(int32_t),
+                               cudaMemcpyDeviceToHost, s));
+        ALN_CU(cudaStreamSynchronize(s));
+        n_level = std::min<int32_t>(b->h_counters[CT_NOPEN + level + 1], (int32_t)cap_open);
+        ++level;
+    }
+    b->info.levels = level;
+    ALN_CU(cudaMemcpyAsync(b->h_counters + CT_NLEAVES, ct + CT_NLEAVES, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    ALN_CU(cudaStreamSynchronize(s));
+    if (b->h_counters[CT_OVERFLOW]) return B200ALN_GENERIC_ERROR;
+    const int32_t n_leaves = b->h_counters[CT_NLEAVES];
+    b->info.n_leaves = n_leaves;
+    if (n_leaves > 0) {
+        aln_leaf_kernel<<<grid_for(n_leaves), 32 * WARPS_PER_BLOCK, 0, s>>>(a, static_cast<const AlnRect*>(b->d_leaves.p),
+                                                                            n_leaves, ct + CT_CURSOR + launch);
+        ALN_CU(cudaGetLastError());
+        ++launch;
+    }
+    aln_runs_kernel<<<grid_for(n_aln), 32 * WARPS_PER_BLOCK, 0, s>>>(a, n_aln, static_cast<uint32_t*>(b->d_runs.p),
+                                                                     (unsigned long long)b->ops_bytes + 64, ct + CT_CURSOR + launch);
+    ALN_CU(cudaGetLastError());
+    ++launch;
+    ALN_CU(cudaEventRecord(b->ev1, s));
+    b->info.kernel_launches = launch;
+    /* compact results: the per-alignment records and the counters now, the used part of the runs arena after them */
+    ALN_CU(cudaMemcpyAsync(b->res.data(), b->d_res.p, sizeof(AlnResult) * (size_t)n_aln, cudaMemcpyDeviceToHost, s));
+    ALN_CU(cudaMemcpyAsync(b->h_counters + CT_RUNS, ct + CT_RUNS, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    ALN_CU(cudaStreamSynchronize(s));
+    unsigned long long n_runs_total = 0, cells = 0;
+    std::memcpy(&n_runs_total, b->h_counters + CT_RUNS, 8);
+    std::memcpy(&cells, b->h_counters + CT_CELLS, 8);
+    b->info.cells = (int64_t)cells;
+    n_runs_total = std::min<unsigned long long>(n_runs_total, (unsigned long long)b->ops_bytes + 64);
+    b->h_runs.used = 0;
+    if (!b->h_runs.reserve((size_t)n_runs_total * sizeof(uint32_t) + 64)) return B200ALN_GENERIC_ERROR;
+    b->h_runs.used = (size_t)n_runs_total * sizeof(uint32_t);
+    if (n_runs_total)
+        ALN_CU(cudaMemcpyAsync(b->h_runs.p, b->d_runs.p, (size_t)n_runs_total * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    b->info.d2h_bytes = (int64_t)(sizeof(AlnResult) * (size_t)n_aln + (size_t)n_runs_total * sizeof(uint32_t) +
+                                  sizeof(int32_t) * (size_t)(level + 6));
+    b->aligned = true;
+    b->synced = false;
+    return B200ALN_SUCCESS;
+}
+
+int32_t b200aln_batch_sync(b200aln_batch* b) {
+    if (!b) return B200ALN_INVALID_ARGUMENT;
+    if (!b->aligned) return B200ALN_UNINITIALIZED;
+    if (b->synced) return B200ALN_SUCCESS;
+    ALN_CU(cudaSetDevice(b->device));
+    ALN_CU(cudaStreamSynchronize(b->stream));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, b->ev0, b->ev1) == cudaSuccess) b->info.kernel_ms = ms;
+    else cudaGetLastError();
+    b->synced = true;
+    return B200ALN_SUCCESS;
+}
+
+int32_t b200aln_batch_get_alignment(const b200aln_batch* b, int32_t index, const uint32_t** runs, int32_t* n_runs,
+                                    int32_t* n_ops, int32_t* edit_distance, int32_t* status) {
+    if (!b || index < 0 || (size_t)index >= b->jobs.size()) return B200ALN_INVALID_ARGUMENT;
+    if (!b->aligned || !b->synced) return B200ALN_UNINITIALIZED;
+    const AlnResult& r = b->res[(size_t)index];
+    const bool ok = r.status == 0 && r.runs_off >= 0 &&
+                    (size_t)(r.runs_off + r.n_runs) * sizeof(uint32_t) <= b->h_runs.used;
+    if (runs) *runs = ok ? reinterpret_cast<const uint32_t*>(b->h_runs.p) + r.runs_off : nullptr;
+    if (n_runs) *n_runs = ok ? r.n_runs : 0;
+    if (n_ops) *n_ops = ok ? r.n_ops : 0;
+    if (edit_distance) *edit_distance = r.score;
+    if (status) *status = ok ? B200ALN_SUCCESS : (r.status ? r.status : B200ALN_GENERIC_ERROR);
+    return B200ALN_SUCCESS;
+}
+
+int64_t b200aln_batch_get_cigar(const b200aln_batch* b, int32_t index, char* out, int64_t cap) {
+    const uint32_t* runs = nullptr;
+    int32_t n_runs = 0, n_ops = 0, st = 0;
+    const int32_t rc = b200aln_batch_get_alignment(b, index, &runs, &n_runs, &n_ops, nullptr, &st);
+    if (rc != B200ALN_SUCCESS) return -(int64_t)rc;
+    if (st != B200ALN_SUCCESS) return -(int64_t)st;
+    const std::string c = aln_runs_to_cigar(runs, n_runs, n_ops);
+    if (out && cap > 0) {
+        const size_t k = std::min<size_t>(c.size(), (size_t)cap - 1);
+        std::memcpy(out, c.data(), k);
+        out[k] = 0;
+    }
+    return (int64_t)c.size();
+}
+
+int64_t b200aln_batch_get_ops(const b200aln_batch* b, int32_t index, uint8_t* out, int64_t cap) {
+    const uint32_t* runs = nullptr;
+    int32_t n_runs = 0, n_ops = 0, st = 0;
+    const int32_t rc = b200aln_batch_get_alignment(b, index, &runs, &n_runs, &n_ops, nullptr, &st);
+    if (rc != B200ALN_SUCCESS) return -(int64_t)rc;
+    if (st != B200ALN_SUCCESS) return -(int64_t)st;
+    if (out && cap > 0) {
+        std::vector<uint8_t> ops;
+        aln_expand_runs(runs, n_runs, n_ops, ops);
+        std::memcpy(out, ops.data(), (size_t)std::min<int64_t>(cap, n_ops));
+    }
+    return n_ops;
+}
+
+int32_t b200aln_batch_reset(b200aln_batch* b) {
+    if (!b) return B200ALN_INVALID_ARGUMENT;
+    cudaSetDevice(b->device);
+    if (b->aligned && !b->synced) cudaStreamSynchronize(b->stream);
+    cudaGetLastError();
+    b->jobs.clear();
+    b->h_seq.used = 0;
+    b->ops_bytes = 0;
+    b->cap_open = b->cap_leaves = 0;
+    b->var_bytes = 0;
+    b->max_len = 0;
+    b->res.clear();
+    b->h_runs.used = 0;
+    b->aligned = b->synced = false;
+    return B200ALN_SUCCESS;
+}
+
+int32_t b200aln_batch_get_info(const b200aln_batch* b, b200aln_batch_info* info) {
+    if (!b || !info) return B200ALN_INVALID_ARGUMENT;
+    *info = b->info;
+    return B200ALN_SUCCESS;
+}
+
+int32_t b200aln_align_pairs(int32_t device_id, int64_t max_gpu_mem, int64_t n, const uint8_t* q_bases,
+                            const int64_t* q_off, const uint8_t* t_bases, const int64_t* t_off, int32_t* edit_distance,
+                            char* cigars, int64_t cigar_cap, int64_t* cigar_off, b200aln_batch_info* info) {
+    if (n < 0 || (n > 0 && (!q_bases || !q_off || !t_bases || !t_off || !cigar_off))) return B200ALN_INVALID_ARGUMENT;
+    b200aln_batch* b = nullptr;
+    int32_t st = b200aln_batch_create(device_id, nullptr, max_gpu_mem, 0, &b);
+    if (st != B200ALN_SUCCESS) return st;
+    b200aln_batch_info total{};
+    total.device_id = device_id;
+    int64_t done = 0, used = 0;
+    bool too_small = false;
+    if (n > 0) cigar_off[0] = 0;
+    while (done < n && st == B200ALN_SUCCESS) {
+        int64_t k = done;
+        for (; k < n; ++k) {
+            const int32_t rc = b200aln_batch_add_alignment(b, reinterpret_cast<const char*>(q_bases + q_off[k]),
+                                                           (int32_t)(q_off[k + 1] - q_off[k]),
+                                                           reinterpret_cast<const char*>(t_bases + t_off[k]),
+                                                           (int32_t)(t_off[k + 1] - t_off[k]));
+            if (rc == B200ALN_EXCEEDED_MAX_ALIGNMENTS && k > done) break;
+            if (rc != B200ALN_SUCCESS) { st = rc == B200ALN_EXCEEDED_MAX_ALIGNMENTS ? B200ALN_EXCEEDED_MAX_LENGTH : rc; break; }
+        }
+        if (st != B200ALN_SUCCESS) break;
+        st = b200aln_batch_align_all(b);
+        if (st == B200ALN_SUCCESS) st = b200aln_batch_sync(b);
+        if (st != B200ALN_SUCCESS) break;
+        for (int64_t i = done; i < k; ++i) {
+            int32_t ed = 0, ast = 0;
+            b200aln_batch_get_alignment(b, (int32_t)(i - done), nullptr, nullptr, nullptr, &ed, &ast);
+            if (ast != B200ALN_SUCCESS) { st = ast; break; }
+            if (edit_distance) edit_distance[i] = ed;
+            const int64_t room = too_small ? 0 : cigar_cap - used;
+            const int64_t len = b200aln_batch_get_cigar(b, (int32_t)(i - done), room > 0 ? cigars + used : nullptr, room);
+            if (len < 0) { st = (int32_t)-len; break; }
+            if (len + 1 > room) too_small = true;
+            used += len + 1;
+            cigar_off[i + 1] = used;
+        }
+        b200aln_batch_info bi;
+        b200aln_batch_get_info(b, &bi);
+        total.n_slots = bi.n_slots;
+        total.levels = std::max(total.levels, bi.levels);
+        total.kernel_launches += bi.kernel_launches;
+        total.n_open += bi.n_open;
+        total.n_leaves += bi.n_leaves;
+        total.cells += bi.cells;
+        total.h2d_bytes += bi.h2d_bytes;
+        total.d2h_bytes += bi.d2h_bytes;
+        total.kernel_ms += bi.kernel_ms;
+        b200aln_batch_reset(b);
+        done = k;
+    }
+    b200aln_batch_destroy(b);
+    if (info) *info = total;
+    if (st == B200ALN_SUCCESS && too_small) return B200ALN_EXCEEDED_MAX_LENGTH;
+    return st;
+}
+
+} // extern "C"

@@ -1,32 +1,51 @@
 /*
- * aln_levels.hpp -- the host side of the level-synchronous Hirschberg recursion (aln_core.cuh): which open sub-problems
- * are leaves (edlib.cpp:1135-1157), and the two children of a split one (edlib.cpp:1321-1333).  Shared by the batch
- * runtime (csrc/b200aln.cu) and the lane emulation (tests/emu/emu_aln.cpp).
+ * aln_levels.hpp -- host-side helpers of the level-synchronous Hirschberg recursion (aln_core.cuh) shared by the batch
+ * runtime (csrc/b200aln.cu) and the lane emulation (tests/emu/emu_aln.cpp): capacity of the sub-problem lists, and the
+ * expansion of run starts (aln_runs) into operations / a CIGAR string.
  */
 #pragma once
-#include <algorithm>
+#include <cstdint>
+#include <string>
 #include <vector>
 
 #include "../aln_core.cuh"
 
 namespace b200aln {
 
-/* leaves go to `leaves`, the rest to `open`, largest first (a persistent grid drains the expensive ones first) */
-inline void aln_classify(const std::vector<AlnRect>& level, std::vector<AlnRect>& open, std::vector<AlnRect>& leaves) {
-    open.clear();
-    for (const AlnRect& r : level) (aln_is_leaf(r.n, r.m) ? leaves : open).push_back(r);
-    std::stable_sort(open.begin(), open.end(), [](const AlnRect& a, const AlnRect& b) {
-        return (int64_t)a.n * a.m > (int64_t)b.n * b.m;
-    });
+/* How many sub-problems one n x m alignment can have open at one level / leave as leaves in total.  A split halves the
+ * columns and partitions the rows, so level d holds <= min(2^d, data / 2^d / 1 MB + 1) open sub-problems (each open one
+ * carries >= 1 MB of leaf data, edlib.cpp:1155-1157); every open sub-problem has two children. */
+inline int64_t aln_open_capacity(int32_t n, int32_t m) {
+    const int64_t data = 20 * (int64_t)((n + 63) / 64) * m + 8 * (int64_t)m;
+    return 2 * (data / ALN_LEAF_DATA_LIMIT + 1) + 2;
 }
+inline int64_t aln_leaf_capacity(int32_t n, int32_t m) { return 4 * aln_open_capacity(n, m) + 2; }
 
-/* upper-left and lower-right sub-problems of rect `r` split at query index s.r (relative, -1 .. n-1) */
-inline bool aln_children(const AlnRect& r, const AlnSplit& s, AlnRect& ul, AlnRect& lr) {
-    if (s.r < -1 || s.r > r.n - 1) return false;
-    const int32_t lh = r.m / 2, uh = s.r + 1;
-    ul = AlnRect{r.aln, r.r0, uh, r.c0, lh, 0};
-    lr = AlnRect{r.aln, r.r0 + uh, r.n - uh, r.c0 + lh, r.m - lh, 0};
-    return true;
+/* run starts (start << 2 | op) + total operation count -> one operation per position (edlib's EDLIB_EDOP_* codes) */
+inline void aln_expand_runs(const uint32_t* runs, int32_t n_runs, int32_t n_ops, std::vector<uint8_t>& out) {
+    out.resize((size_t)n_ops);
+    for (int32_t k = 0; k < n_runs; ++k) {
+        const int32_t b = (int32_t)(runs[k] >> 2), e = k + 1 < n_runs ? (int32_t)(runs[k + 1] >> 2) : n_ops;
+        for (int32_t x = b; x < e; ++x) out[(size_t)x] = (uint8_t)(runs[k] & 3u);
+    }
+}
+/* edlibAlignmentToCigar(..., EDLIB_CIGAR_STANDARD) (edlib.cpp:1482-1520): match and mismatch are both 'M', a query
+ * character alone is 'I', a target character alone is 'D' */
+inline std::string aln_runs_to_cigar(const uint32_t* runs, int32_t n_runs, int32_t n_ops) {
+    static const char letter[4] = {'M', 'I', 'D', 'M'};
+    std::string out;
+    int32_t k = 0;
+    while (k < n_runs) {
+        const char c = letter[runs[k] & 3u];
+        const int32_t b = (int32_t)(runs[k] >> 2);
+        int32_t e = k + 1;
+        while (e < n_runs && letter[runs[e] & 3u] == c) ++e;
+        const int32_t end = e < n_runs ? (int32_t)(runs[e] >> 2) : n_ops;
+        out += std::to_string(end - b);
+        out += c;
+        k = e;
+    }
+    return out;
 }
 
 } // namespace b200aln

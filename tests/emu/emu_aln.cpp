@@ -2,9 +2,10 @@
  * emu_aln.cpp -- lock-step CPU emulation of the overlap aligner (TEST INFRASTRUCTURE).
  *
  * Compiles racon_gpu_b200/csrc/aln_core.cuh in its host flavour (poa_simt.cuh: POA_LANES loops over 32 lanes, shuffles
- * are plain loops) and drives it with the product's own level logic (csrc/host/aln_levels.hpp), so that the wavefront
- * bit-vector passes, the split rule, the leaf records and the traceback are checked against the oracle / the unmodified
- * edlib without a GPU.  Never linked into the product library.
+ * are plain loops) and drives it level by level exactly like the batch runtime (csrc/b200aln.cu) does on the device --
+ * aln_push files the children, the leaf list is traced back at the end, aln_runs forms the runs -- so that the wavefront
+ * bit-vector passes, the split rule, the leaf records, the traceback and the run formation are checked against the
+ * oracle / the unmodified edlib without a GPU.  Never linked into the product library.
  */
 #include <cstdint>
 #include <cstring>
@@ -16,10 +17,11 @@ using namespace b200aln;
 
 extern "C" {
 
-/* Aligns one pair; ops_out must hold n + m bytes.  Returns the number of operations (holes removed), -1 on an
- * inconsistent split; *score the edit distance; *levels (nullable) the depth of the recursion; *n_leaves likewise. */
+/* Aligns one pair; ops_out must hold n + m bytes.  Returns the number of operations (holes removed); -1 inconsistent
+ * split, -2 list overflow, -3 the runs do not spell the operations.  *score the edit distance; *levels (nullable) the
+ * depth of the recursion; *n_leaves likewise; cigar_out (nullable, cigar_cap bytes) the CIGAR formed from the runs. */
 int64_t emu_align(const uint8_t* q, int32_t n, const uint8_t* t, int32_t m, uint8_t* ops_out, int32_t* score,
-                  int32_t* levels, int32_t* n_leaves) {
+                  int32_t* levels, int32_t* n_leaves, char* cigar_out, int64_t cigar_cap) {
     const int32_t max_len = (n > m ? n : m) + 1;
     size_t slot_bytes = 0;
     AlnSlot s;
@@ -27,30 +29,51 @@ int64_t emu_align(const uint8_t* q, int32_t n, const uint8_t* t, int32_t m, uint
     std::vector<uint8_t> slab(slot_bytes + 512);
     aln_slot_bind(s, reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(slab.data()) + 255) & ~uintptr_t(255)), max_len, nullptr);
     std::vector<uint8_t> ops((size_t)n + (size_t)m, OP_NONE);
-    std::vector<AlnRect> level{AlnRect{0, 0, n, 0, m, 1}}, open, leaves, next;
-    int32_t depth = 0;
-    while (!level.empty()) {
-        aln_classify(level, open, leaves);
-        next.clear();
-        for (const AlnRect& r : open) {
+    const int32_t cap_open = (int32_t)aln_open_capacity(n, m), cap_leaves = (int32_t)aln_leaf_capacity(n, m);
+    std::vector<AlnRect> level((size_t)cap_open), next((size_t)cap_open), leaves((size_t)cap_leaves);
+    int32_t n_level = 0, n_next = 0, n_leaf = 0, overflow = 0, depth = 0;
+    AlnLists first{level.data(), &n_level, cap_open, leaves.data(), &n_leaf, cap_leaves, &overflow};
+    aln_push(first, AlnRect{0, 0, n, 0, m, 1});
+    while (n_level > 0) {
+        n_next = 0;
+        AlnLists L{next.data(), &n_next, cap_open, leaves.data(), &n_leaf, cap_leaves, &overflow};
+        for (int32_t k = 0; k < n_level; ++k) {
+            const AlnRect r = level[(size_t)k];
             AlnSplit sp;
             aln_split(s, q + r.r0, t + r.c0, r.n, r.m, &sp);
             if (r.top) *score = sp.best;
             AlnRect ul, lr;
-            if (!aln_children(r, sp, ul, lr)) return -1;
-            next.push_back(ul);
-            next.push_back(lr);
+            if (!aln_children(r, sp.r, ul, lr)) return -1;
+            aln_push(L, ul);
+            aln_push(L, lr);
         }
         level.swap(next);
-        if (!open.empty()) ++depth;
+        n_level = n_next;
+        ++depth;
     }
-    for (const AlnRect& r : leaves)
+    if (overflow) return -2;
+    for (int32_t k = 0; k < n_leaf; ++k) {
+        const AlnRect r = leaves[(size_t)k];
         aln_leaf(s, q + r.r0, t + r.c0, r.n, r.m, ops.data() + r.r0 + r.c0, r.top ? score : nullptr);
+    }
     int64_t k = 0;
     for (uint8_t op : ops)
         if (op != OP_NONE) ops_out[k++] = op;
+    /* the runs must spell the same operations */
+    int32_t n_ops = -1;
+    const int32_t n_runs = aln_runs(ops.data(), n + m, nullptr, &n_ops);
+    std::vector<uint32_t> runs((size_t)n_runs + 1);
+    if (aln_runs(ops.data(), n + m, runs.data(), &n_ops) != n_runs || n_ops != k) return -3;
+    std::vector<uint8_t> spelled;
+    aln_expand_runs(runs.data(), n_runs, n_ops, spelled);
+    if (spelled.size() != (size_t)k || (k > 0 && std::memcmp(spelled.data(), ops_out, (size_t)k) != 0)) return -3;
+    if (cigar_out) {
+        const std::string c = aln_runs_to_cigar(runs.data(), n_runs, n_ops);
+        if ((int64_t)c.size() + 1 > cigar_cap) return -3;
+        std::memcpy(cigar_out, c.c_str(), c.size() + 1);
+    }
     if (levels) *levels = depth;
-    if (n_leaves) *n_leaves = (int32_t)leaves.size();
+    if (n_leaves) *n_leaves = n_leaf;
     return k;
 }
 

@@ -64,10 +64,13 @@ class EmuAligner:
         self.lib.emu_align.restype = C.c_int64
 
     def align(self, q: bytes, t: bytes):
-        """(ops, edit distance, recursion depth, leaves)"""
+        """(ops, edit distance, recursion depth, leaves); self.cigar = the CIGAR formed from the engine's runs"""
         ops = np.zeros(len(q) + len(t) + 8, dtype=np.uint8)
         score, levels, leaves = C.c_int32(-1), C.c_int32(0), C.c_int32(0)
+        cap = 4 * (len(q) + len(t)) + 16
+        cigar = C.create_string_buffer(cap)
         n = self.lib.emu_align(C.c_char_p(q), C.c_int32(len(q)), C.c_char_p(t), C.c_int32(len(t)), _p(ops, C.c_uint8),
-                               C.byref(score), C.byref(levels), C.byref(leaves))
-        assert n >= 0, "inconsistent split"
+                               C.byref(score), C.byref(levels), C.byref(leaves), cigar, C.c_int64(cap))
+        assert n >= 0, {-1: "inconsistent split", -2: "list overflow", -3: "runs do not spell the operations"}.get(n, n)
+        self.cigar = cigar.value
         return ops[:n].copy(), int(score.value), int(levels.value), int(leaves.value)

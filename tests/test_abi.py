@@ -10,10 +10,10 @@ from racon_gpu_b200 import api
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "b200poa.h")).read()
+def declared_symbols(header="b200poa.h", prefix="b200poa_"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(b200poa_[a-z_0-9]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(" + prefix + r"[a-z_0-9]+)\s*\(", text)))
 
 
 def test_library_exports_every_declared_symbol():
@@ -23,6 +23,18 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(api.ABI_SYMBOLS) == names
+
+
+def test_library_exports_every_aligner_symbol():
+    """include/b200aln.h (overlap alignment step); no compute calls without a GPU."""
+    from racon_gpu_b200 import aligner
+    lib = api.load_library()
+    names = declared_symbols("b200aln.h", "b200aln_")
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(aligner.ALN_ABI_SYMBOLS) == names
+    assert aligner.status_string(2) == "exceeded_max_alignments"
 
 
 def test_config_default_follows_cudapoa_batchconfig():

@@ -73,6 +73,7 @@ def test_emulated_aligner_equals_oracle_on_random_pairs(oracle, emu):
         a, sa = oracle_align(oracle, q, t)
         b, sb, depth, leaves = emu.align(q, t)
         assert sa == sb and a.shape == b.shape and (a == b).all(), (len(q), len(t))
+        assert emu.cigar == ops_to_cigar(oracle, a)  # run starts (aln_runs) -> CIGAR like edlibAlignmentToCigar
         depths.add(depth)
     assert 0 in depths and max(depths) >= 2  # direct tracebacks and Hirschberg recursions both occurred
 

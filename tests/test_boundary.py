@@ -40,3 +40,32 @@ def test_racons_cudabatch_builds_against_the_shim_with_the_documented_diff(tmp_p
            "-I", "/usr/local/cuda/include", str(tmp_path / "cudabatch.cpp")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     assert res.returncode == 0, res.stderr[-3000:]
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src", "cuda")), reason="reference sources not present")
+def test_racons_cudaaligner_builds_against_the_shim_with_the_documented_diff(tmp_path):
+    """racon's CUDABatchAligner (src/cuda/cudaaligner.{hpp,cpp}) over b200aln_aligner.hpp."""
+    for f in ("cudaaligner.hpp", "cudaaligner.cpp"):
+        shutil.copy(os.path.join(REF, "src", "cuda", f), tmp_path / f)
+        os.chmod(tmp_path / f, 0o644)
+    hpp = (tmp_path / "cudaaligner.hpp").read_text()
+    for inc in ("cudaaligner.hpp", "aligner.hpp", "alignment.hpp"):
+        line = "#include <claraparabricks/genomeworks/cudaaligner/%s>" % inc
+        assert line in hpp
+        hpp = hpp.replace(line, '#include "b200aln_aligner.hpp"' if inc == "aligner.hpp" else "")
+    assert "std::unique_ptr<claraparabricks::genomeworks::cudaaligner::Aligner> aligner_;" in hpp
+    hpp = hpp.replace("std::unique_ptr<claraparabricks::genomeworks::cudaaligner::Aligner> aligner_;",
+                      "std::unique_ptr<b200aln_cpp::Aligner> aligner_;")
+    (tmp_path / "cudaaligner.hpp").write_text(hpp)
+    cpp = (tmp_path / "cudaaligner.cpp").read_text()
+    assert "using namespace claraparabricks::genomeworks::cudaaligner;" in cpp
+    cpp = cpp.replace("using namespace claraparabricks::genomeworks::cudaaligner;", "using namespace b200aln_cpp;")
+    (tmp_path / "cudaaligner.cpp").write_text(cpp)
+    cmd = ["g++", "-std=c++14", "-fsyntax-only", "-DCUDA_ENABLED", "-I", str(tmp_path),
+           "-I", os.path.join(REF, "src"), "-I", os.path.join(REF, "src", "cuda"),
+           "-I", os.path.join(ROOT, "racon_gpu_b200", "csrc", "host"), "-I", os.path.join(ROOT, "include"),
+           "-I", os.path.join(REF, "vendor", "GenomeWorks", "common", "base", "include"),  # GW_CU_CHECK_ERR only
+           "-I", os.path.join(REF, "vendor", "GenomeWorks", "3rdparty", "spdlog", "include"),
+           "-I", "/usr/local/cuda/include", str(tmp_path / "cudaaligner.cpp")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-3000:]

@@ -1,0 +1,142 @@
+"""GPU: the overlap aligner through its C ABI (include/b200aln.h) against racon's CPU path.
+
+Parity bar: bit-exact -- same edit distance, same operations (hence the same CIGAR) as edlib returns for
+edlibAlign(q, t, {-1, EDLIB_MODE_NW, EDLIB_TASK_PATH}) (src/overlap.cpp:205-224): the oracle's restatement on seeded
+random pairs around every threshold of edlib's recursion, the committed digests of the UNMODIFIED edlib on the 181
+real lambda-phage overlaps of the reference's test data, and oracle/_ref live where it travelled to the box."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from common import overlap_fixture, random_pairs
+from oracle_lib import ops_to_cigar, oracle_align, ref_align
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(1, 0.5), (2, 0.5), (5, 0.3), (63, 0.2), (64, 0.2), (65, 0.2), (129, 0.25), (200, 0.15), (700, 0.15),
+          (1500, 0.1), (1800, 0.15), (1850, 0.15), (2000, 0.15), (2600, 0.2), (4000, 0.12), (5000, 0.3)]
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+def _pairs():
+    pairs = []
+    for rep in range(3):
+        pairs += random_pairs(500 + rep, SHAPES)
+    rng = np.random.default_rng(23)
+    # unrelated sequences and extreme shapes: several 32-block stripes, one-row / one-column problems, deep recursions
+    for n, m in [(100, 3000), (3000, 100), (1, 5000), (5000, 1), (2500, 2500), (300, 9000), (9000, 300), (4200, 130),
+                 (7000, 7500)]:
+        pairs.append((rng.choice(ACGT, size=n).tobytes(), rng.choice(ACGT, size=m).tobytes()))
+    q, t = random_pairs(29, [(1200, 0.1)])[0]  # bytes outside ACGT equal only themselves (edlib's alphabet)
+    qa, ta = bytearray(q), bytearray(t)
+    for k in range(0, len(qa), 37):
+        qa[k] = ord("N")
+    for k in range(5, len(ta), 41):
+        ta[k] = ord("N") if k % 2 else ord("R")
+    pairs.append((bytes(qa), bytes(ta)))
+    return pairs
+
+
+@pytest.fixture(scope="module")
+def aligner():
+    from racon_gpu_b200.aligner import CUDABatchAligner
+    a = CUDABatchAligner(device_id=0, max_gpu_memory=8 << 30)
+    yield a
+    a.close()
+
+
+def test_random_pairs_equal_the_oracle(oracle, aligner):
+    pairs = _pairs()
+    aligner.reset()
+    for q, t in pairs:
+        assert aligner.add_overlap(q, t)
+    aligner.align_all()
+    got = aligner.generate_cigar_strings()
+    info = aligner.info()
+    assert info["levels"] >= 2 and info["n_leaves"] >= len(pairs) and info["kernel_launches"] == info["levels"] + 2
+    for k, (q, t) in enumerate(pairs):
+        ops, score = oracle_align(oracle, q, t)
+        cigar, ed = got[k]
+        assert ed == score, (k, len(q), len(t))
+        mine = aligner.ops(k)
+        assert mine.shape == ops.shape and (mine == ops).all(), (k, len(q), len(t))
+        assert cigar == ops_to_cigar(oracle, ops)
+    aligner.reset()
+
+
+def test_real_lambda_overlaps_equal_unmodified_edlib(aligner):
+    """All 181 overlaps of /root/reference/test/data/sample_overlaps.paf.gz, cut like src/overlap.cpp:186-199."""
+    fx = overlap_fixture()
+    aligner.reset()
+    for f in fx:
+        assert aligner.add_overlap(f["q"], f["t"])
+    aligner.align_all()
+    got = aligner.generate_cigar_strings()
+    assert len(got) == len(fx) == 181
+    for k, f in enumerate(fx):
+        cigar, ed = got[k]
+        assert ed == f["score"], k
+        assert hashlib.sha256(cigar).hexdigest() == f["cigar_sha"], k
+        assert aligner.ops(k).shape[0] == f["n_ops"]
+    aligner.reset()
+
+
+def test_full_batch_is_back_pressure_not_an_error(oracle):
+    """Aligner::add_alignment -> exceeded_max_alignments => addOverlap returns false (cudaaligner.cpp:64-67); the
+    caller aligns, resets and goes on (cudapolisher.cpp:139-174).  Results do not depend on the batching."""
+    from racon_gpu_b200.aligner import CUDABatchAligner, pack_pairs, align_pairs
+    pairs = random_pairs(77, [(3000, 0.12)] * 40 + [(800, 0.2)] * 40)
+    small = CUDABatchAligner(device_id=0, max_gpu_memory=4 << 20)  # two slots + about forty of these pairs
+    out, rounds, k = [], 0, 0
+    while k < len(pairs):
+        while k < len(pairs) and small.add_overlap(*pairs[k]):
+            k += 1
+        assert small.has_overlaps()
+        small.align_all()
+        out += small.generate_cigar_strings()
+        small.reset()
+        rounds += 1
+    small.close()
+    assert rounds >= 2 and len(out) == len(pairs)
+    ed, cigars, coff, info = align_pairs(*pack_pairs(pairs), device_id=0, max_gpu_memory=2 << 30)
+    for i, (q, t) in enumerate(pairs):
+        ops, score = oracle_align(oracle, q, t)
+        want = ops_to_cigar(oracle, ops)
+        assert out[i] == (want, score)
+        assert ed[i] == score and cigars[coff[i]:coff[i + 1] - 1].tobytes() == want
+    assert info["cells"] > 0 and info["kernel_ms"] > 0
+
+
+def test_live_against_the_unmodified_edlib(ref, aligner):
+    if not ref.available:
+        pytest.skip("oracle/_ref not built (no /root/reference where it was built)")
+    pairs = random_pairs(901, [(6000, 0.14), (2500, 0.3), (1900, 0.05), (64, 0.3)])
+    aligner.reset()
+    for q, t in pairs:
+        assert aligner.add_overlap(q, t)
+    aligner.align_all()
+    got = aligner.generate_cigar_strings()
+    for k, (q, t) in enumerate(pairs):
+        ops, score, cigar = ref_align(ref, q, t)
+        assert got[k] == (cigar, score)
+        assert (aligner.ops(k) == ops).all()
+    aligner.reset()
+
+
+def test_argument_and_state_errors(aligner):
+    from racon_gpu_b200 import aligner as A
+    aligner.reset()
+    lib = aligner.lib
+    assert lib.b200aln_batch_sync(aligner.h) == A.UNINITIALIZED  # nothing aligned yet
+    assert lib.b200aln_batch_add_alignment(aligner.h, None, 5, b"ACGT", 4) == A.INVALID_ARGUMENT
+    assert lib.b200aln_batch_add_alignment(aligner.h, b"ACGT", -1, b"ACGT", 4) == A.INVALID_ARGUMENT
+    aligner.align_all()  # an empty batch aligns to nothing
+    assert aligner.generate_cigar_strings() == []
+    aligner.reset()
+    assert aligner.add_overlap(b"ACGT", b"")  # degenerate pairs: all insertions / all deletions / identical
+    assert aligner.add_overlap(b"", b"ACG")
+    assert aligner.add_overlap(b"ACGTACGT", b"ACGTACGT")
+    aligner.align_all()
+    assert aligner.generate_cigar_strings() == [(b"4I", 4), (b"3D", 3), (b"8M", 0)]
+    aligner.reset()
