@@ -64,8 +64,14 @@ int32_t b200aln_batch_create(int32_t device_id, void* stream, int64_t max_gpu_me
 int32_t b200aln_batch_add_alignment(b200aln_batch* b, const char* query, int32_t query_length, const char* target,
                                     int32_t target_length);
 
+/* Columnar form of add_alignment for callers that hold their segments back to back (pair k = q_bases[q_off[k] ..
+ * q_off[k + 1]) against t_bases[t_off[k] .. t_off[k + 1])): adds pairs 0, 1, .. until the batch is full; *n_added says
+ * how many went in (B200ALN_SUCCESS if at least one did, or n == 0). */
+int32_t b200aln_batch_add_alignments(b200aln_batch* b, int64_t n, const uint8_t* q_bases, const int64_t* q_off,
+                                     const uint8_t* t_bases, const int64_t* t_off, int64_t* n_added);
+
 /* Aligner::align_all() (aligner.hpp:56): upload, the level-synchronous Hirschberg recursion, the leaf tracebacks, run
- * formation, and the asynchronous download of the compact results. */
+ * and CIGAR formation on the device, and the asynchronous download of the compact results (the CIGAR bytes). */
 int32_t b200aln_batch_align_all(b200aln_batch* b);
 
 /* Aligner::sync_alignments() (aligner.hpp:62): blocks until the results are on the host. */
@@ -76,9 +82,16 @@ int32_t b200aln_batch_num_alignments(const b200aln_batch* b);
 
 /* One alignment after sync (Alignment::get_status / get_edit_distance / get_alignment, alignment.hpp:87-101).
  * *runs points at n_runs words `start << 2 | op` -- run k covers operations [start_k, start_{k+1}) and the last one ends
- * at *n_ops; valid until reset/destroy.  Any out pointer may be NULL. */
+ * at *n_ops; valid until reset/destroy.  Any out pointer may be NULL; asking for `runs` fetches the batch's run starts
+ * from the device on first use (racon only needs the CIGARs, which align_all already brought back). */
 int32_t b200aln_batch_get_alignment(const b200aln_batch* b, int32_t index, const uint32_t** runs, int32_t* n_runs,
                                     int32_t* n_ops, int32_t* edit_distance, int32_t* status);
+
+/* All CIGARs of the batch after sync, in place (what CUDABatchAligner::generate_cigar_strings walks,
+ * cudaaligner.cpp:88-103): alignment k's string is text[off[k] .. off[k] + len[k]) followed by a 0; edit_distance[k],
+ * status[k] per alignment.  Valid until reset/destroy; any out pointer may be NULL. */
+int32_t b200aln_batch_get_cigars(const b200aln_batch* b, const char** text, const int64_t** off, const int32_t** len,
+                                 const int32_t** edit_distance, const int32_t** status);
 
 /* Alignment::convert_to_cigar() (alignment.hpp:72) in edlib's EDLIB_CIGAR_STANDARD spelling ("12M1I3M2D...").
  * Returns the string's length (without the terminating 0); writes at most cap bytes including the 0; out may be NULL

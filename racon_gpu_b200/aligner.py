@@ -17,7 +17,7 @@ ALN_ABI_SYMBOLS = (
     "b200aln_init", "b200aln_batch_create", "b200aln_batch_add_alignment", "b200aln_batch_align_all",
     "b200aln_batch_sync", "b200aln_batch_num_alignments", "b200aln_batch_get_alignment", "b200aln_batch_get_cigar",
     "b200aln_batch_get_ops", "b200aln_batch_reset", "b200aln_batch_destroy", "b200aln_batch_get_info",
-    "b200aln_status_string", "b200aln_align_pairs",
+    "b200aln_status_string", "b200aln_align_pairs", "b200aln_batch_add_alignments", "b200aln_batch_get_cigars",
 )
 
 SUCCESS, UNINITIALIZED, EXCEEDED_MAX_ALIGNMENTS, EXCEEDED_MAX_LENGTH = 0, 1, 2, 3
@@ -80,6 +80,36 @@ class CUDABatchAligner:
         if st != SUCCESS:
             raise RuntimeError(f"b200aln_batch_add_alignment: {status_string(st)}")
         return True
+
+    def add_overlaps(self, q: np.ndarray, q_off: np.ndarray, t: np.ndarray, t_off: np.ndarray, first: int = 0) -> int:
+        """b200aln_batch_add_alignments from pair `first` on: how many went in before the batch was full."""
+        n = len(q_off) - 1 - first
+        added = C.c_int64(0)
+        p = lambda a, ty: a.ctypes.data_as(C.POINTER(ty))
+        st = self.lib.b200aln_batch_add_alignments(self.h, C.c_int64(n), p(q, C.c_uint8), p(q_off[first:], C.c_int64),
+                                                   p(t, C.c_uint8), p(t_off[first:], C.c_int64), C.byref(added))
+        if st != SUCCESS:
+            raise RuntimeError(f"b200aln_batch_add_alignments: {status_string(st)}")
+        return int(added.value)
+
+    def cigars(self):
+        """b200aln_batch_get_cigars after sync: (text bytes view, off int64[n], len int32[n], edit distance int32[n])."""
+        st = self.lib.b200aln_batch_sync(self.h)
+        if st != SUCCESS:
+            raise RuntimeError(f"b200aln_batch_sync: {status_string(st)}")
+        n = self.lib.b200aln_batch_num_alignments(self.h)
+        text, off, ln, ed, ast = C.c_void_p(), C.POINTER(C.c_int64)(), C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)()
+        self.lib.b200aln_batch_get_cigars(self.h, C.byref(text), C.byref(off), C.byref(ln), C.byref(ed), C.byref(ast))
+        if n == 0:
+            return b"", np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros(0, np.int32)
+        off_a = np.ctypeslib.as_array(off, shape=(n,)).copy()
+        len_a = np.ctypeslib.as_array(ln, shape=(n,)).copy()
+        ed_a = np.ctypeslib.as_array(ed, shape=(n,)).copy()
+        st_a = np.ctypeslib.as_array(ast, shape=(n,))
+        if (st_a != SUCCESS).any():
+            raise RuntimeError(f"alignment {int(np.flatnonzero(st_a != SUCCESS)[0])}: {status_string(int(st_a[st_a != SUCCESS][0]))}")
+        total = int((off_a + len_a).max()) + 1
+        return C.string_at(text, total), off_a, len_a, ed_a
 
     def has_overlaps(self) -> bool:
         return self.lib.b200aln_batch_num_alignments(self.h) > 0

@@ -40,6 +40,7 @@ using b200poa::poa_uniform;
 using b200poa::poa_uniform_pred;
 using b200poa::warp_ballot;
 using b200poa::warp_bcast0;
+using b200poa::warp_exscan;
 using b200poa::warp_get;
 using b200poa::warp_min;
 using b200poa::warp_shift_up1;
@@ -84,14 +85,19 @@ struct AlnLists {
     int32_t* overflow;
 };
 
+/* one leaf record: the vertical deltas of a 64-row block after a column (+1 bits, -1 bits) */
+struct alignas(16) RecPM {
+    uint64_t p, m;
+};
+
 /* per resident warp workspace */
 struct AlnSlot {
-    int8_t* hbuf;  /* [max_len + 64]  horizontal deltas of the row between two stripes */
-    int32_t* Lc;   /* [max_len + 2]   last column of the forward pass:  Lc[i] = D(q[0..i), left half)        */
-    int32_t* Rr;   /* [max_len + 2]   last column of the backward pass: Rr[i] = D(q[n-i..n), right half)    */
-    uint64_t* P;   /* [leaf entries]  leaf records in wavefront order, see leaf_entry() */
-    uint64_t* M;
-    int32_t* S;
+    uint8_t* hbuf;  /* [max_len + 64]   horizontal deltas (code: 1 = +1, 2 = -1, 0) of the row between two stripes   */
+    uint8_t* tcode; /* [max_len + 192]  the pass's target as codes 0..3 = ACGT, 4 = other; 64 bytes of padding in front */
+    int32_t* Lc;    /* [max_len + 2]    last column of the forward pass:  Lc[i] = D(q[0..i), left half)              */
+    int32_t* Rr;    /* [max_len + 2]    last column of the backward pass: Rr[i] = D(q[n-i..n), right half)          */
+    RecPM* PM;      /* [leaf entries]   leaf records in wavefront order, see leaf_entry()                            */
+    int32_t* S;     /* [leaf entries]   score under the block's last row                                             */
 };
 ALN_HD int64_t aln_leaf_entries(int32_t max_len) { return ALN_LEAF_DATA_LIMIT / 20 + 31 * (int64_t)((max_len + 63) / 64) + 64; }
 ALN_HD void aln_slot_bind(AlnSlot& s, uint8_t* base, int32_t max_len, size_t* total_out) {
@@ -103,15 +109,42 @@ ALN_HD void aln_slot_bind(AlnSlot& s, uint8_t* base, int32_t max_len, size_t* to
         s.field = base ? reinterpret_cast<type*>(base + o) : nullptr;  \
         o += sizeof(type) * (size_t)(count);                           \
     } while (0)
-    ALN_CARVE(hbuf, int8_t, (size_t)max_len + 64);
+    ALN_CARVE(hbuf, uint8_t, (size_t)max_len + 64);
+    ALN_CARVE(tcode, uint8_t, (size_t)max_len + 192);
     ALN_CARVE(Lc, int32_t, (size_t)max_len + 2);
     ALN_CARVE(Rr, int32_t, (size_t)max_len + 2);
-    ALN_CARVE(P, uint64_t, E);
-    ALN_CARVE(M, uint64_t, E);
+    ALN_CARVE(PM, RecPM, E);
     ALN_CARVE(S, int32_t, E);
 #undef ALN_CARVE
     o = (o + 255) / 256 * 256;
     if (total_out) *total_out = o;
+}
+
+/* The match masks of a lane's block, one 64-bit word per character code, looked up once per column: shared memory on
+ * the device (one LDS instead of a chain of selects; [5][32] words per warp), a plain array in the emulation. */
+#define ALN_EQ_WORDS (5 * 32)
+struct EqTab {
+#if POA_DEVICE
+    uint32_t sa; /* shared-memory address of this warp's table */
+#else
+    uint64_t v[ALN_EQ_WORDS];
+#endif
+};
+POA_FN void eq_store(EqTab& t, int code, int lane, uint64_t x) {
+#if POA_DEVICE
+    asm volatile("st.shared.u64 [%0], %1;" ::"r"(t.sa + (uint32_t)(code * 32 + lane) * 8u), "l"(x) : "memory");
+#else
+    t.v[code * 32 + lane] = x;
+#endif
+}
+POA_FN uint64_t eq_load(const EqTab& t, int code, int lane) {
+#if POA_DEVICE
+    uint64_t x;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(x) : "r"(t.sa + (uint32_t)(code * 32 + lane) * 8u) : "memory");
+    return x;
+#else
+    return t.v[code * 32 + lane];
+#endif
 }
 
 POA_FN int32_t aln_take(int32_t* counter) { /* called by ONE lane */
@@ -145,6 +178,16 @@ struct SeqView {
 };
 POA_FN uint8_t seq_at(const SeqView s, int32_t k) { return s.p[(int64_t)k * s.step]; }
 
+/* a byte of the slot / the sequence arena (global memory, written earlier by this warp: a coherent load) */
+POA_FN int glb_u8(const uint8_t* p) {
+#if POA_DEVICE
+    unsigned v;
+    asm volatile("ld.global.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return (int)v;
+#else
+    return (int)*p;
+#endif
+}
 POA_FN int aln_popc64(uint64_t x) {
 #if POA_DEVICE
     return __popcll(x);
@@ -164,29 +207,52 @@ POA_FN int64_t leaf_entry(int32_t b, int32_t j, int32_t B, int32_t cols) {
     return (int64_t)s0 * (cols + 31) + (int64_t)(j + l) * nb + l;
 }
 
+/* a character that is none of ACGT equals only itself (edlib's alphabet is the set of bytes seen): rare */
+POA_FN uint64_t eq_other(const SeqView q, int32_t row0, int32_t cnt, int tc) {
+    uint64_t Eq = 0;
+    for (int32_t k = 0; k < cnt; ++k)
+        if ((int)seq_at(q, row0 + k) == tc) Eq |= (uint64_t)1 << k;
+    return Eq;
+}
+
 /*
  * One bit-vector pass: the distance matrix of q[0..n) against t[0..cols), boundary D[i][0] = i, D[0][j] = j.
  *   out_col (nullable): receives the last column, out_col[i] = D[i][cols], i = 0..n
- *   P/M/S   (nullable): receive the record of every (block, column), leaf_entry() order
+ *   PM / S  (nullable): receive the record of every (block, column), leaf_entry() order
  * Myers' block recurrence in Hyyro's formulation (64 rows per word): with Pv/Mv the +1/-1 vertical deltas of the previous
  * column, Eq the rows whose character equals the column's and hin the horizontal delta entering from above,
  *   Xv = Eq | Mv;  Eq |= (hin < 0);  Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;  Ph = Mv | ~(Xh | Pv);  Mh = Pv & Xh;
  *   hout = bit63(Ph) - bit63(Mh);  Ph = Ph << 1 | (hin > 0);  Mh = Mh << 1 | (hin < 0);
  *   Pv' = Mh | ~(Xv | Ph);  Mv' = Ph & Xv.
+ * Wavefront: lane l owns block s0 + l and works on column (step - l); what crosses lanes is the 2-bit delta code
+ * (1 = +1, 2 = -1) of the block's last row, one shuffle per step -- the only thing on the step's dependency chain.
+ * The column's character code comes straight from the slot's code row (loaded one step ahead), its match mask from the
+ * lane's shared-memory table.
  */
-POA_FN_NOINLINE void myers_pass(const SeqView q, int32_t n, const SeqView t, int32_t cols, int8_t* hbuf, int32_t* out_col,
-                                uint64_t* P, uint64_t* M, int32_t* S) {
+POA_FN_NOINLINE void myers_pass(const SeqView q, int32_t n, const SeqView t, int32_t cols, uint8_t* hbuf, uint8_t* tcode_base,
+                                const EqTab eq_in, int32_t* out_col, RecPM* PM, int32_t* S) {
     n = poa_uniform(n);
     cols = poa_uniform(cols);
+    EqTab eq = eq_in; /* by value: a reference would live in local memory and be re-read every step */
     const int32_t B = (n + 63) / 64;
+    uint8_t* tcode = tcode_base + 64; /* tcode[-64 .. cols + 63] may be read (by lanes whose column is out of range) */
+    for (int32_t base = -64; base < cols + 64; base += 32) {
+        POA_LANES(l) {
+            const int32_t c = base + l;
+            tcode[c] = (c >= 0 && c < cols) ? (uint8_t)aln_code(seq_at(t, c)) : (uint8_t)0;
+        }
+    }
     if (out_col) {
         POA_LANE0 { out_col[0] = cols; }
     }
+    POA_SYNC();
+    POA_FENCE();
     for (int32_t s0 = 0; s0 < B; s0 += 32) {
         const int32_t nb = B - s0 < 32 ? B - s0 : 32;
         const bool more = s0 + 32 < B; /* another stripe follows: the last lane's horizontal deltas are kept */
-        PerLane<uint64_t> Pv, Mv, E0, E1, E2, E3;
-        PerLane<int> bot, link, tcur, tnext, hcur, hnext;
+        const bool lower = s0 > 0;     /* lane 0 enters with the deltas the stripe above left behind */
+        PerLane<uint64_t> Pv, Mv;
+        PerLane<int> bot, link, tc_next, h_next;
         POA_LANES(l) {
             const int32_t b = s0 + l;
             uint64_t e0 = 0, e1 = 0, e2 = 0, e3 = 0;
@@ -202,81 +268,57 @@ POA_FN_NOINLINE void myers_pass(const SeqView q, int32_t n, const SeqView t, int
                     else if (c == 3) e3 |= bit;
                 }
             }
-            E0[l] = e0;
-            E1[l] = e1;
-            E2[l] = e2;
-            E3[l] = e3;
+            eq_store(eq, 0, l, e0);
+            eq_store(eq, 1, l, e1);
+            eq_store(eq, 2, l, e2);
+            eq_store(eq, 3, l, e3);
+            eq_store(eq, 4, l, 0);
             Pv[l] = ~(uint64_t)0;
             Mv[l] = 0;
             bot[l] = 64 * (b + 1);
             link[l] = 0;
-            /* the column stream (target character, entering delta) is fetched 32 columns at a time, one per lane, a block
-             * ahead, and handed to lane 0 by a shuffle */
-            tcur[l] = l < cols ? (int)seq_at(t, l) : 0;
-            tnext[l] = 32 + l < cols ? (int)seq_at(t, 32 + l) : 0;
-            hcur[l] = (s0 > 0 && l < cols) ? (int)hbuf[l] : 1;
-            hnext[l] = (s0 > 0 && 32 + l < cols) ? (int)hbuf[32 + l] : 1;
+            tc_next[l] = glb_u8(tcode - l);
+            h_next[l] = (lower && l == 0) ? glb_u8(hbuf) : 1;
         }
+        POA_SYNC();
         const int32_t steps = cols + nb - 1;
         for (int32_t step = 0; step < steps; ++step) {
-            if (step > 0 && (step & 31) == 0) {
-                POA_LANES(l) {
-                    tcur[l] = tnext[l];
-                    hcur[l] = hnext[l];
-                    const int32_t c = step + 32 + l;
-                    tnext[l] = c < cols ? (int)seq_at(t, c) : 0;
-                    hnext[l] = (s0 > 0 && c < cols) ? (int)hbuf[c] : 1;
-                }
-            }
-            const int tch0 = warp_get(tcur, step & 31);
-            const int hin0 = warp_get(hcur, step & 31);
             PerLane<int> in;
-            warp_shift_up1(link, in); /* in[l] = what lane l - 1 produced in the previous step */
+            warp_shift_up1(link, in); /* in[l] = the delta code lane l - 1 produced in the previous step */
             POA_LANES(l) {
-                const int32_t j = step - l;
-                int v = in[l];
-                if (l == 0) v = step < cols ? ((hin0 + 1) | (tch0 << 8) | 0x10000) : 0;
-                int nl = 0;
-                if (l < nb && (v & 0x10000)) { /* lane l works on column j = step - l */
-                    const int hin = (v & 0xFF) - 1;
-                    const int tc = (v >> 8) & 0xFF;
+                const int32_t c = step - l;
+                const int code = tc_next[l];
+                const int hcode = l == 0 ? h_next[l] : in[l];
+                tc_next[l] = glb_u8(tcode + (c + 1)); /* next step's column, a step ahead of its use */
+                if (lower && l == 0) h_next[l] = glb_u8(hbuf + (step + 1));
+                if (l < nb && (uint32_t)c < (uint32_t)cols) { /* lane l works on column c */
                     uint64_t Eq;
-                    if (tc == 'A') Eq = E0[l];
-                    else if (tc == 'C') Eq = E1[l];
-                    else if (tc == 'G') Eq = E2[l];
-                    else if (tc == 'T') Eq = E3[l];
-                    else { /* any other character equals only itself (edlib's alphabet is the set of bytes seen) */
-                        Eq = 0;
-                        const int32_t row0 = 64 * (s0 + l);
-                        const int32_t cnt = n - row0 < 64 ? n - row0 : 64;
-                        for (int32_t k = 0; k < cnt; ++k)
-                            if ((int)seq_at(q, row0 + k) == tc) Eq |= (uint64_t)1 << k;
-                    }
+                    if (code < 4) Eq = eq_load(eq, code, l);
+                    else Eq = eq_other(q, 64 * (s0 + l), n - 64 * (s0 + l) < 64 ? n - 64 * (s0 + l) : 64, (int)seq_at(t, c));
                     const uint64_t pv = Pv[l], mv = Mv[l];
-                    const uint64_t neg = hin < 0 ? 1u : 0u, pos = hin > 0 ? 1u : 0u;
+                    const uint64_t pos = (uint64_t)(hcode & 1), neg = (uint64_t)((hcode >> 1) & 1);
                     const uint64_t Xv = Eq | mv;
                     const uint64_t Eh = Eq | neg;
                     const uint64_t Xh = (((Eh & pv) + pv) ^ pv) | Eh;
                     uint64_t Ph = mv | ~(Xh | pv);
                     uint64_t Mh = pv & Xh;
-                    const int hout = (int)(Ph >> 63) - (int)(Mh >> 63);
+                    const int ph63 = (int)(Ph >> 63), mh63 = (int)(Mh >> 63);
                     Ph = (Ph << 1) | pos;
                     Mh = (Mh << 1) | neg;
                     const uint64_t npv = Mh | ~(Xv | Ph);
                     const uint64_t nmv = Ph & Xv;
                     Pv[l] = npv;
                     Mv[l] = nmv;
-                    bot[l] = bot[l] + hout;
-                    if (P) {
+                    bot[l] = bot[l] + ph63 - mh63;
+                    const int out = ph63 | (mh63 << 1);
+                    if (PM) {
                         const int64_t e = (int64_t)s0 * (cols + 31) + (int64_t)step * nb + l;
-                        P[e] = npv;
-                        M[e] = nmv;
+                        PM[e] = RecPM{npv, nmv};
                         S[e] = bot[l];
                     }
-                    if (more && l == 31) hbuf[j] = (int8_t)hout; /* column j was consumed by lane 0 at step j <= step */
-                    nl = (hout + 1) | (tc << 8) | 0x10000;
+                    if (more && l == 31) hbuf[c] = (uint8_t)out; /* column c was consumed by lane 0 at step c <= step */
+                    link[l] = out;
                 }
-                link[l] = nl;
             }
         }
         if (out_col) { /* the last column, row by row: D = (score above the block) + running sum of the vertical deltas */
@@ -294,20 +336,21 @@ POA_FN_NOINLINE void myers_pass(const SeqView q, int32_t n, const SeqView t, int
             }
         }
         POA_SYNC();
-        POA_FENCE(); /* hbuf / out_col written by one lane are read by others next */
+        POA_FENCE(); /* hbuf / out_col written by one lane are read by others next; the Eq table is rebuilt */
     }
 }
 
 /* ------------------------------------------------------------------------------------------
  * One Hirschberg step (edlib.cpp:1198-1344)
  * ---------------------------------------------------------------------------------------- */
-POA_FN_NOINLINE void aln_split(const AlnSlot& s_ref, const uint8_t* q, const uint8_t* t, int32_t n, int32_t m, AlnSplit* out) {
+POA_FN_NOINLINE void aln_split(const AlnSlot& s_ref, EqTab& eq, const uint8_t* q, const uint8_t* t, int32_t n, int32_t m,
+                               AlnSplit* out) {
     const AlnSlot s = s_ref;
     n = poa_uniform(n);
     m = poa_uniform(m);
     const int32_t lh = m / 2, rh = m - lh; /* edlib.cpp:1216-1217 */
-    myers_pass(SeqView{q, 1}, n, SeqView{t, 1}, lh, s.hbuf, s.Lc, nullptr, nullptr, nullptr);
-    myers_pass(SeqView{q + (n - 1), -1}, n, SeqView{t + (m - 1), -1}, rh, s.hbuf, s.Rr, nullptr, nullptr, nullptr);
+    myers_pass(SeqView{q, 1}, n, SeqView{t, 1}, lh, s.hbuf, s.tcode, eq, s.Lc, nullptr, nullptr);
+    myers_pass(SeqView{q + (n - 1), -1}, n, SeqView{t + (m - 1), -1}, rh, s.hbuf, s.tcode, eq, s.Rr, nullptr, nullptr);
     /* the optimum of the sub-problem is the smallest left + right sum over all crossing points of the middle */
     PerLane<int> acc;
     POA_LANES(l) { acc[l] = 0x7FFFFFFF; }
@@ -383,8 +426,9 @@ POA_FN void leaf_window_load(const AlnSlot& s, LeafWindow& w, int32_t b, int32_t
         int sc = 0;
         if (c >= 0) {
             const int64_t e = leaf_entry(b, c, B, cols);
-            p = s.P[e];
-            m = s.M[e];
+            const RecPM r = s.PM[e];
+            p = r.p;
+            m = r.m;
             sc = s.S[e];
         }
         w.P[l] = p;
@@ -402,8 +446,8 @@ POA_FN void leaf_window_load(const AlnSlot& s, LeafWindow& w, int32_t b, int32_t
  *   diagonal  = left - bit_k(Pl) + bit_k(Ml)
  * so a step costs no memory access; a new window is loaded every 31 columns or when the path enters the block above.
  */
-POA_FN_NOINLINE void aln_leaf(const AlnSlot& s_ref, const uint8_t* q, const uint8_t* t, int32_t n, int32_t m, uint8_t* ops,
-                              int32_t* score_out) {
+POA_FN_NOINLINE void aln_leaf(const AlnSlot& s_ref, EqTab& eq, const uint8_t* q, const uint8_t* t, int32_t n, int32_t m,
+                              uint8_t* ops, int32_t* score_out) {
     const AlnSlot s = s_ref;
     n = poa_uniform(n);
     m = poa_uniform(m);
@@ -421,7 +465,7 @@ POA_FN_NOINLINE void aln_leaf(const AlnSlot& s_ref, const uint8_t* q, const uint
         POA_SYNC();
         return;
     }
-    myers_pass(SeqView{q, 1}, n, SeqView{t, 1}, m, s.hbuf, nullptr, s.P, s.M, s.S);
+    myers_pass(SeqView{q, 1}, n, SeqView{t, 1}, m, s.hbuf, s.tcode, eq, nullptr, s.PM, s.S);
     const int32_t B = (n + 63) / 64;
     LeafWindow win;
     int32_t i = n - 1, j = m - 1, jw = j;
@@ -515,7 +559,7 @@ POA_FN int aln_fls(unsigned x) { /* index of the highest set bit, x != 0 */
     return 31 - __builtin_clz(x);
 #endif
 }
-POA_FN_NOINLINE int32_t aln_runs(const uint8_t* ops, int32_t len, uint32_t* runs, int32_t* n_ops_out) {
+POA_FN_NOINLINE int32_t aln_runs(const uint8_t* ops, int32_t len, uint32_t* runs, int32_t& n_ops_out) {
     len = poa_uniform(len);
     int32_t n_runs = 0, n_valid = 0, carry = 4; /* carry: the last operation seen, 4 = none yet */
     for (int32_t base = 0; base < len; base += 32) {
@@ -555,11 +599,90 @@ POA_FN_NOINLINE int32_t aln_runs(const uint8_t* ops, int32_t len, uint32_t* runs
         const int p = aln_fls(valid);
         carry = (int)((m0 >> p) & 1u) | (int)(((m1 >> p) & 1u) << 1);
     }
-    if (n_ops_out) {
-        POA_LANE0 { *n_ops_out = n_valid; }
+    n_ops_out = n_valid;
+    POA_SYNC();
+    POA_FENCE(); /* the run starts are read by other lanes next (aln_cigar_text) */
+    return n_runs;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Run starts -> CIGAR text, on the device: edlibAlignmentToCigar(EDLIB_CIGAR_STANDARD) (edlib.cpp:1482-1520) spells
+ * match and mismatch 'M', a query character alone 'I', a target character alone 'D', each maximal run as <length><letter>.
+ * Returns the number of bytes (no terminator); out nullable (count only).  32 run starts per round: a start whose
+ * letter differs from its predecessor's closes the run opened before it; lengths come from the neighbouring start.
+ * ---------------------------------------------------------------------------------------- */
+POA_FN void warp_gather(const PerLane<int>& x, const PerLane<int>& src, PerLane<int>& out) {
+#if POA_DEVICE
+    out.v = __shfl_sync(0xffffffffu, x.v, src.v);
+#else
+    for (int l = 0; l < 32; ++l) out.v[l] = x.v[src.v[l]];
+#endif
+}
+POA_FN int aln_ndigits(int32_t v) {
+    int d = 1;
+    for (int32_t p = 10; d < 10 && v >= p; p *= 10) ++d;
+    return d;
+}
+POA_FN void aln_write_run(uint8_t* out, int32_t len, int nd, int cls) {
+    for (int k = nd - 1; k >= 0; --k) {
+        out[k] = (uint8_t)('0' + len % 10);
+        len /= 10;
+    }
+    out[nd] = cls == 1 ? (uint8_t)'I' : cls == 2 ? (uint8_t)'D' : (uint8_t)'M';
+}
+POA_FN_NOINLINE int32_t aln_cigar_text(const uint32_t* runs, int32_t n_runs, int32_t n_ops, uint8_t* out) {
+    n_runs = poa_uniform(n_runs);
+    n_ops = poa_uniform(n_ops);
+    int32_t bytes = 0, open_start = 0, open_cls = -1; /* the letter run that is open: where it starts, its class */
+    for (int32_t base = 0; base < n_runs; base += 32) {
+        PerLane<int> st, cl, prevc, flag, src, pst, pcl, nb;
+        POA_LANES(l) {
+            const int32_t k = base + l;
+            const uint32_t r = k < n_runs ? runs[k] : 0u;
+            const int c = (int)(r & 3u);
+            st[l] = (int)(r >> 2);
+            cl[l] = k < n_runs ? (c == 1 ? 1 : c == 2 ? 2 : 0) : 3;
+        }
+        warp_shift_up1(cl, prevc);
+        POA_LANES(l) { flag[l] = cl[l] != 3 && cl[l] != (l == 0 ? open_cls : prevc[l]); }
+        const unsigned mask = warp_ballot(flag);
+        if (mask == 0) continue;
+        POA_LANES(l) {
+            const unsigned under = mask & ((1u << l) - 1u);
+            src[l] = under ? aln_fls(under) : l;
+        }
+        warp_gather(st, src, pst);
+        warp_gather(cl, src, pcl);
+        PerLane<int> len, cls;
+        POA_LANES(l) {
+            const unsigned under = mask & ((1u << l) - 1u);
+            const int32_t s0 = under ? pst[l] : open_start;
+            cls[l] = under ? pcl[l] : open_cls;
+            len[l] = st[l] - s0;
+            nb[l] = (flag[l] && cls[l] >= 0) ? aln_ndigits(len[l]) + 1 : 0;
+        }
+        PerLane<int> off = nb;
+        const int32_t total = warp_exscan(off);
+        if (out) {
+            POA_LANES(l) {
+                if (nb[l]) aln_write_run(out + bytes + off[l], len[l], nb[l] - 1, cls[l]);
+            }
+        }
+        bytes += total;
+        const int p = aln_fls(mask);
+        open_start = warp_get(st, p);
+        open_cls = warp_get(cl, p);
+    }
+    if (open_cls >= 0) {
+        const int32_t len = n_ops - open_start;
+        const int nd = aln_ndigits(len);
+        if (out) {
+            POA_LANE0 { aln_write_run(out + bytes, len, nd, open_cls); }
+        }
+        bytes += nd + 1;
     }
     POA_SYNC();
-    return n_runs;
+    return bytes;
 }
 
 } // namespace b200aln

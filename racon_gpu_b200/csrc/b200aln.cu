@@ -37,7 +37,10 @@ struct AlnJob { /* one alignment of the batch */
 };
 struct AlnResult {
     int32_t score, status, n_runs, n_ops;
-    int64_t runs_off;
+    int64_t runs_off;  /* into the runs arena (words)  */
+    int64_t cigar_off; /* into the text arena (bytes)  */
+    int32_t cigar_len; /* without the terminating 0    */
+    int32_t pad;
 };
 
 enum { /* int32 words of the device counter block */
@@ -47,6 +50,7 @@ enum { /* int32 words of the device counter block */
     CT_OVERFLOW = 129,
     CT_RUNS = 130,      /* u64: entries used in the runs arena                               */
     CT_CELLS = 132,     /* u64: distance-matrix cells computed                               */
+    CT_TEXT = 134,      /* u64: bytes used in the CIGAR text arena                           */
     CT_WORDS = 136,
     MAX_LEVELS = 60
 };
@@ -63,10 +67,16 @@ struct AlnKernelArgs {
 };
 
 constexpr int WARPS_PER_BLOCK = 2;
+#ifndef ALN_MIN_BLOCKS
+#define ALN_MIN_BLOCKS 16 /* 32 warps per SM => at most 64 registers per thread */
+#endif
 
 __device__ __forceinline__ void bind_slot(const AlnKernelArgs& a, AlnSlot& s) {
     const size_t slot = (size_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     aln_slot_bind(s, a.slab + slot * a.slot_bytes, a.max_len, nullptr);
+}
+__device__ __forceinline__ void bind_eq(EqTab& eq, uint64_t* tab) {
+    eq.sa = (uint32_t)__cvta_generic_to_shared(tab + (threadIdx.x >> 5) * ALN_EQ_WORDS);
 }
 __device__ __forceinline__ int32_t take_work(int32_t* cursor) {
     int32_t t = 0;
@@ -75,18 +85,21 @@ __device__ __forceinline__ int32_t take_work(int32_t* cursor) {
 }
 
 /* one Hirschberg level: every open sub-problem is split, its children are filed for the next level or as leaves */
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) aln_split_kernel(const AlnKernelArgs a, const AlnRect* level,
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, ALN_MIN_BLOCKS) aln_split_kernel(const AlnKernelArgs a, const AlnRect* level,
                                                                          int32_t n_level, const AlnLists next,
                                                                          int32_t* cursor) {
+    __shared__ uint64_t eq_tab[WARPS_PER_BLOCK * ALN_EQ_WORDS];
     AlnSlot s;
     bind_slot(a, s);
+    EqTab eq;
+    bind_eq(eq, eq_tab);
     for (;;) {
         const int32_t k = take_work(cursor);
         if (k >= n_level) break;
         const AlnRect r = level[k];
         const AlnJob job = a.jobs[r.aln];
         AlnSplit sp;
-        aln_split(s, a.seq + job.q_off + r.r0, a.seq + job.t_off + r.c0, r.n, r.m, &sp);
+        aln_split(s, eq, a.seq + job.q_off + r.r0, a.seq + job.t_off + r.c0, r.n, r.m, &sp);
         if ((threadIdx.x & 31u) == 0u) {
             if (r.top) a.res[r.aln].score = sp.best;
             AlnRect ul, lr;
@@ -103,16 +116,19 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) aln_split_kernel(const A
 }
 
 /* all leaves of all levels: the matrix as block records, the walk back, operations into the alignment's region */
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) aln_leaf_kernel(const AlnKernelArgs a, const AlnRect* leaves,
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, ALN_MIN_BLOCKS) aln_leaf_kernel(const AlnKernelArgs a, const AlnRect* leaves,
                                                                         int32_t n_leaves, int32_t* cursor) {
+    __shared__ uint64_t eq_tab[WARPS_PER_BLOCK * ALN_EQ_WORDS];
     AlnSlot s;
     bind_slot(a, s);
+    EqTab eq;
+    bind_eq(eq, eq_tab);
     for (;;) {
         const int32_t k = take_work(cursor);
         if (k >= n_leaves) break;
         const AlnRect r = leaves[k];
         const AlnJob job = a.jobs[r.aln];
-        aln_leaf(s, a.seq + job.q_off + r.r0, a.seq + job.t_off + r.c0, r.n, r.m, a.ops + job.ops_off + r.r0 + r.c0,
+        aln_leaf(s, eq, a.seq + job.q_off + r.r0, a.seq + job.t_off + r.c0, r.n, r.m, a.ops + job.ops_off + r.r0 + r.c0,
                  r.top ? &a.res[r.aln].score : nullptr);
         if ((threadIdx.x & 31u) == 0u)
             atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + CT_CELLS), (unsigned long long)r.n * (unsigned long long)r.m);
@@ -120,29 +136,45 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) aln_leaf_kernel(const Al
     }
 }
 
-/* operations -> run starts, bump-allocated into the compact runs arena */
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) aln_runs_kernel(const AlnKernelArgs a, int32_t n_alignments,
-                                                                        uint32_t* runs, unsigned long long runs_cap,
-                                                                        int32_t* cursor) {
+/* operations -> run starts -> CIGAR text, both bump-allocated into compact arenas */
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) aln_cigar_kernel(const AlnKernelArgs a, int32_t n_alignments,
+                                                                         uint32_t* runs, unsigned long long runs_cap,
+                                                                         uint8_t* text, unsigned long long text_cap,
+                                                                         int32_t* cursor) {
+    const bool lane0 = (threadIdx.x & 31u) == 0u;
     for (;;) {
         const int32_t k = take_work(cursor);
         if (k >= n_alignments) break;
         const AlnJob job = a.jobs[k];
         const uint8_t* ops = a.ops + job.ops_off;
-        const int32_t n_runs = aln_runs(ops, job.n + job.m, nullptr, nullptr);
+        int32_t n_ops = 0;
+        const int32_t n_runs = aln_runs(ops, job.n + job.m, nullptr, n_ops);
         unsigned long long off = 0;
-        if ((threadIdx.x & 31u) == 0u)
-            off = atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + CT_RUNS), (unsigned long long)n_runs);
+        if (lane0) off = atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + CT_RUNS), (unsigned long long)n_runs);
         off = __shfl_sync(0xffffffffu, off, 0);
-        if (off + (unsigned long long)n_runs <= runs_cap) {
-            aln_runs(ops, job.n + job.m, runs + off, &a.res[k].n_ops);
-            if ((threadIdx.x & 31u) == 0u) {
-                a.res[k].n_runs = n_runs;
-                a.res[k].runs_off = (int64_t)off;
+        bool ok = off + (unsigned long long)n_runs <= runs_cap;
+        if (ok) {
+            aln_runs(ops, job.n + job.m, runs + off, n_ops);
+            const int32_t bytes = aln_cigar_text(runs + off, n_runs, n_ops, nullptr);
+            unsigned long long toff = 0;
+            if (lane0) toff = atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + CT_TEXT), (unsigned long long)bytes + 1ull);
+            toff = __shfl_sync(0xffffffffu, toff, 0);
+            ok = toff + (unsigned long long)bytes + 1ull <= text_cap;
+            if (ok) {
+                aln_cigar_text(runs + off, n_runs, n_ops, text + toff);
+                if (lane0) {
+                    text[toff + (unsigned long long)bytes] = 0;
+                    AlnResult r = a.res[k];
+                    r.n_runs = n_runs;
+                    r.n_ops = n_ops;
+                    r.runs_off = (int64_t)off;
+                    r.cigar_off = (int64_t)toff;
+                    r.cigar_len = bytes;
+                    a.res[k] = r;
+                }
             }
-        } else if ((threadIdx.x & 31u) == 0u) {
-            a.res[k].status = B200ALN_GENERIC_ERROR;
         }
+        if (!ok && lane0) a.res[k].status = B200ALN_GENERIC_ERROR;
         __syncwarp();
     }
 }
@@ -209,13 +241,17 @@ struct b200aln_batch {
     int64_t var_bytes = 0; /* device bytes the staged alignments need besides the slots */
 
     /* device */
-    DevBuf d_slab, d_seq, d_jobs, d_ops, d_res, d_runs, d_list[2], d_leaves, d_counters;
+    DevBuf d_slab, d_seq, d_jobs, d_ops, d_res, d_runs, d_text, d_list[2], d_leaves, d_counters;
     int32_t n_slots = 0, slot_max_len = 0;
     size_t slot_bytes = 0;
 
     /* results */
     std::vector<AlnResult> res;
-    PinnedBuf h_runs;
+    PinnedBuf h_runs, h_text;
+    unsigned long long n_runs_total = 0;
+    bool runs_on_host = false; /* the run starts are fetched only when a caller asks for operations */
+    std::vector<int64_t> t_off; /* per alignment, for b200aln_batch_get_cigars */
+    std::vector<int32_t> t_len, t_ed, t_st;
     int32_t* h_counters = nullptr; /* pinned, CT_WORDS */
     bool aligned = false, synced = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -247,7 +283,7 @@ int32_t round_len(int32_t len) { /* slots are re-made only when the longest sequ
 /* device bytes one alignment needs besides the slots: sequences, operations, run starts, its share of the lists */
 int64_t var_bytes_for(int32_t n, int32_t m) {
     const int64_t len = (int64_t)n + m;
-    return 6 * len + 64 + (int64_t)sizeof(AlnJob) + (int64_t)sizeof(AlnResult) +
+    return 8 * len + 80 + (int64_t)sizeof(AlnJob) + (int64_t)sizeof(AlnResult) +
            (2 * aln_open_capacity(n, m) + aln_leaf_capacity(n, m)) * (int64_t)sizeof(AlnRect);
 }
 
@@ -304,12 +340,14 @@ void b200aln_batch_destroy(b200aln_batch* b) {
     b->d_ops.release();
     b->d_res.release();
     b->d_runs.release();
+    b->d_text.release();
     b->d_list[0].release();
     b->d_list[1].release();
     b->d_leaves.release();
     b->d_counters.release();
     b->h_seq.release();
     b->h_runs.release();
+    b->h_text.release();
     if (b->h_counters) cudaFreeHost(b->h_counters);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
@@ -413,7 +451,10 @@ int32_t b200aln_batch_align_all(b200aln_batch* b) {
     b->info.n_open = b->info.n_leaves = b->info.cells = 0;
     b->info.h2d_bytes = b->info.d2h_bytes = 0;
     b->info.kernel_ms = 0.f;
-    b->res.assign((size_t)n_aln, AlnResult{0, 0, 0, 0, 0});
+    b->res.assign((size_t)n_aln, AlnResult{0, 0, 0, 0, 0, 0, 0, 0});
+    b->runs_on_host = false;
+    b->n_runs_total = 0;
+    b->h_text.used = 0;
     if (n_aln == 0) {
         b->aligned = b->synced = true;
         return B200ALN_SUCCESS;
@@ -441,6 +482,8 @@ int32_t b200aln_batch_align_all(b200aln_batch* b) {
     ALN_CU(b->d_ops.need((size_t)b->ops_bytes + 64));
     ALN_CU(b->d_res.need(sizeof(AlnResult) * (size_t)n_aln));
     ALN_CU(b->d_runs.need(sizeof(uint32_t) * ((size_t)b->ops_bytes + 64)));
+    const unsigned long long text_cap = 2ull * (unsigned long long)b->ops_bytes + (unsigned long long)n_aln + 64; /* "1M1I..." at worst */
+    ALN_CU(b->d_text.need((size_t)text_cap));
     ALN_CU(b->d_list[0].need(sizeof(AlnRect) * (size_t)cap_open));
     ALN_CU(b->d_list[1].need(sizeof(AlnRect) * (size_t)cap_open));
     ALN_CU(b->d_leaves.need(sizeof(AlnRect) * (size_t)cap_leaves));
@@ -515,28 +558,31 @@ int32_t b200aln_batch_align_all(b200aln_batch* b) {
         ALN_CU(cudaGetLastError());
         ++launch;
     }
-    aln_runs_kernel<<<grid_for(n_aln), 32 * WARPS_PER_BLOCK, 0, s>>>(a, n_aln, static_cast<uint32_t*>(b->d_runs.p),
-                                                                     (unsigned long long)b->ops_bytes + 64, ct + CT_CURSOR + launch);
+    aln_cigar_kernel<<<grid_for(n_aln), 32 * WARPS_PER_BLOCK, 0, s>>>(a, n_aln, static_cast<uint32_t*>(b->d_runs.p),
+                                                                      (unsigned long long)b->ops_bytes + 64,
+                                                                      static_cast<uint8_t*>(b->d_text.p), text_cap,
+                                                                      ct + CT_CURSOR + launch);
     ALN_CU(cudaGetLastError());
     ++launch;
     ALN_CU(cudaEventRecord(b->ev1, s));
     b->info.kernel_launches = launch;
-    /* compact results: the per-alignment records and the counters now, the used part of the runs arena after them */
+    /* compact results: the per-alignment records and the counters now, then exactly the CIGAR bytes produced; the run
+     * starts stay on the device until a caller asks for operations (b200aln_batch_get_alignment / _get_ops) */
     ALN_CU(cudaMemcpyAsync(b->res.data(), b->d_res.p, sizeof(AlnResult) * (size_t)n_aln, cudaMemcpyDeviceToHost, s));
-    ALN_CU(cudaMemcpyAsync(b->h_counters + CT_RUNS, ct + CT_RUNS, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    ALN_CU(cudaMemcpyAsync(b->h_counters + CT_RUNS, ct + CT_RUNS, 6 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     ALN_CU(cudaStreamSynchronize(s));
-    unsigned long long n_runs_total = 0, cells = 0;
+    unsigned long long n_runs_total = 0, cells = 0, text_total = 0;
     std::memcpy(&n_runs_total, b->h_counters + CT_RUNS, 8);
     std::memcpy(&cells, b->h_counters + CT_CELLS, 8);
+    std::memcpy(&text_total, b->h_counters + CT_TEXT, 8);
     b->info.cells = (int64_t)cells;
-    n_runs_total = std::min<unsigned long long>(n_runs_total, (unsigned long long)b->ops_bytes + 64);
-    b->h_runs.used = 0;
-    if (!b->h_runs.reserve((size_t)n_runs_total * sizeof(uint32_t) + 64)) return B200ALN_GENERIC_ERROR;
-    b->h_runs.used = (size_t)n_runs_total * sizeof(uint32_t);
-    if (n_runs_total)
-        ALN_CU(cudaMemcpyAsync(b->h_runs.p, b->d_runs.p, (size_t)n_runs_total * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    b->info.d2h_bytes = (int64_t)(sizeof(AlnResult) * (size_t)n_aln + (size_t)n_runs_total * sizeof(uint32_t) +
-                                  sizeof(int32_t) * (size_t)(level + 6));
+    b->n_runs_total = std::min<unsigned long long>(n_runs_total, (unsigned long long)b->ops_bytes + 64);
+    text_total = std::min<unsigned long long>(text_total, text_cap);
+    if (!b->h_text.reserve((size_t)text_total + 64)) return B200ALN_GENERIC_ERROR;
+    b->h_text.used = (size_t)text_total;
+    if (text_total)
+        ALN_CU(cudaMemcpyAsync(b->h_text.p, b->d_text.p, (size_t)text_total, cudaMemcpyDeviceToHost, s));
+    b->info.d2h_bytes = (int64_t)(sizeof(AlnResult) * (size_t)n_aln + (size_t)text_total + sizeof(int32_t) * (size_t)(level + 8));
     b->aligned = true;
     b->synced = false;
     return B200ALN_SUCCESS;
@@ -551,7 +597,66 @@ int32_t b200aln_batch_sync(b200aln_batch* b) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, b->ev0, b->ev1) == cudaSuccess) b->info.kernel_ms = ms;
     else cudaGetLastError();
+    const size_t n_aln = b->jobs.size();
+    b->t_off.resize(n_aln);
+    b->t_len.resize(n_aln);
+    b->t_ed.resize(n_aln);
+    b->t_st.resize(n_aln);
+    for (size_t k = 0; k < n_aln; ++k) {
+        const AlnResult& r = b->res[k];
+        const bool ok = r.status == 0 && r.cigar_off >= 0 && r.cigar_len >= 0 &&
+                        (size_t)(r.cigar_off + r.cigar_len) < b->h_text.used; /* its terminating 0 included */
+        b->t_off[k] = ok ? r.cigar_off : 0;
+        b->t_len[k] = ok ? r.cigar_len : 0;
+        b->t_ed[k] = r.score;
+        b->t_st[k] = ok ? B200ALN_SUCCESS : (r.status ? r.status : B200ALN_GENERIC_ERROR);
+    }
     b->synced = true;
+    return B200ALN_SUCCESS;
+}
+
+int32_t b200aln_batch_get_cigars(const b200aln_batch* b, const char** text, const int64_t** off, const int32_t** len,
+                                 const int32_t** edit_distance, const int32_t** status) {
+    if (!b) return B200ALN_INVALID_ARGUMENT;
+    if (!b->aligned || !b->synced) return B200ALN_UNINITIALIZED;
+    if (text) *text = reinterpret_cast<const char*>(b->h_text.p);
+    if (off) *off = b->t_off.data();
+    if (len) *len = b->t_len.data();
+    if (edit_distance) *edit_distance = b->t_ed.data();
+    if (status) *status = b->t_st.data();
+    return B200ALN_SUCCESS;
+}
+
+int32_t b200aln_batch_add_alignments(b200aln_batch* b, int64_t n, const uint8_t* q_bases, const int64_t* q_off,
+                                     const uint8_t* t_bases, const int64_t* t_off, int64_t* n_added) {
+    if (n_added) *n_added = 0;
+    if (!b || n < 0 || (n > 0 && (!q_bases || !q_off || !t_bases || !t_off))) return B200ALN_INVALID_ARGUMENT;
+    int64_t k = 0;
+    int32_t st = B200ALN_SUCCESS;
+    for (; k < n; ++k) {
+        st = b200aln_batch_add_alignment(b, reinterpret_cast<const char*>(q_bases + q_off[k]), (int32_t)(q_off[k + 1] - q_off[k]),
+                                         reinterpret_cast<const char*>(t_bases + t_off[k]), (int32_t)(t_off[k + 1] - t_off[k]));
+        if (st != B200ALN_SUCCESS) break;
+    }
+    if (n_added) *n_added = k;
+    if (st == B200ALN_EXCEEDED_MAX_ALIGNMENTS && k > 0) return B200ALN_SUCCESS; /* full: align, reset, go on from k */
+    return st;
+}
+
+/* the run starts of the last align_all, fetched on first use */
+static int32_t fetch_runs(const b200aln_batch* cb) {
+    b200aln_batch* b = const_cast<b200aln_batch*>(cb);
+    if (b->runs_on_host) return B200ALN_SUCCESS;
+    ALN_CU(cudaSetDevice(b->device));
+    b->h_runs.used = 0;
+    if (!b->h_runs.reserve((size_t)b->n_runs_total * sizeof(uint32_t) + 64)) return B200ALN_GENERIC_ERROR;
+    if (b->n_runs_total) {
+        ALN_CU(cudaMemcpyAsync(b->h_runs.p, b->d_runs.p, (size_t)b->n_runs_total * sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
+        ALN_CU(cudaStreamSynchronize(b->stream));
+    }
+    b->h_runs.used = (size_t)b->n_runs_total * sizeof(uint32_t);
+    b->info.d2h_bytes += (int64_t)b->h_runs.used;
+    b->runs_on_host = true;
     return B200ALN_SUCCESS;
 }
 
@@ -559,9 +664,13 @@ int32_t b200aln_batch_get_alignment(const b200aln_batch* b, int32_t index, const
                                     int32_t* n_ops, int32_t* edit_distance, int32_t* status) {
     if (!b || index < 0 || (size_t)index >= b->jobs.size()) return B200ALN_INVALID_ARGUMENT;
     if (!b->aligned || !b->synced) return B200ALN_UNINITIALIZED;
+    if (runs) {
+        const int32_t fs = fetch_runs(b);
+        if (fs != B200ALN_SUCCESS) return fs;
+    }
     const AlnResult& r = b->res[(size_t)index];
-    const bool ok = r.status == 0 && r.runs_off >= 0 &&
-                    (size_t)(r.runs_off + r.n_runs) * sizeof(uint32_t) <= b->h_runs.used;
+    const bool ok = r.status == 0 && r.runs_off >= 0 && (!runs ||
+                    (size_t)(r.runs_off + r.n_runs) * sizeof(uint32_t) <= b->h_runs.used);
     if (runs) *runs = ok ? reinterpret_cast<const uint32_t*>(b->h_runs.p) + r.runs_off : nullptr;
     if (n_runs) *n_runs = ok ? r.n_runs : 0;
     if (n_ops) *n_ops = ok ? r.n_ops : 0;
@@ -571,18 +680,16 @@ int32_t b200aln_batch_get_alignment(const b200aln_batch* b, int32_t index, const
 }
 
 int64_t b200aln_batch_get_cigar(const b200aln_batch* b, int32_t index, char* out, int64_t cap) {
-    const uint32_t* runs = nullptr;
-    int32_t n_runs = 0, n_ops = 0, st = 0;
-    const int32_t rc = b200aln_batch_get_alignment(b, index, &runs, &n_runs, &n_ops, nullptr, &st);
-    if (rc != B200ALN_SUCCESS) return -(int64_t)rc;
-    if (st != B200ALN_SUCCESS) return -(int64_t)st;
-    const std::string c = aln_runs_to_cigar(runs, n_runs, n_ops);
+    if (!b || index < 0 || (size_t)index >= b->jobs.size()) return -(int64_t)B200ALN_INVALID_ARGUMENT;
+    if (!b->aligned || !b->synced) return -(int64_t)B200ALN_UNINITIALIZED;
+    if (b->t_st[(size_t)index] != B200ALN_SUCCESS) return -(int64_t)b->t_st[(size_t)index];
+    const int64_t len = b->t_len[(size_t)index];
     if (out && cap > 0) {
-        const size_t k = std::min<size_t>(c.size(), (size_t)cap - 1);
-        std::memcpy(out, c.data(), k);
+        const size_t k = (size_t)std::min<int64_t>(len, cap - 1);
+        std::memcpy(out, b->h_text.p + b->t_off[(size_t)index], k);
         out[k] = 0;
     }
-    return (int64_t)c.size();
+    return len;
 }
 
 int64_t b200aln_batch_get_ops(const b200aln_batch* b, int32_t index, uint8_t* out, int64_t cap) {
@@ -612,6 +719,9 @@ int32_t b200aln_batch_reset(b200aln_batch* b) {
     b->max_len = 0;
     b->res.clear();
     b->h_runs.used = 0;
+    b->h_text.used = 0;
+    b->runs_on_host = false;
+    b->n_runs_total = 0;
     b->aligned = b->synced = false;
     return B200ALN_SUCCESS;
 }

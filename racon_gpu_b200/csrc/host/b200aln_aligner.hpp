@@ -50,15 +50,37 @@ public:
     AlignmentType get_alignment_type() const { return global_alignment; }
     bool is_optimal() const { return status_ == success; } /* no band: an alignment that exists is optimal */
     StatusType get_status() const { return status_; }
-    const std::vector<AlignmentState>& get_alignment() const { return alignment_; }
     int32_t get_edit_distance() const { return edit_distance_; }
+    /* one state per position; expanded from the batch's run starts on first use (racon only reads the CIGAR, so the
+     * run starts stay on the device unless somebody asks), available until the Aligner is reset */
+    const std::vector<AlignmentState>& get_alignment() const {
+        if (!expanded_ && batch_ && status_ == success) {
+            const uint32_t* runs = nullptr;
+            int32_t n_runs = 0, n_ops = 0, ast = B200ALN_GENERIC_ERROR;
+            if (b200aln_batch_get_alignment(batch_, index_, &runs, &n_runs, &n_ops, nullptr, &ast) == B200ALN_SUCCESS &&
+                ast == B200ALN_SUCCESS) {
+                static const AlignmentState state[4] = {match, insertion, deletion, mismatch}; /* b200aln_op -> state */
+                alignment_.reserve(static_cast<size_t>(n_ops));
+                for (int32_t r = 0; r < n_runs; ++r) {
+                    const int32_t b = static_cast<int32_t>(runs[r] >> 2);
+                    const int32_t e = r + 1 < n_runs ? static_cast<int32_t>(runs[r + 1] >> 2) : n_ops;
+                    alignment_.insert(alignment_.end(), static_cast<size_t>(e - b), state[runs[r] & 3u]);
+                }
+            }
+            expanded_ = true;
+        }
+        return alignment_;
+    }
 
 private:
     friend class Aligner;
     std::string query_, target_, cigar_;
-    std::vector<AlignmentState> alignment_;
+    mutable std::vector<AlignmentState> alignment_;
+    mutable bool expanded_ = false;
     StatusType status_ = uninitialized;
     int32_t edit_distance_ = -1;
+    const b200aln_batch* batch_ = nullptr;
+    int32_t index_ = 0;
 };
 
 class Aligner { /* aligner.hpp:43-83 */
@@ -68,7 +90,10 @@ public:
         if (st == B200ALN_INVALID_ARGUMENT) throw std::invalid_argument("create_aligner: invalid device or memory budget");
         if (st != B200ALN_SUCCESS) throw std::runtime_error(std::string("create_aligner: ") + b200aln_status_string(st));
     }
-    ~Aligner() { b200aln_batch_destroy(b_); }
+    ~Aligner() {
+        detach();
+        b200aln_batch_destroy(b_);
+    }
     Aligner(const Aligner&) = delete;
     Aligner& operator=(const Aligner&) = delete;
 
@@ -87,40 +112,37 @@ public:
     StatusType sync_alignments() {
         const int32_t st = b200aln_batch_sync(b_);
         if (st != B200ALN_SUCCESS) return to_status(st);
+        const char* text = nullptr;
+        const int64_t* off = nullptr;
+        const int32_t *len = nullptr, *ed = nullptr, *ast = nullptr;
+        if (b200aln_batch_get_cigars(b_, &text, &off, &len, &ed, &ast) != B200ALN_SUCCESS) return generic_error;
         for (size_t k = 0; k < alignments_.size(); ++k) {
             Alignment& a = *alignments_[k];
-            const uint32_t* runs = nullptr;
-            int32_t n_runs = 0, n_ops = 0, ed = -1, ast = B200ALN_GENERIC_ERROR;
-            b200aln_batch_get_alignment(b_, static_cast<int32_t>(k), &runs, &n_runs, &n_ops, &ed, &ast);
-            a.status_ = to_status(ast);
-            a.edit_distance_ = ed;
+            a.status_ = to_status(ast[k]);
+            a.edit_distance_ = ed[k];
+            a.batch_ = b_;
+            a.index_ = static_cast<int32_t>(k);
             a.alignment_.clear();
-            a.cigar_.clear();
-            if (ast != B200ALN_SUCCESS) continue;
-            static const AlignmentState state[4] = {match, insertion, deletion, mismatch}; /* b200aln_op -> state */
-            a.alignment_.reserve(static_cast<size_t>(n_ops));
-            for (int32_t r = 0; r < n_runs; ++r) {
-                const int32_t b = static_cast<int32_t>(runs[r] >> 2);
-                const int32_t e = r + 1 < n_runs ? static_cast<int32_t>(runs[r + 1] >> 2) : n_ops;
-                a.alignment_.insert(a.alignment_.end(), static_cast<size_t>(e - b), state[runs[r] & 3u]);
-            }
-            const int64_t len = b200aln_batch_get_cigar(b_, static_cast<int32_t>(k), nullptr, 0);
-            if (len > 0) {
-                a.cigar_.resize(static_cast<size_t>(len) + 1);
-                b200aln_batch_get_cigar(b_, static_cast<int32_t>(k), &a.cigar_[0], len + 1);
-                a.cigar_.resize(static_cast<size_t>(len));
-            }
+            a.expanded_ = false;
+            a.cigar_.assign(ast[k] == B200ALN_SUCCESS ? text + off[k] : "", ast[k] == B200ALN_SUCCESS ? static_cast<size_t>(len[k]) : 0);
         }
         return success;
     }
     const std::vector<std::shared_ptr<Alignment>>& get_alignments() const { return alignments_; }
     void reset() {
+        detach();
         alignments_.clear();
         b200aln_batch_reset(b_);
     }
     b200aln_batch* handle() const { return b_; }
 
 private:
+    void detach() { /* Alignment objects a caller still holds keep what they have, but can no longer reach the batch */
+        for (auto& a : alignments_) {
+            if (a.use_count() > 1) a->get_alignment();
+            a->batch_ = nullptr;
+        }
+    }
     b200aln_batch* b_ = nullptr;
     std::vector<std::shared_ptr<Alignment>> alignments_;
 };

@@ -17,25 +17,37 @@ def main():
     ap.add_argument("--mem-gb", type=float, default=32)
     a = ap.parse_args()
     from common import overlap_fixture
-    from racon_gpu_b200.aligner import align_pairs, pack_pairs
+    from racon_gpu_b200.aligner import CUDABatchAligner, pack_pairs
     fx = overlap_fixture()
     pairs = [(f["q"], f["t"]) for f in fx] * a.rep
     q, qo, t, to = pack_pairs(pairs)
     nominal = float(sum(len(x) * len(y) for x, y in pairs))
     out = {"pairs": len(pairs), "bases": int(qo[-1] + to[-1]), "matrix_cells": nominal}
     best = None
+    al = CUDABatchAligner(device_id=0, max_gpu_memory=int(a.mem_gb * (1 << 30)))
     for it in range(a.iters + 1):
         t0 = time.perf_counter()
-        ed, cig, coff, info = align_pairs(q, qo, t, to, device_id=0, max_gpu_memory=int(a.mem_gb * (1 << 30)))
-        dt = time.perf_counter() - t0
+        first, rec = 0, {"kernel_ms": 0.0, "cells_computed": 0, "n_open": 0, "n_leaves": 0, "h2d": 0, "d2h": 0, "launches": 0,
+                         "levels": 0, "batches": 0}
+        eds = []
+        while first < len(pairs):  # host buffers in, CIGAR bytes out; as many batches as the memory budget asks for
+            first += al.add_overlaps(q, qo, t, to, first)
+            al.align_all()
+            text, off, ln, ed = al.cigars()
+            info = al.info()
+            al.reset()
+            eds.append(ed)
+            rec["kernel_ms"] += info["kernel_ms"]; rec["cells_computed"] += info["cells"]; rec["n_open"] += info["n_open"]
+            rec["n_leaves"] += info["n_leaves"]; rec["h2d"] += info["h2d_bytes"]; rec["d2h"] += info["d2h_bytes"]
+            rec["launches"] += info["kernel_launches"]; rec["levels"] = max(rec["levels"], info["levels"]); rec["batches"] += 1
+            rec["slots"] = info["n_slots"]
+        rec["wall_s"] = time.perf_counter() - t0
         if it == 0:
-            assert [int(x) for x in ed[:len(fx)]] == [f["score"] for f in fx]
+            assert [int(x) for x in np.concatenate(eds)[:len(fx)]] == [f["score"] for f in fx]
             continue  # warm-up (allocations, first launches)
-        rec = {"wall_s": dt, "kernel_ms": info["kernel_ms"], "levels": info["levels"], "launches": info["kernel_launches"],
-               "cells_computed": info["cells"], "n_open": info["n_open"], "n_leaves": info["n_leaves"],
-               "h2d": info["h2d_bytes"], "d2h": info["d2h_bytes"], "slots": info["n_slots"]}
-        if best is None or dt < best["wall_s"]:
+        if best is None or rec["wall_s"] < best["wall_s"]:
             best = rec
+    al.close()
     out["gpu"] = best
     out["gpu"]["overlaps_per_s_e2e"] = len(pairs) / best["wall_s"]
     out["gpu"]["gcups_matrix_e2e"] = nominal / best["wall_s"] / 1e9
@@ -43,7 +55,7 @@ def main():
     try:
         from oracle_lib import Ref, ref_align
         r = Ref()
-        if r.available:
+        if r.available and a.cpu_sample > 0:
             cores = len(os.sched_getaffinity(0))
             sample = pairs[:a.cpu_sample * max(1, cores)][:len(pairs)]
             t0 = time.perf_counter()

@@ -25,6 +25,7 @@ int64_t emu_align(const uint8_t* q, int32_t n, const uint8_t* t, int32_t m, uint
     const int32_t max_len = (n > m ? n : m) + 1;
     size_t slot_bytes = 0;
     AlnSlot s;
+    EqTab eq;
     aln_slot_bind(s, nullptr, max_len, &slot_bytes);
     std::vector<uint8_t> slab(slot_bytes + 512);
     aln_slot_bind(s, reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(slab.data()) + 255) & ~uintptr_t(255)), max_len, nullptr);
@@ -40,7 +41,7 @@ int64_t emu_align(const uint8_t* q, int32_t n, const uint8_t* t, int32_t m, uint
         for (int32_t k = 0; k < n_level; ++k) {
             const AlnRect r = level[(size_t)k];
             AlnSplit sp;
-            aln_split(s, q + r.r0, t + r.c0, r.n, r.m, &sp);
+            aln_split(s, eq, q + r.r0, t + r.c0, r.n, r.m, &sp);
             if (r.top) *score = sp.best;
             AlnRect ul, lr;
             if (!aln_children(r, sp.r, ul, lr)) return -1;
@@ -54,23 +55,26 @@ int64_t emu_align(const uint8_t* q, int32_t n, const uint8_t* t, int32_t m, uint
     if (overflow) return -2;
     for (int32_t k = 0; k < n_leaf; ++k) {
         const AlnRect r = leaves[(size_t)k];
-        aln_leaf(s, q + r.r0, t + r.c0, r.n, r.m, ops.data() + r.r0 + r.c0, r.top ? score : nullptr);
+        aln_leaf(s, eq, q + r.r0, t + r.c0, r.n, r.m, ops.data() + r.r0 + r.c0, r.top ? score : nullptr);
     }
     int64_t k = 0;
     for (uint8_t op : ops)
         if (op != OP_NONE) ops_out[k++] = op;
     /* the runs must spell the same operations */
     int32_t n_ops = -1;
-    const int32_t n_runs = aln_runs(ops.data(), n + m, nullptr, &n_ops);
+    const int32_t n_runs = aln_runs(ops.data(), n + m, nullptr, n_ops);
     std::vector<uint32_t> runs((size_t)n_runs + 1);
-    if (aln_runs(ops.data(), n + m, runs.data(), &n_ops) != n_runs || n_ops != k) return -3;
+    if (aln_runs(ops.data(), n + m, runs.data(), n_ops) != n_runs || n_ops != k) return -3;
     std::vector<uint8_t> spelled;
     aln_expand_runs(runs.data(), n_runs, n_ops, spelled);
     if (spelled.size() != (size_t)k || (k > 0 && std::memcmp(spelled.data(), ops_out, (size_t)k) != 0)) return -3;
-    if (cigar_out) {
+    if (cigar_out) { /* the engine's own text (aln_cigar_text) must equal the host-side spelling of the runs */
         const std::string c = aln_runs_to_cigar(runs.data(), n_runs, n_ops);
-        if ((int64_t)c.size() + 1 > cigar_cap) return -3;
-        std::memcpy(cigar_out, c.c_str(), c.size() + 1);
+        const int32_t bytes = aln_cigar_text(runs.data(), n_runs, n_ops, nullptr);
+        if ((int64_t)bytes + 1 > cigar_cap || bytes != (int32_t)c.size()) return -3;
+        if (aln_cigar_text(runs.data(), n_runs, n_ops, reinterpret_cast<uint8_t*>(cigar_out)) != bytes) return -3;
+        cigar_out[bytes] = 0;
+        if (c != cigar_out) return -3;
     }
     if (levels) *levels = depth;
     if (n_leaves) *n_leaves = n_leaf;

@@ -99,6 +99,14 @@ def test_full_batch_is_back_pressure_not_an_error(oracle):
         rounds += 1
     small.close()
     assert rounds >= 2 and len(out) == len(pairs)
+    # columnar add + in-place CIGAR table (b200aln_batch_add_alignments / _get_cigars), same answers
+    q, qo, t, to = pack_pairs(pairs)
+    bulk = CUDABatchAligner(device_id=0, max_gpu_memory=1 << 30)
+    assert bulk.add_overlaps(q, qo, t, to) == len(pairs)
+    bulk.align_all()
+    text, off, ln, ed2 = bulk.cigars()
+    assert [(text[off[i]:off[i] + ln[i]], int(ed2[i])) for i in range(len(pairs))] == out
+    bulk.close()
     ed, cigars, coff, info = align_pairs(*pack_pairs(pairs), device_id=0, max_gpu_memory=2 << 30)
     for i, (q, t) in enumerate(pairs):
         ops, score = oracle_align(oracle, q, t)
