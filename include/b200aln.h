@@ -111,6 +111,8 @@ typedef struct b200aln_batch_info {
     int32_t n_slots;          /* resident warps = per-warp workspaces                         */
     int32_t levels;           /* Hirschberg levels of the last align_all                      */
     int32_t kernel_launches;  /* launches of the last align_all                               */
+    int32_t team_launches;    /* of them: team launches (a block of warps per tall sub-problem) */
+    int32_t n_team_blocks;    /* resident team blocks = team workspaces                        */
     int64_t n_open;           /* sub-problems split in the last align_all                     */
     int64_t n_leaves;         /* sub-problems traced back directly                            */
     int64_t cells;            /* distance-matrix cells computed (splits + leaves)             */

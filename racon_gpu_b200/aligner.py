@@ -26,6 +26,7 @@ GENERIC_ERROR, INVALID_ARGUMENT, CUDA_ERROR = 5, 6, 7
 
 class AlnBatchInfo(C.Structure):
     _fields_ = [("device_id", C.c_int32), ("n_slots", C.c_int32), ("levels", C.c_int32), ("kernel_launches", C.c_int32),
+                ("team_launches", C.c_int32), ("n_team_blocks", C.c_int32),
                 ("n_open", C.c_int64), ("n_leaves", C.c_int64), ("cells", C.c_int64), ("h2d_bytes", C.c_int64),
                 ("d2h_bytes", C.c_int64), ("kernel_ms", C.c_float)]
 

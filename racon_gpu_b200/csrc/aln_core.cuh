@@ -62,6 +62,9 @@ ALN_HD bool aln_is_leaf(int32_t n, int32_t m) {
     return (2 * 8 + 4) * blocks * (int64_t)m + 2 * 4 * (int64_t)m < ALN_LEAF_DATA_LIMIT;
 }
 
+/* more than one 32-block stripe of rows? */
+ALN_HD bool aln_is_tall(int32_t n) { return n > 64 * 32; }
+
 /* one open sub-problem: rows [r0, r0 + n) of the query, columns [c0, c0 + m) of the target */
 struct AlnRect {
     int32_t aln;
@@ -76,9 +79,11 @@ struct AlnSplit { /* result of one Hirschberg step */
 
 /* the open list of the next level, the leaf list, and where an overflow of either is reported */
 struct AlnLists {
-    AlnRect* open;
+    AlnRect* open;  /* sub-problems of at most one 32-block stripe (one warp each)                                  */
     int32_t* n_open;
-    int32_t cap_open;
+    AlnRect* tall;  /* taller ones: a team of warps each when the level is too small to fill the device otherwise  */
+    int32_t* n_tall;
+    int32_t cap_open; /* of either list */
     AlnRect* leaves;
     int32_t* n_leaves;
     int32_t cap_leaves;
@@ -92,13 +97,14 @@ struct alignas(16) RecPM {
 
 /* per resident warp workspace */
 struct AlnSlot {
-    uint8_t* hbuf;  /* [max_len + 64]   horizontal deltas (code: 1 = +1, 2 = -1, 0) of the row between two stripes   */
+    uint32_t* hbuf; /* [hrow words]     horizontal deltas of the row between two stripes, 2 bits a column (1 = +1, 2 = -1) */
     uint8_t* tcode; /* [max_len + 192]  the pass's target as codes 0..3 = ACGT, 4 = other; 64 bytes of padding in front */
     int32_t* Lc;    /* [max_len + 2]    last column of the forward pass:  Lc[i] = D(q[0..i), left half)              */
     int32_t* Rr;    /* [max_len + 2]    last column of the backward pass: Rr[i] = D(q[n-i..n), right half)          */
     RecPM* PM;      /* [leaf entries]   leaf records in wavefront order, see leaf_entry()                            */
     int32_t* S;     /* [leaf entries]   score under the block's last row                                             */
 };
+ALN_HD int64_t aln_hrow_words(int32_t max_len) { return (int64_t)max_len / 16 + 8; } /* one hand-over row */
 ALN_HD int64_t aln_leaf_entries(int32_t max_len) { return ALN_LEAF_DATA_LIMIT / 20 + 31 * (int64_t)((max_len + 63) / 64) + 64; }
 ALN_HD void aln_slot_bind(AlnSlot& s, uint8_t* base, int32_t max_len, size_t* total_out) {
     size_t o = 0;
@@ -109,7 +115,7 @@ ALN_HD void aln_slot_bind(AlnSlot& s, uint8_t* base, int32_t max_len, size_t* to
         s.field = base ? reinterpret_cast<type*>(base + o) : nullptr;  \
         o += sizeof(type) * (size_t)(count);                           \
     } while (0)
-    ALN_CARVE(hbuf, uint8_t, (size_t)max_len + 64);
+    ALN_CARVE(hbuf, uint32_t, (size_t)aln_hrow_words(max_len));
     ALN_CARVE(tcode, uint8_t, (size_t)max_len + 192);
     ALN_CARVE(Lc, int32_t, (size_t)max_len + 2);
     ALN_CARVE(Rr, int32_t, (size_t)max_len + 2);
@@ -158,8 +164,9 @@ POA_FN int32_t aln_take(int32_t* counter) { /* called by ONE lane */
 POA_FN void aln_push(const AlnLists& L, const AlnRect r) {
     if (r.n == 0 && r.m == 0) return;
     const bool leaf = aln_is_leaf(r.n, r.m);
-    const int32_t k = aln_take(leaf ? L.n_leaves : L.n_open);
-    if (k < (leaf ? L.cap_leaves : L.cap_open)) (leaf ? L.leaves : L.open)[k] = r;
+    const bool tall = aln_is_tall(r.n);
+    const int32_t k = aln_take(leaf ? L.n_leaves : tall ? L.n_tall : L.n_open);
+    if (k < (leaf ? L.cap_leaves : L.cap_open)) (leaf ? L.leaves : tall ? L.tall : L.open)[k] = r;
     else *L.overflow = 1;
 }
 /* upper-left and lower-right sub-problems of `r` split at query index sr (relative, -1 .. n-1), edlib.cpp:1321-1333 */
@@ -207,6 +214,64 @@ POA_FN int64_t leaf_entry(int32_t b, int32_t j, int32_t B, int32_t cols) {
     return (int64_t)s0 * (cols + 31) + (int64_t)(j + l) * nb + l;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Teams.  A tall sub-problem is many stripes; stripe s + 1 needs, column by column, the horizontal deltas stripe s leaves
+ * under its last row.  One warp runs the stripes one after the other (n = 1).  A TEAM of n warps of one block runs them
+ * as a pipeline: warp w takes stripes w, w + n, ...; a stripe's last lane packs its deltas 16 columns to a word into the
+ * stripe's hand-over row (global memory, row s mod n) and publishes its progress -- (stripe << 32 | columns done), one
+ * word of shared memory per warp -- every 32 columns; the next stripe's warp polls that word before it fetches the row's
+ * next word, 16 columns ahead of their use.  Producers never wait, so the pipeline cannot deadlock.
+ * ---------------------------------------------------------------------------------------- */
+struct TeamCtx {
+    int32_t w, n;     /* this warp's place in its team, warps in the team (1: a warp on its own) */
+    int32_t bar_id;   /* the team's named barrier (device, n > 1) */
+    uint32_t prog_sa; /* shared-memory address of the team's n progress words (device, n > 1) */
+};
+POA_FN void team_barrier(const TeamCtx c) {
+#if POA_DEVICE
+    if (c.n > 1) { /* literal barrier numbers: a register id would make ptxas reserve all sixteen */
+        if (c.bar_id == 1) asm volatile("bar.sync 1, %0;" ::"r"(c.n * 32) : "memory");
+        else asm volatile("bar.sync 2, %0;" ::"r"(c.n * 32) : "memory");
+    } else {
+        __syncwarp();
+    }
+#else
+    (void)c;
+#endif
+}
+POA_FN void team_publish(const TeamCtx c, int32_t stripe, int32_t cols_done) { /* ONE lane, after its row stores */
+#if POA_DEVICE
+    __threadfence_block();
+    const unsigned long long v = ((unsigned long long)(uint32_t)stripe << 32) | (uint32_t)cols_done;
+    asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(c.prog_sa + 8u * (uint32_t)c.w), "l"(v) : "memory");
+#else
+    (void)c; (void)stripe; (void)cols_done;
+#endif
+}
+POA_FN void team_wait(const TeamCtx c, int32_t stripe, int32_t cols_needed) { /* whole warp: until `stripe` got that far */
+#if POA_DEVICE
+    const unsigned long long target = ((unsigned long long)(uint32_t)stripe << 32) | (uint32_t)cols_needed;
+    const uint32_t sa = c.prog_sa + 8u * (uint32_t)(stripe % c.n);
+    unsigned long long v;
+    do {
+        asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(sa) : "memory");
+    } while (v < target);
+    __threadfence_block();
+#else
+    (void)c; (void)stripe; (void)cols_needed;
+#endif
+}
+/* a word of a hand-over row: written by another warp of the block moments ago, so not through a stale L1 line */
+POA_FN uint32_t hrow_load(const uint32_t* p) {
+#if POA_DEVICE
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+#else
+    return *p;
+#endif
+}
+
 /* a character that is none of ACGT equals only itself (edlib's alphabet is the set of bytes seen): rare */
 POA_FN uint64_t eq_other(const SeqView q, int32_t row0, int32_t cnt, int tc) {
     uint64_t Eq = 0;
@@ -229,30 +294,46 @@ POA_FN uint64_t eq_other(const SeqView q, int32_t row0, int32_t cnt, int tc) {
  * The column's character code comes straight from the slot's code row (loaded one step ahead), its match mask from the
  * lane's shared-memory table.
  */
-POA_FN_NOINLINE void myers_pass(const SeqView q, int32_t n, const SeqView t, int32_t cols, uint8_t* hbuf, uint8_t* tcode_base,
-                                const EqTab eq_in, int32_t* out_col, RecPM* PM, int32_t* S) {
+POA_FN_NOINLINE void myers_pass(const SeqView q, int32_t n, const SeqView t, int32_t cols, const TeamCtx team, uint32_t* hbuf,
+                                int32_t hrow_words, uint8_t* tcode_base, const EqTab eq_in, int32_t* out_col, RecPM* PM,
+                                int32_t* S) {
     n = poa_uniform(n);
     cols = poa_uniform(cols);
     EqTab eq = eq_in; /* by value: a reference would live in local memory and be re-read every step */
     const int32_t B = (n + 63) / 64;
     uint8_t* tcode = tcode_base + 64; /* tcode[-64 .. cols + 63] may be read (by lanes whose column is out of range) */
-    for (int32_t base = -64; base < cols + 64; base += 32) {
+    if (team.n > 1) {
+        POA_LANE0 { team_publish(team, 0, 0); } /* progress words of the previous pass are void */
+    }
+    for (int32_t base = -64 + 32 * team.w; base < cols + 64; base += 32 * team.n) {
         POA_LANES(l) {
             const int32_t c = base + l;
             tcode[c] = (c >= 0 && c < cols) ? (uint8_t)aln_code(seq_at(t, c)) : (uint8_t)0;
         }
     }
-    if (out_col) {
+    if (out_col && team.w == 0) {
         POA_LANE0 { out_col[0] = cols; }
     }
     POA_SYNC();
     POA_FENCE();
-    for (int32_t s0 = 0; s0 < B; s0 += 32) {
+    team_barrier(team);
+    const int32_t n_stripes = (B + 31) / 32;
+    for (int32_t sidx = team.w; sidx < n_stripes; sidx += team.n) {
+        const int32_t s0 = 32 * sidx;
         const int32_t nb = B - s0 < 32 ? B - s0 : 32;
         const bool more = s0 + 32 < B; /* another stripe follows: the last lane's horizontal deltas are kept */
         const bool lower = s0 > 0;     /* lane 0 enters with the deltas the stripe above left behind */
+        const bool piped = lower && team.n > 1;
+        const uint32_t* row_in = hbuf + (int64_t)((sidx + team.n - 1) % team.n) * hrow_words;
+        uint32_t* row_out = hbuf + (int64_t)(sidx % team.n) * hrow_words;
+        uint32_t hword = 0x55555555u, hword_next = 0x55555555u; /* stripe 0: D[0][j] = j, every delta + 1 */
+        if (piped) team_wait(team, sidx - 1, cols < 32 ? cols : 32);
+        if (lower) {
+            hword = hrow_load(row_in);
+            hword_next = hrow_load(row_in + 1);
+        }
         PerLane<uint64_t> Pv, Mv;
-        PerLane<int> bot, link, tc_next, h_next;
+        PerLane<int> bot, link, tc_next, hacc;
         POA_LANES(l) {
             const int32_t b = s0 + l;
             uint64_t e0 = 0, e1 = 0, e2 = 0, e3 = 0;
@@ -278,19 +359,24 @@ POA_FN_NOINLINE void myers_pass(const SeqView q, int32_t n, const SeqView t, int
             bot[l] = 64 * (b + 1);
             link[l] = 0;
             tc_next[l] = glb_u8(tcode - l);
-            h_next[l] = (lower && l == 0) ? glb_u8(hbuf) : 1;
+            hacc[l] = 0;
         }
         POA_SYNC();
         const int32_t steps = cols + nb - 1;
         for (int32_t step = 0; step < steps; ++step) {
+            if ((step & 15) == 0 && step > 0) { /* the next 16 entering deltas; their successor word a word ahead */
+                hword = hword_next;
+                if (piped) team_wait(team, sidx - 1, cols < step + 32 ? cols : step + 32);
+                if (lower) hword_next = hrow_load(row_in + (step >> 4) + 1);
+            }
+            const int h0 = (int)((hword >> ((step & 15) * 2)) & 3u);
             PerLane<int> in;
             warp_shift_up1(link, in); /* in[l] = the delta code lane l - 1 produced in the previous step */
             POA_LANES(l) {
                 const int32_t c = step - l;
                 const int code = tc_next[l];
-                const int hcode = l == 0 ? h_next[l] : in[l];
+                const int hcode = l == 0 ? h0 : in[l];
                 tc_next[l] = glb_u8(tcode + (c + 1)); /* next step's column, a step ahead of its use */
-                if (lower && l == 0) h_next[l] = glb_u8(hbuf + (step + 1));
                 if (l < nb && (uint32_t)c < (uint32_t)cols) { /* lane l works on column c */
                     uint64_t Eq;
                     if (code < 4) Eq = eq_load(eq, code, l);
@@ -316,7 +402,14 @@ POA_FN_NOINLINE void myers_pass(const SeqView q, int32_t n, const SeqView t, int
                         PM[e] = RecPM{npv, nmv};
                         S[e] = bot[l];
                     }
-                    if (more && l == 31) hbuf[c] = (uint8_t)out; /* column c was consumed by lane 0 at step c <= step */
+                    if (more && l == 31) { /* 16 columns to a word; this row's reader is at least 16 columns behind */
+                        hacc[l] |= out << ((c & 15) * 2);
+                        if ((c & 15) == 15 || c == cols - 1) {
+                            row_out[c >> 4] = (uint32_t)hacc[l];
+                            hacc[l] = 0;
+                            if (team.n > 1 && ((c & 31) == 31 || c == cols - 1)) team_publish(team, sidx, c + 1);
+                        }
+                    }
                     link[l] = out;
                 }
             }
@@ -343,14 +436,11 @@ POA_FN_NOINLINE void myers_pass(const SeqView q, int32_t n, const SeqView t, int
 /* ------------------------------------------------------------------------------------------
  * One Hirschberg step (edlib.cpp:1198-1344)
  * ---------------------------------------------------------------------------------------- */
-POA_FN_NOINLINE void aln_split(const AlnSlot& s_ref, EqTab& eq, const uint8_t* q, const uint8_t* t, int32_t n, int32_t m,
-                               AlnSplit* out) {
-    const AlnSlot s = s_ref;
+/* the split rule on the two middle columns: Lc[i] = D(q[0..i), left half), Rr[i] = D(q[n-i..n), right half) */
+POA_FN_NOINLINE void aln_split_rule(const int32_t* Lc, const int32_t* Rr, int32_t n, int32_t m, AlnSplit* out) {
     n = poa_uniform(n);
     m = poa_uniform(m);
     const int32_t lh = m / 2, rh = m - lh; /* edlib.cpp:1216-1217 */
-    myers_pass(SeqView{q, 1}, n, SeqView{t, 1}, lh, s.hbuf, s.tcode, eq, s.Lc, nullptr, nullptr);
-    myers_pass(SeqView{q + (n - 1), -1}, n, SeqView{t + (m - 1), -1}, rh, s.hbuf, s.tcode, eq, s.Rr, nullptr, nullptr);
     /* the optimum of the sub-problem is the smallest left + right sum over all crossing points of the middle */
     PerLane<int> acc;
     POA_LANES(l) { acc[l] = 0x7FFFFFFF; }
@@ -358,14 +448,14 @@ POA_FN_NOINLINE void aln_split(const AlnSlot& s_ref, EqTab& eq, const uint8_t* q
         POA_LANES(l) {
             const int32_t idx = base + l;
             if (idx <= n - 2) {
-                const int v = s.Lc[idx + 1] + s.Rr[n - idx - 1];
+                const int v = Lc[idx + 1] + Rr[n - idx - 1];
                 if (v < acc[l]) acc[l] = v;
             }
         }
     }
     int32_t best = warp_min(acc);
-    const int32_t top_sum = poa_uniform(lh + s.Rr[n]);    /* r = -1: the left half is all deletions  (:1292-1299) */
-    const int32_t bot_sum = poa_uniform(s.Lc[n] + rh);    /* r = n-1: the right half is all deletions (:1300-1308) */
+    const int32_t top_sum = poa_uniform(lh + Rr[n]);    /* r = -1: the left half is all deletions  (:1292-1299) */
+    const int32_t bot_sum = poa_uniform(Lc[n] + rh);    /* r = n-1: the right half is all deletions (:1300-1308) */
     if (top_sum < best) best = top_sum;
     if (bot_sum < best) best = bot_sum;
     int32_t r = -2;
@@ -373,15 +463,15 @@ POA_FN_NOINLINE void aln_split(const AlnSlot& s_ref, EqTab& eq, const uint8_t* q
         PerLane<int> hit;
         POA_LANES(l) {
             const int32_t idx = base + l;
-            hit[l] = (idx <= n - 2 && s.Lc[idx + 1] + s.Rr[n - idx - 1] == best) ? 1 : 0;
+            hit[l] = (idx <= n - 2 && Lc[idx + 1] + Rr[n - idx - 1] == best) ? 1 : 0;
         }
         const unsigned mask = warp_ballot(hit);
         if (mask) r = base + poa_ffs(mask);
     }
     int32_t ls = 0, rs = 0;
     if (r >= 0) {
-        ls = poa_uniform(s.Lc[r + 1]);
-        rs = poa_uniform(s.Rr[n - r - 1]);
+        ls = poa_uniform(Lc[r + 1]);
+        rs = poa_uniform(Rr[n - r - 1]);
     } else if (top_sum == best) {
         r = -1;
         ls = lh;
@@ -398,6 +488,18 @@ POA_FN_NOINLINE void aln_split(const AlnSlot& s_ref, EqTab& eq, const uint8_t* q
         out->best = best;
     }
     POA_SYNC();
+}
+
+POA_FN_NOINLINE void aln_split(const AlnSlot& s_ref, EqTab& eq, const uint8_t* q, const uint8_t* t, int32_t n, int32_t m,
+                               AlnSplit* out) {
+    const AlnSlot s = s_ref;
+    n = poa_uniform(n);
+    m = poa_uniform(m);
+    const int32_t lh = m / 2, rh = m - lh;
+    myers_pass(SeqView{q, 1}, n, SeqView{t, 1}, lh, TeamCtx{0, 1, 0, 0}, s.hbuf, 0, s.tcode, eq, s.Lc, nullptr, nullptr);
+    myers_pass(SeqView{q + (n - 1), -1}, n, SeqView{t + (m - 1), -1}, rh, TeamCtx{0, 1, 0, 0}, s.hbuf, 0, s.tcode, eq, s.Rr, nullptr,
+               nullptr);
+    aln_split_rule(s.Lc, s.Rr, n, m, out);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -465,7 +567,7 @@ POA_FN_NOINLINE void aln_leaf(const AlnSlot& s_ref, EqTab& eq, const uint8_t* q,
         POA_SYNC();
         return;
     }
-    myers_pass(SeqView{q, 1}, n, SeqView{t, 1}, m, s.hbuf, s.tcode, eq, nullptr, s.PM, s.S);
+    myers_pass(SeqView{q, 1}, n, SeqView{t, 1}, m, TeamCtx{0, 1, 0, 0}, s.hbuf, 0, s.tcode, eq, nullptr, s.PM, s.S);
     const int32_t B = (n + 63) / 64;
     LeafWindow win;
     int32_t i = n - 1, j = m - 1, jw = j;

@@ -44,20 +44,22 @@ struct AlnResult {
 };
 
 enum { /* int32 words of the device counter block */
-    CT_CURSOR = 0,      /* [64] one work cursor per launch                                   */
-    CT_NOPEN = 64,      /* [64] sub-problems open at level k                                 */
-    CT_NLEAVES = 128,
-    CT_OVERFLOW = 129,
-    CT_RUNS = 130,      /* u64: entries used in the runs arena                               */
-    CT_CELLS = 132,     /* u64: distance-matrix cells computed                               */
-    CT_TEXT = 134,      /* u64: bytes used in the CIGAR text arena                           */
-    CT_WORDS = 136,
+    CT_CURSOR = 0,      /* [128] one work cursor per launch                                  */
+    CT_NOPEN = 128,     /* [64][2] sub-problems open at level k: short, tall (adjacent words) */
+    CT_NLEAVES = 256,
+    CT_OVERFLOW = 257,
+    CT_RUNS = 258,      /* u64: entries used in the runs arena                               */
+    CT_CELLS = 260,     /* u64: distance-matrix cells computed                               */
+    CT_TEXT = 262,      /* u64: bytes used in the CIGAR text arena                           */
+    CT_WORDS = 264,
     MAX_LEVELS = 60
 };
 
 struct AlnKernelArgs {
     uint8_t* slab;
     size_t slot_bytes;
+    uint8_t* team_slab; /* n_team_blocks * team_slot_bytes */
+    size_t team_slot_bytes;
     int32_t max_len;
     const uint8_t* seq;
     const AlnJob* jobs;
@@ -112,6 +114,89 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, ALN_MIN_BLOCKS) aln_spli
             atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + CT_CELLS), (unsigned long long)r.n * (unsigned long long)r.m);
         }
         __syncwarp();
+    }
+}
+
+/* The same for TALL sub-problems when a level has too few of them to fill the device one warp each: a block per
+ * sub-problem, a team of ALN_TEAM warps on the forward pass and another on the backward pass at the same time, the
+ * stripes of a pass pipelined through the team (aln_core.cuh: Teams).  Block workspace: 2 x ALN_TEAM hand-over rows, two
+ * code rows, the two middle columns. */
+#ifndef ALN_TEAM
+#define ALN_TEAM 4
+#endif
+#ifndef ALN_TEAM_WAVES
+#define ALN_TEAM_WAVES 4 /* teams while a level's tall sub-problems fit this many waves of team blocks */
+#endif
+struct TeamSlot {
+    uint32_t* hrow[2];
+    uint8_t* tcode[2];
+    int32_t *Lc, *Rr;
+};
+__host__ __device__ inline void team_slot_bind(TeamSlot& t, uint8_t* base, int32_t max_len, size_t* total_out) {
+    size_t o = 0;
+    auto carve = [&](size_t bytes) {
+        o = (o + 255) / 256 * 256;
+        uint8_t* p = base ? base + o : nullptr;
+        o += bytes;
+        return p;
+    };
+    const size_t hrow = (size_t)aln_hrow_words(max_len);
+    for (int k = 0; k < 2; ++k) t.hrow[k] = reinterpret_cast<uint32_t*>(carve(sizeof(uint32_t) * hrow * ALN_TEAM));
+    for (int k = 0; k < 2; ++k) t.tcode[k] = carve((size_t)max_len + 192);
+    t.Lc = reinterpret_cast<int32_t*>(carve(sizeof(int32_t) * ((size_t)max_len + 2)));
+    t.Rr = reinterpret_cast<int32_t*>(carve(sizeof(int32_t) * ((size_t)max_len + 2)));
+    o = (o + 255) / 256 * 256;
+    if (total_out) *total_out = o;
+}
+__global__ void __launch_bounds__(64 * ALN_TEAM, 1024 / (64 * ALN_TEAM)) aln_split_team_kernel(const AlnKernelArgs a, const AlnRect* level,
+                                                                      int32_t n_level, const AlnLists next, int32_t* cursor) {
+    __shared__ uint64_t eq_tab[2 * ALN_TEAM * ALN_EQ_WORDS];
+    __shared__ unsigned long long prog[2 * ALN_TEAM];
+    __shared__ int32_t s_k;
+    TeamSlot ts;
+    team_slot_bind(ts, a.team_slab + (size_t)blockIdx.x * a.team_slot_bytes, a.max_len, nullptr);
+    const int warp = (int)(threadIdx.x >> 5), side = warp / ALN_TEAM; /* side 0: forward pass, side 1: backward pass */
+    EqTab eq;
+    bind_eq(eq, eq_tab);
+    TeamCtx team;
+    team.w = warp % ALN_TEAM;
+    team.n = ALN_TEAM;
+    team.bar_id = 1 + side;
+    team.prog_sa = (uint32_t)__cvta_generic_to_shared(prog + side * ALN_TEAM);
+    const int32_t hrow_words = (int32_t)aln_hrow_words(a.max_len);
+    for (;;) {
+        if (threadIdx.x == 0) s_k = atomicAdd(cursor, 1);
+        __syncthreads();
+        const int32_t k = s_k;
+        if (k >= n_level) break;
+        const AlnRect r = level[k];
+        const AlnJob job = a.jobs[r.aln];
+        const uint8_t* q = a.seq + job.q_off + r.r0;
+        const uint8_t* t = a.seq + job.t_off + r.c0;
+        const int32_t lh = r.m / 2, rh = r.m - lh; /* edlib.cpp:1216-1217 */
+        if (side == 0)
+            myers_pass(SeqView{q, 1}, r.n, SeqView{t, 1}, lh, team, ts.hrow[0], hrow_words, ts.tcode[0], eq, ts.Lc, nullptr, nullptr);
+        else
+            myers_pass(SeqView{q + (r.n - 1), -1}, r.n, SeqView{t + (r.m - 1), -1}, rh, team, ts.hrow[1], hrow_words, ts.tcode[1],
+                       eq, ts.Rr, nullptr, nullptr);
+        __threadfence_block();
+        __syncthreads(); /* both middle columns are complete */
+        if (warp == 0) {
+            AlnSplit sp;
+            aln_split_rule(ts.Lc, ts.Rr, r.n, r.m, &sp);
+            if ((threadIdx.x & 31u) == 0u) {
+                if (r.top) a.res[r.aln].score = sp.best;
+                AlnRect ul, lr;
+                if (aln_children(r, sp.r, ul, lr)) {
+                    aln_push(next, ul);
+                    aln_push(next, lr);
+                } else {
+                    a.res[r.aln].status = B200ALN_GENERIC_ERROR;
+                }
+                atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + CT_CELLS), (unsigned long long)r.n * (unsigned long long)r.m);
+            }
+        }
+        __syncthreads(); /* the columns and s_k are free again */
     }
 }
 
@@ -241,9 +326,9 @@ struct b200aln_batch {
     int64_t var_bytes = 0; /* device bytes the staged alignments need besides the slots */
 
     /* device */
-    DevBuf d_slab, d_seq, d_jobs, d_ops, d_res, d_runs, d_text, d_list[2], d_leaves, d_counters;
-    int32_t n_slots = 0, slot_max_len = 0;
-    size_t slot_bytes = 0;
+    DevBuf d_slab, d_team_slab, d_seq, d_jobs, d_ops, d_res, d_runs, d_text, d_list[2], d_tall[2], d_leaves, d_counters;
+    int32_t n_slots = 0, slot_max_len = 0, n_team_blocks = 0, team_blocks_per_sm = 0;
+    size_t slot_bytes = 0, team_slot_bytes = 0;
 
     /* results */
     std::vector<AlnResult> res;
@@ -292,13 +377,24 @@ int32_t ensure_slots(b200aln_batch* b) {
     if (b->n_slots > 0 && want_len <= b->slot_max_len) return B200ALN_SUCCESS;
     const int64_t sb = slot_bytes_for(want_len);
     const int64_t resident = (int64_t)b->sm_count * b->blocks_per_sm * WARPS_PER_BLOCK;
-    const int64_t avail = b->budget - b->var_bytes;
+    int64_t avail = b->budget - b->var_bytes;
+    /* team workspaces (tall sub-problems of thin levels) take at most a quarter of what is left; none is fine too:
+     * tall sub-problems then run one warp each */
+    size_t tsb = 0;
+    TeamSlot ts;
+    team_slot_bind(ts, nullptr, want_len, &tsb);
+    int64_t nt = std::min<int64_t>((int64_t)b->sm_count * b->team_blocks_per_sm, (avail / 4) / (int64_t)tsb);
+    if (avail - nt * (int64_t)tsb < WARPS_PER_BLOCK * sb) nt = 0;
+    avail -= nt * (int64_t)tsb;
     int64_t n = std::min<int64_t>(resident, avail / sb);
     n -= n % WARPS_PER_BLOCK;
     if (n < WARPS_PER_BLOCK) return B200ALN_EXCEEDED_MAX_LENGTH;
     ALN_CU(b->d_slab.need((size_t)(n * sb), false));
+    if (nt > 0) ALN_CU(b->d_team_slab.need((size_t)(nt * (int64_t)tsb), false));
     b->n_slots = (int32_t)n;
     b->slot_bytes = (size_t)sb;
+    b->n_team_blocks = (int32_t)nt;
+    b->team_slot_bytes = tsb;
     b->slot_max_len = want_len;
     return B200ALN_SUCCESS;
 }
@@ -343,6 +439,9 @@ void b200aln_batch_destroy(b200aln_batch* b) {
     b->d_text.release();
     b->d_list[0].release();
     b->d_list[1].release();
+    b->d_tall[0].release();
+    b->d_tall[1].release();
+    b->d_team_slab.release();
     b->d_leaves.release();
     b->d_counters.release();
     b->h_seq.release();
@@ -393,6 +492,12 @@ int32_t b200aln_batch_create(int32_t device_id, void* stream, int64_t max_gpu_me
             break;
         }
         b->blocks_per_sm = std::max(1, std::min(bps_split, bps_leaf));
+        int bps_team = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_team, aln_split_team_kernel, 64 * ALN_TEAM, 0) != cudaSuccess) {
+            st = B200ALN_CUDA_ERROR;
+            break;
+        }
+        b->team_blocks_per_sm = std::max(0, bps_team);
         if (cudaHostAlloc(reinterpret_cast<void**>(&b->h_counters), CT_WORDS * sizeof(int32_t), cudaHostAllocDefault) != cudaSuccess ||
             cudaEventCreate(&b->ev0) != cudaSuccess || cudaEventCreate(&b->ev1) != cudaSuccess) {
             st = B200ALN_CUDA_ERROR;
@@ -463,17 +568,19 @@ int32_t b200aln_batch_align_all(b200aln_batch* b) {
     int32_t st = ensure_slots(b);
     if (st != B200ALN_SUCCESS) return st;
     b->info.n_slots = b->n_slots;
+    b->info.n_team_blocks = b->n_team_blocks;
 
     /* the first level, classified on the host: largest first, so the persistent grid starts with the long ones */
-    std::vector<AlnRect> first, leaves0;
+    std::vector<AlnRect> first, first_tall, leaves0;
     for (int32_t k = 0; k < n_aln; ++k) {
         const AlnJob& j = b->jobs[(size_t)k];
         if (j.n == 0 && j.m == 0) continue;
-        (aln_is_leaf(j.n, j.m) ? leaves0 : first).push_back(AlnRect{k, 0, j.n, 0, j.m, 1});
+        (aln_is_leaf(j.n, j.m) ? leaves0 : aln_is_tall(j.n) ? first_tall : first).push_back(AlnRect{k, 0, j.n, 0, j.m, 1});
     }
-    std::stable_sort(first.begin(), first.end(),
-                     [](const AlnRect& x, const AlnRect& y) { return (int64_t)x.n * x.m > (int64_t)y.n * y.m; });
-    const int64_t cap_open = std::max<int64_t>(b->cap_open, (int64_t)first.size()) + 16;
+    const auto larger = [](const AlnRect& x, const AlnRect& y) { return (int64_t)x.n * x.m > (int64_t)y.n * y.m; };
+    std::stable_sort(first.begin(), first.end(), larger);
+    std::stable_sort(first_tall.begin(), first_tall.end(), larger);
+    const int64_t cap_open = std::max<int64_t>(b->cap_open, (int64_t)std::max(first.size(), first_tall.size())) + 16;
     const int64_t cap_leaves = std::max<int64_t>(b->cap_leaves, (int64_t)leaves0.size()) + 16;
     if (cap_open >= 0x7FFFFFFF || cap_leaves >= 0x7FFFFFFF) return B200ALN_EXCEEDED_MAX_ALIGNMENTS;
 
@@ -486,6 +593,8 @@ int32_t b200aln_batch_align_all(b200aln_batch* b) {
     ALN_CU(b->d_text.need((size_t)text_cap));
     ALN_CU(b->d_list[0].need(sizeof(AlnRect) * (size_t)cap_open));
     ALN_CU(b->d_list[1].need(sizeof(AlnRect) * (size_t)cap_open));
+    ALN_CU(b->d_tall[0].need(sizeof(AlnRect) * (size_t)cap_open));
+    ALN_CU(b->d_tall[1].need(sizeof(AlnRect) * (size_t)cap_open));
     ALN_CU(b->d_leaves.need(sizeof(AlnRect) * (size_t)cap_leaves));
     ALN_CU(b->d_counters.need(sizeof(int32_t) * CT_WORDS));
 
@@ -493,24 +602,29 @@ int32_t b200aln_batch_align_all(b200aln_batch* b) {
     int32_t* ct = static_cast<int32_t*>(b->d_counters.p);
     std::memset(b->h_counters, 0, sizeof(int32_t) * CT_WORDS);
     b->h_counters[CT_NOPEN] = (int32_t)first.size();
+    b->h_counters[CT_NOPEN + 1] = (int32_t)first_tall.size();
     b->h_counters[CT_NLEAVES] = (int32_t)leaves0.size();
     ALN_CU(cudaMemcpyAsync(ct, b->h_counters, sizeof(int32_t) * CT_WORDS, cudaMemcpyHostToDevice, s));
     ALN_CU(cudaMemcpyAsync(b->d_seq.p, b->h_seq.p, b->h_seq.used, cudaMemcpyHostToDevice, s));
     ALN_CU(cudaMemcpyAsync(b->d_jobs.p, b->jobs.data(), sizeof(AlnJob) * (size_t)n_aln, cudaMemcpyHostToDevice, s));
     if (!first.empty())
         ALN_CU(cudaMemcpyAsync(b->d_list[0].p, first.data(), sizeof(AlnRect) * first.size(), cudaMemcpyHostToDevice, s));
+    if (!first_tall.empty())
+        ALN_CU(cudaMemcpyAsync(b->d_tall[0].p, first_tall.data(), sizeof(AlnRect) * first_tall.size(), cudaMemcpyHostToDevice, s));
     if (!leaves0.empty())
         ALN_CU(cudaMemcpyAsync(b->d_leaves.p, leaves0.data(), sizeof(AlnRect) * leaves0.size(), cudaMemcpyHostToDevice, s));
     ALN_CU(cudaMemsetAsync(b->d_ops.p, 0xFF, (size_t)b->ops_bytes + 64, s));
     ALN_CU(cudaMemsetAsync(b->d_res.p, 0, sizeof(AlnResult) * (size_t)n_aln, s));
     /* the pageable vectors above (jobs, first, leaves0) must not be touched before the copies were issued from them:
      * cudaMemcpyAsync from pageable memory stages them before returning */
-    b->info.h2d_bytes = (int64_t)(b->h_seq.used + sizeof(AlnJob) * (size_t)n_aln + sizeof(AlnRect) * (first.size() + leaves0.size()) +
+    b->info.h2d_bytes = (int64_t)(b->h_seq.used + sizeof(AlnJob) * (size_t)n_aln + sizeof(AlnRect) * (first.size() + first_tall.size() + leaves0.size()) +
                                   sizeof(int32_t) * CT_WORDS);
 
     AlnKernelArgs a;
     a.slab = static_cast<uint8_t*>(b->d_slab.p);
     a.slot_bytes = b->slot_bytes;
+    a.team_slab = static_cast<uint8_t*>(b->d_team_slab.p);
+    a.team_slot_bytes = b->team_slot_bytes;
     a.max_len = b->slot_max_len;
     a.seq = static_cast<const uint8_t*>(b->d_seq.p);
     a.jobs = static_cast<const AlnJob*>(b->d_jobs.p);
@@ -523,27 +637,47 @@ int32_t b200aln_batch_align_all(b200aln_batch* b) {
     };
 
     ALN_CU(cudaEventRecord(b->ev0, s));
-    int32_t n_level = (int32_t)first.size();
+    int32_t n_level = (int32_t)first.size(), n_tall = (int32_t)first_tall.size();
     int32_t level = 0, launch = 0;
-    while (n_level > 0) {
-        if (level + 1 >= MAX_LEVELS) return B200ALN_GENERIC_ERROR;
+    b->info.team_launches = 0;
+    while (n_level + n_tall > 0) {
+        if (level + 1 >= MAX_LEVELS || launch + 4 >= 128) return B200ALN_GENERIC_ERROR;
         AlnLists next;
         next.open = static_cast<AlnRect*>(b->d_list[(level + 1) & 1].p);
-        next.n_open = ct + CT_NOPEN + level + 1;
+        next.n_open = ct + CT_NOPEN + 2 * (level + 1);
+        next.tall = static_cast<AlnRect*>(b->d_tall[(level + 1) & 1].p);
+        next.n_tall = ct + CT_NOPEN + 2 * (level + 1) + 1;
         next.cap_open = (int32_t)cap_open;
         next.leaves = static_cast<AlnRect*>(b->d_leaves.p);
         next.n_leaves = ct + CT_NLEAVES;
         next.cap_leaves = (int32_t)cap_leaves;
         next.overflow = ct + CT_OVERFLOW;
-        aln_split_kernel<<<grid_for(n_level), 32 * WARPS_PER_BLOCK, 0, s>>>(
-            a, static_cast<const AlnRect*>(b->d_list[level & 1].p), n_level, next, ct + CT_CURSOR + launch);
-        ALN_CU(cudaGetLastError());
-        ++launch;
-        b->info.n_open += n_level;
-        ALN_CU(cudaMemcpyAsync(b->h_counters + CT_NOPEN + level + 1, ct + CT_NOPEN + level + 1, sizeof(int32_t),
+        if (n_tall > 0) {
+            /* a team per tall sub-problem while the level is thin (its longest sub-problem bounds the level's time);
+             * one warp each once there are enough of them to fill the device anyway */
+            const AlnRect* tall = static_cast<const AlnRect*>(b->d_tall[level & 1].p);
+            if (b->n_team_blocks > 0 && n_tall <= ALN_TEAM_WAVES * b->n_team_blocks) {
+                aln_split_team_kernel<<<(unsigned)std::min(n_tall, b->n_team_blocks), 64 * ALN_TEAM, 0, s>>>(
+                    a, tall, n_tall, next, ct + CT_CURSOR + launch);
+                ++b->info.team_launches;
+            } else {
+                aln_split_kernel<<<grid_for(n_tall), 32 * WARPS_PER_BLOCK, 0, s>>>(a, tall, n_tall, next, ct + CT_CURSOR + launch);
+            }
+            ALN_CU(cudaGetLastError());
+            ++launch;
+        }
+        if (n_level > 0) {
+            aln_split_kernel<<<grid_for(n_level), 32 * WARPS_PER_BLOCK, 0, s>>>(
+                a, static_cast<const AlnRect*>(b->d_list[level & 1].p), n_level, next, ct + CT_CURSOR + launch);
+            ALN_CU(cudaGetLastError());
+            ++launch;
+        }
+        b->info.n_open += n_level + n_tall;
+        ALN_CU(cudaMemcpyAsync(b->h_counters + CT_NOPEN + 2 * (level + 1), ct + CT_NOPEN + 2 * (level + 1), 2 * sizeof(int32_t),
                                cudaMemcpyDeviceToHost, s));
         ALN_CU(cudaStreamSynchronize(s));
-        n_level = std::min<int32_t>(b->h_counters[CT_NOPEN + level + 1], (int32_t)cap_open);
+        n_level = std::min<int32_t>(b->h_counters[CT_NOPEN + 2 * (level + 1)], (int32_t)cap_open);
+        n_tall = std::min<int32_t>(b->h_counters[CT_NOPEN + 2 * (level + 1) + 1], (int32_t)cap_open);
         ++level;
     }
     b->info.levels = level;
@@ -773,6 +907,8 @@ int32_t b200aln_align_pairs(int32_t device_id, int64_t max_gpu_mem, int64_t n, c
         b200aln_batch_info bi;
         b200aln_batch_get_info(b, &bi);
         total.n_slots = bi.n_slots;
+        total.n_team_blocks = bi.n_team_blocks;
+        total.team_launches += bi.team_launches;
         total.levels = std::max(total.levels, bi.levels);
         total.kernel_launches += bi.kernel_launches;
         total.n_open += bi.n_open;

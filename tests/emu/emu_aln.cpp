@@ -32,14 +32,15 @@ int64_t emu_align(const uint8_t* q, int32_t n, const uint8_t* t, int32_t m, uint
     std::vector<uint8_t> ops((size_t)n + (size_t)m, OP_NONE);
     const int32_t cap_open = (int32_t)aln_open_capacity(n, m), cap_leaves = (int32_t)aln_leaf_capacity(n, m);
     std::vector<AlnRect> level((size_t)cap_open), next((size_t)cap_open), leaves((size_t)cap_leaves);
-    int32_t n_level = 0, n_next = 0, n_leaf = 0, overflow = 0, depth = 0;
-    AlnLists first{level.data(), &n_level, cap_open, leaves.data(), &n_leaf, cap_leaves, &overflow};
+    std::vector<AlnRect> tall((size_t)cap_open), next_tall((size_t)cap_open);
+    int32_t n_level = 0, n_next = 0, n_tall = 0, n_next_tall = 0, n_leaf = 0, overflow = 0, depth = 0;
+    AlnLists first{level.data(), &n_level, tall.data(), &n_tall, cap_open, leaves.data(), &n_leaf, cap_leaves, &overflow};
     aln_push(first, AlnRect{0, 0, n, 0, m, 1});
-    while (n_level > 0) {
-        n_next = 0;
-        AlnLists L{next.data(), &n_next, cap_open, leaves.data(), &n_leaf, cap_leaves, &overflow};
-        for (int32_t k = 0; k < n_level; ++k) {
-            const AlnRect r = level[(size_t)k];
+    while (n_level + n_tall > 0) {
+        n_next = n_next_tall = 0;
+        AlnLists L{next.data(), &n_next, next_tall.data(), &n_next_tall, cap_open, leaves.data(), &n_leaf, cap_leaves, &overflow};
+        for (int32_t k = 0; k < n_level + n_tall; ++k) { /* the emulation runs tall sub-problems on one warp as well */
+            const AlnRect r = k < n_level ? level[(size_t)k] : tall[(size_t)(k - n_level)];
             AlnSplit sp;
             aln_split(s, eq, q + r.r0, t + r.c0, r.n, r.m, &sp);
             if (r.top) *score = sp.best;
@@ -49,7 +50,9 @@ int64_t emu_align(const uint8_t* q, int32_t n, const uint8_t* t, int32_t m, uint
             aln_push(L, lr);
         }
         level.swap(next);
+        tall.swap(next_tall);
         n_level = n_next;
+        n_tall = n_next_tall;
         ++depth;
     }
     if (overflow) return -2;

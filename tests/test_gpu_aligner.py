@@ -54,7 +54,10 @@ def test_random_pairs_equal_the_oracle(oracle, aligner):
     aligner.align_all()
     got = aligner.generate_cigar_strings()
     info = aligner.info()
-    assert info["levels"] >= 2 and info["n_leaves"] >= len(pairs) and info["kernel_launches"] == info["levels"] + 2
+    assert info["levels"] >= 2 and info["n_leaves"] >= len(pairs)
+    # per level one launch for the one-stripe sub-problems and one for the tall ones; then the leaves, then the CIGARs
+    assert info["levels"] + 2 <= info["kernel_launches"] <= 2 * info["levels"] + 2
+    assert info["team_launches"] >= 1  # a thin level's tall sub-problems went to teams of warps
     for k, (q, t) in enumerate(pairs):
         ops, score = oracle_align(oracle, q, t)
         cigar, ed = got[k]
