@@ -17,7 +17,8 @@ scaling).  One step = one pass of the hot path over the whole batch of windows.
              x 2 B x 2 (one write + one read), SURVEY.md 8(d) / BASELINE.md 4.
   cpu_baseline  the reference's own CPU path (oracle/_ref: racon::Window + spoa AVX2) timed on this
              box's host cores over a bounded sample of the same windows (rank 0, N=1).
-  extra      (N=1 only, outside the headline timing) the same measurements for BASELINE configs[2]
+  extra      (N=1 only, outside the headline timing) the overlap aligner on real overlaps, and
+             the same measurements for BASELINE configs[2]
              (A_full: full band, the bit-exact mode) and configs[4]'s shape (B_banded: 1024 bp x 64 reads, 12 %,
              band 256, max_sequence_size 1279), and the headline workload with the MSA output switched on.
 
@@ -336,6 +337,78 @@ def measure_msa(args, local_rank, device, steps=3, warmup=3):
             "note": "kernel with consensus + MSA, inputs resident; the MSA download moves exactly the bytes produced"}
 
 
+def measure_aligner(args, local_rank, rep=32, steps=3, warmup=2, cpu_seconds=6.0):
+    """extra: the overlap alignment step before the POA path (CUDABatchAligner; include/b200aln.h) on REAL
+    overlaps -- the 181 read-to-contig overlaps of the reference's lambda-phage test data (tests/golden/lambda_overlaps.npz,
+    1.4-11 kb, cut like src/overlap.cpp:186-199), replicated `rep` times.  e2e = host buffers in, CIGAR bytes out through
+    the C ABI (staging, H2D, all launches, D2H); kernel = distance-matrix cells computed / device time of the launches."""
+    from concurrent.futures import ThreadPoolExecutor
+    from common import overlap_fixture
+    from racon_gpu_b200.aligner import CUDABatchAligner, pack_pairs
+    fx = overlap_fixture()
+    pairs = [(f["q"], f["t"]) for f in fx] * rep
+    q, qo, t, to = pack_pairs(pairs)
+    matrix = float(sum(len(x) * len(y) for x, y in pairs))
+    al = CUDABatchAligner(device_id=local_rank, max_gpu_memory=32 << 30)
+    recs = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        first, rec, eds = 0, {"kernel_ms": 0.0, "cells": 0, "h2d": 0, "d2h": 0, "launches": 0, "team_launches": 0, "batches": 0}, []
+        while first < len(pairs):
+            first += al.add_overlaps(q, qo, t, to, first)
+            al.align_all()
+            text, off, ln, ed = al.cigars()
+            info = al.info()
+            al.reset()
+            eds.append(ed)
+            for k, kk in (("kernel_ms", "kernel_ms"), ("cells", "cells"), ("h2d", "h2d_bytes"), ("d2h", "d2h_bytes"),
+                          ("launches", "kernel_launches"), ("team_launches", "team_launches")):
+                rec[k] += info[kk]
+            rec["batches"] += 1
+            rec["slots"], rec["levels"] = info["n_slots"], info["levels"]
+        rec["wall_s"] = time.perf_counter() - t0
+        if it == 0 and [int(x) for x in np.concatenate(eds)[:len(fx)]] != [f["score"] for f in fx]:
+            raise RuntimeError("aligner: edit distances differ from the committed edlib results")
+        if it >= warmup:
+            recs.append(rec)
+    al.close()
+    wall = sum(r["wall_s"] for r in recs) / len(recs)
+    kms = sum(r["kernel_ms"] for r in recs) / len(recs)
+    r0 = recs[0]
+    sm_mhz = 1965.0
+    peak = 148 * 4 * sm_mhz * 1e6 / (2.0 * 33.0) * 2048.0  # see DESIGN.md section 11: ALU pipe, 33 instructions a step
+    out = {"workload": f"real lambda-phage overlaps x{rep}: {len(pairs)} pairs, {int(qo[-1] + to[-1])} bases, "
+                       f"{matrix:.3g} matrix cells, unit-cost NW with path (edlib's alignment, bit-exact)",
+           "steps": steps, "warmup": warmup, "unit": "overlaps/s",
+           "e2e": len(pairs) / wall, "value": len(pairs) / (kms / 1e3), "ms_per_step": kms, "e2e_ms_per_step": wall * 1e3,
+           "matrix_gcups_e2e": matrix / wall / 1e9, "h2d_bytes_per_step": r0["h2d"], "d2h_bytes_per_step": r0["d2h"],
+           "gpu_launches_per_step": r0["launches"], "team_launches_per_step": r0["team_launches"], "levels": r0["levels"],
+           "resident_warps": r0["slots"], "batches_per_step": r0["batches"],
+           "roofline": {"bound": "alu", "achieved": r0["cells"] / (kms / 1e3) / 1e9, "peak": peak / 1e9, "unit": "Gcell/s",
+                        "frac": r0["cells"] / (kms / 1e3) / peak, "traffic": None,
+                        "kernel": "aln_split_kernel / aln_split_team_kernel / aln_leaf_kernel (all launches of a step)",
+                        "cells_computed_per_step": r0["cells"],
+                        "peak_source": "148 SMs x 4 schedulers x 1965 MHz / (33 ALU-pipe instructions x 2 cycles) per "
+                                       "32-lane x 64-row step (SASS count, DESIGN.md section 11)"}}
+    try:  # CPU side: the unmodified edlib as racon calls it (oracle/_ref), bounded sample, usable cores
+        from oracle_lib import Ref, ref_align
+        r = Ref()
+        if r.available and not args.no_cpu_baseline:
+            threads, core_info = usable_cores()
+            t0, done = time.perf_counter(), 0
+            with ThreadPoolExecutor(threads) as ex:
+                while time.perf_counter() - t0 < cpu_seconds:
+                    list(ex.map(lambda p: ref_align(r, p[0], p[1])[1], pairs[:len(fx)]))
+                    done += len(fx)
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": done / dt, "unit": "overlaps/s", "cores": threads, "kind": "reference",
+                                   "sample": f"{done} alignments ({done // len(fx)} passes over the 181 overlaps), {dt:.1f} s, "
+                                             f"edlibAlign(NW, path) + edlibAlignmentToCigar as src/overlap.cpp:205-224"}
+    except Exception as e:  # the product's numbers do not depend on the checker
+        out["cpu_baseline"] = {"unavailable": str(e)}
+    return out
+
+
 def roofline_block(name, m, steps):
     bytes_per_window, cells = algorithmic_bytes_per_window(m["batch"], m["banded"])
     peak, peak_src = measured_hbm_peak()
@@ -434,6 +507,7 @@ def main():
                 "h2d_bytes_per_step": x["h2d"], "d2h_bytes_per_step": x["d2h"],
                 "resident_warps": x["info"]["n_slots"], "roofline": roofline_block(name, x, 3)}
         extra["A_banded_msa"] = measure_msa(args, local_rank, device)
+        extra["overlap_aligner"] = measure_aligner(args, local_rank)
         result["extra"] = extra
     print(json.dumps(result))
     if world > 1:

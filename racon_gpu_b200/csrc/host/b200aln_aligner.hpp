@@ -4,7 +4,7 @@
  * (/root/reference/vendor/GenomeWorks/cudaaligner/include/claraparabricks/genomeworks/cudaaligner/
  * aligner.hpp:43-132, alignment.hpp:55-105, cudaaligner.hpp:34-58) over the C ABI (include/b200aln.h), so that the
  * body of racon's src/cuda/cudaaligner.cpp builds against it with only its includes / usings changed (INTEGRATION.md
- * section 6; tests/test_boundary.py compiles exactly that).
+ * section 5; tests/test_boundary.py compiles exactly that).
  *
  * Argument order: cudaaligner's (query, target) are racon's (target, query) -- racon's adapter swaps them at its call
  * site (cudaaligner.cpp:60-63) and reads the CIGAR back in racon's sense.  The shim keeps that call site intact: it

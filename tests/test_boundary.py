@@ -44,7 +44,7 @@ def test_racons_cudabatch_builds_against_the_shim_with_the_documented_diff(tmp_p
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src", "cuda")), reason="reference sources not present")
 def test_racons_cudaaligner_builds_against_the_shim_with_the_documented_diff(tmp_path):
-    """INTEGRATION.md section 6: racon's CUDABatchAligner (src/cuda/cudaaligner.{hpp,cpp}) over b200aln_aligner.hpp."""
+    """INTEGRATION.md section 5: racon's CUDABatchAligner (src/cuda/cudaaligner.{hpp,cpp}) over b200aln_aligner.hpp."""
     for f in ("cudaaligner.hpp", "cudaaligner.cpp"):
         shutil.copy(os.path.join(REF, "src", "cuda", f), tmp_path / f)
         os.chmod(tmp_path / f, 0o644)
