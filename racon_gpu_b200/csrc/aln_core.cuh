@@ -62,8 +62,14 @@ ALN_HD bool aln_is_leaf(int32_t n, int32_t m) {
     return (2 * 8 + 4) * blocks * (int64_t)m + 2 * 4 * (int64_t)m < ALN_LEAF_DATA_LIMIT;
 }
 
-/* more than one 32-block stripe of rows? */
-ALN_HD bool aln_is_tall(int32_t n) { return n > 64 * 32; }
+/* Open sub-problems by shape: 0 = at most one 32-block stripe of rows (one warp is all they can use), 1 = tall (several
+ * stripes), 2 = huge (at least four stripes and so many cells that ONE of them on one warp would outlast a whole level of
+ * ordinary ones: these always go to teams of warps) */
+enum { ALN_SHORT = 0, ALN_TALL = 1, ALN_HUGE = 2, ALN_CLASSES = 3 };
+ALN_HD int aln_shape(int32_t n, int32_t m) {
+    if (n <= 64 * 32) return ALN_SHORT;
+    return (n >= 4 * 64 * 32 && (int64_t)n * m >= (int64_t)32 << 20) ? ALN_HUGE : ALN_TALL;
+}
 
 /* one open sub-problem: rows [r0, r0 + n) of the query, columns [c0, c0 + m) of the target */
 struct AlnRect {
@@ -79,11 +85,9 @@ struct AlnSplit { /* result of one Hirschberg step */
 
 /* the open list of the next level, the leaf list, and where an overflow of either is reported */
 struct AlnLists {
-    AlnRect* open;  /* sub-problems of at most one 32-block stripe (one warp each)                                  */
-    int32_t* n_open;
-    AlnRect* tall;  /* taller ones: a team of warps each when the level is too small to fill the device otherwise  */
-    int32_t* n_tall;
-    int32_t cap_open; /* of either list */
+    AlnRect* open[ALN_CLASSES]; /* the next level's open sub-problems by shape (aln_shape) */
+    int32_t* n_open;            /* [ALN_CLASSES] adjacent counters */
+    int32_t cap_open;           /* of each list */
     AlnRect* leaves;
     int32_t* n_leaves;
     int32_t cap_leaves;
@@ -164,9 +168,9 @@ POA_FN int32_t aln_take(int32_t* counter) { /* called by ONE lane */
 POA_FN void aln_push(const AlnLists& L, const AlnRect r) {
     if (r.n == 0 && r.m == 0) return;
     const bool leaf = aln_is_leaf(r.n, r.m);
-    const bool tall = aln_is_tall(r.n);
-    const int32_t k = aln_take(leaf ? L.n_leaves : tall ? L.n_tall : L.n_open);
-    if (k < (leaf ? L.cap_leaves : L.cap_open)) (leaf ? L.leaves : tall ? L.tall : L.open)[k] = r;
+    const int shape = aln_shape(r.n, r.m);
+    const int32_t k = aln_take(leaf ? L.n_leaves : L.n_open + shape);
+    if (k < (leaf ? L.cap_leaves : L.cap_open)) (leaf ? L.leaves : L.open[shape])[k] = r;
     else *L.overflow = 1;
 }
 /* upper-left and lower-right sub-problems of `r` split at query index sr (relative, -1 .. n-1), edlib.cpp:1321-1333 */
@@ -294,15 +298,17 @@ POA_FN uint64_t eq_other(const SeqView q, int32_t row0, int32_t cnt, int tc) {
  * The column's character code comes straight from the slot's code row (loaded one step ahead), its match mask from the
  * lane's shared-memory table.
  */
-POA_FN_NOINLINE void myers_pass(const SeqView q, int32_t n, const SeqView t, int32_t cols, const TeamCtx team, uint32_t* hbuf,
+template <bool TEAM>
+POA_FN_NOINLINE void myers_pass(const SeqView q, int32_t n, const SeqView t, int32_t cols, const TeamCtx team_in, uint32_t* hbuf,
                                 int32_t hrow_words, uint8_t* tcode_base, const EqTab eq_in, int32_t* out_col, RecPM* PM,
                                 int32_t* S) {
     n = poa_uniform(n);
     cols = poa_uniform(cols);
     EqTab eq = eq_in; /* by value: a reference would live in local memory and be re-read every step */
+    const TeamCtx team = TEAM ? team_in : TeamCtx{0, 1, 0, 0}; /* TEAM = false: the team code folds away */
     const int32_t B = (n + 63) / 64;
     uint8_t* tcode = tcode_base + 64; /* tcode[-64 .. cols + 63] may be read (by lanes whose column is out of range) */
-    if (team.n > 1) {
+    if (TEAM && team.n > 1) {
         POA_LANE0 { team_publish(team, 0, 0); } /* progress words of the previous pass are void */
     }
     for (int32_t base = -64 + 32 * team.w; base < cols + 64; base += 32 * team.n) {
@@ -316,14 +322,14 @@ POA_FN_NOINLINE void myers_pass(const SeqView q, int32_t n, const SeqView t, int
     }
     POA_SYNC();
     POA_FENCE();
-    team_barrier(team);
+    if (TEAM) team_barrier(team);
     const int32_t n_stripes = (B + 31) / 32;
     for (int32_t sidx = team.w; sidx < n_stripes; sidx += team.n) {
         const int32_t s0 = 32 * sidx;
         const int32_t nb = B - s0 < 32 ? B - s0 : 32;
         const bool more = s0 + 32 < B; /* another stripe follows: the last lane's horizontal deltas are kept */
         const bool lower = s0 > 0;     /* lane 0 enters with the deltas the stripe above left behind */
-        const bool piped = lower && team.n > 1;
+        const bool piped = TEAM && lower && team.n > 1;
         const uint32_t* row_in = hbuf + (int64_t)((sidx + team.n - 1) % team.n) * hrow_words;
         uint32_t* row_out = hbuf + (int64_t)(sidx % team.n) * hrow_words;
         uint32_t hword = 0x55555555u, hword_next = 0x55555555u; /* stripe 0: D[0][j] = j, every delta + 1 */
@@ -407,7 +413,7 @@ POA_FN_NOINLINE void myers_pass(const SeqView q, int32_t n, const SeqView t, int
                         if ((c & 15) == 15 || c == cols - 1) {
                             row_out[c >> 4] = (uint32_t)hacc[l];
                             hacc[l] = 0;
-                            if (team.n > 1 && ((c & 31) == 31 || c == cols - 1)) team_publish(team, sidx, c + 1);
+                            if (TEAM && team.n > 1 && ((c & 31) == 31 || c == cols - 1)) team_publish(team, sidx, c + 1);
                         }
                     }
                     link[l] = out;
@@ -496,8 +502,8 @@ POA_FN_NOINLINE void aln_split(const AlnSlot& s_ref, EqTab& eq, const uint8_t* q
     n = poa_uniform(n);
     m = poa_uniform(m);
     const int32_t lh = m / 2, rh = m - lh;
-    myers_pass(SeqView{q, 1}, n, SeqView{t, 1}, lh, TeamCtx{0, 1, 0, 0}, s.hbuf, 0, s.tcode, eq, s.Lc, nullptr, nullptr);
-    myers_pass(SeqView{q + (n - 1), -1}, n, SeqView{t + (m - 1), -1}, rh, TeamCtx{0, 1, 0, 0}, s.hbuf, 0, s.tcode, eq, s.Rr, nullptr,
+    myers_pass<false>(SeqView{q, 1}, n, SeqView{t, 1}, lh, TeamCtx{0, 1, 0, 0}, s.hbuf, 0, s.tcode, eq, s.Lc, nullptr, nullptr);
+    myers_pass<false>(SeqView{q + (n - 1), -1}, n, SeqView{t + (m - 1), -1}, rh, TeamCtx{0, 1, 0, 0}, s.hbuf, 0, s.tcode, eq, s.Rr, nullptr,
                nullptr);
     aln_split_rule(s.Lc, s.Rr, n, m, out);
 }
@@ -567,7 +573,7 @@ POA_FN_NOINLINE void aln_leaf(const AlnSlot& s_ref, EqTab& eq, const uint8_t* q,
         POA_SYNC();
         return;
     }
-    myers_pass(SeqView{q, 1}, n, SeqView{t, 1}, m, TeamCtx{0, 1, 0, 0}, s.hbuf, 0, s.tcode, eq, nullptr, s.PM, s.S);
+    myers_pass<false>(SeqView{q, 1}, n, SeqView{t, 1}, m, TeamCtx{0, 1, 0, 0}, s.hbuf, 0, s.tcode, eq, nullptr, s.PM, s.S);
     const int32_t B = (n + 63) / 64;
     LeafWindow win;
     int32_t i = n - 1, j = m - 1, jw = j;

@@ -45,14 +45,14 @@ struct AlnResult {
 
 enum { /* int32 words of the device counter block */
     CT_CURSOR = 0,      /* [128] one work cursor per launch                                  */
-    CT_NOPEN = 128,     /* [64][2] sub-problems open at level k: short, tall (adjacent words) */
+    CT_NOPEN = 128,     /* [32][4] sub-problems open at level k by shape (3 adjacent words + pad) */
     CT_NLEAVES = 256,
     CT_OVERFLOW = 257,
     CT_RUNS = 258,      /* u64: entries used in the runs arena                               */
     CT_CELLS = 260,     /* u64: distance-matrix cells computed                               */
     CT_TEXT = 262,      /* u64: bytes used in the CIGAR text arena                           */
     CT_WORDS = 264,
-    MAX_LEVELS = 60
+    MAX_LEVELS = 31
 };
 
 struct AlnKernelArgs {
@@ -175,9 +175,9 @@ __global__ void __launch_bounds__(64 * ALN_TEAM, 1024 / (64 * ALN_TEAM)) aln_spl
         const uint8_t* t = a.seq + job.t_off + r.c0;
         const int32_t lh = r.m / 2, rh = r.m - lh; /* edlib.cpp:1216-1217 */
         if (side == 0)
-            myers_pass(SeqView{q, 1}, r.n, SeqView{t, 1}, lh, team, ts.hrow[0], hrow_words, ts.tcode[0], eq, ts.Lc, nullptr, nullptr);
+            myers_pass<true>(SeqView{q, 1}, r.n, SeqView{t, 1}, lh, team, ts.hrow[0], hrow_words, ts.tcode[0], eq, ts.Lc, nullptr, nullptr);
         else
-            myers_pass(SeqView{q + (r.n - 1), -1}, r.n, SeqView{t + (r.m - 1), -1}, rh, team, ts.hrow[1], hrow_words, ts.tcode[1],
+            myers_pass<true>(SeqView{q + (r.n - 1), -1}, r.n, SeqView{t + (r.m - 1), -1}, rh, team, ts.hrow[1], hrow_words, ts.tcode[1],
                        eq, ts.Rr, nullptr, nullptr);
         __threadfence_block();
         __syncthreads(); /* both middle columns are complete */
@@ -313,6 +313,8 @@ struct PinnedBuf { /* grow-only page-locked host buffer, contents preserved */
 struct b200aln_batch {
     int32_t device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr; /* huge sub-problems run on teams beside a saturated level's one-warp grid */
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool own_stream = false;
     int64_t budget = 0;
     int32_t sm_count = 0, blocks_per_sm = 0;
@@ -326,7 +328,7 @@ struct b200aln_batch {
     int64_t var_bytes = 0; /* device bytes the staged alignments need besides the slots */
 
     /* device */
-    DevBuf d_slab, d_team_slab, d_seq, d_jobs, d_ops, d_res, d_runs, d_text, d_list[2], d_tall[2], d_leaves, d_counters;
+    DevBuf d_slab, d_team_slab, d_seq, d_jobs, d_ops, d_res, d_runs, d_text, d_list[ALN_CLASSES][2], d_leaves, d_counters;
     int32_t n_slots = 0, slot_max_len = 0, n_team_blocks = 0, team_blocks_per_sm = 0;
     size_t slot_bytes = 0, team_slot_bytes = 0;
 
@@ -437,11 +439,17 @@ void b200aln_batch_destroy(b200aln_batch* b) {
     b->d_res.release();
     b->d_runs.release();
     b->d_text.release();
-    b->d_list[0].release();
-    b->d_list[1].release();
-    b->d_tall[0].release();
-    b->d_tall[1].release();
+    for (int c = 0; c < ALN_CLASSES; ++c) {
+        b->d_list[c][0].release();
+        b->d_list[c][1].release();
+    }
     b->d_team_slab.release();
+    if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+    if (b->ev_join) cudaEventDestroy(b->ev_join);
+    if (b->side) {
+        cudaStreamSynchronize(b->side);
+        cudaStreamDestroy(b->side);
+    }
     b->d_leaves.release();
     b->d_counters.release();
     b->h_seq.release();
@@ -499,7 +507,10 @@ int32_t b200aln_batch_create(int32_t device_id, void* stream, int64_t max_gpu_me
         }
         b->team_blocks_per_sm = std::max(0, bps_team);
         if (cudaHostAlloc(reinterpret_cast<void**>(&b->h_counters), CT_WORDS * sizeof(int32_t), cudaHostAllocDefault) != cudaSuccess ||
-            cudaEventCreate(&b->ev0) != cudaSuccess || cudaEventCreate(&b->ev1) != cudaSuccess) {
+            cudaEventCreate(&b->ev0) != cudaSuccess || cudaEventCreate(&b->ev1) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming) != cudaSuccess) {
             st = B200ALN_CUDA_ERROR;
             break;
         }
@@ -571,16 +582,20 @@ int32_t b200aln_batch_align_all(b200aln_batch* b) {
     b->info.n_team_blocks = b->n_team_blocks;
 
     /* the first level, classified on the host: largest first, so the persistent grid starts with the long ones */
-    std::vector<AlnRect> first, first_tall, leaves0;
+    std::vector<AlnRect> first[ALN_CLASSES], leaves0;
     for (int32_t k = 0; k < n_aln; ++k) {
         const AlnJob& j = b->jobs[(size_t)k];
         if (j.n == 0 && j.m == 0) continue;
-        (aln_is_leaf(j.n, j.m) ? leaves0 : aln_is_tall(j.n) ? first_tall : first).push_back(AlnRect{k, 0, j.n, 0, j.m, 1});
+        (aln_is_leaf(j.n, j.m) ? leaves0 : first[aln_shape(j.n, j.m)]).push_back(AlnRect{k, 0, j.n, 0, j.m, 1});
     }
     const auto larger = [](const AlnRect& x, const AlnRect& y) { return (int64_t)x.n * x.m > (int64_t)y.n * y.m; };
-    std::stable_sort(first.begin(), first.end(), larger);
-    std::stable_sort(first_tall.begin(), first_tall.end(), larger);
-    const int64_t cap_open = std::max<int64_t>(b->cap_open, (int64_t)std::max(first.size(), first_tall.size())) + 16;
+    size_t first_total = 0, first_max = 0;
+    for (int c = 0; c < ALN_CLASSES; ++c) {
+        std::stable_sort(first[c].begin(), first[c].end(), larger);
+        first_total += first[c].size();
+        first_max = std::max(first_max, first[c].size());
+    }
+    const int64_t cap_open = std::max<int64_t>(b->cap_open, (int64_t)first_max) + 16;
     const int64_t cap_leaves = std::max<int64_t>(b->cap_leaves, (int64_t)leaves0.size()) + 16;
     if (cap_open >= 0x7FFFFFFF || cap_leaves >= 0x7FFFFFFF) return B200ALN_EXCEEDED_MAX_ALIGNMENTS;
 
@@ -591,33 +606,31 @@ int32_t b200aln_batch_align_all(b200aln_batch* b) {
     ALN_CU(b->d_runs.need(sizeof(uint32_t) * ((size_t)b->ops_bytes + 64)));
     const unsigned long long text_cap = 2ull * (unsigned long long)b->ops_bytes + (unsigned long long)n_aln + 64; /* "1M1I..." at worst */
     ALN_CU(b->d_text.need((size_t)text_cap));
-    ALN_CU(b->d_list[0].need(sizeof(AlnRect) * (size_t)cap_open));
-    ALN_CU(b->d_list[1].need(sizeof(AlnRect) * (size_t)cap_open));
-    ALN_CU(b->d_tall[0].need(sizeof(AlnRect) * (size_t)cap_open));
-    ALN_CU(b->d_tall[1].need(sizeof(AlnRect) * (size_t)cap_open));
+    for (int c = 0; c < ALN_CLASSES; ++c) {
+        ALN_CU(b->d_list[c][0].need(sizeof(AlnRect) * (size_t)cap_open));
+        ALN_CU(b->d_list[c][1].need(sizeof(AlnRect) * (size_t)cap_open));
+    }
     ALN_CU(b->d_leaves.need(sizeof(AlnRect) * (size_t)cap_leaves));
     ALN_CU(b->d_counters.need(sizeof(int32_t) * CT_WORDS));
 
     cudaStream_t s = b->stream;
     int32_t* ct = static_cast<int32_t*>(b->d_counters.p);
     std::memset(b->h_counters, 0, sizeof(int32_t) * CT_WORDS);
-    b->h_counters[CT_NOPEN] = (int32_t)first.size();
-    b->h_counters[CT_NOPEN + 1] = (int32_t)first_tall.size();
+    for (int c = 0; c < ALN_CLASSES; ++c) b->h_counters[CT_NOPEN + c] = (int32_t)first[c].size();
     b->h_counters[CT_NLEAVES] = (int32_t)leaves0.size();
     ALN_CU(cudaMemcpyAsync(ct, b->h_counters, sizeof(int32_t) * CT_WORDS, cudaMemcpyHostToDevice, s));
     ALN_CU(cudaMemcpyAsync(b->d_seq.p, b->h_seq.p, b->h_seq.used, cudaMemcpyHostToDevice, s));
     ALN_CU(cudaMemcpyAsync(b->d_jobs.p, b->jobs.data(), sizeof(AlnJob) * (size_t)n_aln, cudaMemcpyHostToDevice, s));
-    if (!first.empty())
-        ALN_CU(cudaMemcpyAsync(b->d_list[0].p, first.data(), sizeof(AlnRect) * first.size(), cudaMemcpyHostToDevice, s));
-    if (!first_tall.empty())
-        ALN_CU(cudaMemcpyAsync(b->d_tall[0].p, first_tall.data(), sizeof(AlnRect) * first_tall.size(), cudaMemcpyHostToDevice, s));
+    for (int c = 0; c < ALN_CLASSES; ++c)
+        if (!first[c].empty())
+            ALN_CU(cudaMemcpyAsync(b->d_list[c][0].p, first[c].data(), sizeof(AlnRect) * first[c].size(), cudaMemcpyHostToDevice, s));
     if (!leaves0.empty())
         ALN_CU(cudaMemcpyAsync(b->d_leaves.p, leaves0.data(), sizeof(AlnRect) * leaves0.size(), cudaMemcpyHostToDevice, s));
     ALN_CU(cudaMemsetAsync(b->d_ops.p, 0xFF, (size_t)b->ops_bytes + 64, s));
     ALN_CU(cudaMemsetAsync(b->d_res.p, 0, sizeof(AlnResult) * (size_t)n_aln, s));
     /* the pageable vectors above (jobs, first, leaves0) must not be touched before the copies were issued from them:
      * cudaMemcpyAsync from pageable memory stages them before returning */
-    b->info.h2d_bytes = (int64_t)(b->h_seq.used + sizeof(AlnJob) * (size_t)n_aln + sizeof(AlnRect) * (first.size() + first_tall.size() + leaves0.size()) +
+    b->info.h2d_bytes = (int64_t)(b->h_seq.used + sizeof(AlnJob) * (size_t)n_aln + sizeof(AlnRect) * (first_total + leaves0.size()) +
                                   sizeof(int32_t) * CT_WORDS);
 
     AlnKernelArgs a;
@@ -637,47 +650,67 @@ int32_t b200aln_batch_align_all(b200aln_batch* b) {
     };
 
     ALN_CU(cudaEventRecord(b->ev0, s));
-    int32_t n_level = (int32_t)first.size(), n_tall = (int32_t)first_tall.size();
+    int32_t n_open[ALN_CLASSES];
+    for (int c = 0; c < ALN_CLASSES; ++c) n_open[c] = (int32_t)first[c].size();
     int32_t level = 0, launch = 0;
     b->info.team_launches = 0;
-    while (n_level + n_tall > 0) {
+    while (n_open[ALN_SHORT] + n_open[ALN_TALL] + n_open[ALN_HUGE] > 0) {
         if (level + 1 >= MAX_LEVELS || launch + 4 >= 128) return B200ALN_GENERIC_ERROR;
+        int32_t* ct_next = ct + CT_NOPEN + 4 * (level + 1);
         AlnLists next;
-        next.open = static_cast<AlnRect*>(b->d_list[(level + 1) & 1].p);
-        next.n_open = ct + CT_NOPEN + 2 * (level + 1);
-        next.tall = static_cast<AlnRect*>(b->d_tall[(level + 1) & 1].p);
-        next.n_tall = ct + CT_NOPEN + 2 * (level + 1) + 1;
+        for (int c = 0; c < ALN_CLASSES; ++c) next.open[c] = static_cast<AlnRect*>(b->d_list[c][(level + 1) & 1].p);
+        next.n_open = ct_next;
         next.cap_open = (int32_t)cap_open;
         next.leaves = static_cast<AlnRect*>(b->d_leaves.p);
         next.n_leaves = ct + CT_NLEAVES;
         next.cap_leaves = (int32_t)cap_leaves;
         next.overflow = ct + CT_OVERFLOW;
-        if (n_tall > 0) {
-            /* a team per tall sub-problem while the level is thin (its longest sub-problem bounds the level's time);
-             * one warp each once there are enough of them to fill the device anyway */
-            const AlnRect* tall = static_cast<const AlnRect*>(b->d_tall[level & 1].p);
-            if (b->n_team_blocks > 0 && n_tall <= ALN_TEAM_WAVES * b->n_team_blocks) {
-                aln_split_team_kernel<<<(unsigned)std::min(n_tall, b->n_team_blocks), 64 * ALN_TEAM, 0, s>>>(
-                    a, tall, n_tall, next, ct + CT_CURSOR + launch);
-                ++b->info.team_launches;
+        const auto list = [&](int c) { return static_cast<const AlnRect*>(b->d_list[c][level & 1].p); };
+        const auto team = [&](int c, cudaStream_t on) {
+            aln_split_team_kernel<<<(unsigned)std::min(n_open[c], b->n_team_blocks), 64 * ALN_TEAM, 0, on>>>(
+                a, list(c), n_open[c], next, ct + CT_CURSOR + launch);
+            ++launch;
+            ++b->info.team_launches;
+        };
+        const auto solo = [&](int c) {
+            aln_split_kernel<<<grid_for(n_open[c]), 32 * WARPS_PER_BLOCK, 0, s>>>(a, list(c), n_open[c], next, ct + CT_CURSOR + launch);
+            ++launch;
+        };
+        /* Thin level (its longest sub-problem bounds its time): a team of warps per tall or huge sub-problem.  Saturated
+         * level (enough sub-problems to fill the device one warp each): the huge ones -- any of which would outlast the rest
+         * of the level on one warp -- still go to teams, on a side stream beside the one-warp grid. */
+        const bool teams = b->n_team_blocks > 0;
+        const bool thin = teams && (int64_t)n_open[ALN_TALL] + n_open[ALN_HUGE] <= (int64_t)ALN_TEAM_WAVES * b->n_team_blocks;
+        bool forked = false;
+        if (n_open[ALN_HUGE] > 0) {
+            if (thin || !teams) {
+                if (teams) team(ALN_HUGE, s);
+                else solo(ALN_HUGE);
             } else {
-                aln_split_kernel<<<grid_for(n_tall), 32 * WARPS_PER_BLOCK, 0, s>>>(a, tall, n_tall, next, ct + CT_CURSOR + launch);
+                ALN_CU(cudaEventRecord(b->ev_fork, s));
+                ALN_CU(cudaStreamWaitEvent(b->side, b->ev_fork, 0));
+                team(ALN_HUGE, b->side);
+                ALN_CU(cudaEventRecord(b->ev_join, b->side));
+                forked = true;
             }
             ALN_CU(cudaGetLastError());
-            ++launch;
         }
-        if (n_level > 0) {
-            aln_split_kernel<<<grid_for(n_level), 32 * WARPS_PER_BLOCK, 0, s>>>(
-                a, static_cast<const AlnRect*>(b->d_list[level & 1].p), n_level, next, ct + CT_CURSOR + launch);
+        if (n_open[ALN_TALL] > 0) {
+            if (thin) team(ALN_TALL, s);
+            else solo(ALN_TALL);
             ALN_CU(cudaGetLastError());
-            ++launch;
         }
-        b->info.n_open += n_level + n_tall;
-        ALN_CU(cudaMemcpyAsync(b->h_counters + CT_NOPEN + 2 * (level + 1), ct + CT_NOPEN + 2 * (level + 1), 2 * sizeof(int32_t),
+        if (n_open[ALN_SHORT] > 0) {
+            solo(ALN_SHORT);
+            ALN_CU(cudaGetLastError());
+        }
+        if (forked) ALN_CU(cudaStreamWaitEvent(s, b->ev_join, 0));
+        b->info.n_open += (int64_t)n_open[0] + n_open[1] + n_open[2];
+        ALN_CU(cudaMemcpyAsync(b->h_counters + CT_NOPEN + 4 * (level + 1), ct_next, ALN_CLASSES * sizeof(int32_t),
                                cudaMemcpyDeviceToHost, s));
         ALN_CU(cudaStreamSynchronize(s));
-        n_level = std::min<int32_t>(b->h_counters[CT_NOPEN + 2 * (level + 1)], (int32_t)cap_open);
-        n_tall = std::min<int32_t>(b->h_counters[CT_NOPEN + 2 * (level + 1) + 1], (int32_t)cap_open);
+        for (int c = 0; c < ALN_CLASSES; ++c)
+            n_open[c] = std::min<int32_t>(b->h_counters[CT_NOPEN + 4 * (level + 1) + c], (int32_t)cap_open);
         ++level;
     }
     b->info.levels = level;

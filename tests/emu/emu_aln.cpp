@@ -31,28 +31,43 @@ int64_t emu_align(const uint8_t* q, int32_t n, const uint8_t* t, int32_t m, uint
     aln_slot_bind(s, reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(slab.data()) + 255) & ~uintptr_t(255)), max_len, nullptr);
     std::vector<uint8_t> ops((size_t)n + (size_t)m, OP_NONE);
     const int32_t cap_open = (int32_t)aln_open_capacity(n, m), cap_leaves = (int32_t)aln_leaf_capacity(n, m);
-    std::vector<AlnRect> level((size_t)cap_open), next((size_t)cap_open), leaves((size_t)cap_leaves);
-    std::vector<AlnRect> tall((size_t)cap_open), next_tall((size_t)cap_open);
-    int32_t n_level = 0, n_next = 0, n_tall = 0, n_next_tall = 0, n_leaf = 0, overflow = 0, depth = 0;
-    AlnLists first{level.data(), &n_level, tall.data(), &n_tall, cap_open, leaves.data(), &n_leaf, cap_leaves, &overflow};
+    std::vector<AlnRect> level[ALN_CLASSES], next[ALN_CLASSES], leaves((size_t)cap_leaves);
+    int32_t n_level[ALN_CLASSES] = {0, 0, 0}, n_next[ALN_CLASSES] = {0, 0, 0}, n_leaf = 0, overflow = 0, depth = 0;
+    AlnLists first, L;
+    for (int c = 0; c < ALN_CLASSES; ++c) {
+        level[c].resize((size_t)cap_open);
+        next[c].resize((size_t)cap_open);
+    }
+    auto bind = [&](AlnLists& x, std::vector<AlnRect>* lists, int32_t* counts) {
+        for (int c = 0; c < ALN_CLASSES; ++c) x.open[c] = lists[c].data();
+        x.n_open = counts;
+        x.cap_open = cap_open;
+        x.leaves = leaves.data();
+        x.n_leaves = &n_leaf;
+        x.cap_leaves = cap_leaves;
+        x.overflow = &overflow;
+    };
+    bind(first, level, n_level);
     aln_push(first, AlnRect{0, 0, n, 0, m, 1});
-    while (n_level + n_tall > 0) {
-        n_next = n_next_tall = 0;
-        AlnLists L{next.data(), &n_next, next_tall.data(), &n_next_tall, cap_open, leaves.data(), &n_leaf, cap_leaves, &overflow};
-        for (int32_t k = 0; k < n_level + n_tall; ++k) { /* the emulation runs tall sub-problems on one warp as well */
-            const AlnRect r = k < n_level ? level[(size_t)k] : tall[(size_t)(k - n_level)];
-            AlnSplit sp;
-            aln_split(s, eq, q + r.r0, t + r.c0, r.n, r.m, &sp);
-            if (r.top) *score = sp.best;
-            AlnRect ul, lr;
-            if (!aln_children(r, sp.r, ul, lr)) return -1;
-            aln_push(L, ul);
-            aln_push(L, lr);
+    while (n_level[0] + n_level[1] + n_level[2] > 0) {
+        n_next[0] = n_next[1] = n_next[2] = 0;
+        bind(L, next, n_next);
+        for (int c = 0; c < ALN_CLASSES; ++c) { /* the emulation runs tall and huge sub-problems on one warp as well */
+            for (int32_t k = 0; k < n_level[c]; ++k) {
+                const AlnRect r = level[c][(size_t)k];
+                AlnSplit sp;
+                aln_split(s, eq, q + r.r0, t + r.c0, r.n, r.m, &sp);
+                if (r.top) *score = sp.best;
+                AlnRect ul, lr;
+                if (!aln_children(r, sp.r, ul, lr)) return -1;
+                aln_push(L, ul);
+                aln_push(L, lr);
+            }
         }
-        level.swap(next);
-        tall.swap(next_tall);
-        n_level = n_next;
-        n_tall = n_next_tall;
+        for (int c = 0; c < ALN_CLASSES; ++c) {
+            level[c].swap(next[c]);
+            n_level[c] = n_next[c];
+        }
         ++depth;
     }
     if (overflow) return -2;

@@ -23,7 +23,11 @@ def sass():
     api.load_library()  # builds if needed
     out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
     assert "poa_window_kernel" in out
-    return out
+    # the POA kernel's own code: the library also holds the overlap aligner's kernels (csrc/b200aln.cu, another module --
+    # its team kernel spins on progress words, which is lane-dependent control flow by construction)
+    start = out.index("poa_window_kernel")
+    nxt = out.find("Function :", start)
+    return out[start:nxt if nxt > 0 else len(out)]
 
 
 def test_no_divergence_slow_paths_anywhere_in_the_kernel(sass):

@@ -28,6 +28,7 @@ def _pairs():
     for n, m in [(100, 3000), (3000, 100), (1, 5000), (5000, 1), (2500, 2500), (300, 9000), (9000, 300), (4200, 130),
                  (7000, 7500)]:
         pairs.append((rng.choice(ACGT, size=n).tobytes(), rng.choice(ACGT, size=m).tobytes()))
+    pairs += random_pairs(31, [(9500, 0.15)])  # >= 8192 rows and 32 M cells: the "huge" shape (always a team of warps)
     q, t = random_pairs(29, [(1200, 0.1)])[0]  # bytes outside ACGT equal only themselves (edlib's alphabet)
     qa, ta = bytearray(q), bytearray(t)
     for k in range(0, len(qa), 37):
@@ -83,6 +84,28 @@ def test_real_lambda_overlaps_equal_unmodified_edlib(aligner):
         assert hashlib.sha256(cigar).hexdigest() == f["cigar_sha"], k
         assert aligner.ops(k).shape[0] == f["n_ops"]
     aligner.reset()
+
+
+def test_saturated_level_with_huge_overlaps_on_the_side_stream():
+    """Enough tall sub-problems to fill the device one warp each (so the level is not 'thin'), among them overlaps of
+    >= 8192 rows: those go to teams of warps on the side stream while the one-warp grid does the rest.  Every CIGAR is
+    still edlib's."""
+    from racon_gpu_b200.aligner import CUDABatchAligner, pack_pairs
+    fx = overlap_fixture()
+    rep = 16
+    assert sum(1 for f in fx if len(f["q"]) >= 8192) >= 2
+    q, qo, t, to = pack_pairs([(f["q"], f["t"]) for f in fx] * rep)
+    al = CUDABatchAligner(device_id=0, max_gpu_memory=24 << 30)
+    assert al.add_overlaps(q, qo, t, to) == len(fx) * rep
+    al.align_all()
+    text, off, ln, ed = al.cigars()
+    info = al.info()
+    al.close()
+    assert info["team_launches"] >= 1 and info["kernel_launches"] > info["team_launches"] + 2
+    for k in range(len(fx) * rep):
+        f = fx[k % len(fx)]
+        assert ed[k] == f["score"], k
+        assert hashlib.sha256(text[off[k]:off[k] + ln[k]]).hexdigest() == f["cigar_sha"], k
 
 
 def test_full_batch_is_back_pressure_not_an_error(oracle):
