@@ -69,6 +69,19 @@ struct AlnKernelArgs {
 };
 
 constexpr int WARPS_PER_BLOCK = 2;
+
+/* what one split launch works through: up to three lists of a level, one after the other (largest shapes first) */
+struct AlnWork {
+    const AlnRect* list[ALN_CLASSES];
+    int32_t n[ALN_CLASSES];
+    int32_t total;
+};
+__device__ __forceinline__ AlnRect work_item(const AlnWork& w, int32_t k) {
+    if (k < w.n[0]) return w.list[0][k];
+    k -= w.n[0];
+    if (k < w.n[1]) return w.list[1][k];
+    return w.list[2][k - w.n[1]];
+}
 #ifndef ALN_MIN_BLOCKS
 #define ALN_MIN_BLOCKS 16 /* 32 warps per SM => at most 64 registers per thread */
 #endif
@@ -87,9 +100,8 @@ __device__ __forceinline__ int32_t take_work(int32_t* cursor) {
 }
 
 /* one Hirschberg level: every open sub-problem is split, its children are filed for the next level or as leaves */
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, ALN_MIN_BLOCKS) aln_split_kernel(const AlnKernelArgs a, const AlnRect* level,
-                                                                         int32_t n_level, const AlnLists next,
-                                                                         int32_t* cursor) {
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, ALN_MIN_BLOCKS) aln_split_kernel(const AlnKernelArgs a, const AlnWork work,
+                                                                                        const AlnLists next, int32_t* cursor) {
     __shared__ uint64_t eq_tab[WARPS_PER_BLOCK * ALN_EQ_WORDS];
     AlnSlot s;
     bind_slot(a, s);
@@ -97,8 +109,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, ALN_MIN_BLOCKS) aln_spli
     bind_eq(eq, eq_tab);
     for (;;) {
         const int32_t k = take_work(cursor);
-        if (k >= n_level) break;
-        const AlnRect r = level[k];
+        if (k >= work.total) break;
+        const AlnRect r = work_item(work, k);
         const AlnJob job = a.jobs[r.aln];
         AlnSplit sp;
         aln_split(s, eq, a.seq + job.q_off + r.r0, a.seq + job.t_off + r.c0, r.n, r.m, &sp);
@@ -148,8 +160,8 @@ __host__ __device__ inline void team_slot_bind(TeamSlot& t, uint8_t* base, int32
     o = (o + 255) / 256 * 256;
     if (total_out) *total_out = o;
 }
-__global__ void __launch_bounds__(64 * ALN_TEAM, 1024 / (64 * ALN_TEAM)) aln_split_team_kernel(const AlnKernelArgs a, const AlnRect* level,
-                                                                      int32_t n_level, const AlnLists next, int32_t* cursor) {
+__global__ void __launch_bounds__(64 * ALN_TEAM, 1024 / (64 * ALN_TEAM)) aln_split_team_kernel(const AlnKernelArgs a, const AlnWork work,
+                                                                                                  const AlnLists next, int32_t* cursor) {
     __shared__ uint64_t eq_tab[2 * ALN_TEAM * ALN_EQ_WORDS];
     __shared__ unsigned long long prog[2 * ALN_TEAM];
     __shared__ int32_t s_k;
@@ -168,8 +180,8 @@ __global__ void __launch_bounds__(64 * ALN_TEAM, 1024 / (64 * ALN_TEAM)) aln_spl
         if (threadIdx.x == 0) s_k = atomicAdd(cursor, 1);
         __syncthreads();
         const int32_t k = s_k;
-        if (k >= n_level) break;
-        const AlnRect r = level[k];
+        if (k >= work.total) break;
+        const AlnRect r = work_item(work, k);
         const AlnJob job = a.jobs[r.aln];
         const uint8_t* q = a.seq + job.q_off + r.r0;
         const uint8_t* t = a.seq + job.t_off + r.c0;
@@ -665,45 +677,54 @@ int32_t b200aln_batch_align_all(b200aln_batch* b) {
         next.n_leaves = ct + CT_NLEAVES;
         next.cap_leaves = (int32_t)cap_leaves;
         next.overflow = ct + CT_OVERFLOW;
-        const auto list = [&](int c) { return static_cast<const AlnRect*>(b->d_list[c][level & 1].p); };
-        const auto team = [&](int c, cudaStream_t on) {
-            aln_split_team_kernel<<<(unsigned)std::min(n_open[c], b->n_team_blocks), 64 * ALN_TEAM, 0, on>>>(
-                a, list(c), n_open[c], next, ct + CT_CURSOR + launch);
+        /* Thin level (its longest sub-problem bounds its time): a team of warps per tall or huge sub-problem, the
+         * one-stripe ones one warp each.  Saturated level (enough sub-problems to fill the device one warp each): the huge
+         * ones -- any of which would outlast the rest of the level on one warp -- still go to teams, on a side stream
+         * beside the one-warp grid that does everything else. */
+        const auto work_of = [&](bool huge, bool tall, bool shrt) {
+            AlnWork w;
+            const bool take[ALN_CLASSES] = {shrt, tall, huge};
+            int slot = 0;
+            w.total = 0;
+            for (int c = ALN_CLASSES - 1; c >= 0; --c) { /* huge, tall, short */
+                w.list[slot] = static_cast<const AlnRect*>(b->d_list[c][level & 1].p);
+                w.n[slot] = take[c] ? n_open[c] : 0;
+                w.total += w.n[slot];
+                ++slot;
+            }
+            return w;
+        };
+        const auto team = [&](const AlnWork& w, cudaStream_t on) {
+            if (w.total == 0) return;
+            aln_split_team_kernel<<<(unsigned)std::min(w.total, b->n_team_blocks), 64 * ALN_TEAM, 0, on>>>(
+                a, w, next, ct + CT_CURSOR + launch);
             ++launch;
             ++b->info.team_launches;
         };
-        const auto solo = [&](int c) {
-            aln_split_kernel<<<grid_for(n_open[c]), 32 * WARPS_PER_BLOCK, 0, s>>>(a, list(c), n_open[c], next, ct + CT_CURSOR + launch);
+        const auto solo = [&](const AlnWork& w) {
+            if (w.total == 0) return;
+            aln_split_kernel<<<grid_for(w.total), 32 * WARPS_PER_BLOCK, 0, s>>>(a, w, next, ct + CT_CURSOR + launch);
             ++launch;
         };
-        /* Thin level (its longest sub-problem bounds its time): a team of warps per tall or huge sub-problem.  Saturated
-         * level (enough sub-problems to fill the device one warp each): the huge ones -- any of which would outlast the rest
-         * of the level on one warp -- still go to teams, on a side stream beside the one-warp grid. */
         const bool teams = b->n_team_blocks > 0;
         const bool thin = teams && (int64_t)n_open[ALN_TALL] + n_open[ALN_HUGE] <= (int64_t)ALN_TEAM_WAVES * b->n_team_blocks;
         bool forked = false;
-        if (n_open[ALN_HUGE] > 0) {
-            if (thin || !teams) {
-                if (teams) team(ALN_HUGE, s);
-                else solo(ALN_HUGE);
-            } else {
+        if (!teams) {
+            solo(work_of(true, true, true));
+        } else if (thin) {
+            team(work_of(true, true, false), s);
+            solo(work_of(false, false, true));
+        } else {
+            if (n_open[ALN_HUGE] > 0) {
                 ALN_CU(cudaEventRecord(b->ev_fork, s));
                 ALN_CU(cudaStreamWaitEvent(b->side, b->ev_fork, 0));
-                team(ALN_HUGE, b->side);
+                team(work_of(true, false, false), b->side);
                 ALN_CU(cudaEventRecord(b->ev_join, b->side));
                 forked = true;
             }
-            ALN_CU(cudaGetLastError());
+            solo(work_of(false, true, true));
         }
-        if (n_open[ALN_TALL] > 0) {
-            if (thin) team(ALN_TALL, s);
-            else solo(ALN_TALL);
-            ALN_CU(cudaGetLastError());
-        }
-        if (n_open[ALN_SHORT] > 0) {
-            solo(ALN_SHORT);
-            ALN_CU(cudaGetLastError());
-        }
+        ALN_CU(cudaGetLastError());
         if (forked) ALN_CU(cudaStreamWaitEvent(s, b->ev_join, 0));
         b->info.n_open += (int64_t)n_open[0] + n_open[1] + n_open[2];
         ALN_CU(cudaMemcpyAsync(b->h_counters + CT_NOPEN + 4 * (level + 1), ct_next, ALN_CLASSES * sizeof(int32_t),

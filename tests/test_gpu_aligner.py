@@ -56,7 +56,7 @@ def test_random_pairs_equal_the_oracle(oracle, aligner):
     got = aligner.generate_cigar_strings()
     info = aligner.info()
     assert info["levels"] >= 2 and info["n_leaves"] >= len(pairs)
-    # per level one launch for the one-stripe sub-problems and one for the tall ones; then the leaves, then the CIGARs
+    # per level at most one launch of warp teams and one of single warps; then the leaves, then the CIGARs
     assert info["levels"] + 2 <= info["kernel_launches"] <= 2 * info["levels"] + 2
     assert info["team_launches"] >= 1  # a thin level's tall sub-problems went to teams of warps
     for k, (q, t) in enumerate(pairs):
