@@ -131,6 +131,25 @@ int32_t b200aln_align_pairs(int32_t device_id, int64_t max_gpu_mem, int64_t n, c
                             const int64_t* q_off, const uint8_t* t_bases, const int64_t* t_off, int32_t* edit_distance,
                             char* cigars, int64_t cigar_cap, int64_t* cigar_off, b200aln_batch_info* info);
 
+/* ---- aligner pool: the GPU section of CUDAPolisher::find_overlap_breaking_points (src/cuda/cudapolisher.cpp:74-214:
+ * `cudaaligner_batches` batches per device, every device, one host thread per batch in a fill -> alignAll ->
+ * generate_cigar_strings -> reset loop, :139-174) over columnar segments.  max_gpu_mem_per_batch <= 0: 90 % of each
+ * device's free memory split between its batches (:118-123). */
+typedef struct b200aln_aligner b200aln_aligner;
+int32_t b200aln_aligner_create(int32_t n_devices, const int32_t* device_ids, int32_t batches_per_device,
+                               int64_t max_gpu_mem_per_batch, b200aln_aligner** out);
+int32_t b200aln_aligner_num_batches(const b200aln_aligner* h);
+/* Aligns n pairs (pair k = q_bases[q_off[k] .. q_off[k + 1]) against t_bases[t_off[k] .. t_off[k + 1])).  Pair k's CIGAR
+ * is the cigar_len[k] bytes at cigars + cigar_off[k], followed by a 0 (the strings of one batch lie together, batches in
+ * completion order); edit_distance[k] its distance (nullable).  *cigar_bytes = bytes of `cigars` used or needed;
+ * B200ALN_EXCEEDED_MAX_LENGTH when cigar_cap was too small (offsets of the strings that did not fit are -1).
+ * info (nullable): sums over the batches (kernel_ms adds device times of batches that overlap). */
+int32_t b200aln_aligner_align(b200aln_aligner* h, int64_t n, const uint8_t* q_bases, const int64_t* q_off,
+                              const uint8_t* t_bases, const int64_t* t_off, int32_t* edit_distance, char* cigars,
+                              int64_t cigar_cap, int64_t* cigar_off, int32_t* cigar_len, int64_t* cigar_bytes,
+                              b200aln_batch_info* info);
+void b200aln_aligner_destroy(b200aln_aligner* h);
+
 #ifdef __cplusplus
 }
 #endif

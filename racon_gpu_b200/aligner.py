@@ -18,6 +18,7 @@ ALN_ABI_SYMBOLS = (
     "b200aln_batch_sync", "b200aln_batch_num_alignments", "b200aln_batch_get_alignment", "b200aln_batch_get_cigar",
     "b200aln_batch_get_ops", "b200aln_batch_reset", "b200aln_batch_destroy", "b200aln_batch_get_info",
     "b200aln_status_string", "b200aln_align_pairs", "b200aln_batch_add_alignments", "b200aln_batch_get_cigars",
+    "b200aln_aligner_create", "b200aln_aligner_num_batches", "b200aln_aligner_align", "b200aln_aligner_destroy",
 )
 
 SUCCESS, UNINITIALIZED, EXCEEDED_MAX_ALIGNMENTS, EXCEEDED_MAX_LENGTH = 0, 1, 2, 3
@@ -39,6 +40,7 @@ def _lib():
     if not getattr(lib, "_aln_typed", False):
         lib.b200aln_status_string.restype = C.c_char_p
         lib.b200aln_batch_destroy.restype = None
+        lib.b200aln_aligner_destroy.restype = None
         lib.b200aln_batch_get_cigar.restype = C.c_int64
         lib.b200aln_batch_get_ops.restype = C.c_int64
         lib._aln_typed = True
@@ -184,3 +186,49 @@ def align_pairs(q, q_off, t, t_off, device_id: int = 0, max_gpu_memory: int = 0,
     if st != SUCCESS:
         raise RuntimeError(f"b200aln_align_pairs: {status_string(st)}")
     return ed[:n], cigars, coff, bi.as_dict()
+
+
+class AlignerPool:
+    """b200aln_aligner_*: batches_per_device batches on every listed device, one host thread per batch -- the GPU section
+    of CUDAPolisher::find_overlap_breaking_points (src/cuda/cudapolisher.cpp:74-214) over columnar segments."""
+
+    def __init__(self, devices=(0,), batches_per_device: int = 2, max_gpu_memory_per_batch: int = 0):
+        self.lib = _lib()
+        self.h = C.c_void_p()
+        dev = (C.c_int32 * len(devices))(*devices)
+        st = self.lib.b200aln_aligner_create(C.c_int32(len(devices)), dev, C.c_int32(batches_per_device),
+                                             C.c_int64(int(max_gpu_memory_per_batch)), C.byref(self.h))
+        if st != SUCCESS:
+            raise RuntimeError(f"b200aln_aligner_create: {status_string(st)}")
+        self._buf = np.zeros(0, dtype=np.uint8)
+
+    def close(self):
+        if self.h:
+            self.lib.b200aln_aligner_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def align(self, q, q_off, t, t_off):
+        """(edit distances, cigar buffer, cigar_off, cigar_len, info dict); pair k's CIGAR = buffer[off[k] : off[k] + len[k]]."""
+        n = len(q_off) - 1
+        need = 2 * int(q_off[-1] + t_off[-1]) + 2 * n + 64  # "1M1I1M...": two characters an operation at worst (+ 0 bytes)
+        if self._buf.shape[0] < need:
+            self._buf = np.zeros(need, dtype=np.uint8)
+        ed = np.zeros(max(n, 1), dtype=np.int32)
+        off = np.zeros(max(n, 1), dtype=np.int64)
+        ln = np.zeros(max(n, 1), dtype=np.int32)
+        used = C.c_int64(0)
+        bi = AlnBatchInfo()
+        p = lambda a, ty: a.ctypes.data_as(C.POINTER(ty))
+        st = self.lib.b200aln_aligner_align(self.h, C.c_int64(n), p(q, C.c_uint8), p(q_off, C.c_int64), p(t, C.c_uint8),
+                                            p(t_off, C.c_int64), p(ed, C.c_int32), p(self._buf, C.c_char),
+                                            C.c_int64(self._buf.shape[0]), p(off, C.c_int64), p(ln, C.c_int32),
+                                            C.byref(used), C.byref(bi))
+        if st != SUCCESS:
+            raise RuntimeError(f"b200aln_aligner_align: {status_string(st)}")
+        return ed[:n], self._buf, off[:n], ln[:n], bi.as_dict()

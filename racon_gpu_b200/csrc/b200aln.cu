@@ -15,11 +15,13 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/b200aln.h"
@@ -548,6 +550,7 @@ int32_t b200aln_batch_add_alignment(b200aln_batch* b, const char* query, int32_t
     if (vb + min_slots > b->budget) return B200ALN_EXCEEDED_MAX_LENGTH;
     if (b->var_bytes + vb + min_slots > b->budget) return B200ALN_EXCEEDED_MAX_ALIGNMENTS;
     if (b->jobs.size() >= (size_t)0x7FFFFF00) return B200ALN_EXCEEDED_MAX_ALIGNMENTS;
+    if (b->h_seq.used + (size_t)n + (size_t)m > b->h_seq.cap) cudaSetDevice(b->device); /* the staging buffer grows: page-lock it in this batch's context */
     if (!b->h_seq.reserve(b->h_seq.used + (size_t)n + (size_t)m)) return B200ALN_GENERIC_ERROR;
     AlnJob j;
     j.q_off = (int64_t)b->h_seq.used;
@@ -978,6 +981,159 @@ int32_t b200aln_align_pairs(int32_t device_id, int64_t max_gpu_mem, int64_t n, c
     if (info) *info = total;
     if (st == B200ALN_SUCCESS && too_small) return B200ALN_EXCEEDED_MAX_LENGTH;
     return st;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* aligner pool: the GPU section of CUDAPolisher::find_overlap_breaking_points (cudapolisher.cpp:74-214) -- several
+ * batches per device, several devices, one host thread per batch filling, aligning and emptying it -- over columnar
+ * segments.  While one batch's kernels run, the other batches' threads stage, upload and copy results out.         */
+/* ------------------------------------------------------------------------------------------ */
+struct b200aln_aligner {
+    std::vector<b200aln_batch*> batches;
+};
+
+void b200aln_aligner_destroy(b200aln_aligner* h) {
+    if (!h) return;
+    for (b200aln_batch* b : h->batches) b200aln_batch_destroy(b);
+    delete h;
+}
+
+int32_t b200aln_aligner_create(int32_t n_devices, const int32_t* device_ids, int32_t batches_per_device,
+                               int64_t max_gpu_mem_per_batch, b200aln_aligner** out) {
+    if (!out) return B200ALN_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (n_devices <= 0 || !device_ids || batches_per_device <= 0 || batches_per_device > 16) return B200ALN_INVALID_ARGUMENT;
+    b200aln_aligner* h = new (std::nothrow) b200aln_aligner();
+    if (!h) return B200ALN_GENERIC_ERROR;
+    for (int32_t d = 0; d < n_devices; ++d) {
+        int64_t per_batch = max_gpu_mem_per_batch;
+        if (per_batch <= 0) { /* like racon: 90 % of the device's free memory, split between its batches (cudapolisher.cpp:118-123) */
+            size_t free_b = 0, total_b = 0;
+            if (cudaSetDevice(device_ids[d]) != cudaSuccess || cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+                cudaGetLastError();
+                b200aln_aligner_destroy(h);
+                return B200ALN_CUDA_ERROR;
+            }
+            int32_t same = 0; /* the same device may be listed more than once */
+            for (int32_t e = 0; e < n_devices; ++e) same += device_ids[e] == device_ids[d];
+            per_batch = (int64_t)((double)free_b * 0.9) / ((int64_t)batches_per_device * same);
+        }
+        for (int32_t k = 0; k < batches_per_device; ++k) {
+            b200aln_batch* b = nullptr;
+            const int32_t st = b200aln_batch_create(device_ids[d], nullptr, per_batch, 0, &b);
+            if (st != B200ALN_SUCCESS) {
+                b200aln_aligner_destroy(h);
+                return st;
+            }
+            h->batches.push_back(b);
+        }
+    }
+    *out = h;
+    return B200ALN_SUCCESS;
+}
+
+int32_t b200aln_aligner_num_batches(const b200aln_aligner* h) { return h ? (int32_t)h->batches.size() : 0; }
+
+int32_t b200aln_aligner_align(b200aln_aligner* h, int64_t n, const uint8_t* q_bases, const int64_t* q_off,
+                              const uint8_t* t_bases, const int64_t* t_off, int32_t* edit_distance, char* cigars,
+                              int64_t cigar_cap, int64_t* cigar_off, int32_t* cigar_len, int64_t* cigar_bytes,
+                              b200aln_batch_info* info) {
+    if (cigar_bytes) *cigar_bytes = 0;
+    if (!h || h->batches.empty() || n < 0) return B200ALN_INVALID_ARGUMENT;
+    if (n > 0 && (!q_bases || !q_off || !t_bases || !t_off || !cigar_off || !cigar_len || (cigar_cap > 0 && !cigars)))
+        return B200ALN_INVALID_ARGUMENT;
+    const int32_t workers = (int32_t)h->batches.size();
+    /* chunks: large enough that a batch's levels fill the device (a thin level is bound by its longest sub-problem, not by
+     * throughput), small enough that the batches take turns: about 1.5e11 matrix cells (10 ms of kernels) or more each */
+    double cells = 0;
+    for (int64_t k = 0; k < n; ++k) cells += (double)(q_off[k + 1] - q_off[k]) * (double)(t_off[k + 1] - t_off[k]);
+    const int64_t n_chunks = std::max<int64_t>(1, std::min<int64_t>(4 * (int64_t)workers, (int64_t)(cells / 1.5e11)));
+    const int64_t chunk = std::max<int64_t>(1, (n + n_chunks - 1) / n_chunks);
+    std::atomic<int64_t> next{0}, used{0};
+    std::atomic<int32_t> first_error{B200ALN_SUCCESS};
+    std::vector<b200aln_batch_info> infos((size_t)workers);
+    auto work = [&](int32_t w) {
+        b200aln_batch* b = h->batches[(size_t)w];
+        b200aln_batch_info acc{};
+        b200aln_batch_get_info(b, &acc);
+        acc.levels = acc.kernel_launches = acc.team_launches = 0;
+        acc.n_open = acc.n_leaves = acc.cells = acc.h2d_bytes = acc.d2h_bytes = 0;
+        acc.kernel_ms = 0.f;
+        b200aln_batch_reset(b);
+        for (;;) {
+            if (first_error.load() != B200ALN_SUCCESS) break;
+            const int64_t start = next.fetch_add(chunk);
+            if (start >= n) break;
+            const int64_t end = std::min(n, start + chunk);
+            int64_t pos = start;
+            while (pos < end) {
+                int64_t added = 0;
+                int32_t st = b200aln_batch_add_alignments(b, end - pos, q_bases, q_off + pos, t_bases, t_off + pos, &added);
+                if (st == B200ALN_SUCCESS) st = b200aln_batch_align_all(b);
+                if (st == B200ALN_SUCCESS) st = b200aln_batch_sync(b);
+                const char* text = nullptr;
+                const int64_t* off = nullptr;
+                const int32_t *len = nullptr, *ed = nullptr, *ast = nullptr;
+                if (st == B200ALN_SUCCESS) st = b200aln_batch_get_cigars(b, &text, &off, &len, &ed, &ast);
+                if (st == B200ALN_SUCCESS) {
+                    /* one reservation and one copy per batch: the batch's text arena as it is; strings end with a 0 */
+                    const int64_t bytes = (int64_t)b->h_text.used;
+                    const int64_t base = used.fetch_add(bytes);
+                    const bool fits = base + bytes <= cigar_cap;
+                    if (fits && bytes) std::memcpy(cigars + base, text, (size_t)bytes);
+                    for (int64_t k = 0; k < added; ++k) {
+                        if (ast[k] != B200ALN_SUCCESS) st = ast[k];
+                        if (edit_distance) edit_distance[pos + k] = ed[k];
+                        cigar_off[pos + k] = fits ? base + off[k] : -1;
+                        cigar_len[pos + k] = len[k];
+                    }
+                }
+                b200aln_batch_info bi;
+                b200aln_batch_get_info(b, &bi);
+                acc.levels = std::max(acc.levels, bi.levels);
+                acc.kernel_launches += bi.kernel_launches;
+                acc.team_launches += bi.team_launches;
+                acc.n_open += bi.n_open;
+                acc.n_leaves += bi.n_leaves;
+                acc.cells += bi.cells;
+                acc.h2d_bytes += bi.h2d_bytes;
+                acc.d2h_bytes += bi.d2h_bytes;
+                acc.kernel_ms += bi.kernel_ms;
+                b200aln_batch_reset(b);
+                if (st != B200ALN_SUCCESS) {
+                    int32_t expect = B200ALN_SUCCESS;
+                    first_error.compare_exchange_strong(expect, st);
+                    break;
+                }
+                pos += added;
+            }
+        }
+        infos[(size_t)w] = acc;
+    };
+    std::vector<std::thread> threads;
+    for (int32_t w = 1; w < workers; ++w) threads.emplace_back(work, w);
+    work(0);
+    for (std::thread& t : threads) t.join();
+    if (info) {
+        b200aln_batch_info total = infos[0];
+        for (int32_t w = 1; w < workers; ++w) {
+            const b200aln_batch_info& x = infos[(size_t)w];
+            total.levels = std::max(total.levels, x.levels);
+            total.kernel_launches += x.kernel_launches;
+            total.team_launches += x.team_launches;
+            total.n_open += x.n_open;
+            total.n_leaves += x.n_leaves;
+            total.cells += x.cells;
+            total.h2d_bytes += x.h2d_bytes;
+            total.d2h_bytes += x.d2h_bytes;
+            total.kernel_ms += x.kernel_ms; /* launches of different batches overlap: a sum of device times, not a span */
+        }
+        *info = total;
+    }
+    if (cigar_bytes) *cigar_bytes = used.load();
+    const int32_t st = first_error.load();
+    if (st != B200ALN_SUCCESS) return st;
+    return used.load() > cigar_cap ? B200ALN_EXCEEDED_MAX_LENGTH : B200ALN_SUCCESS;
 }
 
 } // extern "C"

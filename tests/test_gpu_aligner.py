@@ -108,6 +108,26 @@ def test_saturated_level_with_huge_overlaps_on_the_side_stream():
         assert hashlib.sha256(text[off[k]:off[k] + ln[k]]).hexdigest() == f["cigar_sha"], k
 
 
+@pytest.mark.parametrize("devices,batches", [((0,), 2), ((0, 0), 1), ((0,), 3)])
+def test_aligner_pool_threads_and_devices(devices, batches):
+    """b200aln_aligner_*: several batches per device / several devices, one host thread per batch (the structure of
+    cudapolisher.cpp:74-214).  A small per-batch budget forces every thread through several fill/align/reset rounds."""
+    from racon_gpu_b200.aligner import AlignerPool, pack_pairs
+    fx = overlap_fixture()
+    rep = 3
+    q, qo, t, to = pack_pairs([(f["q"], f["t"]) for f in fx] * rep)
+    pool = AlignerPool(devices=devices, batches_per_device=batches, max_gpu_memory_per_batch=3 << 30)
+    for _ in range(2):  # a pool is reusable
+        ed, buf, off, ln, info = pool.align(q, qo, t, to)
+        for k in range(len(fx) * rep):
+            f = fx[k % len(fx)]
+            assert ed[k] == f["score"], k
+            assert hashlib.sha256(buf[off[k]:off[k] + ln[k]].tobytes()).hexdigest() == f["cigar_sha"], k
+            assert buf[off[k] + ln[k]] == 0
+    assert info["cells"] > 0 and info["kernel_launches"] >= 6
+    pool.close()
+
+
 def test_full_batch_is_back_pressure_not_an_error(oracle):
     """Aligner::add_alignment -> exceeded_max_alignments => addOverlap returns false (cudaaligner.cpp:64-67); the
     caller aligns, resets and goes on (cudapolisher.cpp:139-174).  Results do not depend on the batching."""
