@@ -86,3 +86,20 @@ def test_emulated_aligner_on_real_overlaps(oracle, emu):
         ops, score, depth, leaves = emu.align(f["q"], f["t"])
         assert score == f["score"] and ops.shape[0] == f["n_ops"]
         assert hashlib.sha256(ops_to_cigar(oracle, ops)).hexdigest() == f["cigar_sha"], i
+
+
+def test_emulated_aligner_on_long_reads_against_live_edlib(ref, emu):
+    """40 kb reads: five Hirschberg levels, all three shape classes (short / tall / huge), leaves of many stripes; only
+    the real edlib is fast enough to be the checker here."""
+    if not ref.available:
+        pytest.skip("oracle/_ref not built (no /root/reference on this box)")
+    pairs = random_pairs(902, [(42000, 0.12)])
+    rng = np.random.default_rng(5)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    pairs.append((rng.choice(acgt, size=30000).tobytes(), rng.choice(acgt, size=12000).tobytes()))
+    pairs.append((rng.choice(acgt, size=900).tobytes(), rng.choice(acgt, size=50000).tobytes()))
+    for q, t in pairs:
+        ops, score, cigar = ref_align(ref, q, t)
+        a, sa, depth, leaves = emu.align(q, t)
+        assert sa == score and a.shape == ops.shape and (a == ops).all() and emu.cigar == cigar
+    assert depth >= 3

@@ -166,6 +166,12 @@ def test_live_against_the_unmodified_edlib(ref, aligner):
     if not ref.available:
         pytest.skip("oracle/_ref not built (no /root/reference where it was built)")
     pairs = random_pairs(901, [(6000, 0.14), (2500, 0.3), (1900, 0.05), (64, 0.3)])
+    # long reads: slots re-made for the longer sequences, five and more Hirschberg levels, huge sub-problems on teams at
+    # several levels, leaves of many stripes (tall, narrow) -- only the real edlib is fast enough to check these
+    pairs += random_pairs(902, [(42000, 0.12), (70000, 0.08)])
+    rng = np.random.default_rng(5)
+    pairs.append((rng.choice(ACGT, size=30000).tobytes(), rng.choice(ACGT, size=12000).tobytes()))  # unrelated, tall
+    pairs.append((rng.choice(ACGT, size=900).tobytes(), rng.choice(ACGT, size=50000).tobytes()))    # unrelated, wide
     aligner.reset()
     for q, t in pairs:
         assert aligner.add_overlap(q, t)
