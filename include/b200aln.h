@@ -64,6 +64,28 @@ int32_t b200aln_batch_create(int32_t device_id, void* stream, int64_t max_gpu_me
 int32_t b200aln_batch_add_alignment(b200aln_batch* b, const char* query, int32_t query_length, const char* target,
                                     int32_t target_length);
 
+/* ---- breaking points (extension; what racon does with the CIGAR next: Overlap::find_breaking_points_from_cigar,
+ * src/overlap.cpp:226-290, called per overlap on CPU threads after generate_cigar_strings, cudapolisher.cpp:190-214).
+ * window_length > 0 (racon -w, default 500) makes align_all also form every overlap's breaking points on the device --
+ * per window of the contig that the overlap touches and that holds an aligned column: its first one as (t, q), its last
+ * one as (t + 1, q + 1), contig / read coordinates -- and download them (16 bytes a window).  skip_cigars != 0: the CIGAR
+ * text is then neither formed nor downloaded.  Call on an empty batch (after create or reset). */
+int32_t b200aln_batch_set_window_length(b200aln_batch* b, int32_t window_length, int32_t skip_cigars);
+
+/* add_alignment with the segments' coordinates: q_first = where the read segment starts in the (strand-adjusted) read,
+ * i.e. strand ? q_length - q_end : q_begin (overlap.cpp:241); t_begin = where the contig segment starts (:242). */
+int32_t b200aln_batch_add_overlap(b200aln_batch* b, const char* query, int32_t query_length, const char* target,
+                                  int32_t target_length, int32_t q_first, int32_t t_begin);
+/* columnar (q_first / t_begin nullable = 0) */
+int32_t b200aln_batch_add_overlaps(b200aln_batch* b, int64_t n, const uint8_t* q_bases, const int64_t* q_off,
+                                   const uint8_t* t_bases, const int64_t* t_off, const int32_t* q_first,
+                                   const int32_t* t_begin, int64_t* n_added);
+
+/* After sync: overlap k's breaking points are count[k] pairs (t, q) of uint32 at points + 2 * off[k] (always an even
+ * number: first / last per window, in window order = Overlap::breaking_points(), overlap.hpp:68-70). */
+int32_t b200aln_batch_get_breaking_points(const b200aln_batch* b, const uint32_t** points, const int64_t** off,
+                                          const int32_t** count);
+
 /* Columnar form of add_alignment for callers that hold their segments back to back (pair k = q_bases[q_off[k] ..
  * q_off[k + 1]) against t_bases[t_off[k] .. t_off[k + 1])): adds pairs 0, 1, .. until the batch is full; *n_added says
  * how many went in (B200ALN_SUCCESS if at least one did, or n == 0). */

@@ -187,3 +187,60 @@ int64_t aln_oracle_cigar(const uint8_t* ops, int64_t n_ops, char* out, int64_t c
     out[w] = 0;
     return w;
 }
+
+/*
+ * Breaking points of an overlap from its alignment (racon::Overlap::find_breaking_points_from_cigar,
+ * src/overlap.cpp:226-290), restated on edit operations instead of CIGAR text (M and X both advance query and target and
+ * count as "match" there, :245; I advances the query, :268; D the target, :271).
+ *   window ends (:229-235): every multiple i of window_length with t_begin < i < t_end gives i - 1, then t_end - 1;
+ *   q_ptr starts at q_first - 1 with q_first = strand ? q_length - q_end : q_begin (:241), t_ptr at t_begin - 1 (:242);
+ *   a window that saw at least one M/X emits its first one as (t, q) and its last one as (t + 1, q + 1) when the target
+ *   position reaches the window's end, on an M/X or a D (:252-263, :274-283).
+ * out receives (t, q) pairs, 2 per emitted window; returns the number of pairs, -1 if cap is too small.
+ */
+int64_t aln_oracle_breaking_points(const uint8_t* ops, int64_t n_ops, int32_t q_first, int32_t t_begin, int32_t t_end,
+                                   int32_t window_length, uint32_t* out, int64_t cap) {
+    int64_t n_out = 0;
+    int64_t next_end = -1; /* the current window's end */
+    int64_t i_mult = ((int64_t)t_begin / window_length + 1) * (int64_t)window_length; /* smallest multiple > t_begin */
+    next_end = i_mult < t_end ? i_mult - 1 : (int64_t)t_end - 1;
+    int found = 0;
+    int64_t q_ptr = (int64_t)q_first - 1, t_ptr = (int64_t)t_begin - 1;
+    uint32_t first_t = 0, first_q = 0, last_t = 0, last_q = 0;
+    for (int64_t k = 0; k < n_ops; ++k) {
+        const uint8_t op = ops[k];
+        int target_moved = 0;
+        if (op == OP_MATCH || op == OP_MISMATCH) {
+            ++q_ptr;
+            ++t_ptr;
+            if (!found) {
+                found = 1;
+                first_t = (uint32_t)t_ptr;
+                first_q = (uint32_t)q_ptr;
+            }
+            last_t = (uint32_t)(t_ptr + 1);
+            last_q = (uint32_t)(q_ptr + 1);
+            target_moved = 1;
+        } else if (op == OP_INSERT) {
+            ++q_ptr;
+        } else {
+            ++t_ptr;
+            target_moved = 1;
+        }
+        if (target_moved && t_ptr == next_end) {
+            if (found) {
+                if (n_out + 2 > cap) return -1;
+                out[2 * n_out] = first_t;
+                out[2 * n_out + 1] = first_q;
+                out[2 * n_out + 2] = last_t;
+                out[2 * n_out + 3] = last_q;
+                n_out += 2;
+            }
+            found = 0;
+            if (next_end == (int64_t)t_end - 1) break;
+            i_mult += window_length;
+            next_end = i_mult < t_end ? i_mult - 1 : (int64_t)t_end - 1;
+        }
+    }
+    return n_out;
+}

@@ -25,6 +25,8 @@
 #include "edlib.h"
 #include "spoa/spoa.hpp"
 #include "window.hpp"
+#include "sequence.hpp"
+#include "overlap.hpp"
 
 namespace {
 
@@ -227,3 +229,42 @@ int64_t ref_edlib_nw(const char* q, int32_t q_len, const char* t, int32_t t_len,
 }
 
 } // extern "C"
+
+
+/*
+ * Breaking points of one overlap exactly as racon derives them from a CIGAR: the UNMODIFIED
+ * racon::Overlap::find_breaking_points -> find_breaking_points_from_cigar (src/overlap.cpp:179-203, 226-290).
+ * Overlap's constructors and fields are private; its header befriends bioparser::PafParser<Overlap> (overlap.hpp:76), so
+ * this driver supplies that (otherwise unused here) specialisation to build one PAF overlap, hand it the CIGAR and mark it
+ * transmuted -- no reference source is touched.  out receives (t, q) pairs, two per window; returns their number or -1.
+ */
+namespace bioparser {
+template <>
+class PafParser<racon::Overlap> {
+public:
+    static int64_t breaking_points(const char* cigar, uint32_t q_length, uint32_t q_begin, uint32_t q_end, int strand,
+                                   uint32_t t_length, uint32_t t_begin, uint32_t t_end, uint32_t window_length,
+                                   uint32_t* out, int64_t cap) {
+        std::unique_ptr<racon::Overlap> o(new racon::Overlap("q", 1, q_length, q_begin, q_end, strand ? '-' : '+', "t", 1,
+                                                             t_length, t_begin, t_end, 0, 0, 255));
+        o->cigar_ = cigar;
+        o->is_transmuted_ = true;
+        std::vector<std::unique_ptr<racon::Sequence>> none;
+        o->find_breaking_points(none, window_length);
+        const auto& bp = o->breaking_points();
+        if ((int64_t)bp.size() > cap) return -1;
+        for (size_t k = 0; k < bp.size(); ++k) {
+            out[2 * k] = bp[k].first;
+            out[2 * k + 1] = bp[k].second;
+        }
+        return (int64_t)bp.size();
+    }
+};
+} // namespace bioparser
+
+extern "C" int64_t ref_racon_breaking_points(const char* cigar, uint32_t q_length, uint32_t q_begin, uint32_t q_end, int strand,
+                                             uint32_t t_length, uint32_t t_begin, uint32_t t_end, uint32_t window_length,
+                                             uint32_t* out, int64_t cap) {
+    return bioparser::PafParser<racon::Overlap>::breaking_points(cigar, q_length, q_begin, q_end, strand, t_length, t_begin,
+                                                                 t_end, window_length, out, cap);
+}

@@ -19,6 +19,8 @@ ALN_ABI_SYMBOLS = (
     "b200aln_batch_get_ops", "b200aln_batch_reset", "b200aln_batch_destroy", "b200aln_batch_get_info",
     "b200aln_status_string", "b200aln_align_pairs", "b200aln_batch_add_alignments", "b200aln_batch_get_cigars",
     "b200aln_aligner_create", "b200aln_aligner_num_batches", "b200aln_aligner_align", "b200aln_aligner_destroy",
+    "b200aln_batch_set_window_length", "b200aln_batch_add_overlap", "b200aln_batch_add_overlaps",
+    "b200aln_batch_get_breaking_points",
 )
 
 SUCCESS, UNINITIALIZED, EXCEEDED_MAX_ALIGNMENTS, EXCEEDED_MAX_LENGTH = 0, 1, 2, 3
@@ -84,16 +86,43 @@ class CUDABatchAligner:
             raise RuntimeError(f"b200aln_batch_add_alignment: {status_string(st)}")
         return True
 
-    def add_overlaps(self, q: np.ndarray, q_off: np.ndarray, t: np.ndarray, t_off: np.ndarray, first: int = 0) -> int:
-        """b200aln_batch_add_alignments from pair `first` on: how many went in before the batch was full."""
+    def add_overlaps(self, q: np.ndarray, q_off: np.ndarray, t: np.ndarray, t_off: np.ndarray, first: int = 0,
+                     q_first: np.ndarray | None = None, t_begin: np.ndarray | None = None) -> int:
+        """b200aln_batch_add_overlaps from pair `first` on: how many went in before the batch was full."""
         n = len(q_off) - 1 - first
         added = C.c_int64(0)
         p = lambda a, ty: a.ctypes.data_as(C.POINTER(ty))
-        st = self.lib.b200aln_batch_add_alignments(self.h, C.c_int64(n), p(q, C.c_uint8), p(q_off[first:], C.c_int64),
-                                                   p(t, C.c_uint8), p(t_off[first:], C.c_int64), C.byref(added))
+        qf = p(np.ascontiguousarray(q_first[first:], dtype=np.int32), C.c_int32) if q_first is not None else None
+        tb = p(np.ascontiguousarray(t_begin[first:], dtype=np.int32), C.c_int32) if t_begin is not None else None
+        st = self.lib.b200aln_batch_add_overlaps(self.h, C.c_int64(n), p(q, C.c_uint8), p(q_off[first:], C.c_int64),
+                                                 p(t, C.c_uint8), p(t_off[first:], C.c_int64), qf, tb, C.byref(added))
         if st != SUCCESS:
-            raise RuntimeError(f"b200aln_batch_add_alignments: {status_string(st)}")
+            raise RuntimeError(f"b200aln_batch_add_overlaps: {status_string(st)}")
         return int(added.value)
+
+    def set_window_length(self, window_length: int, skip_cigars: bool = False):
+        """Form breaking points on the device (Overlap::find_breaking_points_from_cigar, src/overlap.cpp:226-290)."""
+        st = self.lib.b200aln_batch_set_window_length(self.h, C.c_int32(window_length), C.c_int32(1 if skip_cigars else 0))
+        if st != SUCCESS:
+            raise RuntimeError(f"b200aln_batch_set_window_length: {status_string(st)}")
+
+    def breaking_points(self):
+        """After align_all: list of (k, 2) uint32 arrays of (t, q), one per overlap (Overlap::breaking_points())."""
+        st = self.lib.b200aln_batch_sync(self.h)
+        if st != SUCCESS:
+            raise RuntimeError(f"b200aln_batch_sync: {status_string(st)}")
+        n = self.lib.b200aln_batch_num_alignments(self.h)
+        pts, off, cnt = C.POINTER(C.c_uint32)(), C.POINTER(C.c_int64)(), C.POINTER(C.c_int32)()
+        st = self.lib.b200aln_batch_get_breaking_points(self.h, C.byref(pts), C.byref(off), C.byref(cnt))
+        if st != SUCCESS:
+            raise RuntimeError(f"b200aln_batch_get_breaking_points: {status_string(st)}")
+        if n == 0:
+            return []
+        off_a = np.ctypeslib.as_array(off, shape=(n,))
+        cnt_a = np.ctypeslib.as_array(cnt, shape=(n,))
+        total = int((off_a + cnt_a).max())
+        flat = np.ctypeslib.as_array(pts, shape=(max(2 * total, 1),))
+        return [flat[2 * off_a[k]:2 * (off_a[k] + cnt_a[k])].reshape(-1, 2).copy() for k in range(n)]
 
     def cigars(self):
         """b200aln_batch_get_cigars after sync: (text bytes view, off int64[n], len int32[n], edit distance int32[n])."""
@@ -102,7 +131,9 @@ class CUDABatchAligner:
             raise RuntimeError(f"b200aln_batch_sync: {status_string(st)}")
         n = self.lib.b200aln_batch_num_alignments(self.h)
         text, off, ln, ed, ast = C.c_void_p(), C.POINTER(C.c_int64)(), C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)()
-        self.lib.b200aln_batch_get_cigars(self.h, C.byref(text), C.byref(off), C.byref(ln), C.byref(ed), C.byref(ast))
+        st = self.lib.b200aln_batch_get_cigars(self.h, C.byref(text), C.byref(off), C.byref(ln), C.byref(ed), C.byref(ast))
+        if st != SUCCESS:
+            raise RuntimeError(f"b200aln_batch_get_cigars: {status_string(st)}")
         if n == 0:
             return b"", np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros(0, np.int32)
         off_a = np.ctypeslib.as_array(off, shape=(n,)).copy()

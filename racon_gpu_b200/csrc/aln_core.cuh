@@ -107,6 +107,7 @@ struct AlnSlot {
     int32_t* Rr;    /* [max_len + 2]    last column of the backward pass: Rr[i] = D(q[n-i..n), right half)          */
     RecPM* PM;      /* [leaf entries]   leaf records in wavefront order, see leaf_entry()                            */
     int32_t* S;     /* [leaf entries]   score under the block's last row                                             */
+    int32_t* pre;   /* [4 max_len + 8]  target / query characters before every run (aln_breaking_points)            */
 };
 ALN_HD int64_t aln_hrow_words(int32_t max_len) { return (int64_t)max_len / 16 + 8; } /* one hand-over row */
 ALN_HD int64_t aln_leaf_entries(int32_t max_len) { return ALN_LEAF_DATA_LIMIT / 20 + 31 * (int64_t)((max_len + 63) / 64) + 64; }
@@ -125,6 +126,7 @@ ALN_HD void aln_slot_bind(AlnSlot& s, uint8_t* base, int32_t max_len, size_t* to
     ALN_CARVE(Rr, int32_t, (size_t)max_len + 2);
     ALN_CARVE(PM, RecPM, E);
     ALN_CARVE(S, int32_t, E);
+    ALN_CARVE(pre, int32_t, 4 * (size_t)max_len + 8);
 #undef ALN_CARVE
     o = (o + 255) / 256 * 256;
     if (total_out) *total_out = o;
@@ -791,6 +793,131 @@ POA_FN_NOINLINE int32_t aln_cigar_text(const uint32_t* runs, int32_t n_runs, int
     }
     POA_SYNC();
     return bytes;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Run starts -> breaking points (racon::Overlap::find_breaking_points_from_cigar, src/overlap.cpp:226-290): the
+ * consumer of the CIGAR, evaluated where the alignment already is.  Windows are the stretches of target coordinates
+ * between consecutive multiples of window_length (:229-235); a window that contains at least one match / mismatch
+ * column emits its first one as (t, q) and its last one as (t + 1, q + 1) (:248-263).
+ * Pass 1 (32 runs a round): target and query characters consumed before every run -> pre[] (two words a run, plus the
+ * totals).  Pass 2 (32 windows a round, a lane each): binary search for the runs around the window's two ends, a short
+ * walk over the runs that consume no target or are deletions; kept windows are written in order (ballot + prefix).
+ * out: (t, q) pairs, capacity 4 words per window; returns the number of pairs.
+ * ---------------------------------------------------------------------------------------- */
+ALN_HD int32_t aln_window_count(int32_t t_begin, int32_t m, int32_t window_length) { /* :229-235 */
+    if (m <= 0 || window_length <= 0) return 0;
+    return (t_begin + m - 1) / window_length - t_begin / window_length + 1;
+}
+POA_FN_NOINLINE int32_t aln_breaking_points(const uint32_t* runs, int32_t n_runs, int32_t n_ops, int32_t q_first, int32_t t_begin,
+                                            int32_t m, int32_t window_length, int32_t* pre, uint32_t* out) {
+    n_runs = poa_uniform(n_runs);
+    n_ops = poa_uniform(n_ops);
+    /* pass 1: pre[2k] = target characters before run k, pre[2k + 1] = query characters before run k; k = n_runs: totals */
+    int32_t t_run = 0, q_run = 0;
+    for (int32_t base = 0; base < n_runs; base += 32) {
+        PerLane<int> tl, ql;
+        POA_LANES(l) {
+            const int32_t k = base + l;
+            int tlen = 0, qlen = 0;
+            if (k < n_runs) {
+                const uint32_t r = runs[k];
+                const int32_t len = (k + 1 < n_runs ? (int32_t)(runs[k + 1] >> 2) : n_ops) - (int32_t)(r >> 2);
+                const int op = (int)(r & 3u);
+                tlen = op == OP_INSERT ? 0 : len;
+                qlen = op == OP_DELETE ? 0 : len;
+            }
+            tl[l] = tlen;
+            ql[l] = qlen;
+        }
+        PerLane<int> to = tl, qo = ql;
+        const int32_t tsum = warp_exscan(to), qsum = warp_exscan(qo);
+        POA_LANES(l) {
+            const int32_t k = base + l;
+            if (k < n_runs) {
+                pre[2 * k] = t_run + to[l];
+                pre[2 * k + 1] = q_run + qo[l];
+            }
+        }
+        t_run += tsum;
+        q_run += qsum;
+    }
+    POA_LANE0 {
+        pre[2 * n_runs] = t_run;
+        pre[2 * n_runs + 1] = q_run;
+    }
+    POA_SYNC();
+    POA_FENCE();
+    /* pass 2 */
+    const int32_t n_win = aln_window_count(t_begin, m, window_length);
+    const int32_t first_mult = (t_begin / window_length + 1) * window_length; /* smallest multiple > t_begin */
+    int32_t n_out = 0;
+    for (int32_t base = 0; base < n_win; base += 32) {
+        PerLane<int> keep, ft, fq, lt, lq;
+        POA_LANES(l) {
+            const int32_t j = base + l;
+            keep[l] = 0;
+            ft[l] = fq[l] = lt[l] = lq[l] = 0;
+            if (j < n_win) {
+                /* the window's target range, relative to the segment: [lo, hi] */
+                const int32_t lo = j == 0 ? 0 : first_mult + (j - 1) * window_length - t_begin;
+                const int32_t hi = (j == n_win - 1 ? t_begin + m : first_mult + j * window_length) - 1 - t_begin;
+                /* first run whose target span ends beyond lo: smallest k with pre[2(k + 1)] > lo */
+                int32_t a = 0, b = n_runs;
+                while (a < b) {
+                    const int32_t mid = (a + b) >> 1;
+                    if (pre[2 * (mid + 1)] > lo) b = mid;
+                    else a = mid + 1;
+                }
+                int32_t k = a;
+                while (k < n_runs && pre[2 * k] <= hi) { /* forward to the first match / mismatch run inside the window */
+                    const int op = (int)(runs[k] & 3u);
+                    if (op == OP_MATCH || op == OP_MISMATCH) {
+                        const int32_t t = pre[2 * k] > lo ? pre[2 * k] : lo;
+                        ft[l] = t_begin + t;
+                        fq[l] = q_first + pre[2 * k + 1] + (t - pre[2 * k]);
+                        keep[l] = 1;
+                        break;
+                    }
+                    ++k;
+                }
+                if (keep[l]) {
+                    /* last run that starts at or before hi: largest k with pre[2k] <= hi */
+                    a = 0;
+                    b = n_runs - 1;
+                    while (a < b) {
+                        const int32_t mid = (a + b + 1) >> 1;
+                        if (pre[2 * mid] <= hi) a = mid;
+                        else b = mid - 1;
+                    }
+                    k = a;
+                    for (;;) { /* backward to the last match / mismatch run (one exists: the first one at the latest) */
+                        const int op = (int)(runs[k] & 3u);
+                        if (op == OP_MATCH || op == OP_MISMATCH) {
+                            const int32_t last = pre[2 * (k + 1)] - 1 < hi ? pre[2 * (k + 1)] - 1 : hi;
+                            lt[l] = t_begin + last + 1;
+                            lq[l] = q_first + pre[2 * k + 1] + (last - pre[2 * k]) + 1;
+                            break;
+                        }
+                        --k;
+                    }
+                }
+            }
+        }
+        const unsigned mask = warp_ballot(keep);
+        POA_LANES(l) {
+            if (keep[l]) {
+                uint32_t* o = out + 4 * (n_out + b200poa::poa_popc(mask & ((1u << l) - 1u)));
+                o[0] = (uint32_t)ft[l];
+                o[1] = (uint32_t)fq[l];
+                o[2] = (uint32_t)lt[l];
+                o[3] = (uint32_t)lq[l];
+            }
+        }
+        n_out += b200poa::poa_popc(mask);
+    }
+    POA_SYNC();
+    return 2 * n_out;
 }
 
 } // namespace b200aln

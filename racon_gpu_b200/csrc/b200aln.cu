@@ -36,13 +36,15 @@ struct AlnJob { /* one alignment of the batch */
     int64_t q_off, t_off; /* into the sequence arena */
     int64_t ops_off;      /* into the operations arena (n + m bytes) */
     int32_t n, m;
+    int32_t q_first, t_begin; /* where the segments start in read / contig coordinates (breaking points only) */
 };
 struct AlnResult {
     int32_t score, status, n_runs, n_ops;
     int64_t runs_off;  /* into the runs arena (words)  */
     int64_t cigar_off; /* into the text arena (bytes)  */
     int32_t cigar_len; /* without the terminating 0    */
-    int32_t pad;
+    int32_t bp_count;  /* breaking points ((t, q) pairs) */
+    int64_t bp_off;    /* into the breaking-point arena (pairs) */
 };
 
 enum { /* int32 words of the device counter block */
@@ -53,7 +55,8 @@ enum { /* int32 words of the device counter block */
     CT_RUNS = 258,      /* u64: entries used in the runs arena                               */
     CT_CELLS = 260,     /* u64: distance-matrix cells computed                               */
     CT_TEXT = 262,      /* u64: bytes used in the CIGAR text arena                           */
-    CT_WORDS = 264,
+    CT_BP = 264,        /* u64: (t, q) pairs reserved in the breaking-point arena            */
+    CT_WORDS = 268,
     MAX_LEVELS = 31
 };
 
@@ -235,12 +238,21 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, ALN_MIN_BLOCKS) aln_leaf
     }
 }
 
-/* operations -> run starts -> CIGAR text, both bump-allocated into compact arenas */
+/* operations -> run starts -> CIGAR text and / or breaking points, all bump-allocated into compact arenas */
+struct AlnOutArgs {
+    uint32_t* runs;
+    unsigned long long runs_cap;
+    uint8_t* text; /* null: no CIGAR text wanted */
+    unsigned long long text_cap;
+    uint32_t* bp;  /* null / window_length 0: no breaking points wanted */
+    unsigned long long bp_cap; /* pairs */
+    int32_t window_length;
+};
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) aln_cigar_kernel(const AlnKernelArgs a, int32_t n_alignments,
-                                                                         uint32_t* runs, unsigned long long runs_cap,
-                                                                         uint8_t* text, unsigned long long text_cap,
-                                                                         int32_t* cursor) {
+                                                                         const AlnOutArgs o, int32_t* cursor) {
     const bool lane0 = (threadIdx.x & 31u) == 0u;
+    AlnSlot s;
+    bind_slot(a, s);
     for (;;) {
         const int32_t k = take_work(cursor);
         if (k >= n_alignments) break;
@@ -251,29 +263,43 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) aln_cigar_kernel(const A
         unsigned long long off = 0;
         if (lane0) off = atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + CT_RUNS), (unsigned long long)n_runs);
         off = __shfl_sync(0xffffffffu, off, 0);
-        bool ok = off + (unsigned long long)n_runs <= runs_cap;
+        bool ok = off + (unsigned long long)n_runs <= o.runs_cap;
+        AlnResult r = a.res[k]; /* score and status were written by the split / leaf kernels */
         if (ok) {
-            aln_runs(ops, job.n + job.m, runs + off, n_ops);
-            const int32_t bytes = aln_cigar_text(runs + off, n_runs, n_ops, nullptr);
+            aln_runs(ops, job.n + job.m, o.runs + off, n_ops);
+            r.n_runs = n_runs;
+            r.n_ops = n_ops;
+            r.runs_off = (int64_t)off;
+        }
+        if (ok && o.text) {
+            const int32_t bytes = aln_cigar_text(o.runs + off, n_runs, n_ops, nullptr);
             unsigned long long toff = 0;
             if (lane0) toff = atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + CT_TEXT), (unsigned long long)bytes + 1ull);
             toff = __shfl_sync(0xffffffffu, toff, 0);
-            ok = toff + (unsigned long long)bytes + 1ull <= text_cap;
+            ok = toff + (unsigned long long)bytes + 1ull <= o.text_cap;
             if (ok) {
-                aln_cigar_text(runs + off, n_runs, n_ops, text + toff);
-                if (lane0) {
-                    text[toff + (unsigned long long)bytes] = 0;
-                    AlnResult r = a.res[k];
-                    r.n_runs = n_runs;
-                    r.n_ops = n_ops;
-                    r.runs_off = (int64_t)off;
-                    r.cigar_off = (int64_t)toff;
-                    r.cigar_len = bytes;
-                    a.res[k] = r;
-                }
+                aln_cigar_text(o.runs + off, n_runs, n_ops, o.text + toff);
+                if (lane0) o.text[toff + (unsigned long long)bytes] = 0;
+                r.cigar_off = (int64_t)toff;
+                r.cigar_len = bytes;
             }
         }
-        if (!ok && lane0) a.res[k].status = B200ALN_GENERIC_ERROR;
+        if (ok && o.bp && o.window_length > 0) {
+            const int32_t n_win = aln_window_count(job.t_begin, job.m, o.window_length);
+            unsigned long long boff = 0;
+            if (lane0) boff = atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + CT_BP), 2ull * (unsigned long long)n_win);
+            boff = __shfl_sync(0xffffffffu, boff, 0);
+            ok = boff + 2ull * (unsigned long long)n_win <= o.bp_cap;
+            if (ok) {
+                r.bp_count = aln_breaking_points(o.runs + off, n_runs, n_ops, job.q_first, job.t_begin, job.m, o.window_length,
+                                                 s.pre, o.bp + 2ull * boff);
+                r.bp_off = (int64_t)boff;
+            }
+        }
+        if (lane0) {
+            if (!ok) r.status = B200ALN_GENERIC_ERROR;
+            a.res[k] = r;
+        }
         __syncwarp();
     }
 }
@@ -342,13 +368,18 @@ struct b200aln_batch {
     int64_t var_bytes = 0; /* device bytes the staged alignments need besides the slots */
 
     /* device */
-    DevBuf d_slab, d_team_slab, d_seq, d_jobs, d_ops, d_res, d_runs, d_text, d_list[ALN_CLASSES][2], d_leaves, d_counters;
+    DevBuf d_slab, d_team_slab, d_seq, d_jobs, d_ops, d_res, d_runs, d_text, d_bp, d_list[ALN_CLASSES][2], d_leaves, d_counters;
     int32_t n_slots = 0, slot_max_len = 0, n_team_blocks = 0, team_blocks_per_sm = 0;
     size_t slot_bytes = 0, team_slot_bytes = 0;
 
     /* results */
     std::vector<AlnResult> res;
-    PinnedBuf h_runs, h_text;
+    PinnedBuf h_runs, h_text, h_bp;
+    int32_t window_length = 0; /* > 0: breaking points are formed on the device */
+    bool skip_cigars = false;  /* the CIGAR text is neither formed nor downloaded */
+    int64_t n_windows = 0;     /* windows the staged overlaps touch */
+    std::vector<int64_t> bp_off_tab;
+    std::vector<int32_t> bp_cnt_tab;
     unsigned long long n_runs_total = 0;
     bool runs_on_host = false; /* the run starts are fetched only when a caller asks for operations */
     std::vector<int64_t> t_off; /* per alignment, for b200aln_batch_get_cigars */
@@ -453,6 +484,7 @@ void b200aln_batch_destroy(b200aln_batch* b) {
     b->d_res.release();
     b->d_runs.release();
     b->d_text.release();
+    b->d_bp.release();
     for (int c = 0; c < ALN_CLASSES; ++c) {
         b->d_list[c][0].release();
         b->d_list[c][1].release();
@@ -469,6 +501,7 @@ void b200aln_batch_destroy(b200aln_batch* b) {
     b->h_seq.release();
     b->h_runs.release();
     b->h_text.release();
+    b->h_bp.release();
     if (b->h_counters) cudaFreeHost(b->h_counters);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
@@ -539,11 +572,28 @@ int32_t b200aln_batch_create(int32_t device_id, void* stream, int64_t max_gpu_me
     return B200ALN_SUCCESS;
 }
 
+int32_t b200aln_batch_set_window_length(b200aln_batch* b, int32_t window_length, int32_t skip_cigars) {
+    if (!b || window_length < 0) return B200ALN_INVALID_ARGUMENT;
+    if (!b->jobs.empty()) return B200ALN_GENERIC_ERROR; /* staged overlaps were budgeted for the old setting */
+    if (window_length == 0 && skip_cigars) return B200ALN_INVALID_ARGUMENT; /* nothing would come back */
+    b->window_length = window_length;
+    b->skip_cigars = skip_cigars != 0;
+    return B200ALN_SUCCESS;
+}
+
 int32_t b200aln_batch_add_alignment(b200aln_batch* b, const char* query, int32_t n, const char* target, int32_t m) {
-    if (!b || n < 0 || m < 0 || (n > 0 && !query) || (m > 0 && !target)) return B200ALN_INVALID_ARGUMENT;
+    return b200aln_batch_add_overlap(b, query, n, target, m, 0, 0);
+}
+
+int32_t b200aln_batch_add_overlap(b200aln_batch* b, const char* query, int32_t n, const char* target, int32_t m,
+                                  int32_t q_first, int32_t t_begin) {
+    if (!b || n < 0 || m < 0 || (n > 0 && !query) || (m > 0 && !target) || q_first < 0 || t_begin < 0)
+        return B200ALN_INVALID_ARGUMENT;
+    if ((int64_t)t_begin + m >= ((int64_t)1 << 31) || (int64_t)q_first + n >= ((int64_t)1 << 31)) return B200ALN_INVALID_ARGUMENT;
     if (b->aligned) return B200ALN_GENERIC_ERROR; /* reset() first, like a cudaaligner batch after align_all */
     if ((int64_t)n + m >= ((int64_t)1 << 30)) return B200ALN_EXCEEDED_MAX_LENGTH; /* run starts are 30-bit */
-    const int64_t vb = var_bytes_for(n, m);
+    const int64_t n_win = aln_window_count(t_begin, m, b->window_length);
+    const int64_t vb = var_bytes_for(n, m) + 16 * n_win;
     const int32_t new_max = std::max(b->max_len, std::max(n, m));
     /* the slots get what the alignments leave; at least one block's worth must remain */
     const int64_t min_slots = WARPS_PER_BLOCK * slot_bytes_for(round_len(new_max));
@@ -562,6 +612,9 @@ int32_t b200aln_batch_add_alignment(b200aln_batch* b, const char* query, int32_t
     j.ops_off = b->ops_bytes;
     j.n = n;
     j.m = m;
+    j.q_first = q_first;
+    j.t_begin = t_begin;
+    b->n_windows += n_win;
     b->ops_bytes += (int64_t)n + m;
     b->cap_open += aln_open_capacity(n, m);
     b->cap_leaves += aln_leaf_capacity(n, m);
@@ -582,7 +635,8 @@ int32_t b200aln_batch_align_all(b200aln_batch* b) {
     b->info.n_open = b->info.n_leaves = b->info.cells = 0;
     b->info.h2d_bytes = b->info.d2h_bytes = 0;
     b->info.kernel_ms = 0.f;
-    b->res.assign((size_t)n_aln, AlnResult{0, 0, 0, 0, 0, 0, 0, 0});
+    b->res.assign((size_t)n_aln, AlnResult{0, 0, 0, 0, 0, 0, 0, 0, 0});
+    b->h_bp.used = 0;
     b->runs_on_host = false;
     b->n_runs_total = 0;
     b->h_text.used = 0;
@@ -621,6 +675,9 @@ int32_t b200aln_batch_align_all(b200aln_batch* b) {
     ALN_CU(b->d_runs.need(sizeof(uint32_t) * ((size_t)b->ops_bytes + 64)));
     const unsigned long long text_cap = 2ull * (unsigned long long)b->ops_bytes + (unsigned long long)n_aln + 64; /* "1M1I..." at worst */
     ALN_CU(b->d_text.need((size_t)text_cap));
+    const bool want_bp = b->window_length > 0;
+    const unsigned long long bp_cap = 2ull * (unsigned long long)b->n_windows + 16; /* (t, q) pairs */
+    if (want_bp) ALN_CU(b->d_bp.need((size_t)bp_cap * 8));
     for (int c = 0; c < ALN_CLASSES; ++c) {
         ALN_CU(b->d_list[c][0].need(sizeof(AlnRect) * (size_t)cap_open));
         ALN_CU(b->d_list[c][1].need(sizeof(AlnRect) * (size_t)cap_open));
@@ -749,10 +806,15 @@ int32_t b200aln_batch_align_all(b200aln_batch* b) {
         ALN_CU(cudaGetLastError());
         ++launch;
     }
-    aln_cigar_kernel<<<grid_for(n_aln), 32 * WARPS_PER_BLOCK, 0, s>>>(a, n_aln, static_cast<uint32_t*>(b->d_runs.p),
-                                                                      (unsigned long long)b->ops_bytes + 64,
-                                                                      static_cast<uint8_t*>(b->d_text.p), text_cap,
-                                                                      ct + CT_CURSOR + launch);
+    AlnOutArgs oa;
+    oa.runs = static_cast<uint32_t*>(b->d_runs.p);
+    oa.runs_cap = (unsigned long long)b->ops_bytes + 64;
+    oa.text = b->skip_cigars ? nullptr : static_cast<uint8_t*>(b->d_text.p);
+    oa.text_cap = text_cap;
+    oa.bp = want_bp ? static_cast<uint32_t*>(b->d_bp.p) : nullptr;
+    oa.bp_cap = bp_cap;
+    oa.window_length = b->window_length;
+    aln_cigar_kernel<<<grid_for(n_aln), 32 * WARPS_PER_BLOCK, 0, s>>>(a, n_aln, oa, ct + CT_CURSOR + launch);
     ALN_CU(cudaGetLastError());
     ++launch;
     ALN_CU(cudaEventRecord(b->ev1, s));
@@ -760,7 +822,7 @@ int32_t b200aln_batch_align_all(b200aln_batch* b) {
     /* compact results: the per-alignment records and the counters now, then exactly the CIGAR bytes produced; the run
      * starts stay on the device until a caller asks for operations (b200aln_batch_get_alignment / _get_ops) */
     ALN_CU(cudaMemcpyAsync(b->res.data(), b->d_res.p, sizeof(AlnResult) * (size_t)n_aln, cudaMemcpyDeviceToHost, s));
-    ALN_CU(cudaMemcpyAsync(b->h_counters + CT_RUNS, ct + CT_RUNS, 6 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    ALN_CU(cudaMemcpyAsync(b->h_counters + CT_RUNS, ct + CT_RUNS, 10 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     ALN_CU(cudaStreamSynchronize(s));
     unsigned long long n_runs_total = 0, cells = 0, text_total = 0;
     std::memcpy(&n_runs_total, b->h_counters + CT_RUNS, 8);
@@ -773,7 +835,14 @@ int32_t b200aln_batch_align_all(b200aln_batch* b) {
     b->h_text.used = (size_t)text_total;
     if (text_total)
         ALN_CU(cudaMemcpyAsync(b->h_text.p, b->d_text.p, (size_t)text_total, cudaMemcpyDeviceToHost, s));
-    b->info.d2h_bytes = (int64_t)(sizeof(AlnResult) * (size_t)n_aln + (size_t)text_total + sizeof(int32_t) * (size_t)(level + 8));
+    unsigned long long bp_total = 0;
+    std::memcpy(&bp_total, b->h_counters + CT_BP, 8);
+    bp_total = want_bp ? std::min<unsigned long long>(bp_total, bp_cap) : 0;
+    if (!b->h_bp.reserve((size_t)bp_total * 8 + 64)) return B200ALN_GENERIC_ERROR;
+    b->h_bp.used = (size_t)bp_total * 8;
+    if (bp_total) ALN_CU(cudaMemcpyAsync(b->h_bp.p, b->d_bp.p, (size_t)bp_total * 8, cudaMemcpyDeviceToHost, s));
+    b->info.d2h_bytes = (int64_t)(sizeof(AlnResult) * (size_t)n_aln + (size_t)text_total + (size_t)bp_total * 8 +
+                                  sizeof(int32_t) * (size_t)(level + 12));
     b->aligned = true;
     b->synced = false;
     return B200ALN_SUCCESS;
@@ -793,12 +862,19 @@ int32_t b200aln_batch_sync(b200aln_batch* b) {
     b->t_len.resize(n_aln);
     b->t_ed.resize(n_aln);
     b->t_st.resize(n_aln);
+    b->bp_off_tab.resize(n_aln);
+    b->bp_cnt_tab.resize(n_aln);
     for (size_t k = 0; k < n_aln; ++k) {
         const AlnResult& r = b->res[k];
-        const bool ok = r.status == 0 && r.cigar_off >= 0 && r.cigar_len >= 0 &&
-                        (size_t)(r.cigar_off + r.cigar_len) < b->h_text.used; /* its terminating 0 included */
-        b->t_off[k] = ok ? r.cigar_off : 0;
-        b->t_len[k] = ok ? r.cigar_len : 0;
+        const bool bp_ok = b->window_length > 0 && r.status == 0 && r.bp_off >= 0 && r.bp_count >= 0 &&
+                           (size_t)(r.bp_off + r.bp_count) * 8 <= b->h_bp.used;
+        b->bp_off_tab[k] = bp_ok ? r.bp_off : 0;
+        b->bp_cnt_tab[k] = bp_ok ? r.bp_count : 0;
+        const bool ok = r.status == 0 && (b->skip_cigars ? (b->window_length == 0 || bp_ok) :
+                        (r.cigar_off >= 0 && r.cigar_len >= 0 &&
+                         (size_t)(r.cigar_off + r.cigar_len) < b->h_text.used)); /* its terminating 0 included */
+        b->t_off[k] = ok && !b->skip_cigars ? r.cigar_off : 0;
+        b->t_len[k] = ok && !b->skip_cigars ? r.cigar_len : 0;
         b->t_ed[k] = r.score;
         b->t_st[k] = ok ? B200ALN_SUCCESS : (r.status ? r.status : B200ALN_GENERIC_ERROR);
     }
@@ -806,10 +882,22 @@ int32_t b200aln_batch_sync(b200aln_batch* b) {
     return B200ALN_SUCCESS;
 }
 
+int32_t b200aln_batch_get_breaking_points(const b200aln_batch* b, const uint32_t** points, const int64_t** off,
+                                          const int32_t** count) {
+    if (!b) return B200ALN_INVALID_ARGUMENT;
+    if (!b->aligned || !b->synced) return B200ALN_UNINITIALIZED;
+    if (b->window_length <= 0) return B200ALN_GENERIC_ERROR; /* b200aln_batch_set_window_length first */
+    if (points) *points = reinterpret_cast<const uint32_t*>(b->h_bp.p);
+    if (off) *off = b->bp_off_tab.data();
+    if (count) *count = b->bp_cnt_tab.data();
+    return B200ALN_SUCCESS;
+}
+
 int32_t b200aln_batch_get_cigars(const b200aln_batch* b, const char** text, const int64_t** off, const int32_t** len,
                                  const int32_t** edit_distance, const int32_t** status) {
     if (!b) return B200ALN_INVALID_ARGUMENT;
     if (!b->aligned || !b->synced) return B200ALN_UNINITIALIZED;
+    if (b->skip_cigars) return B200ALN_GENERIC_ERROR; /* the batch was told not to form them */
     if (text) *text = reinterpret_cast<const char*>(b->h_text.p);
     if (off) *off = b->t_off.data();
     if (len) *len = b->t_len.data();
@@ -820,13 +908,20 @@ int32_t b200aln_batch_get_cigars(const b200aln_batch* b, const char** text, cons
 
 int32_t b200aln_batch_add_alignments(b200aln_batch* b, int64_t n, const uint8_t* q_bases, const int64_t* q_off,
                                      const uint8_t* t_bases, const int64_t* t_off, int64_t* n_added) {
+    return b200aln_batch_add_overlaps(b, n, q_bases, q_off, t_bases, t_off, nullptr, nullptr, n_added);
+}
+
+int32_t b200aln_batch_add_overlaps(b200aln_batch* b, int64_t n, const uint8_t* q_bases, const int64_t* q_off,
+                                   const uint8_t* t_bases, const int64_t* t_off, const int32_t* q_first,
+                                   const int32_t* t_begin, int64_t* n_added) {
     if (n_added) *n_added = 0;
     if (!b || n < 0 || (n > 0 && (!q_bases || !q_off || !t_bases || !t_off))) return B200ALN_INVALID_ARGUMENT;
     int64_t k = 0;
     int32_t st = B200ALN_SUCCESS;
     for (; k < n; ++k) {
-        st = b200aln_batch_add_alignment(b, reinterpret_cast<const char*>(q_bases + q_off[k]), (int32_t)(q_off[k + 1] - q_off[k]),
-                                         reinterpret_cast<const char*>(t_bases + t_off[k]), (int32_t)(t_off[k + 1] - t_off[k]));
+        st = b200aln_batch_add_overlap(b, reinterpret_cast<const char*>(q_bases + q_off[k]), (int32_t)(q_off[k + 1] - q_off[k]),
+                                       reinterpret_cast<const char*>(t_bases + t_off[k]), (int32_t)(t_off[k + 1] - t_off[k]),
+                                       q_first ? q_first[k] : 0, t_begin ? t_begin[k] : 0);
         if (st != B200ALN_SUCCESS) break;
     }
     if (n_added) *n_added = k;
@@ -873,6 +968,7 @@ int32_t b200aln_batch_get_alignment(const b200aln_batch* b, int32_t index, const
 int64_t b200aln_batch_get_cigar(const b200aln_batch* b, int32_t index, char* out, int64_t cap) {
     if (!b || index < 0 || (size_t)index >= b->jobs.size()) return -(int64_t)B200ALN_INVALID_ARGUMENT;
     if (!b->aligned || !b->synced) return -(int64_t)B200ALN_UNINITIALIZED;
+    if (b->skip_cigars) return -(int64_t)B200ALN_GENERIC_ERROR;
     if (b->t_st[(size_t)index] != B200ALN_SUCCESS) return -(int64_t)b->t_st[(size_t)index];
     const int64_t len = b->t_len[(size_t)index];
     if (out && cap > 0) {
@@ -905,6 +1001,8 @@ int32_t b200aln_batch_reset(b200aln_batch* b) {
     b->jobs.clear();
     b->h_seq.used = 0;
     b->ops_bytes = 0;
+    b->n_windows = 0;
+    b->h_bp.used = 0;
     b->cap_open = b->cap_leaves = 0;
     b->var_bytes = 0;
     b->max_len = 0;

@@ -202,7 +202,10 @@ def overlap_fixture():
     qs = _split(_unpack2(z["q_bases"], int(ql.sum())), ql)
     ts = _split(_unpack2(z["t_bases"], int(tl.sum())), tl)
     meta = [l.split() for l in z["cigar_sha"].tobytes().decode().strip().split("\n")]
-    return [{"q": qs[i], "t": ts[i], "score": int(z["score"][i]), "n_ops": int(meta[i][0]), "cigar_sha": meta[i][1]}
+    bo = np.concatenate([[0], np.cumsum(z["bp_count"])]) * 2
+    return [{"q": qs[i], "t": ts[i], "score": int(z["score"][i]), "n_ops": int(meta[i][0]), "cigar_sha": meta[i][1],
+             "q_first": int(z["q_first"][i]), "t_begin": int(z["t_begin"][i]),
+             "bp": z["bp"][bo[i]:bo[i + 1]].reshape(-1, 2)}  # racon's breaking points at window length 500
             for i in range(len(qs))]
 
 

@@ -19,9 +19,11 @@ extern "C" {
 
 /* Aligns one pair; ops_out must hold n + m bytes.  Returns the number of operations (holes removed); -1 inconsistent
  * split, -2 list overflow, -3 the runs do not spell the operations.  *score the edit distance; *levels (nullable) the
- * depth of the recursion; *n_leaves likewise; cigar_out (nullable, cigar_cap bytes) the CIGAR formed from the runs. */
+ * depth of the recursion; *n_leaves likewise; cigar_out (nullable, cigar_cap bytes) the CIGAR formed from the runs;
+ * bp_out (nullable, 4 words per window of the target segment) the breaking points for window_length. */
 int64_t emu_align(const uint8_t* q, int32_t n, const uint8_t* t, int32_t m, uint8_t* ops_out, int32_t* score,
-                  int32_t* levels, int32_t* n_leaves, char* cigar_out, int64_t cigar_cap) {
+                  int32_t* levels, int32_t* n_leaves, char* cigar_out, int64_t cigar_cap, int32_t q_first, int32_t t_begin,
+                  int32_t window_length, uint32_t* bp_out, int32_t* bp_count) {
     const int32_t max_len = (n > m ? n : m) + 1;
     size_t slot_bytes = 0;
     AlnSlot s;
@@ -93,6 +95,10 @@ int64_t emu_align(const uint8_t* q, int32_t n, const uint8_t* t, int32_t m, uint
         if (aln_cigar_text(runs.data(), n_runs, n_ops, reinterpret_cast<uint8_t*>(cigar_out)) != bytes) return -3;
         cigar_out[bytes] = 0;
         if (c != cigar_out) return -3;
+    }
+    if (bp_out && window_length > 0) { /* breaking points from the same run starts */
+        std::vector<int32_t> pre(2 * ((size_t)n_runs + 1) + 2);
+        *bp_count = aln_breaking_points(runs.data(), n_runs, n_ops, q_first, t_begin, m, window_length, pre.data(), bp_out);
     }
     if (levels) *levels = depth;
     if (n_leaves) *n_leaves = n_leaf;

@@ -9,6 +9,9 @@ CPU path calls it (oracle/_ref: ref_edlib_nw = src/overlap.cpp:205-224).
     q_len / t_len       int32  per overlap
     score               int32  edit distance
     cigar_sha           bytes  per overlap "n_ops sha256(cigar)\n" (the CIGAR strings total 2.5 MB; the inputs are here)
+    q_first / t_begin   int32  where the segments start in read (strand-adjusted, src/overlap.cpp:241) / contig coordinates
+    bp / bp_count       uint32 (t, q) breaking points of the UNMODIFIED racon::Overlap::find_breaking_points fed edlib's
+                               CIGAR, window length 500 (oracle/_ref: ref_racon_breaking_points = src/overlap.cpp:226-290)
 """
 import gzip, hashlib, os, sys
 import numpy as np
@@ -34,10 +37,10 @@ def fasta(path):
 
 if __name__ == "__main__":
     from make_lambda_golden import pack2
-    from oracle_lib import Ref, ref_align
+    from oracle_lib import Ref, ref_align, ref_breaking_points
     r = Ref(); assert r.available
     reads, contigs = fasta(os.path.join(DATA, "sample_reads.fasta.gz")), fasta(os.path.join(DATA, "sample_layout.fasta.gz"))
-    qs, ts, scores, shas = [], [], [], []
+    qs, ts, scores, shas, q_first, t_begin, bps, bp_count = [], [], [], [], [], [], [], []
     for line in gzip.open(os.path.join(DATA, "sample_overlaps.paf.gz"), "rt"):
         f = line.split("\t")
         qn, ql, qb, qe, strand, tn, tl, tb, te = f[0], int(f[1]), int(f[2]), int(f[3]), f[4], f[5], int(f[6]), int(f[7]), int(f[8])
@@ -48,10 +51,14 @@ if __name__ == "__main__":
         ops, score, cigar = ref_align(r, q, t)
         qs.append(q); ts.append(t); scores.append(score)
         shas.append(("%d %s\n" % (ops.shape[0], hashlib.sha256(cigar).hexdigest())).encode())
+        bp = ref_breaking_points(r, cigar, ql, qb, qe, 1 if strand == "-" else 0, tl, tb, te, 500)
+        q_first.append(ql - qe if strand == "-" else qb); t_begin.append(tb); bps.append(bp.reshape(-1)); bp_count.append(bp.shape[0])
     np.savez_compressed(os.path.join(HERE, "lambda_overlaps.npz"),
                         q_bases=pack2(np.frombuffer(b"".join(qs), dtype=np.uint8)),
                         t_bases=pack2(np.frombuffer(b"".join(ts), dtype=np.uint8)),
                         q_len=np.asarray([len(x) for x in qs], dtype=np.int32),
                         t_len=np.asarray([len(x) for x in ts], dtype=np.int32),
-                        score=np.asarray(scores, dtype=np.int32), cigar_sha=np.frombuffer(b"".join(shas), dtype=np.uint8))
+                        score=np.asarray(scores, dtype=np.int32), cigar_sha=np.frombuffer(b"".join(shas), dtype=np.uint8),
+                        q_first=np.asarray(q_first, dtype=np.int32), t_begin=np.asarray(t_begin, dtype=np.int32),
+                        bp=np.concatenate(bps).astype(np.uint32), bp_count=np.asarray(bp_count, dtype=np.int32))
     print("wrote", len(qs), "overlaps; mean identity-ish", 1 - sum(scores) / sum(len(x) for x in ts))

@@ -218,3 +218,29 @@ def ref_align(ref: "Ref", q: bytes, t: bytes):
                              C.c_int64(cap), cig, C.c_int64(ccap), C.byref(score))
     assert n >= 0
     return ops[:n].copy(), int(score.value), cig.value
+
+
+def oracle_breaking_points(oracle: "Oracle", ops: np.ndarray, q_first: int, t_begin: int, t_end: int, window_length: int):
+    """(t, q) pairs, two per window with a match (restatement of src/overlap.cpp:226-290 on operations)."""
+    ops = np.ascontiguousarray(ops, dtype=np.uint8)
+    cap = 2 * ((t_end - t_begin) // window_length + 3)
+    out = np.zeros(2 * cap, dtype=np.uint32)
+    oracle.lib.aln_oracle_breaking_points.restype = C.c_int64
+    n = oracle.lib.aln_oracle_breaking_points(_p(ops, C.c_uint8), C.c_int64(ops.shape[0]), C.c_int32(q_first),
+                                              C.c_int32(t_begin), C.c_int32(t_end), C.c_int32(window_length),
+                                              _p(out, C.c_uint32), C.c_int64(cap))
+    assert n >= 0
+    return out[:2 * n].reshape(-1, 2).copy()
+
+
+def ref_breaking_points(ref: "Ref", cigar: bytes, q_length: int, q_begin: int, q_end: int, strand: int, t_length: int,
+                        t_begin: int, t_end: int, window_length: int):
+    """The unmodified racon::Overlap::find_breaking_points (src/overlap.cpp:179-203,226-290) fed this CIGAR."""
+    cap = 2 * ((t_end - t_begin) // window_length + 3)
+    out = np.zeros(2 * cap, dtype=np.uint32)
+    ref.lib.ref_racon_breaking_points.restype = C.c_int64
+    n = ref.lib.ref_racon_breaking_points(C.c_char_p(cigar), C.c_uint32(q_length), C.c_uint32(q_begin), C.c_uint32(q_end),
+                                          C.c_int(strand), C.c_uint32(t_length), C.c_uint32(t_begin), C.c_uint32(t_end),
+                                          C.c_uint32(window_length), _p(out, C.c_uint32), C.c_int64(cap))
+    assert n >= 0
+    return out[:2 * n].reshape(-1, 2).copy()

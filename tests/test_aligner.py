@@ -103,3 +103,36 @@ def test_emulated_aligner_on_long_reads_against_live_edlib(ref, emu):
         a, sa, depth, leaves = emu.align(q, t)
         assert sa == score and a.shape == ops.shape and (a == ops).all() and emu.cigar == cigar
     assert depth >= 3
+
+
+def test_breaking_points_restatement_and_engine(oracle, ref, emu):
+    """src/overlap.cpp:226-290: the oracle's restatement against the UNMODIFIED racon (oracle/_ref) on random overlaps
+    with random coordinates / strands / window lengths, the committed real breaking points (window length 500), and the
+    engine's run-based version (lane emulation) against both."""
+    from oracle_lib import oracle_breaking_points, ref_breaking_points
+    rng = np.random.default_rng(3)
+    for rep in range(60):
+        n, e = int(rng.integers(1, 3000)), float(rng.uniform(0.02, 0.4))
+        q, t = random_pairs(2000 + rep, [(n, e)])[0]
+        w = int(rng.choice([1, 7, 50, 100, 500, 1000, 5000]))
+        t_begin = int(rng.integers(0, 2500))
+        strand, q_len = int(rng.integers(0, 2)), len(q) + int(rng.integers(0, 300))
+        q_begin = int(rng.integers(0, q_len - len(q) + 1))
+        q_first = q_len - (q_begin + len(q)) if strand else q_begin
+        ops, score = oracle_align(oracle, q, t)
+        want = oracle_breaking_points(oracle, ops, q_first, t_begin, t_begin + len(t), w)
+        if ref.available:
+            got = ref_breaking_points(ref, ops_to_cigar(oracle, ops), q_len, q_begin, q_begin + len(q), strand,
+                                      t_begin + len(t) + 5, t_begin, t_begin + len(t), w)
+            assert got.shape == want.shape and (got == want).all(), rep
+        emu.align(q, t, q_first, t_begin, w)
+        assert emu.breaking_points.shape == want.shape and (emu.breaking_points == want).all(), (rep, n, w)
+    fx = overlap_fixture()
+    order = np.argsort([len(f["q"]) * len(f["t"]) for f in fx])
+    for i in list(order[:10]) + [order[100], order[-1]]:
+        f = fx[i]
+        ops, score = oracle_align(oracle, f["q"], f["t"])
+        want = oracle_breaking_points(oracle, ops, f["q_first"], f["t_begin"], f["t_begin"] + len(f["t"]), 500)
+        assert want.shape == f["bp"].shape and (want == f["bp"]).all(), i
+        emu.align(f["q"], f["t"], f["q_first"], f["t_begin"], 500)
+        assert (emu.breaking_points == f["bp"]).all(), i

@@ -128,6 +128,55 @@ def test_aligner_pool_threads_and_devices(devices, batches):
     pool.close()
 
 
+@pytest.mark.parametrize("skip_cigars", [False, True])
+def test_breaking_points_of_real_overlaps_equal_racons(skip_cigars):
+    """Overlap::find_breaking_points_from_cigar (src/overlap.cpp:226-290) on the device: all 181 real overlaps, window
+    length 500, against what the UNMODIFIED racon derives from edlib's CIGAR (tests/golden/lambda_overlaps.npz: bp)."""
+    from racon_gpu_b200.aligner import CUDABatchAligner, pack_pairs
+    fx = overlap_fixture()
+    q, qo, t, to = pack_pairs([(f["q"], f["t"]) for f in fx])
+    al = CUDABatchAligner(device_id=0, max_gpu_memory=8 << 30)
+    al.set_window_length(500, skip_cigars=skip_cigars)
+    assert al.add_overlaps(q, qo, t, to, 0, np.asarray([f["q_first"] for f in fx]), np.asarray([f["t_begin"] for f in fx])) == len(fx)
+    al.align_all()
+    bps = al.breaking_points()
+    for k, f in enumerate(fx):
+        assert bps[k].shape == f["bp"].shape and (bps[k] == f["bp"]).all(), k
+    if skip_cigars:
+        with pytest.raises(RuntimeError):
+            al.cigars()
+        assert al.info()["d2h_bytes"] < 200_000  # 5116 points x 8 B + 48 B per overlap: no CIGAR bytes came back
+    else:
+        text, off, ln, ed = al.cigars()
+        for k, f in enumerate(fx):
+            assert hashlib.sha256(text[off[k]:off[k] + ln[k]]).hexdigest() == f["cigar_sha"], k
+    al.close()
+
+
+def test_breaking_points_random_coordinates_and_window_lengths(oracle):
+    from oracle_lib import oracle_breaking_points
+    from racon_gpu_b200.aligner import CUDABatchAligner
+    rng = np.random.default_rng(9)
+    for w in (1, 7, 100, 500, 5000):
+        al = CUDABatchAligner(device_id=0, max_gpu_memory=2 << 30)
+        al.set_window_length(w)
+        cases = []
+        for rep in range(24):
+            n, e = int(rng.integers(1, 4000)), float(rng.uniform(0.02, 0.4))
+            q, t = random_pairs(3000 + 100 * w + rep, [(n, e)])[0]
+            q_first, t_begin = int(rng.integers(0, 5000)), int(rng.integers(0, 50000))
+            st = al.lib.b200aln_batch_add_overlap(al.h, q, len(q), t, len(t), q_first, t_begin)
+            assert st == 0
+            cases.append((q, t, q_first, t_begin))
+        al.align_all()
+        bps = al.breaking_points()
+        for k, (q, t, q_first, t_begin) in enumerate(cases):
+            ops, score = oracle_align(oracle, q, t)
+            want = oracle_breaking_points(oracle, ops, q_first, t_begin, t_begin + len(t), w)
+            assert bps[k].shape == want.shape and (bps[k] == want).all(), (w, k)
+        al.close()
+
+
 def test_full_batch_is_back_pressure_not_an_error(oracle):
     """Aligner::add_alignment -> exceeded_max_alignments => addOverlap returns false (cudaaligner.cpp:64-67); the
     caller aligns, resets and goes on (cudapolisher.cpp:139-174).  Results do not depend on the batching."""
