@@ -390,7 +390,7 @@ def measure_aligner(args, local_rank, rep=32, steps=3, warmup=2, cpu_seconds=6.0
     kms = sum(r["kernel_ms"] for r in recs) / len(recs)
     r0 = recs[0]
     sm_mhz = 1965.0
-    peak = 148 * 4 * sm_mhz * 1e6 / (2.0 * 33.0) * 2048.0  # see DESIGN.md section 11: ALU pipe, 33 instructions a step
+    peak = 148 * 4 * sm_mhz * 1e6 / (2.0 * 24.0) * 2048.0  # see DESIGN.md section 11: ALU pipe, 24 instructions a step
     out = {"workload": f"real lambda-phage overlaps x{rep}: {len(pairs)} pairs, {int(qo[-1] + to[-1])} bases, "
                        f"{matrix:.3g} matrix cells, unit-cost NW with path (edlib's alignment, bit-exact)",
            "steps": steps, "warmup": warmup, "unit": "overlaps/s",
@@ -403,7 +403,7 @@ def measure_aligner(args, local_rank, rep=32, steps=3, warmup=2, cpu_seconds=6.0
                         "frac": r0["cells"] / (kms / 1e3) / peak, "traffic": None,
                         "kernel": "aln_split_kernel / aln_split_team_kernel / aln_leaf_kernel (all launches of a step)",
                         "cells_computed_per_step": r0["cells"],
-                        "peak_source": "148 SMs x 4 schedulers x 1965 MHz / (33 ALU-pipe instructions x 2 cycles) per "
+                        "peak_source": "148 SMs x 4 schedulers x 1965 MHz / (24 ALU-pipe instructions x 2 cycles) per "
                                        "32-lane x 64-row step (SASS count, DESIGN.md section 11)"}}
     try:  # CPU side: the unmodified edlib as racon calls it (oracle/_ref), bounded sample, usable cores
         from oracle_lib import Ref, ref_align

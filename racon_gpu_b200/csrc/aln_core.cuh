@@ -135,6 +135,9 @@ ALN_HD void aln_slot_bind(AlnSlot& s, uint8_t* base, int32_t max_len, size_t* to
 /* The match masks of a lane's block, one 64-bit word per character code, looked up once per column: shared memory on
  * the device (one LDS instead of a chain of selects; [5][32] words per warp), a plain array in the emulation. */
 #define ALN_EQ_WORDS (5 * 32)
+#ifndef ALN_STEP_UNROLL
+#define ALN_STEP_UNROLL 16 /* 1, 2, 4, 8 or 16 */
+#endif
 struct EqTab {
 #if POA_DEVICE
     uint32_t sa; /* shared-memory address of this warp's table */
@@ -278,6 +281,41 @@ POA_FN uint32_t hrow_load(const uint32_t* p) {
 #endif
 }
 
+/* The step's shifts on the FMA pipe.  LOP3 / IADD3 / SHF all issue on the ALU pipe (one warp instruction per two cycles
+ * per scheduler) and the step is bound by it; integer multiply-add issues on the other pipe.  (x << 1) | bit is
+ * x * 2 + bit (bit 0 of x * 2 is clear), x >> 31 is the high word of x * 2: written as mad / mul.hi in PTX so that the
+ * compiler cannot strength-reduce them back into shifts and adds. */
+POA_FN uint64_t shl1_or_bit(uint64_t x, uint32_t bit) {
+#if POA_DEVICE
+    const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    uint32_t nlo, carry, nhi; /* three multiply-adds; a wide one is turned back into LEA + LEA.HI.X (ALU pipe) */
+    asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(nlo) : "r"(lo), "r"(bit));
+    asm("mul.hi.u32 %0, %1, 2;" : "=r"(carry) : "r"(lo));
+    asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(nhi) : "r"(hi), "r"(carry));
+    return ((uint64_t)nhi << 32) | nlo;
+#else
+    return (x << 1) | bit;
+#endif
+}
+POA_FN int top_bit(uint64_t x) { /* bit 63 */
+#if POA_DEVICE
+    uint32_t r;
+    asm("mul.hi.u32 %0, %1, 2;" : "=r"(r) : "r"((uint32_t)(x >> 32)));
+    return (int)r;
+#else
+    return (int)(x >> 63);
+#endif
+}
+POA_FN int twice_plus(int a, int b) { /* 2 a + b */
+#if POA_DEVICE
+    int r;
+    asm("mad.lo.s32 %0, %1, 2, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+#else
+    return 2 * a + b;
+#endif
+}
+
 /* a character that is none of ACGT equals only itself (edlib's alphabet is the set of bytes seen): rare */
 POA_FN uint64_t eq_other(const SeqView q, int32_t row0, int32_t cnt, int tc) {
     uint64_t Eq = 0;
@@ -313,11 +351,18 @@ POA_FN_NOINLINE void myers_pass(const SeqView q, int32_t n, const SeqView t, int
     if (TEAM && team.n > 1) {
         POA_LANE0 { team_publish(team, 0, 0); } /* progress words of the previous pass are void */
     }
-    for (int32_t base = -64 + 32 * team.w; base < cols + 64; base += 32 * team.n) {
+    /* every warp of a team looks at the whole target once (does it hold a character that is none of ACGT?) and writes
+     * its share of the code row */
+    bool has_other = false;
+    for (int32_t base = -64; base < cols + 64; base += 32) {
+        PerLane<int> other;
         POA_LANES(l) {
             const int32_t c = base + l;
-            tcode[c] = (c >= 0 && c < cols) ? (uint8_t)aln_code(seq_at(t, c)) : (uint8_t)0;
+            const int code = (c >= 0 && c < cols) ? aln_code(seq_at(t, c)) : 0;
+            other[l] = code == 4;
+            if (((base + 64) >> 5) % team.n == team.w) tcode[c] = (uint8_t)code;
         }
+        if (warp_ballot(other)) has_other = true;
     }
     if (out_col && team.w == 0) {
         POA_LANE0 { out_col[0] = cols; }
@@ -371,57 +416,78 @@ POA_FN_NOINLINE void myers_pass(const SeqView q, int32_t n, const SeqView t, int
         }
         POA_SYNC();
         const int32_t steps = cols + nb - 1;
-        for (int32_t step = 0; step < steps; ++step) {
-            if ((step & 15) == 0 && step > 0) { /* the next 16 entering deltas; their successor word a word ahead */
+        /* One step of the wavefront.  OTHER = 0 leaves out the cold path for characters that are none of ACGT (a pass
+         * whose target holds none -- the rule -- runs the unrolled loop below without carrying that code 16 times). */
+#define ALN_STEP(OTHER)                                                                                                  \
+    {                                                                                                                    \
+        const int h0 = (int)((hword >> ((step & 15) * 2)) & 3u);                                                         \
+        PerLane<int> in;                                                                                                 \
+        warp_shift_up1(link, in); /* in[l] = the delta code lane l - 1 produced in the previous step */                  \
+        POA_LANES(l) {                                                                                                   \
+            const int32_t c = step - l;                                                                                  \
+            const int code = tc_next[l];                                                                                 \
+            const int hcode = l == 0 ? h0 : in[l];                                                                       \
+            tc_next[l] = glb_u8(tcode + (c + 1)); /* next step's column, a step ahead of its use */                      \
+            if (l < nb && (uint32_t)c < (uint32_t)cols) { /* lane l works on column c */                                 \
+                uint64_t Eq;                                                                                             \
+                if (!(OTHER) || code < 4) Eq = eq_load(eq, code, l);                                                     \
+                else Eq = eq_other(q, 64 * (s0 + l), n - 64 * (s0 + l) < 64 ? n - 64 * (s0 + l) : 64, (int)seq_at(t, c)); \
+                const uint64_t pv = Pv[l], mv = Mv[l];                                                                   \
+                const uint32_t pos = (uint32_t)(hcode & 1), neg = (uint32_t)(hcode >> 1); /* hcode <= 2 */               \
+                const uint64_t Xv = Eq | mv;                                                                             \
+                const uint64_t Eh = Eq | (uint64_t)neg;                                                                  \
+                const uint64_t Xh = (((Eh & pv) + pv) ^ pv) | Eh;                                                        \
+                uint64_t Ph = mv | ~(Xh | pv);                                                                           \
+                uint64_t Mh = pv & Xh;                                                                                   \
+                const int ph63 = top_bit(Ph), mh63 = top_bit(Mh);                                                        \
+                Ph = shl1_or_bit(Ph, pos);                                                                               \
+                Mh = shl1_or_bit(Mh, neg);                                                                               \
+                const uint64_t npv = Mh | ~(Xv | Ph);                                                                    \
+                const uint64_t nmv = Ph & Xv;                                                                            \
+                Pv[l] = npv;                                                                                             \
+                Mv[l] = nmv;                                                                                             \
+                bot[l] = bot[l] + ph63 - mh63;                                                                           \
+                const int out = twice_plus(mh63, ph63); /* 1 = +1, 2 = -1 */                                             \
+                if (PM) {                                                                                                \
+                    const int64_t e = (int64_t)s0 * (cols + 31) + (int64_t)step * nb + l;                                \
+                    PM[e] = RecPM{npv, nmv};                                                                             \
+                    S[e] = bot[l];                                                                                       \
+                }                                                                                                        \
+                if (more && l == 31) { /* 16 columns to a word; this row's reader is at least 16 columns behind */       \
+                    hacc[l] |= out << ((c & 15) * 2);                                                                    \
+                    if ((c & 15) == 15 || c == cols - 1) {                                                               \
+                        row_out[c >> 4] = (uint32_t)hacc[l];                                                             \
+                        hacc[l] = 0;                                                                                     \
+                        if (TEAM && team.n > 1 && ((c & 31) == 31 || c == cols - 1)) team_publish(team, sidx, c + 1);    \
+                    }                                                                                                    \
+                }                                                                                                        \
+                link[l] = out;                                                                                           \
+            }                                                                                                            \
+        }                                                                                                                \
+    }
+        /* ALN_STEP_UNROLL steps to a group (a divisor of 16): inside a group the entering delta's bit position and the
+         * code row's offsets are immediates and the once-in-16-steps bookkeeping costs nothing; the steps a group runs
+         * past `steps` find every lane's column out of range */
+        for (int32_t step0 = 0; step0 < steps; step0 += ALN_STEP_UNROLL) {
+            if ((step0 & 15) == 0 && step0 > 0) { /* the next 16 entering deltas; their successor word a word ahead */
                 hword = hword_next;
-                if (piped) team_wait(team, sidx - 1, cols < step + 32 ? cols : step + 32);
-                if (lower) hword_next = hrow_load(row_in + (step >> 4) + 1);
+                if (piped) team_wait(team, sidx - 1, cols < step0 + 32 ? cols : step0 + 32);
+                if (lower) hword_next = hrow_load(row_in + (step0 >> 4) + 1);
             }
-            const int h0 = (int)((hword >> ((step & 15) * 2)) & 3u);
-            PerLane<int> in;
-            warp_shift_up1(link, in); /* in[l] = the delta code lane l - 1 produced in the previous step */
-            POA_LANES(l) {
-                const int32_t c = step - l;
-                const int code = tc_next[l];
-                const int hcode = l == 0 ? h0 : in[l];
-                tc_next[l] = glb_u8(tcode + (c + 1)); /* next step's column, a step ahead of its use */
-                if (l < nb && (uint32_t)c < (uint32_t)cols) { /* lane l works on column c */
-                    uint64_t Eq;
-                    if (code < 4) Eq = eq_load(eq, code, l);
-                    else Eq = eq_other(q, 64 * (s0 + l), n - 64 * (s0 + l) < 64 ? n - 64 * (s0 + l) : 64, (int)seq_at(t, c));
-                    const uint64_t pv = Pv[l], mv = Mv[l];
-                    const uint64_t pos = (uint64_t)(hcode & 1), neg = (uint64_t)((hcode >> 1) & 1);
-                    const uint64_t Xv = Eq | mv;
-                    const uint64_t Eh = Eq | neg;
-                    const uint64_t Xh = (((Eh & pv) + pv) ^ pv) | Eh;
-                    uint64_t Ph = mv | ~(Xh | pv);
-                    uint64_t Mh = pv & Xh;
-                    const int ph63 = (int)(Ph >> 63), mh63 = (int)(Mh >> 63);
-                    Ph = (Ph << 1) | pos;
-                    Mh = (Mh << 1) | neg;
-                    const uint64_t npv = Mh | ~(Xv | Ph);
-                    const uint64_t nmv = Ph & Xv;
-                    Pv[l] = npv;
-                    Mv[l] = nmv;
-                    bot[l] = bot[l] + ph63 - mh63;
-                    const int out = ph63 | (mh63 << 1);
-                    if (PM) {
-                        const int64_t e = (int64_t)s0 * (cols + 31) + (int64_t)step * nb + l;
-                        PM[e] = RecPM{npv, nmv};
-                        S[e] = bot[l];
-                    }
-                    if (more && l == 31) { /* 16 columns to a word; this row's reader is at least 16 columns behind */
-                        hacc[l] |= out << ((c & 15) * 2);
-                        if ((c & 15) == 15 || c == cols - 1) {
-                            row_out[c >> 4] = (uint32_t)hacc[l];
-                            hacc[l] = 0;
-                            if (TEAM && team.n > 1 && ((c & 31) == 31 || c == cols - 1)) team_publish(team, sidx, c + 1);
-                        }
-                    }
-                    link[l] = out;
+            if (!has_other) {
+#pragma unroll
+                for (int32_t u = 0; u < ALN_STEP_UNROLL; ++u) {
+                    const int32_t step = step0 + u;
+                    ALN_STEP(0)
+                }
+            } else {
+                for (int32_t u = 0; u < ALN_STEP_UNROLL; ++u) {
+                    const int32_t step = step0 + u;
+                    ALN_STEP(1)
                 }
             }
         }
+#undef ALN_STEP
         if (out_col) { /* the last column, row by row: D = (score above the block) + running sum of the vertical deltas */
             POA_LANES(l) {
                 if (l < nb) {
