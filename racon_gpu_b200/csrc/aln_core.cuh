@@ -589,17 +589,17 @@ POA_FN uint64_t warp_get64(const PerLane<uint64_t>& x, int src) {
 POA_FN uint64_t aln_below(int32_t k) { return k == 63 ? (uint64_t)0 : (~(uint64_t)0 << (k + 1)); } /* rows under row k */
 POA_FN int aln_bit(uint64_t x, int32_t k) { return (int)((x >> k) & 1u); }
 
-/* The records of block b for the 32 columns jw, jw-1, .. jw-31 (lane l holds column jw - l): one strided load per field
- * instead of a dependent round trip per traceback step */
+/* The records of block b for the 32 columns jw, jw-1, .. jw-31 (lane l holds column c = jw - l AND its left neighbour
+ * c - 1): one round of strided loads instead of a dependent round trip per traceback step */
 struct LeafWindow {
-    PerLane<uint64_t> P, M;
-    PerLane<int> S;
+    PerLane<uint64_t> P, M, Pn, Mn; /* column c, column c - 1 */
+    PerLane<int> S, Sn;
 };
 POA_FN void leaf_window_load(const AlnSlot& s, LeafWindow& w, int32_t b, int32_t jw, int32_t B, int32_t cols) {
     POA_LANES(l) {
         const int32_t c = jw - l;
-        uint64_t p = 0, m = 0;
-        int sc = 0;
+        uint64_t p = 0, m = 0, pn = 0, mn = 0;
+        int sc = 0, scn = 0;
         if (c >= 0) {
             const int64_t e = leaf_entry(b, c, B, cols);
             const RecPM r = s.PM[e];
@@ -607,20 +607,33 @@ POA_FN void leaf_window_load(const AlnSlot& s, LeafWindow& w, int32_t b, int32_t
             m = r.m;
             sc = s.S[e];
         }
+        if (c >= 1) {
+            const int64_t e = leaf_entry(b, c - 1, B, cols);
+            const RecPM r = s.PM[e];
+            pn = r.p;
+            mn = r.m;
+            scn = s.S[e];
+        }
         w.P[l] = p;
         w.M[l] = m;
         w.S[l] = sc;
+        w.Pn[l] = pn;
+        w.Mn[l] = mn;
+        w.Sn[l] = scn;
     }
 }
 
 /*
  * ops: the (n + m)-byte region of this sub-problem, filled from its END backwards (holes stay OP_NONE in front).
- * The walk is executed by the whole warp in lock step (every lane holds the same position); cell (i, j) stands for
- * D[i + 1][j + 1].  With (Pj, Mj) the record of (block of i, column j) and (Pl, Ml, Sl) that of column j - 1:
- *   up        = cur - bit_k(Pj) + bit_k(Mj)                      (the vertical delta of row i, k = i mod 64)
- *   left      = Sl - popc(Pl & below k) + popc(Ml & below k)      (bottom of the block minus the deltas under row i)
- *   diagonal  = left - bit_k(Pl) + bit_k(Ml)
- * so a step costs no memory access; a new window is loaded every 31 columns or when the path enters the block above.
+ * Cell (i, j) stands for D[i + 1][j + 1].  Any cell's value follows from its block's record alone -- bottom score minus the
+ * +1 deltas under the row plus the -1 deltas under it -- so the move edlib takes AT a cell (first possible of up, left,
+ * diagonal; edlib.cpp:983-1093) does not depend on how the walk got there.  The warp therefore looks at the 32 cells of
+ * the DIAGONAL through the current one at once: lane d rates cell (i - d, j - d) from the records of its column and the
+ * column to the left (with k = row mod 64:  cell = S - popc(P & below k) + popc(M & below k);  up = cell - bit_k(P) +
+ * bit_k(M);  left and diagonal the same from the neighbour column), one ballot gives the length of the run of diagonal
+ * moves in front of the walk, and the whole run -- matches and mismatches -- is written in one coalesced store.  Up and
+ * left moves take a round each.  A new window of records is loaded every 25 columns or when the walk enters the block
+ * above.
  */
 POA_FN_NOINLINE void aln_leaf(const AlnSlot& s_ref, EqTab& eq, const uint8_t* q, const uint8_t* t, int32_t n, int32_t m,
                               uint8_t* ops, int32_t* score_out) {
@@ -644,70 +657,63 @@ POA_FN_NOINLINE void aln_leaf(const AlnSlot& s_ref, EqTab& eq, const uint8_t* q,
     myers_pass<false>(SeqView{q, 1}, n, SeqView{t, 1}, m, TeamCtx{0, 1, 0, 0}, s.hbuf, 0, s.tcode, eq, nullptr, s.PM, s.S);
     const int32_t B = (n + 63) / 64;
     LeafWindow win;
-    int32_t i = n - 1, j = m - 1, jw = j;
-    leaf_window_load(s, win, i >> 6, jw, B, m);
-    uint64_t Pj = warp_get64(win.P, 0), Mj = warp_get64(win.M, 0);
-    uint64_t Pl = warp_get64(win.P, 1), Ml = warp_get64(win.M, 1);
-    int32_t Sl = warp_get(win.S, 1);
-    int32_t cur = warp_get(win.S, 0) - aln_popc64(Pj & aln_below(i & 63)) + aln_popc64(Mj & aln_below(i & 63));
+    int32_t i = n - 1, j = m - 1;
+    int32_t jw = j, wb = i >> 6; /* the window: columns jw .. jw - 31 of block wb */
+    leaf_window_load(s, win, wb, jw, B, m);
     if (score_out) {
-        POA_LANE0 { *score_out = cur; }
+        POA_LANE0 {
+            const int32_t k = i & 63;
+            *score_out = win.S[0] - aln_popc64(win.P[0] & aln_below(k)) + aln_popc64(win.M[0] & aln_below(k));
+        }
     }
     int32_t w = n + m; /* next write position + 1 */
     while (i >= 0 && j >= 0) {
-        const int32_t k = i & 63;
-        const int32_t u = cur - aln_bit(Pj, k) + aln_bit(Mj, k);
-        int32_t lf, ul;
-        if (j > 0) {
-            lf = Sl - aln_popc64(Pl & aln_below(k)) + aln_popc64(Ml & aln_below(k));
-            ul = lf - aln_bit(Pl, k) + aln_bit(Ml, k);
-        } else { /* the left border: D[i + 1][0] = i + 1 */
-            lf = i + 1;
-            ul = i;
-        }
-        uint8_t op;
-        bool row_move, col_move;
-        if (u + 1 == cur) { /* up: the query character stands alone (edlib.cpp:983-1013) */
-            op = OP_INSERT;
-            row_move = true;
-            col_move = false;
-            cur = u;
-        } else if (lf + 1 == cur) { /* left: the target character stands alone (:1015-1044) */
-            op = OP_DELETE;
-            row_move = false;
-            col_move = true;
-            cur = lf;
-        } else { /* diagonal (:1046-1093) */
-            op = ul == cur ? OP_MATCH : OP_MISMATCH;
-            row_move = col_move = true;
-            cur = ul;
-        }
-        --w;
-        POA_LANE0 { ops[w] = op; }
-        if (row_move) --i;
-        if (col_move) --j;
-        if (i < 0 || j < 0) break;
-        if (row_move && k == 0) { /* the path entered the block above: its records, from column j on */
+        if ((i >> 6) != wb || jw - j > 24) { /* the walk left the window, or fewer than 7 cells of its diagonal are in it */
+            wb = i >> 6;
             jw = j;
-            leaf_window_load(s, win, i >> 6, jw, B, m);
-            Pj = warp_get64(win.P, 0);
-            Mj = warp_get64(win.M, 0);
-            Pl = warp_get64(win.P, 1);
-            Ml = warp_get64(win.M, 1);
-            Sl = warp_get(win.S, 1);
-        } else if (col_move) {
-            Pj = Pl;
-            Mj = Ml;
-            if (j > 0) {
-                if (jw - (j - 1) > 31) {
-                    jw = j;
-                    leaf_window_load(s, win, i >> 6, jw, B, m);
+            leaf_window_load(s, win, wb, jw, B, m);
+        }
+        const int32_t off = jw - j, k = i & 63;
+        PerLane<int> is_diag, is_up, is_match;
+        POA_LANES(l) {
+            const int32_t d = l - off, kk = k - d; /* lane l rates cell (i - d, j - d): row kk of the block, column jw - l */
+            int diag = 0, up = 0, match = 0;
+            if (d >= 0 && kk >= 0 && jw - l >= 0) {
+                const uint64_t under = aln_below(kk);
+                const int32_t cell = win.S[l] - aln_popc64(win.P[l] & under) + aln_popc64(win.M[l] & under);
+                const int32_t u = cell - aln_bit(win.P[l], kk) + aln_bit(win.M[l], kk);
+                int32_t lf, ul;
+                if (jw - l > 0) {
+                    lf = win.Sn[l] - aln_popc64(win.Pn[l] & under) + aln_popc64(win.Mn[l] & under);
+                    ul = lf - aln_bit(win.Pn[l], kk) + aln_bit(win.Mn[l], kk);
+                } else { /* the left border: D[r + 1][0] = r + 1 */
+                    lf = (i - d) + 1;
+                    ul = i - d;
                 }
-                const int src = jw - (j - 1);
-                Pl = warp_get64(win.P, src);
-                Ml = warp_get64(win.M, src);
-                Sl = warp_get(win.S, src);
+                if (u + 1 == cell) up = 1;                 /* up: the query character stands alone (edlib.cpp:983-1013) */
+                else if (lf + 1 != cell) diag = 1;          /* not left (:1015-1044) either: diagonal (:1046-1093)        */
+                match = ul == cell;
             }
+            is_diag[l] = diag;
+            is_up[l] = up;
+            is_match[l] = match;
+        }
+        const unsigned dm = warp_ballot(is_diag) >> off; /* bit d: the cell d steps down the diagonal moves diagonally */
+        const int32_t run = ~dm == 0u ? 32 : poa_ffs(~dm);
+        if (run > 0) {
+            POA_LANES(l) {
+                const int32_t d = l - off;
+                if (d >= 0 && d < run) ops[w - 1 - d] = is_match[l] ? OP_MATCH : OP_MISMATCH;
+            }
+            w -= run;
+            i -= run;
+            j -= run;
+        } else {
+            const bool up = ((warp_ballot(is_up) >> off) & 1u) != 0u;
+            --w;
+            POA_LANE0 { ops[w] = up ? OP_INSERT : OP_DELETE; }
+            if (up) --i;
+            else --j;
         }
     }
     /* along the left border (insertions) or the top border (deletions) */
