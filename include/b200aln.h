@@ -81,6 +81,16 @@ int32_t b200aln_batch_add_overlaps(b200aln_batch* b, int64_t n, const uint8_t* q
                                    const uint8_t* t_bases, const int64_t* t_off, const int32_t* q_first,
                                    const int32_t* t_begin, int64_t* n_added);
 
+/* The same without the staging copy: the batch (which must be empty) REFERENCES the caller's columnar buffers for pairs
+ * 0 .. *n_added - 1 and uploads those byte ranges straight from them in align_all; the buffers must stay valid and
+ * unchanged until align_all has returned.  Page-lock them once (b200aln_host_register, or any pinned allocation) and the
+ * upload runs at full PCIe speed. */
+int32_t b200aln_batch_add_overlaps_view(b200aln_batch* b, int64_t n, const uint8_t* q_bases, const int64_t* q_off,
+                                        const uint8_t* t_bases, const int64_t* t_off, const int32_t* q_first,
+                                        const int32_t* t_begin, int64_t* n_added);
+int32_t b200aln_host_register(const void* p, int64_t bytes);   /* cudaHostRegister (portable) */
+int32_t b200aln_host_unregister(const void* p);
+
 /* After sync: overlap k's breaking points are count[k] pairs (t, q) of uint32 at points + 2 * off[k] (always an even
  * number: first / last per window, in window order = Overlap::breaking_points(), overlap.hpp:68-70). */
 int32_t b200aln_batch_get_breaking_points(const b200aln_batch* b, const uint32_t** points, const int64_t** off,

@@ -20,7 +20,8 @@ ALN_ABI_SYMBOLS = (
     "b200aln_status_string", "b200aln_align_pairs", "b200aln_batch_add_alignments", "b200aln_batch_get_cigars",
     "b200aln_aligner_create", "b200aln_aligner_num_batches", "b200aln_aligner_align", "b200aln_aligner_destroy",
     "b200aln_batch_set_window_length", "b200aln_batch_add_overlap", "b200aln_batch_add_overlaps",
-    "b200aln_batch_get_breaking_points",
+    "b200aln_batch_get_breaking_points", "b200aln_batch_add_overlaps_view", "b200aln_host_register",
+    "b200aln_host_unregister",
 )
 
 SUCCESS, UNINITIALIZED, EXCEEDED_MAX_ALIGNMENTS, EXCEEDED_MAX_LENGTH = 0, 1, 2, 3
@@ -87,15 +88,17 @@ class CUDABatchAligner:
         return True
 
     def add_overlaps(self, q: np.ndarray, q_off: np.ndarray, t: np.ndarray, t_off: np.ndarray, first: int = 0,
-                     q_first: np.ndarray | None = None, t_begin: np.ndarray | None = None) -> int:
-        """b200aln_batch_add_overlaps from pair `first` on: how many went in before the batch was full."""
+                     q_first: np.ndarray | None = None, t_begin: np.ndarray | None = None, view: bool = False) -> int:
+        """b200aln_batch_add_overlaps[_view] from pair `first` on: how many went in before the batch was full.
+        view=True: no staging copy, the arrays must stay alive and unchanged until align_all has returned."""
         n = len(q_off) - 1 - first
         added = C.c_int64(0)
         p = lambda a, ty: a.ctypes.data_as(C.POINTER(ty))
         qf = p(np.ascontiguousarray(q_first[first:], dtype=np.int32), C.c_int32) if q_first is not None else None
         tb = p(np.ascontiguousarray(t_begin[first:], dtype=np.int32), C.c_int32) if t_begin is not None else None
-        st = self.lib.b200aln_batch_add_overlaps(self.h, C.c_int64(n), p(q, C.c_uint8), p(q_off[first:], C.c_int64),
-                                                 p(t, C.c_uint8), p(t_off[first:], C.c_int64), qf, tb, C.byref(added))
+        fn = self.lib.b200aln_batch_add_overlaps_view if view else self.lib.b200aln_batch_add_overlaps
+        st = fn(self.h, C.c_int64(n), p(q, C.c_uint8), p(q_off[first:], C.c_int64), p(t, C.c_uint8), p(t_off[first:], C.c_int64),
+                qf, tb, C.byref(added))
         if st != SUCCESS:
             raise RuntimeError(f"b200aln_batch_add_overlaps: {status_string(st)}")
         return int(added.value)
@@ -263,3 +266,28 @@ class AlignerPool:
         if st != SUCCESS:
             raise RuntimeError(f"b200aln_aligner_align: {status_string(st)}")
         return ed[:n], self._buf, off[:n], ln[:n], bi.as_dict()
+
+
+class pinned:
+    """Context manager: page-lock numpy arrays for the duration (b200aln_host_register / _unregister)."""
+
+    def __init__(self, *arrays):
+        self.arrays = [a for a in arrays if a.nbytes > 0]
+        self.done = []
+
+    def __enter__(self):
+        lib = _lib()
+        for a in self.arrays:
+            st = lib.b200aln_host_register(C.c_void_p(a.ctypes.data), C.c_int64(a.nbytes))
+            if st != SUCCESS:
+                self.__exit__(None, None, None)
+                raise RuntimeError(f"b200aln_host_register: {status_string(st)}")
+            self.done.append(a)
+        return self
+
+    def __exit__(self, *exc):
+        lib = _lib()
+        for a in self.done:
+            lib.b200aln_host_unregister(C.c_void_p(a.ctypes.data))
+        self.done = []
+        return False

@@ -361,6 +361,10 @@ struct b200aln_batch {
 
     /* host staging */
     PinnedBuf h_seq;
+    /* view mode (b200aln_batch_add_overlaps_view): the caller's columnar buffers are uploaded as they are */
+    const uint8_t* view_q = nullptr;
+    const uint8_t* view_t = nullptr;
+    int64_t view_q_bytes = 0, view_t_bytes = 0;
     std::vector<AlnJob> jobs;
     int64_t ops_bytes = 0;
     int64_t cap_open = 0, cap_leaves = 0; /* list capacities the staged alignments need */
@@ -590,7 +594,7 @@ int32_t b200aln_batch_add_overlap(b200aln_batch* b, const char* query, int32_t n
     if (!b || n < 0 || m < 0 || (n > 0 && !query) || (m > 0 && !target) || q_first < 0 || t_begin < 0)
         return B200ALN_INVALID_ARGUMENT;
     if ((int64_t)t_begin + m >= ((int64_t)1 << 31) || (int64_t)q_first + n >= ((int64_t)1 << 31)) return B200ALN_INVALID_ARGUMENT;
-    if (b->aligned) return B200ALN_GENERIC_ERROR; /* reset() first, like a cudaaligner batch after align_all */
+    if (b->aligned || b->view_q) return B200ALN_GENERIC_ERROR; /* reset() first, like a cudaaligner batch after align_all */
     if ((int64_t)n + m >= ((int64_t)1 << 30)) return B200ALN_EXCEEDED_MAX_LENGTH; /* run starts are 30-bit */
     const int64_t n_win = aln_window_count(t_begin, m, b->window_length);
     const int64_t vb = var_bytes_for(n, m) + 16 * n_win;
@@ -668,7 +672,8 @@ int32_t b200aln_batch_align_all(b200aln_batch* b) {
     const int64_t cap_leaves = std::max<int64_t>(b->cap_leaves, (int64_t)leaves0.size()) + 16;
     if (cap_open >= 0x7FFFFFFF || cap_leaves >= 0x7FFFFFFF) return B200ALN_EXCEEDED_MAX_ALIGNMENTS;
 
-    ALN_CU(b->d_seq.need(b->h_seq.used + 64));
+    const size_t seq_bytes = b->view_q ? (size_t)(b->view_q_bytes + b->view_t_bytes) : b->h_seq.used;
+    ALN_CU(b->d_seq.need(seq_bytes + 64));
     ALN_CU(b->d_jobs.need(sizeof(AlnJob) * (size_t)n_aln));
     ALN_CU(b->d_ops.need((size_t)b->ops_bytes + 64));
     ALN_CU(b->d_res.need(sizeof(AlnResult) * (size_t)n_aln));
@@ -691,7 +696,15 @@ int32_t b200aln_batch_align_all(b200aln_batch* b) {
     for (int c = 0; c < ALN_CLASSES; ++c) b->h_counters[CT_NOPEN + c] = (int32_t)first[c].size();
     b->h_counters[CT_NLEAVES] = (int32_t)leaves0.size();
     ALN_CU(cudaMemcpyAsync(ct, b->h_counters, sizeof(int32_t) * CT_WORDS, cudaMemcpyHostToDevice, s));
-    ALN_CU(cudaMemcpyAsync(b->d_seq.p, b->h_seq.p, b->h_seq.used, cudaMemcpyHostToDevice, s));
+    if (b->view_q) { /* straight from the caller's buffers (page-locked ones upload at full PCIe speed) */
+        if (b->view_q_bytes)
+            ALN_CU(cudaMemcpyAsync(b->d_seq.p, b->view_q, (size_t)b->view_q_bytes, cudaMemcpyHostToDevice, s));
+        if (b->view_t_bytes)
+            ALN_CU(cudaMemcpyAsync(static_cast<uint8_t*>(b->d_seq.p) + b->view_q_bytes, b->view_t, (size_t)b->view_t_bytes,
+                                   cudaMemcpyHostToDevice, s));
+    } else {
+        ALN_CU(cudaMemcpyAsync(b->d_seq.p, b->h_seq.p, b->h_seq.used, cudaMemcpyHostToDevice, s));
+    }
     ALN_CU(cudaMemcpyAsync(b->d_jobs.p, b->jobs.data(), sizeof(AlnJob) * (size_t)n_aln, cudaMemcpyHostToDevice, s));
     for (int c = 0; c < ALN_CLASSES; ++c)
         if (!first[c].empty())
@@ -702,7 +715,7 @@ int32_t b200aln_batch_align_all(b200aln_batch* b) {
     ALN_CU(cudaMemsetAsync(b->d_res.p, 0, sizeof(AlnResult) * (size_t)n_aln, s));
     /* the pageable vectors above (jobs, first, leaves0) must not be touched before the copies were issued from them:
      * cudaMemcpyAsync from pageable memory stages them before returning */
-    b->info.h2d_bytes = (int64_t)(b->h_seq.used + sizeof(AlnJob) * (size_t)n_aln + sizeof(AlnRect) * (first_total + leaves0.size()) +
+    b->info.h2d_bytes = (int64_t)(seq_bytes + sizeof(AlnJob) * (size_t)n_aln + sizeof(AlnRect) * (first_total + leaves0.size()) +
                                   sizeof(int32_t) * CT_WORDS);
 
     AlnKernelArgs a;
@@ -929,6 +942,78 @@ int32_t b200aln_batch_add_overlaps(b200aln_batch* b, int64_t n, const uint8_t* q
     return st;
 }
 
+int32_t b200aln_batch_add_overlaps_view(b200aln_batch* b, int64_t n, const uint8_t* q_bases, const int64_t* q_off,
+                                        const uint8_t* t_bases, const int64_t* t_off, const int32_t* q_first,
+                                        const int32_t* t_begin, int64_t* n_added) {
+    if (n_added) *n_added = 0;
+    if (!b || n < 0 || (n > 0 && (!q_bases || !q_off || !t_bases || !t_off))) return B200ALN_INVALID_ARGUMENT;
+    if (b->aligned || !b->jobs.empty()) return B200ALN_GENERIC_ERROR; /* an empty batch only: one view per fill */
+    if (n == 0) return B200ALN_SUCCESS;
+    int64_t k = 0;
+    int32_t st = B200ALN_SUCCESS;
+    for (; k < n; ++k) { /* the same admission as add_overlap, without the copy */
+        const int64_t nn = q_off[k + 1] - q_off[k], mm = t_off[k + 1] - t_off[k];
+        const int32_t qf = q_first ? q_first[k] : 0, tb = t_begin ? t_begin[k] : 0;
+        if (nn < 0 || mm < 0 || qf < 0 || tb < 0 || (int64_t)tb + mm >= ((int64_t)1 << 31) || (int64_t)qf + nn >= ((int64_t)1 << 31)) {
+            st = B200ALN_INVALID_ARGUMENT;
+            break;
+        }
+        if (nn + mm >= ((int64_t)1 << 30)) { st = B200ALN_EXCEEDED_MAX_LENGTH; break; }
+        const int32_t ni = (int32_t)nn, mi = (int32_t)mm;
+        const int64_t n_win = aln_window_count(tb, mi, b->window_length);
+        const int64_t vb = var_bytes_for(ni, mi) + 16 * n_win;
+        const int32_t new_max = std::max(b->max_len, std::max(ni, mi));
+        const int64_t min_slots = WARPS_PER_BLOCK * slot_bytes_for(round_len(new_max));
+        if (vb + min_slots > b->budget) { st = B200ALN_EXCEEDED_MAX_LENGTH; break; }
+        if (b->var_bytes + vb + min_slots > b->budget || b->jobs.size() >= (size_t)0x7FFFFF00) { st = B200ALN_EXCEEDED_MAX_ALIGNMENTS; break; }
+        AlnJob j;
+        j.q_off = q_off[k] - q_off[0];
+        j.t_off = t_off[k] - t_off[0]; /* + the query bytes, once their total is known */
+        j.ops_off = b->ops_bytes;
+        j.n = ni;
+        j.m = mi;
+        j.q_first = qf;
+        j.t_begin = tb;
+        b->n_windows += n_win;
+        b->ops_bytes += nn + mm;
+        b->cap_open += aln_open_capacity(ni, mi);
+        b->cap_leaves += aln_leaf_capacity(ni, mi);
+        b->var_bytes += vb;
+        b->max_len = new_max;
+        b->jobs.push_back(j);
+    }
+    if (k > 0) {
+        b->view_q = q_bases + q_off[0];
+        b->view_t = t_bases + t_off[0];
+        b->view_q_bytes = q_off[k] - q_off[0];
+        b->view_t_bytes = t_off[k] - t_off[0];
+        for (AlnJob& j : b->jobs) j.t_off += b->view_q_bytes;
+    }
+    if (n_added) *n_added = k;
+    if (st == B200ALN_EXCEEDED_MAX_ALIGNMENTS && k > 0) return B200ALN_SUCCESS;
+    return st;
+}
+
+int32_t b200aln_host_register(const void* p, int64_t bytes) {
+    if (!p || bytes <= 0) return B200ALN_INVALID_ARGUMENT;
+    if (cudaHostRegister(const_cast<void*>(p), (size_t)bytes, cudaHostRegisterPortable | cudaHostRegisterReadOnly) != cudaSuccess) {
+        cudaGetLastError();
+        if (cudaHostRegister(const_cast<void*>(p), (size_t)bytes, cudaHostRegisterPortable) != cudaSuccess) {
+            cudaGetLastError();
+            return B200ALN_CUDA_ERROR;
+        }
+    }
+    return B200ALN_SUCCESS;
+}
+int32_t b200aln_host_unregister(const void* p) {
+    if (!p) return B200ALN_INVALID_ARGUMENT;
+    if (cudaHostUnregister(const_cast<void*>(p)) != cudaSuccess) {
+        cudaGetLastError();
+        return B200ALN_CUDA_ERROR;
+    }
+    return B200ALN_SUCCESS;
+}
+
 /* the run starts of the last align_all, fetched on first use */
 static int32_t fetch_runs(const b200aln_batch* cb) {
     b200aln_batch* b = const_cast<b200aln_batch*>(cb);
@@ -1000,6 +1085,8 @@ int32_t b200aln_batch_reset(b200aln_batch* b) {
     cudaGetLastError();
     b->jobs.clear();
     b->h_seq.used = 0;
+    b->view_q = b->view_t = nullptr;
+    b->view_q_bytes = b->view_t_bytes = 0;
     b->ops_bytes = 0;
     b->n_windows = 0;
     b->h_bp.used = 0;
@@ -1166,7 +1253,7 @@ int32_t b200aln_aligner_align(b200aln_aligner* h, int64_t n, const uint8_t* q_ba
             int64_t pos = start;
             while (pos < end) {
                 int64_t added = 0;
-                int32_t st = b200aln_batch_add_alignments(b, end - pos, q_bases, q_off + pos, t_bases, t_off + pos, &added);
+                int32_t st = b200aln_batch_add_overlaps_view(b, end - pos, q_bases, q_off + pos, t_bases, t_off + pos, nullptr, nullptr, &added);
                 if (st == B200ALN_SUCCESS) st = b200aln_batch_align_all(b);
                 if (st == B200ALN_SUCCESS) st = b200aln_batch_sync(b);
                 const char* text = nullptr;

@@ -15,6 +15,7 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=24)
     ap.add_argument("--mem-gb", type=float, default=32)
+    ap.add_argument("--view", type=int, default=0, help="1: no staging copy, upload from the page-locked input arrays")
     a = ap.parse_args()
     from common import overlap_fixture
     from racon_gpu_b200.aligner import CUDABatchAligner, pack_pairs
@@ -23,6 +24,10 @@ def main():
     q, qo, t, to = pack_pairs(pairs)
     nominal = float(sum(len(x) * len(y) for x, y in pairs))
     out = {"pairs": len(pairs), "bases": int(qo[-1] + to[-1]), "matrix_cells": nominal}
+    if a.view:
+        from racon_gpu_b200.aligner import _lib
+        for arr in (q, t):
+            _lib().b200aln_host_register(arr.ctypes.data_as(__import__('ctypes').c_void_p), __import__('ctypes').c_int64(arr.nbytes))
     best = None
     al = CUDABatchAligner(device_id=0, max_gpu_memory=int(a.mem_gb * (1 << 30)))
     for it in range(a.iters + 1):
@@ -31,7 +36,7 @@ def main():
                          "levels": 0, "batches": 0}
         eds = []
         while first < len(pairs):  # host buffers in, CIGAR bytes out; as many batches as the memory budget asks for
-            first += al.add_overlaps(q, qo, t, to, first)
+            first += al.add_overlaps(q, qo, t, to, first, view=bool(a.view))
             al.align_all()
             text, off, ln, ed = al.cigars()
             info = al.info()

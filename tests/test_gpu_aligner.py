@@ -202,6 +202,15 @@ def test_full_batch_is_back_pressure_not_an_error(oracle):
     text, off, ln, ed2 = bulk.cigars()
     assert [(text[off[i]:off[i] + ln[i]], int(ed2[i])) for i in range(len(pairs))] == out
     bulk.close()
+    # the view form: no staging copy, upload straight from the caller's (here page-locked) buffers
+    from racon_gpu_b200.aligner import pinned
+    viewb = CUDABatchAligner(device_id=0, max_gpu_memory=1 << 30)
+    with pinned(q, t):
+        assert viewb.add_overlaps(q, qo, t, to, view=True) == len(pairs)
+        viewb.align_all()
+    text, off, ln, ed2 = viewb.cigars()
+    assert [(text[off[i]:off[i] + ln[i]], int(ed2[i])) for i in range(len(pairs))] == out
+    viewb.close()
     ed, cigars, coff, info = align_pairs(*pack_pairs(pairs), device_id=0, max_gpu_memory=2 << 30)
     for i, (q, t) in enumerate(pairs):
         ops, score = oracle_align(oracle, q, t)
