@@ -996,12 +996,9 @@ int32_t b200aln_batch_add_overlaps_view(b200aln_batch* b, int64_t n, const uint8
 
 int32_t b200aln_host_register(const void* p, int64_t bytes) {
     if (!p || bytes <= 0) return B200ALN_INVALID_ARGUMENT;
-    if (cudaHostRegister(const_cast<void*>(p), (size_t)bytes, cudaHostRegisterPortable | cudaHostRegisterReadOnly) != cudaSuccess) {
+    if (cudaHostRegister(const_cast<void*>(p), (size_t)bytes, cudaHostRegisterPortable) != cudaSuccess) {
         cudaGetLastError();
-        if (cudaHostRegister(const_cast<void*>(p), (size_t)bytes, cudaHostRegisterPortable) != cudaSuccess) {
-            cudaGetLastError();
-            return B200ALN_CUDA_ERROR;
-        }
+        return B200ALN_CUDA_ERROR;
     }
     return B200ALN_SUCCESS;
 }

@@ -258,3 +258,37 @@ def test_argument_and_state_errors(aligner):
     aligner.align_all()
     assert aligner.generate_cigar_strings() == [(b"4I", 4), (b"3D", 3), (b"8M", 0)]
     aligner.reset()
+
+
+def test_limits_and_call_order_are_statuses():
+    """Nothing crashes or falls back: a pair that can never fit the budget, calls in the wrong order and options set on
+    a non-empty batch all come back as status codes (cudaaligner.hpp:34-42 values where they exist)."""
+    from racon_gpu_b200 import aligner as A
+    al = A.CUDABatchAligner(device_id=0, max_gpu_memory=8 << 20)
+    lib, h = al.lib, al.h
+    big = b"A" * 3_000_000  # 6 M operations need 48 MB of arenas: more than this batch will ever have
+    assert lib.b200aln_batch_add_alignment(h, big, len(big), big, len(big)) == A.EXCEEDED_MAX_LENGTH
+    assert not al.has_overlaps()
+    assert al.add_overlap(b"ACGTACGTAC", b"ACGTTCGTAC")
+    assert lib.b200aln_batch_set_window_length(h, 500, 0) == A.GENERIC_ERROR      # not on a batch that holds overlaps
+    assert lib.b200aln_batch_get_breaking_points(h, None, None, None) == A.UNINITIALIZED
+    q = np.frombuffer(b"ACGT", dtype=np.uint8)
+    off = np.asarray([0, 4], dtype=np.int64)
+    with pytest.raises(RuntimeError):
+        al.add_overlaps(q, off, q, off, view=True)                                # a view needs an empty batch
+    al.align_all()
+    assert lib.b200aln_batch_add_alignment(h, b"AC", 2, b"AC", 2) == A.GENERIC_ERROR  # reset() first
+    assert al.generate_cigar_strings() == [(b"10M", 1)]
+    assert lib.b200aln_batch_get_breaking_points(h, None, None, None) == A.GENERIC_ERROR  # no window length was set
+    al.reset()
+    assert lib.b200aln_batch_set_window_length(h, 0, 1) == A.INVALID_ARGUMENT     # nothing would come back
+    assert lib.b200aln_batch_set_window_length(h, -5, 0) == A.INVALID_ARGUMENT
+    al.set_window_length(4)
+    assert lib.b200aln_batch_add_overlap(h, b"ACGTACGTAC", 10, b"ACGTTCGTAC", 10, 3, 6) == 0
+    al.align_all()
+    bp = al.breaking_points()[0]
+    # windows of the contig: [6,7] [8,11] [12,15]; every column is a match or mismatch
+    assert bp.tolist() == [[6, 3], [8, 5], [8, 5], [12, 9], [12, 9], [16, 13]]
+    al.close()
+    with pytest.raises(RuntimeError):
+        A.CUDABatchAligner(device_id=999)
