@@ -1,6 +1,6 @@
 /*
- * aln_core.cuh -- batched global (Needleman-Wunsch, unit cost) alignment of overlaps with path, one warp per
- * sub-problem, written against poa_simt.cuh (CUDA flavour = the product, lane emulation = tests/emu).
+ * aln_core.cuh -- batched global (Needleman-Wunsch, unit cost) alignment of overlaps with path, a warp or a team of
+ * warps per sub-problem, written against poa_simt.cuh (CUDA flavour = the product, lane emulation = tests/emu).
  *
  * Replaces, for racon's overlap alignment step (src/cuda/cudapolisher.cpp:74-214, src/cuda/cudaaligner.cpp:50-98), what
  * the reference runs in vendor/GenomeWorks/cudaaligner (Aligner::align_all: Myers / Hirschberg-Myers kernels) -- but
@@ -14,21 +14,26 @@
  *   - split: first query index r = 0..n-2 with L[r] + R[r+1] == optimum, else r = -1, else r = n-1 (:1282-1308).
  *
  * Design (not a port of either library):
- *   - the recursion is LEVEL-SYNCHRONOUS over the whole batch: the list of open sub-problems lives on the device, one
- *     launch of aln_split_kernel resolves every sub-problem of a level (one warp each: a forward and a backward bit-vector
- *     pass to the middle column, then the split rule) and appends its two children to the next level's list or to the
- *     leaf list (aln_push); the host only reads one counter per level.  ONE launch of aln_leaf_kernel then traces back
- *     all leaves of all levels, one of aln_runs_kernel turns every alignment's operations into run starts;
+ *   - the recursion is LEVEL-SYNCHRONOUS over the whole batch: the lists of open sub-problems live on the device, a
+ *     level's launches resolve every open sub-problem (a forward and a backward bit-vector pass to the middle column, then
+ *     the split rule) and file the two children by shape -- short / tall / huge, aln_shape -- into the next level's lists
+ *     or the leaf list (aln_push); the host only reads a counter per shape and level.  One warp per sub-problem where a
+ *     level fills the device that way; a TEAM of warps (forward and backward pass at once, stripes pipelined) per tall
+ *     sub-problem where the level is thin, and per huge one always.  ONE launch then traces back all leaves of all
+ *     levels, one more turns every alignment's operations into run starts, CIGAR text and (on request) racon's
+ *     breaking points;
  *   - bit-vector passes (Myers 1999 / Hyyro 2003 block recurrence, 64 rows per word) run as a WAVEFRONT across the
- *     warp: lane l owns block l of a 32-block stripe (2048 rows) and works on column (step - l); the horizontal delta
- *     of its last row and the column's target character travel to lane l + 1 in one packed shuffle per step.  Taller
- *     sub-problems take several stripes; the last lane's deltas spill to a per-warp byte row in between;
+ *     warp: lane l owns block l of a 32-block stripe (2048 rows) and works on column (step - l); the 2-bit horizontal
+ *     delta of its last row travels to lane l + 1 in one shuffle per step, the column's character code comes from a code
+ *     row, its match mask from the lane's shared-memory table; 16 steps to a group (immediates instead of bookkeeping).
+ *     Taller sub-problems take several stripes; the last lane's deltas go to the next stripe packed 16 columns to a word;
  *   - no band: every cell is exact, 64 cells per word operation, so the choice rules above need no band bookkeeping;
  *   - a leaf stores (Pv, Mv, bottom score) per block and column -- 20 bytes, the record edlib keeps, which is why the
  *     1 MB rule bounds a leaf's workspace -- in wavefront order (coalesced), and any cell's value is
- *     bottom - popc(Pv & below) + popc(Mv & below);
+ *     bottom - popc(Pv & below) + popc(Mv & below): the traceback rates the 32 cells of the diagonal in front of the walk
+ *     at once and emits whole runs of diagonal moves;
  *   - edit operations go to ops[r0 + c0 ...] of the alignment's (n + m)-byte region: sub-problems never overlap there,
- *     holes stay 0xFF and are dropped when the CIGAR is formed.
+ *     holes stay 0xFF and are dropped when the run starts are formed.
  */
 #pragma once
 #include "poa_simt.cuh"

@@ -6,10 +6,15 @@
  * path (edlib, src/overlap.cpp:205-224).  Runtime design:
  *   - per-RESIDENT-WARP workspaces ("slots": two distance columns, the stripe hand-over row, 1 MB of leaf records),
  *     reused by every sub-problem the warp takes from the level's list; persistent grids, one atomic cursor per launch;
- *   - the Hirschberg recursion is level-synchronous over the whole batch and its lists live on the device: per level one
- *     launch and one 4-byte read-back (how many sub-problems the next level has);
- *   - results leave the device compact: run starts (4 bytes per run of equal operations) bump-allocated into one arena,
- *     a 24-byte record per alignment -- not (n + m) bytes per alignment.
+ *   - per-resident-BLOCK team workspaces (hand-over rows, code rows, the two middle columns) for sub-problems that a team
+ *     of warps takes (aln_split_team_kernel);
+ *   - the Hirschberg recursion is level-synchronous over the whole batch and its lists live on the device: per level at
+ *     most one team launch and one one-warp launch (huge sub-problems of a saturated level: teams on a side stream) and
+ *     one 12-byte read-back (how many sub-problems of each shape the next level has);
+ *   - results leave the device compact: CIGAR text and / or breaking points formed on the device and bump-allocated into
+ *     arenas, a 48-byte record per alignment -- not (n + m) bytes per alignment; run starts only when somebody asks;
+ *   - uploads come from the batch's pinned staging copy or straight from the caller's page-locked columnar buffers (view);
+ *   - a pool (b200aln_aligner_*) runs several such batches per device on every device, one host thread each.
  * Nothing here falls back to a CPU aligner; a CUDA failure is a status, not a different code path.
  */
 #include <cuda_runtime.h>
