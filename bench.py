@@ -423,6 +423,42 @@ def measure_aligner(args, local_rank, rep=32, steps=3, warmup=2, cpu_seconds=6.0
                                              f"edlibAlign(NW, path) + edlibAlignmentToCigar as src/overlap.cpp:205-224"}
     except Exception as e:  # the product's numbers do not depend on the checker
         out["cpu_baseline"] = {"unavailable": str(e)}
+    try:  # long reads (what current ONT / HiFi overlaps look like): 40 kb pairs at 10 % edits, seeded
+        from common import random_pairs
+        base = random_pairs(4242, [(40000, 0.10)] * 24)
+        lp = base * 20
+        q2, qo2, t2, to2 = pack_pairs(lp)
+        pool = AlignerPool(devices=(local_rank,), batches_per_device=3, max_gpu_memory_per_batch=20 << 30)
+        walls = []
+        with pinned(q2, t2):
+            for it in range(2 + steps):  # the first rounds also teach every batch its band guess (verified on the device)
+                t0 = time.perf_counter()
+                ed2, buf2, off2, ln2, pinfo2 = pool.align(q2, qo2, t2, to2)
+                if it >= 2:
+                    walls.append(time.perf_counter() - t0)
+        pool.close()
+        lr = {"workload": f"synthetic long reads: {len(lp)} pairs of 40 kb, 10 % edits ({len(base)} distinct, seeded), "
+                          f"{float(sum(len(a) * len(b) for a, b in lp)):.3g} matrix cells",
+              "e2e": len(lp) / (sum(walls) / len(walls)), "unit": "overlaps/s", "e2e_ms_per_step": 1e3 * sum(walls) / len(walls),
+              "cells_computed_per_step": pinfo2["cells"], "gpu_launches_per_step": pinfo2["kernel_launches"]}
+        from oracle_lib import Ref, ref_align
+        r = Ref()
+        if r.available and not args.no_cpu_baseline:
+            threads, core_info = usable_cores()
+            ref_scores = [ref_align(r, a, b)[1] for a, b in base[:4]]
+            if [int(x) for x in ed2[:4]] != ref_scores:
+                raise RuntimeError("aligner (long reads): edit distances differ from edlib's")
+            t0, done = time.perf_counter(), 0
+            with ThreadPoolExecutor(threads) as ex:
+                while time.perf_counter() - t0 < cpu_seconds / 2:
+                    list(ex.map(lambda p: ref_align(r, p[0], p[1])[1], base * 4))
+                    done += 4 * len(base)
+            dt = time.perf_counter() - t0
+            lr["cpu_baseline"] = {"value": done / dt, "unit": "overlaps/s", "cores": threads, "kind": "reference",
+                                  "sample": f"{done} alignments of the same pairs, {dt:.1f} s, edlib as above"}
+        out["long_reads"] = lr
+    except Exception as e:
+        out["long_reads"] = {"error": f"{type(e).__name__}: {e}"}
     return out
 
 

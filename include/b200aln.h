@@ -57,6 +57,14 @@ int32_t b200aln_init(void);
 int32_t b200aln_batch_create(int32_t device_id, void* stream, int64_t max_gpu_mem, int32_t max_bandwidth,
                              b200aln_batch** out);
 
+/* How a batch bands the TOP level of its alignments.  Sub-problems below the top know their optimum exactly and run in a
+ * band of that width; the top one's is unknown, so the host guesses `permille` edits per 1000 characters of the longer
+ * sequence and the kernels verify (an alignment whose distance exceeds the guess is redone without a band: results never
+ * depend on the guess, only speed does).  -1 (default): learnt from the batch's previous align_all (1.25 x the rate 90 % of
+ * its alignments stayed under; a fresh batch does not guess); 0: never; > 0: that rate.  max_bandwidth of create_aligner
+ * is NOT this: cudaaligner's band silently yields sub-optimal alignments, this one cannot. */
+int32_t b200aln_batch_set_band_guess(b200aln_batch* b, int32_t permille);
+
 /* Aligner::add_alignment(query, query_length, target, target_length) (aligner.hpp:73-74).  The bytes are copied.
  * NOTE the argument order is edlib's (query = the read segment, target = the contig segment, src/overlap.cpp:205-209);
  * racon's adapter swaps them for cudaaligner (cudaaligner.cpp:60-63) -- the C++ shim keeps that call site intact by
@@ -147,7 +155,7 @@ typedef struct b200aln_batch_info {
     int32_t n_team_blocks;    /* resident team blocks = team workspaces                        */
     int64_t n_open;           /* sub-problems split in the last align_all                     */
     int64_t n_leaves;         /* sub-problems traced back directly                            */
-    int64_t cells;            /* distance-matrix cells computed (splits + leaves)             */
+    int64_t cells;            /* distance-matrix cells actually computed (splits + leaves, inside their bands) */
     int64_t h2d_bytes, d2h_bytes;
     float kernel_ms;          /* device time of the last align_all's launches (CUDA events)   */
 } b200aln_batch_info;

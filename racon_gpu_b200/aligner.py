@@ -21,7 +21,7 @@ ALN_ABI_SYMBOLS = (
     "b200aln_aligner_create", "b200aln_aligner_num_batches", "b200aln_aligner_align", "b200aln_aligner_destroy",
     "b200aln_batch_set_window_length", "b200aln_batch_add_overlap", "b200aln_batch_add_overlaps",
     "b200aln_batch_get_breaking_points", "b200aln_batch_add_overlaps_view", "b200aln_host_register",
-    "b200aln_host_unregister",
+    "b200aln_host_unregister", "b200aln_batch_set_band_guess",
 )
 
 SUCCESS, UNINITIALIZED, EXCEEDED_MAX_ALIGNMENTS, EXCEEDED_MAX_LENGTH = 0, 1, 2, 3
@@ -102,6 +102,12 @@ class CUDABatchAligner:
         if st != SUCCESS:
             raise RuntimeError(f"b200aln_batch_add_overlaps: {status_string(st)}")
         return int(added.value)
+
+    def set_band_guess(self, permille: int):
+        """-1: learn the top level's band from the previous align_all (default); 0: never band the top level; > 0: fixed."""
+        st = self.lib.b200aln_batch_set_band_guess(self.h, C.c_int32(permille))
+        if st != SUCCESS:
+            raise RuntimeError(f"b200aln_batch_set_band_guess: {status_string(st)}")
 
     def set_window_length(self, window_length: int, skip_cigars: bool = False):
         """Form breaking points on the device (Overlap::find_breaking_points_from_cigar, src/overlap.cpp:226-290)."""

@@ -80,8 +80,11 @@ ALN_HD int aln_shape(int32_t n, int32_t m) {
 struct AlnRect {
     int32_t aln;
     int32_t r0, n, c0, m;
-    int32_t top; /* 1: the whole alignment (its optimum is reported as the edit distance) */
+    int32_t top;  /* bit 0: the whole alignment (its optimum is reported as the edit distance); bit 1: `best` is a guess */
+    int32_t best; /* the sub-problem's optimum (children of a split know theirs exactly), a guess to be verified, or -1 */
 };
+enum { ALN_TOP = 1, ALN_GUESS = 2 };
+constexpr int32_t ALN_INF = 1 << 28; /* a distance no path has */
 struct AlnSplit { /* result of one Hirschberg step */
     int32_t r;      /* split query index relative to the rect, -1 .. n-1; -2: inconsistent */
     int32_t ls, rs; /* optima of the upper-left and lower-right sub-problems */
@@ -106,7 +109,9 @@ struct alignas(16) RecPM {
 
 /* per resident warp workspace */
 struct AlnSlot {
-    uint32_t* hbuf; /* [hrow words]     horizontal deltas of the row between two stripes, 2 bits a column (1 = +1, 2 = -1) */
+    uint32_t* hbuf; /* [hrow words]     horizontal deltas of the row between two stripes, 2 bits a column (1 = +1, 2 = -1);
+                       the row's last word is the anchor (the value under the stripe at the next strip's first column) */
+    int32_t hrow_words;
     uint8_t* tcode; /* [max_len + 192]  the pass's target as codes 0..3 = ACGT, 4 = other; 64 bytes of padding in front */
     int32_t* Lc;    /* [max_len + 2]    last column of the forward pass:  Lc[i] = D(q[0..i), left half)              */
     int32_t* Rr;    /* [max_len + 2]    last column of the backward pass: Rr[i] = D(q[n-i..n), right half)          */
@@ -126,6 +131,7 @@ ALN_HD void aln_slot_bind(AlnSlot& s, uint8_t* base, int32_t max_len, size_t* to
         o += sizeof(type) * (size_t)(count);                           \
     } while (0)
     ALN_CARVE(hbuf, uint32_t, (size_t)aln_hrow_words(max_len));
+    s.hrow_words = (int32_t)aln_hrow_words(max_len);
     ALN_CARVE(tcode, uint8_t, (size_t)max_len + 192);
     ALN_CARVE(Lc, int32_t, (size_t)max_len + 2);
     ALN_CARVE(Rr, int32_t, (size_t)max_len + 2);
@@ -184,13 +190,17 @@ POA_FN void aln_push(const AlnLists& L, const AlnRect r) {
     else *L.overflow = 1;
 }
 /* upper-left and lower-right sub-problems of `r` split at query index sr (relative, -1 .. n-1), edlib.cpp:1321-1333 */
-POA_FN bool aln_children(const AlnRect r, int32_t sr, AlnRect& ul, AlnRect& lr) {
+POA_FN bool aln_children(const AlnRect r, const AlnSplit sp, AlnRect& ul, AlnRect& lr) {
+    const int32_t sr = sp.r;
     if (sr < -1 || sr > r.n - 1) return false;
     const int32_t lh = r.m / 2, uh = sr + 1;
-    ul = AlnRect{r.aln, r.r0, uh, r.c0, lh, 0};
-    lr = AlnRect{r.aln, r.r0 + uh, r.n - uh, r.c0 + lh, r.m - lh, 0};
+    ul = AlnRect{r.aln, r.r0, uh, r.c0, lh, 0, sp.ls}; /* the children's optima are the two terms of the parent's */
+    lr = AlnRect{r.aln, r.r0 + uh, r.n - uh, r.c0 + lh, r.m - lh, 0, sp.rs};
     return true;
 }
+/* The band a pass may confine itself to when nothing above `best` matters: cells with |i - j| <= best hold every value
+ * <= best exactly (Ukkonen); two more diagonals so that the traceback's neighbours of path cells are computed cells. */
+POA_FN int32_t aln_band_of(int32_t best) { return best < 0 ? -1 : best + 2; }
 
 /* a sequence read forwards (step +1) or backwards (step -1): element k = p[k * step] */
 struct SeqView {
@@ -333,6 +343,7 @@ POA_FN uint64_t eq_other(const SeqView q, int32_t row0, int32_t cnt, int tc) {
  * One bit-vector pass: the distance matrix of q[0..n) against t[0..cols), boundary D[i][0] = i, D[0][j] = j.
  *   out_col (nullable): receives the last column, out_col[i] = D[i][cols], i = 0..n
  *   PM / S  (nullable): receive the record of every (block, column), leaf_entry() order
+ * Returns the number of matrix cells this warp computed (its stripes' rows x the columns they ran).
  * Myers' block recurrence in Hyyro's formulation (64 rows per word): with Pv/Mv the +1/-1 vertical deltas of the previous
  * column, Eq the rows whose character equals the column's and hin the horizontal delta entering from above,
  *   Xv = Eq | Mv;  Eq |= (hin < 0);  Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;  Ph = Mv | ~(Xh | Pv);  Mh = Pv & Xh;
@@ -342,13 +353,22 @@ POA_FN uint64_t eq_other(const SeqView q, int32_t row0, int32_t cnt, int tc) {
  * (1 = +1, 2 = -1) of the block's last row, one shuffle per step -- the only thing on the step's dependency chain.
  * The column's character code comes straight from the slot's code row (loaded one step ahead), its match mask from the
  * lane's shared-memory table.
+ * Band (band >= 0: the caller only needs values <= band - 2 to be exact, and anything larger to stay larger): a cell
+ * (i, j) with D <= band has |i - j| <= band, so the stripe of rows (R0, R1] only runs the columns R0 - band .. R1 + band - 1
+ * -- for a Hirschberg half that is a diagonal strip instead of the whole rectangle.  What it does not compute it
+ * OVERESTIMATES: it starts at its first column with all vertical deltas + 1 under the value the stripe above had there
+ * (the "anchor", handed over with the deltas), takes + 1 for every entering delta beyond the stripe above's last column,
+ * and reports ALN_INF for rows whose strip ends before the last column.  Overestimates never win a minimum against the
+ * exact values of the cells a path of cost <= band - 2 runs through, all of which are computed (edlib's own band rests on
+ * the same argument, edlib.cpp:540-760).
  */
 template <bool TEAM>
-POA_FN_NOINLINE void myers_pass(const SeqView q, int32_t n, const SeqView t, int32_t cols, const TeamCtx team_in, uint32_t* hbuf,
-                                int32_t hrow_words, uint8_t* tcode_base, const EqTab eq_in, int32_t* out_col, RecPM* PM,
-                                int32_t* S) {
+POA_FN_NOINLINE int64_t myers_pass(const SeqView q, int32_t n, const SeqView t, int32_t cols, int32_t band, const TeamCtx team_in,
+                                uint32_t* hbuf, int32_t hrow_words, uint8_t* tcode_base, const EqTab eq_in, int32_t* out_col,
+                                RecPM* PM, int32_t* S) {
     n = poa_uniform(n);
     cols = poa_uniform(cols);
+    band = poa_uniform(band);
     EqTab eq = eq_in; /* by value: a reference would live in local memory and be re-read every step */
     const TeamCtx team = TEAM ? team_in : TeamCtx{0, 1, 0, 0}; /* TEAM = false: the team code folds away */
     const int32_t B = (n + 63) / 64;
@@ -376,6 +396,7 @@ POA_FN_NOINLINE void myers_pass(const SeqView q, int32_t n, const SeqView t, int
     POA_FENCE();
     if (TEAM) team_barrier(team);
     const int32_t n_stripes = (B + 31) / 32;
+    int64_t cells_done = 0;
     for (int32_t sidx = team.w; sidx < n_stripes; sidx += team.n) {
         const int32_t s0 = 32 * sidx;
         const int32_t nb = B - s0 < 32 ? B - s0 : 32;
@@ -384,11 +405,32 @@ POA_FN_NOINLINE void myers_pass(const SeqView q, int32_t n, const SeqView t, int
         const bool piped = TEAM && lower && team.n > 1;
         const uint32_t* row_in = hbuf + (int64_t)((sidx + team.n - 1) % team.n) * hrow_words;
         uint32_t* row_out = hbuf + (int64_t)(sidx % team.n) * hrow_words;
+        /* the columns this stripe runs, the last one the stripe above ran, the first one the stripe below will run */
+        const int32_t R0 = 64 * s0, R1 = 64 * (s0 + nb) < n ? 64 * (s0 + nb) : n;
+        const int32_t c_lo = band < 0 || R0 - band < 0 ? 0 : R0 - band;
+        const int32_t c_hi = band < 0 || R1 + band - 1 > cols - 1 ? cols - 1 : R1 + band - 1;
+        const int32_t p_hi = band < 0 || R0 + band - 1 > cols - 1 ? cols - 1 : R0 + band - 1;
+        const int32_t a_col = (band < 0 || R1 - band <= 0) ? -1 : R1 - band - 1; /* the anchor column for the stripe below */
+        if (c_lo > c_hi) { /* the strip has left the matrix: no row from here on reaches the last column */
+            if (out_col) {
+                for (int32_t r = R0 + 1; r <= R1; r += 32) {
+                    POA_LANES(l) {
+                        if (r + l <= R1) out_col[r + l] = ALN_INF;
+                    }
+                }
+            }
+            continue;
+        }
+        cells_done += (int64_t)(R1 - R0) * (c_hi - c_lo + 1);
+        const int32_t step_first = c_lo & ~15;
+        const int32_t w_last_in = p_hi >> 4; /* words of the row above this index were never written: every delta + 1 */
         uint32_t hword = 0x55555555u, hword_next = 0x55555555u; /* stripe 0: D[0][j] = j, every delta + 1 */
-        if (piped) team_wait(team, sidx - 1, cols < 32 ? cols : 32);
+        int32_t base_top = lower ? R0 : 0; /* D[R0][c_lo]: the left border's R0 when the strip starts at column 0 */
+        if (piped) team_wait(team, sidx - 1, step_first + 32 < p_hi + 1 ? step_first + 32 : p_hi + 1);
         if (lower) {
-            hword = hrow_load(row_in);
-            hword_next = hrow_load(row_in + 1);
+            if ((step_first >> 4) <= w_last_in) hword = hrow_load(row_in + (step_first >> 4));
+            if ((step_first >> 4) + 1 <= w_last_in) hword_next = hrow_load(row_in + (step_first >> 4) + 1);
+            if (c_lo > 0) base_top = (int32_t)hrow_load(row_in + (hrow_words - 1));
         }
         PerLane<uint64_t> Pv, Mv;
         PerLane<int> bot, link, tc_next, hacc;
@@ -414,13 +456,13 @@ POA_FN_NOINLINE void myers_pass(const SeqView q, int32_t n, const SeqView t, int
             eq_store(eq, 4, l, 0);
             Pv[l] = ~(uint64_t)0;
             Mv[l] = 0;
-            bot[l] = 64 * (b + 1);
+            bot[l] = base_top + 64 * (l + 1); /* all vertical deltas + 1 under the stripe's top at its first column */
             link[l] = 0;
-            tc_next[l] = glb_u8(tcode - l);
+            tc_next[l] = glb_u8(tcode + (step_first - l));
             hacc[l] = 0;
         }
         POA_SYNC();
-        const int32_t steps = cols + nb - 1;
+        const int32_t steps = c_hi + nb; /* the last lane's last column is step c_hi + nb - 1 */
         /* One step of the wavefront.  OTHER = 0 leaves out the cold path for characters that are none of ACGT (a pass
          * whose target holds none -- the rule -- runs the unrolled loop below without carrying that code 16 times). */
 #define ALN_STEP(OTHER)                                                                                                  \
@@ -433,7 +475,7 @@ POA_FN_NOINLINE void myers_pass(const SeqView q, int32_t n, const SeqView t, int
             const int code = tc_next[l];                                                                                 \
             const int hcode = l == 0 ? h0 : in[l];                                                                       \
             tc_next[l] = glb_u8(tcode + (c + 1)); /* next step's column, a step ahead of its use */                      \
-            if (l < nb && (uint32_t)c < (uint32_t)cols) { /* lane l works on column c */                                 \
+            if (l < nb && (uint32_t)(c - c_lo) <= (uint32_t)(c_hi - c_lo)) { /* lane l works on column c */                 \
                 uint64_t Eq;                                                                                             \
                 if (!(OTHER) || code < 4) Eq = eq_load(eq, code, l);                                                     \
                 else Eq = eq_other(q, 64 * (s0 + l), n - 64 * (s0 + l) < 64 ? n - 64 * (s0 + l) : 64, (int)seq_at(t, c)); \
@@ -460,10 +502,13 @@ POA_FN_NOINLINE void myers_pass(const SeqView q, int32_t n, const SeqView t, int
                 }                                                                                                        \
                 if (more && l == 31) { /* 16 columns to a word; this row's reader is at least 16 columns behind */       \
                     hacc[l] |= out << ((c & 15) * 2);                                                                    \
-                    if ((c & 15) == 15 || c == cols - 1) {                                                               \
+                    if (c == a_col) row_out[hrow_words - 1] = (uint32_t)bot[l]; /* the anchor of the stripe below */     \
+                    if ((c & 15) == 15 || c == c_hi) {                                                                   \
+                        /* beyond the strip's last column every delta counts + 1 */                                      \
+                        if (c == c_hi && (c & 15) != 15) hacc[l] |= (int)(0x55555555u << (((c & 15) + 1) * 2));          \
                         row_out[c >> 4] = (uint32_t)hacc[l];                                                             \
                         hacc[l] = 0;                                                                                     \
-                        if (TEAM && team.n > 1 && ((c & 31) == 31 || c == cols - 1)) team_publish(team, sidx, c + 1);    \
+                        if (TEAM && team.n > 1 && ((c & 31) == 31 || c == c_hi)) team_publish(team, sidx, c + 1);        \
                     }                                                                                                    \
                 }                                                                                                        \
                 link[l] = out;                                                                                           \
@@ -473,11 +518,14 @@ POA_FN_NOINLINE void myers_pass(const SeqView q, int32_t n, const SeqView t, int
         /* ALN_STEP_UNROLL steps to a group (a divisor of 16): inside a group the entering delta's bit position and the
          * code row's offsets are immediates and the once-in-16-steps bookkeeping costs nothing; the steps a group runs
          * past `steps` find every lane's column out of range */
-        for (int32_t step0 = 0; step0 < steps; step0 += ALN_STEP_UNROLL) {
-            if ((step0 & 15) == 0 && step0 > 0) { /* the next 16 entering deltas; their successor word a word ahead */
+        for (int32_t step0 = step_first; step0 < steps; step0 += ALN_STEP_UNROLL) {
+            if ((step0 & 15) == 0 && step0 > step_first) { /* the next 16 entering deltas; their successor word a word ahead */
                 hword = hword_next;
-                if (piped) team_wait(team, sidx - 1, cols < step0 + 32 ? cols : step0 + 32);
-                if (lower) hword_next = hrow_load(row_in + (step0 >> 4) + 1);
+                hword_next = 0x55555555u;
+                if (lower && (step0 >> 4) + 1 <= w_last_in) {
+                    if (piped) team_wait(team, sidx - 1, p_hi + 1 < step0 + 32 ? p_hi + 1 : step0 + 32);
+                    hword_next = hrow_load(row_in + (step0 >> 4) + 1);
+                }
             }
             if (!has_other) {
 #pragma unroll
@@ -493,7 +541,13 @@ POA_FN_NOINLINE void myers_pass(const SeqView q, int32_t n, const SeqView t, int
             }
         }
 #undef ALN_STEP
-        if (out_col) { /* the last column, row by row: D = (score above the block) + running sum of the vertical deltas */
+        if (out_col && c_hi < cols - 1) { /* the strip ends before the last column: nothing cheap enough ends in these rows */
+            for (int32_t r = R0 + 1; r <= R1; r += 32) {
+                POA_LANES(l) {
+                    if (r + l <= R1) out_col[r + l] = ALN_INF;
+                }
+            }
+        } else if (out_col) { /* the last column, row by row: D = (score above the block) + running sum of the vertical deltas */
             POA_LANES(l) {
                 if (l < nb) {
                     const int32_t row0 = 64 * (s0 + l);
@@ -510,6 +564,7 @@ POA_FN_NOINLINE void myers_pass(const SeqView q, int32_t n, const SeqView t, int
         POA_SYNC();
         POA_FENCE(); /* hbuf / out_col written by one lane are read by others next; the Eq table is rebuilt */
     }
+    return cells_done;
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -569,16 +624,18 @@ POA_FN_NOINLINE void aln_split_rule(const int32_t* Lc, const int32_t* Rr, int32_
     POA_SYNC();
 }
 
-POA_FN_NOINLINE void aln_split(const AlnSlot& s_ref, EqTab& eq, const uint8_t* q, const uint8_t* t, int32_t n, int32_t m,
-                               AlnSplit* out) {
+POA_FN_NOINLINE int64_t aln_split(const AlnSlot& s_ref, EqTab& eq, const uint8_t* q, const uint8_t* t, int32_t n, int32_t m,
+                                  int32_t band, AlnSplit* out) {
     const AlnSlot s = s_ref;
     n = poa_uniform(n);
     m = poa_uniform(m);
     const int32_t lh = m / 2, rh = m - lh;
-    myers_pass<false>(SeqView{q, 1}, n, SeqView{t, 1}, lh, TeamCtx{0, 1, 0, 0}, s.hbuf, 0, s.tcode, eq, s.Lc, nullptr, nullptr);
-    myers_pass<false>(SeqView{q + (n - 1), -1}, n, SeqView{t + (m - 1), -1}, rh, TeamCtx{0, 1, 0, 0}, s.hbuf, 0, s.tcode, eq, s.Rr, nullptr,
-               nullptr);
+    int64_t cells = myers_pass<false>(SeqView{q, 1}, n, SeqView{t, 1}, lh, band, TeamCtx{0, 1, 0, 0}, s.hbuf, s.hrow_words, s.tcode, eq,
+                                      s.Lc, nullptr, nullptr);
+    cells += myers_pass<false>(SeqView{q + (n - 1), -1}, n, SeqView{t + (m - 1), -1}, rh, band, TeamCtx{0, 1, 0, 0}, s.hbuf,
+                               s.hrow_words, s.tcode, eq, s.Rr, nullptr, nullptr);
     aln_split_rule(s.Lc, s.Rr, n, m, out);
+    return cells;
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -640,8 +697,8 @@ POA_FN void leaf_window_load(const AlnSlot& s, LeafWindow& w, int32_t b, int32_t
  * left moves take a round each.  A new window of records is loaded every 25 columns or when the walk enters the block
  * above.
  */
-POA_FN_NOINLINE void aln_leaf(const AlnSlot& s_ref, EqTab& eq, const uint8_t* q, const uint8_t* t, int32_t n, int32_t m,
-                              uint8_t* ops, int32_t* score_out) {
+POA_FN_NOINLINE int64_t aln_leaf(const AlnSlot& s_ref, EqTab& eq, const uint8_t* q, const uint8_t* t, int32_t n, int32_t m,
+                                 int32_t band, uint8_t* ops, int32_t* score_out) {
     const AlnSlot s = s_ref;
     n = poa_uniform(n);
     m = poa_uniform(m);
@@ -657,9 +714,10 @@ POA_FN_NOINLINE void aln_leaf(const AlnSlot& s_ref, EqTab& eq, const uint8_t* q,
             POA_LANE0 { *score_out = len; }
         }
         POA_SYNC();
-        return;
+        return 0;
     }
-    myers_pass<false>(SeqView{q, 1}, n, SeqView{t, 1}, m, TeamCtx{0, 1, 0, 0}, s.hbuf, 0, s.tcode, eq, nullptr, s.PM, s.S);
+    const int64_t cells = myers_pass<false>(SeqView{q, 1}, n, SeqView{t, 1}, m, band, TeamCtx{0, 1, 0, 0}, s.hbuf, s.hrow_words, s.tcode,
+                                            eq, nullptr, s.PM, s.S);
     const int32_t B = (n + 63) / 64;
     LeafWindow win;
     int32_t i = n - 1, j = m - 1;
@@ -730,6 +788,7 @@ POA_FN_NOINLINE void aln_leaf(const AlnSlot& s_ref, EqTab& eq, const uint8_t* q,
         }
     }
     POA_SYNC();
+    return cells;
 }
 
 /* ------------------------------------------------------------------------------------------

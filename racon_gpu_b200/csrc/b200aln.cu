@@ -123,17 +123,21 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, ALN_MIN_BLOCKS) aln_spli
         const AlnRect r = work_item(work, k);
         const AlnJob job = a.jobs[r.aln];
         AlnSplit sp;
-        aln_split(s, eq, a.seq + job.q_off + r.r0, a.seq + job.t_off + r.c0, r.n, r.m, &sp);
+        int64_t cells = aln_split(s, eq, a.seq + job.q_off + r.r0, a.seq + job.t_off + r.c0, r.n, r.m, aln_band_of(r.best), &sp);
+        if (r.top & ALN_GUESS) { /* the host's guess was too small? then nothing of that pass can be trusted: no band */
+            const int32_t found = __shfl_sync(0xffffffffu, sp.best, 0);
+            if (found > r.best) cells += aln_split(s, eq, a.seq + job.q_off + r.r0, a.seq + job.t_off + r.c0, r.n, r.m, -1, &sp);
+        }
         if ((threadIdx.x & 31u) == 0u) {
-            if (r.top) a.res[r.aln].score = sp.best;
+            if (r.top & ALN_TOP) a.res[r.aln].score = sp.best;
             AlnRect ul, lr;
-            if (aln_children(r, sp.r, ul, lr)) {
+            if (aln_children(r, sp, ul, lr)) {
                 aln_push(next, ul);
                 aln_push(next, lr);
             } else {
                 a.res[r.aln].status = B200ALN_GENERIC_ERROR;
             }
-            atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + CT_CELLS), (unsigned long long)r.n * (unsigned long long)r.m);
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + CT_CELLS), (unsigned long long)cells);
         }
         __syncwarp();
     }
@@ -174,7 +178,7 @@ __global__ void __launch_bounds__(64 * ALN_TEAM, 1024 / (64 * ALN_TEAM)) aln_spl
                                                                                                   const AlnLists next, int32_t* cursor) {
     __shared__ uint64_t eq_tab[2 * ALN_TEAM * ALN_EQ_WORDS];
     __shared__ unsigned long long prog[2 * ALN_TEAM];
-    __shared__ int32_t s_k;
+    __shared__ int32_t s_k, s_redo;
     TeamSlot ts;
     team_slot_bind(ts, a.team_slab + (size_t)blockIdx.x * a.team_slot_bytes, a.max_len, nullptr);
     const int warp = (int)(threadIdx.x >> 5), side = warp / ALN_TEAM; /* side 0: forward pass, side 1: backward pass */
@@ -196,26 +200,36 @@ __global__ void __launch_bounds__(64 * ALN_TEAM, 1024 / (64 * ALN_TEAM)) aln_spl
         const uint8_t* q = a.seq + job.q_off + r.r0;
         const uint8_t* t = a.seq + job.t_off + r.c0;
         const int32_t lh = r.m / 2, rh = r.m - lh; /* edlib.cpp:1216-1217 */
-        if (side == 0)
-            myers_pass<true>(SeqView{q, 1}, r.n, SeqView{t, 1}, lh, team, ts.hrow[0], hrow_words, ts.tcode[0], eq, ts.Lc, nullptr, nullptr);
-        else
-            myers_pass<true>(SeqView{q + (r.n - 1), -1}, r.n, SeqView{t + (r.m - 1), -1}, rh, team, ts.hrow[1], hrow_words, ts.tcode[1],
-                       eq, ts.Rr, nullptr, nullptr);
-        __threadfence_block();
-        __syncthreads(); /* both middle columns are complete */
-        if (warp == 0) {
-            AlnSplit sp;
-            aln_split_rule(ts.Lc, ts.Rr, r.n, r.m, &sp);
-            if ((threadIdx.x & 31u) == 0u) {
-                if (r.top) a.res[r.aln].score = sp.best;
-                AlnRect ul, lr;
-                if (aln_children(r, sp.r, ul, lr)) {
-                    aln_push(next, ul);
-                    aln_push(next, lr);
-                } else {
-                    a.res[r.aln].status = B200ALN_GENERIC_ERROR;
-                }
-                atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + CT_CELLS), (unsigned long long)r.n * (unsigned long long)r.m);
+        AlnSplit sp;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            /* banded first when the sub-problem's optimum is known or guessed; a guess that proves too small: once more, whole */
+            const int32_t band = attempt == 0 ? aln_band_of(r.best) : -1;
+            int64_t cells;
+            if (side == 0)
+                cells = myers_pass<true>(SeqView{q, 1}, r.n, SeqView{t, 1}, lh, band, team, ts.hrow[0], hrow_words, ts.tcode[0], eq, ts.Lc,
+                                         nullptr, nullptr);
+            else
+                cells = myers_pass<true>(SeqView{q + (r.n - 1), -1}, r.n, SeqView{t + (r.m - 1), -1}, rh, band, team, ts.hrow[1],
+                                         hrow_words, ts.tcode[1], eq, ts.Rr, nullptr, nullptr);
+            if ((threadIdx.x & 31u) == 0u && cells)
+                atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + CT_CELLS), (unsigned long long)cells);
+            __threadfence_block();
+            __syncthreads(); /* both middle columns are complete */
+            if (warp == 0) {
+                aln_split_rule(ts.Lc, ts.Rr, r.n, r.m, &sp);
+                if ((threadIdx.x & 31u) == 0u) s_redo = (attempt == 0 && (r.top & ALN_GUESS) && sp.best > r.best) ? 1 : 0;
+            }
+            __syncthreads();
+            if (!s_redo) break;
+        }
+        if (warp == 0 && (threadIdx.x & 31u) == 0u) {
+            if (r.top & ALN_TOP) a.res[r.aln].score = sp.best;
+            AlnRect ul, lr;
+            if (aln_children(r, sp, ul, lr)) {
+                aln_push(next, ul);
+                aln_push(next, lr);
+            } else {
+                a.res[r.aln].status = B200ALN_GENERIC_ERROR;
             }
         }
         __syncthreads(); /* the columns and s_k are free again */
@@ -235,10 +249,11 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, ALN_MIN_BLOCKS) aln_leaf
         if (k >= n_leaves) break;
         const AlnRect r = leaves[k];
         const AlnJob job = a.jobs[r.aln];
-        aln_leaf(s, eq, a.seq + job.q_off + r.r0, a.seq + job.t_off + r.c0, r.n, r.m, a.ops + job.ops_off + r.r0 + r.c0,
-                 r.top ? &a.res[r.aln].score : nullptr);
+        const int64_t cells = aln_leaf(s, eq, a.seq + job.q_off + r.r0, a.seq + job.t_off + r.c0, r.n, r.m,
+                                       (r.top & ALN_GUESS) ? -1 : aln_band_of(r.best), a.ops + job.ops_off + r.r0 + r.c0,
+                                       (r.top & ALN_TOP) ? &a.res[r.aln].score : nullptr);
         if ((threadIdx.x & 31u) == 0u)
-            atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + CT_CELLS), (unsigned long long)r.n * (unsigned long long)r.m);
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + CT_CELLS), (unsigned long long)cells);
         __syncwarp();
     }
 }
@@ -384,6 +399,8 @@ struct b200aln_batch {
     /* results */
     std::vector<AlnResult> res;
     PinnedBuf h_runs, h_text, h_bp;
+    int32_t band_guess_permille = -1; /* -1: learn from the previous align_all; 0: never guess; > 0: fixed */
+    int32_t learnt_permille = 0;
     int32_t window_length = 0; /* > 0: breaking points are formed on the device */
     bool skip_cigars = false;  /* the CIGAR text is neither formed nor downloaded */
     int64_t n_windows = 0;     /* windows the staged overlaps touch */
@@ -661,10 +678,18 @@ int32_t b200aln_batch_align_all(b200aln_batch* b) {
 
     /* the first level, classified on the host: largest first, so the persistent grid starts with the long ones */
     std::vector<AlnRect> first[ALN_CLASSES], leaves0;
+    /* the guessed distance per 1000 characters of the longer sequence: fixed by the caller, or learnt from this batch's
+     * previous align_all (1.25 x the rate 90 % of its alignments stayed under); none for a batch that has seen nothing yet */
+    const int32_t rate_permille = b->band_guess_permille >= 0 ? b->band_guess_permille : b->learnt_permille;
     for (int32_t k = 0; k < n_aln; ++k) {
         const AlnJob& j = b->jobs[(size_t)k];
         if (j.n == 0 && j.m == 0) continue;
-        (aln_is_leaf(j.n, j.m) ? leaves0 : first[aln_shape(j.n, j.m)]).push_back(AlnRect{k, 0, j.n, 0, j.m, 1});
+        /* a top sub-problem's optimum is unknown: the host guesses (b200aln_batch_set_band_guess), the kernels verify */
+        const bool leaf = aln_is_leaf(j.n, j.m);
+        int32_t guess = -1;
+        if (!leaf && rate_permille > 0)
+            guess = (int32_t)std::min<int64_t>(((int64_t)std::max(j.n, j.m) * rate_permille + 999) / 1000 + 32, (int64_t)1 << 29);
+        (leaf ? leaves0 : first[aln_shape(j.n, j.m)]).push_back(AlnRect{k, 0, j.n, 0, j.m, guess >= 0 ? (ALN_TOP | ALN_GUESS) : ALN_TOP, guess});
     }
     const auto larger = [](const AlnRect& x, const AlnRect& y) { return (int64_t)x.n * x.m > (int64_t)y.n * y.m; };
     size_t first_total = 0, first_max = 0;
@@ -896,7 +921,26 @@ int32_t b200aln_batch_sync(b200aln_batch* b) {
         b->t_ed[k] = r.score;
         b->t_st[k] = ok ? B200ALN_SUCCESS : (r.status ? r.status : B200ALN_GENERIC_ERROR);
     }
+    if (n_aln >= 8) { /* what the next align_all of this batch will guess (verified on the device, so only speed is at stake) */
+        std::vector<int32_t> rates;
+        rates.reserve(n_aln);
+        for (size_t k = 0; k < n_aln; ++k) {
+            const int32_t len = std::max(b->jobs[k].n, b->jobs[k].m);
+            if (len > 0 && b->t_st[k] == B200ALN_SUCCESS) rates.push_back((int32_t)(((int64_t)b->res[k].score * 1000 + len - 1) / len));
+        }
+        if (rates.size() >= 8) {
+            const size_t p90 = rates.size() * 9 / 10;
+            std::nth_element(rates.begin(), rates.begin() + (std::ptrdiff_t)p90, rates.end());
+            b->learnt_permille = std::min(1000, rates[p90] * 5 / 4 + 1);
+        }
+    }
     b->synced = true;
+    return B200ALN_SUCCESS;
+}
+
+int32_t b200aln_batch_set_band_guess(b200aln_batch* b, int32_t permille) {
+    if (!b || permille < -1 || permille > 1000) return B200ALN_INVALID_ARGUMENT;
+    b->band_guess_permille = permille;
     return B200ALN_SUCCESS;
 }
 

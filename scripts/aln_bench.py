@@ -15,12 +15,22 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=24)
     ap.add_argument("--mem-gb", type=float, default=32)
+    ap.add_argument("--synthetic", default="", help="N,len,err: N seeded random pairs of that length and error rate instead of the real overlaps")
+    ap.add_argument("--guess", type=int, default=-1, help="b200aln_batch_set_band_guess: -1 learn, 0 never, > 0 permille")
     ap.add_argument("--view", type=int, default=0, help="1: no staging copy, upload from the page-locked input arrays")
     a = ap.parse_args()
     from common import overlap_fixture
     from racon_gpu_b200.aligner import CUDABatchAligner, pack_pairs
     fx = overlap_fixture()
     pairs = [(f["q"], f["t"]) for f in fx] * a.rep
+    if a.synthetic:  # long-read shapes: every pair is "huge" from 8192 rows on
+        from common import random_pairs
+        from oracle_lib import Ref, ref_align
+        cnt, ln, err = a.synthetic.split(",")
+        base = random_pairs(4242, [(int(ln), float(err))] * min(int(cnt), 48))
+        pairs = (base * (int(cnt) // len(base) + 1))[:int(cnt)]
+        r0 = Ref()
+        fx = [{"score": ref_align(r0, q_, t_)[1]} for q_, t_ in base[:8]] if r0.available else []
     q, qo, t, to = pack_pairs(pairs)
     nominal = float(sum(len(x) * len(y) for x, y in pairs))
     out = {"pairs": len(pairs), "bases": int(qo[-1] + to[-1]), "matrix_cells": nominal}
@@ -30,6 +40,7 @@ def main():
             _lib().b200aln_host_register(arr.ctypes.data_as(__import__('ctypes').c_void_p), __import__('ctypes').c_int64(arr.nbytes))
     best = None
     al = CUDABatchAligner(device_id=0, max_gpu_memory=int(a.mem_gb * (1 << 30)))
+    al.set_band_guess(a.guess)
     for it in range(a.iters + 1):
         t0 = time.perf_counter()
         first, rec = 0, {"kernel_ms": 0.0, "cells_computed": 0, "n_open": 0, "n_leaves": 0, "h2d": 0, "d2h": 0, "launches": 0,

@@ -20,10 +20,12 @@ extern "C" {
 /* Aligns one pair; ops_out must hold n + m bytes.  Returns the number of operations (holes removed); -1 inconsistent
  * split, -2 list overflow, -3 the runs do not spell the operations.  *score the edit distance; *levels (nullable) the
  * depth of the recursion; *n_leaves likewise; cigar_out (nullable, cigar_cap bytes) the CIGAR formed from the runs;
- * bp_out (nullable, 4 words per window of the target segment) the breaking points for window_length. */
+ * bp_out (nullable, 4 words per window of the target segment) the breaking points for window_length;
+ * guess (< 0: none) a guessed bound on the edit distance: the top sub-problem runs banded and is redone without a band when
+ * its optimum turns out larger (what the kernels do with the host's guess). */
 int64_t emu_align(const uint8_t* q, int32_t n, const uint8_t* t, int32_t m, uint8_t* ops_out, int32_t* score,
                   int32_t* levels, int32_t* n_leaves, char* cigar_out, int64_t cigar_cap, int32_t q_first, int32_t t_begin,
-                  int32_t window_length, uint32_t* bp_out, int32_t* bp_count) {
+                  int32_t window_length, uint32_t* bp_out, int32_t* bp_count, int32_t guess) {
     const int32_t max_len = (n > m ? n : m) + 1;
     size_t slot_bytes = 0;
     AlnSlot s;
@@ -50,7 +52,7 @@ int64_t emu_align(const uint8_t* q, int32_t n, const uint8_t* t, int32_t m, uint
         x.overflow = &overflow;
     };
     bind(first, level, n_level);
-    aln_push(first, AlnRect{0, 0, n, 0, m, 1});
+    aln_push(first, AlnRect{0, 0, n, 0, m, guess >= 0 ? (ALN_TOP | ALN_GUESS) : ALN_TOP, guess >= 0 ? guess : -1});
     while (n_level[0] + n_level[1] + n_level[2] > 0) {
         n_next[0] = n_next[1] = n_next[2] = 0;
         bind(L, next, n_next);
@@ -58,10 +60,12 @@ int64_t emu_align(const uint8_t* q, int32_t n, const uint8_t* t, int32_t m, uint
             for (int32_t k = 0; k < n_level[c]; ++k) {
                 const AlnRect r = level[c][(size_t)k];
                 AlnSplit sp;
-                aln_split(s, eq, q + r.r0, t + r.c0, r.n, r.m, &sp);
-                if (r.top) *score = sp.best;
+                aln_split(s, eq, q + r.r0, t + r.c0, r.n, r.m, aln_band_of(r.best), &sp);
+                if ((r.top & ALN_GUESS) && sp.best > r.best) /* the guess was too small: nothing of that pass can be trusted */
+                    aln_split(s, eq, q + r.r0, t + r.c0, r.n, r.m, -1, &sp);
+                if (r.top & ALN_TOP) *score = sp.best;
                 AlnRect ul, lr;
-                if (!aln_children(r, sp.r, ul, lr)) return -1;
+                if (!aln_children(r, sp, ul, lr)) return -1;
                 aln_push(L, ul);
                 aln_push(L, lr);
             }
@@ -75,7 +79,8 @@ int64_t emu_align(const uint8_t* q, int32_t n, const uint8_t* t, int32_t m, uint
     if (overflow) return -2;
     for (int32_t k = 0; k < n_leaf; ++k) {
         const AlnRect r = leaves[(size_t)k];
-        aln_leaf(s, eq, q + r.r0, t + r.c0, r.n, r.m, ops.data() + r.r0 + r.c0, r.top ? score : nullptr);
+        aln_leaf(s, eq, q + r.r0, t + r.c0, r.n, r.m, (r.top & ALN_GUESS) ? -1 : aln_band_of(r.best), ops.data() + r.r0 + r.c0,
+                 (r.top & ALN_TOP) ? score : nullptr);
     }
     int64_t k = 0;
     for (uint8_t op : ops)

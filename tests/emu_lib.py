@@ -63,7 +63,7 @@ class EmuAligner:
         self.lib = C.CDLL(os.path.join(HERE, "emu", "libaln_emu.so"))
         self.lib.emu_align.restype = C.c_int64
 
-    def align(self, q: bytes, t: bytes, q_first: int = 0, t_begin: int = 0, window_length: int = 0):
+    def align(self, q: bytes, t: bytes, q_first: int = 0, t_begin: int = 0, window_length: int = 0, guess: int = -1):
         """(ops, edit distance, recursion depth, leaves); self.cigar = the CIGAR formed from the engine's runs"""
         ops = np.zeros(len(q) + len(t) + 8, dtype=np.uint8)
         score, levels, leaves = C.c_int32(-1), C.c_int32(0), C.c_int32(0)
@@ -74,7 +74,7 @@ class EmuAligner:
         n = self.lib.emu_align(C.c_char_p(q), C.c_int32(len(q)), C.c_char_p(t), C.c_int32(len(t)), _p(ops, C.c_uint8),
                                C.byref(score), C.byref(levels), C.byref(leaves), cigar, C.c_int64(cap),
                                C.c_int32(q_first), C.c_int32(t_begin), C.c_int32(window_length), _p(bp, C.c_uint32),
-                               C.byref(bp_count))
+                               C.byref(bp_count), C.c_int32(guess))
         self.breaking_points = bp[:2 * bp_count.value].reshape(-1, 2).copy()  # (t, q) pairs, window_length > 0 only
         assert n >= 0, {-1: "inconsistent split", -2: "list overflow", -3: "runs do not spell the operations"}.get(n, n)
         self.cigar = cigar.value

@@ -136,3 +136,25 @@ def test_breaking_points_restatement_and_engine(oracle, ref, emu):
         assert want.shape == f["bp"].shape and (want == f["bp"]).all(), i
         emu.align(f["q"], f["t"], f["q_first"], f["t_begin"], 500)
         assert (emu.breaking_points == f["bp"]).all(), i
+
+
+def test_banded_passes_with_guessed_and_exact_bounds(oracle, ref, emu):
+    """Bands: children of a split know their optimum exactly (every test above already runs them banded); the top
+    sub-problem gets a GUESS from the host and is redone without a band when its optimum turns out larger.  Too small,
+    exact, tight and generous guesses all give edlib's alignment."""
+    pairs = random_pairs(77, [(2600, 0.2), (4000, 0.12), (5000, 0.3), (2300, 0.02)])
+    rng = np.random.default_rng(12)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    pairs.append((rng.choice(acgt, size=4100).tobytes(), rng.choice(acgt, size=2900).tobytes()))  # unrelated: a huge distance
+    pairs.append((rng.choice(acgt, size=300).tobytes(), rng.choice(acgt, size=9000).tobytes()))
+    for q, t in pairs:
+        ops, score = oracle_align(oracle, q, t)
+        for guess in (0, score // 2, score - 1, score, score + 1, 2 * score + 64, 10 ** 6):
+            a, sa, depth, leaves = emu.align(q, t, guess=guess)
+            assert sa == score and a.shape == ops.shape and (a == ops).all(), (len(q), len(t), guess)
+    if ref.available:  # long reads: narrow strips of a large matrix, several stripes handing over anchors
+        for (q, t), frac in zip(random_pairs(903, [(42000, 0.12), (30000, 0.03)]), (0.25, 0.05)):
+            ops, score, cigar = ref_align(ref, q, t)
+            for guess in (int(frac * len(t)), score, score - 1):
+                a, sa, depth, leaves = emu.align(q, t, guess=guess)
+                assert sa == score and (a == ops).all() and emu.cigar == cigar, (len(q), guess)

@@ -86,6 +86,27 @@ def test_real_lambda_overlaps_equal_unmodified_edlib(aligner):
     aligner.reset()
 
 
+@pytest.mark.parametrize("permille", [0, 30, 150, 320, 600, -1])
+def test_top_level_band_guesses_never_change_the_result(permille):
+    """The top sub-problem of every alignment runs in a band the host GUESSES (b200aln_batch_set_band_guess) and the
+    kernels verify: far too small (every alignment is redone whole), about right, generous, learnt from the batch's
+    previous align_all (-1: the second round guesses) -- always edlib's CIGARs, for one-warp and team launches alike."""
+    from racon_gpu_b200.aligner import CUDABatchAligner, pack_pairs
+    fx = overlap_fixture()
+    q, qo, t, to = pack_pairs([(f["q"], f["t"]) for f in fx])
+    al = CUDABatchAligner(device_id=0, max_gpu_memory=8 << 30)
+    al.set_band_guess(permille)
+    for rnd in range(2):
+        assert al.add_overlaps(q, qo, t, to) == len(fx)
+        al.align_all()
+        text, off, ln, ed = al.cigars()
+        for k, f in enumerate(fx):
+            assert ed[k] == f["score"], (rnd, k)
+            assert hashlib.sha256(text[off[k]:off[k] + ln[k]]).hexdigest() == f["cigar_sha"], (rnd, k)
+        al.reset()
+    al.close()
+
+
 def test_saturated_level_with_huge_overlaps_on_the_side_stream():
     """Enough tall sub-problems to fill the device one warp each (so the level is not 'thin'), among them overlaps of
     >= 8192 rows: those go to teams of warps on the side stream while the one-warp grid does the rest.  Every CIGAR is
