@@ -10,7 +10,8 @@
  *     edlibAlign(q, t, {k = -1, EDLIB_MODE_NW, EDLIB_TASK_PATH}) + edlibAlignmentToCigar(EDLIB_CIGAR_STANDARD)
  * (src/overlap.cpp:205-224) -- same edit distance AND the same choice among the optimal alignments, so that racon's
  * breaking points, windows and consensus stay those of `racon -t` (cudaaligner returns *an* optimal or, past its band,
- * a sub-optimal alignment).  No band, no length limit other than memory: nothing is left to a CPU aligner.
+ * a sub-optimal alignment).  No band that can cost optimality (the engine confines itself to bands only where that is
+ * provably or verifiably exact), no length limit other than memory: nothing is left to a CPU aligner.
  *
  * Plain pointers and sizes only; every function returns a b200aln_status (= cudaaligner::StatusType values,
  * cudaaligner.hpp:34-42) unless stated otherwise.  A batch belongs to one device and one stream and is not thread-safe;
@@ -31,7 +32,7 @@ enum b200aln_status { /* cudaaligner.hpp:34-42 */
     B200ALN_UNINITIALIZED = 1,
     B200ALN_EXCEEDED_MAX_ALIGNMENTS = 2,           /* the batch's memory budget is used up: align, reset, add again */
     B200ALN_EXCEEDED_MAX_LENGTH = 3,               /* this one pair can never fit the budget, even alone            */
-    B200ALN_EXCEEDED_MAX_ALIGNMENT_DIFFERENCE = 4, /* never produced (no band); kept for the enum's numbering       */
+    B200ALN_EXCEEDED_MAX_ALIGNMENT_DIFFERENCE = 4, /* never produced (no lossy band); kept for the numbering        */
     B200ALN_GENERIC_ERROR = 5,
     B200ALN_INVALID_ARGUMENT = 6,
     B200ALN_CUDA_ERROR = 7
@@ -53,7 +54,7 @@ int32_t b200aln_init(void);
 /* create_aligner(AlignmentType::global_alignment, max_bandwidth, stream, device_id, max_device_memory)
  * (aligner.hpp:121-132; racon: src/cuda/cudaaligner.cpp:24-45).  `stream` is a cudaStream_t or NULL (the batch then
  * owns one).  max_gpu_mem <= 0: 90 % of the device's free memory.  max_bandwidth is accepted for signature parity and
- * ignored: every cell is computed exactly. */
+ * ignored: the engine never trades optimality for a band (see b200aln_batch_set_band_guess). */
 int32_t b200aln_batch_create(int32_t device_id, void* stream, int64_t max_gpu_mem, int32_t max_bandwidth,
                              b200aln_batch** out);
 

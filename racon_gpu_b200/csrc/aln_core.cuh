@@ -27,7 +27,9 @@
  *     delta of its last row travels to lane l + 1 in one shuffle per step, the column's character code comes from a code
  *     row, its match mask from the lane's shared-memory table; 16 steps to a group (immediates instead of bookkeeping).
  *     Taller sub-problems take several stripes; the last lane's deltas go to the next stripe packed 16 columns to a word;
- *   - no band: every cell is exact, 64 cells per word operation, so the choice rules above need no band bookkeeping;
+ *   - bands only where they are exact: a sub-problem whose optimum is known (every child of a split) runs the diagonal
+ *     strip that holds all values up to it, the top level a guessed strip that the split rule's result verifies; what a
+ *     strip leaves out is overestimated, never underestimated, so the choice rules above see the same values (myers_pass);
  *   - a leaf stores (Pv, Mv, bottom score) per block and column -- 20 bytes, the record edlib keeps, which is why the
  *     1 MB rule bounds a leaf's workspace -- in wavefront order (coalesced), and any cell's value is
  *     bottom - popc(Pv & below) + popc(Mv & below): the traceback rates the 32 cells of the diagonal in front of the walk

@@ -538,7 +538,7 @@ void b200aln_batch_destroy(b200aln_batch* b) {
 
 int32_t b200aln_batch_create(int32_t device_id, void* stream, int64_t max_gpu_mem, int32_t max_bandwidth,
                              b200aln_batch** out) {
-    (void)max_bandwidth; /* no band: every cell is exact (b200aln.h) */
+    (void)max_bandwidth; /* cudaaligner's band can cost optimality; this engine's bands cannot (b200aln.h) */
     if (!out) return B200ALN_INVALID_ARGUMENT;
     *out = nullptr;
     int n_dev = 0;

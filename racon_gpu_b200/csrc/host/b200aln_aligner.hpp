@@ -48,7 +48,7 @@ public:
     const std::string& get_target_sequence() const { return target_; }
     std::string convert_to_cigar() const { return cigar_; }
     AlignmentType get_alignment_type() const { return global_alignment; }
-    bool is_optimal() const { return status_ == success; } /* no band: an alignment that exists is optimal */
+    bool is_optimal() const { return status_ == success; } /* no lossy band: an alignment that exists is optimal */
     StatusType get_status() const { return status_; }
     int32_t get_edit_distance() const { return edit_distance_; }
     /* one state per position; expanded from the batch's run starts on first use (racon only reads the CIGAR, so the
