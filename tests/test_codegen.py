@@ -42,3 +42,30 @@ def test_the_fill_uses_the_packed_int16_pipeline_and_async_copies(sass):
         assert op in sass, op
     n_instr = len(re.findall(r"^\s+/\*[0-9a-f]{4,6}\*/", sass, flags=re.M))
     assert n_instr < 14500, f"kernel grew to {n_instr} instructions: check for divergence fallbacks or unrolling"
+
+
+def _function_section(out, name):
+    import re as _re
+    m = _re.search(r"Function : \S*" + name + r"\S*", out)
+    assert m, name
+    nxt = out.find("Function :", m.end())
+    return out[m.start():nxt if nxt > 0 else len(out)]
+
+
+def test_aligner_step_loop_keeps_its_shape():
+    """csrc/aln_core.cuh myers_pass: the one-warp split kernel's wavefront runs 16 steps to a group (16 SHFL.UP in the
+    unrolled loop + 1 in the cold loop for non-ACGT bytes), looks its match masks up in shared memory, does its shifts as
+    multiply-adds (IMAD.HI for bit 63) and has no divergence slow paths around its shuffles."""
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    from racon_gpu_b200 import api
+    api.load_library()
+    out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
+    solo = _function_section(out, "aln_split_kernel")
+    assert solo.count("SHFL.UP") >= 17
+    assert "LDS.64" in solo and "IMAD.HI.U32" in solo
+    assert solo.count("BRA.DIV") == 0 and solo.count("WARPSYNC.COLLECTIVE") == 0
+    n_instr = len(re.findall(r"^\s+/\*[0-9a-f]{4,6}\*/", solo, flags=re.M))
+    assert n_instr < 3600, f"aln_split_kernel grew to {n_instr} instructions"
+    team = _function_section(out, "aln_split_team_kernel")
+    assert "BAR.SYNC" in team or "BAR.SYNC.DEFER_BLOCKING" in team  # the teams' named barriers
